@@ -1,0 +1,120 @@
+"""Case table for the golden fixtures + builders that turn a case into oracle inputs.
+
+TEST INFRASTRUCTURE.  ``oracle/make_golden.py`` runs the unmodified reference on these cases (in
+the build container) and writes ``tests/golden/<case>.npz``; the tests rebuild the same inputs for
+the oracle and for the CUDA path from this table, so nothing here needs ``/root/reference``.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from oracle import tjm_oracle as O
+
+CASES = {
+    # the reference's own seeded golden test (tests/test_simulator.py:159-207)
+    "ising5_ref_golden": dict(model="ising", L=5, J=1.0, g=0.5, init="zeros", chi=4, thr=1e-6, order=2, dt=0.1, steps=10,
+                              sample_timesteps=False, ntraj=10, seed=42, obs="z",
+                              noise=[("lowering", 0.1), ("pauli_z", 0.1)]),
+    # BASELINE config 1 (L=10, chi=16) on a trajectory subset, order 2 and order 1
+    "ising10_c1_order2": dict(model="ising", L=10, J=1.0, g=0.5, init="zeros", chi=16, thr=1e-6, order=2, dt=0.1, steps=10,
+                              sample_timesteps=True, ntraj=8, seed=42, obs="z",
+                              noise=[("lowering", 0.1), ("pauli_z", 0.1)]),
+    "ising10_c1_order1": dict(model="ising", L=10, J=1.0, g=0.5, init="zeros", chi=16, thr=1e-6, order=1, dt=0.1, steps=10,
+                              sample_timesteps=True, ntraj=8, seed=42, obs="z",
+                              noise=[("lowering", 0.1), ("pauli_z", 0.1)]),
+    # BASELINE config 2 in miniature: Heisenberg, amplitude damping, Z and ZZ observables
+    "heis8_c2_order2": dict(model="heisenberg", L=8, J=1.0, g=0.0, init="Neel", chi=16, thr=1e-6, order=2, dt=0.1, steps=8,
+                            sample_timesteps=True, ntraj=6, seed=7, obs="z+zz",
+                            noise=[("lowering", 0.1)]),
+    # strong noise => many jumps; x+ start => entanglement growth
+    "ising8_strong_order2": dict(model="ising", L=8, J=1.0, g=1.0, init="x+", chi=8, thr=1e-9, order=2, dt=0.1, steps=6,
+                                 sample_timesteps=True, ntraj=6, seed=3, obs="x+z",
+                                 noise=[("lowering", 0.5), ("pauli_x", 0.3), ("raising", 0.2)]),
+    # bond cap reached (chi=4 with a tiny threshold) and frequent jumps
+    "ising8_capped_order2": dict(model="ising", L=8, J=1.0, g=1.0, init="x+", chi=4, thr=1e-12, order=2, dt=0.1, steps=8,
+                                 sample_timesteps=True, ntraj=6, seed=17, obs="z+zz",
+                                 noise=[("lowering", 0.4), ("pauli_z", 0.3)]),
+    # two-site processes: adjacent Pauli crosstalk, adjacent non-Pauli (lowering_two), long-range Pauli crosstalk
+    "ising6_twosite_order1": dict(model="ising", L=6, J=1.0, g=0.7, init="x+", chi=8, thr=1e-8, order=1, dt=0.1, steps=6,
+                                  sample_timesteps=True, ntraj=6, seed=11, obs="z",
+                                  noise=[("lowering", 0.1)],
+                                  noise2=[("crosstalk_xx", (0, 1), 0.3), ("lowering_two", (2, 3), 0.4),
+                                          ("crosstalk_zy", (1, 4), 0.3), ("crosstalk_yy", (4, 5), 0.2)]),
+    "ising6_twosite_order2": dict(model="ising", L=6, J=1.0, g=0.7, init="x+", chi=8, thr=1e-8, order=2, dt=0.1, steps=5,
+                                  sample_timesteps=True, ntraj=5, seed=12, obs="z",
+                                  noise=[("pauli_z", 0.2)],
+                                  noise2=[("crosstalk_xx", (0, 1), 0.8), ("lowering_two", (2, 3), 1.5),
+                                          ("crosstalk_zy", (1, 4), 0.8), ("raising_two", (4, 5), 1.0)]),
+    # noise-free (deterministic) evolution, 2-site and 1-site TDVP
+    "ising6_noiseless_order1": dict(model="ising", L=6, J=1.0, g=0.5, init="x+", chi=8, thr=1e-9, order=1, dt=0.05, steps=8,
+                                    sample_timesteps=True, ntraj=1, seed=1, obs="x+z", noise=[]),
+    "ising6_noiseless_order2": dict(model="ising", L=6, J=1.0, g=0.5, init="x+", chi=8, thr=1e-9, order=2, dt=0.05, steps=8,
+                                    sample_timesteps=True, ntraj=1, seed=1, obs="x+z", noise=[]),
+    # 1-site TDVP needs a full-rank start: on zero-padded product states the QR completion of the null space is decided
+    # by rounding noise, so even the reference is not reproducible there (see DESIGN.md "1TDVP and padded states").
+    "heis6_1site_order1": dict(model="heisenberg", L=6, J=1.0, g=0.0, init="random:4:99", chi=4, thr=1e-9, order=1, dt=0.05,
+                               steps=6, sample_timesteps=True, ntraj=4, seed=5, obs="z", tdvp_mode="1site",
+                               noise=[("lowering", 1.0), ("pauli_z", 0.6)]),
+    "ising6_1site_noiseless": dict(model="ising", L=6, J=1.0, g=0.8, init="random:4:7", chi=4, thr=1e-9, order=1, dt=0.05,
+                                   steps=6, sample_timesteps=True, ntraj=1, seed=5, obs="x+z", tdvp_mode="1site", noise=[]),
+    # final-column-only bookkeeping with order 1
+    "ising6_final_only_order1": dict(model="ising", L=6, J=1.0, g=0.5, init="zeros", chi=8, thr=1e-6, order=1, dt=0.1, steps=5,
+                                     sample_timesteps=False, ntraj=6, seed=21, obs="z",
+                                     noise=[("lowering", 0.3), ("pauli_z", 0.2)]),
+}
+
+
+
+
+def initial_state(cfg: dict) -> O.OracleMPS:
+    """Product preset, optionally zero-padded, or ``random:<chi>:<seed>`` = seeded full-rank random MPS,
+    right-normalised (centre 0)."""
+    L = cfg["L"]
+    kind = cfg["init"]
+    if kind.startswith("random:"):
+        _, chi, seed = kind.split(":")
+        return O.random_mps(L, int(chi), int(seed))
+    init = O.product_state(L, kind)
+    if cfg.get("pad"):
+        init = O.pad_bond_dimension(init, cfg["pad"])
+    return init
+
+
+def oracle_inputs(cfg: dict):
+    """(initial OracleMPS, mpo tensors, noise process list | None, OracleParams, sorted observables)."""
+    L = cfg["L"]
+    if cfg["model"] == "ising":
+        mpo = O.ising_mpo(L, cfg["J"], cfg["g"])
+    else:
+        mpo = O.heisenberg_mpo(L, cfg["J"], cfg["J"], cfg["J"])
+    obs = []
+    for tok in cfg["obs"].split("+"):
+        if tok in ("x", "y", "z"):
+            obs += [(O.OBSERVABLE_MATRICES[tok], [s]) for s in range(L)]
+        else:
+            obs += [(O.OBSERVABLE_MATRICES[tok], [s, s + 1]) for s in range(L - 1)]
+    order = O.sort_observables(obs)
+    obs = [obs[k] for k in order]
+    procs = [O.make_process(n, [i], g) for i in range(L) for (n, g) in cfg["noise"]]
+    procs += [O.make_process(n, list(s), g) for (n, s, g) in cfg.get("noise2", [])]
+    noise = procs if procs else None
+    p = O.OracleParams(dt=cfg["dt"], n_steps=cfg["steps"], order=cfg["order"], max_bond_dim=cfg["chi"],
+                       svd_threshold=cfg["thr"], krylov_tol=cfg.get("krylov_tol", 1e-4),
+                       tdvp_mode=cfg.get("tdvp_mode", "2site"), sample_timesteps=cfg["sample_timesteps"])
+    init = initial_state(cfg)
+    return init, mpo, noise, p, obs
+
+
+def run_oracle_case(cfg: dict, trajectories=None):
+    """Run the oracle with the reference's seeded numpy streams; returns a list of TrajectoryTrace."""
+    init, mpo, noise, p, obs = oracle_inputs(cfg)
+    out = []
+    for tr in (range(cfg["ntraj"]) if trajectories is None else trajectories):
+        rng = O.UniformStream(O.trajectory_stream(cfg["seed"], tr))
+        if cfg["order"] == 2:
+            tr_out = O.analog_tjm_2(init, mpo, noise, p, obs, rng,
+                                    lambda j, _t=tr: O.UniformStream(O.sample_stream(cfg["seed"], _t, j)))
+        else:
+            tr_out = O.analog_tjm_1(init, mpo, noise, p, obs, rng)
+        out.append(tr_out)
+    return out
