@@ -1,0 +1,125 @@
+/* yaqs_b200 -- C ABI of the B200-native batched Tensor Jump Method kernels.
+ *
+ * Drop-in boundary: the reference (munich-quantum-toolkit/yaqs, pure Python) has no FFI; the
+ * place a maintainer would bind these entry points is the per-trajectory backend boundary
+ *   analog_tjm_1 / analog_tjm_2            src/mqt/yaqs/analog/analog_tjm.py:206,369
+ *   run_backend_parallel(worker_fn=...)    src/mqt/yaqs/core/parallel_utils.py:331
+ * with each entry point below replacing the numpy/scipy call(s) cited next to it (paths relative to
+ * src/mqt/yaqs/core).  INTEGRATION.md shows the ctypes stub.
+ *
+ * Conventions
+ *   - All tensors are complex128, interleaved (re, im), in device memory owned by the caller (torch CUDA tensors in
+ *     the Python host); the library never allocates or frees tensor memory.
+ *   - A batch holds `nbatch` trajectories.  Operand p of trajectory b starts at p + b * stride_p (strides in complex
+ *     elements) and is stored packed, C order, with its ACTUAL extents (same index order as the reference's ndarrays).
+ *   - Ragged bond dimensions are read on the device: an "extent" argument is a pointer to the first trajectory's int32
+ *     plus the distance (in ints) to the next trajectory's value.
+ *   - `mask` (optional, may be NULL): int32[nbatch]; trajectories with mask[b] == 0 are skipped.
+ *   - Every function enqueues work on `stream` (a cudaStream_t passed as void*) and returns 0 on success, a negative
+ *     value on error; yb_last_error() returns the message.  Nothing here synchronises the stream.
+ */
+#ifndef YAQS_B200_H
+#define YAQS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct { const int32_t* ptr; int32_t stride; } yb_extent;
+
+const char* yb_last_error(void);
+int yb_version(void);
+/* Number of kernels this library has launched since the last call with reset != 0 (bench.py's gpu_launches). */
+int64_t yb_launch_count(int reset);
+
+/* ---- contractions -------------------------------------------------------------------------------------------------
+ * One grouped / K-segmented batched complex GEMM; `op` selects the index pattern (enum YbGemmOp in csrc/yb_common.cuh):
+ *   0 RCONTRACT  T1[(p,l),(a',r')] = sum_r X[(p,l),r] R[r,(a',r')]          tensordot(ket, right_env, axes=1)     methods/tdvp/primitives.py:105,201
+ *   1 LCONTRACT  Y_o[l',r'] = sum_(l,a) Lenv[(l,a),l'] T2_o[(l,a),r']       tensordot(t, left_env, ((2,1),(0,1))) primitives.py:203, project_bond :226
+ *   2 ENVR3      R'[(l,a),l'] = sum_(o,r') T2_o[(l,a),r'] conj(bra_o[l',r'])  tensordot(t, bra.conj(), ...)        primitives.py:108
+ *   3 ENVL1      U1_o[(l,a),r'] = sum_l' Lenv[(l,a),l'] conj(bra_o[l',r'])    tensordot(left_env, bra.conj(), (2,1)) primitives.py:134
+ *   4 ENVL3      L'[r,(a',r')] = sum_(p,l) ket[(p,l),r] U2[(p,l),(a',r')]     tensordot(ket, t, ((0,1),(0,2)))     primitives.py:136
+ *   5 MERGE      theta_(ss')[l,r] = sum_c A_s[l,c] B_s'[c,r]                  merge_two_site                       methods/decompositions.py:87-102
+ *   6 ABSORB_R   next'_s[k,r] = sum_j G[k,j] next_s[j,r]                      R into the right neighbour          data_structures/mps.py:742-746
+ *   7 ABSORB_L   prev'_s[l,k] = sum_j prev_s[l,j] G[j,k]                      (mirror image, left shifts)          mps.py:771-788
+ * e0,e1,e2: the op's extents (l, r | l, c, r | k, j, r | l, j, k).  conj_b != 0 conjugates the B operand in addition.
+ * max_m / max_n bound the per-trajectory GEMM M and N (grid sizing). */
+int yb_gemm(int op, int nbatch, int ngroups, const int32_t* mask, yb_extent e0, yb_extent e1, yb_extent e2, int dphys, int d_left,
+            int d_right, const void* a, int64_t stride_a, const void* b, int64_t stride_b, void* c, int64_t stride_c, int conj_b,
+            int max_m, int max_n, void* stream);
+
+/* out[x,l,y,r] = sum_(u,v) wt[x,u,y,v] in[u,l,v,r]: the MPO-tensor step of project_site / update_*_environment
+ * (tensordot(op, tensor, axes=((1,3),(0,2))) primitives.py:106,202; tensordot(op, tensor, ((0,2),(2,1))) :135 with the
+ * host-transposed MPO tensor).  wt is shared by all trajectories. */
+int yb_wapply(int nbatch, const int32_t* mask, yb_extent el, yb_extent er, int nx, int nu, int ny, int nv, const void* wt,
+              const void* in, int64_t stride_in, void* out, int64_t stride_out, int max_lr, void* stream);
+
+/* env[b][i,a,j] = delta_ij for a < D, i,j < chi[b]  (primitives.py:162-168, integrators.py:186-193). */
+int yb_env_identity(int nbatch, const int32_t* mask, yb_extent echi, int dmpo, void* env, int64_t stride_env, int max_chi, void* stream);
+
+/* ---- Lanczos / Krylov exponential (methods/matrix_exponential.py:33-201) ------------------------------------------
+ * basis: [nbatch][kmax+1][nloc_max] Lanczos vectors; the matvec writes H v_j into slot j+1, yb_lanczos_step turns it into
+ * v_{j+1} in place.  n_loc[b] = dphys * el[b] * er[b]. */
+int yb_lanczos_init(int nbatch, const int32_t* mask, yb_extent el, yb_extent er, int dphys, const void* x, int64_t stride_x,
+                    void* basis, int64_t stride_basis, int64_t stride_vec, double* nrm, int32_t* active, int32_t* kdone, void* stream);
+/* One Lanczos iteration for all active trajectories: alpha_j, orthogonalise, beta_j, breakdown / convergence test
+ * (k x k tridiagonal eigen-solve = scipy.linalg.eigh_tridiagonal, linalg/eigh.py:29), normalise.  On finish writes the
+ * k complex combination coefficients y (already times |v|) to coef[b][0..k) and kdone[b] = k, clears active[b].
+ * n_active (device int32) is zeroed by the caller and receives the number of trajectories still iterating. */
+int yb_lanczos_step(int nbatch, int j, int kmax, double dt, double tol, yb_extent el, yb_extent er, int dphys, void* basis,
+                    int64_t stride_basis, int64_t stride_vec, double* alpha, double* beta, const double* nrm, int32_t* active,
+                    int32_t* kdone, void* coef, int32_t* n_active, void* stream);
+/* out = sum_j coef_j v_j for trajectories with kdone[b] > 0 (zero-norm inputs are returned untouched, :67-69). */
+int yb_lanczos_combine(int nbatch, const int32_t* mask, yb_extent el, yb_extent er, int dphys, const void* basis, int64_t stride_basis,
+                       int64_t stride_vec, const void* coef, int kmax, const int32_t* kdone, void* out, int64_t stride_out, void* stream);
+
+/* ---- truncated SVD by one-sided Jacobi (linalg/svd.py:51 + linalg/svd_utils.py:22 + decompositions.py:105-185) ----
+ * The matrix of trajectory b is M[b] (rows x cols), gathered from `src` by `mode`:
+ *   0 THETA   src = merged theta ((s s'), l, r): rows (s, l), cols (s', r)           split_two_site :147-154
+ *   1 ROWS    src = site tensor (s, l, r) read as (s l) x r                          right shift (mps.py:736-764)
+ *   2 COLS    src = site tensor (s, l, r) read as l x (s r)                          left shift  (mps.py:771-788)
+ * yb_svd_prepare builds the Jacobi work matrix W (the smaller side's vectors as contiguous rows) and Q = I.
+ * yb_svd_round does one round of a cyclic block sweep (round r of `nrounds`), counting rotations per trajectory.
+ * yb_svd_finalize sorts the singular values, applies truncate(mode, threshold, max_bond, min_keep) and writes
+ *   keep[b], sval[b][:], U f(S) as rows x keep (row-major) to `uout`, g(S) Vh as keep x cols to `vout`
+ *   (dist: 0 = S to the left factor, 1 = right, 2 = sqrt on both). */
+int yb_svd_prepare(int nbatch, const int32_t* mask, int mode, yb_extent el, yb_extent er, int dphys, const void* src, int64_t stride_src,
+                   void* w, int64_t stride_w, void* q, int64_t stride_q, int32_t* meta, int32_t* rot_count, void* stream);
+int yb_svd_round(int nbatch, const int32_t* mask, int32_t* meta, int block_rows, int nblocks, int round, int full_panel, int inner_sweeps,
+                 void* w, int64_t stride_w, void* q, int64_t stride_q, int32_t* rot_count, int max_len, int max_k, void* stream);
+/* After a sweep: meta.done = (rot_count == 0); n_pending (device int32, zeroed by caller) counts unfinished trajectories. */
+int yb_svd_check(int nbatch, const int32_t* mask, int32_t* meta, int32_t* rot_count, int32_t* n_pending, void* stream);
+int yb_svd_finalize(int nbatch, const int32_t* mask, const int32_t* meta, int trunc_mode, double threshold, int max_bond, int min_keep,
+                    int dist, const void* w, int64_t stride_w, const void* q, int64_t stride_q, double* sval, int64_t stride_s,
+                    int32_t* keep, int32_t keep_stride, void* uout, int64_t stride_u, void* vout, int64_t stride_v, int32_t* status,
+                    int max_k, void* stream);
+
+/* ---- site-tensor utilities -----------------------------------------------------------------------------------------
+ * dst(s', k, r) = src(k, (s', r)): unpack g(S) Vh rows into an MPS site tensor (decompositions.py:171-184). */
+int yb_unpack_vh(int nbatch, const int32_t* mask, yb_extent ek, yb_extent er, int dphys, const void* src, int64_t stride_src, void* dst,
+                 int64_t stride_dst, int max_elems, void* stream);
+/* Packed copy of n[b] = mult * e0[b] * e1[b] complex elements per trajectory. */
+int yb_copy_packed(int nbatch, const int32_t* mask, yb_extent e0, yb_extent e1, int mult, const void* src, int64_t stride_src, void* dst,
+                   int64_t stride_dst, int max_elems, void* stream);
+/* A_s <- sum_t op[s,t] A_t  with a dphys x dphys complex matrix, either shared (op_stride = 0) or per trajectory; optional
+ * per-trajectory site selection: trajectory b is touched only if sel == NULL or sel[b] == sel_value.
+ * (dissipation.py:125-126, stochastic_process.py:255,262-263, digital_tjm.py:304-309). */
+int yb_apply_local_op(int nbatch, const int32_t* mask, const int32_t* sel, int sel_value, yb_extent el, yb_extent er, int dphys,
+                      const void* op, int64_t op_stride, void* a, int64_t stride_a, int max_lr, void* stream);
+/* out[b] = sum |a|^2 over the packed tensor (MPS.norm at the centre site, mps.py:1539-1565). */
+int yb_norm2(int nbatch, const int32_t* mask, yb_extent el, yb_extent er, int dphys, const void* a, int64_t stride_a, double* out,
+             void* stream);
+/* a <- a * scale[b] (real). */
+int yb_scale(int nbatch, const int32_t* mask, yb_extent el, yb_extent er, int dphys, const double* scale, void* a, int64_t stride_a,
+             int max_elems, void* stream);
+/* g[b][o][p] = sum_(l,r) conj(a_o[l,r]) x_p[l,r]: local reduced density matrix used for observables
+ * (mps.py:961-1047) and jump weights (stochastic_process.py:139-176). */
+int yb_local_rdm(int nbatch, const int32_t* mask, yb_extent el, yb_extent er, int dphys, const void* a, int64_t stride_a, const void* x,
+                 int64_t stride_x, void* g, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* YAQS_B200_H */

@@ -1,0 +1,315 @@
+"""numpy twin of the C ABI in include/yaqs_b200.h -- TEST INFRASTRUCTURE ONLY.
+
+Same entry points, same buffer layouts, same per-trajectory extents as ``yaqs_b200.kernels.CudaKernels``, evaluated
+with plain numpy loops over the batch on CPU torch tensors.  It exists so that
+  * ``-m gpu`` tests can check every CUDA kernel against an independent statement of its contract, and
+  * ``-m "not gpu"`` tests can run the host-side engine (sweep order, masks, gauge bookkeeping) against the golden
+    fixtures without a GPU.
+It is never imported by the product package; ``yaqs_b200`` fails loudly when the CUDA library is missing.
+"""
+from __future__ import annotations
+
+import numpy as np
+import scipy.linalg
+import torch
+
+from oracle.tjm_oracle import truncate as oracle_truncate
+
+LANCZOS_PITCH = 32
+SVD_META = 8
+_TRUNC_NAMES = {0: "discarded_weight", 1: "relative", 2: "hard_cutoff", 3: "relative_discarded_weight"}
+
+
+def _np(t: torch.Tensor) -> np.ndarray:
+    return t.view(-1).numpy()
+
+
+def _ext(e, b):
+    return int(_np(e.tensor)[e.offset + b * e.stride])
+
+
+def _view(buf, b, n):
+    a = _np(buf.tensor)
+    start = buf.offset + b * buf.stride
+    return a[start:start + n]
+
+
+def _on(mask, b):
+    return mask is None or int(_np(mask)[b]) != 0
+
+
+class NumpyKernels:
+    name = "numpy-twin"
+
+    def __init__(self, device=None):
+        self.device = torch.device("cpu")
+        self._launches = 0
+        self._svd_store: dict[int, tuple] = {}
+
+    def launch_count(self, reset=False):
+        v = self._launches
+        if reset:
+            self._launches = 0
+        return v
+
+    def sync_int(self, t):
+        return int(t.item())
+
+    # -- contractions -------------------------------------------------------------------------------------------------
+    def gemm(self, op, nbatch, ngroups, mask, e0, e1, e2, dphys, Dl, Dr, a, b, c, conj_b, max_m, max_n):
+        self._launches += 1
+        for t in range(nbatch):
+            if not _on(mask, t):
+                continue
+            x0 = _ext(e0, t) if e0 is not None else 0
+            x1 = _ext(e1, t) if e1 is not None else 0
+            x2 = _ext(e2, t) if e2 is not None else 0
+            cj = (lambda z: z.conj()) if conj_b else (lambda z: z)
+            if op == 0:      # RCONTRACT: X[(p,l),r] R[r,(a,r')]
+                X = _view(a, t, dphys * x0 * x1).reshape(dphys * x0, x1)
+                R = cj(_view(b, t, x1 * Dr * x1).reshape(x1, Dr * x1))
+                _view(c, t, dphys * x0 * Dr * x1)[:] = (X @ R).reshape(-1)
+            elif op == 1:    # LCONTRACT: Y_o[l',r'] = sum_(l,a) Lenv[(l,a),l'] T2_o[(l,a),r']
+                Lm = _view(a, t, x0 * Dl * x0).reshape(x0 * Dl, x0)
+                T2 = cj(_view(b, t, dphys * x0 * Dl * x1).reshape(dphys, x0 * Dl, x1))
+                _view(c, t, dphys * x0 * x1)[:] = np.einsum("km,okn->omn", Lm, T2).reshape(-1)
+            elif op == 2:    # ENVR3: R'[(l,a),l'] = sum_(o,r') T2_o[(l,a),r'] conj(bra_o[l',r'])
+                T2 = _view(a, t, dphys * x0 * Dl * x1).reshape(dphys, x0 * Dl, x1)
+                bra = _view(b, t, dphys * x0 * x1).reshape(dphys, x0, x1)
+                bra = bra if conj_b else bra.conj()
+                _view(c, t, x0 * Dl * x0)[:] = np.einsum("omk,onk->mn", T2, bra).reshape(-1)
+            elif op == 3:    # ENVL1: U1_o[(l,a),r'] = sum_l' Lenv[(l,a),l'] conj(bra_o[l',r'])
+                Lm = _view(a, t, x0 * Dl * x0).reshape(x0 * Dl, x0)
+                bra = _view(b, t, dphys * x0 * x1).reshape(dphys, x0, x1)
+                bra = bra if conj_b else bra.conj()
+                _view(c, t, dphys * x0 * Dl * x1)[:] = np.einsum("mk,okn->omn", Lm, bra).reshape(-1)
+            elif op == 4:    # ENVL3: L'[r,(a',r')] = sum_(p,l) ket[(p,l),r] U2[(p,l),(a',r')]
+                ket = _view(a, t, dphys * x0 * x1).reshape(dphys * x0, x1)
+                U2 = cj(_view(b, t, dphys * x0 * Dr * x1).reshape(dphys * x0, Dr * x1))
+                _view(c, t, x1 * Dr * x1)[:] = (ket.T @ U2).reshape(-1)
+            elif op == 5:    # MERGE
+                A = _view(a, t, dphys * x0 * x1).reshape(dphys, x0, x1)
+                Bm = cj(_view(b, t, dphys * x1 * x2).reshape(dphys, x1, x2))
+                _view(c, t, dphys * dphys * x0 * x2)[:] = np.einsum("slc,tcr->stlr", A, Bm).reshape(-1)
+            elif op == 6:    # ABSORB_R: next'_s[k,r] = G[k,j] next_s[j,r]
+                G = _view(a, t, x0 * x1).reshape(x0, x1)
+                nx = cj(_view(b, t, ngroups * x1 * x2).reshape(ngroups, x1, x2))
+                _view(c, t, ngroups * x0 * x2)[:] = np.einsum("kj,sjr->skr", G, nx).reshape(-1)
+            elif op == 7:    # ABSORB_L: prev'_s[l,k] = prev_s[l,j] G[j,k]
+                pv = _view(a, t, ngroups * x0 * x1).reshape(ngroups, x0, x1)
+                G = cj(_view(b, t, x1 * x2).reshape(x1, x2))
+                _view(c, t, ngroups * x0 * x2)[:] = np.einsum("slj,jk->slk", pv, G).reshape(-1)
+            else:
+                raise ValueError(op)
+
+    def wapply(self, nbatch, mask, el, er, nx, nu, ny, nv, wt, src, dst, max_lr):
+        self._launches += 1
+        W = _np(wt)[: nx * nu * ny * nv].reshape(nx, nu, ny, nv)
+        for t in range(nbatch):
+            if not _on(mask, t):
+                continue
+            l, r = _ext(el, t), _ext(er, t)
+            X = _view(src, t, nu * l * nv * r).reshape(nu, l, nv, r)
+            _view(dst, t, nx * l * ny * r)[:] = np.einsum("xuyv,ulvr->xlyr", W, X).reshape(-1)
+
+    def env_identity(self, nbatch, mask, echi, dmpo, env, max_chi):
+        self._launches += 1
+        for t in range(nbatch):
+            if not _on(mask, t):
+                continue
+            chi = _ext(echi, t)
+            e = np.zeros((chi, dmpo, chi), dtype=np.complex128)
+            for i in range(chi):
+                e[i, :, i] = 1
+            _view(env, t, e.size)[:] = e.reshape(-1)
+
+    # -- Lanczos ------------------------------------------------------------------------------------------------------
+    def lanczos_init(self, nbatch, mask, el, er, dphys, x, basis, stride_vec, nrm, active, kdone):
+        self._launches += 1
+        for t in range(nbatch):
+            if not _on(mask, t):
+                _np(active)[t] = 0
+                _np(kdone)[t] = -1
+                continue
+            n = dphys * _ext(el, t) * _ext(er, t)
+            v = _view(x, t, n)
+            nr = float(np.linalg.norm(v))
+            _np(nrm)[t] = nr
+            _np(active)[t] = 1 if nr > 0 else 0
+            _np(kdone)[t] = 0
+            if nr > 0:
+                _view(basis, t, n)[:] = v / nr
+
+    def lanczos_step(self, nbatch, j, kmax, dt, tol, el, er, dphys, basis, stride_vec, alpha, beta, nrm, active, kdone, coef, n_active):
+        self._launches += 1
+        al = _np(alpha).reshape(-1, LANCZOS_PITCH)
+        be = _np(beta).reshape(-1, LANCZOS_PITCH)
+        cf = _np(coef).reshape(-1, LANCZOS_PITCH)
+        for t in range(nbatch):
+            if not int(_np(active)[t]):
+                continue
+            n = dphys * _ext(el, t) * _ext(er, t)
+            vj = _view(basis.at(j * stride_vec), t, n)
+            w = _view(basis.at((j + 1) * stride_vec), t, n)
+            aj = float(np.vdot(vj, w).real)
+            al[t, j] = aj
+            w -= aj * vj
+            if j > 0:
+                w -= be[t, j - 1] * _view(basis.at((j - 1) * stride_vec), t, n)
+            last = j == kmax - 1
+            bj = float(np.linalg.norm(w))
+            if not last:
+                be[t, j] = bj
+            k = j + 1
+            breakdown = (not last) and bj < 100.0 * n * np.finfo(np.float64).eps
+            finish = False
+            if breakdown or j >= 1 or last:
+                if k == 1:
+                    lam, z = np.array([aj]), np.array([[1.0]])
+                else:
+                    lam, z = scipy.linalg.eigh_tridiagonal(al[t, :k], be[t, :k - 1])
+                ph = np.exp(-1j * dt * lam) * z[0]
+                if breakdown or last:
+                    finish = True
+                elif bj * abs(np.dot(z[k - 1], ph)) < tol:
+                    finish = True
+                if finish:
+                    cf[t, :k] = float(_np(nrm)[t]) * (z @ ph)
+            if finish:
+                _np(kdone)[t] = k
+                _np(active)[t] = 0
+            else:
+                w /= bj
+                _np(n_active)[0] += 1
+
+    def lanczos_combine(self, nbatch, mask, el, er, dphys, basis, stride_vec, coef, kmax, kdone, out):
+        self._launches += 1
+        cf = _np(coef).reshape(-1, LANCZOS_PITCH)
+        for t in range(nbatch):
+            if not _on(mask, t):
+                continue
+            k = int(_np(kdone)[t])
+            if k <= 0:
+                continue
+            n = dphys * _ext(el, t) * _ext(er, t)
+            acc = np.zeros(n, dtype=np.complex128)
+            for i in range(k):
+                acc += cf[t, i] * _view(basis.at(i * stride_vec), t, n)
+            _view(out, t, n)[:] = acc
+
+    # -- SVD (LAPACK stands in for the Jacobi rounds; outputs are gauge-equivalent) ------------------------------------
+    def svd_prepare(self, nbatch, mask, mode, el, er, dphys, src, w, q, meta, rot_count):
+        self._launches += 1
+        mt = _np(meta).reshape(-1, SVD_META)
+        for t in range(nbatch):
+            if not _on(mask, t):
+                mt[t, 5] = 1
+                continue
+            l, r = _ext(el, t), _ext(er, t)
+            if mode == 0:
+                M = _view(src, t, dphys * dphys * l * r).reshape(dphys, dphys, l, r).transpose(0, 2, 1, 3).reshape(dphys * l, dphys * r)
+            elif mode == 1:
+                M = _view(src, t, dphys * l * r).reshape(dphys * l, r)
+            else:
+                M = _view(src, t, dphys * l * r).reshape(dphys, l, r).transpose(1, 0, 2).reshape(l, dphys * r)
+            rows, cols = M.shape
+            orient = 0 if rows <= cols else 1
+            k, ln = (cols, rows) if orient else (rows, cols)
+            mt[t] = [k, ln, orient, rows, cols, 0, 0, 0]
+            W = M.conj().T if orient else M
+            _view(w, t, k * ln)[:] = np.ascontiguousarray(W).reshape(-1)
+            _view(q, t, k * k)[:] = np.eye(k, dtype=np.complex128).reshape(-1)
+            _np(rot_count)[t] = 0
+
+    def svd_round(self, nbatch, mask, meta, block_rows, nblocks, rnd, full_panel, inner_sweeps, w, q, rot_count, max_len, max_k):
+        self._launches += 1          # the twin factorises in svd_finalize with LAPACK
+
+    def svd_check(self, nbatch, mask, meta, rot_count, n_pending):
+        self._launches += 1
+        mt = _np(meta).reshape(-1, SVD_META)
+        for t in range(nbatch):
+            if _on(mask, t) and not mt[t, 5]:
+                mt[t, 5] = 1
+                mt[t, 6] += 1
+
+    def svd_finalize(self, nbatch, mask, meta, trunc_mode, threshold, max_bond, min_keep, dist, w, q, sval, stride_s, keep, uout, vout, status, max_k):
+        self._launches += 1
+        mt = _np(meta).reshape(-1, SVD_META)
+        for t in range(nbatch):
+            if not _on(mask, t):
+                continue
+            k, ln, orient, rows, cols = (int(v) for v in mt[t, :5])
+            W = _view(w, t, k * ln).reshape(k, ln)
+            M = W.conj().T if orient else W
+            u, s, vh = scipy.linalg.svd(M, full_matrices=False, lapack_driver="gesdd", check_finite=False)
+            kp = oracle_truncate(s, _TRUNC_NAMES[trunc_mode], threshold, max_bond if max_bond > 0 else None, min_keep)
+            _np(sval)[t * stride_s: t * stride_s + k] = s
+            _np(keep.tensor)[keep.offset + t * keep.stride] = kp
+            u, sk, vh = u[:, :kp], s[:kp], vh[:kp]
+            if dist == 0:
+                u = u * sk
+            elif dist == 1:
+                vh = vh * sk[:, None]
+            else:
+                u = u * np.sqrt(sk)
+                vh = vh * np.sqrt(sk)[:, None]
+            _view(uout, t, rows * kp)[:] = np.ascontiguousarray(u).reshape(-1)
+            _view(vout, t, kp * cols)[:] = np.ascontiguousarray(vh).reshape(-1)
+
+    # -- site-tensor utilities ----------------------------------------------------------------------------------------
+    def unpack_vh(self, nbatch, mask, ek, er, dphys, src, dst, max_elems):
+        self._launches += 1
+        for t in range(nbatch):
+            if not _on(mask, t):
+                continue
+            k, r = _ext(ek, t), _ext(er, t)
+            v = _view(src, t, k * dphys * r).reshape(k, dphys, r)
+            _view(dst, t, k * dphys * r)[:] = np.ascontiguousarray(v.transpose(1, 0, 2)).reshape(-1)
+
+    def copy_packed(self, nbatch, mask, e0, e1, mult, src, dst, max_elems):
+        self._launches += 1
+        for t in range(nbatch):
+            if not _on(mask, t):
+                continue
+            n = mult * _ext(e0, t) * (_ext(e1, t) if e1 is not None else 1)
+            _view(dst, t, n)[:] = _view(src, t, n)
+
+    def apply_local_op(self, nbatch, mask, sel, sel_value, el, er, dphys, op, op_stride, a, max_lr):
+        self._launches += 1
+        ops = _np(op)
+        for t in range(nbatch):
+            if not _on(mask, t):
+                continue
+            if sel is not None and int(_np(sel)[t]) != sel_value:
+                continue
+            l, r = _ext(el, t), _ext(er, t)
+            o = ops[t * op_stride: t * op_stride + dphys * dphys].reshape(dphys, dphys)
+            v = _view(a, t, dphys * l * r).reshape(dphys, l * r)
+            v[:] = o @ v
+
+    def norm2(self, nbatch, mask, el, er, dphys, a, out):
+        self._launches += 1
+        for t in range(nbatch):
+            if not _on(mask, t):
+                continue
+            v = _view(a, t, dphys * _ext(el, t) * _ext(er, t))
+            _np(out)[t] = float(np.vdot(v, v).real)
+
+    def scale(self, nbatch, mask, el, er, dphys, scale, a, max_elems):
+        self._launches += 1
+        for t in range(nbatch):
+            if not _on(mask, t):
+                continue
+            v = _view(a, t, dphys * _ext(el, t) * _ext(er, t))
+            v *= float(_np(scale)[t])
+
+    def local_rdm(self, nbatch, mask, el, er, dphys, a, x, g):
+        self._launches += 1
+        gg = _np(g).reshape(-1, dphys, dphys)
+        for t in range(nbatch):
+            if not _on(mask, t):
+                continue
+            lr = _ext(el, t) * _ext(er, t)
+            av = _view(a, t, dphys * lr).reshape(dphys, lr)
+            xv = _view(x, t, dphys * lr).reshape(dphys, lr)
+            gg[t] = av.conj() @ xv.T

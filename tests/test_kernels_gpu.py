@@ -1,0 +1,295 @@
+"""-m gpu: every CUDA kernel behind the C ABI vs. its numpy twin (oracle/np_kernels.py) on seeded ragged inputs.
+
+complex128 tolerance: 1e-12 relative to the operand norms for contractions (fp64 summation-order differences only);
+SVD outputs are compared through gauge-invariant quantities (singular values, keep counts, reconstruction, isometry).
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle.np_kernels import NumpyKernels
+from yaqs_b200 import kernels as K
+from yaqs_b200.kernels import Buf, Ext
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def backends():
+    return K.CudaKernels("cuda:0"), NumpyKernels()
+
+
+def _rand_c(rng, n):
+    return torch.from_numpy(rng.standard_normal(n) + 1j * rng.standard_normal(n))
+
+
+def _pair(t):
+    return t.clone(), t.clone().cuda()
+
+
+def _cmp(cpu, gpu, tol=1e-12):
+    a, b = cpu.numpy(), gpu.cpu().numpy()
+    scale = max(1.0, float(np.abs(a).max()))
+    assert np.max(np.abs(a - b)) <= tol * scale, float(np.max(np.abs(a - b)))
+
+
+GEMM_CASES = [
+    # (op, ngroups, dphys, Dl, Dr, conj, sizes of A/B/C as functions of (x0, x1, x2))
+    (K.OP_RCONTRACT, 1, 4, 3, 3, 0), (K.OP_RCONTRACT, 1, 2, 5, 4, 0), (K.OP_RCONTRACT, 1, 1, 3, 3, 0),
+    (K.OP_LCONTRACT, 4, 4, 3, 3, 0), (K.OP_LCONTRACT, 2, 2, 4, 5, 0), (K.OP_LCONTRACT, 1, 1, 3, 3, 0),
+    (K.OP_ENVR3, 1, 2, 3, 4, 0), (K.OP_ENVL1, 2, 2, 3, 4, 0), (K.OP_ENVL3, 1, 2, 3, 4, 0), (K.OP_ENVL3, 1, 2, 1, 1, 1),
+    (K.OP_MERGE, 4, 2, 1, 1, 0), (K.OP_ABSORB_R, 2, 2, 1, 1, 0), (K.OP_ABSORB_L, 2, 2, 1, 1, 0),
+]
+
+
+def _gemm_sizes(op, ngroups, dphys, Dl, Dr, cap):
+    c2 = cap * cap
+    if op == K.OP_RCONTRACT:
+        return dphys * c2, Dr * c2, dphys * Dr * c2
+    if op == K.OP_LCONTRACT:
+        return Dl * c2, dphys * Dl * c2, dphys * c2
+    if op == K.OP_ENVR3:
+        return dphys * Dl * c2, dphys * c2, Dl * c2
+    if op == K.OP_ENVL1:
+        return Dl * c2, dphys * c2, dphys * Dl * c2
+    if op == K.OP_ENVL3:
+        return dphys * c2, dphys * Dr * c2, Dr * c2
+    if op == K.OP_MERGE:
+        return dphys * c2, dphys * c2, dphys * dphys * c2
+    return ngroups * c2, ngroups * c2, ngroups * c2
+
+
+@pytest.mark.parametrize("case", GEMM_CASES)
+@pytest.mark.parametrize("cap", [5, 37, 96])
+def test_gemm_ops_match_twin(backends, case, cap):
+    cuda, twin = backends
+    op, ngroups, dphys, Dl, Dr, conj = case
+    rng = np.random.default_rng(1000 * op + cap)
+    nb = 5
+    ext = torch.from_numpy(rng.integers(1, cap + 1, size=(nb, 3)).astype(np.int32))
+    ext[0] = cap                                  # one trajectory at full capacity
+    mask = torch.tensor([1, 1, 0, 1, 1], dtype=torch.int32)
+    sa, sb, sc = _gemm_sizes(op, ngroups, dphys, Dl, Dr, cap)
+    a, b = _rand_c(rng, nb * sa + 7), _rand_c(rng, nb * sb + 3)
+    c = _rand_c(rng, nb * sc)
+    ext_c, ext_g = _pair(ext)
+    mask_c, mask_g = _pair(mask)
+    a_c, a_g = _pair(a)
+    b_c, b_g = _pair(b)
+    c_c, c_g = _pair(c)
+    maxm = 4 * 5 * cap
+    for kern, e, m, aa, bb, cc in ((twin, ext_c, mask_c, a_c, b_c, c_c), (cuda, ext_g, mask_g, a_g, b_g, c_g)):
+        kern.gemm(op, nb, ngroups, m, Ext(e, 0, 3), Ext(e, 1, 3), Ext(e, 2, 3), dphys, Dl, Dr, Buf(aa, 7, sa), Buf(bb, 3, sb),
+                  Buf(cc, 0, sc), conj, maxm, maxm)
+    torch.cuda.synchronize()
+    _cmp(c_c, c_g, 1e-12 * cap)
+
+
+@pytest.mark.parametrize("dims", [(4, 4, 3, 3), (2, 2, 5, 4), (2, 2, 1, 1), (4, 4, 5, 5)])
+def test_wapply_matches_twin(backends, dims):
+    cuda, twin = backends
+    nx, nu, ny, nv = dims
+    rng = np.random.default_rng(7)
+    nb, cap = 4, 19
+    ext = torch.from_numpy(rng.integers(1, cap + 1, size=(nb, 2)).astype(np.int32))
+    w = _rand_c(rng, nx * nu * ny * nv)
+    w[::3] = 0                                        # sparse MPO tensors: zero entries are skipped
+    sin, sout = nu * nv * cap * cap, nx * ny * cap * cap
+    src, dst = _rand_c(rng, nb * sin), _rand_c(rng, nb * sout)
+    ext_c, ext_g = _pair(ext)
+    w_c, w_g = _pair(w)
+    s_c, s_g = _pair(src)
+    d_c, d_g = _pair(dst)
+    for kern, e, ww, ss, dd in ((twin, ext_c, w_c, s_c, d_c), (cuda, ext_g, w_g, s_g, d_g)):
+        kern.wapply(nb, None, Ext(e, 0, 2), Ext(e, 1, 2), nx, nu, ny, nv, ww, Buf(ss, 0, sin), Buf(dd, 0, sout), cap * cap)
+    torch.cuda.synchronize()
+    _cmp(d_c, d_g)
+
+
+def test_small_utilities_match_twin(backends):
+    cuda, twin = backends
+    rng = np.random.default_rng(11)
+    nb, cap, d = 6, 13, 2
+    ext = torch.from_numpy(rng.integers(1, cap + 1, size=(nb, 2)).astype(np.int32))
+    mask = torch.tensor([1, 0, 1, 1, 1, 1], dtype=torch.int32)
+    sel = torch.tensor([3, 3, 2, 3, 1, 3], dtype=torch.int32)
+    slot = d * cap * cap
+    a = _rand_c(rng, nb * slot)
+    x = _rand_c(rng, nb * slot)
+    ops = _rand_c(rng, nb * d * d)
+    scale = torch.from_numpy(rng.standard_normal(nb))
+    res = {}
+    for name, kern, dev in (("cpu", twin, "cpu"), ("gpu", cuda, "cuda")):
+        e, m, s = ext.to(dev), mask.to(dev), sel.to(dev)
+        aa, xx, oo, sc = a.clone().to(dev), x.clone().to(dev), ops.to(dev), scale.to(dev)
+        el, er = Ext(e, 0, 2), Ext(e, 1, 2)
+        out = {}
+        n2 = torch.zeros(nb, dtype=torch.float64, device=dev)
+        kern.norm2(nb, m, el, er, d, Buf(aa, 0, slot), n2)
+        out["norm2"] = n2
+        g = torch.zeros(nb * d * d, dtype=torch.complex128, device=dev)
+        kern.local_rdm(nb, m, el, er, d, Buf(aa, 0, slot), Buf(xx, 0, slot), g)
+        out["rdm"] = g
+        kern.apply_local_op(nb, m, s, 3, el, er, d, oo, d * d, Buf(aa, 0, slot), cap * cap)
+        kern.apply_local_op(nb, None, None, 0, el, er, d, oo[: d * d].clone(), 0, Buf(xx, 0, slot), cap * cap)
+        kern.scale(nb, m, el, er, d, sc, Buf(xx, 0, slot), slot)
+        env = torch.zeros(nb * cap * 3 * cap, dtype=torch.complex128, device=dev)
+        kern.env_identity(nb, m, el, 3, Buf(env, 0, cap * 3 * cap), cap)
+        out["env"] = env
+        un = torch.zeros(nb * slot, dtype=torch.complex128, device=dev)
+        kern.unpack_vh(nb, m, el, er, d, Buf(aa, 0, slot), Buf(un, 0, slot), slot)
+        cp = torch.zeros(nb * slot, dtype=torch.complex128, device=dev)
+        kern.copy_packed(nb, m, el, er, d, Buf(xx, 0, slot), Buf(cp, 0, slot), slot)
+        out.update(a=aa, x=xx, unpack=un, copy=cp)
+        res[name] = out
+    torch.cuda.synchronize()
+    for key in res["cpu"]:
+        _cmp(res["cpu"][key], res["gpu"][key])
+
+
+def _run_lanczos(kern, dev, nb, n_list, hmats, x0, dt, tol, kmax=25):
+    """Drive init/step/combine with a dense Hermitian matvec done on the host side of the test."""
+    nmax = max(n_list)
+    ext = torch.tensor([[1, n] for n in n_list], dtype=torch.int32, device=dev)
+    el, er = Ext(ext, 0, 2), Ext(ext, 1, 2)
+    svec = nmax
+    basis = torch.zeros(nb * (kmax + 1) * svec, dtype=torch.complex128, device=dev)
+    bb = Buf(basis, 0, (kmax + 1) * svec)
+    x = torch.zeros(nb * nmax, dtype=torch.complex128, device=dev)
+    for t, n in enumerate(n_list):
+        x[t * nmax: t * nmax + n] = torch.from_numpy(x0[t]).to(dev)
+    nrm = torch.zeros(nb, dtype=torch.float64, device=dev)
+    active = torch.zeros(nb, dtype=torch.int32, device=dev)
+    kdone = torch.zeros(nb, dtype=torch.int32, device=dev)
+    alpha = torch.zeros(nb * 32, dtype=torch.float64, device=dev)
+    beta = torch.zeros(nb * 32, dtype=torch.float64, device=dev)
+    coef = torch.zeros(nb * 32, dtype=torch.complex128, device=dev)
+    nact = torch.zeros(1, dtype=torch.int32, device=dev)
+    kern.lanczos_init(nb, None, el, er, 1, Buf(x, 0, nmax), bb, svec, nrm, active, kdone)
+    for j in range(kmax):
+        bview = basis.view(nb, kmax + 1, svec)
+        for t, n in enumerate(n_list):                      # matvec: w = H v_j into slot j+1
+            if int(active[t]):
+                h = torch.from_numpy(hmats[t]).to(dev)
+                bview[t, j + 1, :n] = h @ bview[t, j, :n]
+        nact.zero_()
+        kern.lanczos_step(nb, j, kmax, dt, tol, el, er, 1, bb, svec, alpha, beta, nrm, active, kdone, coef, nact)
+        if kern.sync_int(nact) == 0:
+            break
+    out = x.clone()
+    kern.lanczos_combine(nb, None, el, er, 1, bb, svec, coef, kmax, kdone, Buf(out, 0, nmax))
+    return out.cpu().numpy().reshape(nb, nmax), kdone.cpu().numpy()
+
+
+def test_lanczos_matches_twin_and_expm(backends):
+    import scipy.linalg
+    cuda, twin = backends
+    rng = np.random.default_rng(5)
+    n_list = [40, 3, 64, 1, 17, 64]
+    hm, xs = [], []
+    for n in n_list:
+        m = rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))
+        hm.append((m + m.conj().T) / (2 * np.sqrt(n)))
+        xs.append(rng.standard_normal(n) + 1j * rng.standard_normal(n))
+    xs[3] = np.zeros(1, dtype=np.complex128)                 # zero vector is returned untouched
+    dt, tol = 0.1, 1e-10
+    out_g, k_g = _run_lanczos(cuda, "cuda", len(n_list), n_list, hm, xs, dt, tol)
+    out_c, k_c = _run_lanczos(twin, "cpu", len(n_list), n_list, hm, xs, dt, tol)
+    assert np.array_equal(k_g, k_c)
+    for t, n in enumerate(n_list):
+        assert np.max(np.abs(out_g[t, :n] - out_c[t, :n])) < 1e-12
+        exact = scipy.linalg.expm(-1j * dt * hm[t]) @ xs[t]
+        assert np.max(np.abs(out_g[t, :n] - exact)) < 1e-8
+
+
+def _run_svd(kern, dev, mode, dphys, ext_np, src_np, slot, trunc, thr, cap_bond, min_keep, dist, block_rows=8):
+    nb = ext_np.shape[0]
+    ext = torch.from_numpy(ext_np).to(dev)
+    el, er = Ext(ext, 0, 2), Ext(ext, 1, 2)
+    cap = int(ext_np.max())
+    maxdim = dphys * cap
+    src = torch.from_numpy(src_np).to(dev)
+    w = torch.zeros(nb * maxdim * maxdim, dtype=torch.complex128, device=dev)
+    q = torch.zeros(nb * maxdim * maxdim, dtype=torch.complex128, device=dev)
+    meta = torch.zeros(nb * 8, dtype=torch.int32, device=dev)
+    rot = torch.zeros(nb, dtype=torch.int32, device=dev)
+    pend = torch.zeros(1, dtype=torch.int32, device=dev)
+    wb, qb = Buf(w, 0, maxdim * maxdim), Buf(q, 0, maxdim * maxdim)
+    kern.svd_prepare(nb, None, mode, el, er, dphys, Buf(src, 0, slot), wb, qb, meta, rot)
+    nblocks = max(2, 2 * ((maxdim + 2 * block_rows - 1) // (2 * block_rows)))
+    for sweep in range(40):
+        for rnd in range(nblocks - 1):
+            kern.svd_round(nb, None, meta, block_rows, nblocks, rnd, rnd == 0, 1, wb, qb, rot, maxdim, maxdim)
+        pend.zero_()
+        kern.svd_check(nb, None, meta, rot, pend)
+        if kern.sync_int(pend) == 0:
+            break
+    sval = torch.zeros(nb * maxdim, dtype=torch.float64, device=dev)
+    keep = torch.zeros(nb, dtype=torch.int32, device=dev)
+    status = torch.zeros(nb, dtype=torch.int32, device=dev)
+    u = torch.zeros(nb * maxdim * maxdim, dtype=torch.complex128, device=dev)
+    v = torch.zeros(nb * maxdim * maxdim, dtype=torch.complex128, device=dev)
+    kern.svd_finalize(nb, None, meta, trunc, thr, cap_bond, min_keep, dist, wb, qb, sval, maxdim, Ext(keep, 0, 1),
+                      Buf(u, 0, maxdim * maxdim), Buf(v, 0, maxdim * maxdim), status, maxdim)
+    return (sval.cpu().numpy().reshape(nb, maxdim), keep.cpu().numpy(), u.cpu().numpy().reshape(nb, -1), v.cpu().numpy().reshape(nb, -1),
+            meta.cpu().numpy().reshape(nb, 8), status.cpu().numpy(), sweep + 1)
+
+
+@pytest.mark.parametrize("mode", [K.SVD_THETA, K.SVD_ROWS, K.SVD_COLS])
+@pytest.mark.parametrize("dist", [0, 1, 2])
+def test_svd_matches_lapack(backends, mode, dist):
+    cuda, twin = backends
+    rng = np.random.default_rng(100 + 10 * mode + dist)
+    d, cap, nb = 2, 24, 6
+    ext = rng.integers(1, cap + 1, size=(nb, 2)).astype(np.int32)
+    ext[0] = cap
+    ext[1] = (cap, 3)
+    ext[2] = (2, cap)
+    nphys = d * d if mode == K.SVD_THETA else d
+    slot = nphys * cap * cap
+    src = (rng.standard_normal(nb * slot) + 1j * rng.standard_normal(nb * slot))
+    # graded spectrum for trajectory 3 so that the threshold actually truncates: low-rank + tiny noise
+    l3, r3 = ext[3]
+    args = (mode, d, ext, src, slot, 0, 1e-3, 12, 2, dist)
+    sg, kg, ug, vg, mg, stg, nsweeps = _run_svd(cuda, "cuda", *args)
+    sc, kc, uc, vc, mc, _, _ = _run_svd(twin, "cpu", *args)
+    assert nsweeps < 30 and not stg.any()
+    assert np.array_equal(kg, kc)
+    for t in range(nb):
+        k, rows, cols = mc[t, 0], mc[t, 3], mc[t, 4]
+        assert np.max(np.abs(sg[t, :k] - sc[t, :k])) < 1e-12 * max(1.0, sc[t, 0])
+        kp = kg[t]
+        U_g, V_g = ug[t, : rows * kp].reshape(rows, kp), vg[t, : kp * cols].reshape(kp, cols)
+        U_c, V_c = uc[t, : rows * kp].reshape(rows, kp), vc[t, : kp * cols].reshape(kp, cols)
+        assert np.max(np.abs(U_g @ V_g - U_c @ V_c)) < 1e-11 * max(1.0, sc[t, 0])
+        iso = (V_g @ V_g.conj().T) if dist == 0 else (U_g.conj().T @ U_g) if dist == 1 else None
+        if iso is not None:
+            assert np.max(np.abs(iso - np.eye(kp))) < 1e-12
+
+
+def test_svd_rank_deficient_min_keep(backends):
+    """Product-state theta: rank 1, min_keep = 2 forces a zero singular value into the kept set; the non-S factor must
+    still be an isometry (LAPACK returns an arbitrary orthonormal completion there)."""
+    cuda, _ = backends
+    d, nb = 2, 3
+    ext = np.array([[1, 1], [2, 3], [4, 4]], dtype=np.int32)
+    cap = 4
+    slot = d * d * cap * cap
+    src = np.zeros(nb * slot, dtype=np.complex128)
+    rng = np.random.default_rng(3)
+    for t, (l, r) in enumerate(ext):
+        a = rng.standard_normal(d * l) + 1j * rng.standard_normal(d * l)
+        b = rng.standard_normal(d * r) + 1j * rng.standard_normal(d * r)
+        theta = np.outer(a, b).reshape(d, l, d, r).transpose(0, 2, 1, 3)          # ((s s'), l, r)
+        src[t * slot: t * slot + theta.size] = theta.reshape(-1)
+    for dist in (0, 1):
+        sg, kg, ug, vg, mg, stg, _ = _run_svd(cuda, "cuda", K.SVD_THETA, d, ext, src, slot, 0, 1e-9, 8, 2, dist)
+        assert list(kg) == [2, 2, 2]
+        for t, (l, r) in enumerate(ext):
+            rows, cols, kp = d * l, d * r, 2
+            U, V = ug[t, : rows * kp].reshape(rows, kp), vg[t, : kp * cols].reshape(kp, cols)
+            theta = src[t * slot: t * slot + d * d * l * r].reshape(d, d, l, r).transpose(0, 2, 1, 3).reshape(rows, cols)
+            assert np.max(np.abs(U @ V - theta)) < 1e-13 * np.abs(theta).max() + 1e-14
+            iso = V @ V.conj().T if dist == 0 else U.conj().T @ U
+            assert np.max(np.abs(iso - np.eye(kp))) < 1e-12
+            assert sg[t, 1] < 1e-14 * sg[t, 0]

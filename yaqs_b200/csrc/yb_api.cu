@@ -1,0 +1,205 @@
+// extern "C" boundary of libyaqs_b200.so (declared in include/yaqs_b200.h).  Plain pointers and sizes only.
+#include "../../include/yaqs_b200.h"
+#include "yb_common.cuh"
+#include <atomic>
+#include <stdio.h>
+#include <string.h>
+
+// unity build: the kernels live in the same translation unit (no -rdc needed)
+#include "yb_gemm.cu"
+#include "yb_ops.cu"
+#include "yb_svd.cu"
+
+namespace {
+thread_local char g_err[512] = "";
+std::atomic<long long> g_launches{0};
+
+int fail(const char* where, cudaError_t e) {
+    snprintf(g_err, sizeof(g_err), "%s: %s", where, cudaGetErrorString(e));
+    return -1;
+}
+int fail_msg(const char* msg) {
+    snprintf(g_err, sizeof(g_err), "%s", msg);
+    return -2;
+}
+inline int done(const char* where) {
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : fail(where, e);
+}
+inline int grid_for(long long n, int threads, int cap = 4096) {
+    long long g = (n + threads - 1) / threads;
+    if (g < 1) g = 1;
+    if (g > cap) g = cap;
+    return (int)g;
+}
+}  // namespace
+
+extern "C" {
+
+const char* yb_last_error(void) { return g_err; }
+int yb_version(void) { return 100; }
+int64_t yb_launch_count(int reset) {
+    long long v = g_launches.load();
+    if (reset) g_launches.store(0);
+    return v;
+}
+
+int yb_gemm(int op, int nbatch, int ngroups, const int32_t* mask, yb_extent e0, yb_extent e1, yb_extent e2, int dphys, int d_left, int d_right,
+            const void* a, int64_t stride_a, const void* b, int64_t stride_b, void* c, int64_t stride_c, int conj_b, int max_m, int max_n,
+            void* stream) {
+    if (op < 0 || op > YB_OP_ABSORB_L) return fail_msg("yb_gemm: unknown op");
+    if (nbatch <= 0) return 0;
+    YbGemmParams P;
+    memset(&P, 0, sizeof(P));
+    P.op = op; P.nbatch = nbatch; P.ngroups = ngroups; P.mask = mask;
+    P.e0 = e0.ptr; P.es0 = e0.stride; P.e1 = e1.ptr; P.es1 = e1.stride; P.e2 = e2.ptr; P.es2 = e2.stride;
+    P.dphys = dphys; P.Dl = d_left; P.Dr = d_right;
+    P.A = (const cplx*)a; P.Bm = (const cplx*)b; P.C = (cplx*)c; P.sA = stride_a; P.sB = stride_b; P.sC = stride_c;
+    P.conj_extra = conj_b;
+    cudaError_t e = yb_launch_gemm(P, max_m, max_n, (cudaStream_t)stream);
+    if (e != cudaSuccess) return fail("yb_gemm", e);
+    return done("yb_gemm");
+}
+
+int yb_wapply(int nbatch, const int32_t* mask, yb_extent el, yb_extent er, int nx, int nu, int ny, int nv, const void* wt, const void* in,
+              int64_t stride_in, void* out, int64_t stride_out, int max_lr, void* stream) {
+    if (nbatch <= 0 || max_lr <= 0) return 0;
+    dim3 grid((max_lr + 255) / 256, nx * ny, nbatch);
+    k_wapply<<<grid, 256, 0, (cudaStream_t)stream>>>(nx, nu, ny, nv, (const cplx*)wt, (const cplx*)in, stride_in, (cplx*)out, stride_out, el.ptr,
+                                                      el.stride, er.ptr, er.stride, mask);
+    return done("yb_wapply");
+}
+
+int yb_env_identity(int nbatch, const int32_t* mask, yb_extent echi, int dmpo, void* env, int64_t stride_env, int max_chi, void* stream) {
+    if (nbatch <= 0) return 0;
+    dim3 grid(grid_for((long long)max_chi * dmpo * max_chi, 256, 64), nbatch);
+    k_env_identity<<<grid, 256, 0, (cudaStream_t)stream>>>(dmpo, (cplx*)env, stride_env, echi.ptr, echi.stride, mask);
+    return done("yb_env_identity");
+}
+
+int yb_lanczos_init(int nbatch, const int32_t* mask, yb_extent el, yb_extent er, int dphys, const void* x, int64_t stride_x, void* basis,
+                    int64_t stride_basis, int64_t stride_vec, double* nrm, int32_t* active, int32_t* kdone, void* stream) {
+    (void)stride_vec;
+    if (nbatch <= 0) return 0;
+    k_lanczos_init<<<nbatch, 1024, 0, (cudaStream_t)stream>>>(dphys, (const cplx*)x, stride_x, (cplx*)basis, stride_basis, nrm, active, kdone, el.ptr,
+                                                               el.stride, er.ptr, er.stride, mask);
+    return done("yb_lanczos_init");
+}
+
+int yb_lanczos_step(int nbatch, int j, int kmax, double dt, double tol, yb_extent el, yb_extent er, int dphys, void* basis, int64_t stride_basis,
+                    int64_t stride_vec, double* alpha, double* beta, const double* nrm, int32_t* active, int32_t* kdone, void* coef,
+                    int32_t* n_active, void* stream) {
+    if (nbatch <= 0) return 0;
+    if (kmax > 32 || j >= kmax) return fail_msg("yb_lanczos_step: kmax must be <= 32 and j < kmax");
+    k_lanczos_step<<<nbatch, 1024, 0, (cudaStream_t)stream>>>(j, kmax, dt, tol, dphys, (cplx*)basis, stride_basis, stride_vec, alpha, beta, nrm, active,
+                                                               kdone, (cplx*)coef, n_active, el.ptr, el.stride, er.ptr, er.stride);
+    return done("yb_lanczos_step");
+}
+
+int yb_lanczos_combine(int nbatch, const int32_t* mask, yb_extent el, yb_extent er, int dphys, const void* basis, int64_t stride_basis,
+                       int64_t stride_vec, const void* coef, int kmax, const int32_t* kdone, void* out, int64_t stride_out, void* stream) {
+    (void)kmax;
+    if (nbatch <= 0) return 0;
+    dim3 grid(grid_for(stride_vec, 256, 64), nbatch);
+    k_lanczos_combine<<<grid, 256, 0, (cudaStream_t)stream>>>(dphys, (const cplx*)basis, stride_basis, stride_vec, (const cplx*)coef, kdone, (cplx*)out,
+                                                               stride_out, el.ptr, el.stride, er.ptr, er.stride, mask);
+    return done("yb_lanczos_combine");
+}
+
+int yb_svd_prepare(int nbatch, const int32_t* mask, int mode, yb_extent el, yb_extent er, int dphys, const void* src, int64_t stride_src, void* w,
+                   int64_t stride_w, void* q, int64_t stride_q, int32_t* meta, int32_t* rot_count, void* stream) {
+    if (nbatch <= 0) return 0;
+    dim3 grid(grid_for(stride_w, 256, 64), nbatch);
+    k_svd_prepare<<<grid, 256, 0, (cudaStream_t)stream>>>(mode, dphys, (const cplx*)src, stride_src, (cplx*)w, stride_w, (cplx*)q, stride_q, meta,
+                                                           rot_count, el.ptr, el.stride, er.ptr, er.stride, mask);
+    return done("yb_svd_prepare");
+}
+
+int yb_svd_round(int nbatch, const int32_t* mask, int32_t* meta, int block_rows, int nblocks, int round, int full_panel, int inner_sweeps, void* w,
+                 int64_t stride_w, void* q, int64_t stride_q, int32_t* rot_count, int max_len, int max_k, void* stream) {
+    if (nbatch <= 0) return 0;
+    if (nblocks < 2 || (nblocks & 1)) return fail_msg("yb_svd_round: nblocks must be even and >= 2");
+    const size_t smem = (size_t)2 * block_rows * ((size_t)max_len + max_k) * sizeof(cplx);
+    if (smem > 227 * 1024) return fail_msg("yb_svd_round: panel does not fit in shared memory");
+    static size_t configured = 0;
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(k_svd_round, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return fail("yb_svd_round(attr)", e);
+        configured = smem;
+    }
+    dim3 grid(nblocks / 2, nbatch);
+    k_svd_round<<<grid, 512, smem, (cudaStream_t)stream>>>(block_rows, nblocks, round, full_panel, inner_sweeps, (cplx*)w, stride_w, (cplx*)q, stride_q,
+                                                            meta, rot_count, max_len, max_k, mask);
+    return done("yb_svd_round");
+}
+
+int yb_svd_check(int nbatch, const int32_t* mask, int32_t* meta, int32_t* rot_count, int32_t* n_pending, void* stream) {
+    if (nbatch <= 0) return 0;
+    k_svd_check<<<(nbatch + 127) / 128, 128, 0, (cudaStream_t)stream>>>(nbatch, meta, rot_count, n_pending, mask);
+    return done("yb_svd_check");
+}
+
+int yb_svd_finalize(int nbatch, const int32_t* mask, const int32_t* meta, int trunc_mode, double threshold, int max_bond, int min_keep, int dist,
+                    const void* w, int64_t stride_w, const void* q, int64_t stride_q, double* sval, int64_t stride_s, int32_t* keep,
+                    int32_t keep_stride, void* uout, int64_t stride_u, void* vout, int64_t stride_v, int32_t* status, int max_k, void* stream) {
+    if (nbatch <= 0) return 0;
+    if (max_k > 1024) return fail_msg("yb_svd_finalize: max_k > 1024 unsupported");
+    k_svd_finalize<<<nbatch, 512, 0, (cudaStream_t)stream>>>(trunc_mode, threshold, max_bond, min_keep, dist, (const cplx*)w, stride_w, (const cplx*)q,
+                                                              stride_q, meta, sval, stride_s, keep, keep_stride, (cplx*)uout, stride_u, (cplx*)vout,
+                                                              stride_v, status, mask);
+    return done("yb_svd_finalize");
+}
+
+int yb_unpack_vh(int nbatch, const int32_t* mask, yb_extent ek, yb_extent er, int dphys, const void* src, int64_t stride_src, void* dst,
+                 int64_t stride_dst, int max_elems, void* stream) {
+    if (nbatch <= 0) return 0;
+    dim3 grid(grid_for(max_elems, 256, 64), nbatch);
+    k_unpack_vh<<<grid, 256, 0, (cudaStream_t)stream>>>(dphys, (const cplx*)src, stride_src, (cplx*)dst, stride_dst, ek.ptr, ek.stride, er.ptr,
+                                                         er.stride, mask);
+    return done("yb_unpack_vh");
+}
+
+int yb_copy_packed(int nbatch, const int32_t* mask, yb_extent e0, yb_extent e1, int mult, const void* src, int64_t stride_src, void* dst,
+                   int64_t stride_dst, int max_elems, void* stream) {
+    if (nbatch <= 0) return 0;
+    dim3 grid(grid_for(max_elems, 256, 64), nbatch);
+    k_copy_packed<<<grid, 256, 0, (cudaStream_t)stream>>>(mult, (const cplx*)src, stride_src, (cplx*)dst, stride_dst, e0.ptr, e0.stride, e1.ptr,
+                                                           e1.stride, mask);
+    return done("yb_copy_packed");
+}
+
+int yb_apply_local_op(int nbatch, const int32_t* mask, const int32_t* sel, int sel_value, yb_extent el, yb_extent er, int dphys, const void* op,
+                      int64_t op_stride, void* a, int64_t stride_a, int max_lr, void* stream) {
+    if (nbatch <= 0) return 0;
+    if (dphys > 4) return fail_msg("yb_apply_local_op: dphys > 4 unsupported");
+    dim3 grid(grid_for(max_lr, 256, 64), nbatch);
+    k_apply_local_op<<<grid, 256, 0, (cudaStream_t)stream>>>(dphys, (const cplx*)op, op_stride, (cplx*)a, stride_a, el.ptr, el.stride, er.ptr,
+                                                              er.stride, mask, sel, sel_value);
+    return done("yb_apply_local_op");
+}
+
+int yb_norm2(int nbatch, const int32_t* mask, yb_extent el, yb_extent er, int dphys, const void* a, int64_t stride_a, double* out, void* stream) {
+    if (nbatch <= 0) return 0;
+    k_norm2<<<nbatch, 1024, 0, (cudaStream_t)stream>>>(dphys, (const cplx*)a, stride_a, out, el.ptr, el.stride, er.ptr, er.stride, mask);
+    return done("yb_norm2");
+}
+
+int yb_scale(int nbatch, const int32_t* mask, yb_extent el, yb_extent er, int dphys, const double* scale, void* a, int64_t stride_a, int max_elems,
+             void* stream) {
+    if (nbatch <= 0) return 0;
+    dim3 grid(grid_for(max_elems, 256, 64), nbatch);
+    k_scale<<<grid, 256, 0, (cudaStream_t)stream>>>(dphys, scale, (cplx*)a, stride_a, el.ptr, el.stride, er.ptr, er.stride, mask);
+    return done("yb_scale");
+}
+
+int yb_local_rdm(int nbatch, const int32_t* mask, yb_extent el, yb_extent er, int dphys, const void* a, int64_t stride_a, const void* x,
+                 int64_t stride_x, void* g, void* stream) {
+    if (nbatch <= 0) return 0;
+    if (dphys > 4) return fail_msg("yb_local_rdm: dphys > 4 unsupported");
+    k_local_rdm<<<nbatch, 512, 0, (cudaStream_t)stream>>>(dphys, (const cplx*)a, stride_a, (const cplx*)x, stride_x, (cplx*)g, el.ptr, el.stride, er.ptr,
+                                                           er.stride, mask);
+    return done("yb_local_rdm");
+}
+
+}  // extern "C"

@@ -1,0 +1,251 @@
+// Batched complex128 contraction kernel for the TDVP hot path (sm_100a).
+//
+// Every contraction of the reference's tensordot chain (core/methods/tdvp/primitives.py:77-226,
+// core/methods/decompositions.py:87-102) is a (grouped, K-segmented) complex GEMM over per-trajectory
+// operands with ragged extents.  FP64 has no tcgen05 kind, so the tensor path is the warp-level
+// DMMA (mma.sync.m8n8k4.f64 -> SASS DMMA.8x8x4); one complex MAC = 4 DMMA issues with the sign of the
+// Ai*Bi term folded into the A fragment (integer XOR on the sign bit, off the FP64 pipe).
+//
+// Tiling: CTA 64 x 128 complex, BK = 8, 4-stage cp.async (LDGSTS.128, one complex per copy, zero-fill
+// for ragged edges), 8 warps as 2 x 4, warp tile 32 x 32 => 64 fp64 accumulators per thread.  Operands
+// stay interleaved in shared memory so one LDS.128 feeds both the real and imaginary fragment; the row
+// pitches (12 / 66 / 130 complex) make every quarter-warp LDS.128 hit 8 distinct 16-byte bank groups.
+#include "yb_common.cuh"
+
+namespace {
+
+constexpr int BM = 64, BN = 128, BKT = 8, STAGES = 4, NTHREADS = 256;
+constexpr int A_KIN_LD = BKT + 4;   // A stored [m][k]
+constexpr int A_KOUT_LD = BM + 2;   // A stored [k][m]
+constexpr int B_KIN_LD = BKT + 4;   // B stored [n][k]
+constexpr int B_KOUT_LD = BN + 2;   // B stored [k][n]
+constexpr int A_STAGE = (BM * A_KIN_LD > BKT * A_KOUT_LD) ? BM * A_KIN_LD : BKT * A_KOUT_LD;   // complex elements
+constexpr int B_STAGE = (BN * B_KIN_LD > BKT * B_KOUT_LD) ? BN * B_KIN_LD : BKT * B_KOUT_LD;
+
+enum { LAY_AK = 0, LAY_AM = 1 };   // A global layout: k contiguous / m contiguous
+enum { LAY_BN = 0, LAY_BK = 1 };   // B global layout: n contiguous / k contiguous
+
+struct Desc {
+    const cplx* A; const cplx* B; cplx* C;
+    int M, N, K, nseg;
+    long long a_rs, a_cs, a_ss, b_rs, b_cs, b_ss, c_rs;
+    bool conjB;
+};
+
+__device__ __forceinline__ bool make_desc(const YbGemmParams& P, int b, int g, Desc& d) {
+    const int x0 = P.e0 ? P.e0[(long long)b * P.es0] : 0;
+    const int x1 = P.e1 ? P.e1[(long long)b * P.es1] : 0;
+    const int x2 = P.e2 ? P.e2[(long long)b * P.es2] : 0;
+    const cplx* A = P.A + (long long)b * P.sA;
+    const cplx* B = P.Bm + (long long)b * P.sB;
+    cplx* C = P.C + (long long)b * P.sC;
+    d.nseg = 1; d.a_ss = 0; d.b_ss = 0; d.conjB = false; d.a_cs = 1; d.b_cs = 1;
+    switch (P.op) {
+    case YB_OP_RCONTRACT: {           // x0 = l, x1 = r
+        d.M = P.dphys * x0; d.K = x1; d.N = P.Dr * x1;
+        d.A = A; d.a_rs = x1;
+        d.B = B; d.b_rs = (long long)P.Dr * x1;
+        d.C = C; d.c_rs = (long long)P.Dr * x1;
+    } break;
+    case YB_OP_LCONTRACT: {           // x0 = l, x1 = r ; group o
+        d.M = x0; d.K = x0 * P.Dl; d.N = x1;
+        d.A = A; d.a_rs = 1; d.a_cs = x0;
+        d.B = B + (long long)g * x0 * P.Dl * x1; d.b_rs = x1;
+        d.C = C + (long long)g * x0 * x1; d.c_rs = x1;
+    } break;
+    case YB_OP_ENVR3: {               // x0 = l, x1 = r ; segments o
+        d.M = x0 * P.Dl; d.N = x0; d.K = x1; d.nseg = P.dphys;
+        d.A = A; d.a_rs = x1; d.a_ss = (long long)x0 * P.Dl * x1;
+        d.B = B; d.b_rs = 1; d.b_cs = x1; d.b_ss = (long long)x0 * x1; d.conjB = true;
+        d.C = C; d.c_rs = x0;
+    } break;
+    case YB_OP_ENVL1: {               // x0 = l, x1 = r ; group o
+        d.M = x0 * P.Dl; d.K = x0; d.N = x1;
+        d.A = A; d.a_rs = x0;
+        d.B = B + (long long)g * x0 * x1; d.b_rs = x1; d.conjB = true;
+        d.C = C + (long long)g * x0 * P.Dl * x1; d.c_rs = x1;
+    } break;
+    case YB_OP_ENVL3: {               // x0 = l, x1 = r
+        d.M = x1; d.K = P.dphys * x0; d.N = P.Dr * x1;
+        d.A = A; d.a_rs = 1; d.a_cs = x1;
+        d.B = B; d.b_rs = (long long)P.Dr * x1;
+        d.C = C; d.c_rs = (long long)P.Dr * x1;
+    } break;
+    case YB_OP_MERGE: {               // x0 = l, x1 = c, x2 = r ; group s*d + s'
+        const int s = g / P.dphys, sp = g % P.dphys;
+        d.M = x0; d.K = x1; d.N = x2;
+        d.A = A + (long long)s * x0 * x1; d.a_rs = x1;
+        d.B = B + (long long)sp * x1 * x2; d.b_rs = x2;
+        d.C = C + (long long)g * x0 * x2; d.c_rs = x2;
+    } break;
+    case YB_OP_ABSORB_R: {            // x0 = k_new, x1 = j_old, x2 = r ; group s
+        d.M = x0; d.K = x1; d.N = x2;
+        d.A = A; d.a_rs = x1;
+        d.B = B + (long long)g * x1 * x2; d.b_rs = x2;
+        d.C = C + (long long)g * x0 * x2; d.c_rs = x2;
+    } break;
+    case YB_OP_ABSORB_L: {            // x0 = l, x1 = j_old, x2 = k_new ; group s
+        d.M = x0; d.K = x1; d.N = x2;
+        d.A = A + (long long)g * x0 * x1; d.a_rs = x1;
+        d.B = B; d.b_rs = x2;
+        d.C = C + (long long)g * x0 * x2; d.c_rs = x2;
+    } break;
+    default: return false;
+    }
+    if (P.conj_extra) d.conjB = !d.conjB;
+    return d.M > 0 && d.N > 0;
+}
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src, bool valid) {
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+    const int sz = valid ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" :: "r"(dst), "l"(gmem_src), "r"(sz));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" :: "n"(N)); }
+
+__device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+__device__ __forceinline__ double flip_sign(double x) {
+    return __hiloint2double(__double2hiint(x) ^ 0x80000000, __double2loint(x));
+}
+
+template <int ALAY, int BLAY>
+__global__ void __launch_bounds__(NTHREADS, 1) k_gemm(const YbGemmParams P) {
+    const int b = blockIdx.z, g = blockIdx.y;
+    if (P.mask && !P.mask[b]) return;
+    Desc d;
+    if (!make_desc(P, b, g, d)) return;
+    const int tiles_n = (d.N + BN - 1) / BN;
+    const int tiles_m = (d.M + BM - 1) / BM;
+    if ((int)blockIdx.x >= tiles_m * tiles_n) return;
+    const int m0 = ((int)blockIdx.x / tiles_n) * BM, n0 = ((int)blockIdx.x % tiles_n) * BN;
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cplx* As = reinterpret_cast<cplx*>(smem_raw);
+    cplx* Bs = As + STAGES * A_STAGE;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = warp >> 2, wn = warp & 3;
+    const int kt_per_seg = (d.K + BKT - 1) / BKT;
+    const int ktiles = kt_per_seg * d.nseg;
+
+    auto load_stage = [&](int kt, int stage) {
+        if (kt < ktiles) {
+            const int seg = kt / kt_per_seg, k0 = (kt % kt_per_seg) * BKT;
+            const cplx* Ab = d.A + seg * d.a_ss;
+            const cplx* Bb = d.B + seg * d.b_ss;
+            cplx* as = As + stage * A_STAGE;
+            cplx* bs = Bs + stage * B_STAGE;
+#pragma unroll
+            for (int q = 0; q < (BM * BKT) / NTHREADS; ++q) {
+                const int e = tid + q * NTHREADS;
+                int m, k;
+                if (ALAY == LAY_AK) { k = e % BKT; m = e / BKT; } else { m = e % BM; k = e / BM; }
+                const bool ok = (m0 + m < d.M) && (k0 + k < d.K);
+                const cplx* src = ok ? (Ab + (long long)(m0 + m) * d.a_rs + (long long)(k0 + k) * d.a_cs) : Ab;
+                cplx* dst = (ALAY == LAY_AK) ? (as + m * A_KIN_LD + k) : (as + k * A_KOUT_LD + m);
+                cp_async16(dst, src, ok);
+            }
+#pragma unroll
+            for (int q = 0; q < (BN * BKT) / NTHREADS; ++q) {
+                const int e = tid + q * NTHREADS;
+                int n, k;
+                if (BLAY == LAY_BN) { n = e % BN; k = e / BN; } else { k = e % BKT; n = e / BKT; }
+                const bool ok = (n0 + n < d.N) && (k0 + k < d.K);
+                const cplx* src = ok ? (Bb + (long long)(k0 + k) * d.b_rs + (long long)(n0 + n) * d.b_cs) : Bb;
+                cplx* dst = (BLAY == LAY_BN) ? (bs + k * B_KOUT_LD + n) : (bs + n * B_KIN_LD + k);
+                cp_async16(dst, src, ok);
+            }
+        }
+        cp_async_commit();
+    };
+
+    double cr[4][4][2], ci[4][4][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { cr[i][j][0] = cr[i][j][1] = ci[i][j][0] = ci[i][j][1] = 0.0; }
+
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; ++s) load_stage(s, s);
+
+    const int fr = lane >> 2, fk = lane & 3;
+    for (int kt = 0; kt < ktiles; ++kt) {
+        cp_async_wait<STAGES - 2>();
+        __syncthreads();
+        load_stage(kt + STAGES - 1, (kt + STAGES - 1) % STAGES);
+        const cplx* as = As + (kt % STAGES) * A_STAGE;
+        const cplx* bs = Bs + (kt % STAGES) * B_STAGE;
+#pragma unroll
+        for (int kk = 0; kk < BKT; kk += 4) {
+            double ar[4], ai[4], an[4], br[4], bi[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int row = wm * 32 + i * 8 + fr, k = kk + fk;
+                const cplx v = (ALAY == LAY_AK) ? as[row * A_KIN_LD + k] : as[k * A_KOUT_LD + row];
+                ar[i] = v.x; ai[i] = v.y; an[i] = flip_sign(v.y);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int n = wn * 32 + j * 8 + fr, k = kk + fk;
+                const cplx v = (BLAY == LAY_BN) ? bs[k * B_KOUT_LD + n] : bs[n * B_KIN_LD + k];
+                br[j] = v.x; bi[j] = d.conjB ? flip_sign(v.y) : v.y;
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    dmma(cr[i][j][0], cr[i][j][1], ar[i], br[j]);
+                    dmma(ci[i][j][0], ci[i][j][1], ar[i], bi[j]);
+                    dmma(cr[i][j][0], cr[i][j][1], an[i], bi[j]);
+                    dmma(ci[i][j][0], ci[i][j][1], ai[i], br[j]);
+                }
+        }
+    }
+    cp_async_wait<0>();
+
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int row = m0 + wm * 32 + i * 8 + fr;
+        if (row >= d.M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int col = n0 + wn * 32 + j * 8 + 2 * fk;
+            cplx* dst = d.C + (long long)row * d.c_rs + col;
+            if (col < d.N) dst[0] = make_double2(cr[i][j][0], ci[i][j][0]);
+            if (col + 1 < d.N) dst[1] = make_double2(cr[i][j][1], ci[i][j][1]);
+        }
+    }
+}
+
+constexpr size_t GEMM_SMEM = (size_t)STAGES * (A_STAGE + B_STAGE) * sizeof(cplx);
+
+template <int ALAY, int BLAY>
+cudaError_t launch_t(const YbGemmParams& P, int maxM, int maxN, cudaStream_t st) {
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(k_gemm<ALAY, BLAY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    const int tiles = ((maxM + BM - 1) / BM) * ((maxN + BN - 1) / BN);
+    dim3 grid(tiles, P.ngroups, P.nbatch);
+    k_gemm<ALAY, BLAY><<<grid, NTHREADS, GEMM_SMEM, st>>>(P);
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+// maxM / maxN: upper bounds of the per-trajectory M and N (grid is sized for them; empty tiles exit).
+cudaError_t yb_launch_gemm(const YbGemmParams& P, int maxM, int maxN, cudaStream_t st) {
+    if (P.nbatch <= 0 || maxM <= 0 || maxN <= 0) return cudaSuccess;
+    switch (P.op) {
+    case YB_OP_LCONTRACT:
+    case YB_OP_ENVL3: return launch_t<LAY_AM, LAY_BN>(P, maxM, maxN, st);
+    case YB_OP_ENVR3: return launch_t<LAY_AK, LAY_BK>(P, maxM, maxN, st);
+    default: return launch_t<LAY_AK, LAY_BN>(P, maxM, maxN, st);
+    }
+}

@@ -1,0 +1,334 @@
+// Memory-bound batched kernels of the TJM hot path: MPO-tensor application, Lanczos vector work + the tiny
+// tridiagonal eigen-solve, site-tensor utilities, local reduced density matrices.  All are HBM-bound streaming
+// kernels: coalesced 16-byte accesses along the fastest (right-bond) index, one launch covers the whole batch.
+#include "yb_common.cuh"
+#include <math.h>
+
+// ---------------------------------------------------------------------------------------------------------------------
+// out[x,l,y,r] = sum_(u,v) wt[x,u,y,v] in[u,l,v,r]      (primitives.py:106,135,202)
+// grid = (ceil(l*r / 256), nx*ny, B).  wt is tiny and identical for all trajectories -> read through the read-only path;
+// zero entries of the (sparse, ~30 % dense) MPO tensor are skipped block-uniformly.
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void k_wapply(int nx, int nu, int ny, int nv, const cplx* __restrict__ wt, const cplx* __restrict__ in, long long s_in,
+                         cplx* __restrict__ out, long long s_out, const int* el, int esl, const int* er, int esr, const int* mask) {
+    const int b = blockIdx.z;
+    if (mask && !mask[b]) return;
+    const int l = el[(long long)b * esl], r = er[(long long)b * esr];
+    const long long lr = (long long)l * r;
+    const long long pos = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pos >= lr) return;
+    const int x = blockIdx.y / ny, y = blockIdx.y % ny;
+    const int li = (int)(pos / r), ri = (int)(pos % r);
+    const cplx* src = in + (long long)b * s_in;
+    cplx acc = make_double2(0.0, 0.0);
+    for (int u = 0; u < nu; ++u)
+        for (int v = 0; v < nv; ++v) {
+            const cplx w = __ldg(&wt[((x * nu + u) * ny + y) * nv + v]);
+            if (w.x == 0.0 && w.y == 0.0) continue;
+            const cplx t = src[(((long long)u * l + li) * nv + v) * r + ri];
+            acc = cfma(w, t, acc);
+        }
+    out[(long long)b * s_out + (((long long)x * l + li) * ny + y) * r + ri] = acc;
+}
+
+// env[i,a,j] = delta_ij
+__global__ void k_env_identity(int dmpo, cplx* env, long long s_env, const int* echi, int es, const int* mask) {
+    const int b = blockIdx.y;
+    if (mask && !mask[b]) return;
+    const int chi = echi[(long long)b * es];
+    const long long n = (long long)chi * dmpo * chi;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+        const int j = (int)(e % chi);
+        const int i = (int)(e / ((long long)dmpo * chi));
+        env[(long long)b * s_env + e] = make_double2(i == j ? 1.0 : 0.0, 0.0);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Lanczos (matrix_exponential.py:33-201).  One CTA per trajectory.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int LZ_THREADS = 1024;
+constexpr int LZ_KMAX = 32;
+
+__global__ void __launch_bounds__(LZ_THREADS) k_lanczos_init(int dphys, const cplx* __restrict__ x, long long s_x, cplx* basis, long long s_basis,
+                                                               double* nrm, int* active, int* kdone, const int* el, int esl, const int* er,
+                                                               int esr, const int* mask) {
+    __shared__ double red[32];
+    const int b = blockIdx.x;
+    if (mask && !mask[b]) { active[b] = 0; kdone[b] = -1; return; }
+    const long long n = (long long)dphys * el[(long long)b * esl] * er[(long long)b * esr];
+    const cplx* xb = x + (long long)b * s_x;
+    cplx* v0 = basis + (long long)b * s_basis;
+    double s[1] = {0.0};
+    for (long long e = threadIdx.x; e < n; e += blockDim.x) s[0] += cabs2(xb[e]);
+    block_sum<1>(s, red);
+    const double nr = sqrt(s[0]);
+    if (threadIdx.x == 0) { nrm[b] = nr; active[b] = nr > 0.0 ? 1 : 0; kdone[b] = 0; }
+    if (nr == 0.0) return;                                   // zero vector: returned untouched (:67-69)
+    const double inv = 1.0 / nr;
+    for (long long e = threadIdx.x; e < n; e += blockDim.x) { const cplx t = xb[e]; v0[e] = make_double2(t.x * inv, t.y * inv); }
+}
+
+// Symmetric tridiagonal eigen-decomposition by implicit QL (one warp; lane r owns row r of Z).
+// d[0..k) diagonal -> eigenvalues, e[0..k-1) off-diagonal (destroyed), z row-major [k][LZ_KMAX].
+__device__ void tridiag_eig_warp(int k, double* d, double* e, double* z, int lane) {
+    for (int i = lane; i < k * LZ_KMAX; i += 32) z[i] = 0.0;
+    __syncwarp();
+    if (lane < k) z[lane * LZ_KMAX + lane] = 1.0;
+    if (lane == 0) e[k - 1] = 0.0;
+    __syncwarp();
+    const double eps = 2.220446049250313e-16;
+    for (int l = 0; l < k; ++l) {
+        for (int iter = 0; iter < 60; ++iter) {
+            int m = l;
+            for (; m < k - 1; ++m) {
+                const double dd = fabs(d[m]) + fabs(d[m + 1]);
+                if (fabs(e[m]) <= eps * dd) break;
+            }
+            if (m == l) break;
+            double g = (d[l + 1] - d[l]) / (2.0 * e[l]);
+            double r = hypot(g, 1.0);
+            g = d[m] - d[l] + e[l] / (g + copysign(r, g));
+            double s = 1.0, c = 1.0, p = 0.0;
+            int i = m - 1;
+            bool underflow = false;
+            for (; i >= l; --i) {
+                double f = s * e[i];
+                const double bb = c * e[i];
+                r = hypot(f, g);
+                __syncwarp();
+                if (lane == 0) e[i + 1] = r;
+                if (r == 0.0) {
+                    if (lane == 0) { d[i + 1] -= p; e[m] = 0.0; }
+                    underflow = true;
+                    break;
+                }
+                s = f / r; c = g / r;
+                g = d[i + 1] - p;
+                r = (d[i] - g) * s + 2.0 * c * bb;
+                p = s * r;
+                __syncwarp();
+                if (lane == 0) d[i + 1] = g + p;
+                g = c * r - bb;
+                if (lane < k) {
+                    const double f2 = z[lane * LZ_KMAX + i + 1], zi = z[lane * LZ_KMAX + i];
+                    z[lane * LZ_KMAX + i + 1] = s * zi + c * f2;
+                    z[lane * LZ_KMAX + i] = c * zi - s * f2;
+                }
+                __syncwarp();
+            }
+            __syncwarp();
+            if (underflow) continue;
+            if (lane == 0) { d[l] -= p; e[l] = g; e[m] = 0.0; }
+            __syncwarp();
+        }
+    }
+    __syncwarp();
+}
+
+__global__ void __launch_bounds__(LZ_THREADS) k_lanczos_step(int j, int kmax, double dt, double tol, int dphys, cplx* basis, long long s_basis,
+                                                               long long s_vec, double* alpha, double* beta, const double* nrm, int* active,
+                                                               int* kdone, cplx* coef, int* n_active, const int* el, int esl, const int* er,
+                                                               int esr) {
+    __shared__ double red[64];
+    __shared__ double sd[LZ_KMAX], se[LZ_KMAX], sz[LZ_KMAX * LZ_KMAX];
+    __shared__ int s_finish, s_k;
+    const int b = blockIdx.x;
+    if (!active[b]) return;
+    const long long n = (long long)dphys * el[(long long)b * esl] * er[(long long)b * esr];
+    cplx* vj = basis + (long long)b * s_basis + (long long)j * s_vec;
+    cplx* w = vj + s_vec;
+    const cplx* vp = vj - s_vec;
+    double* al = alpha + (long long)b * LZ_KMAX;
+    double* be = beta + (long long)b * LZ_KMAX;
+    // alpha_j = Re <v_j, w>   (:117)
+    double s[1] = {0.0};
+    for (long long e = threadIdx.x; e < n; e += blockDim.x) { const cplx a = vj[e], c = w[e]; s[0] += a.x * c.x + a.y * c.y; }
+    block_sum<1>(s, red);
+    const double aj = s[0];
+    const double bprev = j > 0 ? be[j - 1] : 0.0;
+    // w -= alpha_j v_j + beta_{j-1} v_{j-1}; beta_j = |w|   (:121-128)
+    double t[1] = {0.0};
+    for (long long e = threadIdx.x; e < n; e += blockDim.x) {
+        cplx c = w[e];
+        const cplx a = vj[e];
+        c.x -= aj * a.x; c.y -= aj * a.y;
+        if (j > 0) { const cplx p = vp[e]; c.x -= bprev * p.x; c.y -= bprev * p.y; }
+        w[e] = c;
+        t[0] += cabs2(c);
+    }
+    block_sum<1>(t, red);
+    const double bj = sqrt(t[0]);
+    const bool last = (j == kmax - 1);
+    const double eps_cut = 100.0 * (double)n * 2.220446049250313e-16;
+    if (threadIdx.x < 32) {
+        const int lane = threadIdx.x;
+        if (lane == 0) { al[j] = aj; if (!last) be[j] = bj; }
+        __syncwarp();
+        int finish = 0, k = j + 1;
+        const bool breakdown = (!last) && (bj < eps_cut);
+        if (breakdown || j >= 1 || last) {
+            if (k == 1) {
+                if (lane == 0) { sd[0] = aj; sz[0] = 1.0; }
+            } else {
+                for (int i = lane; i < k; i += 32) { sd[i] = al[i]; se[i] = (i < k - 1) ? be[i] : 0.0; }
+                __syncwarp();
+                tridiag_eig_warp(k, sd, se, sz, lane);
+            }
+            __syncwarp();
+            if (breakdown || last) finish = 1;
+            else {
+                // err = beta_j * | sum_m z[k-1,m] exp(-i dt lam_m) z[0,m] |   (:154-160)
+                double pr = 0.0, pi = 0.0;
+                for (int m = 0; m < k; ++m) {
+                    double sn, cs; sincos(-dt * sd[m], &sn, &cs);
+                    const double ww = sz[(k - 1) * LZ_KMAX + m] * sz[m];
+                    pr += ww * cs; pi += ww * sn;
+                }
+                if (bj * sqrt(pr * pr + pi * pi) < tol) finish = 1;
+            }
+            if (finish && lane < k) {
+                // y_i = |v| sum_m z[i,m] exp(-i dt lam_m) z[0,m]   (:162-163, :199-201)
+                double pr = 0.0, pi = 0.0;
+                for (int m = 0; m < k; ++m) {
+                    double sn, cs; sincos(-dt * sd[m], &sn, &cs);
+                    const double ww = sz[lane * LZ_KMAX + m] * sz[m];
+                    pr += ww * cs; pi += ww * sn;
+                }
+                const double nr = nrm[b];
+                coef[(long long)b * LZ_KMAX + lane] = make_double2(nr * pr, nr * pi);
+            }
+        }
+        if (lane == 0) {
+            s_finish = finish; s_k = k;
+            if (finish) { kdone[b] = k; active[b] = 0; } else atomicAdd(n_active, 1);
+        }
+    }
+    __syncthreads();
+    if (s_finish) return;
+    // v_{j+1} = w / beta_j   (:134)
+    const double inv = 1.0 / bj;
+    for (long long e = threadIdx.x; e < n; e += blockDim.x) { cplx c = w[e]; c.x *= inv; c.y *= inv; w[e] = c; }
+}
+
+__global__ void k_lanczos_combine(int dphys, const cplx* __restrict__ basis, long long s_basis, long long s_vec, const cplx* __restrict__ coef,
+                                  const int* kdone, cplx* out, long long s_out, const int* el, int esl, const int* er, int esr, const int* mask) {
+    const int b = blockIdx.y;
+    if (mask && !mask[b]) return;
+    const int k = kdone[b];
+    if (k <= 0) return;
+    const long long n = (long long)dphys * el[(long long)b * esl] * er[(long long)b * esr];
+    __shared__ cplx cf[LZ_KMAX];
+    if (threadIdx.x < k) cf[threadIdx.x] = coef[(long long)b * LZ_KMAX + threadIdx.x];
+    __syncthreads();
+    const cplx* vb = basis + (long long)b * s_basis;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+        cplx acc = make_double2(0.0, 0.0);
+        for (int i = 0; i < k; ++i) acc = cfma(cf[i], vb[(long long)i * s_vec + e], acc);
+        out[(long long)b * s_out + e] = acc;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// site-tensor utilities
+// ---------------------------------------------------------------------------------------------------------------------
+// dst(s, k, r) = src(k, (s, r))
+__global__ void k_unpack_vh(int dphys, const cplx* __restrict__ src, long long s_src, cplx* dst, long long s_dst, const int* ek, int esk,
+                            const int* er, int esr, const int* mask) {
+    const int b = blockIdx.y;
+    if (mask && !mask[b]) return;
+    const int k = ek[(long long)b * esk], r = er[(long long)b * esr];
+    const long long n = (long long)dphys * k * r;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+        const int ri = (int)(e % r);
+        const long long q = e / r;
+        const int ki = (int)(q % k), s = (int)(q / k);
+        dst[(long long)b * s_dst + e] = src[(long long)b * s_src + ((long long)ki * dphys + s) * r + ri];
+    }
+}
+
+__global__ void k_copy_packed(int mult, const cplx* __restrict__ src, long long s_src, cplx* dst, long long s_dst, const int* e0, int es0,
+                              const int* e1, int es1, const int* mask) {
+    const int b = blockIdx.y;
+    if (mask && !mask[b]) return;
+    const long long n = (long long)mult * e0[(long long)b * es0] * (e1 ? e1[(long long)b * es1] : 1);
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x)
+        dst[(long long)b * s_dst + e] = src[(long long)b * s_src + e];
+}
+
+// A_s <- sum_t op[s,t] A_t   (dphys <= 4)
+__global__ void k_apply_local_op(int dphys, const cplx* __restrict__ op, long long s_op, cplx* a, long long s_a, const int* el, int esl,
+                                 const int* er, int esr, const int* mask, const int* sel, int sel_value) {
+    const int b = blockIdx.y;
+    if (mask && !mask[b]) return;
+    if (sel && sel[b] != sel_value) return;
+    const long long lr = (long long)el[(long long)b * esl] * er[(long long)b * esr];
+    const cplx* o = op + (long long)b * s_op;
+    cplx* ab = a + (long long)b * s_a;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < lr; e += (long long)gridDim.x * blockDim.x) {
+        cplx v[4], res[4];
+        for (int t = 0; t < dphys; ++t) v[t] = ab[(long long)t * lr + e];
+        for (int s = 0; s < dphys; ++s) {
+            cplx acc = make_double2(0.0, 0.0);
+            for (int t = 0; t < dphys; ++t) acc = cfma(o[s * dphys + t], v[t], acc);
+            res[s] = acc;
+        }
+        for (int s = 0; s < dphys; ++s) ab[(long long)s * lr + e] = res[s];
+    }
+}
+
+__global__ void __launch_bounds__(1024) k_norm2(int dphys, const cplx* __restrict__ a, long long s_a, double* out, const int* el, int esl,
+                                                 const int* er, int esr, const int* mask) {
+    __shared__ double red[32];
+    const int b = blockIdx.x;
+    if (mask && !mask[b]) return;
+    const long long n = (long long)dphys * el[(long long)b * esl] * er[(long long)b * esr];
+    const cplx* ab = a + (long long)b * s_a;
+    double s[1] = {0.0};
+    for (long long e = threadIdx.x; e < n; e += blockDim.x) s[0] += cabs2(ab[e]);
+    block_sum<1>(s, red);
+    if (threadIdx.x == 0) out[b] = s[0];
+}
+
+__global__ void k_scale(int dphys, const double* scale, cplx* a, long long s_a, const int* el, int esl, const int* er, int esr, const int* mask) {
+    const int b = blockIdx.y;
+    if (mask && !mask[b]) return;
+    const long long n = (long long)dphys * el[(long long)b * esl] * er[(long long)b * esr];
+    const double f = scale[b];
+    cplx* ab = a + (long long)b * s_a;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+        cplx v = ab[e]; v.x *= f; v.y *= f; ab[e] = v;
+    }
+}
+
+// g[b][o][p] = sum_(l,r) conj(a_o[l,r]) x_p[l,r]; one CTA per trajectory, dphys <= 4.
+__global__ void __launch_bounds__(512) k_local_rdm(int dphys, const cplx* __restrict__ a, long long s_a, const cplx* __restrict__ x, long long s_x,
+                                                    cplx* g, const int* el, int esl, const int* er, int esr, const int* mask) {
+    __shared__ double red[32 * 32];
+    const int b = blockIdx.x;
+    if (mask && !mask[b]) return;
+    const long long lr = (long long)el[(long long)b * esl] * er[(long long)b * esr];
+    const cplx* ab = a + (long long)b * s_a;
+    const cplx* xb = x + (long long)b * s_x;
+    double acc[32];
+#pragma unroll
+    for (int q = 0; q < 32; ++q) acc[q] = 0.0;
+    for (long long e = threadIdx.x; e < lr; e += blockDim.x) {
+        cplx av[4], xv[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) if (t < dphys) { av[t] = ab[(long long)t * lr + e]; xv[t] = xb[(long long)t * lr + e]; }
+#pragma unroll
+        for (int o = 0; o < 4; ++o)
+#pragma unroll
+            for (int p = 0; p < 4; ++p)
+                if (o < dphys && p < dphys) {
+                    acc[(o * 4 + p) * 2] += av[o].x * xv[p].x + av[o].y * xv[p].y;
+                    acc[(o * 4 + p) * 2 + 1] += av[o].x * xv[p].y - av[o].y * xv[p].x;
+                }
+    }
+    block_sum<32>(acc, red);
+    if (threadIdx.x < dphys * dphys) {
+        const int o = threadIdx.x / dphys, p = threadIdx.x % dphys;
+        g[(long long)b * dphys * dphys + threadIdx.x] = make_double2(acc[(o * 4 + p) * 2], acc[(o * 4 + p) * 2 + 1]);
+    }
+}

@@ -1,0 +1,354 @@
+// Batched truncated SVD by one-sided (Hestenes) Jacobi -- replaces scipy.linalg.svd (zgesdd) + linalg.truncate at
+// core/linalg/svd.py:51-104, core/linalg/svd_utils.py:22-104, core/methods/decompositions.py:105-185.
+//
+// Why Jacobi: the reference's gauge shifts truncate at a discarded weight of 1e-12, i.e. they resolve singular values
+// down to ~1e-6 relative; one-sided Jacobi delivers high RELATIVE accuracy for every singular value, a Gram-matrix
+// eigen-solve does not (DESIGN.md "SVD").  The vectors being orthogonalised are the contiguous rows of W (the smaller
+// side of the matrix), so every access is a coalesced 16-byte stream; a CTA owns one block pair of one trajectory,
+// keeps the 2*block_rows rows of W and of the accumulated rotation Q in shared memory and sweeps all row pairs with
+// one warp per pair.  A full cyclic sweep = (nblocks-1) rounds of a round-robin over block pairs.
+#include "yb_common.cuh"
+#include <math.h>
+
+// meta[b][8]: 0 k (rows of W), 1 len (row length), 2 orient (0: W = M, 1: W = M^H), 3 rows(M), 4 cols(M), 5 done, 6 sweeps, 7 spare
+constexpr int META = 8;
+
+__global__ void k_svd_prepare(int mode, int dphys, const cplx* __restrict__ src, long long s_src, cplx* w, long long s_w, cplx* q, long long s_q,
+                              int* meta, int* rot_count, const int* el, int esl, const int* er, int esr, const int* mask) {
+    const int b = blockIdx.y;
+    if (mask && !mask[b]) { if (blockIdx.x == 0 && threadIdx.x == 0) meta[b * META + 5] = 1; return; }
+    const int l = el[(long long)b * esl], r = er[(long long)b * esr];
+    int rows, cols;
+    if (mode == 0) { rows = dphys * l; cols = dphys * r; }
+    else if (mode == 1) { rows = dphys * l; cols = r; }
+    else { rows = l; cols = dphys * r; }
+    const int orient = rows <= cols ? 0 : 1;
+    const int k = orient ? cols : rows, len = orient ? rows : cols;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        int* m = meta + b * META;
+        m[0] = k; m[1] = len; m[2] = orient; m[3] = rows; m[4] = cols; m[5] = 0; m[6] = 0; m[7] = 0;
+        rot_count[b] = 0;
+    }
+    const cplx* sb = src + (long long)b * s_src;
+    cplx* wb = w + (long long)b * s_w;
+    cplx* qb = q + (long long)b * s_q;
+    const long long nw = (long long)k * len;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < nw; e += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(e / len), jj = (int)(e % len);
+        const int row = orient ? jj : i, col = orient ? i : jj;           // element M[row][col]
+        long long idx;
+        if (mode == 0) {            // theta[(s*d+s'), l, r]; row = s*l + li, col = s'*r + ri
+            const int s = row / l, li = row % l, sp = col / r, ri = col % r;
+            idx = (((long long)(s * dphys + sp)) * l + li) * r + ri;
+        } else if (mode == 1) {     // (s l) x r contiguous
+            idx = (long long)row * r + col;
+        } else {                    // l x (s r): src[(s*l + li)*r + ri]
+            const int s = col / r, ri = col % r;
+            idx = ((long long)s * l + row) * r + ri;
+        }
+        cplx v = sb[idx];
+        if (orient) v.y = -v.y;
+        wb[e] = v;
+    }
+    const long long nq = (long long)k * k;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < nq; e += (long long)gridDim.x * blockDim.x)
+        qb[e] = make_double2((e / k) == (e % k) ? 1.0 : 0.0, 0.0);
+}
+
+// One pair rotation by a full warp.  wi/wj: rows of W (length len) in shared memory, qi/qj: rows of Q (length k).
+__device__ __forceinline__ int jacobi_pair(cplx* wi, cplx* wj, int len, cplx* qi, cplx* qj, int k, double tol2, int lane) {
+    double a = 0.0, bb = 0.0, cr = 0.0, ci = 0.0;
+    for (int e = lane; e < len; e += 32) {
+        const cplx x = wi[e], y = wj[e];
+        a += x.x * x.x + x.y * x.y;
+        bb += y.x * y.x + y.y * y.y;
+        cr += x.x * y.x + x.y * y.y;        // conj(x) * y
+        ci += x.x * y.y - x.y * y.x;
+    }
+    a = warp_sum(a); bb = warp_sum(bb); cr = warp_sum(cr); ci = warp_sum(ci);
+    const double c2 = cr * cr + ci * ci;
+    if (!(c2 > tol2 * a * bb) || c2 == 0.0) return 0;
+    const double absc = sqrt(c2);
+    const double zeta = (bb - a) / (2.0 * absc);
+    const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+    const double cs = 1.0 / sqrt(1.0 + t * t), sn = cs * t;
+    // wj~ = conj(e) wj with e = c/|c|;  wi' = cs wi - sn wj~ ;  wj' = sn wi + cs wj~
+    const double er = cr / absc, ei = -ci / absc;     // conj(e)
+    for (int e = lane; e < len; e += 32) {
+        const cplx x = wi[e], y = wj[e];
+        const double yr = er * y.x - ei * y.y, yi = er * y.y + ei * y.x;
+        wi[e] = make_double2(cs * x.x - sn * yr, cs * x.y - sn * yi);
+        wj[e] = make_double2(sn * x.x + cs * yr, sn * x.y + cs * yi);
+    }
+    for (int e = lane; e < k; e += 32) {
+        const cplx x = qi[e], y = qj[e];
+        const double yr = er * y.x - ei * y.y, yi = er * y.y + ei * y.x;
+        qi[e] = make_double2(cs * x.x - sn * yr, cs * x.y - sn * yi);
+        qj[e] = make_double2(sn * x.x + cs * yr, sn * x.y + cs * yi);
+    }
+    return 1;
+}
+
+// grid = (nblocks/2, B); block = 512 threads; dynamic smem = 2*block_rows*(max_len + max_k) complex.
+__global__ void __launch_bounds__(512) k_svd_round(int block_rows, int nblocks, int round, int full_panel, int inner_sweeps, cplx* w, long long s_w,
+                                                    cplx* q, long long s_q, int* meta, int* rot_count, int max_len, int max_k, const int* mask) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ int s_rot;
+    const int b = blockIdx.y;
+    if (mask && !mask[b]) return;
+    const int* m = meta + b * META;
+    if (m[5]) return;
+    const int k = m[0], len = m[1];
+    // round-robin (circle method) over nblocks players
+    const int p = blockIdx.x, N1 = nblocks - 1;
+    int bi, bj;
+    if (p == 0) { bi = N1; bj = round % N1; }
+    else { bi = (round + p) % N1; bj = ((round - p) % N1 + N1) % N1; }
+    if (bi > bj) { const int t = bi; bi = bj; bj = t; }
+    const int i0 = bi * block_rows, j0 = bj * block_rows;
+    const int ni = max(0, min(block_rows, k - i0)), nj = max(0, min(block_rows, k - j0));
+    if (ni == 0 || (nj == 0 && !full_panel)) return;
+    const int nrows = ni + nj;
+    cplx* Wp = reinterpret_cast<cplx*>(smem_raw);
+    cplx* Qp = Wp + (size_t)2 * block_rows * max_len;
+    cplx* wb = w + (long long)b * s_w;
+    cplx* qb = q + (long long)b * s_q;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    for (int t = 0; t < nrows; ++t) {
+        const int gr = t < ni ? i0 + t : j0 + (t - ni);
+        for (int e = tid; e < len; e += blockDim.x) Wp[(size_t)t * max_len + e] = wb[(long long)gr * len + e];
+        for (int e = tid; e < k; e += blockDim.x) Qp[(size_t)t * max_k + e] = qb[(long long)gr * k + e];
+    }
+    if (tid == 0) s_rot = 0;
+    __syncthreads();
+    const double tolr = fmax(10.0, sqrt((double)len)) * 2.220446049250313e-16;
+    const double tol2 = tolr * tolr;
+    int report_rot = 0;
+    for (int sweep = 0; sweep < inner_sweeps; ++sweep) {
+        int my_rot = 0;
+        if (full_panel) {
+            // all pairs among nrows rows: circle method over ne = even(nrows) players
+            const int ne = (nrows + 1) & ~1, n1 = ne - 1;
+            for (int rr = 0; rr < n1; ++rr) {
+                for (int pp = warp; pp < ne / 2; pp += nwarps) {
+                    int x, y;
+                    if (pp == 0) { x = n1; y = rr % n1; } else { x = (rr + pp) % n1; y = ((rr - pp) % n1 + n1) % n1; }
+                    if (x < nrows && y < nrows)
+                        my_rot += jacobi_pair(Wp + (size_t)min(x, y) * max_len, Wp + (size_t)max(x, y) * max_len, len,
+                                              Qp + (size_t)min(x, y) * max_k, Qp + (size_t)max(x, y) * max_k, k, tol2, lane);
+                }
+                __syncthreads();
+            }
+        } else {
+            const int mm = max(ni, nj);
+            for (int qq = 0; qq < mm; ++qq) {
+                for (int t = warp; t < mm; t += nwarps) {
+                    const int x = t, y = (t + qq) % mm;
+                    if (x < ni && y < nj)
+                        my_rot += jacobi_pair(Wp + (size_t)x * max_len, Wp + (size_t)(ni + y) * max_len, len, Qp + (size_t)x * max_k,
+                                              Qp + (size_t)(ni + y) * max_k, k, tol2, lane);
+                }
+                __syncthreads();
+            }
+        }
+        if (lane == 0 && my_rot) atomicAdd(&s_rot, my_rot);
+        __syncthreads();
+        report_rot = s_rot;          // rotations of the most recent sweep (0 => this panel is converged)
+        __syncthreads();
+        if (tid == 0) s_rot = 0;
+        __syncthreads();
+        if (report_rot == 0) break;
+    }
+    for (int t = 0; t < nrows; ++t) {
+        const int gr = t < ni ? i0 + t : j0 + (t - ni);
+        for (int e = tid; e < len; e += blockDim.x) wb[(long long)gr * len + e] = Wp[(size_t)t * max_len + e];
+        for (int e = tid; e < k; e += blockDim.x) qb[(long long)gr * k + e] = Qp[(size_t)t * max_k + e];
+    }
+    if (tid == 0 && report_rot) atomicAdd(&rot_count[b], report_rot);
+}
+
+__global__ void k_svd_check(int nbatch, int* meta, int* rot_count, int* n_pending, const int* mask) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nbatch) return;
+    if (mask && !mask[b]) return;
+    int* m = meta + b * META;
+    if (m[5]) return;
+    m[6] += 1;
+    if (rot_count[b] == 0) m[5] = 1; else atomicAdd(n_pending, 1);
+    rot_count[b] = 0;
+}
+
+// truncate() of core/linalg/svd_utils.py:22-104 on a descending spectrum (serial: the discarded-weight mode accumulates
+// from the smallest value upward, and that summation order is part of the keep decision).
+__device__ int truncate_keep(const double* s, int n, int mode, double threshold, int max_bond, int min_keep) {
+    if (n == 0) return 0;
+    int keep = n;
+    if (mode == 2) {                     // hard_cutoff
+        keep = 0;
+        for (int i = 0; i < n; ++i) keep += s[i] > threshold;
+    } else if (mode == 1) {              // relative
+        keep = 0;
+        if (s[0] > 0.0) for (int i = 0; i < n; ++i) keep += (s[i] / s[0]) >= threshold;
+    } else if (mode == 0) {              // discarded_weight
+        double acc = 0.0;
+        for (int idx = 0; idx < n; ++idx) {
+            const double v = s[n - 1 - idx];
+            acc += v * v;
+            if (acc >= threshold) { keep = max(n - idx, min_keep); break; }
+        }
+    } else {                             // relative_discarded_weight
+        if (s[0] <= 0.0) keep = 0;
+        else {
+            double total = 0.0;
+            for (int i = 0; i < n; ++i) { const double x = s[i] / s[0]; total += x * x; }
+            double acc = 0.0;
+            for (int idx = 0; idx < n; ++idx) {
+                const double x = s[n - 1 - idx] / s[0];
+                const double cand = acc + x * x;
+                if (cand / total <= threshold) { acc = cand; keep = n - idx - 1; } else break;
+            }
+        }
+    }
+    if (max_bond > 0) keep = min(keep, max_bond);
+    keep = max(keep, min_keep);
+    return min(keep, n);
+}
+
+constexpr int SVD_KMAX = 1024;
+
+// One CTA per trajectory.
+__global__ void __launch_bounds__(512) k_svd_finalize(int trunc_mode, double threshold, int max_bond, int min_keep, int dist, const cplx* __restrict__ w,
+                                                       long long s_w, const cplx* __restrict__ q, long long s_q, const int* meta, double* sval,
+                                                       long long s_s, int* keep_out, int keep_stride, cplx* uout, long long s_u, cplx* vout,
+                                                       long long s_v, int* status, const int* mask) {
+    __shared__ double sig[SVD_KMAX];
+    __shared__ double ssort[SVD_KMAX];
+    __shared__ int perm[SVD_KMAX];
+    __shared__ int s_keep, s_ndef;
+    __shared__ double red[32];
+    const int b = blockIdx.x;
+    if (mask && !mask[b]) return;
+    const int* m = meta + b * META;
+    const int k = m[0], len = m[1], orient = m[2], rows = m[3], cols = m[4];
+    const cplx* wb = w + (long long)b * s_w;
+    const cplx* qb = q + (long long)b * s_q;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    for (int i = warp; i < k; i += nwarps) {
+        double s = 0.0;
+        for (int e = lane; e < len; e += 32) s += cabs2(wb[(long long)i * len + e]);
+        s = warp_sum(s);
+        if (lane == 0) sig[i] = sqrt(s);
+    }
+    __syncthreads();
+    for (int i = tid; i < k; i += blockDim.x) {
+        const double si = sig[i];
+        int rank = 0;
+        for (int j = 0; j < k; ++j) { const double sj = sig[j]; rank += (sj > si) || (sj == si && j < i); }
+        perm[rank] = i; ssort[rank] = si;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        s_keep = truncate_keep(ssort, k, trunc_mode, threshold, max_bond, min_keep);
+        bool bad = false;
+        for (int i = 0; i < k; ++i) bad |= !isfinite(ssort[i]);
+        if (bad || !m[5]) atomicOr(&status[b], bad ? 2 : 1);       // 2: non-finite, 1: Jacobi not converged
+        int nd = 0;
+        const double tiny = ssort[0] * 1e-290;
+        for (int i = 0; i < s_keep; ++i) nd += !(ssort[i] > tiny);
+        s_ndef = nd;
+        keep_out[(long long)b * keep_stride] = s_keep;
+    }
+    __syncthreads();
+    const int keep = s_keep;
+    for (int i = tid; i < k; i += blockDim.x) sval[(long long)b * s_s + i] = ssort[i];
+    cplx* ub = uout + (long long)b * s_u;    // rows x keep
+    cplx* vb = vout + (long long)b * s_v;    // keep x cols
+    const double tiny = ssort[0] * 1e-290;
+    // Q-side factor (exactly unitary rows of Q) and W-side factor (rows of W / sigma)
+    if (orient == 0) {
+        // U[:, c] = conj(Q[perm c, :]) * f ;  Vh[c, :] = W[perm c, :] * (g / sigma)
+        for (long long e = tid; e < (long long)rows * keep; e += blockDim.x) {
+            const int j = (int)(e / keep), c = (int)(e % keep);
+            const double s = ssort[c];
+            const double f = dist == 0 ? s : (dist == 1 ? 1.0 : sqrt(s));
+            const cplx v = qb[(long long)perm[c] * k + j];
+            ub[e] = make_double2(v.x * f, -v.y * f);
+        }
+        for (long long e = tid; e < (long long)keep * cols; e += blockDim.x) {
+            const int c = (int)(e / cols), j = (int)(e % cols);
+            const double s = ssort[c];
+            double sc;
+            if (dist == 1) sc = 1.0; else if (!(s > tiny)) sc = 0.0; else sc = (dist == 0 ? 1.0 / s : 1.0 / sqrt(s));
+            const cplx v = wb[(long long)perm[c] * len + j];
+            vb[e] = make_double2(v.x * sc, v.y * sc);
+        }
+    } else {
+        // U[:, c] = conj(W[perm c, :]) * (f / sigma) ;  Vh[c, :] = Q[perm c, :] * g
+        for (long long e = tid; e < (long long)rows * keep; e += blockDim.x) {
+            const int j = (int)(e / keep), c = (int)(e % keep);
+            const double s = ssort[c];
+            double sc;
+            if (dist == 0) sc = 1.0; else if (!(s > tiny)) sc = 0.0; else sc = (dist == 1 ? 1.0 / s : 1.0 / sqrt(s));
+            const cplx v = wb[(long long)perm[c] * len + j];
+            ub[e] = make_double2(v.x * sc, -v.y * sc);
+        }
+        for (long long e = tid; e < (long long)keep * cols; e += blockDim.x) {
+            const int c = (int)(e / cols), j = (int)(e % cols);
+            const double s = ssort[c];
+            const double g = dist == 0 ? 1.0 : (dist == 1 ? s : sqrt(s));
+            const cplx v = qb[(long long)perm[c] * k + j];
+            vb[e] = make_double2(v.x * g, v.y * g);
+        }
+    }
+    if (s_ndef == 0) return;
+    // Rank-deficient kept vectors (sigma == 0, only reachable through min_keep): LAPACK returns an arbitrary orthonormal
+    // completion; we build one by Gram-Schmidt of unit vectors against the vectors already present.  Only needed where
+    // the W-side factor must stay an isometry, i.e. when it does not carry S.
+    const bool wside_is_v = (orient == 0);
+    if ((wside_is_v && dist == 1) || (!wside_is_v && dist == 0)) return;    // W-side carries S: zero vector is exact
+    __syncthreads();
+    cplx* base = wside_is_v ? vb : ub;
+    const long long vstride = wside_is_v ? cols : 1;      // distance between vectors
+    const long long estride = wside_is_v ? 1 : keep;      // distance between elements of one vector
+    const int vlen = wside_is_v ? cols : rows;
+    int next_unit = 0;
+    for (int c = 0; c < keep; ++c) {
+        if (ssort[c] > tiny) continue;
+        cplx* vc = base + (long long)c * vstride;
+        for (int attempt = 0; attempt < vlen; ++attempt, ++next_unit) {
+            const int u = next_unit % vlen;
+            __syncthreads();
+            for (int e = tid; e < vlen; e += blockDim.x) vc[(long long)e * estride] = make_double2(e == u ? 1.0 : 0.0, 0.0);
+            __syncthreads();
+            for (int pass = 0; pass < 2; ++pass)
+                for (int o = 0; o < keep; ++o) {
+                    if (o == c || (o > c && !(ssort[o] > tiny))) continue;
+                    const cplx* vo = base + (long long)o * vstride;
+                    double pr[2] = {0.0, 0.0};
+                    for (int e = tid; e < vlen; e += blockDim.x) {
+                        const cplx x = vo[(long long)e * estride], y = vc[(long long)e * estride];
+                        pr[0] += x.x * y.x + x.y * y.y; pr[1] += x.x * y.y - x.y * y.x;
+                    }
+                    double p0[1] = {pr[0]}, p1[1] = {pr[1]};
+                    block_sum<1>(p0, red); block_sum<1>(p1, red);
+                    for (int e = tid; e < vlen; e += blockDim.x) {
+                        const cplx x = vo[(long long)e * estride];
+                        cplx y = vc[(long long)e * estride];
+                        y.x -= p0[0] * x.x - p1[0] * x.y; y.y -= p0[0] * x.y + p1[0] * x.x;
+                        vc[(long long)e * estride] = y;
+                    }
+                    __syncthreads();
+                }
+            double nn[1] = {0.0};
+            for (int e = tid; e < vlen; e += blockDim.x) nn[0] += cabs2(vc[(long long)e * estride]);
+            block_sum<1>(nn, red);
+            if (nn[0] > 0.25) {
+                const double inv = 1.0 / sqrt(nn[0]);
+                for (int e = tid; e < vlen; e += blockDim.x) { cplx y = vc[(long long)e * estride]; y.x *= inv; y.y *= inv; vc[(long long)e * estride] = y; }
+                ++next_unit;
+                break;
+            }
+        }
+        __syncthreads();
+    }
+}

@@ -1,0 +1,201 @@
+"""ctypes binding of libyaqs_b200.so (include/yaqs_b200.h) -- torch tensors only lend ``data_ptr()``.
+
+There is NO CPU fallback: constructing :class:`CudaKernels` without the built extension or without a CUDA device
+raises.  (A numpy twin of these entry points exists under ``oracle/np_kernels.py``; it is test infrastructure and is
+never imported from this package.)
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from dataclasses import dataclass
+
+import torch
+
+_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libyaqs_b200.so")
+
+# op codes of yb_gemm (csrc/yb_common.cuh)
+OP_RCONTRACT, OP_LCONTRACT, OP_ENVR3, OP_ENVL1, OP_ENVL3, OP_MERGE, OP_ABSORB_R, OP_ABSORB_L = range(8)
+# yb_svd_prepare modes
+SVD_THETA, SVD_ROWS, SVD_COLS = 0, 1, 2
+# truncation modes (core/linalg/svd_utils.py) and singular-value distribution (decompositions.py)
+TRUNC_MODES = {"discarded_weight": 0, "relative": 1, "hard_cutoff": 2, "relative_discarded_weight": 3}
+DIST = {"left": 0, "right": 1, "sqrt": 2}
+LANCZOS_PITCH = 32          # alpha/beta/coef rows are 32 wide (LZ_KMAX in csrc/yb_ops.cu)
+SVD_META = 8
+
+
+class YbExtent(ctypes.Structure):
+    _fields_ = [("ptr", ctypes.c_void_p), ("stride", ctypes.c_int32)]
+
+
+@dataclass
+class Ext:
+    """Per-trajectory int32 extent: value of trajectory b is ``tensor.view(-1)[offset + b * stride]``."""
+    tensor: torch.Tensor
+    offset: int
+    stride: int
+
+    def values(self):
+        flat = self.tensor.view(-1)
+        n = (flat.numel() - self.offset + self.stride - 1) // self.stride
+        return flat[self.offset::self.stride][:n]
+
+
+@dataclass
+class Buf:
+    """Per-trajectory complex128 operand: trajectory b starts at ``tensor.view(-1)[offset + b * stride]``."""
+    tensor: torch.Tensor
+    offset: int
+    stride: int
+
+    def at(self, extra: int) -> "Buf":
+        return Buf(self.tensor, self.offset + extra, self.stride)
+
+
+class KernelError(RuntimeError):
+    pass
+
+
+def load_library() -> ctypes.CDLL:
+    if not os.path.exists(_LIB_PATH):
+        raise KernelError(f"{_LIB_PATH} is missing: build it with `python -m yaqs_b200.build` (there is no CPU fallback)")
+    lib = ctypes.CDLL(_LIB_PATH)
+    lib.yb_last_error.restype = ctypes.c_char_p
+    lib.yb_launch_count.restype = ctypes.c_int64
+    return lib
+
+
+EXPORTED_SYMBOLS = [
+    "yb_last_error", "yb_version", "yb_launch_count", "yb_gemm", "yb_wapply", "yb_env_identity", "yb_lanczos_init",
+    "yb_lanczos_step", "yb_lanczos_combine", "yb_svd_prepare", "yb_svd_round", "yb_svd_check", "yb_svd_finalize",
+    "yb_unpack_vh", "yb_copy_packed", "yb_apply_local_op", "yb_norm2", "yb_scale", "yb_local_rdm",
+]
+
+
+class CudaKernels:
+    """The product backend: every method enqueues one kernel of libyaqs_b200.so on torch's current stream."""
+
+    name = "cuda"
+
+    def __init__(self, device: torch.device | str | None = None):
+        if not torch.cuda.is_available():
+            raise KernelError("yaqs_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.lib = load_library()
+        self.device = torch.device(device if device is not None else "cuda:0")
+        if self.device.type != "cuda":
+            raise KernelError("yaqs_b200 kernels run on CUDA devices only")
+
+    # -- helpers ------------------------------------------------------------------------------------------------------
+    def _stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    @staticmethod
+    def _cptr(buf: Buf | None):
+        if buf is None:
+            return ctypes.c_void_p(0)
+        return ctypes.c_void_p(buf.tensor.data_ptr() + 16 * buf.offset)
+
+    @staticmethod
+    def _ptr(t: torch.Tensor | None, offset_bytes: int = 0):
+        if t is None:
+            return ctypes.c_void_p(0)
+        return ctypes.c_void_p(t.data_ptr() + offset_bytes)
+
+    @staticmethod
+    def _ext(e: Ext | None):
+        if e is None:
+            return YbExtent(ctypes.c_void_p(0), 0)
+        return YbExtent(ctypes.c_void_p(e.tensor.data_ptr() + 4 * e.offset), e.stride)
+
+    def _check(self, rc: int):
+        if rc != 0:
+            raise KernelError(self.lib.yb_last_error().decode())
+
+    def launch_count(self, reset: bool = False) -> int:
+        return int(self.lib.yb_launch_count(1 if reset else 0))
+
+    def sync_int(self, t: torch.Tensor) -> int:
+        """Read a device int (blocks the host until the stream reaches it)."""
+        return int(t.item())
+
+    # -- contractions -------------------------------------------------------------------------------------------------
+    def gemm(self, op, nbatch, ngroups, mask, e0, e1, e2, dphys, d_left, d_right, a: Buf, b: Buf, c: Buf, conj_b, max_m, max_n):
+        self._check(self.lib.yb_gemm(
+            op, nbatch, ngroups, self._ptr(mask), self._ext(e0), self._ext(e1), self._ext(e2), dphys, d_left, d_right,
+            self._cptr(a), ctypes.c_int64(a.stride), self._cptr(b), ctypes.c_int64(b.stride), self._cptr(c), ctypes.c_int64(c.stride),
+            int(conj_b), int(max_m), int(max_n), self._stream()))
+
+    def wapply(self, nbatch, mask, el, er, nx, nu, ny, nv, wt: torch.Tensor, src: Buf, dst: Buf, max_lr):
+        self._check(self.lib.yb_wapply(
+            nbatch, self._ptr(mask), self._ext(el), self._ext(er), nx, nu, ny, nv, self._ptr(wt), self._cptr(src),
+            ctypes.c_int64(src.stride), self._cptr(dst), ctypes.c_int64(dst.stride), int(max_lr), self._stream()))
+
+    def env_identity(self, nbatch, mask, echi, dmpo, env: Buf, max_chi):
+        self._check(self.lib.yb_env_identity(nbatch, self._ptr(mask), self._ext(echi), dmpo, self._cptr(env), ctypes.c_int64(env.stride),
+                                             int(max_chi), self._stream()))
+
+    # -- Lanczos ------------------------------------------------------------------------------------------------------
+    def lanczos_init(self, nbatch, mask, el, er, dphys, x: Buf, basis: Buf, stride_vec, nrm, active, kdone):
+        self._check(self.lib.yb_lanczos_init(
+            nbatch, self._ptr(mask), self._ext(el), self._ext(er), dphys, self._cptr(x), ctypes.c_int64(x.stride), self._cptr(basis),
+            ctypes.c_int64(basis.stride), ctypes.c_int64(stride_vec), self._ptr(nrm), self._ptr(active), self._ptr(kdone), self._stream()))
+
+    def lanczos_step(self, nbatch, j, kmax, dt, tol, el, er, dphys, basis: Buf, stride_vec, alpha, beta, nrm, active, kdone, coef, n_active):
+        self._check(self.lib.yb_lanczos_step(
+            nbatch, j, kmax, ctypes.c_double(dt), ctypes.c_double(tol), self._ext(el), self._ext(er), dphys, self._cptr(basis),
+            ctypes.c_int64(basis.stride), ctypes.c_int64(stride_vec), self._ptr(alpha), self._ptr(beta), self._ptr(nrm), self._ptr(active),
+            self._ptr(kdone), self._ptr(coef), self._ptr(n_active), self._stream()))
+
+    def lanczos_combine(self, nbatch, mask, el, er, dphys, basis: Buf, stride_vec, coef, kmax, kdone, out: Buf):
+        self._check(self.lib.yb_lanczos_combine(
+            nbatch, self._ptr(mask), self._ext(el), self._ext(er), dphys, self._cptr(basis), ctypes.c_int64(basis.stride),
+            ctypes.c_int64(stride_vec), self._ptr(coef), kmax, self._ptr(kdone), self._cptr(out), ctypes.c_int64(out.stride), self._stream()))
+
+    # -- SVD ----------------------------------------------------------------------------------------------------------
+    def svd_prepare(self, nbatch, mask, mode, el, er, dphys, src: Buf, w: Buf, q: Buf, meta, rot_count):
+        self._check(self.lib.yb_svd_prepare(
+            nbatch, self._ptr(mask), mode, self._ext(el), self._ext(er), dphys, self._cptr(src), ctypes.c_int64(src.stride), self._cptr(w),
+            ctypes.c_int64(w.stride), self._cptr(q), ctypes.c_int64(q.stride), self._ptr(meta), self._ptr(rot_count), self._stream()))
+
+    def svd_round(self, nbatch, mask, meta, block_rows, nblocks, rnd, full_panel, inner_sweeps, w: Buf, q: Buf, rot_count, max_len, max_k):
+        self._check(self.lib.yb_svd_round(
+            nbatch, self._ptr(mask), self._ptr(meta), block_rows, nblocks, rnd, int(full_panel), inner_sweeps, self._cptr(w),
+            ctypes.c_int64(w.stride), self._cptr(q), ctypes.c_int64(q.stride), self._ptr(rot_count), int(max_len), int(max_k), self._stream()))
+
+    def svd_check(self, nbatch, mask, meta, rot_count, n_pending):
+        self._check(self.lib.yb_svd_check(nbatch, self._ptr(mask), self._ptr(meta), self._ptr(rot_count), self._ptr(n_pending), self._stream()))
+
+    def svd_finalize(self, nbatch, mask, meta, trunc_mode, threshold, max_bond, min_keep, dist, w: Buf, q: Buf, sval, stride_s, keep: Ext,
+                     uout: Buf, vout: Buf, status, max_k):
+        self._check(self.lib.yb_svd_finalize(
+            nbatch, self._ptr(mask), self._ptr(meta), trunc_mode, ctypes.c_double(threshold), int(max_bond), int(min_keep), dist,
+            self._cptr(w), ctypes.c_int64(w.stride), self._cptr(q), ctypes.c_int64(q.stride), self._ptr(sval), ctypes.c_int64(stride_s),
+            self._ptr(keep.tensor, 4 * keep.offset), keep.stride, self._cptr(uout), ctypes.c_int64(uout.stride), self._cptr(vout),
+            ctypes.c_int64(vout.stride), self._ptr(status), int(max_k), self._stream()))
+
+    # -- site-tensor utilities ----------------------------------------------------------------------------------------
+    def unpack_vh(self, nbatch, mask, ek, er, dphys, src: Buf, dst: Buf, max_elems):
+        self._check(self.lib.yb_unpack_vh(nbatch, self._ptr(mask), self._ext(ek), self._ext(er), dphys, self._cptr(src),
+                                          ctypes.c_int64(src.stride), self._cptr(dst), ctypes.c_int64(dst.stride), int(max_elems), self._stream()))
+
+    def copy_packed(self, nbatch, mask, e0, e1, mult, src: Buf, dst: Buf, max_elems):
+        self._check(self.lib.yb_copy_packed(nbatch, self._ptr(mask), self._ext(e0), self._ext(e1), mult, self._cptr(src),
+                                            ctypes.c_int64(src.stride), self._cptr(dst), ctypes.c_int64(dst.stride), int(max_elems), self._stream()))
+
+    def apply_local_op(self, nbatch, mask, sel, sel_value, el, er, dphys, op: torch.Tensor, op_stride, a: Buf, max_lr):
+        self._check(self.lib.yb_apply_local_op(nbatch, self._ptr(mask), self._ptr(sel), int(sel_value), self._ext(el), self._ext(er), dphys,
+                                               self._ptr(op), ctypes.c_int64(op_stride), self._cptr(a), ctypes.c_int64(a.stride), int(max_lr),
+                                               self._stream()))
+
+    def norm2(self, nbatch, mask, el, er, dphys, a: Buf, out):
+        self._check(self.lib.yb_norm2(nbatch, self._ptr(mask), self._ext(el), self._ext(er), dphys, self._cptr(a), ctypes.c_int64(a.stride),
+                                      self._ptr(out), self._stream()))
+
+    def scale(self, nbatch, mask, el, er, dphys, scale, a: Buf, max_elems):
+        self._check(self.lib.yb_scale(nbatch, self._ptr(mask), self._ext(el), self._ext(er), dphys, self._ptr(scale), self._cptr(a),
+                                      ctypes.c_int64(a.stride), int(max_elems), self._stream()))
+
+    def local_rdm(self, nbatch, mask, el, er, dphys, a: Buf, x: Buf, g):
+        self._check(self.lib.yb_local_rdm(nbatch, self._ptr(mask), self._ext(el), self._ext(er), dphys, self._cptr(a), ctypes.c_int64(a.stride),
+                                          self._cptr(x), ctypes.c_int64(x.stride), self._ptr(g), self._stream()))
