@@ -1,0 +1,43 @@
+"""Shared test helpers: build a BatchedTJM from a golden case and compare its outputs with the fixture."""
+import os
+
+import numpy as np
+import torch
+
+from oracle.golden_cases import CASES, oracle_inputs
+from yaqs_b200.engine import BatchedTJM, EngineParams
+from yaqs_b200.rng import numpy_tables
+
+
+def engine_for_case(name, kernels, trajectories=None, **kw):
+    cfg = CASES[name]
+    init, mpo, noise, p, obs = oracle_inputs(cfg)
+    traj = list(range(cfg["ntraj"])) if trajectories is None else list(trajectories)
+    ep = EngineParams(dt=p.dt, n_steps=p.n_steps, order=p.order, max_bond_dim=p.max_bond_dim, svd_threshold=p.svd_threshold,
+                      trunc_mode=p.trunc_mode, krylov_tol=p.krylov_tol, tdvp_mode=p.tdvp_mode, tdvp_sweeps=p.tdvp_sweeps,
+                      sample_timesteps=p.sample_timesteps)
+    eng = BatchedTJM(kernels, cfg["L"], len(traj), mpo, ep, noise, obs, init.tensors, **kw)
+    tu, su = numpy_tables(cfg["seed"], traj, ep.n_times, ep.order)
+    dev = kernels.device
+    tu = torch.from_numpy(tu).to(dev)
+    su = torch.from_numpy(su).to(dev) if su is not None else None
+    return eng, tu, su, traj
+
+
+def check_against_golden(name, golden_dir, results, diag, log, traj, obs_tol=1e-10):
+    """Same seeds => same jump sequence, observables within obs_tol, identical diagnostics (bond dimensions)."""
+    g = np.load(os.path.join(golden_dir, f"{name}.npz"))
+    res, dg = results.cpu().numpy(), diag.cpu().numpy()
+    for row, t in enumerate(traj):
+        assert np.array_equal(dg[row], g["diagnostics"][t]), (name, t, dg[row], g["diagnostics"][t])
+        assert np.max(np.abs(res[row] - g["results"][t])) < obs_tol, (name, t, float(np.max(np.abs(res[row] - g["results"][t]))))
+        n = int(g["ncalls"][t])
+        assert len(log) >= n or n == 0
+        for c in range(n):
+            rec = log[c]
+            assert bool(rec["jumped"][row]) == bool(g["jumped"][t, c]), (name, t, c)
+            assert rec["u1"][row] == g["u1"][t, c]
+            if g["jumped"][t, c]:
+                assert int(rec["choice"][row]) == int(g["choice"][t, c]), (name, t, c)
+                npr = rec["pdf"].shape[1]
+                assert np.max(np.abs(rec["pdf"][row] - g["pdf"][t, c, :npr])) < 1e-9

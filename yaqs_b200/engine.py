@@ -1,0 +1,867 @@
+"""Batched Tensor Jump Method engine: all trajectories of a batch advance in lock-step on one GPU.
+
+Host-side mirror of the reference's per-trajectory drivers (``analog/analog_tjm.py``) and methods
+(``core/methods/tdvp``, ``dissipation.py``, ``stochastic_process.py``, the gauge moves of ``data_structures/mps.py``),
+re-designed for a batch: every step below is ONE kernel launch over all trajectories (ragged bond dimensions live in a
+device int32 array, data-dependent work is gated by device masks), and the only host synchronisations are the
+"any trajectory still iterating?" reads of the Lanczos and Jacobi loops and the "did any trajectory jump?" read.
+
+The arithmetic is done by ``kernels`` -- the ctypes binding of libyaqs_b200.so in production.  Tests may inject the
+numpy twin from ``oracle/`` to exercise this host logic on CPU; the package itself never falls back to it.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Sequence
+
+import numpy as np
+import scipy.linalg
+import torch
+
+from .kernels import (DIST, LANCZOS_PITCH, OP_ABSORB_L, OP_ABSORB_R, OP_ENVL1, OP_ENVL3, OP_ENVR3, OP_LCONTRACT, OP_MERGE,
+                      OP_RCONTRACT, SVD_COLS, SVD_META, SVD_ROWS, SVD_THETA, TRUNC_MODES, Buf, Ext)
+
+C128 = torch.complex128
+KRYLOV_MAX = 25          # max_lanczos_iterations (matrix_exponential.py:37)
+SHIFT_THRESHOLD = 1e-12  # hard-coded policy of SVD gauge shifts (mps.py:757-759)
+
+# status bits reported per trajectory
+STATUS_SVD_NOT_CONVERGED = 1
+STATUS_NONFINITE = 2
+STATUS_ZERO_JUMP_WEIGHT = 4
+
+
+@dataclass
+class EngineParams:
+    """The fields of AnalogSimParams / DigitalSimParams the hot path reads (simulation_parameters.py:477-750)."""
+    dt: float = 0.1
+    n_steps: int = 10
+    order: int = 2
+    max_bond_dim: int | None = 128
+    svd_threshold: float = 1e-6
+    trunc_mode: str = "discarded_weight"
+    krylov_tol: float = 1e-4
+    tdvp_mode: str = "2site"
+    tdvp_sweeps: int = 1
+    sample_timesteps: bool = True
+    digital: bool = False
+
+    @property
+    def n_times(self) -> int:
+        return self.n_steps + 1
+
+    @property
+    def tdvp_min_keep(self) -> int:
+        """sweep_utils.py:33-46."""
+        return 2 if self.max_bond_dim is None else min(2, self.max_bond_dim)
+
+
+@dataclass
+class JumpProcess:
+    """One entry of the site-ordered jump table (stochastic_process.py:139-176)."""
+    kind: str                       # "one" | "pauli2" | "adjacent"
+    sites: tuple[int, ...]
+    strength: float
+    ldl: np.ndarray | None = None   # L^dagger L (2x2 or 4x4) for non-scalar weights
+    ops: tuple = ()                 # jump operator(s): (L,) for one/adjacent, (F0, F1) for long-range Pauli
+
+
+class BatchLayout:
+    """Slot capacities and offsets of the per-trajectory tensors (DESIGN.md "Data layout in HBM")."""
+
+    def __init__(self, length: int, nbatch: int, chi_cap: int | None, mpo_bonds: Sequence[int], init_bonds: Sequence[int], d: int = 2):
+        self.L, self.B, self.d = length, nbatch, d
+        natural = [d ** min(j, length - j) for j in range(length + 1)]
+        if chi_cap is None:
+            if max(natural) > 4096:
+                raise ValueError("max_bond_dim=None needs bonds up to d**(L/2); give an explicit max_bond_dim for this chain length")
+            cap = natural
+        else:
+            cap = [min(chi_cap, n) for n in natural]
+        self.cap = [max(c, int(b)) for c, b in zip(cap, init_bonds)]
+        self.cap[0] = self.cap[length] = 1
+        self.D = [int(x) for x in mpo_bonds]                       # MPO bond dims, D[0] = D[L] = 1 for open chains
+        self.slot = [d * self.cap[i] * self.cap[i + 1] for i in range(length)]
+        self.site_off = [0] * length
+        acc = 0
+        for i in range(length):
+            self.site_off[i] = acc
+            acc += self.slot[i] * nbatch
+        self.state_elems = acc
+        self.env_slot = [self.cap[j] * self.D[j] * self.cap[j] for j in range(length + 1)]
+        self.env_off = [0] * (length + 1)
+        acc = 0
+        for j in range(length + 1):
+            self.env_off[j] = acc
+            acc += self.env_slot[j] * nbatch
+        self.env_elems = acc
+        self.cmax = max(self.cap)
+        self.Dmax = max(self.D)
+        pair = [self.cap[i] * self.cap[i + 2] for i in range(length - 1)] or [1]
+        single = [self.cap[i] * self.cap[i + 1] for i in range(length)]
+        self.theta_slot = d * d * max(pair)
+        self.nloc_max = max(self.theta_slot, d * max(single))
+        self.t_slot = self.nloc_max * self.Dmax
+        self.svd_dim = d * self.cmax
+
+
+class BatchedState:
+    """B matrix-product states: packed site tensors + the device-resident bond dimensions (mps.py:54-69)."""
+
+    def __init__(self, layout: BatchLayout, device):
+        self.layout = layout
+        self.A = torch.zeros(layout.state_elems, dtype=C128, device=device)
+        self.bond = torch.ones((layout.B, layout.L + 1), dtype=torch.int32, device=device)
+
+    def site(self, i: int) -> Buf:
+        return Buf(self.A, self.layout.site_off[i], self.layout.slot[i])
+
+    def ext(self, j: int) -> Ext:
+        return Ext(self.bond, j, self.layout.L + 1)
+
+    def copy_from(self, other: "BatchedState") -> None:
+        self.A.copy_(other.A)
+        self.bond.copy_(other.bond)
+
+    def load(self, tensors_per_traj: Sequence[Sequence[np.ndarray]] | Sequence[np.ndarray]) -> None:
+        """Upload host MPS tensors (s, l, r).  A single MPS (list of arrays) is broadcast to all trajectories."""
+        lay = self.layout
+        single = isinstance(tensors_per_traj[0], np.ndarray)
+        host = torch.zeros(lay.state_elems, dtype=C128)
+        bond = torch.ones((lay.B, lay.L + 1), dtype=torch.int32)
+        hn = host.numpy()
+        for b in range(lay.B):
+            tensors = tensors_per_traj if single else tensors_per_traj[b]
+            for i, t in enumerate(tensors):
+                d, l, r = t.shape
+                if l > lay.cap[i] or r > lay.cap[i + 1] or d != lay.d:
+                    raise ValueError(f"site {i}: tensor {t.shape} exceeds the slot capacity ({lay.d},{lay.cap[i]},{lay.cap[i + 1]})")
+                off = lay.site_off[i] + b * lay.slot[i]
+                hn[off: off + t.size] = np.ascontiguousarray(t, dtype=np.complex128).reshape(-1)
+                bond[b, i], bond[b, i + 1] = l, r
+        self.A.copy_(host)
+        self.bond.copy_(bond)
+
+    def download(self, b: int) -> list[np.ndarray]:
+        lay = self.layout
+        bond = self.bond[b].cpu().numpy()
+        out = []
+        for i in range(lay.L):
+            l, r = int(bond[i]), int(bond[i + 1])
+            off = lay.site_off[i] + b * lay.slot[i]
+            out.append(self.A[off: off + lay.d * l * r].cpu().numpy().reshape(lay.d, l, r).copy())
+        return out
+
+
+class BatchedTJM:
+    """Lock-step TJM over a batch.  ``kernels`` is a CudaKernels instance (production) or a test double."""
+
+    def __init__(self, kernels, length: int, nbatch: int, mpo: Sequence[np.ndarray], params: EngineParams,
+                 noise: Sequence[dict] | None, observables: Sequence[tuple[np.ndarray, Sequence[int]]],
+                 init_tensors, svd_block_rows: int | None = None):
+        self.K = kernels
+        self.dev = kernels.device
+        self.p = params
+        self.L, self.B, self.d = length, nbatch, 2
+        single = isinstance(init_tensors[0], np.ndarray)
+        ref = init_tensors if single else init_tensors[0]
+        init_bonds = [1] * (length + 1)
+        for tensors in ([init_tensors] if single else init_tensors):
+            for i, t in enumerate(tensors):
+                init_bonds[i] = max(init_bonds[i], t.shape[1])
+                init_bonds[i + 1] = max(init_bonds[i + 1], t.shape[2])
+        del ref
+        mpo_bonds = [int(mpo[0].shape[2])] + [int(w.shape[3]) for w in mpo]
+        self.lay = BatchLayout(length, nbatch, params.max_bond_dim, mpo_bonds, init_bonds)
+        lay = self.lay
+        dev = self.dev
+        self.phi = BatchedState(lay, dev)
+        self.psi = BatchedState(lay, dev) if params.order == 2 else None
+        self.phi.load(init_tensors)
+        # environments: bond-slot storage; the left and right blocks of a 2-site sweep never need the same bond at the
+        # same time, 1TDVP's bond update does.
+        self.renv = torch.zeros(lay.env_elems, dtype=C128, device=dev)
+        self.lenv = torch.zeros(lay.env_elems, dtype=C128, device=dev) if params.tdvp_mode == "1site" else self.renv
+        # MPO tensors (shared by all trajectories): W[o,p,a,a'], its left-environment transpose WT[p,o,a',a], merged pairs
+        self.W1 = [torch.from_numpy(np.ascontiguousarray(w, dtype=np.complex128).reshape(-1)).to(dev) for w in mpo]
+        self.W1T = [torch.from_numpy(np.ascontiguousarray(np.transpose(w, (1, 0, 3, 2)), dtype=np.complex128).reshape(-1)).to(dev) for w in mpo]
+        self.W2 = []
+        for i in range(length - 1):
+            m = np.einsum("acei,bdif->abcdef", mpo[i], mpo[i + 1])
+            s = m.shape
+            self.W2.append(torch.from_numpy(np.ascontiguousarray(m.reshape(s[0] * s[1], s[2] * s[3], s[4], s[5])).reshape(-1)).to(dev))
+        # workspaces
+        B = nbatch
+        self.theta = torch.zeros(B * lay.theta_slot, dtype=C128, device=dev)
+        self.T1 = torch.zeros(B * lay.t_slot, dtype=C128, device=dev)
+        self.T2 = torch.zeros(B * lay.t_slot, dtype=C128, device=dev)
+        self.svec = lay.nloc_max
+        self.basis = torch.zeros(B * (KRYLOV_MAX + 1) * self.svec, dtype=C128, device=dev)
+        self.tmp = torch.zeros(B * lay.nloc_max, dtype=C128, device=dev)
+        sd = lay.svd_dim
+        self.svd_w = torch.zeros(B * sd * sd, dtype=C128, device=dev)
+        self.svd_q = torch.zeros(B * sd * sd, dtype=C128, device=dev)
+        self.svd_u = torch.zeros(B * sd * sd, dtype=C128, device=dev)
+        self.svd_v = torch.zeros(B * sd * sd, dtype=C128, device=dev)
+        self.svd_s = torch.zeros(B * sd, dtype=torch.float64, device=dev)
+        self.svd_meta = torch.zeros(B * SVD_META, dtype=torch.int32, device=dev)
+        self.svd_rot = torch.zeros(B, dtype=torch.int32, device=dev)
+        self.keep = torch.ones(B, dtype=torch.int32, device=dev)
+        self.counter = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.status = torch.zeros(B, dtype=torch.int32, device=dev)
+        self.alpha = torch.zeros(B * LANCZOS_PITCH, dtype=torch.float64, device=dev)
+        self.beta = torch.zeros(B * LANCZOS_PITCH, dtype=torch.float64, device=dev)
+        self.coef = torch.zeros(B * LANCZOS_PITCH, dtype=C128, device=dev)
+        self.nrm = torch.zeros(B, dtype=torch.float64, device=dev)
+        self.active = torch.zeros(B, dtype=torch.int32, device=dev)
+        self.kdone = torch.zeros(B, dtype=torch.int32, device=dev)
+        self.norm_buf = torch.zeros(B, dtype=torch.float64, device=dev)
+        self.scale_buf = torch.zeros(B, dtype=torch.float64, device=dev)
+        self.rdm1 = torch.zeros(B * 4, dtype=C128, device=dev)
+        self.rdm2 = torch.zeros(B * 16, dtype=C128, device=dev)
+        # Jacobi panel height: largest power of two whose 2*rows*(len+k) panel fits in ~200 KB of shared memory
+        if svd_block_rows is None:
+            svd_block_rows = 16
+            while svd_block_rows > 1 and 2 * svd_block_rows * (2 * sd) * 16 > 200 * 1024:
+                svd_block_rows //= 2
+        self.svd_block_rows = svd_block_rows
+        self.svd_nblocks = max(2, 2 * ((sd + 2 * svd_block_rows - 1) // (2 * svd_block_rows)))
+        # noise tables
+        self.noise = list(noise) if noise else None
+        if self.noise is not None and all(pr["strength"] == 0 for pr in self.noise):
+            self.noise_active = False
+        else:
+            self.noise_active = self.noise is not None
+        self._diss_cache: dict[float, list] = {}
+        self.jump_table = self._build_jump_table() if self.noise is not None else []
+        # observables (already in the reference's sorted order)
+        self.observables = [(np.asarray(m, dtype=np.complex128), tuple(int(s) for s in sites)) for m, sites in observables]
+        self.stats = {"krylov_calls": 0, "matvecs": 0, "svd_calls": 0, "svd_sweeps": 0, "jumps": 0}
+
+    # ------------------------------------------------------------------------------------------------------------------
+    # small helpers
+    # ------------------------------------------------------------------------------------------------------------------
+    def env(self, j: int, left: bool) -> Buf:
+        return Buf(self.lenv if left else self.renv, self.lay.env_off[j], self.lay.env_slot[j])
+
+    def _buf(self, t: torch.Tensor, slot: int) -> Buf:
+        return Buf(t, 0, slot)
+
+    def _set_bond(self, st: BatchedState, j: int, mask) -> None:
+        if mask is None:
+            st.bond[:, j] = self.keep
+        else:
+            st.bond[:, j] = torch.where(mask != 0, self.keep, st.bond[:, j])
+
+    def _trunc_args(self, mode: str, threshold: float, max_bond: int | None, min_keep: int):
+        return TRUNC_MODES[mode], float(threshold), int(max_bond) if max_bond else 0, int(min_keep)
+
+    # ------------------------------------------------------------------------------------------------------------------
+    # contractions
+    # ------------------------------------------------------------------------------------------------------------------
+    def heff_matvec(self, st: BatchedState, i: int, nsites: int, x: Buf, y: Buf, mask) -> None:
+        """project_site (primitives.py:180-204) on sites i..i+nsites-1: three launches."""
+        lay, K, B = self.lay, self.K, self.B
+        dphys = self.d ** nsites
+        Dl, Dr = lay.D[i], lay.D[i + nsites]
+        el, er = st.ext(i), st.ext(i + nsites)
+        cl, cr = lay.cap[i], lay.cap[i + nsites]
+        w = self.W1[i] if nsites == 1 else self.W2[i]
+        t1, t2 = self._buf(self.T1, lay.t_slot), self._buf(self.T2, lay.t_slot)
+        K.gemm(OP_RCONTRACT, B, 1, mask, el, er, None, dphys, Dl, Dr, x, self.env(i + nsites, False), t1, 0, dphys * cl, Dr * cr)
+        K.wapply(B, mask, el, er, dphys, dphys, Dl, Dr, w, t1, t2, cl * cr)
+        K.gemm(OP_LCONTRACT, B, dphys, mask, el, er, None, dphys, Dl, Dr, self.env(i, True), t2, y, 0, cl, cr)
+        self.stats["matvecs"] += 1
+
+    def bond_matvec(self, el: Ext, er: Ext, jbond: int, x: Buf, y: Buf, mask, cl: int, cr: int) -> None:
+        """project_bond (primitives.py:207-226) at bond jbond."""
+        lay, K, B = self.lay, self.K, self.B
+        D = lay.D[jbond]
+        t1 = self._buf(self.T1, lay.t_slot)
+        K.gemm(OP_RCONTRACT, B, 1, mask, el, er, None, 1, D, D, x, self.env(jbond, False), t1, 0, cl, D * cr)
+        K.gemm(OP_LCONTRACT, B, 1, mask, el, er, None, 1, D, D, self.env(jbond, True), t1, y, 0, cl, cr)
+        self.stats["matvecs"] += 1
+
+    def env_boundaries(self, st: BatchedState) -> None:
+        """Identity blocks at both chain ends (primitives.py:162-168, integrators.py:186-193)."""
+        lay = self.lay
+        self.K.env_identity(self.B, None, st.ext(lay.L), lay.D[lay.L], self.env(lay.L, False), lay.cap[lay.L])
+        self.K.env_identity(self.B, None, st.ext(0), lay.D[0], self.env(0, True), lay.cap[0])
+
+    def env_update_right(self, st: BatchedState, s: int) -> None:
+        """update_right_environment (primitives.py:77-108): block at bond s+1 -> block at bond s."""
+        lay, K, B, d = self.lay, self.K, self.B, self.d
+        Dl, Dr = lay.D[s], lay.D[s + 1]
+        el, er = st.ext(s), st.ext(s + 1)
+        cl, cr = lay.cap[s], lay.cap[s + 1]
+        a = st.site(s)
+        t1, t2 = self._buf(self.T1, lay.t_slot), self._buf(self.T2, lay.t_slot)
+        K.gemm(OP_RCONTRACT, B, 1, None, el, er, None, d, Dl, Dr, a, self.env(s + 1, False), t1, 0, d * cl, Dr * cr)
+        K.wapply(B, None, el, er, d, d, Dl, Dr, self.W1[s], t1, t2, cl * cr)
+        K.gemm(OP_ENVR3, B, 1, None, el, er, None, d, Dl, Dr, t2, a, self.env(s, False), 0, Dl * cl, cl)
+
+    def env_update_left(self, st: BatchedState, s: int) -> None:
+        """update_left_environment (primitives.py:111-136): block at bond s -> block at bond s+1."""
+        lay, K, B, d = self.lay, self.K, self.B, self.d
+        Dl, Dr = lay.D[s], lay.D[s + 1]
+        el, er = st.ext(s), st.ext(s + 1)
+        cl, cr = lay.cap[s], lay.cap[s + 1]
+        a = st.site(s)
+        t1, t2 = self._buf(self.T1, lay.t_slot), self._buf(self.T2, lay.t_slot)
+        K.gemm(OP_ENVL1, B, d, None, el, er, None, d, Dl, Dr, self.env(s, True), a, t1, 0, Dl * cl, cr)
+        K.wapply(B, None, el, er, d, d, Dr, Dl, self.W1T[s], t1, t2, cl * cr)
+        K.gemm(OP_ENVL3, B, 1, None, el, er, None, d, Dl, Dr, a, t2, self.env(s + 1, True), 0, cr, Dr * cr)
+
+    def init_right_envs(self, st: BatchedState) -> None:
+        """initialize_right_environments (primitives.py:139-174)."""
+        self.env_boundaries(st)
+        for s in reversed(range(1, self.L)):
+            self.env_update_right(st, s)
+
+    def merge(self, st: BatchedState, i: int, mask=None) -> Buf:
+        """merge_two_site (decompositions.py:87-102) of sites i, i+1 into the theta workspace."""
+        lay = self.lay
+        th = self._buf(self.theta, lay.theta_slot)
+        self.K.gemm(OP_MERGE, self.B, self.d * self.d, mask, st.ext(i), st.ext(i + 1), st.ext(i + 2), self.d, 1, 1, st.site(i), st.site(i + 1),
+                    th, 0, lay.cap[i], lay.cap[i + 2])
+        return th
+
+    # ------------------------------------------------------------------------------------------------------------------
+    # Lanczos exponential (matrix_exponential.py:33-201)
+    # ------------------------------------------------------------------------------------------------------------------
+    def krylov(self, x: Buf, out: Buf, el: Ext, er: Ext, dphys: int, matvec, dt: float, mask) -> None:
+        K, B = self.K, self.B
+        basis = self._buf(self.basis, (KRYLOV_MAX + 1) * self.svec)
+        K.lanczos_init(B, mask, el, er, dphys, x, basis, self.svec, self.nrm, self.active, self.kdone)
+        self.stats["krylov_calls"] += 1
+        for j in range(KRYLOV_MAX):
+            matvec(basis.at(j * self.svec), basis.at((j + 1) * self.svec), self.active)
+            self.counter.zero_()
+            K.lanczos_step(B, j, KRYLOV_MAX, dt, self.p.krylov_tol, el, er, dphys, basis, self.svec, self.alpha, self.beta, self.nrm,
+                           self.active, self.kdone, self.coef, self.counter)
+            if K.sync_int(self.counter) == 0:
+                break
+        K.lanczos_combine(B, mask, el, er, dphys, basis, self.svec, self.coef, KRYLOV_MAX, self.kdone, out)
+
+    def update_site(self, st: BatchedState, i: int, nsites: int, x: Buf, dt: float, mask=None) -> None:
+        """update_site (primitives.py:484-517): x <- exp(-i dt H_eff) x in place."""
+        self.krylov(x, x, st.ext(i), st.ext(i + nsites), self.d ** nsites,
+                    lambda src, dst, m: self.heff_matvec(st, i, nsites, src, dst, m), dt, mask)
+
+    # ------------------------------------------------------------------------------------------------------------------
+    # SVD driver + splits / gauge shifts
+    # ------------------------------------------------------------------------------------------------------------------
+    def _svd(self, mode: int, src: Buf, el: Ext, er: Ext, trunc, dist: str, mask) -> None:
+        """prepare -> cyclic Jacobi sweeps until every trajectory is clean -> finalize (keep, U f(S), g(S) Vh)."""
+        K, B, lay = self.K, self.B, self.lay
+        sd = lay.svd_dim
+        w, q = self._buf(self.svd_w, sd * sd), self._buf(self.svd_q, sd * sd)
+        K.svd_prepare(B, mask, mode, el, er, self.d, src, w, q, self.svd_meta, self.svd_rot)
+        nb, rows = self.svd_nblocks, self.svd_block_rows
+        inner = 30 if nb == 2 else 1
+        self.stats["svd_calls"] += 1
+        for _sweep in range(60):
+            for rnd in range(nb - 1):
+                K.svd_round(B, mask, self.svd_meta, rows, nb, rnd, rnd == 0, inner, w, q, self.svd_rot, sd, sd)
+            self.counter.zero_()
+            K.svd_check(B, mask, self.svd_meta, self.svd_rot, self.counter)
+            self.stats["svd_sweeps"] += 1
+            if K.sync_int(self.counter) == 0:
+                break
+        tm, thr, mb, mk = trunc
+        K.svd_finalize(B, mask, self.svd_meta, tm, thr, mb, mk, DIST[dist], w, q, self.svd_s, sd, Ext(self.keep, 0, 1),
+                       self._buf(self.svd_u, sd * sd), self._buf(self.svd_v, sd * sd), self.status, sd)
+
+    def split_theta(self, st: BatchedState, i: int, dist: str, trunc, mask=None) -> None:
+        """split_two_site (decompositions.py:105-185): theta workspace -> sites i, i+1; bond i+1 <- keep."""
+        lay, K, B, d = self.lay, self.K, self.B, self.d
+        sd = lay.svd_dim
+        self._svd(SVD_THETA, self._buf(self.theta, lay.theta_slot), st.ext(i), st.ext(i + 2), trunc, dist, mask)
+        kx = Ext(self.keep, 0, 1)
+        K.copy_packed(B, mask, st.ext(i), kx, d, self._buf(self.svd_u, sd * sd), st.site(i), lay.slot[i])
+        K.unpack_vh(B, mask, kx, st.ext(i + 2), d, self._buf(self.svd_v, sd * sd), st.site(i + 1), lay.slot[i + 1])
+        self._set_bond(st, i + 1, mask)
+
+    def shift_right(self, st: BatchedState, i: int, trunc, mask=None) -> None:
+        """Centre i -> i+1 (mps.py:719-769).  The reference merges the pair and splits it; because site i+1 is a right
+        isometry the SVD of the centre tensor alone gives the same singular values / keep decision."""
+        lay, K, B, d = self.lay, self.K, self.B, self.d
+        sd = lay.svd_dim
+        self._svd(SVD_ROWS, st.site(i), st.ext(i), st.ext(i + 1), trunc, "right", mask)
+        kx = Ext(self.keep, 0, 1)
+        K.copy_packed(B, mask, st.ext(i), kx, d, self._buf(self.svd_u, sd * sd), st.site(i), lay.slot[i])
+        tmp = self._buf(self.tmp, lay.nloc_max)
+        K.gemm(OP_ABSORB_R, B, d, mask, kx, st.ext(i + 1), st.ext(i + 2), d, 1, 1, self._buf(self.svd_v, sd * sd), st.site(i + 1), tmp, 0,
+               lay.cap[i + 1], lay.cap[i + 2])
+        K.copy_packed(B, mask, kx, st.ext(i + 2), d, tmp, st.site(i + 1), lay.slot[i + 1])
+        self._set_bond(st, i + 1, mask)
+
+    def shift_left(self, st: BatchedState, i: int, trunc, mask=None) -> None:
+        """Centre i -> i-1 (mps.py:771-788), reduced form (site i-1 must be a left isometry)."""
+        lay, K, B, d = self.lay, self.K, self.B, self.d
+        sd = lay.svd_dim
+        self._svd(SVD_COLS, st.site(i), st.ext(i), st.ext(i + 1), trunc, "left", mask)
+        kx = Ext(self.keep, 0, 1)
+        tmp = self._buf(self.tmp, lay.nloc_max)
+        K.gemm(OP_ABSORB_L, B, d, mask, st.ext(i - 1), st.ext(i), kx, d, 1, 1, st.site(i - 1), self._buf(self.svd_u, sd * sd), tmp, 0,
+               lay.cap[i - 1], lay.cap[i])
+        K.copy_packed(B, mask, st.ext(i - 1), kx, d, tmp, st.site(i - 1), lay.slot[i - 1])
+        K.unpack_vh(B, mask, kx, st.ext(i + 1), d, self._buf(self.svd_v, sd * sd), st.site(i), lay.slot[i])
+        self._set_bond(st, i, mask)
+
+    def normalize_site(self, st: BatchedState, i: int, mask=None) -> None:
+        """QR at a chain end with R dropped == divide the (1-column) centre tensor by its norm (mps.py:736-746)."""
+        K, B = self.K, self.B
+        K.norm2(B, mask, st.ext(i), st.ext(i + 1), self.d, st.site(i), self.norm_buf)
+        torch.rsqrt(self.norm_buf, out=self.scale_buf)
+        K.scale(B, mask, st.ext(i), st.ext(i + 1), self.d, self.scale_buf, st.site(i), self.lay.slot[i])
+
+    # ------------------------------------------------------------------------------------------------------------------
+    # TDVP sweeps (integrators.py:44-291)
+    # ------------------------------------------------------------------------------------------------------------------
+    def _substep_dt(self, scale: float) -> float:
+        return scale if self.p.digital else float(self.p.dt) * scale
+
+    def tdvp(self, st: BatchedState) -> None:
+        """tdvp (tdvp.py:69-112)."""
+        mode = self.p.tdvp_mode
+        if mode in ("2site", "dynamic") and self.L == 1:
+            mode = "1site"
+        plan = [1.0 / self.p.tdvp_sweeps] * self.p.tdvp_sweeps
+        if mode == "2site":
+            self.sweep_2site(st, plan)
+        elif mode == "1site":
+            for s in plan:
+                self.sweep_1site(st, s)
+        else:
+            raise NotImplementedError("tdvp_mode='dynamic' is a SURVEY.md 8(f) 'next' row")
+
+    def sweep_2site(self, st: BatchedState, plan: Sequence[float]) -> None:
+        n, lay, p = self.L, self.lay, self.p
+        trunc = self._trunc_args(p.trunc_mode, p.svd_threshold, p.max_bond_dim, p.tdvp_min_keep)
+        th = self._buf(self.theta, lay.theta_slot)
+        self.init_right_envs(st)
+        for scale in plan:
+            dt = self._substep_dt(scale)
+            for i in range(n - 2):
+                self.merge(st, i)
+                self.update_site(st, i, 2, th, 0.5 * dt)
+                self.split_theta(st, i, "right", trunc)
+                self.env_update_left(st, i)
+                self.update_site(st, i + 1, 1, st.site(i + 1), -0.5 * dt)
+            i = n - 2
+            self.merge(st, i)
+            self.update_site(st, i, 2, th, dt)
+            self.split_theta(st, i, "left", trunc)
+            self.env_update_right(st, i + 1)
+            for i in reversed(range(n - 2)):
+                self.update_site(st, i + 1, 1, st.site(i + 1), -0.5 * dt)
+                self.merge(st, i)
+                self.update_site(st, i, 2, th, 0.5 * dt)
+                self.split_theta(st, i, "left", trunc)
+                self.env_update_right(st, i + 1)
+
+    def sweep_1site(self, st: BatchedState, scale: float) -> None:
+        n, lay, K, B, d = self.L, self.lay, self.K, self.B, self.d
+        keep_all = self._trunc_args("discarded_weight", 0.0, None, 1)      # QR: no truncation (integrators.py:100,131)
+        dt = self._substep_dt(scale)
+        sd = lay.svd_dim
+        kx = Ext(self.keep, 0, 1)
+        cbuf = self._buf(self.theta, lay.theta_slot)
+        tmp = self._buf(self.tmp, lay.nloc_max)
+        self.init_right_envs(st)
+        if n == 1:
+            self.update_site(st, 0, 1, st.site(0), dt)
+            return
+        for i in range(n - 1):
+            self.update_site(st, i, 1, st.site(i), 0.5 * dt)
+            self._svd(SVD_ROWS, st.site(i), st.ext(i), st.ext(i + 1), keep_all, "right", None)
+            K.copy_packed(B, None, st.ext(i), kx, d, self._buf(self.svd_u, sd * sd), st.site(i), lay.slot[i])
+            K.copy_packed(B, None, kx, st.ext(i + 1), 1, self._buf(self.svd_v, sd * sd), cbuf, lay.theta_slot)      # C (k x r_old)
+            r_old = st.bond[:, i + 1].clone()
+            st.bond[:, i + 1] = self.keep                   # site i now has right bond k
+            self.env_update_left(st, i)                     # lb[i+1] with extents (k, D, k)
+            st.bond[:, i + 1] = r_old                       # rb[i] still has the old extent
+            kt = self.keep.clone()
+            ek, eo = Ext(kt, 0, 1), st.ext(i + 1)
+            self.krylov(cbuf, cbuf, ek, eo, 1, lambda s_, d_, m, ek=ek, eo=eo, j=i + 1: self.bond_matvec(ek, eo, j, s_, d_, m, lay.cap[j], lay.cap[j]),
+                        -0.5 * dt, None)
+            K.gemm(OP_ABSORB_R, B, d, None, ek, eo, st.ext(i + 2), d, 1, 1, cbuf, st.site(i + 1), tmp, 0, lay.cap[i + 1], lay.cap[i + 2])
+            K.copy_packed(B, None, ek, st.ext(i + 2), d, tmp, st.site(i + 1), lay.slot[i + 1])
+            st.bond[:, i + 1] = kt
+        self.update_site(st, n - 1, 1, st.site(n - 1), dt)
+        for i in reversed(range(1, n)):
+            self._svd(SVD_COLS, st.site(i), st.ext(i), st.ext(i + 1), keep_all, "left", None)
+            K.unpack_vh(B, None, kx, st.ext(i + 1), d, self._buf(self.svd_v, sd * sd), st.site(i), lay.slot[i])
+            K.copy_packed(B, None, st.ext(i), kx, 1, self._buf(self.svd_u, sd * sd), cbuf, lay.theta_slot)          # C (l_old x k)
+            l_old = st.bond[:, i].clone()
+            kt = self.keep.clone()
+            st.bond[:, i] = kt
+            self.env_update_right(st, i)                    # rb[i-1] with extents (k, D, k)
+            st.bond[:, i] = l_old
+            eo, ek = st.ext(i), Ext(kt, 0, 1)
+            self.krylov(cbuf, cbuf, eo, ek, 1, lambda s_, d_, m, ek=ek, eo=eo, j=i: self.bond_matvec(eo, ek, j, s_, d_, m, lay.cap[j], lay.cap[j]),
+                        -0.5 * dt, None)
+            K.gemm(OP_ABSORB_L, B, d, None, st.ext(i - 1), eo, ek, d, 1, 1, st.site(i - 1), cbuf, tmp, 0, lay.cap[i - 1], lay.cap[i])
+            K.copy_packed(B, None, st.ext(i - 1), ek, d, tmp, st.site(i - 1), lay.slot[i - 1])
+            st.bond[:, i] = kt
+            self.update_site(st, i - 1, 1, st.site(i - 1), 0.5 * dt)
+
+    # ------------------------------------------------------------------------------------------------------------------
+    # dissipation (dissipation.py:50-183)
+    # ------------------------------------------------------------------------------------------------------------------
+    def _dissipators(self, dt: float):
+        """Per-site local factors for time step dt: (op2x2 | None, pair4x4 | None).  Identical for every trajectory, so
+        scipy.linalg.expm of the 2x2 / 4x4 generators runs once per (dt) on the host."""
+        if dt in self._diss_cache:
+            return self._diss_cache[dt]
+        from .noise import is_pauli
+        n = self.L
+        out = []
+        for i in range(n):
+            op1 = np.eye(2, dtype=np.complex128)
+            touched = False
+            gen = np.zeros((2, 2), dtype=np.complex128)
+            has_one, all_pauli = False, True
+            for pr in self.noise:
+                if len(pr["sites"]) == 1 and pr["sites"][0] == i:
+                    has_one = True
+                    if is_pauli(pr):
+                        gen += pr["strength"] * np.eye(2)
+                    else:
+                        all_pauli = False
+                        m = np.asarray(pr["matrix"], dtype=np.complex128)
+                        gen += pr["strength"] * (m.conj().T @ m)
+            if has_one:
+                touched = True
+                op1 = (np.exp(-0.5 * dt * float(gen[0, 0].real)) * np.eye(2)) if all_pauli else scipy.linalg.expm(-0.5 * dt * gen)
+            pair = None
+            scalar2 = 1.0
+            if i != 0:
+                gen2 = np.zeros((4, 4), dtype=np.complex128)
+                has_adj, all_pauli2 = False, True
+                for pr in self.noise:
+                    if len(pr["sites"]) == 2 and pr["sites"][1] == i:
+                        if abs(pr["sites"][1] - pr["sites"][0]) > 1:
+                            if not is_pauli(pr):
+                                raise NotImplementedError("Non-Pauli Long-range processes are not implemented yet")
+                            scalar2 *= np.exp(-0.5 * dt * pr["strength"])
+                        else:
+                            has_adj = True
+                            if is_pauli(pr):
+                                gen2 += pr["strength"] * np.eye(4)
+                            else:
+                                all_pauli2 = False
+                                m = np.asarray(pr["matrix"], dtype=np.complex128)
+                                gen2 += pr["strength"] * (m.conj().T @ m)
+                if has_adj:
+                    if all_pauli2:
+                        scalar2 *= np.exp(-0.5 * dt * float(gen2[0, 0].real))
+                    else:
+                        pair = scipy.linalg.expm(-0.5 * dt * gen2)
+            out.append((op1 if touched else None, None if scalar2 == 1.0 else scalar2, pair))
+        self._diss_cache[dt] = out
+        return out
+
+    def apply_dissipation(self, st: BatchedState, dt: float) -> None:
+        lay, K, B, d, n, p = self.lay, self.K, self.B, self.d, self.L, self.p
+        if not self.noise_active:
+            self.normalize_site(st, 0)                      # dissipation.py:79-86 (QR at site 0, R dropped)
+            return
+        shift = self._trunc_args("discarded_weight", SHIFT_THRESHOLD, None, 1)
+        user = self._trunc_args(p.trunc_mode, p.svd_threshold, p.max_bond_dim, 1)
+        for i in range(n - 1):                              # centre 0 -> L-1 with SVD shifts (:88-92)
+            self.shift_right(st, i, shift)
+        facs = self._dissipators(dt)
+        for i in reversed(range(n)):
+            op1, scalar2, pair = facs[i]
+            if op1 is not None:
+                op_t = torch.from_numpy(np.ascontiguousarray(op1).reshape(-1)).to(self.dev)
+                K.apply_local_op(B, None, None, 0, st.ext(i), st.ext(i + 1), d, op_t, 0, st.site(i), lay.cap[i] * lay.cap[i + 1])
+            if scalar2 is not None:
+                op_t = torch.from_numpy((scalar2 * np.eye(2, dtype=np.complex128)).reshape(-1)).to(self.dev)
+                K.apply_local_op(B, None, None, 0, st.ext(i), st.ext(i + 1), d, op_t, 0, st.site(i), lay.cap[i] * lay.cap[i + 1])
+            if pair is not None:
+                th = self.merge(st, i - 1)
+                op_t = torch.from_numpy(np.ascontiguousarray(pair).reshape(-1)).to(self.dev)
+                K.apply_local_op(B, None, None, 0, st.ext(i - 1), st.ext(i + 1), d * d, op_t, 0, th, lay.cap[i - 1] * lay.cap[i + 1])
+                self.split_theta(st, i - 1, "right", user)
+            if i != 0:
+                self.shift_left(st, i, shift)
+
+    # ------------------------------------------------------------------------------------------------------------------
+    # local reduced density matrices by a left-to-right transfer sweep (observables + jump weights)
+    # ------------------------------------------------------------------------------------------------------------------
+    def rho_sweep(self, st: BatchedState, need1: Sequence[int], need2: Sequence[int], mask=None):
+        """g1[i][b,o,p] = <psi| |o><p|_i |psi> for i in need1 and the two-site analogue for pairs (i,i+1), i in need2,
+        valid when every site right of the queried one is a right isometry (centre 0).  Replaces the reference's
+        copy + QR-shift + local contraction (mps.py:1178-1234, stochastic_process.py:139-176) by two GEMMs per site."""
+        lay, K, B, d, n = self.lay, self.K, self.B, self.d, self.L
+        need1, need2 = set(need1), set(need2)
+        last = max([*need1, *[i + 1 for i in need2], 0])
+        out1, out2 = {}, {}
+        x = self._buf(self.T1, lay.t_slot)
+        K.env_identity(B, mask, st.ext(0), 1, Buf(self.lenv, lay.env_off[0], lay.env_slot[0]), 1)
+        for i in range(last + 1):
+            e_i = Buf(self.lenv, lay.env_off[i], lay.env_slot[i])
+            if i in need2:
+                th = self.merge(st, i, mask)
+                K.gemm(OP_LCONTRACT, B, d * d, mask, st.ext(i), st.ext(i + 2), None, d * d, 1, 1, e_i, th, x, 0, lay.cap[i], lay.cap[i + 2])
+                K.local_rdm(B, mask, st.ext(i), st.ext(i + 2), d * d, th, x, self.rdm2)
+                out2[i] = self.rdm2.view(B, d * d, d * d).clone()
+            a = st.site(i)
+            K.gemm(OP_LCONTRACT, B, d, mask, st.ext(i), st.ext(i + 1), None, d, 1, 1, e_i, a, x, 0, lay.cap[i], lay.cap[i + 1])
+            if i in need1:
+                K.local_rdm(B, mask, st.ext(i), st.ext(i + 1), d, a, x, self.rdm1)
+                out1[i] = self.rdm1.view(B, d, d).clone()
+            if i < last:
+                e_n = Buf(self.lenv, lay.env_off[i + 1], lay.env_slot[i + 1])
+                K.gemm(OP_ENVL3, B, 1, mask, st.ext(i), st.ext(i + 1), None, d, 1, 1, x, a, e_n, 1, lay.cap[i + 1], lay.cap[i + 1])
+        return out1, out2
+
+    def evaluate_observables(self, st: BatchedState) -> torch.Tensor:
+        """[B, n_obs] expectation values in the given (sorted) observable order (mps.py:1178-1234)."""
+        need1 = [s[0] for _, s in self.observables if len(s) == 1]
+        need2 = [s[0] for _, s in self.observables if len(s) == 2]
+        for _, s in self.observables:
+            if len(s) == 2 and s[1] != s[0] + 1:
+                raise AssertionError("Only nearest-neighbor observables are currently implemented.")
+        g1, g2 = self.rho_sweep(st, need1, need2)
+        res = torch.zeros((self.B, len(self.observables)), dtype=torch.float64, device=self.dev)
+        for k, (mat, sites) in enumerate(self.observables):
+            g = g1[sites[0]] if len(sites) == 1 else g2[sites[0]]
+            m = torch.from_numpy(mat).to(self.dev)
+            val = torch.einsum("op,bop->b", m, g)
+            res[:, k] = val.real
+        return res
+
+    def diagnostics(self, st: BatchedState) -> torch.Tensor:
+        """[B, 3]: cost = sum chi^3, max bond (includes d, mps.py:560-565), total bond (mps.py:549-602)."""
+        inner = st.bond[:, 1:self.L].to(torch.float64)
+        out = torch.zeros((self.B, 3), dtype=torch.float64, device=self.dev)
+        if inner.shape[1] > 0:
+            out[:, 0] = (inner ** 3).sum(dim=1)
+            out[:, 2] = inner.sum(dim=1)
+            out[:, 1] = torch.clamp(inner.max(dim=1).values, min=float(self.d))
+        else:
+            out[:, 1] = float(self.d)
+        return out
+
+    # ------------------------------------------------------------------------------------------------------------------
+    # stochastic process (stochastic_process.py:36-292)
+    # ------------------------------------------------------------------------------------------------------------------
+    def _build_jump_table(self) -> list[JumpProcess]:
+        from .noise import is_pauli
+        table: list[JumpProcess] = []
+        n = self.L
+        for site in range(n):
+            for pr in self.noise:
+                if len(pr["sites"]) == 1 and pr["sites"][0] == site:
+                    m = np.asarray(pr["matrix"], dtype=np.complex128)
+                    table.append(JumpProcess("one", (site,), float(pr["strength"]), m.conj().T @ m, (m,)))
+            if site < n - 1:
+                for pr in self.noise:
+                    if len(pr["sites"]) == 2 and pr["sites"][0] == site:
+                        if is_pauli(pr):
+                            if abs(pr["sites"][1] - site) > 1:
+                                ops = tuple(np.asarray(f, dtype=np.complex128) for f in pr["factors"])
+                                table.append(JumpProcess("pauli_lr", tuple(pr["sites"]), float(pr["strength"]), None, ops))
+                            else:
+                                m = np.asarray(pr["matrix"], dtype=np.complex128)
+                                table.append(JumpProcess("pauli_adj", tuple(pr["sites"]), float(pr["strength"]), None, (m,)))
+                        elif pr["sites"][1] == site + 1:
+                            m = np.asarray(pr["matrix"], dtype=np.complex128)
+                            table.append(JumpProcess("adjacent", tuple(pr["sites"]), float(pr["strength"]), m.conj().T @ m, (m,)))
+                        else:
+                            raise NotImplementedError("Non-Pauli long-range two-site jumps are not supported")
+        return table
+
+    def jump_weights(self, st: BatchedState, dt: float, mask) -> torch.Tensor:
+        """[B, n_proc] un-normalised weights dt * gamma * ||L psi||^2 in site-sweep order (stochastic_process.py:86-187)."""
+        tab = self.jump_table
+        need1 = sorted({p.sites[0] for p in tab if p.kind in ("one", "pauli_lr", "pauli_adj")})
+        need2 = sorted({p.sites[0] for p in tab if p.kind == "adjacent"})
+        g1, g2 = self.rho_sweep(st, need1, need2, mask)
+        w = torch.zeros((self.B, len(tab)), dtype=torch.float64, device=self.dev)
+        for k, pr in enumerate(tab):
+            if pr.kind == "one":
+                m = torch.from_numpy(pr.ldl).to(self.dev)
+                w[:, k] = dt * pr.strength * torch.einsum("op,bop->b", m, g1[pr.sites[0]]).real
+            elif pr.kind in ("pauli_lr", "pauli_adj"):
+                w[:, k] = dt * pr.strength * torch.einsum("boo->b", g1[pr.sites[0]]).real
+            else:
+                m = torch.from_numpy(pr.ldl).to(self.dev)
+                w[:, k] = dt * pr.strength * torch.einsum("op,bop->b", m, g2[pr.sites[0]]).real
+        return w
+
+    def stochastic_process(self, st: BatchedState, dt: float, u1: torch.Tensor | None, u2: torch.Tensor | None, log: list | None = None,
+                           tag: str = "") -> torch.Tensor | None:
+        """One jump test for every trajectory.  u1/u2: [B] uniforms (u2 is consumed only by trajectories that jump).
+        Returns the int32 jump mask (or None when there is no noise model)."""
+        K, B, lay, d, n = self.K, self.B, self.lay, self.d, self.L
+        if self.noise is None:
+            self.normalize_site(st, 0)                      # :226-231 (the uniform is not drawn)
+            return None
+        K.norm2(B, None, st.ext(0), st.ext(1), d, st.site(0), self.norm_buf)
+        dp = 1.0 - self.norm_buf
+        jump = (u1 < dp)
+        jmask = jump.to(torch.int32)
+        njump = K.sync_int(jmask.sum())
+        rec = None
+        if log is not None:
+            rec = dict(tag=tag, dp=dp.cpu().numpy().copy(), u1=u1.cpu().numpy().copy(), jumped=jump.cpu().numpy().copy(), choice=None, pdf=None)
+            log.append(rec)
+        if njump < B:
+            self.normalize_site(st, 0, None if njump == 0 else (1 - jmask))
+        if njump == 0:
+            return jmask
+        self.stats["jumps"] += njump
+        w = self.jump_weights(st, dt, jmask)
+        total = w.sum(dim=1)
+        bad = jump & ~(torch.isfinite(total) & (total > 0))
+        if K.sync_int(bad.to(torch.int32).sum()) > 0:
+            self.status |= bad.to(torch.int32) * STATUS_ZERO_JUMP_WEIGHT
+            raise ValueError("Jump probability weights are zero or non-finite. Reduce process strengths and/or the timestep dt so that "
+                             "dt * strength * ||L|psi>||^2 remains representable.")
+        total = torch.where(jump, total, torch.ones_like(total))
+        probs = w / total[:, None]
+        cdf = torch.cumsum(probs, dim=1)
+        cdf = cdf / torch.where(jump, cdf[:, -1], torch.ones_like(total))[:, None]
+        choice = torch.searchsorted(cdf, u2[:, None].contiguous(), right=True).squeeze(1).clamp(max=len(self.jump_table) - 1)
+        if rec is not None:
+            rec["choice"] = choice.cpu().numpy().copy()
+            rec["pdf"] = probs.cpu().numpy().copy()
+            rec["u2"] = u2.cpu().numpy().copy()
+        self._apply_jumps(st, jmask, choice)
+        return jmask
+
+    def _apply_jumps(self, st: BatchedState, jmask: torch.Tensor, choice: torch.Tensor) -> None:
+        """Left-canonicalise the jumping trajectories (the reference's PDF sweep leaves the centre at L-1,
+        stochastic_process.py:139-141), apply the selected operators (:251-288) and renormalise with the right-to-left
+        SVD sweep of normalize("B", "SVD") (:291, mps.py:815-839)."""
+        K, B, lay, d, n, p = self.K, self.B, self.lay, self.d, self.L, self.p
+        tab = self.jump_table
+        dev = self.dev
+        keep_all = self._trunc_args("discarded_weight", 0.0, None, 1)
+        shift = self._trunc_args("discarded_weight", SHIFT_THRESHOLD, None, 1)
+        user = self._trunc_args(p.trunc_mode, p.svd_threshold, p.max_bond_dim, 1)
+        for i in range(n - 1):
+            self.shift_right(st, i, keep_all, jmask)
+        # per-trajectory operator tables
+        kinds = {pr.kind for pr in tab}
+        site_a = torch.tensor([pr.sites[0] for pr in tab], dtype=torch.int32, device=dev)[choice]
+        ops_a = torch.from_numpy(np.stack([pr.ops[0] if pr.kind in ("one", "pauli_lr") else np.eye(2) for pr in tab]).astype(np.complex128)).to(dev)[choice].contiguous()
+        is_a = torch.tensor([1 if pr.kind in ("one", "pauli_lr") else 0 for pr in tab], dtype=torch.int32, device=dev)[choice]
+        broken = [torch.where((jmask != 0) & (is_a != 0), site_a, torch.full_like(site_a, -1))]
+        mask_a = jmask * is_a
+        for s in range(n):
+            K.apply_local_op(B, mask_a, site_a, s, st.ext(s), st.ext(s + 1), d, ops_a.view(-1), d * d, st.site(s), lay.cap[s] * lay.cap[s + 1])
+        if "pauli_lr" in kinds:
+            site_b = torch.tensor([pr.sites[1] if pr.kind == "pauli_lr" else -1 for pr in tab], dtype=torch.int32, device=dev)[choice]
+            ops_b = torch.from_numpy(np.stack([pr.ops[1] if pr.kind == "pauli_lr" else np.eye(2) for pr in tab]).astype(np.complex128)).to(dev)[choice].contiguous()
+            mask_b = jmask * (site_b >= 0).to(torch.int32)
+            for s in range(n):
+                K.apply_local_op(B, mask_b, site_b, s, st.ext(s), st.ext(s + 1), d, ops_b.view(-1), d * d, st.site(s), lay.cap[s] * lay.cap[s + 1])
+            broken.append(torch.where(mask_b != 0, site_b, torch.full_like(site_b, -1)))
+        if kinds & {"adjacent", "pauli_adj"}:
+            site_c = torch.tensor([pr.sites[0] if pr.kind in ("adjacent", "pauli_adj") else -1 for pr in tab], dtype=torch.int32, device=dev)[choice]
+            ops_c = torch.from_numpy(np.stack([pr.ops[0] if pr.kind in ("adjacent", "pauli_adj") else np.eye(4) for pr in tab]).astype(np.complex128)).to(dev)[choice].contiguous()
+            mask_c = jmask * (site_c >= 0).to(torch.int32)
+            if K.sync_int(mask_c.sum()) > 0:
+                for s in range(n - 1):
+                    m_s = mask_c * (site_c == s).to(torch.int32)
+                    if K.sync_int(m_s.sum()) == 0:
+                        continue
+                    th = self.merge(st, s, m_s)
+                    K.apply_local_op(B, m_s, None, 0, st.ext(s), st.ext(s + 2), d * d, ops_c.view(-1), d * d * d * d, th, lay.cap[s] * lay.cap[s + 2])
+                    self.split_theta(st, s, "right", user, m_s)
+                broken.append(torch.where(mask_c != 0, site_c + 1, torch.full_like(site_c, -1)))
+        # normalize("B", "SVD"): right-to-left merged SVD shifts.  Where the left neighbour is still a left isometry the
+        # reduced shift is identical; where it carries a jump operator the literal merge + split is needed.
+        th_trunc_left = shift
+        for i in reversed(range(1, n)):
+            lit = torch.zeros(B, dtype=torch.bool, device=dev)
+            for br in broken:
+                lit |= (br == (i - 1))
+            lit_mask = jmask * lit.to(torch.int32)
+            red_mask = jmask * (~lit).to(torch.int32)
+            nlit = K.sync_int(lit_mask.sum())
+            if nlit > 0:
+                self.merge(st, i - 1, lit_mask)
+                self.split_theta(st, i - 1, "left", th_trunc_left, lit_mask)
+            if nlit < K.sync_int(jmask.sum()):
+                self.shift_left(st, i, shift, red_mask)
+        self.normalize_site(st, 0, jmask)
+
+    # ------------------------------------------------------------------------------------------------------------------
+    # trajectory drivers (analog/analog_tjm.py:86-462)
+    # ------------------------------------------------------------------------------------------------------------------
+    def run(self, traj_uniforms: torch.Tensor | None, sample_uniforms: torch.Tensor | None, log: list | None = None):
+        """Run all time steps.  traj_uniforms: [B, 2*n_times] trajectory stream (consumed 1 or 2 per jump test);
+        sample_uniforms: [B, n_times, 2] per-timestep measurement streams (order 2).  Returns (results [B, n_obs, T],
+        diagnostics [B, 3, T]) as device tensors."""
+        p = self.p
+        nt = p.n_times
+        ncol = nt if p.sample_timesteps else 1
+        nobs = len(self.observables)
+        results = torch.zeros((self.B, nobs, ncol), dtype=torch.float64, device=self.dev)
+        diag = torch.zeros((self.B, 3, ncol), dtype=torch.float64, device=self.dev)
+        self._pos = torch.zeros(self.B, dtype=torch.int64, device=self.dev)
+        self._traj_u = traj_uniforms
+
+        def record(state, col):
+            diag[:, :, col] = self.diagnostics(state)
+            if nobs:
+                results[:, :, col] = self.evaluate_observables(state)
+
+        def traj_jump_test(state, tag):
+            if self.noise is None:
+                self.stochastic_process(state, p.dt, None, None, log, tag)
+                return
+            u1 = self._traj_u.gather(1, self._pos[:, None]).squeeze(1)
+            u2 = self._traj_u.gather(1, (self._pos + 1)[:, None]).squeeze(1)
+            jm = self.stochastic_process(state, p.dt, u1, u2, log, tag)
+            self._pos += 1 + jm.to(torch.int64)
+
+        phi = self.phi
+        if p.order == 2:
+            psi = self.psi
+
+            def sample(j):
+                psi.copy_from(phi)
+                self.tdvp(psi)
+                self.apply_dissipation(psi, p.dt / 2)
+                if self.noise is None:
+                    self.stochastic_process(psi, p.dt, None, None, log, f"sample{j}")
+                else:
+                    self.stochastic_process(psi, p.dt, sample_uniforms[:, j, 0].contiguous(), sample_uniforms[:, j, 1].contiguous(), log, f"sample{j}")
+                record(psi, j if p.sample_timesteps else 0)
+
+            if nt == 1 or p.sample_timesteps:
+                record(phi, 0)
+            if nt == 1:
+                return results, diag
+            self.apply_dissipation(phi, p.dt / 2)           # initialize (:86-108)
+            traj_jump_test(phi, "init")
+            if p.sample_timesteps or nt == 2:
+                sample(1)
+            for j in range(2, nt):
+                self.tdvp(phi)                              # step_through (:111-140)
+                self.apply_dissipation(phi, p.dt)
+                traj_jump_test(phi, f"step{j}")
+                if p.sample_timesteps or j == nt - 1:
+                    sample(j)
+            return results, diag
+        # first-order scheme (:369-462)
+        if p.sample_timesteps:
+            record(phi, 0)
+        for j in range(1, nt):
+            self.tdvp(phi)
+            if self.noise is not None:
+                self.apply_dissipation(phi, p.dt)
+                traj_jump_test(phi, f"step{j}")
+            if p.sample_timesteps or j == nt - 1:
+                record(phi, j if p.sample_timesteps else 0)
+        if not p.sample_timesteps and nt <= 1:
+            record(phi, 0)
+        return results, diag
