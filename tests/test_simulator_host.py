@@ -1,0 +1,136 @@
+"""-m "not gpu": the public Simulator surface (validation, noise sampling, observable ordering, Result assembly, trajectory
+sharding over torch.distributed) with the numpy kernel twin injected in place of the CUDA library."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+from oracle.np_kernels import NumpyKernels
+from yaqs_b200 import AnalogSimParams, Hamiltonian, MPO, NoiseModel, Observable, Simulator, State, X, Z, ZZ
+from yaqs_b200.simulator import shard_range
+
+REF_GOLDEN_Z = [0.748947146695782, 0.8720515025769692, 0.8652609567462763, 0.8673233347433466, 0.6872036335377433]
+
+
+def _golden_run(**kw):
+    length = 5
+    sp = AnalogSimParams(observables=[Observable(Z(), s) for s in range(length)], elapsed_time=1, dt=0.1, num_traj=10, max_bond_dim=4,
+                         svd_threshold=1e-6, order=2, sample_timesteps=False, random_seed=42)
+    noise = NoiseModel([{"name": n, "sites": [i], "strength": 0.1} for i in range(length) for n in ["lowering", "pauli_z"]])
+    return Simulator(show_progress=False, kernels=NumpyKernels(), **kw).run(State(length, initial="zeros"), Hamiltonian.ising(length, J=1, g=0.5),
+                                                                          sp, noise), sp
+
+
+def test_reference_golden_through_simulator():
+    """The reference's own seeded test (tests/test_simulator.py:159-207, atol there 2e-4) through our public API."""
+    res, sp = _golden_run()
+    got = np.array([res.expectation_values[i][0] for i in range(5)])
+    assert np.max(np.abs(got - REF_GOLDEN_Z)) < 1e-10
+    assert all(len(t) == sp.num_traj for t in res.trajectories)
+    assert res.times.shape == (1,) and res.max_bond.shape == (1,)
+
+
+def test_waves_do_not_change_results():
+    a, _ = _golden_run()
+    b, _ = _golden_run(batch_size=3)
+    for x, y in zip(a.trajectories, b.trajectories):
+        assert np.array_equal(x, y)
+
+
+def test_user_order_and_two_site_observables():
+    length = 4
+    obs = [Observable(ZZ(), [1, 2]), Observable(X(), 3), Observable(Z(), 0), Observable("x", 0)]
+    sp = AnalogSimParams(observables=obs, elapsed_time=0.2, dt=0.1, max_bond_dim=4, order=1)
+    res = Simulator(kernels=NumpyKernels()).run(State(length, initial="x+"), Hamiltonian.ising(length, 1.0, 0.5), sp)
+    assert len(res.trajectories[0]) == 1            # noise-free => a single trajectory (simulator.py:1549-1555)
+    import scipy.linalg
+    h = MPO.ising(length, 1.0, 0.5).to_matrix()
+    psi0 = np.ones(2 ** length) / 4.0
+    zz, x, z = np.kron(np.diag([1, -1]), np.diag([1, -1])), np.array([[0, 1], [1, 0]]), np.diag([1.0, -1.0])
+    full = [np.kron(np.kron(np.eye(2), zz), np.eye(2)), np.kron(np.eye(8), x), np.kron(z, np.eye(8)), np.kron(x, np.eye(8))]
+    for col, t in enumerate(sp.times):
+        psi = scipy.linalg.expm(-1j * t * h) @ psi0
+        for k, op in enumerate(full):
+            assert abs(res.expectation_values[k][col] - np.vdot(psi, op @ psi).real) < 5e-5
+
+
+def test_mpo_factories_match_dense():
+    z, x, y, i2 = np.diag([1.0, -1.0]), np.array([[0, 1.0], [1, 0]]), np.array([[0, -1j], [1j, 0]]), np.eye(2)
+
+    def emb(op, site, n):
+        out = np.eye(1)
+        for s in range(n):
+            out = np.kron(out, op if s == site else i2)
+        return out
+
+    n = 4
+    h = sum(-1.3 * emb(z, s, n) @ emb(z, s + 1, n) for s in range(n - 1)) + sum(-0.7 * emb(x, s, n) for s in range(n))
+    assert np.allclose(MPO.ising(n, 1.3, 0.7).to_matrix(), h)
+    hp = h - 1.3 * emb(z, n - 1, n) @ emb(z, 0, n)
+    assert np.allclose(MPO.ising(n, 1.3, 0.7, bc="periodic").to_matrix(), hp)
+    hh = sum(-(0.5 * emb(x, s, n) @ emb(x, s + 1, n) + 0.8 * emb(y, s, n) @ emb(y, s + 1, n) + 1.1 * emb(z, s, n) @ emb(z, s + 1, n))
+             for s in range(n - 1)) + sum(-0.3 * emb(z, s, n) for s in range(n))
+    assert np.allclose(MPO.heisenberg(n, 0.5, 0.8, 1.1, 0.3).to_matrix(), hh)
+
+
+def test_validation_errors_match_reference():
+    with pytest.raises(ValueError, match="integer multiple of dt"):
+        AnalogSimParams(elapsed_time=0.25, dt=0.1)
+    with pytest.raises(ValueError, match="Unknown noise operator"):
+        NoiseModel([{"name": "bogus", "sites": [0], "strength": 0.1}])
+    with pytest.raises(ValueError, match="nonnegative"):
+        NoiseModel([{"name": "lowering", "sites": [0], "strength": -0.1}])
+    with pytest.raises(ValueError, match="No output specified"):
+        Simulator(kernels=NumpyKernels()).run(State(3), Hamiltonian.ising(3, 1, 1), AnalogSimParams())
+    sp = AnalogSimParams(observables=[Observable(Z(), 0)], get_state=True)
+    with pytest.raises(ValueError, match="Cannot return state in noisy"):
+        Simulator(kernels=NumpyKernels()).run(State(3), Hamiltonian.ising(3, 1, 1), sp, NoiseModel([{"name": "lowering", "sites": [0], "strength": 0.1}]))
+
+
+def test_product_without_cuda_fails_loudly():
+    """No CPU fallback: without a CUDA device the default backend must raise, not degrade."""
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    from yaqs_b200.kernels import KernelError
+    sp = AnalogSimParams(observables=[Observable(Z(), 0)])
+    with pytest.raises(KernelError):
+        Simulator().run(State(3), Hamiltonian.ising(3, 1, 1), sp)
+
+
+def test_shard_range_partitions():
+    for n in (0, 1, 7, 4096):
+        for w in (1, 2, 3, 8):
+            ids = [i for r in range(w) for i in shard_range(n, r, w)]
+            assert ids == list(range(n))
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    import torch.distributed as dist
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        res, _ = _golden_run()
+        if rank == 0:
+            out.put((np.array([res.expectation_values[i][0] for i in range(5)]), np.stack([t[:, 0] for t in res.trajectories])))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_gloo_sharding_matches_single_process():
+    """N > 1 path on CPU (gloo, world_size 2): trajectories are sharded by index range, sums combined by one all-reduce."""
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    means, traj = q.get(timeout=600)
+    for p in procs:
+        p.join(timeout=600)
+        assert p.exitcode == 0
+    single, _ = _golden_run()
+    assert np.max(np.abs(means - REF_GOLDEN_Z)) < 1e-10
+    assert np.array_equal(traj, np.stack([t[:, 0] for t in single.trajectories]))

@@ -1,0 +1,280 @@
+"""Host-side containers that materialise the inputs of a run: MPS, MPO, State, Hamiltonian, Result.
+
+These are the drop-in counterparts of the reference's data structures for ``representation="mps"``:
+  MPS          core/data_structures/mps.py:54-301,409-452,815-839   (tensors (s, l, r), presets, pad, normalize)
+  MPO          core/data_structures/mpo.py:41-50,248-404,1146-1170  (tensors (s_out, s_in, l, r); ising / heisenberg / pauli / custom)
+  State        core/data_structures/state.py:35-60
+  Hamiltonian  core/data_structures/hamiltonian.py:36-441
+  Result       core/data_structures/result.py:155-189
+They run once per ``Simulator.run`` on the host (numpy); the device only consumes their tensors.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+import numpy as np
+
+C = np.complex128
+_PAULI = {
+    "I": np.eye(2, dtype=C), "X": np.array([[0, 1], [1, 0]], dtype=C),
+    "Y": np.array([[0, -1j], [1j, 0]], dtype=C), "Z": np.array([[1, 0], [0, -1]], dtype=C),
+}
+_PRESETS = {
+    "zeros": [1, 0], "ones": [0, 1],
+    "x+": [1 / np.sqrt(2), 1 / np.sqrt(2)], "x-": [1 / np.sqrt(2), -1 / np.sqrt(2)],
+    "y+": [1 / np.sqrt(2), 1j / np.sqrt(2)], "y-": [1 / np.sqrt(2), -1j / np.sqrt(2)],
+}
+
+
+class MPS:
+    """Matrix product state on the host: list of (s, l, r) complex128 tensors + tracked orthogonality centre."""
+
+    def __init__(self, length: int, tensors=None, physical_dimensions=None, state: str = "zeros", pad: int | None = None,
+                 basis_string: str | None = None) -> None:
+        if length <= 0:
+            raise ValueError("length must be a positive integer.")
+        self.length = length
+        dims = physical_dimensions if physical_dimensions is not None else [2] * length
+        if isinstance(dims, int):
+            dims = [dims] * length
+        if any(d != 2 for d in dims):
+            raise NotImplementedError("the B200 TJM path supports qubits (d = 2) only")
+        self.physical_dimensions = list(dims)
+        self.flipped = False
+        self.orthogonality_center: int | None
+        if tensors is not None:
+            if len(tensors) != length:
+                raise ValueError("Number of tensors must match the chain length.")
+            self.tensors = [np.asarray(t, dtype=C) for t in tensors]
+            self.orthogonality_center = None
+            self.normalize()
+            return
+        self.tensors = []
+        if state == "haar-random":
+            chi = 1 if pad is None else pad
+            rng = np.random.default_rng()
+            bonds = [1] + [min(chi, 2 ** min(i + 1, length - 1 - i)) for i in range(length - 1)] + [1]
+            self.tensors = [(rng.standard_normal((2, bonds[i], bonds[i + 1])) + 1j * rng.standard_normal((2, bonds[i], bonds[i + 1]))).astype(C)
+                            for i in range(length)]
+            self.orthogonality_center = None
+            self.normalize()
+            return
+        if state == "basis":
+            if basis_string is None or len(basis_string) != length:
+                raise ValueError("basis_string must be provided with one character per site for 'basis' initialization.")
+        for i in range(length):
+            if state in _PRESETS:
+                v = _PRESETS[state]
+            elif state == "Neel":
+                v = [1, 0] if i % 2 else [0, 1]
+            elif state == "wall":
+                v = [1, 0] if i < length // 2 else [0, 1]
+            elif state == "basis":
+                v = [1, 0] if basis_string[i] == "0" else [0, 1]
+            elif state == "random":
+                r = np.random.default_rng().random()
+                v = [r, 1 - r]
+            else:
+                raise ValueError("Invalid state string")
+            self.tensors.append(np.asarray(v, dtype=C).reshape(2, 1, 1))
+        self.orthogonality_center = 0
+        if state == "random":
+            self.normalize()
+        if pad is not None:
+            self.pad_bond_dimension(pad)
+
+    # mps.py:815-839 with QR: right-canonical form, centre 0, unit norm
+    def normalize(self) -> None:
+        t = self.tensors
+        for i in reversed(range(1, self.length)):
+            d, l, r = t[i].shape
+            q, rm = np.linalg.qr(np.ascontiguousarray(t[i].transpose(0, 2, 1)).reshape(d * r, l))
+            t[i] = q.reshape(d, r, q.shape[1]).transpose(0, 2, 1)
+            t[i - 1] = np.einsum("slj,kj->slk", t[i - 1], rm)
+        nrm = np.linalg.norm(t[0])
+        if nrm > 0:
+            t[0] = t[0] / nrm
+        self.orthogonality_center = 0
+
+    def pad_bond_dimension(self, target_dim: int) -> None:
+        """mps.py:409-452."""
+        n = self.length
+        for i, t in enumerate(self.tensors):
+            d, l, r = t.shape
+            lt = 1 if i == 0 else min(target_dim, 2 ** min(i, n - i))
+            rt = 1 if i == n - 1 else min(target_dim, 2 ** min(i + 1, n - 1 - i))
+            if l > lt or r > rt:
+                raise ValueError("Target bond dim must be at least current bond dim.")
+            new = np.zeros((d, lt, rt), dtype=C)
+            new[:, :l, :r] = t
+            self.tensors[i] = new
+        self.normalize()
+
+    def to_vector(self) -> np.ndarray:
+        acc = self.tensors[0][:, 0, :]
+        for t in self.tensors[1:]:
+            acc = np.einsum("sr,prq->spq", acc, t).reshape(-1, t.shape[2])
+        return acc[:, 0]
+
+
+class MPO:
+    """Matrix product operator: tensors (s_out, s_in, l, r).  Factories build the operator with an exact finite-state
+    construction (bond dimension 2 + number of two-body terms); the reference reaches the same operator through an FSM +
+    SVD compression (mpo.py:1171-1423), i.e. a different MPO gauge with identical H."""
+
+    def __init__(self) -> None:
+        self.tensors: list[np.ndarray] = []
+        self.length = 0
+        self.physical_dimension = 2
+
+    @classmethod
+    def custom(cls, tensors) -> "MPO":
+        m = cls()
+        m.tensors = [np.asarray(t, dtype=C) for t in tensors]
+        m.length = len(m.tensors)
+        for t in m.tensors:
+            if t.ndim != 4 or t.shape[0] != 2 or t.shape[1] != 2:
+                raise ValueError("MPO tensors must have shape (2, 2, Dl, Dr)")
+        return m
+
+    @classmethod
+    def pauli(cls, *, length: int, two_body=None, one_body=None, bc: str = "open", **_unused) -> "MPO":
+        """H = sum_i sum_k c_k A_k(i) B_k(i+1) + sum_i sum_m c_m P_m(i)   (mpo.py:248-325)."""
+        if bc not in ("open", "periodic"):
+            raise ValueError("bc must be 'open' or 'periodic'")
+        two = [(complex(c), _PAULI[a.upper()], _PAULI[b.upper()]) for c, a, b in (two_body or []) if c != 0]
+        one = sum((complex(c) * _PAULI[p.upper()] for c, p in (one_body or [])), np.zeros((2, 2), dtype=C))
+        nt = len(two)
+        periodic = bc == "periodic" and length > 2 and nt > 0
+        dim = 2 + nt + (nt if periodic else 0)
+        last = dim - 1
+        w = np.zeros((dim, dim, 2, 2), dtype=C)
+        w[0, 0] = _PAULI["I"]
+        w[last, last] = _PAULI["I"]
+        w[last, 0] = one
+        for k, (c, a, b) in enumerate(two):
+            w[1 + k, 0] = b
+            w[last, 1 + k] = c * a
+            if periodic:                       # channel carrying B_k(0) through the chain to c_k A_k(L-1)
+                w[1 + nt + k, 1 + nt + k] = _PAULI["I"]
+        tensors = []
+        for i in range(length):
+            if length == 1:
+                t = w[last:last + 1, 0:1].copy()
+            elif i == 0:
+                t = w[last:last + 1, :].copy()
+                if periodic:
+                    for k, (c, a, b) in enumerate(two):
+                        t[0, 1 + nt + k] = b
+            elif i == length - 1:
+                t = w[:, 0:1].copy()
+                if periodic:
+                    for k, (c, a, b) in enumerate(two):
+                        t[1 + nt + k, 0] = c * a
+            else:
+                t = w
+            tensors.append(np.ascontiguousarray(t.transpose(2, 3, 0, 1)))
+        return cls.custom(tensors)
+
+    @classmethod
+    def ising(cls, length: int, J: float, g: float, *, bc: str = "open", **kw) -> "MPO":   # noqa: N803
+        """-J sum Z Z - g sum X   (mpo.py:327-364)."""
+        return cls.pauli(length=length, two_body=[(-J, "Z", "Z")], one_body=[(-g, "X")], bc=bc)
+
+    @classmethod
+    def heisenberg(cls, length: int, Jx: float, Jy: float, Jz: float, h: float = 0.0, *, bc: str = "open", **kw) -> "MPO":   # noqa: N803
+        """-(Jx XX + Jy YY + Jz ZZ) - h sum Z   (mpo.py:366-404)."""
+        return cls.pauli(length=length, two_body=[(-Jx, "X", "X"), (-Jy, "Y", "Y"), (-Jz, "Z", "Z")],
+                         one_body=[(-h, "Z")] if h != 0 else [], bc=bc)
+
+    def to_matrix(self) -> np.ndarray:
+        acc = self.tensors[0][:, :, 0, :]
+        for w in self.tensors[1:]:
+            acc = np.einsum("oir,pqrs->opiqs", acc, w)
+            s = acc.shape
+            acc = acc.reshape(s[0] * s[1], s[2] * s[3], s[4])
+        return acc[:, :, 0]
+
+
+class State:
+    """Initial state specification for ``Simulator.run`` (state.py:35-60); only ``representation="mps"`` is in scope."""
+
+    def __init__(self, length: int | None = None, *, initial: str = "zeros", representation: str | None = None,
+                 physical_dimensions=None, tensors=None, vector=None, density_matrix=None, pad: int | None = None,
+                 basis_string: str | None = None, seed: int | None = None) -> None:
+        if length is not None and length <= 0:
+            raise ValueError("length must be a positive integer.")
+        if sum(x is not None for x in (tensors, vector, density_matrix)) > 1:
+            raise ValueError("Specify at most one of tensors, vector, and density_matrix.")
+        if vector is not None or density_matrix is not None or (representation not in (None, "mps")):
+            raise NotImplementedError("the B200 TJM path takes representation='mps' states only (vector / density-matrix "
+                                      "backends are outside SURVEY.md section 8)")
+        self.representation = "mps"
+        self.initial, self.pad, self.basis_string, self.seed = initial, pad, basis_string, seed
+        if tensors is not None:
+            if len(tensors) == 0:
+                raise ValueError("tensors must be a non-empty list of MPS cores.")
+            if length is not None and length != len(tensors):
+                raise ValueError(f"length={length} does not match len(tensors)={len(tensors)}.")
+            self.length = len(tensors)
+            self.mps = MPS(self.length, tensors=tensors)
+        else:
+            if length is None:
+                raise ValueError("length is required for preset states.")
+            self.length = length
+            self.mps = MPS(length, state=initial, pad=pad, basis_string=basis_string, physical_dimensions=physical_dimensions)
+        self.physical_dimensions = self.mps.physical_dimensions
+
+
+class Hamiltonian:
+    """Analog operator wrapper (hamiltonian.py:36-441): factories delegate to :class:`MPO`."""
+
+    def __init__(self, mpo: MPO) -> None:
+        self._mpo = mpo
+        self.length = mpo.length
+        self.is_piecewise = False
+
+    @classmethod
+    def from_mpo(cls, mpo: MPO) -> "Hamiltonian":
+        return cls(mpo)
+
+    @classmethod
+    def ising(cls, length: int, J: float, g: float, **kw) -> "Hamiltonian":   # noqa: N803
+        return cls(MPO.ising(length, J, g, **kw))
+
+    @classmethod
+    def heisenberg(cls, length: int, Jx: float, Jy: float, Jz: float, h: float = 0.0, **kw) -> "Hamiltonian":   # noqa: N803
+        return cls(MPO.heisenberg(length, Jx, Jy, Jz, h, **kw))
+
+    @classmethod
+    def pauli(cls, **kw) -> "Hamiltonian":
+        return cls(MPO.pauli(**kw))
+
+    def ensure_mpo(self) -> "Hamiltonian":
+        return self
+
+    @property
+    def mpo(self) -> MPO:
+        return self._mpo
+
+    def to_matrix(self) -> np.ndarray:
+        return self._mpo.to_matrix()
+
+
+@dataclass
+class Result:
+    """Outputs of ``Simulator.run`` (result.py:155-189): rows follow the user's observable order."""
+    sim_params: object = None
+    observables: list = field(default_factory=list)
+    expectation_values: list = field(default_factory=list)
+    trajectories: list = field(default_factory=list)
+    times: np.ndarray | None = None
+    runtime_cost: np.ndarray | None = None
+    max_bond: np.ndarray | None = None
+    total_bond: np.ndarray | None = None
+    noise_model: object = None
+    output_state: object = None
+    measurements: list = field(default_factory=list)
+    counts: dict | None = None
+    status: np.ndarray | None = None          # per-trajectory device status words (0 = clean)
+    stats: dict | None = None                 # engine counters (matvecs, Krylov calls, SVD sweeps, kernel launches)

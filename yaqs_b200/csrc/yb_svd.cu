@@ -68,9 +68,14 @@ __device__ __forceinline__ int jacobi_pair(cplx* wi, cplx* wj, int len, cplx* qi
     a = warp_sum(a); bb = warp_sum(bb); cr = warp_sum(cr); ci = warp_sum(ci);
     const double c2 = cr * cr + ci * ci;
     if (!(c2 > tol2 * a * bb) || c2 == 0.0) return 0;
+    // A row whose norm is below eps times its partner's is rounding residue of earlier rotations (rank-deficient input):
+    // orthogonalising it again only produces residue of residue (1e-16 -> 1e-32 -> ...), so it is deflated here.  Its
+    // singular value stays <= eps * sigma_max, i.e. within the absolute accuracy zgesdd gives the reference.
+    constexpr double EPS2 = 2.220446049250313e-16 * 2.220446049250313e-16;
+    if (a < EPS2 * bb || bb < EPS2 * a) return 0;
     const double absc = sqrt(c2);
     const double zeta = (bb - a) / (2.0 * absc);
-    const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+    const double t = fabs(zeta) > 1e100 ? 0.5 / zeta : copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
     const double cs = 1.0 / sqrt(1.0 + t * t), sn = cs * t;
     // wj~ = conj(e) wj with e = c/|c|;  wi' = cs wi - sn wj~ ;  wj' = sn wi + cs wj~
     const double er = cr / absc, ei = -ci / absc;     // conj(e)
@@ -253,7 +258,7 @@ __global__ void __launch_bounds__(512) k_svd_finalize(int trunc_mode, double thr
         for (int i = 0; i < k; ++i) bad |= !isfinite(ssort[i]);
         if (bad || !m[5]) atomicOr(&status[b], bad ? 2 : 1);       // 2: non-finite, 1: Jacobi not converged
         int nd = 0;
-        const double tiny = ssort[0] * 1e-290;
+        const double tiny = ssort[0] * 4.5e-16;
         for (int i = 0; i < s_keep; ++i) nd += !(ssort[i] > tiny);
         s_ndef = nd;
         keep_out[(long long)b * keep_stride] = s_keep;
@@ -263,7 +268,7 @@ __global__ void __launch_bounds__(512) k_svd_finalize(int trunc_mode, double thr
     for (int i = tid; i < k; i += blockDim.x) sval[(long long)b * s_s + i] = ssort[i];
     cplx* ub = uout + (long long)b * s_u;    // rows x keep
     cplx* vb = vout + (long long)b * s_v;    // keep x cols
-    const double tiny = ssort[0] * 1e-290;
+    const double tiny = ssort[0] * 4.5e-16;        // deflated rows (see jacobi_pair) count as exact zeros
     // Q-side factor (exactly unitary rows of Q) and W-side factor (rows of W / sigma)
     if (orient == 0) {
         // U[:, c] = conj(Q[perm c, :]) * f ;  Vh[c, :] = W[perm c, :] * (g / sigma)

@@ -576,14 +576,14 @@ class BatchedTJM:
         for i in reversed(range(n)):
             op1, scalar2, pair = facs[i]
             if op1 is not None:
-                op_t = torch.from_numpy(np.ascontiguousarray(op1).reshape(-1)).to(self.dev)
+                op_t = torch.from_numpy(np.ascontiguousarray(op1, dtype=np.complex128).reshape(-1)).to(self.dev)
                 K.apply_local_op(B, None, None, 0, st.ext(i), st.ext(i + 1), d, op_t, 0, st.site(i), lay.cap[i] * lay.cap[i + 1])
             if scalar2 is not None:
                 op_t = torch.from_numpy((scalar2 * np.eye(2, dtype=np.complex128)).reshape(-1)).to(self.dev)
                 K.apply_local_op(B, None, None, 0, st.ext(i), st.ext(i + 1), d, op_t, 0, st.site(i), lay.cap[i] * lay.cap[i + 1])
             if pair is not None:
                 th = self.merge(st, i - 1)
-                op_t = torch.from_numpy(np.ascontiguousarray(pair).reshape(-1)).to(self.dev)
+                op_t = torch.from_numpy(np.ascontiguousarray(pair, dtype=np.complex128).reshape(-1)).to(self.dev)
                 K.apply_local_op(B, None, None, 0, st.ext(i - 1), st.ext(i + 1), d * d, op_t, 0, th, lay.cap[i - 1] * lay.cap[i + 1])
                 self.split_theta(st, i - 1, "right", user)
             if i != 0:

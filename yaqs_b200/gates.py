@@ -1,0 +1,171 @@
+"""Observable / gate library: the matrices the device consumes as 2x2 / 4x4 constants.
+
+Mirrors the part of the reference's ``GateLibrary`` (core/libraries/gate_library.py:129-2048) that the TJM path needs:
+named one- and two-qubit gates with ``.name``, ``.matrix``, ``.interaction``, ``.sites`` / ``set_sites`` and, for the
+rotation gates, the product-form generator used by TDVP gate windows.  Matrix conventions follow the reference
+(qiskit little-endian remaps are handled where gates are applied, mpo_utils.py:104-160).
+"""
+from __future__ import annotations
+
+import copy
+
+import numpy as np
+
+C = np.complex128
+_I = np.eye(2, dtype=C)
+_X = np.array([[0, 1], [1, 0]], dtype=C)
+_Y = np.array([[0, -1j], [1j, 0]], dtype=C)
+_Z = np.array([[1, 0], [0, -1]], dtype=C)
+
+
+class BaseGate:
+    """gate_library.py:129-567 (the fields the hot path reads)."""
+
+    name = "custom"
+    interaction = 1
+
+    def __init__(self, matrix: np.ndarray, name: str | None = None, interaction: int | None = None) -> None:
+        self.matrix = np.asarray(matrix, dtype=C)
+        if name is not None:
+            self.name = name
+        n = int(round(np.log2(self.matrix.shape[0])))
+        self.interaction = interaction if interaction is not None else n
+        self.sites: list[int] | None = None
+        self.generator = None
+
+    @property
+    def tensor(self) -> np.ndarray:
+        if self.interaction == 1:
+            return self.matrix
+        return self.matrix.reshape(2, 2, 2, 2)
+
+    def set_sites(self, *sites) -> None:
+        flat: list[int] = []
+        for s in sites:
+            if isinstance(s, (list, tuple)):
+                flat.extend(int(v) for v in s)
+            else:
+                flat.append(int(s))
+        if len(flat) != self.interaction:
+            raise ValueError(f"Number of sites {len(flat)} must be equal to the interaction level {self.interaction}")
+        self.sites = flat
+
+    def dag(self) -> "BaseGate":
+        g = copy.deepcopy(self)
+        g.matrix = self.matrix.conj().T.copy()
+        return g
+
+
+def _fixed(name: str, matrix, interaction: int | None = None):
+    def factory() -> BaseGate:
+        return BaseGate(np.array(matrix, dtype=C), name=name, interaction=interaction)
+    factory.__name__ = name
+    return factory
+
+
+def _rot(axis: np.ndarray):
+    def mat(theta: float) -> np.ndarray:
+        return np.cos(theta / 2) * _I - 1j * np.sin(theta / 2) * axis
+    return mat
+
+
+def _rot2(pa: np.ndarray, pb: np.ndarray):
+    def mat(theta: float) -> np.ndarray:
+        return np.cos(theta / 2) * np.eye(4, dtype=C) - 1j * np.sin(theta / 2) * np.kron(pa, pb)
+    return mat
+
+
+class GateLibrary:
+    """Namespace of gate factories; ``getattr(GateLibrary, name)`` resolves names as in the reference
+    (gate_library.py:1996-2048)."""
+
+    x = staticmethod(_fixed("x", _X))
+    y = staticmethod(_fixed("y", _Y))
+    z = staticmethod(_fixed("z", _Z))
+    id = staticmethod(_fixed("id", _I))
+    h = staticmethod(_fixed("h", np.array([[1, 1], [1, -1]]) / np.sqrt(2)))
+    sx = staticmethod(_fixed("sx", 0.5 * np.array([[1 + 1j, 1 - 1j], [1 - 1j, 1 + 1j]])))
+    s = staticmethod(_fixed("s", np.array([[1, 0], [0, 1j]])))
+    sdg = staticmethod(_fixed("sdg", np.array([[1, 0], [0, -1j]])))
+    t = staticmethod(_fixed("t", np.array([[1, 0], [0, np.exp(1j * np.pi / 4)]])))
+    tdg = staticmethod(_fixed("tdg", np.array([[1, 0], [0, np.exp(-1j * np.pi / 4)]])))
+    p0 = staticmethod(_fixed("p0", np.array([[1, 0], [0, 0]])))
+    p1 = staticmethod(_fixed("p1", np.array([[0, 0], [0, 1]])))
+    destroy = staticmethod(_fixed("destroy", np.array([[0, 1], [0, 0]])))
+    create = staticmethod(_fixed("create", np.array([[0, 0], [1, 0]])))
+    xx = staticmethod(_fixed("xx", np.kron(_X, _X)))
+    yy = staticmethod(_fixed("yy", np.kron(_Y, _Y)))
+    zz = staticmethod(_fixed("zz", np.kron(_Z, _Z)))
+    cx = staticmethod(_fixed("cx", np.array([[1, 0, 0, 0], [0, 1, 0, 0], [0, 0, 0, 1], [0, 0, 1, 0]])))
+    cz = staticmethod(_fixed("cz", np.diag([1, 1, 1, -1])))
+    swap = staticmethod(_fixed("swap", np.array([[1, 0, 0, 0], [0, 0, 1, 0], [0, 1, 0, 0], [0, 0, 0, 1]])))
+
+    @staticmethod
+    def local(matrix) -> BaseGate:
+        m = np.asarray(matrix, dtype=C)
+        if m.ndim != 2 or m.shape[0] != m.shape[1]:
+            raise ValueError("local observable must be a square matrix")
+        return BaseGate(m, name="local", interaction=1)
+
+    @staticmethod
+    def rx(theta: float) -> BaseGate:
+        g = BaseGate(_rot(_X)(theta), name="rx")
+        g.theta = theta
+        return g
+
+    @staticmethod
+    def ry(theta: float) -> BaseGate:
+        g = BaseGate(_rot(_Y)(theta), name="ry")
+        g.theta = theta
+        return g
+
+    @staticmethod
+    def rz(theta: float) -> BaseGate:
+        g = BaseGate(_rot(_Z)(theta), name="rz")
+        g.theta = theta
+        return g
+
+    @staticmethod
+    def p(theta: float) -> BaseGate:
+        g = BaseGate(np.array([[1, 0], [0, np.exp(1j * theta)]]), name="p")
+        g.theta = theta
+        return g
+
+    @staticmethod
+    def u(theta: float, phi: float, lam: float) -> BaseGate:
+        m = np.array([[np.cos(theta / 2), -np.exp(1j * lam) * np.sin(theta / 2)],
+                      [np.exp(1j * phi) * np.sin(theta / 2), np.exp(1j * (phi + lam)) * np.cos(theta / 2)]])
+        return BaseGate(m, name="u")
+
+    @staticmethod
+    def _two_rot(name: str, pa, pb, theta: float) -> BaseGate:
+        g = BaseGate(_rot2(pa, pb)(theta), name=name, interaction=2)
+        g.theta = theta
+        # exp(-i theta/2 A (x) B): generator factors with theta/2 folded into the first one (gate_library.py:1546,1608,1670)
+        g.generator = [(theta / 2) * pa, pb.copy()]
+        return g
+
+    @staticmethod
+    def rxx(theta: float) -> BaseGate:
+        return GateLibrary._two_rot("rxx", _X, _X, theta)
+
+    @staticmethod
+    def ryy(theta: float) -> BaseGate:
+        return GateLibrary._two_rot("ryy", _Y, _Y, theta)
+
+    @staticmethod
+    def rzz(theta: float) -> BaseGate:
+        return GateLibrary._two_rot("rzz", _Z, _Z, theta)
+
+    @staticmethod
+    def cp(theta: float) -> BaseGate:
+        g = BaseGate(np.diag([1, 1, 1, np.exp(1j * theta)]), name="cp", interaction=2)
+        g.theta = theta
+        return g
+
+
+# Class-style aliases used as ``Observable(Z(), site)`` in the reference's examples and tests.
+X, Y, Z, Id, H = GateLibrary.x, GateLibrary.y, GateLibrary.z, GateLibrary.id, GateLibrary.h
+XX, YY, ZZ = GateLibrary.xx, GateLibrary.yy, GateLibrary.zz
+P0, P1, Destroy, Create = GateLibrary.p0, GateLibrary.p1, GateLibrary.destroy, GateLibrary.create
+Rx, Ry, Rz, Rxx, Ryy, Rzz = GateLibrary.rx, GateLibrary.ry, GateLibrary.rz, GateLibrary.rxx, GateLibrary.ryy, GateLibrary.rzz

@@ -94,6 +94,8 @@ class CudaKernels:
     def _cptr(buf: Buf | None):
         if buf is None:
             return ctypes.c_void_p(0)
+        if buf.tensor.dtype != torch.complex128:
+            raise KernelError(f"complex128 operand expected, got {buf.tensor.dtype}")
         return ctypes.c_void_p(buf.tensor.data_ptr() + 16 * buf.offset)
 
     @staticmethod
@@ -127,6 +129,8 @@ class CudaKernels:
             int(conj_b), int(max_m), int(max_n), self._stream()))
 
     def wapply(self, nbatch, mask, el, er, nx, nu, ny, nv, wt: torch.Tensor, src: Buf, dst: Buf, max_lr):
+        if wt.dtype != torch.complex128:
+            raise KernelError(f"wapply: complex128 MPO tensor expected, got {wt.dtype}")
         self._check(self.lib.yb_wapply(
             nbatch, self._ptr(mask), self._ext(el), self._ext(er), nx, nu, ny, nv, self._ptr(wt), self._cptr(src),
             ctypes.c_int64(src.stride), self._cptr(dst), ctypes.c_int64(dst.stride), int(max_lr), self._stream()))
@@ -184,6 +188,8 @@ class CudaKernels:
                                             ctypes.c_int64(src.stride), self._cptr(dst), ctypes.c_int64(dst.stride), int(max_elems), self._stream()))
 
     def apply_local_op(self, nbatch, mask, sel, sel_value, el, er, dphys, op: torch.Tensor, op_stride, a: Buf, max_lr):
+        if op.dtype != torch.complex128:
+            raise KernelError(f"apply_local_op: complex128 operator expected, got {op.dtype}")
         self._check(self.lib.yb_apply_local_op(nbatch, self._ptr(mask), self._ptr(sel), int(sel_value), self._ext(el), self._ext(er), dphys,
                                                self._ptr(op), ctypes.c_int64(op_stride), self._cptr(a), ctypes.c_int64(a.stride), int(max_lr),
                                                self._stream()))

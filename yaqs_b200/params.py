@@ -1,0 +1,183 @@
+"""Simulation parameters and observables: the configuration surface of the reference, kept name for name.
+
+``Observable``              core/data_structures/simulation_parameters.py:360-416
+observable ordering         :419-456  (workers evaluate in site-sorted order; Result is in user order)
+``SIMULATION_PRESETS``      :46-51
+``AnalogSimParams``         :477-613
+``DigitalSimParams``        :616-750
+"""
+from __future__ import annotations
+
+import copy
+
+import numpy as np
+
+from .gates import BaseGate, GateLibrary
+
+SIMULATION_PRESETS = {
+    "fast": {"svd_threshold": 1e-3, "max_bond_dim": 16, "num_traj": 128, "krylov_tol": 1e-3},
+    "balanced": {"svd_threshold": 1e-6, "max_bond_dim": 128, "num_traj": 256, "krylov_tol": 1e-4},
+    "accurate": {"svd_threshold": 1e-9, "max_bond_dim": 4096, "num_traj": 1024, "krylov_tol": 1e-6},
+    "exact": {"svd_threshold": 1e-13, "max_bond_dim": None, "num_traj": 1024, "krylov_tol": 1e-12},
+}
+_USE_PRESET = object()
+_TRUNC_MODES = ("discarded_weight", "relative", "hard_cutoff", "relative_discarded_weight")
+
+
+class Observable:
+    """What to measure: a gate (or named gate, or raw one-site matrix) and the site(s)."""
+
+    def __init__(self, gate, sites=None, **gate_kwargs) -> None:
+        if isinstance(gate, str):
+            if not hasattr(GateLibrary, gate):
+                raise NotImplementedError(f"observable {gate!r}: only GateLibrary names are supported on the B200 TJM path "
+                                          "(pvm / entropy / schmidt_spectrum are SURVEY.md 8(f) 'next' rows)")
+            resolved = getattr(GateLibrary, gate)(**gate_kwargs)
+        elif isinstance(gate, BaseGate):
+            if gate_kwargs:
+                raise TypeError("Observable parameters are only supported for named observables.")
+            resolved = gate
+        else:
+            if gate_kwargs:
+                raise TypeError("Observable parameters are only supported for named observables.")
+            resolved = GateLibrary.local(gate)
+        self.gate = copy.deepcopy(resolved)
+        assert sites is not None
+        self.sites = sites
+        self.gate.set_sites(self.sites)
+
+
+def prepare_observable_ordering(observables):
+    """Stable sort by first site (:419-456): returns (sorted list, user index -> sorted row)."""
+    if not observables:
+        return [], ()
+    pairs = sorted(enumerate(observables), key=lambda p: ((p[1].sites[0] if isinstance(p[1].sites, list) else p[1].sites), p[0]))
+    user_to_sorted = [0] * len(observables)
+    for row, (user_i, _) in enumerate(pairs):
+        user_to_sorted[user_i] = row
+    return [o for _, o in pairs], tuple(user_to_sorted)
+
+
+class _Ordering:
+    observables: list
+
+    @property
+    def sorted_observables(self):
+        return prepare_observable_ordering(self.observables)[0]
+
+    @property
+    def observable_sorted_indices(self):
+        return prepare_observable_ordering(self.observables)[1]
+
+
+def _validate_seed(seed) -> None:
+    if seed is None:
+        return
+    if isinstance(seed, bool) or not isinstance(seed, int):
+        raise TypeError(f"random_seed must be int or None, got {type(seed).__name__}.")
+    if seed < 0:
+        raise ValueError(f"random_seed must be non-negative, got {seed}.")
+
+
+def _time_grid(elapsed_time, dt) -> int:
+    """:92-160: elapsed_time must be an integer multiple of dt."""
+    for name, v in (("elapsed_time", elapsed_time), ("dt", dt)):
+        if isinstance(v, bool) or not isinstance(v, (int, float, np.floating, np.integer)):
+            raise TypeError(f"{name} must be a real number, got {type(v).__name__}.")
+    e, d = float(elapsed_time), float(dt)
+    if not np.isfinite(e):
+        raise ValueError(f"elapsed_time must be finite, got {elapsed_time!r}.")
+    if not np.isfinite(d):
+        raise ValueError(f"dt must be finite, got {dt!r}.")
+    if d <= 0.0:
+        raise ValueError(f"dt must be positive, got {d}.")
+    if e < 0.0:
+        raise ValueError(f"elapsed_time must be non-negative, got {e}.")
+    if not e > 0.0:
+        return 0
+    n = round(e / d)
+    residual = abs(e - n * d)
+    tol = min(max(np.spacing(e), abs(n) * np.spacing(d), 8 * np.finfo(np.float64).eps * max(e, n * d, d)), 0.25 * d)
+    if n <= 0 or residual > tol:
+        raise ValueError(f"elapsed_time ({e}) must be an integer multiple of dt ({d}); got elapsed_time/dt = {e / d} "
+                         f"(nearest integer {n}, time residual {residual}).")
+    return n
+
+
+def _common(self, preset, num_traj, max_bond_dim, trunc_mode, svd_threshold, krylov_tol, tdvp_sweeps, tdvp_mode, random_seed):
+    _validate_seed(random_seed)
+    if preset not in SIMULATION_PRESETS:
+        raise ValueError(f"preset must be one of {tuple(SIMULATION_PRESETS)!r}, got {preset!r}.")
+    pv = SIMULATION_PRESETS[preset]
+    self.preset = preset
+    self.num_traj = num_traj if num_traj is not None else pv["num_traj"]
+    self.max_bond_dim = pv["max_bond_dim"] if max_bond_dim is _USE_PRESET else max_bond_dim
+    if self.max_bond_dim is not None and (isinstance(self.max_bond_dim, bool) or int(self.max_bond_dim) < 1):
+        raise ValueError(f"max_bond_dim must be a positive int or None, got {self.max_bond_dim!r}.")
+    if trunc_mode not in _TRUNC_MODES:
+        raise ValueError(f"trunc_mode must be one of {_TRUNC_MODES!r}, got {trunc_mode!r}.")
+    self.trunc_mode = trunc_mode
+    thr = float(svd_threshold if svd_threshold is not None else pv["svd_threshold"])
+    if not np.isfinite(thr) or thr < 0.0:
+        raise ValueError(f"svd_threshold must be a finite non-negative float, got {thr!r}.")
+    self.svd_threshold = thr
+    kt = float(krylov_tol if krylov_tol is not None else pv["krylov_tol"])
+    if not np.isfinite(kt) or kt <= 0.0:
+        raise ValueError(f"krylov_tol must be a finite positive float, got {kt!r}.")
+    self.krylov_tol = kt
+    if isinstance(tdvp_sweeps, bool) or not isinstance(tdvp_sweeps, int):
+        raise TypeError(f"tdvp_sweeps must be int, got {type(tdvp_sweeps).__name__}.")
+    if tdvp_sweeps < 1:
+        raise ValueError(f"tdvp_sweeps must be >= 1, got {tdvp_sweeps}.")
+    self.tdvp_sweeps = tdvp_sweeps
+    if tdvp_mode not in ("1site", "2site", "dynamic"):
+        raise ValueError(f"tdvp_mode must be one of ('1site', '2site', 'dynamic'), got {tdvp_mode!r}.")
+    self.tdvp_mode = tdvp_mode
+    self.random_seed = random_seed
+
+
+class AnalogSimParams(_Ordering):
+    """Hamiltonian-evolution parameters (:477-613).  Defaults: order=1, tdvp_mode="2site", preset "balanced"."""
+
+    def __init__(self, observables=None, elapsed_time: float = 0.1, dt: float = 0.1, num_traj: int | None = None,
+                 max_bond_dim=_USE_PRESET, trunc_mode: str = "discarded_weight", svd_threshold: float | None = None,
+                 krylov_tol: float | None = None, order: int = 1, *, preset: str = "balanced", sample_timesteps: bool = True,
+                 evolution_mode: str = "tdvp", get_state: bool = False, random_seed: int | None = None,
+                 multi_time_observables=None, tdvp_sweeps: int = 1, tdvp_mode: str = "2site") -> None:
+        _common(self, preset, num_traj, max_bond_dim, trunc_mode, svd_threshold, krylov_tol, tdvp_sweeps, tdvp_mode, random_seed)
+        self.observables = [] if observables is None else list(observables)
+        n_steps = _time_grid(elapsed_time, dt)
+        self.elapsed_time, self.dt = float(elapsed_time), float(dt)
+        self.times = self.dt * np.arange(n_steps + 1, dtype=np.float64)
+        if n_steps > 0:
+            self.times[-1] = self.elapsed_time
+        self.sample_timesteps = sample_timesteps
+        self.order = order
+        mode = getattr(evolution_mode, "value", evolution_mode)
+        if str(mode).lower() != "tdvp":
+            raise NotImplementedError("evolution_mode=BUG is outside the B200 hot-path scope (SURVEY.md 2.1 #20)")
+        self.evolution_mode = "tdvp"
+        self.get_state = get_state
+        self.multi_time_observables = [] if multi_time_observables is None else list(multi_time_observables)
+
+
+class DigitalSimParams(_Ordering):
+    """Circuit-simulation parameters, keyword-only as in the reference (:616-750)."""
+
+    def __init__(self, *, observables=None, num_traj: int | None = None, max_bond_dim=_USE_PRESET, trunc_mode: str = "discarded_weight",
+                 svd_threshold: float | None = None, krylov_tol: float | None = None, preset: str = "balanced", get_state: bool = False,
+                 sample_layers: bool = False, shots: int | None = None, random_seed: int | None = None, gate_mode: str = "mpo",
+                 tdvp_sweeps: int = 1, tdvp_mode: str = "2site") -> None:
+        _common(self, preset, num_traj, max_bond_dim, trunc_mode, svd_threshold, krylov_tol, tdvp_sweeps, tdvp_mode, random_seed)
+        self.observables = [] if observables is None else list(observables)
+        if gate_mode not in ("tdvp", "full-tdvp", "swaps", "mpo"):
+            raise ValueError(f"gate_mode must be one of ('tdvp', 'full-tdvp', 'swaps', 'mpo'), got {gate_mode!r}.")
+        self.gate_mode = gate_mode
+        self.get_state = get_state
+        self.sample_layers = sample_layers
+        self.shots = shots
+        self.num_mid_measurements = 0
+
+
+StrongSimParams = DigitalSimParams   # pre-0.6 names used by BASELINE.json's north_star (UPGRADING.md:49-60)
+WeakSimParams = DigitalSimParams

@@ -1,0 +1,223 @@
+"""``Simulator.run`` for the TJM hot path: same call, same ``Result`` as the reference, trajectories run as GPU batches.
+
+Reference: ``Simulator`` (simulator.py:1059-1111), ``run`` (:1173-1312), ``_run_analog`` (:1444-1682).  The reference fans
+trajectories out over a fork pool (core/parallel_utils.py:331-390); here ``run`` slices the trajectory index range into
+waves that fit the GPU's HBM, runs every wave as one lock-step batch on the device (``engine.BatchedTJM``) and, when
+``torch.distributed`` is initialised with more than one rank, shards the index range over ranks and combines the
+per-column sums and sample counts with ONE all-reduce (NCCL over NVLink on GPU ranks, gloo in CPU tests).
+"""
+from __future__ import annotations
+
+import math
+from typing import Sequence
+
+import numpy as np
+import torch
+
+from .containers import Hamiltonian, Result, State
+from .engine import BatchedTJM, BatchLayout, EngineParams
+from .noise import NoiseModel
+from .params import AnalogSimParams, DigitalSimParams
+from .rng import make_disorder_rng, numpy_tables, philox_tables
+
+
+def shard_range(n: int, rank: int, world: int) -> range:
+    """Contiguous trajectory-index shard of rank `rank`."""
+    per = math.ceil(n / world) if world > 0 else n
+    return range(min(n, rank * per), min(n, (rank + 1) * per))
+
+
+def validate_noise_model_for_run(noise: NoiseModel, length: int) -> None:
+    """core/data_structures/noise_model.py:668-757 (the MPS-analog checks)."""
+    if noise.scheduled_jumps:
+        raise NotImplementedError("scheduled_jumps are a SURVEY.md 8(f) 'next' row of the B200 path")
+    for pr in noise.processes:
+        for s in pr["sites"]:
+            if s >= length:
+                raise ValueError(f"Noise process '{pr['name']}' acts on site {s} but the chain has {length} sites.")
+        if len(pr["sites"]) == 1 and np.asarray(pr["matrix"]).shape != (2, 2):
+            raise ValueError(f"Noise process '{pr['name']}': one-site matrix must be 2x2 for qubit chains.")
+        if len(pr["sites"]) == 2 and "matrix" in pr and np.asarray(pr["matrix"]).shape != (4, 4):
+            raise ValueError(f"Noise process '{pr['name']}': two-site matrix must be 4x4 for qubit chains.")
+
+
+def bytes_per_trajectory(lay_one: BatchLayout, order: int, one_site: bool) -> int:
+    """Device bytes one trajectory occupies (DESIGN.md 'Data layout in HBM'); used to size waves."""
+    c = 16
+    state = lay_one.state_elems * (2 if order == 2 else 1)
+    env = lay_one.env_elems * (2 if one_site else 1)
+    work = lay_one.theta_slot + 2 * lay_one.t_slot + 26 * lay_one.nloc_max + lay_one.nloc_max + 4 * lay_one.svd_dim ** 2
+    return c * (state + env + work) + 4096
+
+
+class Simulator:
+    """Drop-in for ``mqt.yaqs.Simulator``.  ``parallel`` / ``max_workers`` / ``mp_context`` / retry options are accepted for
+    signature compatibility and ignored: there is no process pool, the batch is the parallelism."""
+
+    def __init__(self, *, parallel: bool = True, max_workers: int | None = None, show_progress: bool = True, mp_context=None,
+                 max_retries: int = 10, retry_exceptions=None, device: str | torch.device | None = None, kernels=None,
+                 batch_size: int | None = None, rng_mode: str = "numpy", collect_log: bool = False) -> None:
+        self.parallel, self.max_workers, self.show_progress = parallel, max_workers, show_progress
+        self.device = device
+        self._kernels = kernels
+        self.batch_size = batch_size
+        if rng_mode not in ("numpy", "philox"):
+            raise ValueError("rng_mode must be 'numpy' (reference-identical seeded streams) or 'philox' (device generator)")
+        self.rng_mode = rng_mode
+        self.collect_log = collect_log
+        self.last_log: list | None = None
+
+    # ------------------------------------------------------------------------------------------------------------------
+    def _get_kernels(self):
+        if self._kernels is None:
+            from .kernels import CudaKernels          # raises when the CUDA library / device is missing: no CPU fallback
+            dev = self.device
+            if dev is None:
+                dev = f"cuda:{torch.cuda.current_device()}" if torch.cuda.is_available() else "cuda:0"
+            self._kernels = CudaKernels(dev)
+        return self._kernels
+
+    def run(self, initial_state: State, operator, sim_params=None, noise_model: NoiseModel | None = None) -> Result:
+        if sim_params is None:
+            raise TypeError("Standalone simulation requires AnalogSimParams or DigitalSimParams.")
+        if not isinstance(sim_params, (AnalogSimParams, DigitalSimParams)):
+            raise TypeError(f"sim_params must be AnalogSimParams or DigitalSimParams, got {type(sim_params).__name__}.")
+        if isinstance(initial_state, list):
+            raise NotImplementedError("list[State] unitary ensembles are outside the B200 hot-path scope (SURVEY.md 2.1 #3)")
+        if not isinstance(initial_state, State):
+            raise TypeError("Analog simulation requires initial_state to be a list or State.")
+        if noise_model is not None:
+            noise_model = noise_model.sample(rng=make_disorder_rng(getattr(sim_params, "random_seed", None)))   # :1269-1271
+        result = Result(sim_params=sim_params, noise_model=noise_model)
+        if isinstance(sim_params, AnalogSimParams):
+            if not sim_params.get_state and not sim_params.observables:
+                raise ValueError("No output specified: either observables or get_state must be set.")
+            if not isinstance(operator, Hamiltonian):
+                raise TypeError("Analog simulation requires a Hamiltonian operator.")
+            self._run_analog(initial_state, operator, sim_params, noise_model, result)
+            return result
+        from .digital import run_digital                # digital TJM (digital/digital_tjm.py:636-749)
+        return run_digital(self, initial_state, operator, sim_params, noise_model, result)
+
+    # ------------------------------------------------------------------------------------------------------------------
+    def _run_analog(self, state: State, ham: Hamiltonian, sp: AnalogSimParams, noise: NoiseModel | None, result: Result) -> None:
+        length = state.length
+        if ham.length != length:
+            raise ValueError("State and Hamiltonian must have the same number of sites.")
+        if noise is not None:
+            validate_noise_model_for_run(noise, length)
+        noiseless = noise is None or all(pr["strength"] == 0 for pr in noise.processes)
+        if noiseless:
+            ntraj = 1                                                                     # :1549-1555
+        else:
+            if sp.get_state:
+                raise ValueError("Cannot return state in noisy analog simulation due to stochastics.")
+            ntraj = sp.num_traj
+        sorted_obs = sp.sorted_observables
+        to_sorted = sp.observable_sorted_indices
+        for o in sorted_obs:
+            if o.gate.interaction not in (1, 2):
+                raise ValueError("Local observable must be one-site or nearest-neighbor two-site.")
+        obs = [(np.asarray(o.gate.matrix, dtype=np.complex128), ([o.sites] if isinstance(o.sites, int) else list(o.sites))) for o in sorted_obs]
+        ep = EngineParams(dt=sp.dt, n_steps=len(sp.times) - 1, order=2 if sp.order != 1 else 1, max_bond_dim=sp.max_bond_dim,
+                          svd_threshold=sp.svd_threshold, trunc_mode=sp.trunc_mode, krylov_tol=sp.krylov_tol, tdvp_mode=sp.tdvp_mode,
+                          tdvp_sweeps=sp.tdvp_sweeps, sample_timesteps=sp.sample_timesteps)
+        procs = noise.processes if noise is not None else None
+        mpo = ham.mpo.tensors
+        init = state.mps.tensors
+        ncol = ep.n_times if ep.sample_timesteps else 1
+
+        import torch.distributed as dist
+        world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        rank = dist.get_rank() if world > 1 else 0
+        mine = shard_range(ntraj, rank, world)
+
+        K = self._get_kernels()
+        dev = K.device
+        res_local = np.zeros((len(mine), len(obs), ncol))
+        diag_local = np.zeros((len(mine), 3, ncol))
+        status_local = np.zeros(len(mine), dtype=np.int32)
+        stats: dict = {}
+        final_tensors = None
+        log_all = [] if self.collect_log else None
+        wave = self._wave_size(len(mine), length, ep, mpo, init, dev)
+        K.launch_count(reset=True)
+        for w0 in range(0, len(mine), max(wave, 1)):
+            idx = list(mine[w0: w0 + wave])
+            eng = BatchedTJM(K, length, len(idx), mpo, ep, procs, obs, init)
+            if self.rng_mode == "numpy":
+                tu, su = numpy_tables(sp.random_seed, idx, ep.n_times, ep.order)
+                tu = torch.from_numpy(tu).to(dev)
+                su = torch.from_numpy(su).to(dev) if su is not None else None
+            else:
+                tu, su = philox_tables(sp.random_seed, idx, ep.n_times, ep.order, dev)
+            log = [] if self.collect_log else None
+            r, dg = eng.run(tu, su, log)
+            res_local[w0: w0 + len(idx)] = r.cpu().numpy()
+            diag_local[w0: w0 + len(idx)] = dg.cpu().numpy()
+            status_local[w0: w0 + len(idx)] = eng.status.cpu().numpy()
+            for k, v in eng.stats.items():
+                stats[k] = stats.get(k, 0) + v
+            if log_all is not None:
+                log_all.append((idx, log))
+            if sp.get_state and noiseless:
+                final_tensors = (eng.psi if ep.order == 2 and ep.n_times > 1 else eng.phi).download(0)
+            del eng
+        stats["kernel_launches"] = K.launch_count()
+        self.last_log = log_all
+
+        # ---- combine: one all-reduce of per-column sums + counts; per-trajectory rows are gathered for Result.trajectories
+        sums = torch.from_numpy(np.concatenate([res_local.sum(axis=0).reshape(-1), diag_local.sum(axis=0).reshape(-1), [float(len(mine))]]))
+        if world > 1:
+            backend = dist.get_backend()
+            buf = sums.to(dev) if backend == "nccl" else sums
+            dist.all_reduce(buf, op=dist.ReduceOp.SUM)
+            sums = buf.cpu()
+            gathered: list = [None] * world
+            dist.all_gather_object(gathered, (list(mine), res_local, diag_local, status_local))
+            res_all = np.zeros((ntraj, len(obs), ncol))
+            diag_all = np.zeros((ntraj, 3, ncol))
+            status_all = np.zeros(ntraj, dtype=np.int32)
+            for ids, r_, d_, s_ in gathered:
+                if len(ids):
+                    res_all[ids], diag_all[ids], status_all[ids] = r_, d_, s_
+        else:
+            res_all, diag_all, status_all = res_local, diag_local, status_local
+        sums = sums.numpy()
+        count = sums[-1]
+        nres = len(obs) * ncol
+        mean_res = (sums[:nres] / count).reshape(len(obs), ncol)
+        mean_diag = (sums[nres: nres + 3 * ncol] / count).reshape(3, ncol)
+
+        # ---- Result in the user's observable order (simulator.py:932-942, result.py:125-138)
+        result.observables = list(sp.observables)
+        result.times = np.asarray(sp.times, dtype=np.float64) if sp.sample_timesteps else np.asarray([sp.elapsed_time], dtype=np.float64)
+        result.trajectories = [res_all[:, to_sorted[i], :].copy() for i in range(len(sp.observables))]
+        result.expectation_values = [mean_res[to_sorted[i]].copy() for i in range(len(sp.observables))]
+        result.runtime_cost, result.max_bond, result.total_bond = mean_diag[0], mean_diag[1], mean_diag[2]
+        result.status = status_all
+        result.stats = stats
+        if final_tensors is not None:
+            result.output_state = State(tensors=final_tensors)
+        if status_all.any():
+            bad = np.nonzero(status_all)[0]
+            raise RuntimeError(f"device status words non-zero for trajectories {bad[:8].tolist()} (bit 1: Jacobi SVD not converged, "
+                               "bit 2: non-finite singular values, bit 4: zero jump weights)")
+
+    def _wave_size(self, n: int, length: int, ep: EngineParams, mpo, init, dev) -> int:
+        if n == 0:
+            return 0
+        if self.batch_size is not None:
+            return max(1, min(n, self.batch_size))
+        init_bonds = [1] * (length + 1)
+        for i, t in enumerate(init):
+            init_bonds[i] = max(init_bonds[i], t.shape[1])
+            init_bonds[i + 1] = max(init_bonds[i + 1], t.shape[2])
+        mpo_bonds = [int(mpo[0].shape[2])] + [int(w.shape[3]) for w in mpo]
+        one = BatchLayout(length, 1, ep.max_bond_dim, mpo_bonds, init_bonds)
+        per = bytes_per_trajectory(one, ep.order, ep.tdvp_mode == "1site")
+        if torch.device(dev).type == "cuda":
+            free, _total = torch.cuda.mem_get_info(dev)
+        else:
+            free = 8 << 30
+        return max(1, min(n, int(0.85 * free // per)))
