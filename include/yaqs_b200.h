@@ -34,6 +34,10 @@ int yb_version(void);
 /* Number of kernels this library has launched since the last call with reset != 0 (bench.py's gpu_launches). */
 int64_t yb_launch_count(int reset);
 
+/* Optional instrumentation: a device uint64 that every contraction CTA increments by the real flops of its tile (8 per
+ * complex multiply-add); NULL (default) disables it.  bench.py uses it for roofline.achieved. */
+void yb_set_flop_counter(void* device_u64);
+
 /* ---- contractions -------------------------------------------------------------------------------------------------
  * One grouped / K-segmented batched complex GEMM; `op` selects the index pattern (enum YbGemmOp in csrc/yb_common.cuh):
  *   0 RCONTRACT  T1[(p,l),(a',r')] = sum_r X[(p,l),r] R[r,(a',r')]          tensordot(ket, right_env, axes=1)     methods/tdvp/primitives.py:105,201

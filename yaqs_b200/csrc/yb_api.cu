@@ -13,6 +13,7 @@
 namespace {
 thread_local char g_err[512] = "";
 std::atomic<long long> g_launches{0};
+unsigned long long* g_flop_counter = nullptr;
 
 int fail(const char* where, cudaError_t e) {
     snprintf(g_err, sizeof(g_err), "%s: %s", where, cudaGetErrorString(e));
@@ -45,6 +46,8 @@ int64_t yb_launch_count(int reset) {
     return v;
 }
 
+void yb_set_flop_counter(void* device_u64) { g_flop_counter = (unsigned long long*)device_u64; }
+
 int yb_gemm(int op, int nbatch, int ngroups, const int32_t* mask, yb_extent e0, yb_extent e1, yb_extent e2, int dphys, int d_left, int d_right,
             const void* a, int64_t stride_a, const void* b, int64_t stride_b, void* c, int64_t stride_c, int conj_b, int max_m, int max_n,
             void* stream) {
@@ -57,6 +60,7 @@ int yb_gemm(int op, int nbatch, int ngroups, const int32_t* mask, yb_extent e0, 
     P.dphys = dphys; P.Dl = d_left; P.Dr = d_right;
     P.A = (const cplx*)a; P.Bm = (const cplx*)b; P.C = (cplx*)c; P.sA = stride_a; P.sB = stride_b; P.sC = stride_c;
     P.conj_extra = conj_b;
+    P.flops = g_flop_counter;
     cudaError_t e = yb_launch_gemm(P, max_m, max_n, (cudaStream_t)stream);
     if (e != cudaSuccess) return fail("yb_gemm", e);
     return done("yb_gemm");

@@ -76,4 +76,5 @@ struct YbGemmParams {
     const cplx* A; const cplx* Bm; cplx* C;
     long long sA, sB, sC; // per-trajectory slot strides (elements)
     int conj_extra;       // != 0: conjugate the B operand in addition to the op's own rule
+    unsigned long long* flops;   // optional device counter: every CTA adds the real flops of its tile (8 per complex MAC)
 };

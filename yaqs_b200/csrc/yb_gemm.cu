@@ -122,6 +122,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm(const YbGemmParams P) {
     const int tiles_m = (d.M + BM - 1) / BM;
     if ((int)blockIdx.x >= tiles_m * tiles_n) return;
     const int m0 = ((int)blockIdx.x / tiles_n) * BM, n0 = ((int)blockIdx.x % tiles_n) * BN;
+    if (P.flops && threadIdx.x == 0)
+        atomicAdd(P.flops, 8ull * (unsigned long long)min(BM, d.M - m0) * (unsigned long long)min(BN, d.N - n0) * (unsigned long long)d.K * d.nseg);
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cplx* As = reinterpret_cast<cplx*>(smem_raw);

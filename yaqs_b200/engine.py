@@ -865,3 +865,18 @@ class BatchedTJM:
         if not p.sample_timesteps and nt <= 1:
             record(phi, 0)
         return results, diag
+
+    def steady_state_step(self, u_traj: torch.Tensor, u_sample: torch.Tensor):
+        """One steady-state sampled time step of the second-order scheme for the whole batch: step_through on the
+        trajectory state (TDVP sweep, dissipation dt, jump test) followed by sample() on a copy (TDVP sweep, dissipation
+        dt/2, jump test, diagnostics + observables) -- analog_tjm.py:111-199,352-360.  u_traj / u_sample: [B, 2] uniforms.
+        Returns (observables [B, n_obs], diagnostics [B, 3]).  Used by bench.py to time exactly one unit of work."""
+        p, phi, psi = self.p, self.phi, self.psi
+        self.tdvp(phi)
+        self.apply_dissipation(phi, p.dt)
+        self.stochastic_process(phi, p.dt, u_traj[:, 0].contiguous(), u_traj[:, 1].contiguous())
+        psi.copy_from(phi)
+        self.tdvp(psi)
+        self.apply_dissipation(psi, p.dt / 2)
+        self.stochastic_process(psi, p.dt, u_sample[:, 0].contiguous(), u_sample[:, 1].contiguous())
+        return self.evaluate_observables(psi), self.diagnostics(psi)

@@ -67,7 +67,7 @@ def load_library() -> ctypes.CDLL:
 
 
 EXPORTED_SYMBOLS = [
-    "yb_last_error", "yb_version", "yb_launch_count", "yb_gemm", "yb_wapply", "yb_env_identity", "yb_lanczos_init",
+    "yb_last_error", "yb_version", "yb_launch_count", "yb_set_flop_counter", "yb_gemm", "yb_wapply", "yb_env_identity", "yb_lanczos_init",
     "yb_lanczos_step", "yb_lanczos_combine", "yb_svd_prepare", "yb_svd_round", "yb_svd_check", "yb_svd_finalize",
     "yb_unpack_vh", "yb_copy_packed", "yb_apply_local_op", "yb_norm2", "yb_scale", "yb_local_rdm",
 ]
@@ -85,6 +85,34 @@ class CudaKernels:
         self.device = torch.device(device if device is not None else "cuda:0")
         if self.device.type != "cuda":
             raise KernelError("yaqs_b200 kernels run on CUDA devices only")
+        self._timed: dict[str, list] | None = None
+        self._flops = None
+
+    # -- instrumentation (bench.py): CUDA events around every launch of a kernel family + on-device flop counter --------
+    def start_timing(self) -> None:
+        self._timed = {}
+        self._flops = torch.zeros(1, dtype=torch.int64, device=self.device)
+        self.lib.yb_set_flop_counter(ctypes.c_void_p(self._flops.data_ptr()))
+
+    def stop_timing(self) -> dict:
+        """Returns {family: {"launches": n, "ms": total}} and "gemm_flops" (algorithmic, counted on the device)."""
+        torch.cuda.synchronize(self.device)
+        self.lib.yb_set_flop_counter(ctypes.c_void_p(0))
+        out = {k: {"launches": len(v), "ms": float(sum(a.elapsed_time(b) for a, b in v))} for k, v in (self._timed or {}).items()}
+        out["gemm_flops"] = int(self._flops.item()) if self._flops is not None else 0
+        self._timed, self._flops = None, None
+        return out
+
+    def _timed_call(self, family: str, fn) -> None:
+        if self._timed is None:
+            fn()
+            return
+        st = torch.cuda.current_stream(self.device)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(st)
+        fn()
+        e1.record(st)
+        self._timed.setdefault(family, []).append((e0, e1))
 
     # -- helpers ------------------------------------------------------------------------------------------------------
     def _stream(self):
@@ -123,17 +151,17 @@ class CudaKernels:
 
     # -- contractions -------------------------------------------------------------------------------------------------
     def gemm(self, op, nbatch, ngroups, mask, e0, e1, e2, dphys, d_left, d_right, a: Buf, b: Buf, c: Buf, conj_b, max_m, max_n):
-        self._check(self.lib.yb_gemm(
+        self._timed_call("gemm", lambda: self._check(self.lib.yb_gemm(
             op, nbatch, ngroups, self._ptr(mask), self._ext(e0), self._ext(e1), self._ext(e2), dphys, d_left, d_right,
             self._cptr(a), ctypes.c_int64(a.stride), self._cptr(b), ctypes.c_int64(b.stride), self._cptr(c), ctypes.c_int64(c.stride),
-            int(conj_b), int(max_m), int(max_n), self._stream()))
+            int(conj_b), int(max_m), int(max_n), self._stream())))
 
     def wapply(self, nbatch, mask, el, er, nx, nu, ny, nv, wt: torch.Tensor, src: Buf, dst: Buf, max_lr):
         if wt.dtype != torch.complex128:
             raise KernelError(f"wapply: complex128 MPO tensor expected, got {wt.dtype}")
-        self._check(self.lib.yb_wapply(
+        self._timed_call("wapply", lambda: self._check(self.lib.yb_wapply(
             nbatch, self._ptr(mask), self._ext(el), self._ext(er), nx, nu, ny, nv, self._ptr(wt), self._cptr(src),
-            ctypes.c_int64(src.stride), self._cptr(dst), ctypes.c_int64(dst.stride), int(max_lr), self._stream()))
+            ctypes.c_int64(src.stride), self._cptr(dst), ctypes.c_int64(dst.stride), int(max_lr), self._stream())))
 
     def env_identity(self, nbatch, mask, echi, dmpo, env: Buf, max_chi):
         self._check(self.lib.yb_env_identity(nbatch, self._ptr(mask), self._ext(echi), dmpo, self._cptr(env), ctypes.c_int64(env.stride),
@@ -146,10 +174,10 @@ class CudaKernels:
             ctypes.c_int64(basis.stride), ctypes.c_int64(stride_vec), self._ptr(nrm), self._ptr(active), self._ptr(kdone), self._stream()))
 
     def lanczos_step(self, nbatch, j, kmax, dt, tol, el, er, dphys, basis: Buf, stride_vec, alpha, beta, nrm, active, kdone, coef, n_active):
-        self._check(self.lib.yb_lanczos_step(
+        self._timed_call("lanczos_step", lambda: self._check(self.lib.yb_lanczos_step(
             nbatch, j, kmax, ctypes.c_double(dt), ctypes.c_double(tol), self._ext(el), self._ext(er), dphys, self._cptr(basis),
             ctypes.c_int64(basis.stride), ctypes.c_int64(stride_vec), self._ptr(alpha), self._ptr(beta), self._ptr(nrm), self._ptr(active),
-            self._ptr(kdone), self._ptr(coef), self._ptr(n_active), self._stream()))
+            self._ptr(kdone), self._ptr(coef), self._ptr(n_active), self._stream())))
 
     def lanczos_combine(self, nbatch, mask, el, er, dphys, basis: Buf, stride_vec, coef, kmax, kdone, out: Buf):
         self._check(self.lib.yb_lanczos_combine(
@@ -163,9 +191,9 @@ class CudaKernels:
             ctypes.c_int64(w.stride), self._cptr(q), ctypes.c_int64(q.stride), self._ptr(meta), self._ptr(rot_count), self._stream()))
 
     def svd_round(self, nbatch, mask, meta, block_rows, nblocks, rnd, full_panel, inner_sweeps, w: Buf, q: Buf, rot_count, max_len, max_k):
-        self._check(self.lib.yb_svd_round(
+        self._timed_call("svd_round", lambda: self._check(self.lib.yb_svd_round(
             nbatch, self._ptr(mask), self._ptr(meta), block_rows, nblocks, rnd, int(full_panel), inner_sweeps, self._cptr(w),
-            ctypes.c_int64(w.stride), self._cptr(q), ctypes.c_int64(q.stride), self._ptr(rot_count), int(max_len), int(max_k), self._stream()))
+            ctypes.c_int64(w.stride), self._cptr(q), ctypes.c_int64(q.stride), self._ptr(rot_count), int(max_len), int(max_k), self._stream())))
 
     def svd_check(self, nbatch, mask, meta, rot_count, n_pending):
         self._check(self.lib.yb_svd_check(nbatch, self._ptr(mask), self._ptr(meta), self._ptr(rot_count), self._ptr(n_pending), self._stream()))
