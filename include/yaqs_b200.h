@@ -48,7 +48,10 @@ void yb_set_flop_counter(void* device_u64);
  *   5 MERGE      theta_(ss')[l,r] = sum_c A_s[l,c] B_s'[c,r]                  merge_two_site                       methods/decompositions.py:87-102
  *   6 ABSORB_R   next'_s[k,r] = sum_j G[k,j] next_s[j,r]                      R into the right neighbour          data_structures/mps.py:742-746
  *   7 ABSORB_L   prev'_s[l,k] = sum_j prev_s[l,j] G[j,k]                      (mirror image, left shifts)          mps.py:771-788
- * e0,e1,e2: the op's extents (l, r | l, c, r | k, j, r | l, j, k).  conj_b != 0 conjugates the B operand in addition.
+ *   8 GRAM       G[i,j] = sum_e W[i,e] conj(W[j,e])       Gram matrix of the packed SVD work matrix (k rows of length len)
+ *   9 EVEC       Qacc[c,j] = sum_i Zt[c,i] conj(Qh[j,i])  conjugated eigenvectors of G as rows (yb_heev outputs)
+ *  10 ROTATE     Wf[c,e] = sum_j Qacc[c,j] W[j,e]         rows of Wf are orthogonal with norms = singular values
+ * e0,e1,e2: the op's extents (l, r | l, c, r | k, j, r | l, j, k | k, len).  conj_b != 0 conjugates the B operand in addition.
  * max_m / max_n bound the per-trajectory GEMM M and N (grid sizing). */
 int yb_gemm(int op, int nbatch, int ngroups, const int32_t* mask, yb_extent e0, yb_extent e1, yb_extent e2, int dphys, int d_left,
             int d_right, const void* a, int64_t stride_a, const void* b, int64_t stride_b, void* c, int64_t stride_c, int conj_b,
@@ -93,6 +96,18 @@ int yb_svd_prepare(int nbatch, const int32_t* mask, int mode, yb_extent el, yb_e
                    void* w, int64_t stride_w, void* q, int64_t stride_q, int32_t* meta, int32_t* rot_count, void* stream);
 int yb_svd_round(int nbatch, const int32_t* mask, int32_t* meta, int block_rows, int nblocks, int round, int full_panel, int inner_sweeps,
                  void* w, int64_t stride_w, void* q, int64_t stride_q, int32_t* rot_count, int max_len, int max_k, void* stream);
+/* yb_svd_prepare `mode` may carry an orientation request in bits 4-5 (0: by shape, 1: W = M, 2: W = M^H).
+ *
+ * Gram-matrix route for the large matrices (replaces the bulk of zgesdd at linalg/svd.py:89-104): after yb_svd_prepare,
+ *   yb_gemm(GRAM) -> yb_heev -> yb_gemm(EVEC) -> yb_gemm(ROTATE) -> yb_svd_finalize(w = Wf, q = Qacc).
+ * yb_heev: Hermitian eigen-decomposition G = (Qh Z) diag(d) (Qh Z)^H of the k x k matrices in `g` (k = ek[b]; g is
+ * overwritten with the Householder vectors): Householder tridiagonalisation, explicit Qh, implicit-QL with accumulated
+ * rotations.  Outputs: qh (k x k), zt (k x k complex, row c = eigenvector c of the tridiagonal), d (eigenvalues, unsorted);
+ * zr (k*k doubles), e, tau (k) are workspace; d/e/tau rows are stride_vec apart.  meta (optional, the SVD meta block) gets
+ * done = 1 on convergence; status bit 1 is set otherwise. */
+int yb_heev(int nbatch, const int32_t* mask, yb_extent ek, void* g, int64_t stride_g, void* qh, int64_t stride_q, void* zt, int64_t stride_z,
+            double* zr, int64_t stride_zr, double* d, double* e, void* tau, int64_t stride_vec, int32_t* meta, int32_t* status, int max_k,
+            void* stream);
 /* After a sweep: meta.done = (rot_count == 0); n_pending (device int32, zeroed by caller) counts unfinished trajectories. */
 int yb_svd_check(int nbatch, const int32_t* mask, int32_t* meta, int32_t* rot_count, int32_t* n_pending, void* stream);
 int yb_svd_finalize(int nbatch, const int32_t* mask, const int32_t* meta, int trunc_mode, double threshold, int max_bond, int min_keep,

@@ -99,6 +99,18 @@ class NumpyKernels:
                 pv = _view(a, t, ngroups * x0 * x1).reshape(ngroups, x0, x1)
                 G = cj(_view(b, t, x1 * x2).reshape(x1, x2))
                 _view(c, t, ngroups * x0 * x2)[:] = np.einsum("slj,jk->slk", pv, G).reshape(-1)
+            elif op == 8:    # GRAM: G = W W^H
+                W = _view(a, t, x0 * x1).reshape(x0, x1)
+                W2 = _view(b, t, x0 * x1).reshape(x0, x1)
+                _view(c, t, x0 * x0)[:] = (W @ W2.conj().T).reshape(-1)
+            elif op == 9:    # EVEC: Qacc[c,j] = sum_i Zt[c,i] conj(Qh[j,i])
+                Zt = _view(a, t, x0 * x0).reshape(x0, x0)
+                Qh = _view(b, t, x0 * x0).reshape(x0, x0)
+                _view(c, t, x0 * x0)[:] = (Zt @ Qh.conj().T).reshape(-1)
+            elif op == 10:   # ROTATE: Wf = Qacc W
+                Qa = _view(a, t, x0 * x0).reshape(x0, x0)
+                W = _view(b, t, x0 * x1).reshape(x0, x1)
+                _view(c, t, x0 * x1)[:] = (Qa @ W).reshape(-1)
             else:
                 raise ValueError(op)
 
@@ -201,6 +213,7 @@ class NumpyKernels:
     def svd_prepare(self, nbatch, mask, mode, el, er, dphys, src, w, q, meta, rot_count):
         self._launches += 1
         mt = _np(meta).reshape(-1, SVD_META)
+        force, mode = (mode >> 4) & 3, mode & 3
         for t in range(nbatch):
             if not _on(mask, t):
                 mt[t, 5] = 1
@@ -214,6 +227,8 @@ class NumpyKernels:
                 M = _view(src, t, dphys * l * r).reshape(dphys, l, r).transpose(1, 0, 2).reshape(l, dphys * r)
             rows, cols = M.shape
             orient = 0 if rows <= cols else 1
+            if force:
+                orient = force - 1
             k, ln = (cols, rows) if orient else (rows, cols)
             mt[t] = [k, ln, orient, rows, cols, 0, 0, 0]
             W = M.conj().T if orient else M
@@ -240,10 +255,13 @@ class NumpyKernels:
                 continue
             k, ln, orient, rows, cols = (int(v) for v in mt[t, :5])
             W = _view(w, t, k * ln).reshape(k, ln)
+            Qm = _view(q, t, k * k).reshape(k, k)          # identity on the Jacobi route (the twin's rounds are no-ops)
+            W = Qm.conj().T @ W
             M = W.conj().T if orient else W
             u, s, vh = scipy.linalg.svd(M, full_matrices=False, lapack_driver="gesdd", check_finite=False)
             kp = oracle_truncate(s, _TRUNC_NAMES[trunc_mode], threshold, max_bond if max_bond > 0 else None, min_keep)
-            _np(sval)[t * stride_s: t * stride_s + k] = s
+            _np(sval)[t * stride_s: t * stride_s + k] = 0.0
+            _np(sval)[t * stride_s: t * stride_s + len(s)] = s
             _np(keep.tensor)[keep.offset + t * keep.stride] = kp
             u, sk, vh = u[:, :kp], s[:kp], vh[:kp]
             if dist == 0:
@@ -255,6 +273,22 @@ class NumpyKernels:
                 vh = vh * np.sqrt(sk)[:, None]
             _view(uout, t, rows * kp)[:] = np.ascontiguousarray(u).reshape(-1)
             _view(vout, t, kp * cols)[:] = np.ascontiguousarray(vh).reshape(-1)
+
+    def heev(self, nbatch, mask, ek, g, qh, zt, zr, stride_zr, d, e, tau, stride_vec, meta, status, max_k):
+        """LAPACK stands in for tridiagonalisation + QL: Qh = I, row c of zt = conj-free eigenvector c (so EVEC gives E^H)."""
+        self._launches += 3
+        mt = _np(meta).reshape(-1, SVD_META) if meta is not None else None
+        for t in range(nbatch):
+            if not _on(mask, t):
+                continue
+            k = _ext(ek, t)
+            G = _view(g, t, k * k).reshape(k, k)
+            lam, vec = np.linalg.eigh(0.5 * (G + G.conj().T))
+            _view(qh, t, k * k)[:] = np.eye(k, dtype=np.complex128).reshape(-1)
+            _view(zt, t, k * k)[:] = np.ascontiguousarray(vec.conj().T).reshape(-1)
+            _np(d)[t * stride_vec: t * stride_vec + k] = lam
+            if mt is not None:
+                mt[t, 5] = 1
 
     # -- site-tensor utilities ----------------------------------------------------------------------------------------
     def unpack_vh(self, nbatch, mask, ek, er, dphys, src, dst, max_elems):

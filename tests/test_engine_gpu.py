@@ -31,3 +31,18 @@ def test_cuda_engine_multi_block_jacobi(golden_dir, block_rows):
     log = []
     results, diag = eng.run(tu, su, log)
     check_against_golden("heis8_c2_order2", golden_dir, results, diag, log, traj)
+
+
+@pytest.mark.parametrize("name", ["ising10_c1_order2", "heis8_c2_order2", "ising8_capped_order2", "ising8_strong_order2", "ising6_twosite_order2",
+                                  "ising10_c1_order1"])
+def test_cuda_engine_gram_svd_route(golden_dir, name):
+    """Force the Gram-matrix / Hermitian eigen-solver SVD route (production default only for 2 chi >= 33) on the small
+    fixtures: same jump sequence, observables <= 1e-10, identical bond dimensions; marginal decisions fall back to Jacobi."""
+    kern = CudaKernels("cuda:0")
+    eng, tu, su, traj = engine_for_case(name, kern, gram_min_k=0)
+    log = []
+    results, diag = eng.run(tu, su, log)
+    torch.cuda.synchronize()
+    assert int(eng.status.max().item()) == 0
+    assert eng.stats["gram_svd_calls"] > 0
+    check_against_golden(name, golden_dir, results, diag, log, traj)

@@ -39,6 +39,7 @@ GEMM_CASES = [
     (K.OP_LCONTRACT, 4, 4, 3, 3, 0), (K.OP_LCONTRACT, 2, 2, 4, 5, 0), (K.OP_LCONTRACT, 1, 1, 3, 3, 0),
     (K.OP_ENVR3, 1, 2, 3, 4, 0), (K.OP_ENVL1, 2, 2, 3, 4, 0), (K.OP_ENVL3, 1, 2, 3, 4, 0), (K.OP_ENVL3, 1, 2, 1, 1, 1),
     (K.OP_MERGE, 4, 2, 1, 1, 0), (K.OP_ABSORB_R, 2, 2, 1, 1, 0), (K.OP_ABSORB_L, 2, 2, 1, 1, 0),
+    (K.OP_GRAM, 1, 1, 1, 1, 0), (K.OP_EVEC, 1, 1, 1, 1, 0), (K.OP_ROTATE, 1, 1, 1, 1, 0),
 ]
 
 
@@ -293,3 +294,60 @@ def test_svd_rank_deficient_min_keep(backends):
             iso = V @ V.conj().T if dist == 0 else U.conj().T @ U
             assert np.max(np.abs(iso - np.eye(kp))) < 1e-12
             assert sg[t, 1] < 1e-14 * sg[t, 0]
+
+
+def _run_heev(kern, dev, ks, mats):
+    nb, kmax = len(ks), max(ks)
+    sq = kmax * kmax
+    ek = torch.tensor(ks, dtype=torch.int32, device=dev)
+    g = torch.zeros(nb * sq, dtype=torch.complex128, device=dev)
+    for t, (k, m) in enumerate(zip(ks, mats)):
+        g[t * sq: t * sq + k * k] = torch.from_numpy(np.ascontiguousarray(m).reshape(-1)).to(dev)
+    qh = torch.zeros(nb * sq, dtype=torch.complex128, device=dev)
+    zt = torch.zeros(nb * sq, dtype=torch.complex128, device=dev)
+    qa = torch.zeros(nb * sq, dtype=torch.complex128, device=dev)
+    zr = torch.zeros(nb * sq, dtype=torch.float64, device=dev)
+    d = torch.zeros(nb * kmax, dtype=torch.float64, device=dev)
+    e = torch.zeros(nb * kmax, dtype=torch.float64, device=dev)
+    tau = torch.zeros(nb * kmax, dtype=torch.complex128, device=dev)
+    meta = torch.zeros(nb * 8, dtype=torch.int32, device=dev)
+    status = torch.zeros(nb, dtype=torch.int32, device=dev)
+    ext = Ext(ek, 0, 1)
+    kern.heev(nb, None, ext, Buf(g, 0, sq), Buf(qh, 0, sq), Buf(zt, 0, sq), zr, sq, d, e, tau, kmax, meta, status, kmax)
+    kern.gemm(K.OP_EVEC, nb, 1, None, ext, None, None, 1, 1, 1, Buf(zt, 0, sq), Buf(qh, 0, sq), Buf(qa, 0, sq), 0, kmax, kmax)
+    return d.cpu().numpy().reshape(nb, kmax), qa.cpu().numpy().reshape(nb, sq), meta.cpu().numpy().reshape(nb, 8), status.cpu().numpy()
+
+
+@pytest.mark.parametrize("ks", [[1, 2, 3, 5, 33], [64, 130, 17, 128], [256, 200], [512, 300]])
+def test_heev_eigendecomposition(backends, ks):
+    """Householder tridiagonalisation + implicit QL: rows of Qacc are the conjugated eigenvectors, d the eigenvalues."""
+    cuda, _ = backends
+    rng = np.random.default_rng(sum(ks))
+    mats = []
+    for i, k in enumerate(ks):
+        r = max(1, k // 2) if i % 2 else k                 # every other matrix is a rank-deficient Gram matrix
+        a = rng.standard_normal((k, r)) + 1j * rng.standard_normal((k, r))
+        a *= np.logspace(0, -6, r)[None, :]                 # graded spectrum like a Schmidt spectrum
+        mats.append(a @ a.conj().T)
+    d, qa, meta, status = _run_heev(cuda, "cuda", ks, mats)
+    assert not status.any()
+    for t, k in enumerate(ks):
+        assert meta[t, 5] == 1
+        E = qa[t, : k * k].reshape(k, k).conj().T           # columns = eigenvectors
+        lam = d[t, :k]
+        scale = np.abs(np.linalg.eigvalsh(mats[t])).max()
+        assert np.max(np.abs(E.conj().T @ E - np.eye(k))) < 1e-12 * max(1, k / 16)
+        assert np.max(np.abs(mats[t] @ E - E * lam[None, :])) < 2e-13 * scale * max(1, k / 16)
+        assert np.max(np.abs(np.sort(lam) - np.linalg.eigvalsh(mats[t]))) < 1e-13 * scale * max(1, k / 16)
+
+
+def test_heev_diagonal_and_identity(backends):
+    cuda, _ = backends
+    ks = [4, 6, 40]
+    mats = [np.diag([3.0, 1.0, 2.0, 0.0]).astype(np.complex128), np.eye(6, dtype=np.complex128), np.zeros((40, 40), dtype=np.complex128)]
+    d, qa, meta, status = _run_heev(cuda, "cuda", ks, mats)
+    assert not status.any()
+    assert np.allclose(np.sort(d[0, :4]), [0, 1, 2, 3]) and np.allclose(d[1, :6], 1.0) and np.allclose(d[2, :40], 0.0)
+    for t, k in enumerate(ks):
+        E = qa[t, : k * k].reshape(k, k)
+        assert np.max(np.abs(E @ E.conj().T - np.eye(k))) < 1e-13

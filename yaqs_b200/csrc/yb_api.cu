@@ -9,6 +9,7 @@
 #include "yb_gemm.cu"
 #include "yb_ops.cu"
 #include "yb_svd.cu"
+#include "yb_heev.cu"
 
 namespace {
 thread_local char g_err[512] = "";
@@ -51,7 +52,7 @@ void yb_set_flop_counter(void* device_u64) { g_flop_counter = (unsigned long lon
 int yb_gemm(int op, int nbatch, int ngroups, const int32_t* mask, yb_extent e0, yb_extent e1, yb_extent e2, int dphys, int d_left, int d_right,
             const void* a, int64_t stride_a, const void* b, int64_t stride_b, void* c, int64_t stride_c, int conj_b, int max_m, int max_n,
             void* stream) {
-    if (op < 0 || op > YB_OP_ABSORB_L) return fail_msg("yb_gemm: unknown op");
+    if (op < 0 || op > YB_OP_LAST) return fail_msg("yb_gemm: unknown op");
     if (nbatch <= 0) return 0;
     YbGemmParams P;
     memset(&P, 0, sizeof(P));
@@ -153,6 +154,34 @@ int yb_svd_finalize(int nbatch, const int32_t* mask, const int32_t* meta, int tr
                                                               stride_q, meta, sval, stride_s, keep, keep_stride, (cplx*)uout, stride_u, (cplx*)vout,
                                                               stride_v, status, mask);
     return done("yb_svd_finalize");
+}
+
+int yb_heev(int nbatch, const int32_t* mask, yb_extent ek, void* g, int64_t stride_g, void* qh, int64_t stride_q, void* zt, int64_t stride_z,
+            double* zr, int64_t stride_zr, double* d, double* e, void* tau, int64_t stride_vec, int32_t* meta, int32_t* status, int max_k,
+            void* stream) {
+    if (nbatch <= 0) return 0;
+    if (max_k > heev::KMAX) return fail_msg("yb_heev: max_k > 512 unsupported");
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e1 = cudaFuncSetAttribute(heev::k_hetrd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)heev::SMEM_BYTES);
+        if (e1 != cudaSuccess) return fail("yb_heev(attr)", e1);
+        e1 = cudaFuncSetAttribute(heev::k_ungtr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)heev::SMEM_BYTES);
+        if (e1 != cudaSuccess) return fail("yb_heev(attr)", e1);
+        configured = true;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    heev::k_hetrd<<<nbatch, heev::THREADS, heev::SMEM_BYTES, st>>>((cplx*)g, stride_g, ek.ptr, ek.stride, d, e, (cplx*)tau, stride_vec, mask);
+    if (int rc = done("yb_heev(hetrd)")) return rc;
+    heev::k_ungtr<<<nbatch, heev::THREADS, heev::SMEM_BYTES, st>>>((const cplx*)g, stride_g, (const cplx*)tau, stride_vec, (cplx*)qh, stride_q, ek.ptr,
+                                                                  ek.stride, mask);
+    if (int rc = done("yb_heev(ungtr)")) return rc;
+    if (max_k <= 128)
+        heev::k_steqr<128><<<nbatch, 128 + 32, 0, st>>>(d, e, stride_vec, zr, stride_zr, (cplx*)zt, stride_z, ek.ptr, ek.stride, meta, status, mask);
+    else if (max_k <= 256)
+        heev::k_steqr<256><<<nbatch, 256 + 32, 0, st>>>(d, e, stride_vec, zr, stride_zr, (cplx*)zt, stride_z, ek.ptr, ek.stride, meta, status, mask);
+    else
+        heev::k_steqr<512><<<nbatch, 512 + 32, 0, st>>>(d, e, stride_vec, zr, stride_zr, (cplx*)zt, stride_z, ek.ptr, ek.stride, meta, status, mask);
+    return done("yb_heev(steqr)");
 }
 
 int yb_unpack_vh(int nbatch, const int32_t* mask, yb_extent ek, yb_extent er, int dphys, const void* src, int64_t stride_src, void* dst,

@@ -60,6 +60,11 @@ enum YbGemmOp {
     YB_OP_MERGE = 5,       // theta_(s s')[l,r] = sum_c A_s[l,c] B_s'[c,r]                          decompositions.py:100
     YB_OP_ABSORB_R = 6,    // next'_s[k,r]      = sum_j G[k,j] next_s[j,r]                          mps.py:742-746
     YB_OP_ABSORB_L = 7,    // prev'_s[l,k]      = sum_j prev_s[l,j] G[j,k]
+    // Gram-matrix SVD path (yb_heev.cu): plain 2-D products on the packed Jacobi work matrix W (k rows of length len)
+    YB_OP_GRAM = 8,        // G[i,j]            = sum_e W[i,e] conj(W[j,e])                         x0 = k, x1 = len
+    YB_OP_EVEC = 9,        // Qacc[c,j]         = sum_i Zt[c,i] conj(Qh[j,i])   (rows = conj eigenvectors)   x0 = k
+    YB_OP_ROTATE = 10,     // Wf[c,e]           = sum_j Qacc[c,j] W[j,e]                            x0 = k, x1 = len
+    YB_OP_LAST = 10,
 };
 
 struct YbGemmParams {

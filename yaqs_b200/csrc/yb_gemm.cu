@@ -90,6 +90,24 @@ __device__ __forceinline__ bool make_desc(const YbGemmParams& P, int b, int g, D
         d.B = B; d.b_rs = x2;
         d.C = C + (long long)g * x0 * x2; d.c_rs = x2;
     } break;
+    case YB_OP_GRAM: {                // x0 = k, x1 = len
+        d.M = x0; d.N = x0; d.K = x1;
+        d.A = A; d.a_rs = x1;
+        d.B = B; d.b_rs = 1; d.b_cs = x1; d.conjB = true;
+        d.C = C; d.c_rs = x0;
+    } break;
+    case YB_OP_EVEC: {                // x0 = k
+        d.M = x0; d.N = x0; d.K = x0;
+        d.A = A; d.a_rs = x0;
+        d.B = B; d.b_rs = 1; d.b_cs = x0; d.conjB = true;
+        d.C = C; d.c_rs = x0;
+    } break;
+    case YB_OP_ROTATE: {              // x0 = k, x1 = len
+        d.M = x0; d.K = x0; d.N = x1;
+        d.A = A; d.a_rs = x0;
+        d.B = B; d.b_rs = x1;
+        d.C = C; d.c_rs = x1;
+    } break;
     default: return false;
     }
     if (P.conj_extra) d.conjB = !d.conjB;
@@ -247,7 +265,9 @@ cudaError_t yb_launch_gemm(const YbGemmParams& P, int maxM, int maxN, cudaStream
     switch (P.op) {
     case YB_OP_LCONTRACT:
     case YB_OP_ENVL3: return launch_t<LAY_AM, LAY_BN>(P, maxM, maxN, st);
-    case YB_OP_ENVR3: return launch_t<LAY_AK, LAY_BK>(P, maxM, maxN, st);
+    case YB_OP_ENVR3:
+    case YB_OP_GRAM:
+    case YB_OP_EVEC: return launch_t<LAY_AK, LAY_BK>(P, maxM, maxN, st);
     default: return launch_t<LAY_AK, LAY_BN>(P, maxM, maxN, st);
     }
 }

@@ -18,11 +18,13 @@ __global__ void k_svd_prepare(int mode, int dphys, const cplx* __restrict__ src,
     const int b = blockIdx.y;
     if (mask && !mask[b]) { if (blockIdx.x == 0 && threadIdx.x == 0) meta[b * META + 5] = 1; return; }
     const int l = el[(long long)b * esl], r = er[(long long)b * esr];
+    const int force = (mode >> 4) & 3;          // 0: orient by shape, 1: W = M, 2: W = M^H (Gram path picks the isometric side)
+    mode &= 3;
     int rows, cols;
     if (mode == 0) { rows = dphys * l; cols = dphys * r; }
     else if (mode == 1) { rows = dphys * l; cols = r; }
     else { rows = l; cols = dphys * r; }
-    const int orient = rows <= cols ? 0 : 1;
+    const int orient = force == 1 ? 0 : (force == 2 ? 1 : (rows <= cols ? 0 : 1));
     const int k = orient ? cols : rows, len = orient ? rows : cols;
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         int* m = meta + b * META;
@@ -253,7 +255,7 @@ __global__ void __launch_bounds__(512) k_svd_finalize(int trunc_mode, double thr
     }
     __syncthreads();
     if (tid == 0) {
-        s_keep = truncate_keep(ssort, k, trunc_mode, threshold, max_bond, min_keep);
+        s_keep = truncate_keep(ssort, min(k, min(rows, cols)), trunc_mode, threshold, max_bond, min_keep);   // k > min(rows, cols) only on the Gram path
         bool bad = false;
         for (int i = 0; i < k; ++i) bad |= !isfinite(ssort[i]);
         if (bad || !m[5]) atomicOr(&status[b], bad ? 2 : 1);       // 2: non-finite, 1: Jacobi not converged

@@ -18,8 +18,8 @@ import numpy as np
 import scipy.linalg
 import torch
 
-from .kernels import (DIST, LANCZOS_PITCH, OP_ABSORB_L, OP_ABSORB_R, OP_ENVL1, OP_ENVL3, OP_ENVR3, OP_LCONTRACT, OP_MERGE,
-                      OP_RCONTRACT, SVD_COLS, SVD_META, SVD_ROWS, SVD_THETA, TRUNC_MODES, Buf, Ext)
+from .kernels import (DIST, LANCZOS_PITCH, OP_ABSORB_L, OP_ABSORB_R, OP_ENVL1, OP_ENVL3, OP_ENVR3, OP_EVEC, OP_GRAM, OP_LCONTRACT, OP_MERGE,
+                      OP_RCONTRACT, OP_ROTATE, SVD_COLS, SVD_META, SVD_ORIENT_COLS, SVD_ORIENT_ROWS, SVD_ROWS, SVD_THETA, TRUNC_MODES, Buf, Ext)
 
 C128 = torch.complex128
 KRYLOV_MAX = 25          # max_lanczos_iterations (matrix_exponential.py:37)
@@ -158,7 +158,7 @@ class BatchedTJM:
 
     def __init__(self, kernels, length: int, nbatch: int, mpo: Sequence[np.ndarray], params: EngineParams,
                  noise: Sequence[dict] | None, observables: Sequence[tuple[np.ndarray, Sequence[int]]],
-                 init_tensors, svd_block_rows: int | None = None):
+                 init_tensors, svd_block_rows: int | None = None, gram_min_k: int = 33):
         self.K = kernels
         self.dev = kernels.device
         self.p = params
@@ -226,6 +226,19 @@ class BatchedTJM:
                 svd_block_rows //= 2
         self.svd_block_rows = svd_block_rows
         self.svd_nblocks = max(2, 2 * ((sd + 2 * svd_block_rows - 1) // (2 * svd_block_rows)))
+        # Gram-matrix SVD route (Hermitian eigen-solver) for matrices whose Jacobi side would exceed one shared-memory panel
+        self.gram_min_k = gram_min_k
+        self.use_gram = sd >= gram_min_k and sd <= 512
+        if self.use_gram:
+            self.heev_g = torch.zeros(B * sd * sd, dtype=C128, device=dev)
+            self.heev_q = torch.zeros(B * sd * sd, dtype=C128, device=dev)
+            self.heev_z = torch.zeros(B * sd * sd, dtype=C128, device=dev)
+            self.heev_zr = torch.zeros(B * sd * sd, dtype=torch.float64, device=dev)
+            self.heev_d = torch.zeros(B * sd, dtype=torch.float64, device=dev)
+            self.heev_e = torch.zeros(B * sd, dtype=torch.float64, device=dev)
+            self.heev_tau = torch.zeros(B * sd, dtype=C128, device=dev)
+            self.status_scratch = torch.zeros(B, dtype=torch.int32, device=dev)
+            self._iota_sd = torch.arange(sd, device=dev)
         # noise tables
         self.noise = list(noise) if noise else None
         if self.noise is not None and all(pr["strength"] == 0 for pr in self.noise):
@@ -236,7 +249,7 @@ class BatchedTJM:
         self.jump_table = self._build_jump_table() if self.noise is not None else []
         # observables (already in the reference's sorted order)
         self.observables = [(np.asarray(m, dtype=np.complex128), tuple(int(s) for s in sites)) for m, sites in observables]
-        self.stats = {"krylov_calls": 0, "matvecs": 0, "svd_calls": 0, "svd_sweeps": 0, "jumps": 0}
+        self.stats = {"krylov_calls": 0, "matvecs": 0, "svd_calls": 0, "svd_sweeps": 0, "jumps": 0, "gram_svd_calls": 0, "gram_fallbacks": 0}
 
     # ------------------------------------------------------------------------------------------------------------------
     # small helpers
@@ -351,7 +364,63 @@ class BatchedTJM:
     # ------------------------------------------------------------------------------------------------------------------
     # SVD driver + splits / gauge shifts
     # ------------------------------------------------------------------------------------------------------------------
-    def _svd(self, mode: int, src: Buf, el: Ext, er: Ext, trunc, dist: str, mask) -> None:
+    def _svd(self, mode: int, src: Buf, el: Ext, er: Ext, trunc, dist: str, mask, kcap: int = 0) -> None:
+        """Truncated SVD of every trajectory's matrix.  kcap > 0 (capacity of the side that becomes the isometry) selects the
+        Gram-matrix route for large matrices; the one-sided Jacobi is used otherwise and as its accurate fallback."""
+        if self.use_gram and kcap > 0 and kcap >= self.gram_min_k and dist in ("left", "right") and trunc[0] in (0, 1):
+            self._svd_gram(mode, src, el, er, trunc, dist, mask)
+        else:
+            self._svd_jacobi(mode, src, el, er, trunc, dist, mask)
+
+    def _svd_gram(self, mode: int, src: Buf, el: Ext, er: Ext, trunc, dist: str, mask) -> None:
+        """M = U S Vh through the Hermitian eigen-problem of the Gram matrix over the index that must become an isometry
+        (rows for dist='right', columns for dist='left'): the isometric factor is the eigenvector matrix itself and the
+        other factor is the exact product E^H M, so no division by a singular value ever happens.  The eigenvalues of a
+        Gram matrix carry an ABSOLUTE error ~ k eps s_max^2; trajectories whose keep decision lies within that error of
+        the threshold are redone with the Jacobi route (high relative accuracy)."""
+        K, B, lay = self.K, self.B, self.lay
+        sd = lay.svd_dim
+        sq = sd * sd
+        w, q = self._buf(self.svd_w, sq), self._buf(self.svd_q, sq)
+        g, qh, zt = self._buf(self.heev_g, sq), self._buf(self.heev_q, sq), self._buf(self.heev_z, sq)
+        orient = SVD_ORIENT_ROWS if dist == "right" else SVD_ORIENT_COLS
+        K.svd_prepare(B, mask, mode | orient, el, er, self.d, src, w, q, self.svd_meta, self.svd_rot)
+        ek, eln = Ext(self.svd_meta, 0, SVD_META), Ext(self.svd_meta, 1, SVD_META)
+        K.gemm(OP_GRAM, B, 1, mask, ek, eln, None, 1, 1, 1, w, w, g, 0, sd, sd)
+        self.status_scratch.zero_()
+        K.heev(B, mask, ek, g, qh, zt, self.heev_zr, sq, self.heev_d, self.heev_e, self.heev_tau, sd, self.svd_meta, self.status_scratch, sd)
+        K.gemm(OP_EVEC, B, 1, mask, ek, None, None, 1, 1, 1, zt, qh, q, 0, sd, sd)
+        K.gemm(OP_ROTATE, B, 1, mask, ek, eln, None, 1, 1, 1, q, w, g, 0, sd, sd)
+        tm, thr, mb, mk = trunc
+        K.svd_finalize(B, mask, self.svd_meta, tm, thr, mb, mk, DIST[dist], g, q, self.svd_s, sd, Ext(self.keep, 0, 1),
+                       self._buf(self.svd_u, sq), self._buf(self.svd_v, sq), self.status_scratch, sd)
+        self.stats["gram_svd_calls"] += 1
+        # ---- decisions within the Gram error of the threshold -> Jacobi
+        meta = self.svd_meta.view(B, SVD_META)
+        nsv = torch.minimum(meta[:, 3], meta[:, 4])
+        valid = self._iota_sd[None, :] < nsv[:, None]
+        s = self.svd_s.view(B, sd)
+        s2 = torch.where(valid, s * s, torch.zeros_like(s))
+        smax2 = s2[:, 0]
+        noise = 16.0 * sd * 2.220446049250313e-16
+        if tm == 0:
+            if thr > 0.0:
+                cum = torch.flip(torch.cumsum(torch.flip(s2, dims=[1]), dim=1), dims=[1])
+                amb = (((cum - thr).abs() <= (noise * smax2 + 1e-7 * thr)[:, None]) & valid).any(dim=1)
+            else:
+                amb = torch.zeros(B, dtype=torch.bool, device=self.dev)
+        else:
+            ratio2 = s2 / torch.clamp(smax2, min=1e-300)[:, None]
+            amb = (((ratio2 - thr * thr).abs() <= noise) & valid).any(dim=1)
+        amb |= (meta[:, 5] == 0) | (self.status_scratch != 0) | ~torch.isfinite(smax2)
+        if mask is not None:
+            amb &= (mask != 0)
+        nfb = K.sync_int(amb.sum())
+        if nfb > 0:
+            self.stats["gram_fallbacks"] += nfb
+            self._svd_jacobi(mode, src, el, er, trunc, dist, amb.to(torch.int32))
+
+    def _svd_jacobi(self, mode: int, src: Buf, el: Ext, er: Ext, trunc, dist: str, mask) -> None:
         """prepare -> cyclic Jacobi sweeps until every trajectory is clean -> finalize (keep, U f(S), g(S) Vh)."""
         K, B, lay = self.K, self.B, self.lay
         sd = lay.svd_dim
@@ -372,22 +441,23 @@ class BatchedTJM:
         K.svd_finalize(B, mask, self.svd_meta, tm, thr, mb, mk, DIST[dist], w, q, self.svd_s, sd, Ext(self.keep, 0, 1),
                        self._buf(self.svd_u, sd * sd), self._buf(self.svd_v, sd * sd), self.status, sd)
 
-    def split_theta(self, st: BatchedState, i: int, dist: str, trunc, mask=None) -> None:
+    def split_theta(self, st: BatchedState, i: int, dist: str, trunc, mask=None, fast: bool = False) -> None:
         """split_two_site (decompositions.py:105-185): theta workspace -> sites i, i+1; bond i+1 <- keep."""
         lay, K, B, d = self.lay, self.K, self.B, self.d
         sd = lay.svd_dim
-        self._svd(SVD_THETA, self._buf(self.theta, lay.theta_slot), st.ext(i), st.ext(i + 2), trunc, dist, mask)
+        kcap = (d * (lay.cap[i] if dist == "right" else lay.cap[i + 2])) if fast else 0
+        self._svd(SVD_THETA, self._buf(self.theta, lay.theta_slot), st.ext(i), st.ext(i + 2), trunc, dist, mask, kcap)
         kx = Ext(self.keep, 0, 1)
         K.copy_packed(B, mask, st.ext(i), kx, d, self._buf(self.svd_u, sd * sd), st.site(i), lay.slot[i])
         K.unpack_vh(B, mask, kx, st.ext(i + 2), d, self._buf(self.svd_v, sd * sd), st.site(i + 1), lay.slot[i + 1])
         self._set_bond(st, i + 1, mask)
 
-    def shift_right(self, st: BatchedState, i: int, trunc, mask=None) -> None:
+    def shift_right(self, st: BatchedState, i: int, trunc, mask=None, fast: bool = False) -> None:
         """Centre i -> i+1 (mps.py:719-769).  The reference merges the pair and splits it; because site i+1 is a right
         isometry the SVD of the centre tensor alone gives the same singular values / keep decision."""
         lay, K, B, d = self.lay, self.K, self.B, self.d
         sd = lay.svd_dim
-        self._svd(SVD_ROWS, st.site(i), st.ext(i), st.ext(i + 1), trunc, "right", mask)
+        self._svd(SVD_ROWS, st.site(i), st.ext(i), st.ext(i + 1), trunc, "right", mask, d * lay.cap[i] if fast else 0)
         kx = Ext(self.keep, 0, 1)
         K.copy_packed(B, mask, st.ext(i), kx, d, self._buf(self.svd_u, sd * sd), st.site(i), lay.slot[i])
         tmp = self._buf(self.tmp, lay.nloc_max)
@@ -396,11 +466,11 @@ class BatchedTJM:
         K.copy_packed(B, mask, kx, st.ext(i + 2), d, tmp, st.site(i + 1), lay.slot[i + 1])
         self._set_bond(st, i + 1, mask)
 
-    def shift_left(self, st: BatchedState, i: int, trunc, mask=None) -> None:
+    def shift_left(self, st: BatchedState, i: int, trunc, mask=None, fast: bool = False) -> None:
         """Centre i -> i-1 (mps.py:771-788), reduced form (site i-1 must be a left isometry)."""
         lay, K, B, d = self.lay, self.K, self.B, self.d
         sd = lay.svd_dim
-        self._svd(SVD_COLS, st.site(i), st.ext(i), st.ext(i + 1), trunc, "left", mask)
+        self._svd(SVD_COLS, st.site(i), st.ext(i), st.ext(i + 1), trunc, "left", mask, d * lay.cap[i + 1] if fast else 0)
         kx = Ext(self.keep, 0, 1)
         tmp = self._buf(self.tmp, lay.nloc_max)
         K.gemm(OP_ABSORB_L, B, d, mask, st.ext(i - 1), st.ext(i), kx, d, 1, 1, st.site(i - 1), self._buf(self.svd_u, sd * sd), tmp, 0,
@@ -446,19 +516,19 @@ class BatchedTJM:
             for i in range(n - 2):
                 self.merge(st, i)
                 self.update_site(st, i, 2, th, 0.5 * dt)
-                self.split_theta(st, i, "right", trunc)
+                self.split_theta(st, i, "right", trunc, fast=True)
                 self.env_update_left(st, i)
                 self.update_site(st, i + 1, 1, st.site(i + 1), -0.5 * dt)
             i = n - 2
             self.merge(st, i)
             self.update_site(st, i, 2, th, dt)
-            self.split_theta(st, i, "left", trunc)
+            self.split_theta(st, i, "left", trunc, fast=True)
             self.env_update_right(st, i + 1)
             for i in reversed(range(n - 2)):
                 self.update_site(st, i + 1, 1, st.site(i + 1), -0.5 * dt)
                 self.merge(st, i)
                 self.update_site(st, i, 2, th, 0.5 * dt)
-                self.split_theta(st, i, "left", trunc)
+                self.split_theta(st, i, "left", trunc, fast=True)
                 self.env_update_right(st, i + 1)
 
     def sweep_1site(self, st: BatchedState, scale: float) -> None:
@@ -571,7 +641,7 @@ class BatchedTJM:
         shift = self._trunc_args("discarded_weight", SHIFT_THRESHOLD, None, 1)
         user = self._trunc_args(p.trunc_mode, p.svd_threshold, p.max_bond_dim, 1)
         for i in range(n - 1):                              # centre 0 -> L-1 with SVD shifts (:88-92)
-            self.shift_right(st, i, shift)
+            self.shift_right(st, i, shift, fast=True)
         facs = self._dissipators(dt)
         for i in reversed(range(n)):
             op1, scalar2, pair = facs[i]
@@ -585,9 +655,9 @@ class BatchedTJM:
                 th = self.merge(st, i - 1)
                 op_t = torch.from_numpy(np.ascontiguousarray(pair, dtype=np.complex128).reshape(-1)).to(self.dev)
                 K.apply_local_op(B, None, None, 0, st.ext(i - 1), st.ext(i + 1), d * d, op_t, 0, th, lay.cap[i - 1] * lay.cap[i + 1])
-                self.split_theta(st, i - 1, "right", user)
+                self.split_theta(st, i - 1, "right", user, fast=True)
             if i != 0:
-                self.shift_left(st, i, shift)
+                self.shift_left(st, i, shift, fast=True)
 
     # ------------------------------------------------------------------------------------------------------------------
     # local reduced density matrices by a left-to-right transfer sweep (observables + jump weights)

@@ -15,9 +15,10 @@ import torch
 _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libyaqs_b200.so")
 
 # op codes of yb_gemm (csrc/yb_common.cuh)
-OP_RCONTRACT, OP_LCONTRACT, OP_ENVR3, OP_ENVL1, OP_ENVL3, OP_MERGE, OP_ABSORB_R, OP_ABSORB_L = range(8)
+OP_RCONTRACT, OP_LCONTRACT, OP_ENVR3, OP_ENVL1, OP_ENVL3, OP_MERGE, OP_ABSORB_R, OP_ABSORB_L, OP_GRAM, OP_EVEC, OP_ROTATE = range(11)
 # yb_svd_prepare modes
 SVD_THETA, SVD_ROWS, SVD_COLS = 0, 1, 2
+SVD_ORIENT_ROWS, SVD_ORIENT_COLS = 1 << 4, 2 << 4      # force W = M / W = M^H (Gram path)
 # truncation modes (core/linalg/svd_utils.py) and singular-value distribution (decompositions.py)
 TRUNC_MODES = {"discarded_weight": 0, "relative": 1, "hard_cutoff": 2, "relative_discarded_weight": 3}
 DIST = {"left": 0, "right": 1, "sqrt": 2}
@@ -68,7 +69,7 @@ def load_library() -> ctypes.CDLL:
 
 EXPORTED_SYMBOLS = [
     "yb_last_error", "yb_version", "yb_launch_count", "yb_set_flop_counter", "yb_gemm", "yb_wapply", "yb_env_identity", "yb_lanczos_init",
-    "yb_lanczos_step", "yb_lanczos_combine", "yb_svd_prepare", "yb_svd_round", "yb_svd_check", "yb_svd_finalize",
+    "yb_lanczos_step", "yb_lanczos_combine", "yb_svd_prepare", "yb_svd_round", "yb_svd_check", "yb_svd_finalize", "yb_heev",
     "yb_unpack_vh", "yb_copy_packed", "yb_apply_local_op", "yb_norm2", "yb_scale", "yb_local_rdm",
 ]
 
@@ -205,6 +206,13 @@ class CudaKernels:
             self._cptr(w), ctypes.c_int64(w.stride), self._cptr(q), ctypes.c_int64(q.stride), self._ptr(sval), ctypes.c_int64(stride_s),
             self._ptr(keep.tensor, 4 * keep.offset), keep.stride, self._cptr(uout), ctypes.c_int64(uout.stride), self._cptr(vout),
             ctypes.c_int64(vout.stride), self._ptr(status), int(max_k), self._stream()))
+
+    def heev(self, nbatch, mask, ek: Ext, g: Buf, qh: Buf, zt: Buf, zr: torch.Tensor, stride_zr, d, e, tau: torch.Tensor, stride_vec, meta, status,
+             max_k):
+        self._timed_call("heev", lambda: self._check(self.lib.yb_heev(
+            nbatch, self._ptr(mask), self._ext(ek), self._cptr(g), ctypes.c_int64(g.stride), self._cptr(qh), ctypes.c_int64(qh.stride),
+            self._cptr(zt), ctypes.c_int64(zt.stride), self._ptr(zr), ctypes.c_int64(stride_zr), self._ptr(d), self._ptr(e), self._ptr(tau),
+            ctypes.c_int64(stride_vec), self._ptr(meta), self._ptr(status), int(max_k), self._stream())))
 
     # -- site-tensor utilities ----------------------------------------------------------------------------------------
     def unpack_vh(self, nbatch, mask, ek, er, dphys, src: Buf, dst: Buf, max_elems):
