@@ -108,6 +108,14 @@ int yb_svd_round(int nbatch, const int32_t* mask, int32_t* meta, int block_rows,
 int yb_heev(int nbatch, const int32_t* mask, yb_extent ek, void* g, int64_t stride_g, void* qh, int64_t stride_q, void* zt, int64_t stride_z,
             double* zr, int64_t stride_zr, double* d, double* e, void* tau, int64_t stride_vec, int32_t* meta, int32_t* status, int max_k,
             void* stream);
+/* Second level of the Gram route: yb_svd_select lists, per trajectory, the rows of the rotated work matrix whose squared
+ * norm is below tau_rel * max (sel_n[b] rows, indices in sel_idx[b][0..max_k)); yb_svd_gather copies those rows of (w, q)
+ * into the compact blocks (ws, qs) (dir = 0) or back (dir = 1).  Between the two the caller re-diagonalises the block with
+ * GRAM / yb_heev / EVEC / ROTATE using sel_n as the row extent. */
+int yb_svd_select(int nbatch, const int32_t* mask, const int32_t* meta, const void* w, int64_t stride_w, double tau_rel, int32_t* sel_n,
+                  int32_t* sel_idx, int max_k, void* stream);
+int yb_svd_gather(int nbatch, const int32_t* mask, const int32_t* meta, const int32_t* sel_n, const int32_t* sel_idx, int max_k, int dir, void* w,
+                  int64_t stride_w, void* q, int64_t stride_q, void* ws, int64_t stride_ws, void* qs, int64_t stride_qs, void* stream);
 /* After a sweep: meta.done = (rot_count == 0); n_pending (device int32, zeroed by caller) counts unfinished trajectories. */
 int yb_svd_check(int nbatch, const int32_t* mask, int32_t* meta, int32_t* rot_count, int32_t* n_pending, void* stream);
 int yb_svd_finalize(int nbatch, const int32_t* mask, const int32_t* meta, int trunc_mode, double threshold, int max_bond, int min_keep,

@@ -274,6 +274,35 @@ class NumpyKernels:
             _view(uout, t, rows * kp)[:] = np.ascontiguousarray(u).reshape(-1)
             _view(vout, t, kp * cols)[:] = np.ascontiguousarray(vh).reshape(-1)
 
+    def svd_select(self, nbatch, mask, meta, w, tau_rel, sel_n, sel_idx, max_k):
+        self._launches += 1
+        mt = _np(meta).reshape(-1, SVD_META)
+        for t in range(nbatch):
+            if not _on(mask, t):
+                _np(sel_n)[t] = 0
+                continue
+            k, ln = int(mt[t, 0]), int(mt[t, 1])
+            nu = (np.abs(_view(w, t, k * ln).reshape(k, ln)) ** 2).sum(axis=1)
+            idx = np.nonzero(nu < tau_rel * nu.max())[0] if k else np.zeros(0, dtype=int)
+            _np(sel_n)[t] = len(idx) if len(idx) >= 2 else 0
+            _np(sel_idx)[t * max_k: t * max_k + len(idx)] = idx
+
+    def svd_gather(self, nbatch, mask, meta, sel_n, sel_idx, max_k, direction, w, q, ws, qs):
+        self._launches += 1
+        mt = _np(meta).reshape(-1, SVD_META)
+        for t in range(nbatch):
+            n = int(_np(sel_n)[t])
+            if not _on(mask, t) or n <= 0:
+                continue
+            k, ln = int(mt[t, 0]), int(mt[t, 1])
+            idx = _np(sel_idx)[t * max_k: t * max_k + n]
+            W, Q = _view(w, t, k * ln).reshape(k, ln), _view(q, t, k * k).reshape(k, k)
+            Ws, Qs = _view(ws, t, n * ln).reshape(n, ln), _view(qs, t, n * k).reshape(n, k)
+            if direction == 0:
+                Ws[:], Qs[:] = W[idx], Q[idx]
+            else:
+                W[idx], Q[idx] = Ws, Qs
+
     def heev(self, nbatch, mask, ek, g, qh, zt, zr, stride_zr, d, e, tau, stride_vec, meta, status, max_k):
         """LAPACK stands in for tridiagonalisation + QL: Qh = I, row c of zt = conj-free eigenvector c (so EVEC gives E^H)."""
         self._launches += 3

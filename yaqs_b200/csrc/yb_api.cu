@@ -156,6 +156,23 @@ int yb_svd_finalize(int nbatch, const int32_t* mask, const int32_t* meta, int tr
     return done("yb_svd_finalize");
 }
 
+int yb_svd_select(int nbatch, const int32_t* mask, const int32_t* meta, const void* w, int64_t stride_w, double tau_rel, int32_t* sel_n,
+                  int32_t* sel_idx, int max_k, void* stream) {
+    if (nbatch <= 0) return 0;
+    if (max_k > 1024) return fail_msg("yb_svd_select: max_k > 1024 unsupported");
+    k_svd_select<<<nbatch, 512, 0, (cudaStream_t)stream>>>((const cplx*)w, stride_w, meta, tau_rel, sel_n, sel_idx, max_k, mask);
+    return done("yb_svd_select");
+}
+
+int yb_svd_gather(int nbatch, const int32_t* mask, const int32_t* meta, const int32_t* sel_n, const int32_t* sel_idx, int max_k, int dir, void* w,
+                  int64_t stride_w, void* q, int64_t stride_q, void* ws, int64_t stride_ws, void* qs, int64_t stride_qs, void* stream) {
+    if (nbatch <= 0) return 0;
+    dim3 grid(32, nbatch);
+    k_svd_gather<<<grid, 256, 0, (cudaStream_t)stream>>>(dir, (cplx*)w, stride_w, (cplx*)q, stride_q, (cplx*)ws, stride_ws, (cplx*)qs, stride_qs, meta,
+                                                          sel_n, sel_idx, max_k, mask);
+    return done("yb_svd_gather");
+}
+
 int yb_heev(int nbatch, const int32_t* mask, yb_extent ek, void* g, int64_t stride_g, void* qh, int64_t stride_q, void* zt, int64_t stride_z,
             double* zr, int64_t stride_zr, double* d, double* e, void* tau, int64_t stride_vec, int32_t* meta, int32_t* status, int max_k,
             void* stream) {
@@ -170,17 +187,34 @@ int yb_heev(int nbatch, const int32_t* mask, yb_extent ek, void* g, int64_t stri
         configured = true;
     }
     cudaStream_t st = (cudaStream_t)stream;
+    // k_ungtr (needs the reflectors) and k_steqr (needs d, e) are independent: the bandwidth-bound Q accumulation runs on a
+    // side stream underneath the latency-bound QL chain.
+    static cudaStream_t side[16] = {nullptr};
+    static cudaEvent_t ev_fork[16] = {nullptr}, ev_join[16] = {nullptr};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    dev &= 15;
+    if (!side[dev]) {
+        cudaError_t e2 = cudaStreamCreateWithFlags(&side[dev], cudaStreamNonBlocking);
+        if (e2 == cudaSuccess) e2 = cudaEventCreateWithFlags(&ev_fork[dev], cudaEventDisableTiming);
+        if (e2 == cudaSuccess) e2 = cudaEventCreateWithFlags(&ev_join[dev], cudaEventDisableTiming);
+        if (e2 != cudaSuccess) return fail("yb_heev(side stream)", e2);
+    }
     heev::k_hetrd<<<nbatch, heev::THREADS, heev::SMEM_BYTES, st>>>((cplx*)g, stride_g, ek.ptr, ek.stride, d, e, (cplx*)tau, stride_vec, mask);
     if (int rc = done("yb_heev(hetrd)")) return rc;
-    heev::k_ungtr<<<nbatch, heev::THREADS, heev::SMEM_BYTES, st>>>((const cplx*)g, stride_g, (const cplx*)tau, stride_vec, (cplx*)qh, stride_q, ek.ptr,
-                                                                  ek.stride, mask);
+    cudaEventRecord(ev_fork[dev], st);
+    cudaStreamWaitEvent(side[dev], ev_fork[dev], 0);
+    heev::k_ungtr<<<nbatch, heev::THREADS, heev::SMEM_BYTES, side[dev]>>>((const cplx*)g, stride_g, (const cplx*)tau, stride_vec, (cplx*)qh, stride_q,
+                                                                         ek.ptr, ek.stride, mask);
     if (int rc = done("yb_heev(ungtr)")) return rc;
+    cudaEventRecord(ev_join[dev], side[dev]);
     if (max_k <= 128)
         heev::k_steqr<128><<<nbatch, 128 + 32, 0, st>>>(d, e, stride_vec, zr, stride_zr, (cplx*)zt, stride_z, ek.ptr, ek.stride, meta, status, mask);
     else if (max_k <= 256)
         heev::k_steqr<256><<<nbatch, 256 + 32, 0, st>>>(d, e, stride_vec, zr, stride_zr, (cplx*)zt, stride_z, ek.ptr, ek.stride, meta, status, mask);
     else
         heev::k_steqr<512><<<nbatch, 512 + 32, 0, st>>>(d, e, stride_vec, zr, stride_zr, (cplx*)zt, stride_z, ek.ptr, ek.stride, meta, status, mask);
+    cudaStreamWaitEvent(st, ev_join[dev], 0);
     return done("yb_heev(steqr)");
 }
 

@@ -305,20 +305,25 @@ __global__ void __launch_bounds__(NT + 32) k_steqr(double* dio, const double* ei
             double s = 1.0, c = 1.0, p = 0.0;
             int i = m - 1;
             bool under = false;
+            // operands of rotation i are pre-loaded one iteration ahead so that no shared-memory latency sits on the chain
+            double e_i = e[i], d_i = d[i], d_ip1 = d[i + 1];
             for (; i >= l; --i) {
-                const double f = s * e[i], bq = c * e[i];
+                double e_n = 0.0, d_n = 0.0;
+                if (i - 1 >= l) { e_n = e[i - 1]; d_n = d[i - 1]; }
+                const double f = s * e_i, bq = c * e_i;
                 const double h2 = f * f + g * g;
-                if (h2 == 0.0) { e[i + 1] = 0.0; d[i + 1] -= p; e[m] = 0.0; under = true; break; }
+                if (h2 == 0.0) { e[i + 1] = 0.0; d[i + 1] = d_ip1 - p; e[m] = 0.0; under = true; break; }
                 const double ri = rsqrt(h2);
                 r = h2 * ri;
                 e[i + 1] = r;
                 s = f * ri; c = g * ri;
-                g = d[i + 1] - p;
-                r = (d[i] - g) * s + 2.0 * c * bq;
+                g = d_ip1 - p;
+                r = (d_i - g) * s + 2.0 * c * bq;
                 p = s * r;
                 d[i + 1] = g + p;
                 g = c * r - bq;
                 cs[buf][i] = c; sn[buf][i] = s;
+                e_i = e_n; d_ip1 = d_i; d_i = d_n;
             }
             if (!under) { d[l] -= p; e[l] = g; e[m] = 0.0; }
             sd.valid = 1; sd.m = m; sd.iend = under ? i + 1 : l;

@@ -12,6 +12,7 @@
 
 // meta[b][8]: 0 k (rows of W), 1 len (row length), 2 orient (0: W = M, 1: W = M^H), 3 rows(M), 4 cols(M), 5 done, 6 sweeps, 7 spare
 constexpr int META = 8;
+constexpr int SVD_KMAX = 1024;
 
 __global__ void k_svd_prepare(int mode, int dphys, const cplx* __restrict__ src, long long s_src, cplx* w, long long s_w, cplx* q, long long s_q,
                               int* meta, int* rot_count, const int* el, int esl, const int* er, int esr, const int* mask) {
@@ -221,7 +222,6 @@ __device__ int truncate_keep(const double* s, int n, int mode, double threshold,
     return min(keep, n);
 }
 
-constexpr int SVD_KMAX = 1024;
 
 // One CTA per trajectory.
 __global__ void __launch_bounds__(512) k_svd_finalize(int trunc_mode, double threshold, int max_bond, int min_keep, int dist, const cplx* __restrict__ w,
@@ -357,5 +357,63 @@ __global__ void __launch_bounds__(512) k_svd_finalize(int trunc_mode, double thr
             }
         }
         __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Second level of the Gram route.  The eigenvalues of a Gram matrix carry an ABSOLUTE error ~ k eps s_max^2, so after the
+// first rotation the rows of Wf whose squared norm is below tau_rel * s_max^2 are only orthogonal to that absolute level.
+// They are gathered into a compact block, re-diagonalised through THEIR OWN Gram matrix (whose scale is tau_rel times
+// smaller, hence tau_rel times more accurate) and scattered back -- the singular values around the 1e-12 discarded-weight
+// threshold of the gauge shifts (mps.py:757-759) come out with ~1e-8 relative accuracy instead of ~1e-3.
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(512) k_svd_select(const cplx* __restrict__ w, long long s_w, const int* meta, double tau_rel, int* sel_n,
+                                                     int* sel_idx, int max_k, const int* mask) {
+    __shared__ double nu[SVD_KMAX];
+    const int b = blockIdx.x;
+    if (mask && !mask[b]) { if (threadIdx.x == 0) sel_n[b] = 0; return; }
+    const int* m = meta + b * META;
+    const int k = m[0], len = m[1];
+    const cplx* wb = w + (long long)b * s_w;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    for (int i = warp; i < k; i += nwarps) {
+        double s = 0.0;
+        for (int e = lane; e < len; e += 32) s += cabs2(wb[(long long)i * len + e]);
+        s = warp_sum(s);
+        if (lane == 0) nu[i] = s;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        double mx = 0.0;
+        for (int i = 0; i < k; ++i) mx = fmax(mx, nu[i]);
+        int n = 0;
+        int* idx = sel_idx + (long long)b * max_k;
+        for (int i = 0; i < k; ++i) if (nu[i] < tau_rel * mx) idx[n++] = i;
+        sel_n[b] = n >= 2 ? n : 0;
+    }
+}
+
+// dir = 0: ws[r] = w[idx[r]], qs[r] = q[idx[r]] ;  dir = 1: the reverse.
+__global__ void k_svd_gather(int dir, cplx* w, long long s_w, cplx* q, long long s_q, cplx* ws, long long s_ws, cplx* qs, long long s_qs,
+                             const int* meta, const int* sel_n, const int* sel_idx, int max_k, const int* mask) {
+    const int b = blockIdx.y;
+    if (mask && !mask[b]) return;
+    const int n = sel_n[b];
+    if (n <= 0) return;
+    const int* m = meta + b * META;
+    const int k = m[0], len = m[1];
+    const int* idx = sel_idx + (long long)b * max_k;
+    cplx* wb = w + (long long)b * s_w; cplx* qb = q + (long long)b * s_q;
+    cplx* wsb = ws + (long long)b * s_ws; cplx* qsb = qs + (long long)b * s_qs;
+    const long long nw = (long long)n * len, nq = (long long)n * k;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < nw + nq; e += (long long)gridDim.x * blockDim.x) {
+        if (e < nw) {
+            const int r = (int)(e / len), c = (int)(e % len);
+            if (dir == 0) wsb[e] = wb[(long long)idx[r] * len + c]; else wb[(long long)idx[r] * len + c] = wsb[e];
+        } else {
+            const long long f = e - nw;
+            const int r = (int)(f / k), c = (int)(f % k);
+            if (dir == 0) qsb[f] = qb[(long long)idx[r] * k + c]; else qb[(long long)idx[r] * k + c] = qsb[f];
+        }
     }
 }

@@ -237,6 +237,9 @@ class BatchedTJM:
             self.heev_d = torch.zeros(B * sd, dtype=torch.float64, device=dev)
             self.heev_e = torch.zeros(B * sd, dtype=torch.float64, device=dev)
             self.heev_tau = torch.zeros(B * sd, dtype=C128, device=dev)
+            self.heev_s = torch.zeros(B * sd * sd, dtype=C128, device=dev)
+            self.sel_n = torch.zeros(B, dtype=torch.int32, device=dev)
+            self.sel_idx = torch.zeros(B * sd, dtype=torch.int32, device=dev)
             self.status_scratch = torch.zeros(B, dtype=torch.int32, device=dev)
             self._iota_sd = torch.arange(sd, device=dev)
         # noise tables
@@ -372,30 +375,48 @@ class BatchedTJM:
         else:
             self._svd_jacobi(mode, src, el, er, trunc, dist, mask)
 
+    GRAM_TAU = 1e-6          # rows below GRAM_TAU * s_max^2 are re-diagonalised at their own scale (second level)
+
     def _svd_gram(self, mode: int, src: Buf, el: Ext, er: Ext, trunc, dist: str, mask) -> None:
-        """M = U S Vh through the Hermitian eigen-problem of the Gram matrix over the index that must become an isometry
-        (rows for dist='right', columns for dist='left'): the isometric factor is the eigenvector matrix itself and the
-        other factor is the exact product E^H M, so no division by a singular value ever happens.  The eigenvalues of a
-        Gram matrix carry an ABSOLUTE error ~ k eps s_max^2; trajectories whose keep decision lies within that error of
-        the threshold are redone with the Jacobi route (high relative accuracy)."""
+        """M = U S Vh through the Hermitian eigen-problem of a Gram matrix.
+        * split_two_site matrices (THETA): the Gram matrix is taken over the index that must become an isometry (rows for
+          dist='right', columns for dist='left'), so the isometric factor is the eigenvector matrix itself and the other
+          factor is the exact product E^H M -- no division by a singular value.
+        * gauge shifts (ROWS / COLS): Gram matrix over the SMALL side (chi x chi instead of 2 chi x 2 chi).
+        Gram eigenvalues carry an ABSOLUTE error ~ k eps s_max^2.  When the truncation threshold is small (the 1e-12 of the
+        gauge shifts) the rows below GRAM_TAU * s_max^2 are re-diagonalised through their own Gram matrix (second level).
+        Trajectories whose keep decision still lies within the error bound of the threshold are redone with the one-sided
+        Jacobi (high relative accuracy)."""
         K, B, lay = self.K, self.B, self.lay
         sd = lay.svd_dim
         sq = sd * sd
         w, q = self._buf(self.svd_w, sq), self._buf(self.svd_q, sq)
         g, qh, zt = self._buf(self.heev_g, sq), self._buf(self.heev_q, sq), self._buf(self.heev_z, sq)
-        orient = SVD_ORIENT_ROWS if dist == "right" else SVD_ORIENT_COLS
+        tm, thr, mb, mk = trunc
+        orient = 0 if mode != SVD_THETA else (SVD_ORIENT_ROWS if dist == "right" else SVD_ORIENT_COLS)
         K.svd_prepare(B, mask, mode | orient, el, er, self.d, src, w, q, self.svd_meta, self.svd_rot)
         ek, eln = Ext(self.svd_meta, 0, SVD_META), Ext(self.svd_meta, 1, SVD_META)
         K.gemm(OP_GRAM, B, 1, mask, ek, eln, None, 1, 1, 1, w, w, g, 0, sd, sd)
         self.status_scratch.zero_()
         K.heev(B, mask, ek, g, qh, zt, self.heev_zr, sq, self.heev_d, self.heev_e, self.heev_tau, sd, self.svd_meta, self.status_scratch, sd)
         K.gemm(OP_EVEC, B, 1, mask, ek, None, None, 1, 1, 1, zt, qh, q, 0, sd, sd)
-        K.gemm(OP_ROTATE, B, 1, mask, ek, eln, None, 1, 1, 1, q, w, g, 0, sd, sd)
-        tm, thr, mb, mk = trunc
+        K.gemm(OP_ROTATE, B, 1, mask, ek, eln, None, 1, 1, 1, q, w, g, 0, sd, sd)          # Wf -> heev_g
+        two_level = thr < 1e-7
+        if two_level:
+            ws, qs, g2, hs = w, self._buf(self.svd_u, sq), self._buf(self.svd_v, sq), self._buf(self.heev_s, sq)
+            K.svd_select(B, mask, self.svd_meta, g, self.GRAM_TAU, self.sel_n, self.sel_idx, sd)
+            K.svd_gather(B, mask, self.svd_meta, self.sel_n, self.sel_idx, sd, 0, g, q, ws, qs)
+            en = Ext(self.sel_n, 0, 1)
+            K.gemm(OP_GRAM, B, 1, mask, en, eln, None, 1, 1, 1, ws, ws, g2, 0, sd, sd)
+            K.heev(B, mask, en, g2, qh, zt, self.heev_zr, sq, self.heev_d, self.heev_e, self.heev_tau, sd, None, self.status_scratch, sd)
+            K.gemm(OP_EVEC, B, 1, mask, en, None, None, 1, 1, 1, zt, qh, g2, 0, sd, sd)
+            K.gemm(OP_ROTATE, B, 1, mask, en, eln, None, 1, 1, 1, g2, ws, hs, 0, sd, sd)
+            K.gemm(OP_ROTATE, B, 1, mask, en, ek, None, 1, 1, 1, g2, qs, ws, 0, sd, sd)
+            K.svd_gather(B, mask, self.svd_meta, self.sel_n, self.sel_idx, sd, 1, g, q, hs, ws)
         K.svd_finalize(B, mask, self.svd_meta, tm, thr, mb, mk, DIST[dist], g, q, self.svd_s, sd, Ext(self.keep, 0, 1),
                        self._buf(self.svd_u, sq), self._buf(self.svd_v, sq), self.status_scratch, sd)
         self.stats["gram_svd_calls"] += 1
-        # ---- decisions within the Gram error of the threshold -> Jacobi
+        # ---- keep decisions within the error bound of the threshold -> Jacobi
         meta = self.svd_meta.view(B, SVD_META)
         nsv = torch.minimum(meta[:, 3], meta[:, 4])
         valid = self._iota_sd[None, :] < nsv[:, None]
@@ -403,15 +424,17 @@ class BatchedTJM:
         s2 = torch.where(valid, s * s, torch.zeros_like(s))
         smax2 = s2[:, 0]
         noise = 16.0 * sd * 2.220446049250313e-16
+        err = noise * smax2[:, None].expand(B, sd)
+        if two_level:
+            err = torch.where(s2 >= self.GRAM_TAU * smax2[:, None], err, err * self.GRAM_TAU)
         if tm == 0:
             if thr > 0.0:
                 cum = torch.flip(torch.cumsum(torch.flip(s2, dims=[1]), dim=1), dims=[1])
-                amb = (((cum - thr).abs() <= (noise * smax2 + 1e-7 * thr)[:, None]) & valid).any(dim=1)
+                amb = (((cum - thr).abs() <= err + 1e-9 * thr) & valid).any(dim=1)
             else:
                 amb = torch.zeros(B, dtype=torch.bool, device=self.dev)
         else:
-            ratio2 = s2 / torch.clamp(smax2, min=1e-300)[:, None]
-            amb = (((ratio2 - thr * thr).abs() <= noise) & valid).any(dim=1)
+            amb = (((s2 - thr * thr * smax2[:, None]).abs() <= err) & valid).any(dim=1)
         amb |= (meta[:, 5] == 0) | (self.status_scratch != 0) | ~torch.isfinite(smax2)
         if mask is not None:
             amb &= (mask != 0)
@@ -457,7 +480,7 @@ class BatchedTJM:
         isometry the SVD of the centre tensor alone gives the same singular values / keep decision."""
         lay, K, B, d = self.lay, self.K, self.B, self.d
         sd = lay.svd_dim
-        self._svd(SVD_ROWS, st.site(i), st.ext(i), st.ext(i + 1), trunc, "right", mask, d * lay.cap[i] if fast else 0)
+        self._svd(SVD_ROWS, st.site(i), st.ext(i), st.ext(i + 1), trunc, "right", mask, min(d * lay.cap[i], lay.cap[i + 1]) if fast else 0)
         kx = Ext(self.keep, 0, 1)
         K.copy_packed(B, mask, st.ext(i), kx, d, self._buf(self.svd_u, sd * sd), st.site(i), lay.slot[i])
         tmp = self._buf(self.tmp, lay.nloc_max)
@@ -470,7 +493,7 @@ class BatchedTJM:
         """Centre i -> i-1 (mps.py:771-788), reduced form (site i-1 must be a left isometry)."""
         lay, K, B, d = self.lay, self.K, self.B, self.d
         sd = lay.svd_dim
-        self._svd(SVD_COLS, st.site(i), st.ext(i), st.ext(i + 1), trunc, "left", mask, d * lay.cap[i + 1] if fast else 0)
+        self._svd(SVD_COLS, st.site(i), st.ext(i), st.ext(i + 1), trunc, "left", mask, min(lay.cap[i], d * lay.cap[i + 1]) if fast else 0)
         kx = Ext(self.keep, 0, 1)
         tmp = self._buf(self.tmp, lay.nloc_max)
         K.gemm(OP_ABSORB_L, B, d, mask, st.ext(i - 1), st.ext(i), kx, d, 1, 1, st.site(i - 1), self._buf(self.svd_u, sd * sd), tmp, 0,
@@ -816,7 +839,7 @@ class BatchedTJM:
         shift = self._trunc_args("discarded_weight", SHIFT_THRESHOLD, None, 1)
         user = self._trunc_args(p.trunc_mode, p.svd_threshold, p.max_bond_dim, 1)
         for i in range(n - 1):
-            self.shift_right(st, i, keep_all, jmask)
+            self.shift_right(st, i, keep_all, jmask, fast=True)
         # per-trajectory operator tables
         kinds = {pr.kind for pr in tab}
         site_a = torch.tensor([pr.sites[0] for pr in tab], dtype=torch.int32, device=dev)[choice]
@@ -844,7 +867,7 @@ class BatchedTJM:
                         continue
                     th = self.merge(st, s, m_s)
                     K.apply_local_op(B, m_s, None, 0, st.ext(s), st.ext(s + 2), d * d, ops_c.view(-1), d * d * d * d, th, lay.cap[s] * lay.cap[s + 2])
-                    self.split_theta(st, s, "right", user, m_s)
+                    self.split_theta(st, s, "right", user, m_s, fast=True)
                 broken.append(torch.where(mask_c != 0, site_c + 1, torch.full_like(site_c, -1)))
         # normalize("B", "SVD"): right-to-left merged SVD shifts.  Where the left neighbour is still a left isometry the
         # reduced shift is identical; where it carries a jump operator the literal merge + split is needed.
@@ -858,9 +881,9 @@ class BatchedTJM:
             nlit = K.sync_int(lit_mask.sum())
             if nlit > 0:
                 self.merge(st, i - 1, lit_mask)
-                self.split_theta(st, i - 1, "left", th_trunc_left, lit_mask)
+                self.split_theta(st, i - 1, "left", th_trunc_left, lit_mask, fast=True)
             if nlit < K.sync_int(jmask.sum()):
-                self.shift_left(st, i, shift, red_mask)
+                self.shift_left(st, i, shift, red_mask, fast=True)
         self.normalize_site(st, 0, jmask)
 
     # ------------------------------------------------------------------------------------------------------------------

@@ -69,7 +69,7 @@ def load_library() -> ctypes.CDLL:
 
 EXPORTED_SYMBOLS = [
     "yb_last_error", "yb_version", "yb_launch_count", "yb_set_flop_counter", "yb_gemm", "yb_wapply", "yb_env_identity", "yb_lanczos_init",
-    "yb_lanczos_step", "yb_lanczos_combine", "yb_svd_prepare", "yb_svd_round", "yb_svd_check", "yb_svd_finalize", "yb_heev",
+    "yb_lanczos_step", "yb_lanczos_combine", "yb_svd_prepare", "yb_svd_round", "yb_svd_check", "yb_svd_finalize", "yb_heev", "yb_svd_select", "yb_svd_gather",
     "yb_unpack_vh", "yb_copy_packed", "yb_apply_local_op", "yb_norm2", "yb_scale", "yb_local_rdm",
 ]
 
@@ -213,6 +213,15 @@ class CudaKernels:
             nbatch, self._ptr(mask), self._ext(ek), self._cptr(g), ctypes.c_int64(g.stride), self._cptr(qh), ctypes.c_int64(qh.stride),
             self._cptr(zt), ctypes.c_int64(zt.stride), self._ptr(zr), ctypes.c_int64(stride_zr), self._ptr(d), self._ptr(e), self._ptr(tau),
             ctypes.c_int64(stride_vec), self._ptr(meta), self._ptr(status), int(max_k), self._stream())))
+
+    def svd_select(self, nbatch, mask, meta, w: Buf, tau_rel, sel_n, sel_idx, max_k):
+        self._check(self.lib.yb_svd_select(nbatch, self._ptr(mask), self._ptr(meta), self._cptr(w), ctypes.c_int64(w.stride),
+                                           ctypes.c_double(tau_rel), self._ptr(sel_n), self._ptr(sel_idx), int(max_k), self._stream()))
+
+    def svd_gather(self, nbatch, mask, meta, sel_n, sel_idx, max_k, direction, w: Buf, q: Buf, ws: Buf, qs: Buf):
+        self._check(self.lib.yb_svd_gather(nbatch, self._ptr(mask), self._ptr(meta), self._ptr(sel_n), self._ptr(sel_idx), int(max_k),
+                                           int(direction), self._cptr(w), ctypes.c_int64(w.stride), self._cptr(q), ctypes.c_int64(q.stride),
+                                           self._cptr(ws), ctypes.c_int64(ws.stride), self._cptr(qs), ctypes.c_int64(qs.stride), self._stream()))
 
     # -- site-tensor utilities ----------------------------------------------------------------------------------------
     def unpack_vh(self, nbatch, mask, ek, er, dphys, src: Buf, dst: Buf, max_elems):
