@@ -118,3 +118,54 @@ def run_oracle_case(cfg: dict, trajectories=None):
             tr_out = O.analog_tjm_1(init, mpo, noise, p, obs, rng)
         out.append(tr_out)
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# digital TJM fixtures: Ising Trotter circuits (core/libraries/circuit_library.py:28-79), hand-compiled to layers
+# ---------------------------------------------------------------------------------------------
+DIGITAL_CASES = {
+    # BASELINE config 4 in miniature: NN circuit (TEBD path), relaxation + dephasing on every qubit, sampled every Trotter step
+    "dig_ising6_nn_noisy": dict(L=6, J=1.0, g=0.9, dt=0.3, timesteps=5, periodic=False, chi=8, thr=1e-9, ntraj=6, seed=42,
+                                init="zeros", obs="z", sample=True, gate_mode="mpo",
+                                noise=[("lowering", 0.05), ("pauli_z", 0.03)]),
+    # two-qubit Pauli noise on every NN pair ("2-qubit depolarizing"-style channel from crosstalk_ab processes), x+ start
+    "dig_ising5_pair_noise": dict(L=5, J=1.0, g=0.8, dt=0.3, timesteps=4, periodic=False, chi=4, thr=1e-8, ntraj=6, seed=7,
+                                  init="x+", obs="z+zz", sample=False, gate_mode="mpo",
+                                  noise=[("pauli_x", 0.04)],
+                                  noise2=[("crosstalk_xx", 0.05), ("crosstalk_zy", 0.03), ("crosstalk_yz", 0.03)]),
+    # noise-free circuit (one deterministic trajectory), sampled
+    "dig_ising6_noiseless": dict(L=6, J=1.0, g=0.7, dt=0.3, timesteps=5, periodic=False, chi=8, thr=1e-10, ntraj=1, seed=1,
+                                 init="x+", obs="x+z", sample=True, gate_mode="mpo", noise=[]),
+    # periodic circuit: the long-range rzz(0, L-1) runs through the TDVP gate window (gate_mode="tdvp"), no bond cap
+    "dig_ising5_periodic_window": dict(L=5, J=1.0, g=0.8, dt=0.25, timesteps=4, periodic=True, chi=None, thr=1e-9, ntraj=4, seed=11,
+                                       init="zeros", obs="z", sample=True, gate_mode="tdvp",
+                                       noise=[("lowering", 0.04), ("pauli_z", 0.04)]),
+}
+
+
+def digital_inputs(cfg: dict):
+    """(initial OracleMPS, layers, noise | None, OracleParams, sorted observables)."""
+    L = cfg["L"]
+    layers = O.ising_trotter_layers(L, cfg["J"], cfg["g"], cfg["dt"], cfg["timesteps"], cfg["periodic"], sample_each_step=cfg["sample"])
+    obs = []
+    for tok in cfg["obs"].split("+"):
+        if tok in ("x", "y", "z"):
+            obs += [(O.OBSERVABLE_MATRICES[tok], [s]) for s in range(L)]
+        else:
+            obs += [(O.OBSERVABLE_MATRICES[tok], [s, s + 1]) for s in range(L - 1)]
+    order = O.sort_observables(obs)
+    obs = [obs[k] for k in order]
+    procs = [O.make_process(n, [i], g) for i in range(L) for (n, g) in cfg["noise"]]
+    procs += [O.make_process(n, [i, i + 1], g) for i in range(L - 1) for (n, g) in cfg.get("noise2", [])]
+    p = O.OracleParams(dt=1.0, n_steps=1, order=1, max_bond_dim=cfg["chi"], svd_threshold=cfg["thr"], krylov_tol=cfg.get("krylov_tol", 1e-4),
+                       digital=True)
+    return O.product_state(L, cfg["init"]), layers, (procs if procs else None), p, obs
+
+
+def run_oracle_digital_case(cfg: dict, trajectories=None):
+    init, layers, noise, p, obs = digital_inputs(cfg)
+    out = []
+    for tr in (range(cfg["ntraj"]) if trajectories is None else trajectories):
+        rng = O.UniformStream(O.trajectory_stream(cfg["seed"], tr))
+        out.append(O.digital_tjm(init, layers, noise, p, obs, rng, sample_layers=cfg["sample"], gate_mode=cfg["gate_mode"]))
+    return out

@@ -23,7 +23,7 @@ from oracle.ref_shim import load_reference  # noqa: E402
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
 
-from oracle.golden_cases import CASES, initial_state  # noqa: E402
+from oracle.golden_cases import CASES, DIGITAL_CASES, initial_state  # noqa: E402
 
 
 class _RecordingRng:
@@ -138,11 +138,102 @@ def run_case(name: str, cfg: dict) -> dict:
                 sorted_obs_names=np.array(sorted_names), times=np.asarray(sim.times), krylov_tol=np.float64(sim.krylov_tol))
 
 
+def run_digital_case(name: str, cfg: dict) -> dict:
+    """Run the reference's digital_tjm (digital/digital_tjm.py:636) on a hand-compiled Ising Trotter circuit.  qiskit is
+    absent here, so the DAG front end is bypassed exactly as SURVEY.md 8(c) shim 3 describes: the layers the reference's
+    _compile_circuit would produce for create_ising_circuit (one gate per layer, even/odd by lowest qubit) are built
+    from the reference's own GateLibrary gates and passed through ``compiled_circuit=``."""
+    load_reference()
+    import mqt.yaqs.digital.digital_tjm as ref_dig
+    from mqt.yaqs.core.data_structures.mps import MPS
+    from mqt.yaqs.core.data_structures.noise_model import NoiseModel
+    from mqt.yaqs.core.data_structures.simulation_parameters import DigitalSimParams, Observable
+    from mqt.yaqs.core.libraries.gate_library import ZZ, GateLibrary, X, Z
+    from mqt.yaqs.core.random_utils import make_trajectory_rng
+
+    L = cfg["L"]
+    alpha, beta = -2 * cfg["dt"] * cfg["g"], -2 * cfg["dt"] * cfg["J"]
+    layers = []
+
+    def layer(single=(), even=(), odd=(), pts=0):
+        return ref_dig._CompiledCircuitLayer(tuple(single), tuple(even), tuple(odd), pts)
+
+    for step in range(cfg["timesteps"]):
+        for s in range(L):
+            g = GateLibrary.rx([alpha])
+            g.set_sites(s)
+            layers.append(layer(single=[g]))
+        pairs = [(2 * s, 2 * s + 1) for s in range(L // 2)] + [(2 * s - 1, 2 * s) for s in range(1, L // 2)]
+        if L % 2 != 0 and L != 1:
+            pairs.append((L - 2, L - 1))
+        if cfg["periodic"] and L > 1:
+            pairs.append((0, L - 1))
+        for a, b in pairs:
+            g = GateLibrary.rzz([beta])
+            g.set_sites(a, b)
+            layers.append(layer(even=[g]) if min(a, b) % 2 == 0 else layer(odd=[g]))
+        if cfg["sample"] and step < cfg["timesteps"] - 1:
+            layers.append(layer(pts=1))
+    mid = sum(l.sample_points for l in layers)
+    compiled = ref_dig._CompiledCircuit(tuple(layers), mid)
+
+    obs = []
+    for tok in cfg["obs"].split("+"):
+        if tok == "z":
+            obs += [Observable(Z(), s) for s in range(L)]
+        elif tok == "x":
+            obs += [Observable(X(), s) for s in range(L)]
+        elif tok == "zz":
+            obs += [Observable(ZZ(), [s, s + 1]) for s in range(L - 1)]
+    procs = [{"name": n, "sites": [i], "strength": g} for i in range(L) for (n, g) in cfg["noise"]]
+    procs += [{"name": n, "sites": [i, i + 1], "strength": g} for i in range(L - 1) for (n, g) in cfg.get("noise2", [])]
+    noise = NoiseModel(procs) if procs else None
+    sim = DigitalSimParams(observables=obs, num_traj=cfg["ntraj"], max_bond_dim=cfg["chi"], svd_threshold=cfg["thr"],
+                           sample_layers=cfg["sample"], random_seed=cfg["seed"], gate_mode=cfg["gate_mode"])
+    sim.num_mid_measurements = mid
+    out_res, out_diag, out_bonds, logs = [], [], [], []
+    orig_record = MPS.record_diagnostics
+    for tr in range(cfg["ntraj"]):
+        log: list[dict] = []
+        bonds: list[list[int]] = []
+
+        def rec(self, diagnostics, column_index, _b=bonds):
+            _b.append([t.shape[1] for t in self.tensors[1:]])
+            return orig_record(self, diagnostics, column_index)
+
+        MPS.record_diagnostics = rec
+        try:
+            mps = MPS(L, state=cfg["init"])
+            rng = _RecordingRng(make_trajectory_rng(tr, base_seed=cfg["seed"]), log, "traj")
+            res, diag, _counts, _final = ref_dig.digital_tjm((tr, mps, noise, sim, None), rng=rng, compiled_circuit=compiled)
+        finally:
+            MPS.record_diagnostics = orig_record
+        out_res.append(np.asarray(res, dtype=np.float64))
+        out_diag.append(np.asarray(diag, dtype=np.float64))
+        out_bonds.append(bonds)
+        logs.append(log)
+    ncalls = max([len(lg) for lg in logs] + [1])
+    nproc = max([len(r["p"]) for lg in logs for r in lg] + [1])
+    nt = cfg["ntraj"]
+    u1 = np.full((nt, ncalls), np.nan)
+    u2 = np.full((nt, ncalls), np.nan)
+    jumped = np.zeros((nt, ncalls), dtype=np.int8)
+    choice = np.full((nt, ncalls), -1, dtype=np.int32)
+    pdf = np.zeros((nt, ncalls, nproc))
+    for t, lg in enumerate(logs):
+        for c, r in enumerate(lg):
+            u1[t, c], u2[t, c], jumped[t, c], choice[t, c] = r["u1"], r["u2"], r["jumped"], r["choice"]
+            pdf[t, c, :len(r["p"])] = r["p"]
+    return dict(results=np.array(out_res), diagnostics=np.array(out_diag), bonds=np.array(out_bonds, dtype=np.int32), u1=u1, u2=u2,
+                jumped=jumped, choice=choice, pdf=pdf, ncalls=np.array([len(lg) for lg in logs], dtype=np.int32),
+                sorted_obs_names=np.array([o.gate.name for o in sim.sorted_observables]))
+
+
 def main(argv: list[str]) -> int:
     os.makedirs(GOLDEN_DIR, exist_ok=True)
-    names = argv or list(CASES)
+    names = argv or (list(CASES) + list(DIGITAL_CASES))
     for name in names:
-        data = run_case(name, CASES[name])
+        data = run_digital_case(name, DIGITAL_CASES[name]) if name in DIGITAL_CASES else run_case(name, CASES[name])
         path = os.path.join(GOLDEN_DIR, f"{name}.npz")
         np.savez_compressed(path, **data)
         njump = int(data["jumped"].sum())

@@ -41,3 +41,21 @@ def check_against_golden(name, golden_dir, results, diag, log, traj, obs_tol=1e-
                 assert int(rec["choice"][row]) == int(g["choice"][t, c]), (name, t, c)
                 npr = rec["pdf"].shape[1]
                 assert np.max(np.abs(rec["pdf"][row] - g["pdf"][t, c, :npr])) < 1e-9
+
+
+def digital_engine_for_case(name, kernels, trajectories=None, **kw):
+    """BatchedTJM + compiled layers + uniform table for a digital fixture (oracle/golden_cases.DIGITAL_CASES)."""
+    from oracle.golden_cases import DIGITAL_CASES, digital_inputs
+    from yaqs_b200.circuits import compile_circuit, create_ising_circuit
+    cfg = DIGITAL_CASES[name]
+    init, _layers, noise, p, obs = digital_inputs(cfg)
+    L = cfg["L"]
+    compiled = compile_circuit(create_ising_circuit(L, cfg["J"], cfg["g"], cfg["dt"], cfg["timesteps"], periodic=cfg["periodic"],
+                                                    sample_every_step=cfg["sample"]))
+    traj = list(range(cfg["ntraj"])) if trajectories is None else list(trajectories)
+    ep = EngineParams(dt=1.0, n_steps=1, order=1, max_bond_dim=cfg["chi"], svd_threshold=cfg["thr"], krylov_tol=p.krylov_tol, digital=True)
+    mpo = [np.eye(2, dtype=np.complex128).reshape(2, 2, 1, 1) for _ in range(L)]
+    eng = BatchedTJM(kernels, L, len(traj), mpo, ep, noise if noise is not None else None, obs, init.tensors, **kw)
+    n2q = sum(len(l.even_two_qubit_gates) + len(l.odd_two_qubit_gates) for l in compiled.layers)
+    tu, _ = numpy_tables(cfg["seed"], traj, max(n2q, 1), 1)
+    return eng, compiled, torch.from_numpy(tu).to(kernels.device), traj, cfg

@@ -46,3 +46,21 @@ def test_cuda_engine_gram_svd_route(golden_dir, name):
     assert int(eng.status.max().item()) == 0
     assert eng.stats["gram_svd_calls"] > 0
     check_against_golden(name, golden_dir, results, diag, log, traj)
+
+
+from oracle.golden_cases import DIGITAL_CASES  # noqa: E402
+from tests.helpers import digital_engine_for_case  # noqa: E402
+
+
+@pytest.mark.parametrize("name", sorted(DIGITAL_CASES))
+@pytest.mark.parametrize("gram_min_k", [33, 0])
+def test_cuda_digital_tjm_matches_reference(golden_dir, name, gram_min_k):
+    """Digital TJM on the B200 through the C ABI vs the unmodified reference's digital_tjm (TEBD gates, per-gate local
+    noise and jumps, TDVP gate windows, sample barriers); also with the Gram-SVD route forced."""
+    kern = CudaKernels("cuda:0")
+    eng, compiled, tu, traj, cfg = digital_engine_for_case(name, kern, gram_min_k=gram_min_k)
+    log = []
+    results, diag = eng.run_digital(compiled.layers, tu, cfg["sample"], cfg["gate_mode"], log)
+    torch.cuda.synchronize()
+    assert int(eng.status.max().item()) == 0
+    check_against_golden(name, golden_dir, results, diag, log, traj)

@@ -1,0 +1,188 @@
+"""Qiskit-free circuit description + the reference's layer compilation for the digital TJM.
+
+The reference takes a qiskit ``QuantumCircuit`` and schedules it with ``circuit_to_dag`` / ``dag.front_layer()``
+(digital/digital_tjm.py:142-184, 233-301).  qiskit is not available on the B200 boxes, so this module provides
+  * ``Circuit``: a minimal gate list with the qiskit-style builder methods the YAQS circuit library uses
+    (``rx, ry, rz, h, x, ..., rzz, rxx, ryy, cx, cz, swap, cp, barrier(label=...)``),
+  * ``compile_circuit``: the same front-layer scheduling restated on that list -- per layer: single-qubit gates, then
+    multi-qubit gates split into "even" / "odd" groups by their lowest qubit index, labelled ``SAMPLE_OBSERVABLES``
+    barriers as sample points, other barriers dropped, terminal measurements dropped, and
+  * ``create_ising_circuit`` (core/libraries/circuit_library.py:28-79).
+A real ``qiskit.QuantumCircuit`` is accepted too when qiskit is importable (converted through ``circuit.data``).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+from .gates import BaseGate, GateLibrary
+
+SAMPLE_LABEL = "SAMPLE_OBSERVABLES"
+_PARAM_GATES = {"rx", "ry", "rz", "p", "rxx", "ryy", "rzz", "cp", "u"}
+_FIXED_GATES = {"x", "y", "z", "h", "id", "sx", "s", "sdg", "t", "tdg", "cx", "cz", "swap"}
+
+
+@dataclass
+class Op:
+    name: str
+    qubits: tuple[int, ...]
+    params: tuple[float, ...] = ()
+    label: str | None = None
+
+
+@dataclass
+class Circuit:
+    """Ordered gate list on ``num_qubits`` wires (the subset of qiskit's builder API that the YAQS libraries use)."""
+    num_qubits: int
+    ops: list[Op] = field(default_factory=list)
+
+    def _add(self, name, qubits, params=(), label=None):
+        for q in qubits:
+            if not 0 <= q < self.num_qubits:
+                raise ValueError(f"qubit index {q} out of range for a {self.num_qubits}-qubit circuit")
+        self.ops.append(Op(name, tuple(int(q) for q in qubits), tuple(float(p) for p in params), label))
+        return self
+
+    def barrier(self, *qubits, label: str | None = None):
+        return self._add("barrier", qubits if qubits else tuple(range(self.num_qubits)), label=label)
+
+    def measure_all(self):
+        for q in range(self.num_qubits):
+            self._add("measure", (q,))
+        return self
+
+    def __getattr__(self, name):
+        if name in _FIXED_GATES:
+            return lambda *qubits: self._add(name, qubits)
+        if name in _PARAM_GATES:
+            nparam = 3 if name == "u" else 1
+
+            def add(*args, **kw):
+                vals = list(args) + [kw[k] for k in ("theta", "phi", "lam") if k in kw]
+                qs = [kw[k] for k in ("qubit", "qubit1", "qubit2") if k in kw]
+                params, qubits = vals[:nparam], vals[nparam:] + qs
+                return self._add(name, qubits, params)
+            return add
+        raise AttributeError(name)
+
+
+@dataclass(frozen=True)
+class CompiledLayer:
+    """digital_tjm.py:49-60."""
+    single_qubit_gates: tuple
+    even_two_qubit_gates: tuple
+    odd_two_qubit_gates: tuple
+    sample_points: int
+
+
+@dataclass(frozen=True)
+class CompiledCircuit:
+    layers: tuple
+    num_mid_measurements: int
+
+
+def _to_gate(op: Op) -> BaseGate:
+    """convert_dag_to_tensor_algorithm (digital/utils/dag_utils.py:305): gate matrix + sites."""
+    factory = getattr(GateLibrary, op.name, None)
+    if factory is None:
+        raise ValueError(f"unsupported gate '{op.name}'")
+    gate = factory(*op.params) if op.params else factory()
+    gate.set_sites(*op.qubits)
+    return gate
+
+
+def from_qiskit(qc) -> Circuit:
+    circ = Circuit(qc.num_qubits)
+    for inst in qc.data:
+        op = inst.operation
+        qubits = tuple(qc.find_bit(q).index for q in inst.qubits)
+        circ._add(op.name, qubits, tuple(float(p) for p in getattr(op, "params", ())), getattr(op, "label", None))
+    return circ
+
+
+def compile_circuit(circuit) -> CompiledCircuit:
+    """_compile_circuit + process_layer (digital_tjm.py:142-184, 233-301) on a gate list."""
+    if not isinstance(circuit, Circuit):
+        circuit = from_qiskit(circuit)
+    ops = list(circuit.ops)
+    alive = [True] * len(ops)
+    wires: list[list[int]] = [[] for _ in range(circuit.num_qubits)]      # op indices per wire, program order
+    for k, op in enumerate(ops):
+        for q in op.qubits:
+            wires[q].append(k)
+    head = [0] * circuit.num_qubits
+
+    def front() -> list[int]:
+        out = []
+        for q in range(circuit.num_qubits):
+            while head[q] < len(wires[q]) and not alive[wires[q][head[q]]]:
+                head[q] += 1
+        seen = set()
+        for q in range(circuit.num_qubits):
+            if head[q] < len(wires[q]):
+                k = wires[q][head[q]]
+                if k not in seen and all(wires[w][head[w]] == k for w in ops[k].qubits):
+                    seen.add(k)
+                    out.append(k)
+        return sorted(out)
+
+    def is_terminal_measure(k: int) -> bool:
+        return not any(alive[j] and set(ops[j].qubits) & set(ops[k].qubits) for j in range(k + 1, len(ops)))
+
+    layers, mid = [], 0
+    while any(alive):
+        single, even, odd, samples = [], [], [], []
+        for k in front():
+            op = ops[k]
+            if op.name == "measure":
+                if not is_terminal_measure(k):
+                    raise ValueError("Non-terminal measure operations are not supported during simulation; "
+                                     "removing them would ignore state collapse and classical dependencies.")
+                alive[k] = False
+            elif op.name == "barrier":
+                if op.label is not None and str(op.label).upper() == SAMPLE_LABEL:
+                    samples.append(k)
+                else:
+                    alive[k] = False
+            elif len(op.qubits) == 1:
+                single.append(k)
+            elif min(op.qubits) % 2 == 0:
+                even.append(k)
+            else:
+                odd.append(k)
+        single.sort(key=lambda k: ops[k].qubits[0])
+        even.sort(key=lambda k: min(ops[k].qubits))
+        odd.sort(key=lambda k: min(ops[k].qubits))
+        for k in (*single, *even, *odd, *samples):
+            alive[k] = False
+        mid += len(samples)
+        if single or even or odd or samples:
+            layers.append(CompiledLayer(tuple(_to_gate(ops[k]) for k in single), tuple(_to_gate(ops[k]) for k in even),
+                                        tuple(_to_gate(ops[k]) for k in odd), len(samples)))
+    return CompiledCircuit(tuple(layers), mid)
+
+
+def create_ising_circuit(L: int, J: float, g: float, dt: float, timesteps: int, *, periodic: bool = False,
+                         sample_every_step: bool = False) -> Circuit:
+    """core/libraries/circuit_library.py:28-79 (same gate order, a full barrier after every gate).  ``sample_every_step``
+    adds a labelled SAMPLE_OBSERVABLES barrier after every Trotter step but the last."""
+    alpha, beta = -2 * dt * g, -2 * dt * J
+    circ = Circuit(L)
+    for step in range(timesteps):
+        for site in range(L):
+            circ.rx(alpha, site)
+            circ.barrier()
+        for site in range(L // 2):
+            circ.rzz(beta, 2 * site, 2 * site + 1)
+            circ.barrier()
+        for site in range(1, L // 2):
+            circ.rzz(beta, 2 * site - 1, 2 * site)
+            circ.barrier()
+        if L % 2 != 0 and L != 1:
+            circ.rzz(beta, L - 2, L - 1)
+            circ.barrier()
+        if periodic and L > 1:
+            circ.rzz(beta, 0, L - 1)
+            circ.barrier()
+        if sample_every_step and step < timesteps - 1:
+            circ.barrier(label=SAMPLE_LABEL)
+    return circ

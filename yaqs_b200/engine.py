@@ -183,13 +183,8 @@ class BatchedTJM:
         self.renv = torch.zeros(lay.env_elems, dtype=C128, device=dev)
         self.lenv = torch.zeros(lay.env_elems, dtype=C128, device=dev) if params.tdvp_mode == "1site" else self.renv
         # MPO tensors (shared by all trajectories): W[o,p,a,a'], its left-environment transpose WT[p,o,a',a], merged pairs
-        self.W1 = [torch.from_numpy(np.ascontiguousarray(w, dtype=np.complex128).reshape(-1)).to(dev) for w in mpo]
-        self.W1T = [torch.from_numpy(np.ascontiguousarray(np.transpose(w, (1, 0, 3, 2)), dtype=np.complex128).reshape(-1)).to(dev) for w in mpo]
-        self.W2 = []
-        for i in range(length - 1):
-            m = np.einsum("acei,bdif->abcdef", mpo[i], mpo[i + 1])
-            s = m.shape
-            self.W2.append(torch.from_numpy(np.ascontiguousarray(m.reshape(s[0] * s[1], s[2] * s[3], s[4], s[5])).reshape(-1)).to(dev))
+        self._mpo_cache: dict = {}
+        self._set_mpo(self._upload_mpo(mpo))
         # workspaces
         B = nbatch
         self.theta = torch.zeros(B * lay.theta_slot, dtype=C128, device=dev)
@@ -243,16 +238,40 @@ class BatchedTJM:
             self.status_scratch = torch.zeros(B, dtype=torch.int32, device=dev)
             self._iota_sd = torch.arange(sd, device=dev)
         # noise tables
-        self.noise = list(noise) if noise else None
-        if self.noise is not None and all(pr["strength"] == 0 for pr in self.noise):
-            self.noise_active = False
-        else:
-            self.noise_active = self.noise is not None
-        self._diss_cache: dict[float, list] = {}
-        self.jump_table = self._build_jump_table() if self.noise is not None else []
+        self._noise_cache: dict = {}
+        self._set_noise(self._make_noise_ctx(noise))
         # observables (already in the reference's sorted order)
         self.observables = [(np.asarray(m, dtype=np.complex128), tuple(int(s) for s in sites)) for m, sites in observables]
         self.stats = {"krylov_calls": 0, "matvecs": 0, "svd_calls": 0, "svd_sweeps": 0, "jumps": 0, "gram_svd_calls": 0, "gram_fallbacks": 0}
+
+    # ------------------------------------------------------------------------------------------------------------------
+    # operator / noise contexts (one each on the analog path; per gate on the digital path)
+    # ------------------------------------------------------------------------------------------------------------------
+    def _upload_mpo(self, mpo: Sequence[np.ndarray]) -> dict:
+        dev = self.dev
+        w1 = [torch.from_numpy(np.ascontiguousarray(w, dtype=np.complex128).reshape(-1)).to(dev) for w in mpo]
+        w1t = [torch.from_numpy(np.ascontiguousarray(np.transpose(w, (1, 0, 3, 2)), dtype=np.complex128).reshape(-1)).to(dev) for w in mpo]
+        w2 = []
+        for i in range(len(mpo) - 1):
+            m = np.einsum("acei,bdif->abcdef", mpo[i], mpo[i + 1])
+            sh = m.shape
+            w2.append(torch.from_numpy(np.ascontiguousarray(m.reshape(sh[0] * sh[1], sh[2] * sh[3], sh[4], sh[5])).reshape(-1)).to(dev))
+        return dict(W1=w1, W1T=w1t, W2=w2)
+
+    def _set_mpo(self, ms: dict) -> None:
+        self.W1, self.W1T, self.W2 = ms["W1"], ms["W1T"], ms["W2"]
+
+    def _make_noise_ctx(self, noise) -> dict:
+        ctx = dict(noise=list(noise) if (noise or isinstance(noise, list) and self.p.digital) else None, diss={}, table=[])
+        ctx["active"] = ctx["noise"] is not None and not all(pr["strength"] == 0 for pr in ctx["noise"])
+        return ctx
+
+    def _set_noise(self, ctx: dict) -> None:
+        self._nctx = ctx
+        self.noise, self.noise_active, self._diss_cache = ctx["noise"], ctx["active"], ctx["diss"]
+        if self.noise is not None and not ctx["table"]:
+            ctx["table"] = self._build_jump_table()
+        self.jump_table = ctx["table"]
 
     # ------------------------------------------------------------------------------------------------------------------
     # small helpers
@@ -328,10 +347,13 @@ class BatchedTJM:
         K.wapply(B, None, el, er, d, d, Dr, Dl, self.W1T[s], t1, t2, cl * cr)
         K.gemm(OP_ENVL3, B, 1, None, el, er, None, d, Dl, Dr, a, t2, self.env(s + 1, True), 0, cr, Dr * cr)
 
-    def init_right_envs(self, st: BatchedState) -> None:
-        """initialize_right_environments (primitives.py:139-174)."""
-        self.env_boundaries(st)
-        for s in reversed(range(1, self.L)):
+    def init_right_envs(self, st: BatchedState, lo: int = 0, hi: int | None = None) -> None:
+        """initialize_right_environments (primitives.py:139-174) for the sites lo..hi (a gate window, or the chain)."""
+        hi = self.L - 1 if hi is None else hi
+        lay = self.lay
+        self.K.env_identity(self.B, None, st.ext(hi + 1), lay.D[hi + 1], self.env(hi + 1, False), lay.cap[hi + 1])
+        self.K.env_identity(self.B, None, st.ext(lo), lay.D[lo], self.env(lo, True), lay.cap[lo])
+        for s in reversed(range(lo + 1, hi + 1)):
             self.env_update_right(st, s)
 
     def merge(self, st: BatchedState, i: int, mask=None) -> Buf:
@@ -529,14 +551,18 @@ class BatchedTJM:
         else:
             raise NotImplementedError("tdvp_mode='dynamic' is a SURVEY.md 8(f) 'next' row")
 
-    def sweep_2site(self, st: BatchedState, plan: Sequence[float]) -> None:
-        n, lay, p = self.L, self.lay, self.p
+    def sweep_2site(self, st: BatchedState, plan: Sequence[float], lo: int = 0, hi: int | None = None) -> None:
+        """integrators.py:161-291 on sites lo..hi (default: the whole chain; a sub-range is a digital gate window whose
+        boundary bonds keep their dimension and get identity environments, digital_tjm.py:360-405)."""
+        lay, p = self.lay, self.p
+        hi = self.L - 1 if hi is None else hi
+        n = hi + 1
         trunc = self._trunc_args(p.trunc_mode, p.svd_threshold, p.max_bond_dim, p.tdvp_min_keep)
         th = self._buf(self.theta, lay.theta_slot)
-        self.init_right_envs(st)
+        self.init_right_envs(st, lo, hi)
         for scale in plan:
             dt = self._substep_dt(scale)
-            for i in range(n - 2):
+            for i in range(lo, n - 2):
                 self.merge(st, i)
                 self.update_site(st, i, 2, th, 0.5 * dt)
                 self.split_theta(st, i, "right", trunc, fast=True)
@@ -547,7 +573,7 @@ class BatchedTJM:
             self.update_site(st, i, 2, th, dt)
             self.split_theta(st, i, "left", trunc, fast=True)
             self.env_update_right(st, i + 1)
-            for i in reversed(range(n - 2)):
+            for i in reversed(range(lo, n - 2)):
                 self.update_site(st, i + 1, 1, st.site(i + 1), -0.5 * dt)
                 self.merge(st, i)
                 self.update_site(st, i, 2, th, 0.5 * dt)
@@ -656,14 +682,19 @@ class BatchedTJM:
         self._diss_cache[dt] = out
         return out
 
-    def apply_dissipation(self, st: BatchedState, dt: float) -> None:
+    def apply_dissipation(self, st: BatchedState, dt: float, start: int = 0) -> None:
+        """dissipation.py:50-183; ``start`` = current orthogonality centre (0 on the analog path, the right site of the
+        gate pair after a TEBD gate)."""
         lay, K, B, d, n, p = self.lay, self.K, self.B, self.d, self.L, self.p
         if not self.noise_active:
-            self.normalize_site(st, 0)                      # dissipation.py:79-86 (QR at site 0, R dropped)
+            keep_all = self._trunc_args("discarded_weight", 0.0, None, 1)
+            for i in reversed(range(1, start + 1)):         # dissipation.py:79-86: centre -> 0 with QR shifts
+                self.shift_left(st, i, keep_all, fast=True)
+            self.normalize_site(st, 0)                      # QR at site 0, R dropped
             return
         shift = self._trunc_args("discarded_weight", SHIFT_THRESHOLD, None, 1)
         user = self._trunc_args(p.trunc_mode, p.svd_threshold, p.max_bond_dim, 1)
-        for i in range(n - 1):                              # centre 0 -> L-1 with SVD shifts (:88-92)
+        for i in range(start, n - 1):                       # centre -> L-1 with SVD shifts (:88-92)
             self.shift_right(st, i, shift, fast=True)
         facs = self._dissipators(dt)
         for i in reversed(range(n)):
@@ -973,3 +1004,157 @@ class BatchedTJM:
         self.apply_dissipation(psi, p.dt / 2)
         self.stochastic_process(psi, p.dt, u_sample[:, 0].contiguous(), u_sample[:, 1].contiguous())
         return self.evaluate_observables(psi), self.diagnostics(psi)
+
+    # ------------------------------------------------------------------------------------------------------------------
+    # digital TJM (digital/digital_tjm.py:187-749): gates, per-gate local noise, TDVP gate windows
+    # ------------------------------------------------------------------------------------------------------------------
+    def apply_single_qubit_gate(self, st: BatchedState, gate) -> None:
+        """_apply_single_qubit_gate (digital_tjm.py:304-309).  A unitary on the physical index keeps every isometry
+        condition, so the batch stays in B form (the reference merely loses track of the centre)."""
+        s = gate.sites[0]
+        op = torch.from_numpy(np.ascontiguousarray(gate.matrix, dtype=np.complex128).reshape(-1)).to(self.dev)
+        self.K.apply_local_op(self.B, None, None, 0, st.ext(s), st.ext(s + 1), self.d, op, 0, st.site(s), self.lay.cap[s] * self.lay.cap[s + 1])
+
+    @staticmethod
+    def _resolve_lr_matrix(gate) -> np.ndarray:
+        """resolve_lr_tensor / convert_nn_matrix (mpo_utils.py:104-160) as a 4x4 on the merged index s_left*2 + s_right."""
+        m = np.asarray(gate.matrix, dtype=np.complex128)
+        if gate.sites[0] < gate.sites[1]:
+            return m
+        t = np.zeros((2, 2, 2, 2), dtype=np.complex128)
+        for col in range(4):
+            il, ir = col % 2, col // 2
+            for row in range(4):
+                ol, orr = row % 2, row // 2
+                t[ol, orr, il, ir] = m[row, col]
+        return t.reshape(4, 4)
+
+    def apply_two_qubit_gate_tebd(self, st: BatchedState, gate) -> int:
+        """apply_two_qubit_gate_tebd (digital_tjm.py:455-533) for a nearest-neighbour pair, entered with the centre at 0:
+        QR-equivalent shifts bring the centre to the pair, merge, gate, truncated split with S to the right.
+        Returns the new centre (the right site)."""
+        lay, K, B, d, p = self.lay, self.K, self.B, self.d, self.p
+        left = min(gate.sites)
+        keep_all = self._trunc_args("discarded_weight", 0.0, None, 1)
+        for i in range(left):
+            self.shift_right(st, i, keep_all, fast=True)
+        th = self.merge(st, left)
+        op = torch.from_numpy(np.ascontiguousarray(self._resolve_lr_matrix(gate)).reshape(-1)).to(self.dev)
+        K.apply_local_op(B, None, None, 0, st.ext(left), st.ext(left + 2), d * d, op, 0, th, lay.cap[left] * lay.cap[left + 2])
+        trunc = self._trunc_args(p.trunc_mode, p.svd_threshold, p.max_bond_dim, p.tdvp_min_keep)
+        self.split_theta(st, left, "right", trunc, fast=True)
+        return left + 1
+
+    def apply_two_qubit_gate_tdvp(self, st: BatchedState, gate) -> int:
+        """apply_two_qubit_gate_tdvp (digital_tjm.py:324-452), entered with the centre at 0: generator MPO of bond
+        dimension 1, window = support +- 1 site, one symmetric 2TDVP sweep over the window with evolution time 1.
+        Returns the new centre (the first window site)."""
+        n, lay, K, B, d, p = self.L, self.lay, self.K, self.B, self.d, self.p
+        if gate.generator is None:
+            raise NotImplementedError("gates without a product-form generator need the gate-MPO route (SURVEY.md 8f)")
+        key = (gate.name, tuple(gate.sites), tuple(np.asarray(f).tobytes() for f in gate.generator))
+        if key not in self._mpo_cache:
+            factors = dict(zip(gate.sites, gate.generator))
+            mpo = []
+            for s in range(n):
+                w = np.zeros((2, 2, 1, 1), dtype=np.complex128)
+                w[:, :, 0, 0] = factors.get(s, np.eye(2))
+                mpo.append(w)
+            self._mpo_cache[key] = self._upload_mpo(mpo)
+        first, last = min(gate.sites), max(gate.sites)
+        w0, w1 = max(first - 1, 0), min(last + 1, n - 1)
+        keep_all = self._trunc_args("discarded_weight", 0.0, None, 1)
+        for i in range(w0):                                             # apply_window: centre -> window start (QR)
+            self.shift_right(st, i, keep_all, fast=True)
+        saved = dict(W1=self.W1, W1T=self.W1T, W2=self.W2)
+        self._set_mpo(self._mpo_cache[key])
+        try:
+            self.sweep_2site(st, [1.0 / p.tdvp_sweeps] * p.tdvp_sweeps, w0, w1)
+        finally:
+            self._set_mpo(saved)
+        if p.max_bond_dim is not None:
+            # renorm_drift (sweep_utils.py:231-243): renormalise trajectories whose norm drifted beyond the tolerance.
+            # The centre is at w0, so the norm is that of the centre tensor and dividing it out IS the normalisation.
+            tol = max(1e-10, float(np.sqrt(p.svd_threshold)))
+            K.norm2(B, None, st.ext(w0), st.ext(w0 + 1), d, st.site(w0), self.norm_buf)
+            nrm = torch.sqrt(torch.clamp(self.norm_buf, min=0.0))
+            self.scale_buf.copy_(torch.where((nrm - 1.0).abs() > tol, 1.0 / nrm, torch.ones_like(nrm)))
+            K.scale(B, None, st.ext(w0), st.ext(w0 + 1), d, self.scale_buf, st.site(w0), lay.slot[w0])
+        return w0
+
+    def _local_noise_ctx(self, sites) -> dict:
+        """create_local_noise_model (digital_tjm.py:187-204): processes whose support lies inside the gate's qubits."""
+        key = tuple(sorted(sites))
+        if key not in self._noise_cache:
+            gs = set(sites)
+            self._noise_cache[key] = self._make_noise_ctx([pr for pr in self._global_noise if set(pr["sites"]).issubset(gs)])
+        return self._noise_cache[key]
+
+    def run_digital(self, layers, traj_uniforms: torch.Tensor | None, sample_layers: bool, gate_mode: str = "mpo", log: list | None = None):
+        """digital_tjm (digital_tjm.py:636-749), observable path, for the whole batch.  ``layers``: compiled circuit layers
+        (single-qubit gates, even / odd two-qubit groups, sample points); traj_uniforms: [B, 2 * n_two_qubit_gates].
+        Returns (results [B, n_obs, cols], diagnostics [B, 3, cols])."""
+        p = self.p
+        if not p.digital:
+            raise ValueError("run_digital needs EngineParams(digital=True)")
+        st = self.phi
+        glob = self._nctx
+        self._global_noise = glob["noise"] or []
+        noisy = glob["active"]
+        mid = sum(l.sample_points for l in layers) if sample_layers else 0
+        ncol = mid + 2 if sample_layers else 1
+        nobs = len(self.observables)
+        results = torch.zeros((self.B, nobs, ncol), dtype=torch.float64, device=self.dev)
+        diag = torch.zeros((self.B, 3, ncol), dtype=torch.float64, device=self.dev)
+        pos = torch.zeros(self.B, dtype=torch.int64, device=self.dev)
+
+        def record(col: int) -> None:
+            diag[:, :, col] = self.diagnostics(st)
+            if nobs:
+                results[:, :, col] = self.evaluate_observables(st)
+
+        if sample_layers:
+            record(0)
+        col = 0
+        try:
+            for layer in layers:
+                for gate in layer.single_qubit_gates:
+                    self.apply_single_qubit_gate(st, gate)
+                for group in (layer.even_two_qubit_gates, layer.odd_two_qubit_gates):
+                    for gate in group:
+                        if gate.interaction != 2:
+                            raise NotImplementedError("gates on three or more qubits use the gate-MPO route (SURVEY.md 8f 'next' row)")
+                        nn = abs(gate.sites[0] - gate.sites[1]) == 1
+                        has_gen = getattr(gate, "generator", None) is not None
+                        if gate_mode == "full-tdvp" and has_gen:
+                            centre = self.apply_two_qubit_gate_tdvp(st, gate)
+                        elif nn:
+                            centre = self.apply_two_qubit_gate_tebd(st, gate)
+                        elif gate_mode == "tdvp" and has_gen:
+                            centre = self.apply_two_qubit_gate_tdvp(st, gate)
+                        else:
+                            raise NotImplementedError(f"long-range gate in gate_mode={gate_mode!r}: the gate-MPO / SWAP-ladder routes are a "
+                                                      "SURVEY.md 8(f) 'next' row; use gate_mode='tdvp'")
+                        if not noisy:
+                            keep_all = self._trunc_args("discarded_weight", 0.0, None, 1)     # normalize("B", "QR")
+                            for i in reversed(range(1, centre + 1)):
+                                self.shift_left(st, i, keep_all, fast=True)
+                            self.normalize_site(st, 0)
+                        else:
+                            self._set_noise(self._local_noise_ctx(gate.sites))
+                            self.apply_dissipation(st, 1.0, start=centre)
+                            if self.noise is None:
+                                self.stochastic_process(st, 1.0, None, None, log, f"gate{tuple(gate.sites)}")
+                            else:
+                                u1 = traj_uniforms.gather(1, pos[:, None]).squeeze(1)
+                                u2 = traj_uniforms.gather(1, (pos + 1)[:, None]).squeeze(1)
+                                jm = self.stochastic_process(st, 1.0, u1, u2, log, f"gate{tuple(gate.sites)}")
+                                pos += 1 + jm.to(torch.int64)
+                if sample_layers:
+                    for _ in range(layer.sample_points):
+                        col += 1
+                        record(col)
+        finally:
+            self._set_noise(glob)
+        record(ncol - 1)
+        return results, diag

@@ -166,7 +166,18 @@ class Simulator:
         stats["kernel_launches"] = K.launch_count()
         self.last_log = log_all
 
-        # ---- combine: one all-reduce of per-column sums + counts; per-trajectory rows are gathered for Result.trajectories
+        times = np.asarray(sp.times, dtype=np.float64) if sp.sample_timesteps else np.asarray([sp.elapsed_time], dtype=np.float64)
+        self._finish(result, sp, res_local, diag_local, status_local, mine, ntraj, len(obs), ncol, to_sorted, times, stats, dev)
+        if final_tensors is not None:
+            result.output_state = State(tensors=final_tensors)
+
+    def _finish(self, result: Result, sp, res_local, diag_local, status_local, mine, ntraj: int, nobs: int, ncol: int, to_sorted, times, stats,
+                dev) -> None:
+        """Combine the shards -- ONE all-reduce of per-column sums + counts (NCCL over NVLink on GPU ranks, gloo on CPU);
+        per-trajectory rows are gathered for Result.trajectories -- and fill Result in the user's observable order
+        (simulator.py:932-942, result.py:112-138)."""
+        import torch.distributed as dist
+        world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         sums = torch.from_numpy(np.concatenate([res_local.sum(axis=0).reshape(-1), diag_local.sum(axis=0).reshape(-1), [float(len(mine))]]))
         if world > 1:
             backend = dist.get_backend()
@@ -175,7 +186,7 @@ class Simulator:
             sums = buf.cpu()
             gathered: list = [None] * world
             dist.all_gather_object(gathered, (list(mine), res_local, diag_local, status_local))
-            res_all = np.zeros((ntraj, len(obs), ncol))
+            res_all = np.zeros((ntraj, nobs, ncol))
             diag_all = np.zeros((ntraj, 3, ncol))
             status_all = np.zeros(ntraj, dtype=np.int32)
             for ids, r_, d_, s_ in gathered:
@@ -185,20 +196,16 @@ class Simulator:
             res_all, diag_all, status_all = res_local, diag_local, status_local
         sums = sums.numpy()
         count = sums[-1]
-        nres = len(obs) * ncol
-        mean_res = (sums[:nres] / count).reshape(len(obs), ncol)
+        nres = nobs * ncol
+        mean_res = (sums[:nres] / count).reshape(nobs, ncol)
         mean_diag = (sums[nres: nres + 3 * ncol] / count).reshape(3, ncol)
-
-        # ---- Result in the user's observable order (simulator.py:932-942, result.py:125-138)
         result.observables = list(sp.observables)
-        result.times = np.asarray(sp.times, dtype=np.float64) if sp.sample_timesteps else np.asarray([sp.elapsed_time], dtype=np.float64)
+        result.times = times
         result.trajectories = [res_all[:, to_sorted[i], :].copy() for i in range(len(sp.observables))]
         result.expectation_values = [mean_res[to_sorted[i]].copy() for i in range(len(sp.observables))]
         result.runtime_cost, result.max_bond, result.total_bond = mean_diag[0], mean_diag[1], mean_diag[2]
         result.status = status_all
         result.stats = stats
-        if final_tensors is not None:
-            result.output_state = State(tensors=final_tensors)
         if status_all.any():
             bad = np.nonzero(status_all)[0]
             raise RuntimeError(f"device status words non-zero for trajectories {bad[:8].tolist()} (bit 1: Jacobi SVD not converged, "
