@@ -38,7 +38,9 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=int(os.environ.get("YB_BENCH_BATCH", "32")), help="trajectories per GPU per step")
+    ap.add_argument("--batch", type=int, default=int(os.environ.get("YB_BENCH_BATCH", "256")), help="trajectories per GPU per step")
+    ap.add_argument("--lanes", type=int, default=int(os.environ.get("YB_BENCH_LANES", "2")),
+                    help="concurrent lock-step sub-batches per GPU (host thread + stream each)")
     ap.add_argument("--length", type=int, default=100)
     ap.add_argument("--chi", type=int, default=128)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -62,7 +64,7 @@ def workload_config(args, nranks):
     return {"workload": "C3", "model": None, "hamiltonian": "ising J=1 g=0.5", "length": args.length, "chi_max": args.chi,
             "noise": "lowering+pauli_z gamma=0.1 per site", "order": 2, "dt": 0.1, "svd_threshold": 1e-6, "krylov_tol": 1e-4,
             "observables": "Z on every site, every step", "initial_state": "seeded random MPS, bonds saturated at chi",
-            "batch_per_gpu": args.batch, "global_batch": args.batch * nranks, "sharding": f"trajectories x{nranks}",
+            "batch_per_gpu": args.batch, "global_batch": args.batch * nranks, "sharding": f"trajectories x{nranks}", "lanes_per_gpu": args.lanes,
             "l2_policy": "inputs larger than L2 (per-step working set >> 126 MB)"}
 
 
@@ -191,33 +193,45 @@ def run_b200_arm(args):
     noise = NoiseModel([{"name": n, "sites": [i], "strength": 0.1} for i in range(L) for n in ("lowering", "pauli_z")])
     obs = [(np.array([[1, 0], [0, -1]], dtype=np.complex128), [s]) for s in range(L)]
     ep = EngineParams(dt=0.1, n_steps=K + W + 2, order=2, max_bond_dim=chi, svd_threshold=1e-6, krylov_tol=1e-4)
-    eng = BatchedTJM(kern, L, B, ham.mpo.tensors, ep, noise.processes, obs, state.mps.tensors)
+    from yaqs_b200.lanes import Lanes
+    nl = max(1, min(args.lanes, B))
+    lanes = Lanes(dev, nl)
+    bounds = [(k * B) // nl for k in range(nl + 1)]
+    engs = [BatchedTJM(kern, L, bounds[k + 1] - bounds[k], ham.mpo.tensors, ep, noise.processes, obs, state.mps.tensors) for k in range(nl)]
     traj_ids = [rank * B + b for b in range(B)]
     tu, su = numpy_tables(42, traj_ids, ep.n_times, 2)
     tu_d, su_d = torch.from_numpy(tu).to(dev), torch.from_numpy(su).to(dev)
     sums = torch.zeros(L + 3 + 1, dtype=torch.float64, device=dev)
 
-    def one_step(j):
-        o, dg = eng.steady_state_step(tu_d[:, 2 * j: 2 * j + 2], su_d[:, j])
-        sums[:L] = o.sum(dim=0)
-        sums[L:L + 3] = dg.sum(dim=0)
+    def lane_step(job):
+        k, j = job
+        sl = slice(bounds[k], bounds[k + 1])
+        o, dg = engs[k].steady_state_step(tu_d[sl, 2 * j: 2 * j + 2], su_d[sl, j])
+        return torch.cat([o.sum(dim=0), dg.sum(dim=0)])
+
+    def one_step(j, concurrent=True):
+        parts = lanes.map(lane_step, [(k, j) for k in range(nl)]) if concurrent else [lane_step((k, j)) for k in range(nl)]
+        sums[:L + 3] = torch.stack(parts).sum(dim=0)
         sums[L + 3] = float(B)
         if world > 1:
             dist.all_reduce(sums)                       # the one collective of the path: per-step observable sums + counts
         return sums
 
     # initialize (F0): half-step dissipation + jump test, then warm-up steps
-    eng.apply_dissipation(eng.phi, ep.dt / 2)
-    eng.stochastic_process(eng.phi, ep.dt, tu_d[:, 0].contiguous(), tu_d[:, 1].contiguous())
+    def lane_init(k):
+        sl = slice(bounds[k], bounds[k + 1])
+        engs[k].apply_dissipation(engs[k].phi, ep.dt / 2)
+        engs[k].stochastic_process(engs[k].phi, ep.dt, tu_d[sl, 0].contiguous(), tu_d[sl, 1].contiguous())
+
+    lanes.map(lane_init, range(nl))
     for j in range(1, W + 1):
         one_step(j)
     torch.cuda.synchronize(dev)
     if world > 1:
         dist.barrier()
     kern.launch_count(reset=True)
-    stats0 = dict(eng.stats)
+    stats0 = {k: sum(e.stats[k] for e in engs) for k in engs[0].stats}
     with ClockSampler(local) as clocks:
-        kern.start_timing()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize(dev)
         e0.record()
@@ -228,16 +242,27 @@ def run_b200_arm(args):
         if world > 1:
             dist.barrier()
         ms_total = e0.elapsed_time(e1)
-        timing = kern.stop_timing()
     launches = kern.launch_count()
     obs_mean = (sums[:L] / sums[L + 3]).cpu().numpy()
-    stats = {k: eng.stats[k] - stats0.get(k, 0) for k in eng.stats}
-    bond_mean = float(eng.psi.bond[:, 1:L].to(torch.float64).mean().item())
+    stats = {k: sum(e.stats[k] for e in engs) - stats0.get(k, 0) for k in engs[0].stats}
+    bond_mean = float(torch.cat([e.psi.bond[:, 1:L].to(torch.float64).reshape(-1) for e in engs]).mean().item())
     t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total = float(t.item())
     value = B * world * K / (ms_total / 1000.0)
+
+    # instrumented pass for the roofline: ONE more step of the same kind, lanes run one after the other so that the CUDA
+    # events around every launch see that kernel alone on the GPU (under concurrent lanes they would overlap)
+    kern.start_timing()
+    i0, i1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    i0.record()
+    one_step(W + 1 + K, concurrent=False)
+    i1.record()
+    torch.cuda.synchronize(dev)
+    ms_instr = i0.elapsed_time(i1)
+    timing = kern.stop_timing()
+    eng = engs[0]
 
     # TDVP sweep alone (BASELINE.json: "TDVP sweep ms")
     torch.cuda.synchronize(dev)
@@ -248,6 +273,7 @@ def run_b200_arm(args):
     s1.record()
     torch.cuda.synchronize(dev)
     sweep_ms = s0.elapsed_time(s1)
+    sweep_batch = eng.B
 
     gemm = timing.get("gemm", {"launches": 0, "ms": 0.0})
     achieved = timing["gemm_flops"] / (gemm["ms"] / 1000.0) / 1e12 if gemm["ms"] > 0 else 0.0
@@ -261,18 +287,19 @@ def run_b200_arm(args):
                 "bound": "tensor", "achieved": achieved, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": achieved / FP64_PEAK_TFLOPS,
                 "traffic": traffic, "peak_source": "measured FP64 DMMA issue peak on this pool (profiles/r01_fp64_peak.json); MEASURED_PEAKS.json "
                 "carries only HBM and bf16", "launches": gemm["launches"], "avg_launch_ms": gemm["ms"] / max(gemm["launches"], 1),
-                "algorithmic_flops": timing["gemm_flops"], "share_of_step": gemm["ms"] / ms_total,
+                "algorithmic_flops": timing["gemm_flops"], "share_of_step": gemm["ms"] / ms_instr,
+                "timing": f"instrumented extra step, lanes serialised ({ms_instr:.0f} ms vs {ms_total / K:.0f} ms per step with {nl} concurrent lanes)",
                 "other_kernels_ms": {k: v["ms"] for k, v in timing.items() if isinstance(v, dict) and k != "gemm"}}
 
     # free the resident engine before the end-to-end pass
-    del eng
+    del eng, engs
     torch.cuda.empty_cache()
 
     e2e = None
     if not args.no_e2e:
         sp = AnalogSimParams(observables=[Observable(Z(), s) for s in range(L)], elapsed_time=0.1 * K, dt=0.1, num_traj=B * world, max_bond_dim=chi,
                              svd_threshold=1e-6, krylov_tol=1e-4, order=2, sample_timesteps=True, random_seed=42)
-        sim = Simulator(show_progress=False, device=dev, kernels=kern)
+        sim = Simulator(show_progress=False, device=dev, kernels=kern, lanes=nl)
         torch.cuda.synchronize(dev)
         if world > 1:
             dist.barrier()
@@ -302,7 +329,7 @@ def run_b200_arm(args):
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_total / K,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "complex128 (f64)", "data": "synthetic",
                 "config": workload_config(args, world), "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks.summary(),
-                "gpu_launches": launches, "tdvp_sweep_ms": {"per_batch": sweep_ms, "per_trajectory": sweep_ms / B},
+                "gpu_launches": launches, "tdvp_sweep_ms": {"per_batch": sweep_ms, "batch": sweep_batch, "per_trajectory": sweep_ms / sweep_batch},
                 "counters": {**stats, "mean_bond": bond_mean, "z_mean_first_sites": [float(x) for x in obs_mean[:4]]}}
         print(json.dumps(line))
     if world > 1:

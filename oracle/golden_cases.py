@@ -57,6 +57,11 @@ CASES = {
                                noise=[("lowering", 1.0), ("pauli_z", 0.6)]),
     "ising6_1site_noiseless": dict(model="ising", L=6, J=1.0, g=0.8, init="random:4:7", chi=4, thr=1e-9, order=1, dt=0.05,
                                    steps=6, sample_timesteps=True, ntraj=1, seed=5, obs="x+z", tdvp_mode="1site", noise=[]),
+    # mid-size bonds (2 chi = 80 > one Jacobi panel): the production Gram / Hermitian-eigen-solver SVD route is taken for the
+    # TDVP splits AND the 1e-12 gauge shifts; saturated random start, frequent jumps
+    "ising12_chi40_gram": dict(model="ising", L=12, J=1.0, g=0.7, init="random:40:5", chi=40, thr=1e-8, order=2, dt=0.1, steps=3,
+                               sample_timesteps=True, ntraj=3, seed=9, obs="z",
+                               noise=[("lowering", 0.5), ("pauli_z", 0.3)]),
     # final-column-only bookkeeping with order 1
     "ising6_final_only_order1": dict(model="ising", L=6, J=1.0, g=0.5, init="zeros", chi=8, thr=1e-6, order=1, dt=0.1, steps=5,
                                      sample_timesteps=False, ntraj=6, seed=21, obs="z",

@@ -189,8 +189,9 @@ int yb_heev(int nbatch, const int32_t* mask, yb_extent ek, void* g, int64_t stri
     cudaStream_t st = (cudaStream_t)stream;
     // k_ungtr (needs the reflectors) and k_steqr (needs d, e) are independent: the bandwidth-bound Q accumulation runs on a
     // side stream underneath the latency-bound QL chain.
-    static cudaStream_t side[16] = {nullptr};
-    static cudaEvent_t ev_fork[16] = {nullptr}, ev_join[16] = {nullptr};
+    // (thread_local: every host thread that drives a lane of trajectories on its own stream gets its own side stream)
+    static thread_local cudaStream_t side[16] = {nullptr};
+    static thread_local cudaEvent_t ev_fork[16] = {nullptr}, ev_join[16] = {nullptr};
     int dev = 0;
     cudaGetDevice(&dev);
     dev &= 15;

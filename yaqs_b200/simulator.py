@@ -56,7 +56,7 @@ class Simulator:
 
     def __init__(self, *, parallel: bool = True, max_workers: int | None = None, show_progress: bool = True, mp_context=None,
                  max_retries: int = 10, retry_exceptions=None, device: str | torch.device | None = None, kernels=None,
-                 batch_size: int | None = None, rng_mode: str = "numpy", collect_log: bool = False) -> None:
+                 batch_size: int | None = None, rng_mode: str = "numpy", collect_log: bool = False, lanes: int | None = None) -> None:
         self.parallel, self.max_workers, self.show_progress = parallel, max_workers, show_progress
         self.device = device
         self._kernels = kernels
@@ -66,6 +66,7 @@ class Simulator:
         self.rng_mode = rng_mode
         self.collect_log = collect_log
         self.last_log: list | None = None
+        self.lanes = lanes          # concurrent sub-batches per GPU (None: 2 on CUDA for waves of >= 64 trajectories, else 1)
 
     # ------------------------------------------------------------------------------------------------------------------
     def _get_kernels(self):
@@ -142,8 +143,14 @@ class Simulator:
         log_all = [] if self.collect_log else None
         wave = self._wave_size(len(mine), length, ep, mpo, init, dev)
         K.launch_count(reset=True)
-        for w0 in range(0, len(mine), max(wave, 1)):
-            idx = list(mine[w0: w0 + wave])
+        from .lanes import Lanes
+        nl = self.lanes if self.lanes is not None else (2 if (torch.device(dev).type == "cuda" and wave >= 64) else 1)
+        lanes = Lanes(dev, nl)
+        chunk = max(1, -(-max(wave, 1) // lanes.n))
+        jobs = [(w0, list(mine[w0: w0 + chunk])) for w0 in range(0, len(mine), chunk)]
+
+        def run_job(job):
+            w0, idx = job
             eng = BatchedTJM(K, length, len(idx), mpo, ep, procs, obs, init)
             if self.rng_mode == "numpy":
                 tu, su = numpy_tables(sp.random_seed, idx, ep.n_times, ep.order)
@@ -153,16 +160,21 @@ class Simulator:
                 tu, su = philox_tables(sp.random_seed, idx, ep.n_times, ep.order, dev)
             log = [] if self.collect_log else None
             r, dg = eng.run(tu, su, log)
-            res_local[w0: w0 + len(idx)] = r.cpu().numpy()
-            diag_local[w0: w0 + len(idx)] = dg.cpu().numpy()
-            status_local[w0: w0 + len(idx)] = eng.status.cpu().numpy()
-            for k, v in eng.stats.items():
+            fin = None
+            if sp.get_state and noiseless:
+                fin = (eng.psi if ep.order == 2 and ep.n_times > 1 else eng.phi).download(0)
+            return w0, idx, r.cpu().numpy(), dg.cpu().numpy(), eng.status.cpu().numpy(), dict(eng.stats), log, fin
+
+        for w0, idx, r, dg, stt, est, log, fin in lanes.map(run_job, jobs):
+            res_local[w0: w0 + len(idx)] = r
+            diag_local[w0: w0 + len(idx)] = dg
+            status_local[w0: w0 + len(idx)] = stt
+            for k, v in est.items():
                 stats[k] = stats.get(k, 0) + v
             if log_all is not None:
                 log_all.append((idx, log))
-            if sp.get_state and noiseless:
-                final_tensors = (eng.psi if ep.order == 2 and ep.n_times > 1 else eng.phi).download(0)
-            del eng
+            if fin is not None:
+                final_tensors = fin
         stats["kernel_launches"] = K.launch_count()
         self.last_log = log_all
 
