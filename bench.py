@@ -280,7 +280,7 @@ def run_b200_arm(args):
     traffic = None
     try:
         with open(os.path.join(ROOT, "profiles", "gemm_traffic.json")) as fh:
-            traffic = json.load(fh).get("dram_bytes_per_launch")
+            traffic = json.load(fh).get("dram_bytes_per_trajectory_launch") * (bounds[1] - bounds[0])     # ncu capture scaled to this lane batch
     except Exception:
         pass
     roofline = {"kernel": "k_gemm (batched complex128 DMMA contraction: project_site / environment updates / merges)",

@@ -351,3 +351,29 @@ def test_heev_diagonal_and_identity(backends):
     for t, k in enumerate(ks):
         E = qa[t, : k * k].reshape(k, k)
         assert np.max(np.abs(E @ E.conj().T - np.eye(k))) < 1e-13
+
+
+@pytest.mark.parametrize("ks", [[65, 97, 160], [256, 255, 129]])
+def test_heev_clustered_spectra(backends, ks):
+    """Divide & conquer deflation paths: exactly degenerate clusters, a projector, a glued block-diagonal matrix."""
+    cuda, _ = backends
+    rng = np.random.default_rng(7 + sum(ks))
+    mats = []
+    for i, k in enumerate(ks):
+        u, _ = np.linalg.qr(rng.standard_normal((k, k)) + 1j * rng.standard_normal((k, k)))
+        if i == 0:
+            lam = np.repeat([1.0, 0.5, 0.25, 1e-9, 0.0], k // 5 + 1)[:k]          # five exactly degenerate clusters
+        elif i == 1:
+            lam = (np.arange(k) < k // 3).astype(float)                            # projector
+        else:
+            lam = 1.0 + 1e-14 * rng.standard_normal(k)                             # one cluster at rounding distance
+        mats.append((u * lam[None, :]) @ u.conj().T)
+    d, qa, meta, status = _run_heev(cuda, "cuda", ks, mats)
+    assert not status.any()
+    for t, k in enumerate(ks):
+        assert meta[t, 5] == 1
+        E = qa[t, : k * k].reshape(k, k).conj().T
+        lam = d[t, :k]
+        assert np.max(np.abs(E.conj().T @ E - np.eye(k))) < 1e-12 * max(1, k / 16)
+        assert np.max(np.abs(mats[t] @ E - E * lam[None, :])) < 2e-13 * max(1, k / 16)
+        assert np.max(np.abs(np.sort(lam) - np.linalg.eigvalsh(mats[t]))) < 1e-13 * max(1, k / 16)

@@ -184,6 +184,10 @@ int yb_heev(int nbatch, const int32_t* mask, yb_extent ek, void* g, int64_t stri
         if (e1 != cudaSuccess) return fail("yb_heev(attr)", e1);
         e1 = cudaFuncSetAttribute(heev::k_ungtr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)heev::SMEM_BYTES);
         if (e1 != cudaSuccess) return fail("yb_heev(attr)", e1);
+        e1 = cudaFuncSetAttribute(heev::k_stedc<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(stedc::Smem<128>));
+        if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(heev::k_stedc<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(stedc::Smem<256>));
+        if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(heev::k_stedc<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(stedc::Smem<512>));
+        if (e1 != cudaSuccess) return fail("yb_heev(attr)", e1);
         configured = true;
     }
     cudaStream_t st = (cudaStream_t)stream;
@@ -209,14 +213,26 @@ int yb_heev(int nbatch, const int32_t* mask, yb_extent ek, void* g, int64_t stri
                                                                          ek.ptr, ek.stride, mask);
     if (int rc = done("yb_heev(ungtr)")) return rc;
     cudaEventRecord(ev_join[dev], side[dev]);
-    if (max_k <= 128)
-        heev::k_steqr<128><<<nbatch, 128 + 32, 0, st>>>(d, e, stride_vec, zr, stride_zr, (cplx*)zt, stride_z, ek.ptr, ek.stride, meta, status, mask);
-    else if (max_k <= 256)
-        heev::k_steqr<256><<<nbatch, 256 + 32, 0, st>>>(d, e, stride_vec, zr, stride_zr, (cplx*)zt, stride_z, ek.ptr, ek.stride, meta, status, mask);
-    else
-        heev::k_steqr<512><<<nbatch, 512 + 32, 0, st>>>(d, e, stride_vec, zr, stride_zr, (cplx*)zt, stride_z, ek.ptr, ek.stride, meta, status, mask);
+    static const bool use_ql = getenv("YB_HEEV_QL") != nullptr;      // diagnostic switch: the implicit-QL kernel instead of divide & conquer
+    if (use_ql) {
+        if (max_k <= 128)
+            heev::k_steqr<128><<<nbatch, 128 + 32, 0, st>>>(d, e, stride_vec, zr, stride_zr, (cplx*)zt, stride_z, ek.ptr, ek.stride, meta, status, mask);
+        else if (max_k <= 256)
+            heev::k_steqr<256><<<nbatch, 256 + 32, 0, st>>>(d, e, stride_vec, zr, stride_zr, (cplx*)zt, stride_z, ek.ptr, ek.stride, meta, status, mask);
+        else
+            heev::k_steqr<512><<<nbatch, 512 + 32, 0, st>>>(d, e, stride_vec, zr, stride_zr, (cplx*)zt, stride_z, ek.ptr, ek.stride, meta, status, mask);
+    } else if (max_k <= 128) {
+        heev::k_stedc<128><<<nbatch, stedc::THREADS, sizeof(stedc::Smem<128>), st>>>(d, e, stride_vec, zr, stride_zr, (cplx*)zt, stride_z, ek.ptr,
+                                                                                  ek.stride, meta, status, mask);
+    } else if (max_k <= 256) {
+        heev::k_stedc<256><<<nbatch, stedc::THREADS, sizeof(stedc::Smem<256>), st>>>(d, e, stride_vec, zr, stride_zr, (cplx*)zt, stride_z, ek.ptr,
+                                                                                  ek.stride, meta, status, mask);
+    } else {
+        heev::k_stedc<512><<<nbatch, stedc::THREADS, sizeof(stedc::Smem<512>), st>>>(d, e, stride_vec, zr, stride_zr, (cplx*)zt, stride_z, ek.ptr,
+                                                                                  ek.stride, meta, status, mask);
+    }
     cudaStreamWaitEvent(st, ev_join[dev], 0);
-    return done("yb_heev(steqr)");
+    return done("yb_heev(stedc)");
 }
 
 int yb_unpack_vh(int nbatch, const int32_t* mask, yb_extent ek, yb_extent er, int dphys, const void* src, int64_t stride_src, void* dst,

@@ -10,6 +10,7 @@
 // fused into ONE read + ONE write of the trailing block per step (k^3/3 elements in total).
 #include "yb_common.cuh"
 #include <math.h>
+#include "yb_stedc.cuh"
 
 namespace heev {
 
@@ -372,6 +373,36 @@ __global__ void __launch_bounds__(NT + 32) k_steqr(double* dio, const double* ei
     for (int i = tid; i < k; i += nthr) dio[(long long)b * s_vec + i] = d[i];
     cplx* zt = Zt + (long long)b * sZ;
     for (long long x = tid; x < (long long)k * k; x += nthr) zt[x] = make_double2(zr[x], 0.0);
+    if (tid == 0) {
+        if (meta) meta[b * 8 + 5] = fail ? 0 : 1;
+        if (fail && status) atomicOr(&status[b], 1);
+    }
+}
+
+// Divide & conquer replacement of k_steqr (yb_stedc.cuh): same contract -- d = eigenvalues (unsorted), Zt = eigenvectors as
+// complex rows (row c = eigenvector c), meta[5] = 1 if converged.  ZR and the storage of Zt itself (2 k^2 doubles) are the two
+// real work matrices of the merge tree.
+template <int KM>
+__global__ void __launch_bounds__(stedc::THREADS, 2) k_stedc(double* dio, const double* ein, long long s_vec, double* ZR, long long sZR, cplx* Zt,
+                                                              long long sZ, const int* ek, int esk, int* meta, int* status, const int* mask) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int b = blockIdx.x;
+    if (mask && !mask[b]) return;
+    const int k = ek[(long long)b * esk];
+    if (k <= 0) return;
+    stedc::Smem<KM>& S = *reinterpret_cast<stedc::Smem<KM>*>(smem_raw);
+    double* QA = ZR + (long long)b * sZR;
+    cplx* zt = Zt + (long long)b * sZ;
+    double* QB = reinterpret_cast<double*>(zt);
+    int fail = 0;
+    double* q = stedc::solve<KM>(S, dio + (long long)b * s_vec, ein + (long long)b * s_vec, k, QA, QB, blockDim.x, &fail);
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const long long kk = (long long)k * k;
+    if (q != QA) {
+        for (long long x = tid; x < kk; x += nthr) QA[x] = QB[x];
+        __syncthreads();
+    }
+    for (long long x = tid; x < kk; x += nthr) zt[x] = make_double2(QA[x], 0.0);
     if (tid == 0) {
         if (meta) meta[b * 8 + 5] = fail ? 0 : 1;
         if (fail && status) atomicOr(&status[b], 1);
