@@ -37,6 +37,10 @@ int64_t yb_launch_count(int reset);
 /* Optional instrumentation: a device uint64 that every contraction CTA increments by the real flops of its tile (8 per
  * complex multiply-add); NULL (default) disables it.  bench.py uses it for roofline.achieved. */
 void yb_set_flop_counter(void* device_u64);
+/* Diagnostic switches for A/B runs (defaults = production route; environment YB_HEEV_QL / YB_HEEV_NORING set the initial value):
+ *   "heev_ql"   1 = implicit-QL tridiagonal eigen-solver instead of divide & conquer          (default 0)
+ *   "heev_ring" 0 = direct register loads instead of the cp.async row ring in k_hetrd/k_ungtr  (default 1) */
+int yb_set_option(const char* name, int value);
 
 /* ---- contractions -------------------------------------------------------------------------------------------------
  * One grouped / K-segmented batched complex GEMM; `op` selects the index pattern (enum YbGemmOp in csrc/yb_common.cuh):
@@ -145,6 +149,17 @@ int yb_scale(int nbatch, const int32_t* mask, yb_extent el, yb_extent er, int dp
  * (mps.py:961-1047) and jump weights (stochastic_process.py:139-176). */
 int yb_local_rdm(int nbatch, const int32_t* mask, yb_extent el, yb_extent er, int dphys, const void* a, int64_t stride_a, const void* x,
                  int64_t stride_x, void* g, void* stream);
+
+
+/* ---- device RNG (rng_mode = "philox") ------------------------------------------------------------------------------
+ * Counter-based replacement of the reference's per-trajectory numpy streams (core/random_utils.py:20-87): stream
+ * (seed, traj, tag) with tag 0x5452414A ("TRAJ": initialize / step_through) or 0x53414D50 ("SAMP": block index = time step
+ * of the measurement copy).  Philox4x32-10, key = seed, counter = (block0 + c, tag, traj_lo, traj_hi); block c yields
+ * out[b][2c], out[b][2c+1] = the two uniforms one jump test can consume (methods/stochastic_process.py:190-292).
+ * traj_index: device int64[nbatch] GLOBAL trajectory indices (tables do not depend on batching or on the GPU count).
+ * Rows of `out` are stride_out doubles apart (even, >= 2 * nblocks, 16-byte aligned). */
+int yb_philox_uniform(int nbatch, uint64_t seed, const int64_t* traj_index, uint32_t tag, int nblocks, uint32_t block0, double* out,
+                      int64_t stride_out, void* stream);
 
 #ifdef __cplusplus
 }

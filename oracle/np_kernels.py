@@ -38,6 +38,34 @@ def _on(mask, b):
     return mask is None or int(_np(mask)[b]) != 0
 
 
+def philox4x32_10(ctr: np.ndarray, key: np.ndarray) -> np.ndarray:
+    """Vectorised Philox4x32-10 (Salmon et al., SC'11): ctr [..., 4] uint32, key [..., 2] uint32 -> [..., 4] uint32."""
+    c = [ctr[..., i].astype(np.uint64) for i in range(4)]
+    k0, k1 = key[..., 0].astype(np.uint64), key[..., 1].astype(np.uint64)
+    m32 = np.uint64(0xFFFFFFFF)
+    for _ in range(10):
+        p0, p1 = np.uint64(0xD2511F53) * c[0], np.uint64(0xCD9E8D57) * c[2]
+        c = [(p1 >> np.uint64(32)) ^ c[1] ^ k0, p1 & m32, (p0 >> np.uint64(32)) ^ c[3] ^ k1, p0 & m32]
+        k0, k1 = (k0 + np.uint64(0x9E3779B9)) & m32, (k1 + np.uint64(0xBB67AE85)) & m32
+    return np.stack(c, axis=-1).astype(np.uint32)
+
+
+def philox_pairs(seed: int, traj: int, tag: int, blocks: np.ndarray) -> np.ndarray:
+    """[len(blocks), 2] float64: the two uniforms of every block of stream (seed, traj, tag)."""
+    n = len(blocks)
+    ctr = np.empty((n, 4), dtype=np.uint32)
+    ctr[:, 0] = np.asarray(blocks, dtype=np.uint64) & np.uint64(0xFFFFFFFF)
+    ctr[:, 1] = tag & 0xFFFFFFFF
+    t = traj & (2 ** 64 - 1)
+    ctr[:, 2], ctr[:, 3] = t & 0xFFFFFFFF, t >> 32
+    s = seed & (2 ** 64 - 1)
+    key = np.broadcast_to(np.array([s & 0xFFFFFFFF, s >> 32], dtype=np.uint32), (n, 2))
+    r = philox4x32_10(ctr, key).astype(np.uint64)
+    hi = np.stack([r[:, 0], r[:, 2]], axis=1) >> np.uint64(5)
+    lo = np.stack([r[:, 1], r[:, 3]], axis=1) >> np.uint64(6)
+    return ((hi << np.uint64(26)) | lo).astype(np.float64) / 9007199254740992.0
+
+
 class NumpyKernels:
     name = "numpy-twin"
 
@@ -365,6 +393,12 @@ class NumpyKernels:
                 continue
             v = _view(a, t, dphys * _ext(el, t) * _ext(er, t))
             v *= float(_np(scale)[t])
+
+    def philox_uniform(self, seed, traj_index, tag, nblocks, block0, out):
+        """numpy restatement of csrc/yb_philox.cuh (Philox4x32-10, key = seed, counter = (block, tag, traj_lo, traj_hi))."""
+        o = out.numpy()
+        for b, t in enumerate(_np(traj_index).tolist()):
+            o[b, : 2 * nblocks] = philox_pairs(int(seed), int(t), int(tag), np.arange(block0, block0 + nblocks, dtype=np.uint64)).reshape(-1)
 
     def local_rdm(self, nbatch, mask, el, er, dphys, a, x, g):
         self._launches += 1

@@ -341,6 +341,28 @@ def test_heev_eigendecomposition(backends, ks):
         assert np.max(np.abs(np.sort(lam) - np.linalg.eigvalsh(mats[t]))) < 1e-13 * scale * max(1, k / 16)
 
 
+@pytest.mark.parametrize("ks", [[256, 200, 131], [512, 97, 64, 33, 7]])
+def test_heev_row_ring_is_bit_identical(backends, ks):
+    """The cp.async row ring of k_hetrd / k_ungtr only changes HOW the trailing block is streamed: same operations in the same
+    order, so eigenvalues and eigenvectors must be bit-identical to the direct-load variant."""
+    cuda, _ = backends
+    rng = np.random.default_rng(11 + sum(ks))
+    mats = []
+    for k in ks:
+        a = rng.standard_normal((k, k)) + 1j * rng.standard_normal((k, k))
+        a *= np.logspace(0, -7, k)[None, :]
+        mats.append(a @ a.conj().T)
+    try:
+        cuda.set_option("heev_ring", 0)
+        d0, qa0, meta0, status0 = _run_heev(cuda, "cuda", ks, mats)
+        cuda.set_option("heev_ring", 1)
+        d1, qa1, meta1, status1 = _run_heev(cuda, "cuda", ks, mats)
+    finally:
+        cuda.set_option("heev_ring", 1)
+    assert not status0.any() and not status1.any()
+    assert np.array_equal(d0, d1) and np.array_equal(qa0, qa1) and np.array_equal(meta0, meta1)
+
+
 def test_heev_diagonal_and_identity(backends):
     cuda, _ = backends
     ks = [4, 6, 40]

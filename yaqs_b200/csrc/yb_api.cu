@@ -49,6 +49,17 @@ int64_t yb_launch_count(int reset) {
 
 void yb_set_flop_counter(void* device_u64) { g_flop_counter = (unsigned long long*)device_u64; }
 
+// diagnostic switches (A/B runs and bisecting a failure); the defaults are the production route
+static std::atomic<int> g_opt_heev_ql{getenv("YB_HEEV_QL") != nullptr ? 1 : 0};
+static std::atomic<int> g_opt_heev_ring{getenv("YB_HEEV_NORING") != nullptr ? 0 : 1};
+
+int yb_set_option(const char* name, int value) {
+    if (!name) return fail_msg("yb_set_option: null name");
+    if (!strcmp(name, "heev_ql")) { g_opt_heev_ql = value != 0; return 0; }
+    if (!strcmp(name, "heev_ring")) { g_opt_heev_ring = value != 0; return 0; }
+    return fail_msg("yb_set_option: unknown option");
+}
+
 int yb_gemm(int op, int nbatch, int ngroups, const int32_t* mask, yb_extent e0, yb_extent e1, yb_extent e2, int dphys, int d_left, int d_right,
             const void* a, int64_t stride_a, const void* b, int64_t stride_b, void* c, int64_t stride_c, int conj_b, int max_m, int max_n,
             void* stream) {
@@ -180,9 +191,10 @@ int yb_heev(int nbatch, const int32_t* mask, yb_extent ek, void* g, int64_t stri
     if (max_k > heev::KMAX) return fail_msg("yb_heev: max_k > 512 unsupported");
     static bool configured = false;
     if (!configured) {
-        cudaError_t e1 = cudaFuncSetAttribute(heev::k_hetrd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)heev::SMEM_BYTES);
-        if (e1 != cudaSuccess) return fail("yb_heev(attr)", e1);
-        e1 = cudaFuncSetAttribute(heev::k_ungtr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)heev::SMEM_BYTES);
+        cudaError_t e1 = cudaFuncSetAttribute(heev::k_hetrd<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)heev::SMEM_BYTES);
+        if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(heev::k_ungtr<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)heev::SMEM_BYTES);
+        if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(heev::k_hetrd<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(heev::SMEM_BYTES + heev::RING_BYTES));
+        if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(heev::k_ungtr<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(heev::SMEM_BYTES + heev::RING_BYTES));
         if (e1 != cudaSuccess) return fail("yb_heev(attr)", e1);
         e1 = cudaFuncSetAttribute(heev::k_stedc<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(stedc::Smem<128>));
         if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(heev::k_stedc<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(stedc::Smem<256>));
@@ -205,15 +217,24 @@ int yb_heev(int nbatch, const int32_t* mask, yb_extent ek, void* g, int64_t stri
         if (e2 == cudaSuccess) e2 = cudaEventCreateWithFlags(&ev_join[dev], cudaEventDisableTiming);
         if (e2 != cudaSuccess) return fail("yb_heev(side stream)", e2);
     }
-    heev::k_hetrd<<<nbatch, heev::THREADS, heev::SMEM_BYTES, st>>>((cplx*)g, stride_g, ek.ptr, ek.stride, d, e, (cplx*)tau, stride_vec, mask);
+    const bool use_ring = g_opt_heev_ring.load() != 0;     // off: direct register loads instead of the cp.async row ring
+    if (use_ring)
+        heev::k_hetrd<true><<<nbatch, heev::THREADS, heev::SMEM_BYTES + heev::RING_BYTES, st>>>((cplx*)g, stride_g, ek.ptr, ek.stride, d, e, (cplx*)tau,
+                                                                                              stride_vec, mask);
+    else
+        heev::k_hetrd<false><<<nbatch, heev::THREADS, heev::SMEM_BYTES, st>>>((cplx*)g, stride_g, ek.ptr, ek.stride, d, e, (cplx*)tau, stride_vec, mask);
     if (int rc = done("yb_heev(hetrd)")) return rc;
     cudaEventRecord(ev_fork[dev], st);
     cudaStreamWaitEvent(side[dev], ev_fork[dev], 0);
-    heev::k_ungtr<<<nbatch, heev::THREADS, heev::SMEM_BYTES, side[dev]>>>((const cplx*)g, stride_g, (const cplx*)tau, stride_vec, (cplx*)qh, stride_q,
-                                                                         ek.ptr, ek.stride, mask);
+    if (use_ring)
+        heev::k_ungtr<true><<<nbatch, heev::THREADS, heev::SMEM_BYTES + heev::RING_BYTES, side[dev]>>>((const cplx*)g, stride_g, (const cplx*)tau, stride_vec,
+                                                                                                      (cplx*)qh, stride_q, ek.ptr, ek.stride, mask);
+    else
+        heev::k_ungtr<false><<<nbatch, heev::THREADS, heev::SMEM_BYTES, side[dev]>>>((const cplx*)g, stride_g, (const cplx*)tau, stride_vec, (cplx*)qh, stride_q,
+                                                                                    ek.ptr, ek.stride, mask);
     if (int rc = done("yb_heev(ungtr)")) return rc;
     cudaEventRecord(ev_join[dev], side[dev]);
-    static const bool use_ql = getenv("YB_HEEV_QL") != nullptr;      // diagnostic switch: the implicit-QL kernel instead of divide & conquer
+    const bool use_ql = g_opt_heev_ql.load() != 0;      // on: the implicit-QL kernel instead of divide & conquer
     if (use_ql) {
         if (max_k <= 128)
             heev::k_steqr<128><<<nbatch, 128 + 32, 0, st>>>(d, e, stride_vec, zr, stride_zr, (cplx*)zt, stride_z, ek.ptr, ek.stride, meta, status, mask);
@@ -284,6 +305,15 @@ int yb_local_rdm(int nbatch, const int32_t* mask, yb_extent el, yb_extent er, in
     k_local_rdm<<<nbatch, 512, 0, (cudaStream_t)stream>>>(dphys, (const cplx*)a, stride_a, (const cplx*)x, stride_x, (cplx*)g, el.ptr, el.stride, er.ptr,
                                                            er.stride, mask);
     return done("yb_local_rdm");
+}
+
+int yb_philox_uniform(int nbatch, uint64_t seed, const int64_t* traj_index, uint32_t tag, int nblocks, uint32_t block0, double* out,
+                      int64_t stride_out, void* stream) {
+    if (nbatch <= 0 || nblocks <= 0) return 0;
+    if (stride_out < 2LL * nblocks || (stride_out & 1) || ((uintptr_t)out & 15)) return fail_msg("yb_philox_uniform: rows must be 16-byte aligned and hold 2 * nblocks doubles");
+    dim3 grid(grid_for(nblocks, 128, 64), nbatch);
+    k_philox_uniform<<<grid, 128, 0, (cudaStream_t)stream>>>((unsigned long long)seed, (const long long*)traj_index, tag, nblocks, block0, out, stride_out);
+    return done("yb_philox_uniform");
 }
 
 }  // extern "C"

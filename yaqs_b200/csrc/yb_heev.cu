@@ -19,6 +19,19 @@ constexpr int NWARPS = THREADS / 32;
 constexpr int KMAX = 512;               // largest matrix (2 * chi_max for chi_max = 256)
 constexpr int RSMAX = 4;                // row groups per column block
 constexpr size_t SMEM_BYTES = (size_t)(3 + RSMAX) * KMAX * sizeof(cplx);
+// Row ring of the streaming passes: every thread keeps RING rows of its column in flight with cp.async (LDGSTS.128 into a
+// warp-private slice of shared memory), so a Householder step is no longer (rows / 4) dependent global-load round trips --
+// ncu (profiles/r01_ncu_heev_full_stedc.json) showed 56-62 % of the stall samples of k_hetrd / k_ungtr on those loads with
+// DRAM at 52 % of its rate.  A thread only ever reads back its own copies, so cp.async.wait_group is the only synchronisation.
+constexpr int RING = 6;
+constexpr size_t RING_BYTES = (size_t)NWARPS * RING * 32 * sizeof(cplx);
+
+__device__ __forceinline__ void ring_load(cplx* smem_dst, const cplx* gmem_src) {
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" :: "r"(dst), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void ring_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N> __device__ __forceinline__ void ring_wait() { asm volatile("cp.async.wait_group %0;\n" :: "n"(N) : "memory"); }
 
 struct Split { int ncb, rsf, cb, rs; bool on; };
 
@@ -56,6 +69,7 @@ __device__ __forceinline__ void householder_from_row(const cplx* row, int ns, cp
 
 // Reduction to real tridiagonal form, lower variant of zhetd2 on full Hermitian storage.  On exit row j of G holds the
 // Householder vector v_j in columns j+1.. (v_j[0] = 1), d/e the tridiagonal, tau the reflector scalars.
+template <bool USE_RING>
 __global__ void __launch_bounds__(THREADS, 1) k_hetrd(cplx* G, long long sG, const int* ek, int esk, double* dout, double* eout, cplx* tauout,
                                                        long long s_vec, const int* mask) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -68,6 +82,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_hetrd(cplx* G, long long sG, con
     cplx* w = v + KMAX;
     cplx* vn = w + KMAX;
     cplx* part = vn + KMAX;                 // [RSMAX][KMAX]
+    cplx* ring = part + RSMAX * KMAX;       // [NWARPS][RING][32]   (USE_RING only)
     cplx* Gb = G + (long long)b * sG;
     double* d = dout + (long long)b * s_vec;
     double* e = eout + (long long)b * s_vec;
@@ -140,7 +155,35 @@ __global__ void __launch_bounds__(THREADS, 1) k_hetrd(cplx* G, long long sG, con
             if (sp.on) {
                 const int c = c0 + sp.cb * 32 + lane;
                 cplx acc = make_double2(0.0, 0.0);
-                if (c < n) {
+                if (c < n && USE_RING) {
+                    const cplx wc = w[c - (j + 1)], vc = v[c - (j + 1)];
+                    cplx* rg = ring + ((tid >> 5) * RING) * 32 + lane;          // slot s of this thread: rg[s * 32]
+                    const int i0 = c0 + sp.rs;
+                    const int nr = (n - i0 + sp.rsf - 1) / sp.rsf;                // rows of this thread
+                    cplx* src = Gb + (long long)i0 * n + c;
+                    const long long step = (long long)sp.rsf * n;
+#pragma unroll
+                    for (int q = 0; q < RING; ++q) {
+                        if (q < nr) ring_load(rg + q * 32, src + q * step);
+                        ring_commit();
+                    }
+                    int slot = 0;
+                    for (int r = 0; r < nr; ++r) {
+                        ring_wait<RING - 1>();
+                        cplx g = rg[slot * 32];
+                        const int ii = i0 + r * sp.rsf;
+                        const cplx vi = v[ii - (j + 1)], wi = w[ii - (j + 1)];
+                        g.x -= vi.x * wc.x + vi.y * wc.y + wi.x * vc.x + wi.y * vc.y;
+                        g.y -= vi.y * wc.x - vi.x * wc.y + wi.y * vc.x - wi.x * vc.y;
+                        src[r * step] = g;
+                        acc = cfma(cconj(g), vn[ii - c0], acc);
+                        if (r + RING < nr) ring_load(rg + slot * 32, src + (r + RING) * step);      // after g has been consumed
+                        ring_commit();
+                        slot = (slot + 1 == RING) ? 0 : slot + 1;
+                    }
+                    ring_wait<0>();
+                    part[sp.rs * KMAX + (c - c0)] = acc;
+                } else if (c < n) {
                     const cplx wc = w[c - (j + 1)], vc = v[c - (j + 1)];
                     int i = c0 + sp.rs;
                     for (; i + 3 * sp.rsf < n; i += 4 * sp.rsf) {
@@ -183,6 +226,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_hetrd(cplx* G, long long sG, con
 }
 
 // Q = H_0 H_1 ... H_{n-2} by backward accumulation (zungtr, lower): one fused pass per reflector over the block it touches.
+template <bool USE_RING>
 __global__ void __launch_bounds__(THREADS, 2) k_ungtr(const cplx* __restrict__ G, long long sG, const cplx* __restrict__ tauin, long long s_vec,
                                                        cplx* Q, long long sQ, const int* ek, int esk, const int* mask) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -194,6 +238,7 @@ __global__ void __launch_bounds__(THREADS, 2) k_ungtr(const cplx* __restrict__ G
     cplx* vp = v + KMAX;                            // v_{j-1} (local index i - j)
     cplx* tv = vp + KMAX;                           // t_j[c - (j+1)] = (v_j^H Q[S,S])[c]
     cplx* part = tv + KMAX;
+    cplx* ring = part + RSMAX * KMAX;               // [NWARPS][RING][32]   (USE_RING only)
     const cplx* Gb = G + (long long)b * sG;
     const cplx* tauv = tauin + (long long)b * s_vec;
     cplx* Qb = Q + (long long)b * sQ;
@@ -216,7 +261,36 @@ __global__ void __launch_bounds__(THREADS, 2) k_ungtr(const cplx* __restrict__ G
         const Split sp = make_split(ns);
         if (sp.on) {
             const int c = r0 + sp.cb * 32 + lane;
-            if (c < n) {
+            if (c < n && USE_RING) {
+                const cplx tc = cmul(tau, tv[c - r0]);
+                cplx acc = make_double2(0.0, 0.0);
+                cplx* rg = ring + ((tid >> 5) * RING) * 32 + lane;
+                const int i0 = r0 + sp.rs;
+                const int nr = (n - i0 + sp.rsf - 1) / sp.rsf;
+                cplx* src = Qb + (long long)i0 * n + c;
+                const long long step = (long long)sp.rsf * n;
+#pragma unroll
+                for (int q = 0; q < RING; ++q) {
+                    if (q < nr) ring_load(rg + q * 32, src + q * step);
+                    ring_commit();
+                }
+                int slot = 0;
+                for (int r = 0; r < nr; ++r) {
+                    ring_wait<RING - 1>();
+                    cplx q = rg[slot * 32];
+                    const int ii = i0 + r * sp.rsf;
+                    const cplx vi = v[ii - r0];
+                    q.x -= vi.x * tc.x - vi.y * tc.y;
+                    q.y -= vi.x * tc.y + vi.y * tc.x;
+                    src[r * step] = q;
+                    if (j >= 1) acc = cfma(cconj(vp[ii - j]), q, acc);
+                    if (r + RING < nr) ring_load(rg + slot * 32, src + (r + RING) * step);
+                    ring_commit();
+                    slot = (slot + 1 == RING) ? 0 : slot + 1;
+                }
+                ring_wait<0>();
+                part[sp.rs * KMAX + (c - r0)] = acc;
+            } else if (c < n) {
                 const cplx tc = cmul(tau, tv[c - r0]);
                 cplx acc = make_double2(0.0, 0.0);
                 int i = r0 + sp.rs;

@@ -2,6 +2,7 @@
 // tridiagonal eigen-solve, site-tensor utilities, local reduced density matrices.  All are HBM-bound streaming
 // kernels: coalesced 16-byte accesses along the fastest (right-bond) index, one launch covers the whole batch.
 #include "yb_common.cuh"
+#include "yb_philox.cuh"
 #include <math.h>
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -330,5 +331,19 @@ __global__ void __launch_bounds__(512) k_local_rdm(int dphys, const cplx* __rest
     if (threadIdx.x < dphys * dphys) {
         const int o = threadIdx.x / dphys, p = threadIdx.x % dphys;
         g[(long long)b * dphys * dphys + threadIdx.x] = make_double2(acc[(o * 4 + p) * 2], acc[(o * 4 + p) * 2 + 1]);
+    }
+}
+
+// out[b][2c], out[b][2c + 1] = the two uniforms of Philox block (block0 + c) of stream (seed, traj[b], tag); one thread per
+// block.  HBM-bound (16 B written per 10-round block), launched once per run.
+__global__ void k_philox_uniform(unsigned long long seed, const long long* __restrict__ traj, unsigned tag, int nblocks, unsigned block0, double* out,
+                                 long long s_out) {
+    const int b = blockIdx.y;
+    const long long t = traj[b];
+    double* ob = out + (long long)b * s_out;
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < nblocks; c += gridDim.x * blockDim.x) {
+        double u0, u1;
+        philox::pair(seed, t, tag, block0 + (unsigned)c, u0, u1);
+        reinterpret_cast<double2*>(ob)[c] = make_double2(u0, u1);
     }
 }

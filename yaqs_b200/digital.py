@@ -71,7 +71,7 @@ def run_digital(simulator, initial_state, operator, sp, noise, result):
             tu, _ = numpy_tables(sp.random_seed, idx, max(n2q, 1), 1)
             tu = torch.from_numpy(tu).to(dev)
         else:
-            tu, _ = philox_tables(sp.random_seed, idx, max(n2q, 1), 1, dev)
+            tu, _ = philox_tables(K, sp.random_seed, idx, max(n2q, 1), 1, dev)
         log = [] if simulator.collect_log else None
         r, dg = eng.run_digital(compiled.layers, tu, sp.sample_layers, sp.gate_mode, log)
         res_local[w0: w0 + len(idx)] = r.cpu().numpy()

@@ -68,9 +68,9 @@ def load_library() -> ctypes.CDLL:
 
 
 EXPORTED_SYMBOLS = [
-    "yb_last_error", "yb_version", "yb_launch_count", "yb_set_flop_counter", "yb_gemm", "yb_wapply", "yb_env_identity", "yb_lanczos_init",
+    "yb_last_error", "yb_version", "yb_launch_count", "yb_set_flop_counter", "yb_set_option", "yb_gemm", "yb_wapply", "yb_env_identity", "yb_lanczos_init",
     "yb_lanczos_step", "yb_lanczos_combine", "yb_svd_prepare", "yb_svd_round", "yb_svd_check", "yb_svd_finalize", "yb_heev", "yb_svd_select", "yb_svd_gather",
-    "yb_unpack_vh", "yb_copy_packed", "yb_apply_local_op", "yb_norm2", "yb_scale", "yb_local_rdm",
+    "yb_unpack_vh", "yb_copy_packed", "yb_apply_local_op", "yb_norm2", "yb_scale", "yb_local_rdm", "yb_philox_uniform",
 ]
 
 
@@ -103,6 +103,10 @@ class CudaKernels:
         out["gemm_flops"] = int(self._flops.item()) if self._flops is not None else 0
         self._timed, self._flops = None, None
         return out
+
+    def set_option(self, name: str, value: int) -> None:
+        """Diagnostic switch of the library (include/yaqs_b200.h: yb_set_option)."""
+        self._check(self.lib.yb_set_option(name.encode(), int(value)))
 
     def _timed_call(self, family: str, fn) -> None:
         if self._timed is None:
@@ -246,6 +250,12 @@ class CudaKernels:
     def scale(self, nbatch, mask, el, er, dphys, scale, a: Buf, max_elems):
         self._check(self.lib.yb_scale(nbatch, self._ptr(mask), self._ext(el), self._ext(er), dphys, self._ptr(scale), self._cptr(a),
                                       ctypes.c_int64(a.stride), int(max_elems), self._stream()))
+
+    def philox_uniform(self, seed: int, traj_index, tag: int, nblocks: int, block0: int, out):
+        """out [nbatch, 2 * nblocks] float64 (contiguous rows); traj_index int64 [nbatch] on the device."""
+        nb = int(traj_index.numel())
+        self._check(self.lib.yb_philox_uniform(nb, ctypes.c_uint64(int(seed) & (2 ** 64 - 1)), self._ptr(traj_index), ctypes.c_uint32(tag), int(nblocks),
+                                               ctypes.c_uint32(block0), self._ptr(out), ctypes.c_int64(out.stride(0)), self._stream()))
 
     def local_rdm(self, nbatch, mask, el, er, dphys, a: Buf, x: Buf, g):
         self._check(self.lib.yb_local_rdm(nbatch, self._ptr(mask), self._ext(el), self._ext(er), dphys, self._cptr(a), ctypes.c_int64(a.stride),

@@ -6,8 +6,9 @@
 (``rng.random()``) and, if it jumps, one more (``rng.choice`` draws exactly one uniform and selects with
 ``searchsorted(cdf, u, side="right")``), so a table of consecutive doubles per stream is an exact replay.
 
-``philox`` mode draws the same tables on the device with torch's Philox4x32-10 CUDA generator keyed by the run seed;
-row b belongs to global trajectory index ``traj_indices[b]`` so results do not depend on how trajectories are sharded.
+``philox`` mode fills the same tables on the device with the hand-written Philox4x32-10 kernel (``yb_philox_uniform``): key =
+run seed, counter = (jump-test index, stream tag, global trajectory index), so row b depends only on ``traj_indices[b]`` and
+results do not depend on how trajectories are batched or sharded.
 """
 from __future__ import annotations
 
@@ -47,16 +48,18 @@ def numpy_tables(seed: int | None, traj_indices, n_times: int, order: int, sampl
     return traj, samp
 
 
-def philox_tables(seed: int | None, traj_indices, n_times: int, order: int, device):
-    """Device-side Philox tables; one generator per trajectory index keeps rows independent of the sharding."""
+def philox_tables(kernels, seed: int | None, traj_indices, n_times: int, order: int, device, sample_offset: int = 0):
+    """Device-side tables from the Philox4x32-10 kernel (csrc/yb_philox.cuh, ``yb_philox_uniform``): stream = (seed, global
+    trajectory index, tag); the trajectory stream uses block c for jump test c, the sample stream uses block j + offset for
+    the measurement copy of time step j -- the counter-based mirror of core/random_utils.py:20-87."""
     nb = len(traj_indices)
+    base = int(seed) if seed is not None else int(np.random.SeedSequence().entropy % (2 ** 64))
+    idx = torch.as_tensor(np.asarray(traj_indices, dtype=np.int64), device=device)
     traj = torch.empty((nb, 2 * n_times), dtype=torch.float64, device=device)
-    samp = torch.empty((nb, n_times, 2), dtype=torch.float64, device=device) if order == 2 else None
-    gen = torch.Generator(device=device)
-    base = int(seed) if seed is not None else int(np.random.SeedSequence().entropy % (2 ** 62))
-    for row, t in enumerate(traj_indices):
-        gen.manual_seed((base * 1000003 + int(t)) % (2 ** 63 - 1))
-        traj[row] = torch.rand(2 * n_times, dtype=torch.float64, device=device, generator=gen)
-        if samp is not None:
-            samp[row] = torch.rand((n_times, 2), dtype=torch.float64, device=device, generator=gen)
+    kernels.philox_uniform(base, idx, STREAM_TRAJECTORY, n_times, 0, traj)
+    samp = None
+    if order == 2:
+        flat = torch.empty((nb, 2 * n_times), dtype=torch.float64, device=device)
+        kernels.philox_uniform(base, idx, STREAM_SAMPLE, n_times, sample_offset, flat)
+        samp = flat.view(nb, n_times, 2)
     return traj, samp

@@ -157,7 +157,7 @@ class Simulator:
                 tu = torch.from_numpy(tu).to(dev)
                 su = torch.from_numpy(su).to(dev) if su is not None else None
             else:
-                tu, su = philox_tables(sp.random_seed, idx, ep.n_times, ep.order, dev)
+                tu, su = philox_tables(K, sp.random_seed, idx, ep.n_times, ep.order, dev)
             log = [] if self.collect_log else None
             r, dg = eng.run(tu, su, log)
             fin = None
