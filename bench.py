@@ -9,7 +9,7 @@ relaxation+dephasing (lowering + pauli_z, gamma=0.1 on every site), second-order
 sampled every step, started from a seeded random MPS whose bonds are saturated at chi (otherwise the first
 ~50 steps run at tiny chi and measure nothing).  A "step" is one steady-state sampled TJM time step of one batch of
 `--batch` trajectories per GPU: step_through (TDVP sweep, dissipation, jump) + sample (copy, TDVP sweep, dissipation,
-jump, diagnostics, observables) + the per-step all-reduce of the observable sums.  Weak scaling: the batch per GPU is
+jump, diagnostics, observables); the K timed steps end with the one all-reduce of the per-time-step observable sums.  Weak scaling: the batch per GPU is
 fixed, value = (batch * N * K) / max-over-ranks device time.
 """
 from __future__ import annotations
@@ -45,6 +45,7 @@ def parse_args():
     ap.add_argument("--chi", type=int, default=128)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-roofline", action="store_true", help="skip the instrumented extra step and the sweep timing (A/B runs)")
     ap.add_argument("--cpu-cores", type=int, default=0, help="cores for the CPU arm (0 = all)")
     return ap.parse_args()
 
@@ -201,20 +202,26 @@ def run_b200_arm(args):
     traj_ids = [rank * B + b for b in range(B)]
     tu, su = numpy_tables(42, traj_ids, ep.n_times, 2)
     tu_d, su_d = torch.from_numpy(tu).to(dev), torch.from_numpy(su).to(dev)
-    sums = torch.zeros(L + 3 + 1, dtype=torch.float64, device=dev)
 
-    def lane_step(job):
-        k, j = job
+    def lane_steps(job):
+        """Lane k advances `count` steady-state steps back to back (no cross-lane barrier inside: lanes are independent
+        trajectories, exactly as in Simulator.run); returns the per-step sums [count, L + 3]."""
+        k, j0, count = job
         sl = slice(bounds[k], bounds[k + 1])
-        o, dg = engs[k].steady_state_step(tu_d[sl, 2 * j: 2 * j + 2], su_d[sl, j])
-        return torch.cat([o.sum(dim=0), dg.sum(dim=0)])
+        rows = []
+        for j in range(j0, j0 + count):
+            o, dg = engs[k].steady_state_step(tu_d[sl, 2 * j: 2 * j + 2], su_d[sl, j])
+            rows.append(torch.cat([o.sum(dim=0), dg.sum(dim=0)]))
+        return torch.stack(rows)
 
-    def one_step(j, concurrent=True):
-        parts = lanes.map(lane_step, [(k, j) for k in range(nl)]) if concurrent else [lane_step((k, j)) for k in range(nl)]
-        sums[:L + 3] = torch.stack(parts).sum(dim=0)
-        sums[L + 3] = float(B)
+    def run_steps(j0, count, concurrent=True):
+        jobs = [(k, j0, count) for k in range(nl)]
+        parts = lanes.map(lane_steps, jobs) if concurrent else [lane_steps(job) for job in jobs]
+        sums = torch.zeros((count, L + 4), dtype=torch.float64, device=dev)
+        sums[:, :L + 3] = torch.stack(parts).sum(dim=0)
+        sums[:, L + 3] = float(B)
         if world > 1:
-            dist.all_reduce(sums)                       # the one collective of the path: per-step observable sums + counts
+            dist.all_reduce(sums)                       # the one collective of the path: per-time-step observable sums + counts
         return sums
 
     # initialize (F0): half-step dissipation + jump test, then warm-up steps
@@ -224,8 +231,8 @@ def run_b200_arm(args):
         engs[k].stochastic_process(engs[k].phi, ep.dt, tu_d[sl, 0].contiguous(), tu_d[sl, 1].contiguous())
 
     lanes.map(lane_init, range(nl))
-    for j in range(1, W + 1):
-        one_step(j)
+    if W > 0:
+        run_steps(1, W)
     torch.cuda.synchronize(dev)
     if world > 1:
         dist.barrier()
@@ -235,15 +242,14 @@ def run_b200_arm(args):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize(dev)
         e0.record()
-        for j in range(W + 1, W + 1 + K):
-            one_step(j)
+        sums = run_steps(W + 1, K)
         e1.record()
         torch.cuda.synchronize(dev)
         if world > 1:
             dist.barrier()
         ms_total = e0.elapsed_time(e1)
     launches = kern.launch_count()
-    obs_mean = (sums[:L] / sums[L + 3]).cpu().numpy()
+    obs_mean = (sums[-1, :L] / sums[-1, L + 3]).cpu().numpy()
     stats = {k: sum(e.stats[k] for e in engs) - stats0.get(k, 0) for k in engs[0].stats}
     bond_mean = float(torch.cat([e.psi.bond[:, 1:L].to(torch.float64).reshape(-1) for e in engs]).mean().item())
     t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
@@ -252,47 +258,51 @@ def run_b200_arm(args):
     ms_total = float(t.item())
     value = B * world * K / (ms_total / 1000.0)
 
-    # instrumented pass for the roofline: ONE more step of the same kind, lanes run one after the other so that the CUDA
-    # events around every launch see that kernel alone on the GPU (under concurrent lanes they would overlap)
-    kern.start_timing()
-    i0, i1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    i0.record()
-    one_step(W + 1 + K, concurrent=False)
-    i1.record()
-    torch.cuda.synchronize(dev)
-    ms_instr = i0.elapsed_time(i1)
-    timing = kern.stop_timing()
-    eng = engs[0]
+    roofline, sweep_ms, sweep_batch = None, float("nan"), engs[0].B
+    if not args.no_roofline:
+        # instrumented pass for the roofline: ONE more step of the same kind, lanes run one after the other so that the CUDA
+        # events around every launch see that kernel alone on the GPU (under concurrent lanes they would overlap)
+        kern.start_timing()
+        i0, i1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        i0.record()
+        run_steps(W + 1 + K, 1, concurrent=False)
+        i1.record()
+        torch.cuda.synchronize(dev)
+        ms_instr = i0.elapsed_time(i1)
+        timing = kern.stop_timing()
+        eng = engs[0]
 
-    # TDVP sweep alone (BASELINE.json: "TDVP sweep ms")
-    torch.cuda.synchronize(dev)
-    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    eng.psi.copy_from(eng.phi)
-    s0.record()
-    eng.tdvp(eng.psi)
-    s1.record()
-    torch.cuda.synchronize(dev)
-    sweep_ms = s0.elapsed_time(s1)
-    sweep_batch = eng.B
+        # TDVP sweep alone (BASELINE.json: "TDVP sweep ms")
+        torch.cuda.synchronize(dev)
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        eng.psi.copy_from(eng.phi)
+        s0.record()
+        eng.tdvp(eng.psi)
+        s1.record()
+        torch.cuda.synchronize(dev)
+        sweep_ms = s0.elapsed_time(s1)
+        sweep_batch = eng.B
 
-    gemm = timing.get("gemm", {"launches": 0, "ms": 0.0})
-    achieved = timing["gemm_flops"] / (gemm["ms"] / 1000.0) / 1e12 if gemm["ms"] > 0 else 0.0
-    traffic = None
-    try:
-        with open(os.path.join(ROOT, "profiles", "gemm_traffic.json")) as fh:
-            traffic = json.load(fh).get("dram_bytes_per_trajectory_launch") * (bounds[1] - bounds[0])     # ncu capture scaled to this lane batch
-    except Exception:
-        pass
-    roofline = {"kernel": "k_gemm (batched complex128 DMMA contraction: project_site / environment updates / merges)",
-                "bound": "tensor", "achieved": achieved, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": achieved / FP64_PEAK_TFLOPS,
-                "traffic": traffic, "peak_source": "measured FP64 DMMA issue peak on this pool (profiles/r01_fp64_peak.json); MEASURED_PEAKS.json "
-                "carries only HBM and bf16", "launches": gemm["launches"], "avg_launch_ms": gemm["ms"] / max(gemm["launches"], 1),
-                "algorithmic_flops": timing["gemm_flops"], "share_of_step": gemm["ms"] / ms_instr,
-                "timing": f"instrumented extra step, lanes serialised ({ms_instr:.0f} ms vs {ms_total / K:.0f} ms per step with {nl} concurrent lanes)",
-                "other_kernels_ms": {k: v["ms"] for k, v in timing.items() if isinstance(v, dict) and k != "gemm"}}
+        gemm = timing.get("gemm", {"launches": 0, "ms": 0.0})
+        achieved = timing["gemm_flops"] / (gemm["ms"] / 1000.0) / 1e12 if gemm["ms"] > 0 else 0.0
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "gemm_traffic.json")) as fh:
+                traffic = json.load(fh).get("dram_bytes_per_trajectory_launch") * (bounds[1] - bounds[0])     # ncu capture scaled to this lane batch
+        except Exception:
+            pass
+        roofline = {"kernel": "k_gemm (batched complex128 DMMA contraction: project_site / environment updates / merges)",
+                    "bound": "tensor", "achieved": achieved, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": achieved / FP64_PEAK_TFLOPS,
+                    "traffic": traffic, "peak_source": "measured FP64 DMMA issue peak on this pool (profiles/r01_fp64_peak.json); MEASURED_PEAKS.json "
+                    "carries only HBM and bf16", "launches": gemm["launches"], "avg_launch_ms": gemm["ms"] / max(gemm["launches"], 1),
+                    "algorithmic_flops": timing["gemm_flops"], "share_of_step": gemm["ms"] / ms_instr,
+                    "timing": f"instrumented extra step, lanes serialised ({ms_instr:.0f} ms vs {ms_total / K:.0f} ms per step with {nl} concurrent lanes)",
+                    "other_kernels_ms": {k: v["ms"] for k, v in timing.items() if isinstance(v, dict) and k != "gemm"}}
+
 
     # free the resident engine before the end-to-end pass
-    del eng, engs
+    eng = None
+    del engs
     torch.cuda.empty_cache()
 
     e2e = None

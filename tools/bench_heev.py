@@ -14,7 +14,8 @@ def main():
     kern = K.CudaKernels("cuda:0")
     dev = "cuda:0"
     out = {}
-    for k, nb in [(256, 8), (256, 148), (256, 296), (128, 296), (512, 74)]:
+    for ring, (k, nb) in [(r, c) for r in (0, 1) for c in [(256, 8), (256, 128), (256, 148), (256, 296), (128, 296), (512, 74)]]:
+        kern.set_option("heev_ring", ring)
         sq = k * k
         rng = np.random.default_rng(k + nb)
         a = rng.standard_normal((k, k)) + 1j * rng.standard_normal((k, k))
@@ -42,7 +43,7 @@ def main():
         kern.gemm(K.OP_EVEC, nb, 1, None, ext, None, None, 1, 1, 1, Buf(zt, 0, sq), Buf(qh, 0, sq), Buf(qa, 0, sq), 0, k, k)
         e1.record()
         torch.cuda.synchronize()
-        out[f"k{k}_b{nb}"] = {"heev_ms": ms, "evec_gemm_ms": e0.elapsed_time(e1), "status": int(status.max().item())}
+        out[f"k{k}_b{nb}_ring{ring}"] = {"heev_ms": ms, "evec_gemm_ms": e0.elapsed_time(e1), "status": int(status.max().item())}
     import json
     print(json.dumps(out))
 
