@@ -62,7 +62,7 @@ def _check(name, rows):
 def test_philox_ensemble_matches_reference_host_twin(name):
     """Host logic + Philox addressing with the numpy kernel twin (small ensemble)."""
     from oracle.np_kernels import NumpyKernels
-    rows = _run(name, 96, 314159, kernels=NumpyKernels())
+    rows = _run(name, 64, 314159, kernels=NumpyKernels())
     _check(name, rows)
 
 

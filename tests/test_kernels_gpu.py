@@ -355,12 +355,14 @@ def test_heev_row_ring_is_bit_identical(backends, ks):
     try:
         cuda.set_option("heev_ring", 0)
         d0, qa0, meta0, status0 = _run_heev(cuda, "cuda", ks, mats)
-        cuda.set_option("heev_ring", 1)
-        d1, qa1, meta1, status1 = _run_heev(cuda, "cuda", ks, mats)
+        assert not status0.any()
+        for depth in (6, 12, 16):
+            cuda.set_option("heev_ring", depth)
+            d1, qa1, meta1, status1 = _run_heev(cuda, "cuda", ks, mats)
+            assert not status1.any()
+            assert np.array_equal(d0, d1) and np.array_equal(qa0, qa1) and np.array_equal(meta0, meta1), f"ring depth {depth}"
     finally:
-        cuda.set_option("heev_ring", 1)
-    assert not status0.any() and not status1.any()
-    assert np.array_equal(d0, d1) and np.array_equal(qa0, qa1) and np.array_equal(meta0, meta1)
+        cuda.set_option("heev_ring", -1)
 
 
 def test_heev_diagonal_and_identity(backends):

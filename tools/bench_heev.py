@@ -14,7 +14,7 @@ def main():
     kern = K.CudaKernels("cuda:0")
     dev = "cuda:0"
     out = {}
-    for ring, (k, nb) in [(r, c) for r in (0, 1) for c in [(256, 8), (256, 128), (256, 148), (256, 296), (128, 296), (512, 74)]]:
+    for ring, (k, nb) in [(r, c) for r in (0, 6, 12, 16) for c in [(256, 8), (256, 128), (256, 296), (128, 296), (512, 74)]]:
         kern.set_option("heev_ring", ring)
         sq = k * k
         rng = np.random.default_rng(k + nb)
@@ -44,6 +44,7 @@ def main():
         e1.record()
         torch.cuda.synchronize()
         out[f"k{k}_b{nb}_ring{ring}"] = {"heev_ms": ms, "evec_gemm_ms": e0.elapsed_time(e1), "status": int(status.max().item())}
+    kern.set_option("heev_ring", -1)
     import json
     print(json.dumps(out))
 

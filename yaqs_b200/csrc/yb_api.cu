@@ -3,6 +3,7 @@
 #include "yb_common.cuh"
 #include <atomic>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 // unity build: the kernels live in the same translation unit (no -rdc needed)
@@ -51,12 +52,12 @@ void yb_set_flop_counter(void* device_u64) { g_flop_counter = (unsigned long lon
 
 // diagnostic switches (A/B runs and bisecting a failure); the defaults are the production route
 static std::atomic<int> g_opt_heev_ql{getenv("YB_HEEV_QL") != nullptr ? 1 : 0};
-static std::atomic<int> g_opt_heev_ring{getenv("YB_HEEV_NORING") != nullptr ? 0 : 1};
+static std::atomic<int> g_opt_heev_ring{getenv("YB_HEEV_RING") != nullptr ? atoi(getenv("YB_HEEV_RING")) : -1};
 
 int yb_set_option(const char* name, int value) {
     if (!name) return fail_msg("yb_set_option: null name");
     if (!strcmp(name, "heev_ql")) { g_opt_heev_ql = value != 0; return 0; }
-    if (!strcmp(name, "heev_ring")) { g_opt_heev_ring = value != 0; return 0; }
+    if (!strcmp(name, "heev_ring")) { g_opt_heev_ring = value; return 0; }
     return fail_msg("yb_set_option: unknown option");
 }
 
@@ -191,10 +192,13 @@ int yb_heev(int nbatch, const int32_t* mask, yb_extent ek, void* g, int64_t stri
     if (max_k > heev::KMAX) return fail_msg("yb_heev: max_k > 512 unsupported");
     static bool configured = false;
     if (!configured) {
-        cudaError_t e1 = cudaFuncSetAttribute(heev::k_hetrd<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)heev::SMEM_BYTES);
-        if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(heev::k_ungtr<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)heev::SMEM_BYTES);
-        if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(heev::k_hetrd<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(heev::SMEM_BYTES + heev::RING_BYTES));
-        if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(heev::k_ungtr<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(heev::SMEM_BYTES + heev::RING_BYTES));
+        cudaError_t e1 = cudaFuncSetAttribute(heev::k_hetrd<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)heev::SMEM_BYTES);
+        if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(heev::k_ungtr<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)heev::SMEM_BYTES);
+#define YB_RING_ATTR(R)                                                                                                                         \
+        if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(heev::k_hetrd<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(heev::SMEM_BYTES + heev::ring_bytes(R))); \
+        if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(heev::k_ungtr<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(heev::SMEM_BYTES + heev::ring_bytes(R)));
+        YB_RING_ATTR(6) YB_RING_ATTR(12) YB_RING_ATTR(16)
+#undef YB_RING_ATTR
         if (e1 != cudaSuccess) return fail("yb_heev(attr)", e1);
         e1 = cudaFuncSetAttribute(heev::k_stedc<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(stedc::Smem<128>));
         if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(heev::k_stedc<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(stedc::Smem<256>));
@@ -217,21 +221,19 @@ int yb_heev(int nbatch, const int32_t* mask, yb_extent ek, void* g, int64_t stri
         if (e2 == cudaSuccess) e2 = cudaEventCreateWithFlags(&ev_join[dev], cudaEventDisableTiming);
         if (e2 != cudaSuccess) return fail("yb_heev(side stream)", e2);
     }
-    const bool use_ring = g_opt_heev_ring.load() != 0;     // off: direct register loads instead of the cp.async row ring
-    if (use_ring)
-        heev::k_hetrd<true><<<nbatch, heev::THREADS, heev::SMEM_BYTES + heev::RING_BYTES, st>>>((cplx*)g, stride_g, ek.ptr, ek.stride, d, e, (cplx*)tau,
-                                                                                              stride_vec, mask);
-    else
-        heev::k_hetrd<false><<<nbatch, heev::THREADS, heev::SMEM_BYTES, st>>>((cplx*)g, stride_g, ek.ptr, ek.stride, d, e, (cplx*)tau, stride_vec, mask);
+    // row-ring depth of the streaming kernels: option "heev_ring" = -1 (default: by matrix size), 0 (direct loads), 6, 12, 16
+    int ring = g_opt_heev_ring.load();
+    if (ring < 0) ring = (max_k > 256) ? 6 : 0;      // measured (profiles/r01_heev_microbench_v5_ring.json): pays off only at k = 512
+    ring = ring >= 16 ? 16 : ring >= 12 ? 12 : ring >= 6 ? 6 : 0;
+#define YB_HETRD(R) heev::k_hetrd<R><<<nbatch, heev::THREADS, heev::SMEM_BYTES + (R ? heev::ring_bytes(R) : 0), st>>>((cplx*)g, stride_g, ek.ptr, ek.stride, d, e, (cplx*)tau, stride_vec, mask)
+    if (ring == 16) YB_HETRD(16); else if (ring == 12) YB_HETRD(12); else if (ring == 6) YB_HETRD(6); else YB_HETRD(0);
+#undef YB_HETRD
     if (int rc = done("yb_heev(hetrd)")) return rc;
     cudaEventRecord(ev_fork[dev], st);
     cudaStreamWaitEvent(side[dev], ev_fork[dev], 0);
-    if (use_ring)
-        heev::k_ungtr<true><<<nbatch, heev::THREADS, heev::SMEM_BYTES + heev::RING_BYTES, side[dev]>>>((const cplx*)g, stride_g, (const cplx*)tau, stride_vec,
-                                                                                                      (cplx*)qh, stride_q, ek.ptr, ek.stride, mask);
-    else
-        heev::k_ungtr<false><<<nbatch, heev::THREADS, heev::SMEM_BYTES, side[dev]>>>((const cplx*)g, stride_g, (const cplx*)tau, stride_vec, (cplx*)qh, stride_q,
-                                                                                    ek.ptr, ek.stride, mask);
+#define YB_UNGTR(R) heev::k_ungtr<R><<<nbatch, heev::THREADS, heev::SMEM_BYTES + (R ? heev::ring_bytes(R) : 0), side[dev]>>>((const cplx*)g, stride_g, (const cplx*)tau, stride_vec, (cplx*)qh, stride_q, ek.ptr, ek.stride, mask)
+    if (ring == 16) YB_UNGTR(16); else if (ring == 12) YB_UNGTR(12); else if (ring == 6) YB_UNGTR(6); else YB_UNGTR(0);
+#undef YB_UNGTR
     if (int rc = done("yb_heev(ungtr)")) return rc;
     cudaEventRecord(ev_join[dev], side[dev]);
     const bool use_ql = g_opt_heev_ql.load() != 0;      // on: the implicit-QL kernel instead of divide & conquer

@@ -23,8 +23,7 @@ constexpr size_t SMEM_BYTES = (size_t)(3 + RSMAX) * KMAX * sizeof(cplx);
 // warp-private slice of shared memory), so a Householder step is no longer (rows / 4) dependent global-load round trips --
 // ncu (profiles/r01_ncu_heev_full_stedc.json) showed 56-62 % of the stall samples of k_hetrd / k_ungtr on those loads with
 // DRAM at 52 % of its rate.  A thread only ever reads back its own copies, so cp.async.wait_group is the only synchronisation.
-constexpr int RING = 6;
-constexpr size_t RING_BYTES = (size_t)NWARPS * RING * 32 * sizeof(cplx);
+constexpr size_t ring_bytes(int ring) { return (size_t)NWARPS * ring * 32 * sizeof(cplx); }
 
 __device__ __forceinline__ void ring_load(cplx* smem_dst, const cplx* gmem_src) {
     const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -69,7 +68,7 @@ __device__ __forceinline__ void householder_from_row(const cplx* row, int ns, cp
 
 // Reduction to real tridiagonal form, lower variant of zhetd2 on full Hermitian storage.  On exit row j of G holds the
 // Householder vector v_j in columns j+1.. (v_j[0] = 1), d/e the tridiagonal, tau the reflector scalars.
-template <bool USE_RING>
+template <int RING>
 __global__ void __launch_bounds__(THREADS, 1) k_hetrd(cplx* G, long long sG, const int* ek, int esk, double* dout, double* eout, cplx* tauout,
                                                        long long s_vec, const int* mask) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -82,7 +81,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_hetrd(cplx* G, long long sG, con
     cplx* w = v + KMAX;
     cplx* vn = w + KMAX;
     cplx* part = vn + KMAX;                 // [RSMAX][KMAX]
-    cplx* ring = part + RSMAX * KMAX;       // [NWARPS][RING][32]   (USE_RING only)
+    cplx* ring = part + RSMAX * KMAX;       // [NWARPS][RING][32]   (RING > 0 only)
     cplx* Gb = G + (long long)b * sG;
     double* d = dout + (long long)b * s_vec;
     double* e = eout + (long long)b * s_vec;
@@ -155,7 +154,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_hetrd(cplx* G, long long sG, con
             if (sp.on) {
                 const int c = c0 + sp.cb * 32 + lane;
                 cplx acc = make_double2(0.0, 0.0);
-                if (c < n && USE_RING) {
+                if constexpr (RING > 0) {
+                  if (c < n) {
                     const cplx wc = w[c - (j + 1)], vc = v[c - (j + 1)];
                     cplx* rg = ring + ((tid >> 5) * RING) * 32 + lane;          // slot s of this thread: rg[s * 32]
                     const int i0 = c0 + sp.rs;
@@ -183,6 +183,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_hetrd(cplx* G, long long sG, con
                     }
                     ring_wait<0>();
                     part[sp.rs * KMAX + (c - c0)] = acc;
+                  }
                 } else if (c < n) {
                     const cplx wc = w[c - (j + 1)], vc = v[c - (j + 1)];
                     int i = c0 + sp.rs;
@@ -226,8 +227,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_hetrd(cplx* G, long long sG, con
 }
 
 // Q = H_0 H_1 ... H_{n-2} by backward accumulation (zungtr, lower): one fused pass per reflector over the block it touches.
-template <bool USE_RING>
-__global__ void __launch_bounds__(THREADS, 2) k_ungtr(const cplx* __restrict__ G, long long sG, const cplx* __restrict__ tauin, long long s_vec,
+template <int RING>
+__global__ void __launch_bounds__(THREADS, RING > 6 ? 1 : 2) k_ungtr(const cplx* __restrict__ G, long long sG, const cplx* __restrict__ tauin, long long s_vec,
                                                        cplx* Q, long long sQ, const int* ek, int esk, const int* mask) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int b = blockIdx.x;
@@ -238,7 +239,7 @@ __global__ void __launch_bounds__(THREADS, 2) k_ungtr(const cplx* __restrict__ G
     cplx* vp = v + KMAX;                            // v_{j-1} (local index i - j)
     cplx* tv = vp + KMAX;                           // t_j[c - (j+1)] = (v_j^H Q[S,S])[c]
     cplx* part = tv + KMAX;
-    cplx* ring = part + RSMAX * KMAX;               // [NWARPS][RING][32]   (USE_RING only)
+    cplx* ring = part + RSMAX * KMAX;               // [NWARPS][RING][32]   (RING > 0 only)
     const cplx* Gb = G + (long long)b * sG;
     const cplx* tauv = tauin + (long long)b * s_vec;
     cplx* Qb = Q + (long long)b * sQ;
@@ -261,7 +262,8 @@ __global__ void __launch_bounds__(THREADS, 2) k_ungtr(const cplx* __restrict__ G
         const Split sp = make_split(ns);
         if (sp.on) {
             const int c = r0 + sp.cb * 32 + lane;
-            if (c < n && USE_RING) {
+            if constexpr (RING > 0) {
+              if (c < n) {
                 const cplx tc = cmul(tau, tv[c - r0]);
                 cplx acc = make_double2(0.0, 0.0);
                 cplx* rg = ring + ((tid >> 5) * RING) * 32 + lane;
@@ -290,6 +292,7 @@ __global__ void __launch_bounds__(THREADS, 2) k_ungtr(const cplx* __restrict__ G
                 }
                 ring_wait<0>();
                 part[sp.rs * KMAX + (c - r0)] = acc;
+              }
             } else if (c < n) {
                 const cplx tc = cmul(tau, tv[c - r0]);
                 cplx acc = make_double2(0.0, 0.0);
