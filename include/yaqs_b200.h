@@ -40,7 +40,7 @@ void yb_set_flop_counter(void* device_u64);
 /* Diagnostic switches for A/B runs (defaults = production route; environment YB_HEEV_QL / YB_HEEV_RING set the initial value):
  *   "heev_ql"   1 = implicit-QL tridiagonal eigen-solver instead of divide & conquer                          (default 0)
  *   "heev_ring" depth of the cp.async row ring in k_hetrd / k_ungtr: 0 = direct register loads, 6, 12, 16;
- *               -1 = by matrix size (default: ring of 6 for k > 256, direct loads below)                        */
+ *               -1 = by matrix size (default: 16 rows in flight for k > 256, direct loads below)                      */
 int yb_set_option(const char* name, int value);
 
 /* ---- contractions -------------------------------------------------------------------------------------------------

@@ -223,7 +223,9 @@ int yb_heev(int nbatch, const int32_t* mask, yb_extent ek, void* g, int64_t stri
     }
     // row-ring depth of the streaming kernels: option "heev_ring" = -1 (default: by matrix size), 0 (direct loads), 6, 12, 16
     int ring = g_opt_heev_ring.load();
-    if (ring < 0) ring = (max_k > 256) ? 6 : 0;      // measured (profiles/r01_heev_microbench_v5_ring.json): pays off only at k = 512
+    // measured (profiles/r01_heev_microbench_v6_ring_depth.json): k = 512, B = 74: 59.3 -> 46.2 ms with 16 rows in flight; at
+    // k = 256 the direct loads win for the lane batches in use (B = 128: 8.6 ms vs 9.1 ms)
+    if (ring < 0) ring = (max_k > 256) ? 16 : 0;
     ring = ring >= 16 ? 16 : ring >= 12 ? 12 : ring >= 6 ? 6 : 0;
 #define YB_HETRD(R) heev::k_hetrd<R><<<nbatch, heev::THREADS, heev::SMEM_BYTES + (R ? heev::ring_bytes(R) : 0), st>>>((cplx*)g, stride_g, ek.ptr, ek.stride, d, e, (cplx*)tau, stride_vec, mask)
     if (ring == 16) YB_HETRD(16); else if (ring == 12) YB_HETRD(12); else if (ring == 6) YB_HETRD(6); else YB_HETRD(0);

@@ -23,6 +23,7 @@ constexpr size_t SMEM_BYTES = (size_t)(3 + RSMAX) * KMAX * sizeof(cplx);
 // warp-private slice of shared memory), so a Householder step is no longer (rows / 4) dependent global-load round trips --
 // ncu (profiles/r01_ncu_heev_full_stedc.json) showed 56-62 % of the stall samples of k_hetrd / k_ungtr on those loads with
 // DRAM at 52 % of its rate.  A thread only ever reads back its own copies, so cp.async.wait_group is the only synchronisation.
+// Depth is a template parameter (0 = direct register loads); yb_heev picks it by matrix size from measurements.
 constexpr size_t ring_bytes(int ring) { return (size_t)NWARPS * ring * 32 * sizeof(cplx); }
 
 __device__ __forceinline__ void ring_load(cplx* smem_dst, const cplx* gmem_src) {
