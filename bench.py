@@ -325,7 +325,9 @@ def run_b200_arm(args):
         d2h = B * (L + 3) * (K + 1) * 8
         e2e = {"value": B * world * K / t_e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d / K), "d2h_bytes_per_step": int(d2h / K),
                "seconds": t_e2e, "api": "Simulator.run(State, Hamiltonian, AnalogSimParams, NoiseModel) with host inputs; includes buffer "
-               "allocation, H2D of state/MPO/uniform tables, D2H of per-trajectory results", "z_mean_site0_last": float(res.expectation_values[0][-1])}
+               "allocation, H2D of state/MPO/uniform tables, D2H of per-trajectory results", "z_mean_site0_last": float(res.expectation_values[0][-1]),
+               "steps_covered": f"initialisation + steps 1..{K} from the initial state (value: steps {W + 1}..{W + K} of the resident batch)",
+               "counters": {k: int(v) for k, v in (res.stats or {}).items()}}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -62,13 +62,45 @@ CASES = {
     "ising12_chi40_gram": dict(model="ising", L=12, J=1.0, g=0.7, init="random:40:5", chi=40, thr=1e-8, order=2, dt=0.1, steps=3,
                                sample_timesteps=True, ntraj=3, seed=9, obs="z",
                                noise=[("lowering", 0.5), ("pauli_z", 0.3)]),
+    # meta-observables: entanglement entropy of every cut and projection-valued measurements, next to Z
+    "ising6_entropy_order2": dict(model="ising", L=6, J=1.0, g=0.8, init="x+", chi=8, thr=1e-8, order=2, dt=0.1, steps=5,
+                                      sample_timesteps=True, ntraj=4, seed=31, obs="z+ent",
+                                      noise=[("lowering", 0.3), ("pauli_z", 0.2)]),
+    "heis6_entropy_order1": dict(model="heisenberg", L=6, J=1.0, g=0.0, init="Neel", chi=8, thr=1e-8, order=1, dt=0.1, steps=5,
+                                     sample_timesteps=True, ntraj=3, seed=32, obs="ent+zz",
+                                     noise=[("lowering", 0.2)]),
+    # PVM observables cannot be mixed with others (simulation_parameters.py:583)
+    "ising6_pvm_order2": dict(model="ising", L=6, J=1.0, g=0.8, init="x+", chi=8, thr=1e-8, order=2, dt=0.1, steps=4,
+                              sample_timesteps=True, ntraj=4, seed=33, obs="pvm0+pvm01+pvm110",
+                              noise=[("lowering", 0.3), ("pauli_z", 0.2)]),
     # final-column-only bookkeeping with order 1
     "ising6_final_only_order1": dict(model="ising", L=6, J=1.0, g=0.5, init="zeros", chi=8, thr=1e-6, order=1, dt=0.1, steps=5,
                                      sample_timesteps=False, ntraj=6, seed=21, obs="z",
                                      noise=[("lowering", 0.3), ("pauli_z", 0.2)]),
 }
 
+# Fixtures at BASELINE.json's own sizes.  The reference (and the oracle) need minutes per case on a CPU core, so the CPU suite
+# checks them only with YB_SLOW_TESTS=1; the `-m gpu` suite always runs them (seconds on the B200).
+LARGE_CASES = {
+    # BASELINE config 2 at its own bond dimension (Heisenberg, D = 5 MPO, chi = 64, Z and ZZ every step), saturated random start
+    "heis30_c2_chi64": dict(model="heisenberg", L=30, J=1.0, g=0.0, init="random:64:5", chi=64, thr=1e-6, order=2, dt=0.1, steps=2,
+                            sample_timesteps=True, ntraj=2, seed=13, obs="z+zz",
+                            noise=[("lowering", 0.1)]),
+    # BASELINE config 3 at FULL size (L = 100, chi = 128, relaxation + dephasing): one sampled order-2 step of two trajectories
+    # from the saturated random state bench.py starts from -- the headline workload itself, checked against the reference
+    "ising100_c3_step": dict(model="ising", L=100, J=1.0, g=0.5, init="random:128:1234", chi=128, thr=1e-6, order=2, dt=0.1, steps=1,
+                             sample_timesteps=True, ntraj=2, seed=42, obs="z",
+                             noise=[("lowering", 0.1), ("pauli_z", 0.1)]),
+}
+ALL_CASES = {**CASES, **LARGE_CASES}
 
+
+
+
+def pvm_bitstring(tok: str, length: int) -> str:
+    """'pvm0' -> 000..., 'pvm01' -> 0101..., 'pvm110' -> 110110... (pattern repeated to the chain length)."""
+    pat = tok[3:]
+    return (pat * length)[:length]
 
 
 def initial_state(cfg: dict) -> O.OracleMPS:
@@ -96,6 +128,10 @@ def oracle_inputs(cfg: dict):
     for tok in cfg["obs"].split("+"):
         if tok in ("x", "y", "z"):
             obs += [(O.OBSERVABLE_MATRICES[tok], [s]) for s in range(L)]
+        elif tok == "ent":
+            obs += [("entropy", [s, s + 1]) for s in range(L - 1)]
+        elif tok.startswith("pvm"):
+            obs += [("pvm:" + pvm_bitstring(tok, L), [])]
         else:
             obs += [(O.OBSERVABLE_MATRICES[tok], [s, s + 1]) for s in range(L - 1)]
     order = O.sort_observables(obs)
@@ -156,6 +192,10 @@ def digital_inputs(cfg: dict):
     for tok in cfg["obs"].split("+"):
         if tok in ("x", "y", "z"):
             obs += [(O.OBSERVABLE_MATRICES[tok], [s]) for s in range(L)]
+        elif tok == "ent":
+            obs += [("entropy", [s, s + 1]) for s in range(L - 1)]
+        elif tok.startswith("pvm"):
+            obs += [("pvm:" + pvm_bitstring(tok, L), [])]
         else:
             obs += [(O.OBSERVABLE_MATRICES[tok], [s, s + 1]) for s in range(L - 1)]
     order = O.sort_observables(obs)

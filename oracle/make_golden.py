@@ -23,7 +23,7 @@ from oracle.ref_shim import load_reference  # noqa: E402
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
 
-from oracle.golden_cases import CASES, DIGITAL_CASES, initial_state  # noqa: E402
+from oracle.golden_cases import ALL_CASES, CASES, DIGITAL_CASES, initial_state, pvm_bitstring  # noqa: E402
 
 
 class _RecordingRng:
@@ -71,6 +71,10 @@ def run_case(name: str, cfg: dict) -> dict:
             obs += [Observable(X(), s) for s in range(L)]
         elif tok == "zz":
             obs += [Observable(ZZ(), [s, s + 1]) for s in range(L - 1)]
+        elif tok == "ent":
+            obs += [Observable("entropy", [s, s + 1]) for s in range(L - 1)]
+        elif tok.startswith("pvm"):
+            obs += [Observable(pvm_bitstring(tok, L))]          # unknown names resolve to GateLibrary.pvm(bitstring)
     procs = [{"name": n, "sites": [i], "strength": g} for i in range(L) for (n, g) in cfg["noise"]]
     procs += [{"name": n, "sites": list(s), "strength": g} for (n, s, g) in cfg.get("noise2", [])]
     noise = NoiseModel(procs) if procs else None
@@ -80,7 +84,7 @@ def run_case(name: str, cfg: dict) -> dict:
                           tdvp_mode=cfg.get("tdvp_mode", "2site"))
     assert len(sim.times) == cfg["steps"] + 1, (len(sim.times), cfg["steps"])
     # the workers see observables in sorted order (simulator.py:1561-1562)
-    sorted_sites = [o.sites for o in sim.sorted_observables]
+    sorted_sites = [getattr(o, "sites", -1) for o in sim.sorted_observables]          # PVM observables carry no sites
     sorted_names = [o.gate.name for o in sim.sorted_observables]
 
     ncol = len(sim.times) if cfg["sample_timesteps"] else 1
@@ -233,7 +237,7 @@ def main(argv: list[str]) -> int:
     os.makedirs(GOLDEN_DIR, exist_ok=True)
     names = argv or (list(CASES) + list(DIGITAL_CASES))
     for name in names:
-        data = run_digital_case(name, DIGITAL_CASES[name]) if name in DIGITAL_CASES else run_case(name, CASES[name])
+        data = run_digital_case(name, DIGITAL_CASES[name]) if name in DIGITAL_CASES else run_case(name, ALL_CASES[name])
         path = os.path.join(GOLDEN_DIR, f"{name}.npz")
         np.savez_compressed(path, **data)
         njump = int(data["jumped"].sum())

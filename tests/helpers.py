@@ -4,13 +4,13 @@ import os
 import numpy as np
 import torch
 
-from oracle.golden_cases import CASES, oracle_inputs
+from oracle.golden_cases import ALL_CASES, oracle_inputs
 from yaqs_b200.engine import BatchedTJM, EngineParams
 from yaqs_b200.rng import numpy_tables
 
 
 def engine_for_case(name, kernels, trajectories=None, **kw):
-    cfg = CASES[name]
+    cfg = ALL_CASES[name]
     init, mpo, noise, p, obs = oracle_inputs(cfg)
     traj = list(range(cfg["ntraj"])) if trajectories is None else list(trajectories)
     ep = EngineParams(dt=p.dt, n_steps=p.n_steps, order=p.order, max_bond_dim=p.max_bond_dim, svd_threshold=p.svd_threshold,

@@ -5,7 +5,7 @@ Bar (BASELINE.json north_star): fed the same uniforms every trajectory takes the
 import pytest
 import torch
 
-from oracle.golden_cases import CASES
+from oracle.golden_cases import CASES, LARGE_CASES
 from tests.helpers import check_against_golden, engine_for_case
 from yaqs_b200.kernels import CudaKernels
 
@@ -20,6 +20,20 @@ def test_cuda_engine_matches_reference(golden_dir, name):
     results, diag = eng.run(tu, su, log)
     torch.cuda.synchronize()
     assert int(eng.status.max().item()) == 0
+    check_against_golden(name, golden_dir, results, diag, log, traj)
+
+
+@pytest.mark.parametrize("name", sorted(LARGE_CASES))
+def test_cuda_engine_matches_reference_at_baseline_sizes(golden_dir, name):
+    """BASELINE.json configs 2 and 3 at their own sizes (Heisenberg L=30 chi=64 with Z and ZZ; Ising L=100 chi=128 -- the bench
+    workload itself): same jumps, identical kept bond dimensions, observables <= 1e-10 against the unmodified reference."""
+    kern = CudaKernels("cuda:0")
+    eng, tu, su, traj = engine_for_case(name, kern)
+    log = []
+    results, diag = eng.run(tu, su, log)
+    torch.cuda.synchronize()
+    assert int(eng.status.max().item()) == 0
+    assert eng.stats["gram_svd_calls"] > 0                 # the production SVD route was taken
     check_against_golden(name, golden_dir, results, diag, log, traj)
 
 

@@ -57,6 +57,35 @@ def test_user_order_and_two_site_observables():
             assert abs(res.expectation_values[k][col] - np.vdot(psi, op @ psi).real) < 5e-5
 
 
+def test_entropy_and_pvm_observables_through_simulator(golden_dir):
+    """Meta-observables through the public API (Observable("entropy", [i, i+1]); any non-GateLibrary string is a PVM bitstring,
+    simulation_parameters.py:388-400) against the fixtures of the unmodified reference."""
+    from oracle.golden_cases import CASES
+    cfg = CASES["ising6_entropy_order2"]
+    L = cfg["L"]
+    obs = [Observable(Z(), s) for s in range(L)] + [Observable("entropy", [s, s + 1]) for s in range(L - 1)]
+    noise = NoiseModel([{"name": n, "sites": [i], "strength": g} for i in range(L) for (n, g) in cfg["noise"]])
+    sp = AnalogSimParams(observables=obs, elapsed_time=cfg["dt"] * cfg["steps"], dt=cfg["dt"], num_traj=cfg["ntraj"], max_bond_dim=cfg["chi"],
+                         svd_threshold=cfg["thr"], krylov_tol=1e-4, order=2, sample_timesteps=True, random_seed=cfg["seed"])
+    res = Simulator(show_progress=False, kernels=NumpyKernels()).run(State(L, initial=cfg["init"]), Hamiltonian.ising(L, cfg["J"], cfg["g"]), sp, noise)
+    g = np.load(os.path.join(golden_dir, "ising6_entropy_order2.npz"))
+    idx = sp.observable_sorted_indices
+    for user_i in range(len(obs)):
+        assert np.max(np.abs(np.asarray(res.trajectories[user_i]) - g["results"][:, idx[user_i], :])) < 1e-10
+    cfg = CASES["ising6_pvm_order2"]
+    pv = [Observable("0" * L), Observable(("01" * L)[:L]), Observable(("110" * L)[:L])]
+    sp = AnalogSimParams(observables=pv, elapsed_time=cfg["dt"] * cfg["steps"], dt=cfg["dt"], num_traj=cfg["ntraj"], max_bond_dim=cfg["chi"],
+                         svd_threshold=cfg["thr"], krylov_tol=1e-4, order=2, sample_timesteps=True, random_seed=cfg["seed"])
+    res = Simulator(show_progress=False, kernels=NumpyKernels()).run(State(L, initial=cfg["init"]), Hamiltonian.ising(L, cfg["J"], cfg["g"]), sp, noise)
+    g = np.load(os.path.join(golden_dir, "ising6_pvm_order2.npz"))
+    for k in range(3):
+        assert np.max(np.abs(np.asarray(res.trajectories[k]) - g["results"][:, k, :])) < 1e-10
+    with pytest.raises(AssertionError, match="mixed observable and projective-measurement"):
+        AnalogSimParams(observables=[Observable(Z(), 0), Observable("0" * L)], elapsed_time=0.1, dt=0.1)
+    with pytest.raises(NotImplementedError):
+        Observable("schmidt_spectrum", [0, 1])
+
+
 def test_mpo_factories_match_dense():
     z, x, y, i2 = np.diag([1.0, -1.0]), np.array([[0, 1.0], [1, 0]]), np.array([[0, -1j], [1j, 0]]), np.eye(2)
 

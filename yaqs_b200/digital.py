@@ -12,6 +12,7 @@ import torch
 
 from .circuits import CompiledCircuit, compile_circuit
 from .engine import BatchedTJM, EngineParams
+from .params import engine_observables
 from .rng import numpy_tables, philox_tables
 
 
@@ -39,7 +40,7 @@ def run_digital(simulator, initial_state, operator, sp, noise, result):
     ntraj = 1 if noiseless else sp.num_traj                                                   # simulator.py:1735-1745
     sorted_obs = sp.sorted_observables
     to_sorted = sp.observable_sorted_indices
-    obs = [(np.asarray(o.gate.matrix, dtype=np.complex128), ([o.sites] if isinstance(o.sites, int) else list(o.sites))) for o in sorted_obs]
+    obs = engine_observables(sorted_obs, length)
     ep = EngineParams(dt=1.0, n_steps=1, order=1, max_bond_dim=sp.max_bond_dim, svd_threshold=sp.svd_threshold, trunc_mode=sp.trunc_mode,
                       krylov_tol=sp.krylov_tol, tdvp_mode=sp.tdvp_mode, tdvp_sweeps=sp.tdvp_sweeps, sample_timesteps=True, digital=True)
     if ep.tdvp_mode != "2site":

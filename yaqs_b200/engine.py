@@ -241,7 +241,9 @@ class BatchedTJM:
         self._noise_cache: dict = {}
         self._set_noise(self._make_noise_ctx(noise))
         # observables (already in the reference's sorted order)
-        self.observables = [(np.asarray(m, dtype=np.complex128), tuple(int(s) for s in sites)) for m, sites in observables]
+        # entries: (matrix, sites) | ("entropy", (i, i+1)) | ("pvm:<bitstring>", ())
+        self.observables = [(m if isinstance(m, str) else np.asarray(m, dtype=np.complex128), tuple(int(s) for s in sites)) for m, sites in observables]
+        self._ones_i32 = torch.ones(B, dtype=torch.int32, device=dev)
         self.stats = {"krylov_calls": 0, "matvecs": 0, "svd_calls": 0, "svd_sweeps": 0, "jumps": 0, "gram_svd_calls": 0, "gram_fallbacks": 0}
 
     # ------------------------------------------------------------------------------------------------------------------
@@ -745,19 +747,69 @@ class BatchedTJM:
 
     def evaluate_observables(self, st: BatchedState) -> torch.Tensor:
         """[B, n_obs] expectation values in the given (sorted) observable order (mps.py:1178-1234)."""
-        need1 = [s[0] for _, s in self.observables if len(s) == 1]
-        need2 = [s[0] for _, s in self.observables if len(s) == 2]
-        for _, s in self.observables:
+        local = [(m, s) for m, s in self.observables if not isinstance(m, str)]
+        need1 = [s[0] for _, s in local if len(s) == 1]
+        need2 = [s[0] for _, s in local if len(s) == 2]
+        for _, s in local:
             if len(s) == 2 and s[1] != s[0] + 1:
                 raise AssertionError("Only nearest-neighbor observables are currently implemented.")
-        g1, g2 = self.rho_sweep(st, need1, need2)
+        g1, g2 = self.rho_sweep(st, need1, need2) if local else ({}, {})
         res = torch.zeros((self.B, len(self.observables)), dtype=torch.float64, device=self.dev)
         for k, (mat, sites) in enumerate(self.observables):
+            if isinstance(mat, str):
+                res[:, k] = self.entropy_of_cut(st, sites[0]) if mat == "entropy" else self.project_onto_bitstring(st, mat[4:])
+                continue
             g = g1[sites[0]] if len(sites) == 1 else g2[sites[0]]
             m = torch.from_numpy(mat).to(self.dev)
             val = torch.einsum("op,bop->b", m, g)
             res[:, k] = val.real
         return res
+
+    def entropy_of_cut(self, st: BatchedState, i: int) -> torch.Tensor:
+        """MPS.get_entropy (mps.py:604-639): von Neumann entropy of the singular values of A_i A_{i+1} read as (d l) x (d r), on
+        the tensors AS STORED (the reference does not move the gauge centre for this meta-observable).  [B] float64."""
+        lay, B = self.lay, self.B
+        sd = lay.svd_dim
+        self.merge(st, i)
+        keep_all = self._trunc_args("discarded_weight", 0.0, None, 1)
+        self._svd(SVD_THETA, self._buf(self.theta, lay.theta_slot), st.ext(i), st.ext(i + 2), keep_all, "right", None, self.d * lay.cap[i])
+        meta = self.svd_meta.view(B, SVD_META)
+        nsv = torch.minimum(meta[:, 3], meta[:, 4])
+        sv = self.svd_s.view(B, sd)
+        s2 = torch.where(torch.arange(sd, device=self.dev)[None, :] < nsv[:, None], sv * sv, torch.zeros_like(sv))
+        norm = s2.sum(dim=1)
+        pr = s2 / torch.where(norm > 0, norm, torch.ones_like(norm))[:, None]
+        ent = -(pr * torch.log(pr + float(np.finfo(np.float64).tiny))).sum(dim=1)
+        return torch.where(norm > 0, ent, torch.zeros_like(ent))
+
+    def project_onto_bitstring(self, st: BatchedState, bits: str) -> torch.Tensor:
+        """MPS.project_onto_bitstring (mps.py:1495-1537): probability of a computational-basis outcome by sequential projection.
+        The carry (1 x chi row vector) lives in the theta workspace; per site one ABSORB_R contraction, a slice selection, a norm
+        and a scaling -- the state itself is not touched (the reference works on a deep copy).  [B] float64."""
+        K, B, d, lay = self.K, self.B, self.d, self.lay
+        assert len(bits) == self.L, "Bitstring length must match number of sites"
+        one = Ext(self._ones_i32, 0, 1)
+        carry = self._buf(self.theta, lay.theta_slot)
+        tmp = self._buf(self.tmp, lay.nloc_max)
+        total = torch.ones(B, dtype=torch.float64, device=self.dev)
+        for site, ch in enumerate(bits):
+            bit = int(ch)
+            assert 0 <= bit < d, f"Invalid state index {bit} at site {site}"
+            er = st.ext(site + 1)
+            if site == 0:
+                K.copy_packed(B, None, st.ext(0), er, d, st.site(0), tmp, lay.slot[0])
+            else:
+                K.gemm(OP_ABSORB_R, B, d, None, one, st.ext(site), er, d, 1, 1, carry, st.site(site), tmp, 0, 1, lay.cap[site + 1])
+            sel = np.zeros((d, d), dtype=np.complex128)
+            sel[0, bit] = 1.0                                            # slice 0 <- slice `bit`, the rest <- 0
+            K.apply_local_op(B, None, None, 0, one, er, d, torch.from_numpy(sel.reshape(-1)).to(self.dev), 0, tmp, lay.cap[site + 1])
+            K.norm2(B, None, one, er, d, tmp, self.norm_buf)
+            nrm = torch.sqrt(self.norm_buf)
+            total = total * nrm
+            self.scale_buf.copy_(torch.where(nrm > 0, 1.0 / torch.where(nrm > 0, nrm, torch.ones_like(nrm)), torch.zeros_like(nrm)))
+            K.scale(B, None, one, er, d, self.scale_buf, tmp, d * lay.cap[site + 1])
+            K.copy_packed(B, None, one, er, 1, tmp, carry, lay.cap[site + 1])
+        return total * total
 
     def diagnostics(self, st: BatchedState) -> torch.Tensor:
         """[B, 3]: cost = sum chi^3, max bond (includes d, mps.py:560-565), total bond (mps.py:549-602)."""

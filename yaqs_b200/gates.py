@@ -75,6 +75,23 @@ def _rot2(pa: np.ndarray, pb: np.ndarray):
     return mat
 
 
+class Entropy(BaseGate):
+    """Meta-observable: bipartite entanglement entropy across a nearest-neighbour cut (gate_library.py:1873-1900)."""
+
+    def __init__(self) -> None:
+        super().__init__(np.eye(2), name="entropy", interaction=2)
+
+
+class PVM(BaseGate):
+    """Projection-valued measurement onto a computational-basis bitstring, site 0 first (gate_library.py:1796-1870)."""
+
+    def __init__(self, bitstring: str) -> None:
+        if not isinstance(bitstring, str) or not bitstring or any(ch not in "01" for ch in bitstring):
+            raise ValueError(f"PVM bitstring must be a non-empty string of 0/1, got {bitstring!r}")
+        super().__init__(np.eye(2), name="pvm", interaction=1)
+        self.bitstring = bitstring
+
+
 class GateLibrary:
     """Namespace of gate factories; ``getattr(GateLibrary, name)`` resolves names as in the reference
     (gate_library.py:1996-2048)."""
@@ -99,6 +116,9 @@ class GateLibrary:
     cx = staticmethod(_fixed("cx", np.array([[1, 0, 0, 0], [0, 1, 0, 0], [0, 0, 0, 1], [0, 0, 1, 0]])))
     cz = staticmethod(_fixed("cz", np.diag([1, 1, 1, -1])))
     swap = staticmethod(_fixed("swap", np.array([[1, 0, 0, 0], [0, 0, 1, 0], [0, 1, 0, 0], [0, 0, 0, 1]])))
+
+    entropy = staticmethod(lambda: Entropy())
+    pvm = staticmethod(lambda bitstring: PVM(bitstring))
 
     @staticmethod
     def local(matrix) -> BaseGate:

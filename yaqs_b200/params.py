@@ -29,10 +29,15 @@ class Observable:
 
     def __init__(self, gate, sites=None, **gate_kwargs) -> None:
         if isinstance(gate, str):
-            if not hasattr(GateLibrary, gate):
-                raise NotImplementedError(f"observable {gate!r}: only GateLibrary names are supported on the B200 TJM path "
-                                          "(pvm / entropy / schmidt_spectrum are SURVEY.md 8(f) 'next' rows)")
-            resolved = getattr(GateLibrary, gate)(**gate_kwargs)
+            if gate == "schmidt_spectrum":
+                raise NotImplementedError("observable 'schmidt_spectrum' (vector-valued, order-1 object arrays in the reference) is a "
+                                          "SURVEY.md 8(f) 'next' row of the B200 TJM path")
+            if gate != "pvm" and hasattr(GateLibrary, gate):
+                resolved = getattr(GateLibrary, gate)(**gate_kwargs)
+            else:                                     # simulation_parameters.py:388-400: any other string is a PVM bitstring
+                if gate_kwargs:
+                    raise TypeError(f"Unknown observable {gate!r} does not accept observable parameters.")
+                resolved = GateLibrary.pvm(gate)
         elif isinstance(gate, BaseGate):
             if gate_kwargs:
                 raise TypeError("Observable parameters are only supported for named observables.")
@@ -42,20 +47,53 @@ class Observable:
                 raise TypeError("Observable parameters are only supported for named observables.")
             resolved = GateLibrary.local(gate)
         self.gate = copy.deepcopy(resolved)
-        assert sites is not None
-        self.sites = sites
-        self.gate.set_sites(self.sites)
+        if resolved.name != "pvm":                    # a PVM acts on the whole chain and carries no sites (:413-416)
+            assert sites is not None
+            self.sites = sites
+            self.gate.set_sites(self.sites)
 
 
 def prepare_observable_ordering(observables):
     """Stable sort by first site (:419-456): returns (sorted list, user index -> sorted row)."""
     if not observables:
         return [], ()
-    pairs = sorted(enumerate(observables), key=lambda p: ((p[1].sites[0] if isinstance(p[1].sites, list) else p[1].sites), p[0]))
+    site_obs = [p for p in enumerate(observables) if p[1].gate.name != "pvm"]
+    pvm_obs = [p for p in enumerate(observables) if p[1].gate.name == "pvm"]          # appended in their original order
+    pairs = sorted(site_obs, key=lambda p: ((p[1].sites[0] if isinstance(p[1].sites, list) else p[1].sites), p[0])) + pvm_obs
     user_to_sorted = [0] * len(observables)
     for row, (user_i, _) in enumerate(pairs):
         user_to_sorted[user_i] = row
     return [o for _, o in pairs], tuple(user_to_sorted)
+
+
+def _check_observable_mix(observables) -> None:
+    """simulation_parameters.py:583,725."""
+    assert all(o.gate.name == "pvm" for o in observables) or all(o.gate.name != "pvm" for o in observables), (
+        "We currently have not implemented mixed observable and projective-measurement simulation.")
+
+
+def engine_observables(sorted_observables, length: int):
+    """The sorted observables as the batched engine takes them: (matrix, sites) for local one-/two-site operators,
+    ("entropy", [i, i+1]) and ("pvm:<bitstring>", []) for the meta-observables (mps.py:1200-1217)."""
+    out = []
+    for o in sorted_observables:
+        name = o.gate.name
+        if name == "pvm":
+            assert len(o.gate.bitstring) == length, "Bitstring length must match number of sites"
+            out.append(("pvm:" + o.gate.bitstring, []))
+        elif name == "entropy":
+            sites = o.sites
+            assert isinstance(sites, list), "Given metric requires a list of sites"
+            assert len(sites) == 2, "Given metric requires 2 sites to act on."
+            assert max(sites) - min(sites) == 1, "Entropy and Schmidt cuts must be nearest neighbor."
+            for s in sites:
+                assert s in range(length), f"Observable acting on non-existing site: {s}"
+            out.append(("entropy", [min(sites), max(sites)]))
+        else:
+            if o.gate.interaction not in (1, 2):
+                raise ValueError("Local observable must be one-site or nearest-neighbor two-site.")
+            out.append((np.asarray(o.gate.matrix, dtype=np.complex128), ([o.sites] if isinstance(o.sites, int) else list(o.sites))))
+    return out
 
 
 class _Ordering:
@@ -146,6 +184,7 @@ class AnalogSimParams(_Ordering):
                  multi_time_observables=None, tdvp_sweeps: int = 1, tdvp_mode: str = "2site") -> None:
         _common(self, preset, num_traj, max_bond_dim, trunc_mode, svd_threshold, krylov_tol, tdvp_sweeps, tdvp_mode, random_seed)
         self.observables = [] if observables is None else list(observables)
+        _check_observable_mix(self.observables)
         n_steps = _time_grid(elapsed_time, dt)
         self.elapsed_time, self.dt = float(elapsed_time), float(dt)
         self.times = self.dt * np.arange(n_steps + 1, dtype=np.float64)
@@ -170,6 +209,7 @@ class DigitalSimParams(_Ordering):
                  tdvp_sweeps: int = 1, tdvp_mode: str = "2site") -> None:
         _common(self, preset, num_traj, max_bond_dim, trunc_mode, svd_threshold, krylov_tol, tdvp_sweeps, tdvp_mode, random_seed)
         self.observables = [] if observables is None else list(observables)
+        _check_observable_mix(self.observables)
         if gate_mode not in ("tdvp", "full-tdvp", "swaps", "mpo"):
             raise ValueError(f"gate_mode must be one of ('tdvp', 'full-tdvp', 'swaps', 'mpo'), got {gate_mode!r}.")
         self.gate_mode = gate_mode

@@ -17,7 +17,7 @@ import torch
 from .containers import Hamiltonian, Result, State
 from .engine import BatchedTJM, BatchLayout, EngineParams
 from .noise import NoiseModel
-from .params import AnalogSimParams, DigitalSimParams
+from .params import AnalogSimParams, DigitalSimParams, engine_observables
 from .rng import make_disorder_rng, numpy_tables, philox_tables
 
 
@@ -116,10 +116,7 @@ class Simulator:
             ntraj = sp.num_traj
         sorted_obs = sp.sorted_observables
         to_sorted = sp.observable_sorted_indices
-        for o in sorted_obs:
-            if o.gate.interaction not in (1, 2):
-                raise ValueError("Local observable must be one-site or nearest-neighbor two-site.")
-        obs = [(np.asarray(o.gate.matrix, dtype=np.complex128), ([o.sites] if isinstance(o.sites, int) else list(o.sites))) for o in sorted_obs]
+        obs = engine_observables(sorted_obs, length)
         ep = EngineParams(dt=sp.dt, n_steps=len(sp.times) - 1, order=2 if sp.order != 1 else 1, max_bond_dim=sp.max_bond_dim,
                           svd_threshold=sp.svd_threshold, trunc_mode=sp.trunc_mode, krylov_tol=sp.krylov_tol, tdvp_mode=sp.tdvp_mode,
                           tdvp_sweeps=sp.tdvp_sweeps, sample_timesteps=sp.sample_timesteps)
