@@ -13,7 +13,7 @@ import torch
 from .circuits import CompiledCircuit, compile_circuit
 from .engine import BatchedTJM, EngineParams
 from .params import engine_observables
-from .rng import numpy_tables, philox_tables
+from .rng import STREAM_SHOTS, numpy_tables, philox_tables
 
 
 def validate_digital_noise(noise, length: int) -> None:
@@ -28,16 +28,15 @@ def validate_digital_noise(noise, length: int) -> None:
 
 def run_digital(simulator, initial_state, operator, sp, noise, result):
     from .simulator import shard_range
-    if sp.shots is not None:
-        raise NotImplementedError("measure_shots (DigitalSimParams(shots=...)) is a SURVEY.md 8(f) 'next' row of the B200 path")
-    if not sp.observables:
-        raise ValueError("No output specified: observables must be set (get_state-only runs are outside the B200 hot path).")
+    wants_obs, wants_shots = bool(sp.observables), sp.shots is not None
+    if not wants_obs and not wants_shots:
+        raise ValueError("No output specified: set observables= and/or shots= (get_state-only runs are outside the B200 hot path).")
     compiled = operator if isinstance(operator, CompiledCircuit) else compile_circuit(operator)
     length = initial_state.length
     if noise is not None:
         validate_digital_noise(noise, length)
     noiseless = noise is None or all(pr["strength"] == 0 for pr in noise.processes)
-    ntraj = 1 if noiseless else sp.num_traj                                                   # simulator.py:1735-1745
+    ntraj, shots_of = plan_digital_shots(sp, noisy=not noiseless)
     sorted_obs = sp.sorted_observables
     to_sorted = sp.observable_sorted_indices
     obs = engine_observables(sorted_obs, length)
@@ -63,6 +62,7 @@ def run_digital(simulator, initial_state, operator, sp, noise, result):
     status_local = np.zeros(len(mine), dtype=np.int32)
     stats: dict = {}
     log_all = [] if simulator.collect_log else None
+    measurements_local: dict[int, dict[int, int]] = {}
     wave = simulator._wave_size(len(mine), length, ep, mpo, init, dev)
     K.launch_count(reset=True)
     for w0 in range(0, len(mine), max(wave, 1)):
@@ -78,6 +78,15 @@ def run_digital(simulator, initial_state, operator, sp, noise, result):
         res_local[w0: w0 + len(idx)] = r.cpu().numpy()
         diag_local[w0: w0 + len(idx)] = dg.cpu().numpy()
         status_local[w0: w0 + len(idx)] = eng.status.cpu().numpy()
+        if wants_shots:
+            per = np.array([shots_of(t) for t in idx], dtype=np.int64)
+            if per.max() > 0:                                                                    # never sample 0 shots (digital_tjm.py:746)
+                su = shot_tables(K, simulator.rng_mode, sp.random_seed, idx, int(per.max()), length, dev)
+                outs = eng.measure_shots(eng.phi, su).cpu().numpy()
+                for row, t in enumerate(idx):
+                    if per[row] > 0:
+                        vals, cnt = np.unique(outs[row, : per[row]], return_counts=True)
+                        measurements_local[t] = {int(v): int(c) for v, c in zip(vals, cnt)}
         for k, v in eng.stats.items():
             stats[k] = stats.get(k, 0) + v
         if log_all is not None:
@@ -87,4 +96,55 @@ def run_digital(simulator, initial_state, operator, sp, noise, result):
     simulator.last_log = log_all
     times = np.arange(ncol, dtype=np.float64)
     simulator._finish(result, sp, res_local, diag_local, status_local, mine, ntraj, len(obs), ncol, to_sorted, times, stats, dev)
+    if wants_shots:
+        if world > 1:
+            gathered: list = [None] * world
+            dist.all_gather_object(gathered, measurements_local)
+            measurements_local = {k: v for part in gathered for k, v in part.items()}
+        # simulator.py:1752-1756,1790-1795: one entry per trajectory when noisy, a single entry otherwise
+        result.measurements = [measurements_local.get(t) for t in range(ntraj if not noiseless else 1)]
+        aggregate_counts(result)
     return result
+
+
+def plan_digital_shots(sp, *, noisy: bool):
+    """_plan_digital_shots + _per_call_shots (simulator.py:1001-1050, digital_tjm.py:752-768): (number of trajectories,
+    trajectory index -> shots to sample from its final state)."""
+    wants_obs, wants_shots = bool(sp.observables), sp.shots is not None
+    if wants_shots and not wants_obs:
+        if noisy:
+            return int(sp.shots), (lambda t: 1)                    # one stochastic state per shot (num_traj is ignored)
+        return 1, (lambda t: int(sp.shots))                        # the whole budget from the one noiseless state
+    ntraj = sp.num_traj if noisy else 1
+    if not wants_shots:
+        return ntraj, (lambda t: 0)
+    if noisy:
+        base, rem = divmod(int(sp.shots), int(ntraj))              # budget spread over the observable ensemble
+        return ntraj, (lambda t: base + (1 if t < rem else 0))
+    return ntraj, (lambda t: int(sp.shots))
+
+
+def shot_tables(kernels, rng_mode: str, seed, traj_indices, nshots: int, length: int, device) -> torch.Tensor:
+    """[B, nshots, L] uniforms for the projective sampling.  The reference draws them from an unseeded Generator
+    (mps.py:1312-1313); here they come from the per-trajectory "SHOT" stream, so shots are reproducible under random_seed."""
+    nb, n = len(traj_indices), nshots * length
+    if rng_mode == "numpy":
+        tab = np.empty((nb, n))
+        for row, t in enumerate(traj_indices):
+            g = np.random.default_rng() if seed is None else np.random.default_rng(np.random.SeedSequence([seed, int(t), STREAM_SHOTS]))
+            tab[row] = g.random(n)
+        return torch.from_numpy(tab).to(device).view(nb, nshots, length)
+    base = int(seed) if seed is not None else int(np.random.SeedSequence().entropy % (2 ** 64))
+    nblocks = (n + 1) // 2
+    flat = torch.empty((nb, 2 * nblocks), dtype=torch.float64, device=device)
+    kernels.philox_uniform(base, torch.as_tensor(np.asarray(traj_indices, dtype=np.int64), device=device), STREAM_SHOTS, nblocks, 0, flat)
+    return flat[:, :n].contiguous().view(nb, nshots, length)
+
+
+def aggregate_counts(result) -> None:
+    """result.py:141-152."""
+    counts: dict[int, int] = {}
+    for m in filter(None, result.measurements):
+        for key, value in m.items():
+            counts[key] = counts.get(key, 0) + value
+    result.counts = dict(sorted(counts.items()))

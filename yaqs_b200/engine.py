@@ -811,6 +811,45 @@ class BatchedTJM:
             K.copy_packed(B, None, one, er, 1, tmp, carry, lay.cap[site + 1])
         return total * total
 
+    def measure_shots(self, st: BatchedState, u: torch.Tensor) -> torch.Tensor:
+        """MPS.measure_single_shot (mps.py:1282-1340) in the Z basis, u.shape[1] shots of every trajectory: sequential projective
+        sampling from site 0 to L-1 with the centre at 0.  Per site the outcome probabilities are the diagonal of the local
+        reduced density matrix of carry x A_site (``k_local_rdm``), the outcome follows numpy's ``Generator.choice``
+        (``searchsorted(cdf, u, 'right')`` on the renormalised CDF), the selected slice, scaled by 1/sqrt(p), is carried into the
+        next site with one ABSORB_R contraction.  u: [B, nshots, L] uniforms.  Returns [B, nshots] int64, bit i = outcome of site
+        i (``sum(c << i)``, mps.py:1340).  The state is not touched (the reference samples a deep copy)."""
+        K, B, d, lay, n = self.K, self.B, self.d, self.lay, self.L
+        assert n <= 62, "outcomes are packed into int64 bit fields"
+        nshots = int(u.shape[1])
+        out = torch.zeros((B, nshots), dtype=torch.int64, device=self.dev)
+        one = Ext(self._ones_i32, 0, 1)
+        carry = self._buf(self.theta, lay.theta_slot)
+        tmp = self._buf(self.tmp, lay.nloc_max)
+        rows = torch.arange(B, device=self.dev)
+        sel = torch.zeros((B, d * d), dtype=torch.complex128, device=self.dev)
+        for shot in range(nshots):
+            for site in range(n):
+                er = st.ext(site + 1)
+                if site == 0:
+                    K.copy_packed(B, None, st.ext(0), er, d, st.site(0), tmp, lay.slot[0])
+                else:
+                    K.gemm(OP_ABSORB_R, B, d, None, one, st.ext(site), er, d, 1, 1, carry, st.site(site), tmp, 0, 1, lay.cap[site + 1])
+                K.local_rdm(B, None, one, er, d, tmp, tmp, self.rdm1)
+                pr = self.rdm1.view(B, d, d).diagonal(dim1=1, dim2=2).real.clone()
+                pr = pr / pr.sum(dim=1, keepdim=True)
+                cdf = torch.cumsum(pr, dim=1)
+                cdf = cdf / cdf[:, -1:]
+                idx = torch.searchsorted(cdf, u[:, shot, site:site + 1].contiguous(), right=True).squeeze(1).clamp_(max=d - 1)
+                out[:, shot] |= idx << site
+                if site != n - 1:
+                    sel.zero_()
+                    sel[rows, idx] = 1.0                                  # op[0, idx] = 1: slice 0 <- slice idx, the rest <- 0
+                    K.apply_local_op(B, None, None, 0, one, er, d, sel.view(-1), d * d, tmp, lay.cap[site + 1])
+                    self.scale_buf.copy_(torch.rsqrt(pr[rows, idx]))
+                    K.scale(B, None, one, er, d, self.scale_buf, tmp, d * lay.cap[site + 1])
+                    K.copy_packed(B, None, one, er, 1, tmp, carry, lay.cap[site + 1])
+        return out
+
     def diagnostics(self, st: BatchedState) -> torch.Tensor:
         """[B, 3]: cost = sum chi^3, max bond (includes d, mps.py:560-565), total bond (mps.py:549-602)."""
         inner = st.bond[:, 1:self.L].to(torch.float64)

@@ -18,6 +18,7 @@ import torch
 STREAM_TRAJECTORY = 0x5452414A  # "TRAJ"
 STREAM_SAMPLE = 0x53414D50      # "SAMP"
 STREAM_DISORDER = 0x4449534F    # "DISO"
+STREAM_SHOTS = 0x53484F54       # "SHOT" (ours: the reference samples shots from an unseeded Generator)
 
 
 def make_disorder_rng(seed: int | None) -> np.random.Generator:
