@@ -73,6 +73,16 @@ CASES = {
     "ising6_pvm_order2": dict(model="ising", L=6, J=1.0, g=0.8, init="x+", chi=8, thr=1e-8, order=2, dt=0.1, steps=4,
                               sample_timesteps=True, ntraj=4, seed=33, obs="pvm0+pvm01+pvm110",
                               noise=[("lowering", 0.3), ("pauli_z", 0.2)]),
+    # scheduled (deterministic) jumps, order 1 only: at t = 0 before the first sample, a one-site jump that
+    # replaces the jump test of its step, and an adjacent two-site jump that goes through merge + truncated split
+    "ising6_scheduled_order1": dict(model="ising", L=6, J=1.0, g=0.7, init="zeros", chi=8, thr=1e-8, order=1, dt=0.1, steps=6,
+                                    sample_timesteps=True, ntraj=4, seed=41, obs="z+zz",
+                                    noise=[("lowering", 0.4), ("pauli_z", 0.6)],
+                                    scheduled=[(0.0, (1,), "pauli_x"), (0.2, (3,), "raising"), (0.4, (4, 3), "crosstalk_xy"), (0.4, (0,), "pauli_y")]),
+    # scheduled jumps without any stochastic process (deterministic evolution, one trajectory)
+    "ising6_scheduled_only_order1": dict(model="ising", L=6, J=1.0, g=0.7, init="x+", chi=8, thr=1e-9, order=1, dt=0.1, steps=5,
+                                         sample_timesteps=True, ntraj=1, seed=42, obs="x+z", noise=[],
+                                         scheduled=[(0.2, (2,), "pauli_z"), (0.3, (1, 2), "crosstalk_zx")]),
     # final-column-only bookkeeping with order 1
     "ising6_final_only_order1": dict(model="ising", L=6, J=1.0, g=0.5, init="zeros", chi=8, thr=1e-6, order=1, dt=0.1, steps=5,
                                      sample_timesteps=False, ntraj=6, seed=21, obs="z",
@@ -146,6 +156,16 @@ def oracle_inputs(cfg: dict):
     return init, mpo, noise, p, obs
 
 
+def scheduled_jumps_for(cfg: dict) -> list[dict]:
+    """cfg["scheduled"] = [(time, sites, name), ...] -> normalised {time, sites (ascending), matrix} dicts
+    (NoiseModel._normalize_scheduled_jump, noise_model.py:298-339)."""
+    out = []
+    for time, sites, name in cfg.get("scheduled", []):
+        proc = O.make_process(name, list(sites), 1.0)
+        out.append({"time": float(time), "sites": proc["sites"], "name": name, "matrix": proc["matrix"]})
+    return out
+
+
 def run_oracle_case(cfg: dict, trajectories=None):
     """Run the oracle with the reference's seeded numpy streams; returns a list of TrajectoryTrace."""
     init, mpo, noise, p, obs = oracle_inputs(cfg)
@@ -156,7 +176,7 @@ def run_oracle_case(cfg: dict, trajectories=None):
             tr_out = O.analog_tjm_2(init, mpo, noise, p, obs, rng,
                                     lambda j, _t=tr: O.UniformStream(O.sample_stream(cfg["seed"], _t, j)))
         else:
-            tr_out = O.analog_tjm_1(init, mpo, noise, p, obs, rng)
+            tr_out = O.analog_tjm_1(init, mpo, noise, p, obs, rng, scheduled_jumps_for(cfg))
         out.append(tr_out)
     return out
 

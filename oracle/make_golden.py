@@ -77,7 +77,8 @@ def run_case(name: str, cfg: dict) -> dict:
             obs += [Observable(pvm_bitstring(tok, L))]          # unknown names resolve to GateLibrary.pvm(bitstring)
     procs = [{"name": n, "sites": [i], "strength": g} for i in range(L) for (n, g) in cfg["noise"]]
     procs += [{"name": n, "sites": list(s), "strength": g} for (n, s, g) in cfg.get("noise2", [])]
-    noise = NoiseModel(procs) if procs else None
+    sched = [{"time": t, "sites": list(st), "name": n} for (t, st, n) in cfg.get("scheduled", [])]
+    noise = NoiseModel(procs, scheduled_jumps=sched or None) if (procs or sched) else None
     sim = AnalogSimParams(observables=obs, elapsed_time=cfg["dt"] * cfg["steps"], dt=cfg["dt"], num_traj=cfg["ntraj"],
                           max_bond_dim=cfg["chi"], svd_threshold=cfg["thr"], order=cfg["order"],
                           sample_timesteps=cfg["sample_timesteps"], random_seed=cfg["seed"],

@@ -9,7 +9,7 @@ from tests.helpers import check_against_golden, engine_for_case
 FAST = ["ising5_ref_golden", "ising10_c1_order1", "ising6_twosite_order1", "ising6_twosite_order2", "ising6_noiseless_order1",
         "ising6_noiseless_order2", "heis6_1site_order1", "ising6_1site_noiseless", "ising6_final_only_order1", "ising8_capped_order2",
         "ising8_strong_order2", "heis8_c2_order2", "ising10_c1_order2", "ising12_chi40_gram", "ising6_entropy_order2", "heis6_entropy_order1",
-        "ising6_pvm_order2"]
+        "ising6_pvm_order2", "ising6_scheduled_order1", "ising6_scheduled_only_order1"]
 
 
 @pytest.mark.parametrize("name", FAST)

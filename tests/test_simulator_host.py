@@ -86,6 +86,39 @@ def test_entropy_and_pvm_observables_through_simulator(golden_dir):
         Observable("schmidt_spectrum", [0, 1])
 
 
+def test_scheduled_jumps_through_simulator(golden_dir):
+    """NoiseModel(processes, scheduled_jumps=[...]) with AnalogSimParams(order=1) through the public API against the fixture of
+    the unmodified reference; the reference's validation errors (order 2, off-grid time, non-adjacent sites, digital runs)."""
+    from oracle.golden_cases import CASES
+    from yaqs_b200 import DigitalSimParams
+    from yaqs_b200.circuits import create_ising_circuit
+    cfg = CASES["ising6_scheduled_order1"]
+    L = cfg["L"]
+    obs = [Observable(Z(), s) for s in range(L)] + [Observable(ZZ(), [s, s + 1]) for s in range(L - 1)]
+    procs = [{"name": n, "sites": [i], "strength": g} for i in range(L) for (n, g) in cfg["noise"]]
+    sched = [{"time": t, "sites": list(st), "name": n} for (t, st, n) in cfg["scheduled"]]
+    noise = NoiseModel(procs, scheduled_jumps=sched)
+    kw = dict(elapsed_time=cfg["dt"] * cfg["steps"], dt=cfg["dt"], num_traj=cfg["ntraj"], max_bond_dim=cfg["chi"], svd_threshold=cfg["thr"],
+              krylov_tol=1e-4, sample_timesteps=True, random_seed=cfg["seed"])
+    sp = AnalogSimParams(observables=obs, order=1, **kw)
+    res = Simulator(show_progress=False, kernels=NumpyKernels()).run(State(L, initial=cfg["init"]), Hamiltonian.ising(L, cfg["J"], cfg["g"]), sp, noise)
+    g = np.load(os.path.join(golden_dir, "ising6_scheduled_order1.npz"))
+    idx = sp.observable_sorted_indices
+    for user_i in range(len(obs)):
+        assert np.max(np.abs(np.asarray(res.trajectories[user_i]) - g["results"][:, idx[user_i], :])) < 1e-10
+    sim, st, ham = Simulator(show_progress=False, kernels=NumpyKernels()), State(L, initial="zeros"), Hamiltonian.ising(L, 1.0, 0.7)
+    with pytest.raises(ValueError, match="only supported for AnalogSimParams\\(order=1\\)"):
+        sim.run(st, ham, AnalogSimParams(observables=obs, order=2, **kw), noise)
+    with pytest.raises(ValueError, match="not on the simulation time grid"):
+        sim.run(st, ham, sp, NoiseModel(procs, scheduled_jumps=[{"time": 0.25, "sites": [0], "name": "pauli_x"}]))
+    with pytest.raises(ValueError, match="non-adjacent"):
+        NoiseModel(procs, scheduled_jumps=[{"time": 0.2, "sites": [0, 2], "name": "crosstalk_xx"}])
+    with pytest.raises(ValueError, match="annihilates the current state"):
+        sim.run(st, ham, sp, NoiseModel(procs, scheduled_jumps=[{"time": 0.0, "sites": [0], "name": "lowering"}]))
+    with pytest.raises(ValueError, match="scheduled_jumps are only supported for single-State analog"):
+        sim.run(st, create_ising_circuit(L, 1.0, 0.7, 0.2, 1), DigitalSimParams(observables=[Observable(Z(), 0)], num_traj=2), noise)
+
+
 def test_mpo_factories_match_dense():
     z, x, y, i2 = np.diag([1.0, -1.0]), np.array([[0, 1.0], [1, 0]]), np.array([[0, -1j], [1j, 0]]), np.eye(2)
 

@@ -18,6 +18,9 @@ from .rng import STREAM_SHOTS, numpy_tables, philox_tables
 
 def validate_digital_noise(noise, length: int) -> None:
     """noise_model.py:668-757, digital branch: two-site processes must act on adjacent, ascending sites (:724-730)."""
+    if getattr(noise, "scheduled_jumps", None):
+        raise ValueError("scheduled_jumps are only supported for single-State analog MPS TJM; they are not supported for MCWF, "
+                         "Lindblad, digital, or list[State] ensemble runs.")
     for pr in noise.processes:
         for s in pr["sites"]:
             if s >= length:

@@ -158,8 +158,9 @@ class BatchedTJM:
 
     def __init__(self, kernels, length: int, nbatch: int, mpo: Sequence[np.ndarray], params: EngineParams,
                  noise: Sequence[dict] | None, observables: Sequence[tuple[np.ndarray, Sequence[int]]],
-                 init_tensors, svd_block_rows: int | None = None, gram_min_k: int = 33):
+                 init_tensors, svd_block_rows: int | None = None, gram_min_k: int = 33, scheduled_jumps: Sequence[dict] | None = None):
         self.K = kernels
+        self.scheduled_jumps = list(scheduled_jumps) if scheduled_jumps else []       # normalised {time, sites, matrix} (order 1 only)
         self.dev = kernels.device
         self.p = params
         self.L, self.B, self.d = length, nbatch, 2
@@ -950,6 +951,43 @@ class BatchedTJM:
         self._apply_jumps(st, jmask, choice)
         return jmask
 
+    def has_scheduled_jump(self, time: float) -> bool:
+        """core/methods/scheduled_jumps.py:29-52."""
+        return any(np.isclose(j["time"], time, atol=self.p.dt * 1e-3, rtol=0.0) for j in self.scheduled_jumps)
+
+    def apply_scheduled_jumps(self, st: BatchedState, time: float) -> None:
+        """apply_scheduled_jumps (core/methods/scheduled_jumps.py:55-119) for the whole batch: the deterministic jump operators
+        of this grid time act on every trajectory (one-site in place, adjacent two-site on the merged tensor followed by the
+        run's truncated split), then normalize("B"): a right-to-left sweep of truncation-free shifts and division by the norm,
+        which is checked first (a jump that annihilates the state raises, :108-115)."""
+        K, B, lay, d, n, p = self.K, self.B, self.lay, self.d, self.L, self.p
+        user = self._trunc_args(p.trunc_mode, p.svd_threshold, p.max_bond_dim, 1)
+        keep_all = self._trunc_args("discarded_weight", 0.0, None, 1)
+        for jump in self.scheduled_jumps:
+            if not np.isclose(jump["time"], time, atol=p.dt * 1e-3, rtol=0.0):
+                continue
+            sites = list(jump["sites"])
+            op = torch.from_numpy(np.ascontiguousarray(jump["matrix"], dtype=np.complex128).reshape(-1)).to(self.dev)
+            if len(sites) == 1:
+                s_ = sites[0]
+                K.apply_local_op(B, None, None, 0, st.ext(s_), st.ext(s_ + 1), d, op, 0, st.site(s_), lay.cap[s_] * lay.cap[s_ + 1])
+            else:
+                a = min(sites)
+                if abs(sites[0] - sites[1]) != 1:
+                    raise ValueError(f"Scheduled jump acts on non-adjacent sites {sites}. Only nearest-neighbor jumps are supported.")
+                th = self.merge(st, a)
+                K.apply_local_op(B, None, None, 0, st.ext(a), st.ext(a + 2), d * d, op, 0, th, lay.cap[a] * lay.cap[a + 2])
+                self.split_theta(st, a, "right", user, None, fast=True)
+        for i in reversed(range(1, n)):
+            self.shift_left(st, i, keep_all, None, fast=True)
+        K.norm2(B, None, st.ext(0), st.ext(1), d, st.site(0), self.norm_buf)
+        bad = ~(torch.isfinite(self.norm_buf) & (self.norm_buf > 0))
+        if K.sync_int(bad.to(torch.int32).sum()) > 0:
+            val = float(self.norm_buf[bad][0].item())
+            raise ValueError(f"Scheduled jump produced a zero or non-finite squared norm (squared_norm={val}). "
+                             "The jump operator annihilates the current state.")
+        self.normalize_site(st, 0)
+
     def _apply_jumps(self, st: BatchedState, jmask: torch.Tensor, choice: torch.Tensor) -> None:
         """Left-canonicalise the jumping trajectories (the reference's PDF sweep leaves the centre at L-1,
         stochastic_process.py:139-141), apply the selected operators (:251-288) and renormalise with the right-to-left
@@ -1068,13 +1106,19 @@ class BatchedTJM:
                     sample(j)
             return results, diag
         # first-order scheme (:369-462)
+        if self.has_scheduled_jump(0.0):                    # :428-431: before the initial sample
+            self.apply_scheduled_jumps(phi, 0.0)
         if p.sample_timesteps:
             record(phi, 0)
         for j in range(1, nt):
             self.tdvp(phi)
-            if self.noise is not None:
-                self.apply_dissipation(phi, p.dt)
-                traj_jump_test(phi, f"step{j}")
+            if self.noise is not None or self.scheduled_jumps:
+                if self.noise is not None:
+                    self.apply_dissipation(phi, p.dt)
+                if self.has_scheduled_jump(j * p.dt):       # replaces the jump test of this step (no uniform is drawn)
+                    self.apply_scheduled_jumps(phi, j * p.dt)
+                else:
+                    traj_jump_test(phi, f"step{j}")
             if p.sample_timesteps or j == nt - 1:
                 record(phi, j if p.sample_timesteps else 0)
         if not p.sample_timesteps and nt <= 1:

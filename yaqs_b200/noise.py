@@ -149,7 +149,7 @@ class NoiseModel:
         if scheduled_jumps is not None:
             if not isinstance(scheduled_jumps, (list, tuple)):
                 raise TypeError("scheduled_jumps must be a list or tuple of dictionaries.")
-            self.scheduled_jumps = [dict(j) for j in scheduled_jumps]
+            self.scheduled_jumps = [self._normalize_scheduled_jump(j) for j in scheduled_jumps]
         if processes is None:
             return
         if not isinstance(processes, (list, tuple)):
@@ -159,6 +159,47 @@ class NoiseModel:
     @staticmethod
     def get_operator(name: str) -> np.ndarray:
         return get_operator(name)
+
+    @staticmethod
+    def _normalize_scheduled_jump(jump: object) -> dict[str, Any]:
+        """noise_model.py:298-339: {time, sites, name[, matrix]} -> sites ascending, 'matrix' resolved."""
+        if not isinstance(jump, dict):
+            raise TypeError("Each scheduled jump must be a dictionary.")
+        for key in ("time", "sites", "name"):
+            if key not in jump:
+                raise ValueError(f"Each scheduled jump must have a '{key}' key.")
+        out = dict(jump)
+        if "factors" in out:
+            raise ValueError("Scheduled jumps do not accept 'factors'; use 'matrix' for custom operators.")
+        if not isinstance(out["name"], str):
+            raise TypeError("Scheduled jump 'name' must be a string.")
+        if not out["name"]:
+            raise ValueError("Scheduled jump 'name' must be a nonempty string.")
+        out["time"] = _real(out["time"], "Scheduled jump time", nonneg=False)
+        sites = _sites(out["sites"], "Scheduled jump")
+        user_matrix = "matrix" in out
+        swapped = False
+        if len(sites) == 2:
+            ordered = sorted(sites)
+            swapped = ordered != sites
+            if abs(ordered[1] - ordered[0]) != 1:
+                raise ValueError(f"Scheduled jump acts on non-adjacent sites {sites}. Only nearest-neighbor scheduled jumps are supported.")
+            if swapped and user_matrix:
+                raise ValueError(f"Custom full scheduled-jump matrices require ascending site order; got sites {sites}.")
+            sites = ordered
+        out["sites"] = sites
+        if user_matrix:
+            out["matrix"] = _square(out["matrix"], "Scheduled jump matrix")
+        else:
+            cross = _CROSSTALK.fullmatch(out["name"])
+            if cross:
+                a, b = cross.group(2)
+                if swapped:
+                    a, b = b, a
+                out["matrix"] = np.kron(PAULI[a], PAULI[b]).copy()
+            else:
+                out["matrix"] = get_operator(out["name"])
+        return out
 
     @staticmethod
     def _normalize(original: object) -> dict[str, Any]:

@@ -27,10 +27,26 @@ def shard_range(n: int, rank: int, world: int) -> range:
     return range(min(n, rank * per), min(n, (rank + 1) * per))
 
 
-def validate_noise_model_for_run(noise: NoiseModel, length: int) -> None:
-    """core/data_structures/noise_model.py:668-757 (the MPS-analog checks)."""
+def validate_noise_model_for_run(noise: NoiseModel, length: int, sim_params=None) -> None:
+    """core/data_structures/noise_model.py:668-780 (the MPS-analog checks, scheduled jumps included)."""
     if noise.scheduled_jumps:
-        raise NotImplementedError("scheduled_jumps are a SURVEY.md 8(f) 'next' row of the B200 path")
+        if not isinstance(sim_params, AnalogSimParams):
+            raise ValueError("scheduled_jumps are only supported for single-State analog MPS TJM; they are not supported for MCWF, "
+                             "Lindblad, digital, or list[State] ensemble runs.")
+        if sim_params.order != 1:
+            raise ValueError(f"scheduled_jumps are only supported for AnalogSimParams(order=1); got order={sim_params.order}. Order-2 TJM "
+                             "applies deterministic jumps inconsistently on the sampling versus trajectory MPS.")
+        times = np.asarray(sim_params.times, dtype=float)
+        atol = sim_params.dt * 1e-3
+        for jump in noise.scheduled_jumps:
+            want = 2 ** len(jump["sites"])
+            if np.asarray(jump["matrix"]).shape != (want, want):
+                raise ValueError(f"Scheduled jump '{jump['name']}': matrix must be {want}x{want} for qubit chains.")
+            for s_ in jump["sites"]:
+                if s_ >= length:
+                    raise ValueError(f"Scheduled jump '{jump['name']}' acts on site {s_} but the chain has {length} sites.")
+            if not np.any(np.isclose(times, float(jump["time"]), atol=atol, rtol=0.0)):
+                raise ValueError(f"Scheduled jump time {float(jump['time'])} is not on the simulation time grid (atol={atol}, rtol=0).")
     for pr in noise.processes:
         for s in pr["sites"]:
             if s >= length:
@@ -106,7 +122,7 @@ class Simulator:
         if ham.length != length:
             raise ValueError("State and Hamiltonian must have the same number of sites.")
         if noise is not None:
-            validate_noise_model_for_run(noise, length)
+            validate_noise_model_for_run(noise, length, sp)
         noiseless = noise is None or all(pr["strength"] == 0 for pr in noise.processes)
         if noiseless:
             ntraj = 1                                                                     # :1549-1555
@@ -121,6 +137,7 @@ class Simulator:
                           svd_threshold=sp.svd_threshold, trunc_mode=sp.trunc_mode, krylov_tol=sp.krylov_tol, tdvp_mode=sp.tdvp_mode,
                           tdvp_sweeps=sp.tdvp_sweeps, sample_timesteps=sp.sample_timesteps)
         procs = noise.processes if noise is not None else None
+        sched = noise.scheduled_jumps if noise is not None else None
         mpo = ham.mpo.tensors
         init = state.mps.tensors
         ncol = ep.n_times if ep.sample_timesteps else 1
@@ -148,7 +165,7 @@ class Simulator:
 
         def run_job(job):
             w0, idx = job
-            eng = BatchedTJM(K, length, len(idx), mpo, ep, procs, obs, init)
+            eng = BatchedTJM(K, length, len(idx), mpo, ep, procs, obs, init, scheduled_jumps=sched)
             if self.rng_mode == "numpy":
                 tu, su = numpy_tables(sp.random_seed, idx, ep.n_times, ep.order)
                 tu = torch.from_numpy(tu).to(dev)
