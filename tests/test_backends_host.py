@@ -1,0 +1,97 @@
+"""The reference's per-trajectory backend boundary: analog_tjm_1 / analog_tjm_2 / digital_tjm keep their argument
+tuple and return shapes as batches of one trajectory; run_batch is the same call for many trajectory indices.  Checked against the
+fixtures of the unmodified reference with the numpy kernel twin (the -m gpu twin of this file runs the CUDA library)."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle.golden_cases import CASES, DIGITAL_CASES
+from yaqs_b200 import AnalogSimParams, DigitalSimParams, Hamiltonian, MPS, NoiseModel, Observable, State, Z, ZZ
+from yaqs_b200 import backends
+from yaqs_b200.circuits import create_ising_circuit
+from yaqs_b200.rng import STREAM_TRAJECTORY
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _analog_inputs(name):
+    cfg = CASES[name]
+    L = cfg["L"]
+    obs = []
+    for tok in cfg["obs"].split("+"):
+        obs += [Observable(Z(), s) for s in range(L)] if tok == "z" else [Observable(ZZ(), [s, s + 1]) for s in range(L - 1)]
+    noise = NoiseModel([{"name": n, "sites": [i], "strength": g} for i in range(L) for (n, g) in cfg["noise"]])
+    sp = AnalogSimParams(observables=obs, elapsed_time=cfg["dt"] * cfg["steps"], dt=cfg["dt"], num_traj=cfg["ntraj"], max_bond_dim=cfg["chi"],
+                         svd_threshold=cfg["thr"], krylov_tol=1e-4, order=cfg["order"], sample_timesteps=cfg["sample_timesteps"],
+                         random_seed=cfg["seed"])
+    ham = Hamiltonian.ising(L, cfg["J"], cfg["g"]) if cfg["model"] == "ising" else Hamiltonian.heisenberg(L, cfg["J"], cfg["J"], cfg["J"])
+    return cfg, State(L, initial=cfg["init"]), noise, sp, ham, np.load(os.path.join(GOLDEN, name + ".npz"))
+
+
+def _check_backends(kernels):
+    backends.set_default_kernels(kernels)
+    try:
+        # order 2: one trajectory through the reference's signature, with the standalone seed and with an external Generator
+        cfg, state, noise, sp, ham, g = _analog_inputs("ising10_c1_order2")
+        for t in (0, 3):
+            res, diag, fin = backends.analog_tjm_2((t, state.mps, noise, sp, ham.mpo))
+            assert res.shape == g["results"][t].shape and diag.shape == (3, res.shape[1]) and fin is None
+            assert np.max(np.abs(res - g["results"][t])) < 1e-10 and np.array_equal(diag, g["diagnostics"][t])
+        rng = np.random.default_rng(np.random.SeedSequence([cfg["seed"], 3, STREAM_TRAJECTORY]))
+        res_b, _, _ = backends.analog_tjm_2((3, state, noise, sp, ham), rng=rng, copy_initial_state=False)
+        assert np.array_equal(res_b, res)
+        with pytest.raises(ValueError, match="order"):
+            backends.analog_tjm_1((0, state, noise, sp, ham))
+        with pytest.raises(NotImplementedError):
+            backends.analog_tjm_2((0, state, noise, sp, ham), continue_trajectory=True)
+        # the batched entry: several trajectory indices in lock step, rows in sorted-observable order
+        res_all, diag_all, status, final = backends.run_batch([5, 1, 2], state, noise, sp, ham)
+        assert not status.any() and final is None
+        for row, t in enumerate([5, 1, 2]):
+            assert np.max(np.abs(res_all[row] - g["results"][t])) < 1e-10 and np.array_equal(diag_all[row], g["diagnostics"][t])
+        # order 1, Heisenberg, Z and ZZ
+        cfg, state, noise, sp, ham, g = _analog_inputs("ising10_c1_order1")
+        res, diag, _ = backends.analog_tjm_1((2, state, noise, sp, ham))
+        assert np.max(np.abs(res - g["results"][2])) < 1e-10 and np.array_equal(diag, g["diagnostics"][2])
+        # noise-free with get_state: the final MPS comes back normalised
+        sp2 = AnalogSimParams(observables=[Observable(Z(), 0)], elapsed_time=0.2, dt=0.1, max_bond_dim=8, order=1, get_state=True)
+        _, _, fin = backends.analog_tjm_1((0, State(6, initial="x+"), None, sp2, Hamiltonian.ising(6, 1.0, 0.5)))
+        assert isinstance(fin, MPS) and fin.length == 6
+        # digital
+        cfg = DIGITAL_CASES["dig_ising6_nn_noisy"]
+        L = cfg["L"]
+        circ = create_ising_circuit(L, cfg["J"], cfg["g"], cfg["dt"], cfg["timesteps"], sample_every_step=True)
+        spd = DigitalSimParams(observables=[Observable(Z(), s) for s in range(L)], num_traj=cfg["ntraj"], max_bond_dim=cfg["chi"],
+                               svd_threshold=cfg["thr"], sample_layers=True, random_seed=cfg["seed"])
+        noise = NoiseModel([{"name": n, "sites": [i], "strength": s_} for i in range(L) for (n, s_) in cfg["noise"]])
+        gd = np.load(os.path.join(GOLDEN, "dig_ising6_nn_noisy.npz"))
+        res, diag, counts, fin = backends.digital_tjm((4, State(L, initial="zeros"), noise, spd, circ))
+        assert counts is None and fin is None
+        assert np.max(np.abs(res - gd["results"][4])) < 1e-10 and np.array_equal(diag, gd["diagnostics"][4])
+        spd2 = DigitalSimParams(shots=7, num_traj=3, max_bond_dim=cfg["chi"], random_seed=1)
+        res, diag, counts, _ = backends.digital_tjm((0, State(L, initial="zeros"), None, spd2, circ))
+        assert res is None and diag is None and sum(counts.values()) == 7
+    finally:
+        backends.set_default_kernels(None)
+
+
+def test_backend_boundary_host_twin():
+    from oracle.np_kernels import NumpyKernels
+    _check_backends(NumpyKernels())
+
+
+@pytest.mark.gpu
+def test_backend_boundary_gpu():
+    from yaqs_b200.kernels import CudaKernels
+    _check_backends(CudaKernels("cuda:0"))
+
+
+def test_backends_fail_loudly_without_cuda():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("needs a machine without CUDA")
+    backends.set_default_kernels(None)
+    cfg, state, noise, sp, ham, _ = _analog_inputs("ising10_c1_order2")
+    with pytest.raises(Exception):
+        backends.analog_tjm_2((0, state, noise, sp, ham))
