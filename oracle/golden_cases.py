@@ -204,6 +204,18 @@ DIGITAL_CASES = {
 }
 
 
+# BASELINE config 4 at its own size: 49 qubits, 13 Trotter steps (circuit depth 40), Pauli noise on every nearest-neighbour
+# pair ("2-qubit depolarizing"-style channel) plus single-qubit dephasing, bond cap 16.  Minutes for the reference; the CPU
+# suite checks it only with YB_SLOW_TESTS=1, the -m gpu suite always runs it.
+LARGE_DIGITAL_CASES = {
+    "dig_ising49_c4": dict(L=49, J=1.0, g=0.8, dt=0.15, timesteps=13, periodic=False, chi=16, thr=1e-8, ntraj=2, seed=2048,
+                           init="zeros", obs="z", sample=False, gate_mode="mpo",
+                           noise=[("pauli_z", 0.01)],
+                           noise2=[("crosstalk_xx", 0.01), ("crosstalk_yy", 0.01), ("crosstalk_zz", 0.01)]),
+}
+ALL_DIGITAL_CASES = {**DIGITAL_CASES, **LARGE_DIGITAL_CASES}
+
+
 def digital_inputs(cfg: dict):
     """(initial OracleMPS, layers, noise | None, OracleParams, sorted observables)."""
     L = cfg["L"]

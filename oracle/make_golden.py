@@ -23,7 +23,7 @@ from oracle.ref_shim import load_reference  # noqa: E402
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
 
-from oracle.golden_cases import ALL_CASES, CASES, DIGITAL_CASES, initial_state, pvm_bitstring  # noqa: E402
+from oracle.golden_cases import ALL_CASES, ALL_DIGITAL_CASES, CASES, DIGITAL_CASES, initial_state, pvm_bitstring  # noqa: E402
 
 
 class _RecordingRng:
@@ -238,7 +238,7 @@ def main(argv: list[str]) -> int:
     os.makedirs(GOLDEN_DIR, exist_ok=True)
     names = argv or (list(CASES) + list(DIGITAL_CASES))
     for name in names:
-        data = run_digital_case(name, DIGITAL_CASES[name]) if name in DIGITAL_CASES else run_case(name, ALL_CASES[name])
+        data = run_digital_case(name, ALL_DIGITAL_CASES[name]) if name in ALL_DIGITAL_CASES else run_case(name, ALL_CASES[name])
         path = os.path.join(GOLDEN_DIR, f"{name}.npz")
         np.savez_compressed(path, **data)
         njump = int(data["jumped"].sum())

@@ -47,9 +47,9 @@ def check_against_golden(name, golden_dir, results, diag, log, traj, obs_tol=1e-
 
 def digital_engine_for_case(name, kernels, trajectories=None, **kw):
     """BatchedTJM + compiled layers + uniform table for a digital fixture (oracle/golden_cases.DIGITAL_CASES)."""
-    from oracle.golden_cases import DIGITAL_CASES, digital_inputs
+    from oracle.golden_cases import ALL_DIGITAL_CASES, digital_inputs
     from yaqs_b200.circuits import compile_circuit, create_ising_circuit
-    cfg = DIGITAL_CASES[name]
+    cfg = ALL_DIGITAL_CASES[name]
     init, _layers, noise, p, obs = digital_inputs(cfg)
     L = cfg["L"]
     compiled = compile_circuit(create_ising_circuit(L, cfg["J"], cfg["g"], cfg["dt"], cfg["timesteps"], periodic=cfg["periodic"],

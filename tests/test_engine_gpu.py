@@ -62,8 +62,21 @@ def test_cuda_engine_gram_svd_route(golden_dir, name):
     check_against_golden(name, golden_dir, results, diag, log, traj)
 
 
-from oracle.golden_cases import DIGITAL_CASES  # noqa: E402
+from oracle.golden_cases import DIGITAL_CASES, LARGE_DIGITAL_CASES  # noqa: E402
 from tests.helpers import digital_engine_for_case  # noqa: E402
+
+
+@pytest.mark.parametrize("name", sorted(LARGE_DIGITAL_CASES))
+def test_cuda_digital_tjm_matches_reference_at_baseline_size(golden_dir, name):
+    """BASELINE.json config 4 at its own size (49 qubits, circuit depth 40, Pauli noise on every nearest-neighbour pair) against
+    the unmodified reference's digital_tjm: same jumps, identical bond dimensions, observables <= 1e-10."""
+    kern = CudaKernels("cuda:0")
+    eng, compiled, tu, traj, cfg = digital_engine_for_case(name, kern)
+    log = []
+    results, diag = eng.run_digital(compiled.layers, tu, cfg["sample"], cfg["gate_mode"], log)
+    torch.cuda.synchronize()
+    assert int(eng.status.max().item()) == 0
+    check_against_golden(name, golden_dir, results, diag, log, traj)
 
 
 @pytest.mark.parametrize("name", sorted(DIGITAL_CASES))

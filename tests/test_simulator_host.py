@@ -169,14 +169,26 @@ def test_shard_range_partitions():
             assert ids == list(range(n))
 
 
+def _digital_shots_run():
+    """Noisy digital run with observables and a shot budget spread over 5 trajectories (3 + 2 on two ranks)."""
+    from yaqs_b200 import DigitalSimParams
+    from yaqs_b200.circuits import create_ising_circuit
+    L = 4
+    noise = NoiseModel([{"name": "lowering", "sites": [i], "strength": 0.1} for i in range(L)])
+    sp = DigitalSimParams(observables=[Observable(Z(), 1)], num_traj=5, shots=12, max_bond_dim=8, random_seed=11)
+    return Simulator(show_progress=False, kernels=NumpyKernels()).run(State(L, initial="zeros"), create_ising_circuit(L, 1.0, 0.7, 0.2, 2), sp, noise)
+
+
 def _worker(rank, world, port, out):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     import torch.distributed as dist
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         res, _ = _golden_run()
+        dig = _digital_shots_run()
         if rank == 0:
-            out.put((np.array([res.expectation_values[i][0] for i in range(5)]), np.stack([t[:, 0] for t in res.trajectories])))
+            out.put((np.array([res.expectation_values[i][0] for i in range(5)]), np.stack([t[:, 0] for t in res.trajectories]),
+                     dig.counts, [dict(m) for m in dig.measurements], np.asarray(dig.trajectories[0])))
     finally:
         dist.destroy_process_group()
 
@@ -189,13 +201,18 @@ def test_two_rank_gloo_sharding_matches_single_process():
     procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    means, traj = q.get(timeout=600)
+    means, traj, counts, measurements, dig_traj = q.get(timeout=600)
     for p in procs:
         p.join(timeout=600)
         assert p.exitcode == 0
     single, _ = _golden_run()
     assert np.max(np.abs(means - REF_GOLDEN_Z)) < 1e-10
     assert np.array_equal(traj, np.stack([t[:, 0] for t in single.trajectories]))
+    # digital path with shots: per-trajectory counts are gathered from both ranks and do not depend on the sharding
+    dig = _digital_shots_run()
+    assert counts == dig.counts and measurements == [dict(m) for m in dig.measurements] and sum(counts.values()) == 12
+    assert [sum(m.values()) for m in measurements] == [3, 3, 2, 2, 2]
+    assert np.array_equal(dig_traj, np.asarray(dig.trajectories[0]))
 
 
 def test_digital_simulator_matches_reference_fixture(golden_dir):
