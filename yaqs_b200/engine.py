@@ -1164,15 +1164,43 @@ class BatchedTJM:
                 t[ol, orr, il, ir] = m[row, col]
         return t.reshape(4, 4)
 
-    def apply_two_qubit_gate_tebd(self, st: BatchedState, gate) -> int:
-        """apply_two_qubit_gate_tebd (digital_tjm.py:455-533) for a nearest-neighbour pair, entered with the centre at 0:
-        QR-equivalent shifts bring the centre to the pair, merge, gate, truncated split with S to the right.
-        Returns the new centre (the right site)."""
-        lay, K, B, d, p = self.lay, self.K, self.B, self.d, self.p
-        left = min(gate.sites)
+    def _move_centre(self, st: BatchedState, cur: int, target: int) -> None:
+        """shift_center_to (mps.py:374-393) with truncation-free shifts (QR-equivalent)."""
         keep_all = self._trunc_args("discarded_weight", 0.0, None, 1)
-        for i in range(left):
+        for i in range(cur, target):
             self.shift_right(st, i, keep_all, fast=True)
+        for i in range(cur, target, -1):
+            self.shift_left(st, i, keep_all, fast=True)
+
+    def apply_two_qubit_gate_tebd(self, st: BatchedState, gate, centre: int = 0) -> int:
+        """apply_two_qubit_gate_tebd (digital_tjm.py:455-533), entered with the orthogonality centre at ``centre``.  Nearest
+        neighbours: truncation-free shifts bring the centre onto the pair, merge, gate, truncated split with S to the right.
+        Other pairs go through the SWAP ladder of :463-481 (swaps from the right end down to left+1, the gate on
+        (left, left+1), swaps back).  Returns the new centre (the right site of the last pair touched)."""
+        lay, K, B, d, p = self.lay, self.K, self.B, self.d, self.p
+        s0, s1 = gate.sites
+        if abs(s0 - s1) != 1:
+            import copy as _copy
+
+            from .gates import GateLibrary
+            left, right = min(s0, s1), max(s0, s1)
+
+            def swap_at(i: int, c: int) -> int:
+                g = GateLibrary.swap()
+                g.set_sites(i, i + 1)
+                return self.apply_two_qubit_gate_tebd(st, g, c)
+
+            for i in range(right - 1, left, -1):
+                centre = swap_at(i, centre)
+            adj = _copy.deepcopy(gate)
+            adj.set_sites(*((left, left + 1) if s0 == left else (left + 1, left)))
+            centre = self.apply_two_qubit_gate_tebd(st, adj, centre)
+            for i in range(left + 1, right):
+                centre = swap_at(i, centre)
+            return centre
+        left = min(s0, s1)
+        if centre not in (left, left + 1):
+            self._move_centre(st, centre, left)
         th = self.merge(st, left)
         op = torch.from_numpy(np.ascontiguousarray(self._resolve_lr_matrix(gate)).reshape(-1)).to(self.dev)
         K.apply_local_op(B, None, None, 0, st.ext(left), st.ext(left + 2), d * d, op, 0, th, lay.cap[left] * lay.cap[left + 2])
@@ -1263,13 +1291,13 @@ class BatchedTJM:
                         has_gen = getattr(gate, "generator", None) is not None
                         if gate_mode == "full-tdvp" and has_gen:
                             centre = self.apply_two_qubit_gate_tdvp(st, gate)
-                        elif nn:
+                        elif nn or gate_mode == "swaps":
                             centre = self.apply_two_qubit_gate_tebd(st, gate)
                         elif gate_mode == "tdvp" and has_gen:
                             centre = self.apply_two_qubit_gate_tdvp(st, gate)
                         else:
-                            raise NotImplementedError(f"long-range gate in gate_mode={gate_mode!r}: the gate-MPO / SWAP-ladder routes are a "
-                                                      "SURVEY.md 8(f) 'next' row; use gate_mode='tdvp'")
+                            raise NotImplementedError(f"long-range gate in gate_mode={gate_mode!r}: the gate-MPO route (MPO.from_gate + multiply + "
+                                                      "compress) is a SURVEY.md 8(f) 'next' row; use gate_mode='tdvp' or 'swaps'")
                         if not noisy:
                             keep_all = self._trunc_args("discarded_weight", 0.0, None, 1)     # normalize("B", "QR")
                             for i in reversed(range(1, centre + 1)):
