@@ -11,6 +11,7 @@ numpy twin from ``oracle/`` to exercise this host logic on CPU; the package itse
 """
 from __future__ import annotations
 
+import copy
 from dataclasses import dataclass, field
 from typing import Sequence
 
@@ -18,6 +19,7 @@ import numpy as np
 import scipy.linalg
 import torch
 
+from .gates import GateLibrary
 from .kernels import (DIST, LANCZOS_PITCH, OP_ABSORB_L, OP_ABSORB_R, OP_ENVL1, OP_ENVL3, OP_ENVR3, OP_EVEC, OP_GRAM, OP_LCONTRACT, OP_MERGE,
                       OP_RCONTRACT, OP_ROTATE, SVD_COLS, SVD_META, SVD_ORIENT_COLS, SVD_ORIENT_ROWS, SVD_ROWS, SVD_THETA, TRUNC_MODES, Buf, Ext)
 
@@ -1180,9 +1182,6 @@ class BatchedTJM:
         lay, K, B, d, p = self.lay, self.K, self.B, self.d, self.p
         s0, s1 = gate.sites
         if abs(s0 - s1) != 1:
-            import copy as _copy
-
-            from .gates import GateLibrary
             left, right = min(s0, s1), max(s0, s1)
 
             def swap_at(i: int, c: int) -> int:
@@ -1192,7 +1191,7 @@ class BatchedTJM:
 
             for i in range(right - 1, left, -1):
                 centre = swap_at(i, centre)
-            adj = _copy.deepcopy(gate)
+            adj = copy.deepcopy(gate)
             adj.set_sites(*((left, left + 1) if s0 == left else (left + 1, left)))
             centre = self.apply_two_qubit_gate_tebd(st, adj, centre)
             for i in range(left + 1, right):
