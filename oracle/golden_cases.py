@@ -102,7 +102,15 @@ LARGE_CASES = {
                              sample_timesteps=True, ntraj=2, seed=42, obs="z",
                              noise=[("lowering", 0.1), ("pauli_z", 0.1)]),
 }
-ALL_CASES = {**CASES, **LARGE_CASES}
+# BASELINE config 5 (stress: Heisenberg L = 200, chi = 256, mixed noise): one sampled order-2 step of ONE trajectory; the reference
+# needs the better part of an hour for it.  Not in LARGE_CASES: the GPU test that consumes it is opt-in (YB_RUN_C5=1) until it has
+# been run on a B200 once.
+STRESS_CASES = {
+    "heis200_c5_step": dict(model="heisenberg", L=200, J=1.0, g=0.0, init="random:256:77", chi=256, thr=1e-6, order=2, dt=0.1, steps=1,
+                            sample_timesteps=True, ntraj=1, seed=5, obs="z",
+                            noise=[("lowering", 0.1), ("pauli_z", 0.1), ("pauli_x", 0.05)]),
+}
+ALL_CASES = {**CASES, **LARGE_CASES, **STRESS_CASES}
 
 
 
