@@ -5,7 +5,9 @@ Bar (BASELINE.json north_star): fed the same uniforms every trajectory takes the
 import pytest
 import torch
 
-from oracle.golden_cases import CASES, LARGE_CASES
+import os
+
+from oracle.golden_cases import CASES, LARGE_CASES, STRESS_CASES
 from tests.helpers import check_against_golden, engine_for_case
 from yaqs_b200.kernels import CudaKernels
 
@@ -34,6 +36,22 @@ def test_cuda_engine_matches_reference_at_baseline_sizes(golden_dir, name):
     torch.cuda.synchronize()
     assert int(eng.status.max().item()) == 0
     assert eng.stats["gram_svd_calls"] > 0                 # the production SVD route was taken
+    check_against_golden(name, golden_dir, results, diag, log, traj)
+
+
+@pytest.mark.skipif(not os.environ.get("YB_RUN_C5"), reason="config-5 stress fixture: opt-in (YB_RUN_C5=1) until it has run on a B200 once")
+@pytest.mark.parametrize("name", sorted(STRESS_CASES))
+def test_cuda_engine_matches_reference_stress(golden_dir, name):
+    """BASELINE.json config 5 (Heisenberg L = 200, chi = 256, mixed noise): one sampled order-2 step of one trajectory against the
+    unmodified reference -- 512 x 512 eigen-problems through the divide & conquer route with the 16-row ring."""
+    if not os.path.exists(os.path.join(golden_dir, f"{name}.npz")):
+        pytest.skip("fixture not generated (oracle/make_golden.py heis200_c5_step, ~1 h on a CPU core)")
+    kern = CudaKernels("cuda:0")
+    eng, tu, su, traj = engine_for_case(name, kern)
+    log = []
+    results, diag = eng.run(tu, su, log)
+    torch.cuda.synchronize()
+    assert int(eng.status.max().item()) == 0
     check_against_golden(name, golden_dir, results, diag, log, traj)
 
 
