@@ -70,6 +70,43 @@ def workload_config(args, nranks):
 
 
 # ----------------------------------------------------------------------------------------------------------------------
+# SURVEY.md 8(d) flop model with real counters
+# ----------------------------------------------------------------------------------------------------------------------
+def flop_model_step(bonds, mpo_bonds, n_mv2: float, n_mv1: float, n_jumps: float, d: int = 2) -> dict:
+    """Algorithmic flops of ONE order-2 sampled TJM step of ONE trajectory by the normative model of SURVEY.md 8(d)
+    (8 real flops per complex multiply-add), evaluated on the measured mean bond profile `bonds` (length L + 1), the MPO
+    bonds `mpo_bonds` (length L + 1) and the measured matvec / jump counts per trajectory-step.  Per-site terms are averaged
+    over the chain and multiplied by the call counts of integrators.py:161-291 / dissipation.py / stochastic_process.py."""
+    L = len(bonds) - 1
+
+    def mv(dt, i, ns):                                   # H_eff matvec on sites i .. i+ns-1 (primitives.py:180-204)
+        cl, cr, Dl, Dr = bonds[i], bonds[i + ns], mpo_bonds[i], mpo_bonds[i + ns]
+        return 8.0 * (dt * cl * cr * (Dr * cr + Dl * cl) + dt * dt * Dl * Dr * cl * cr)
+
+    def svd(m, n):                                       # complex economy SVD, Golub-Van Loan count x 4
+        m, n = max(m, n), min(m, n)
+        return 4.0 * (14.0 * m * n * n + 8.0 * n ** 3)
+
+    def qr(m, n):
+        m, n = max(m, n), min(m, n)
+        return 8.0 * (2.0 * m * n * n - 2.0 / 3.0 * n ** 3)
+
+    mean = lambda xs: float(sum(xs)) / max(len(xs), 1)      # noqa: E731
+    mv2 = mean([mv(d * d, i, 2) for i in range(L - 1)])
+    mv1 = mean([mv(d, i, 1) for i in range(L)])
+    merge = mean([8.0 * d * d * bonds[i] * bonds[i + 1] * bonds[i + 2] for i in range(L - 1)])
+    split = mean([svd(d * bonds[i], d * bonds[i + 2]) for i in range(L - 1)])
+    shift = mean([svd(d * bonds[i], bonds[i + 1]) + 8.0 * d * bonds[i] * bonds[i + 1] ** 2 for i in range(1, L)])
+    jump = L * mean([qr(d * bonds[i], bonds[i + 1]) for i in range(L)]) + (L - 1) * shift
+    sweep_krylov = n_mv2 * mv2 + n_mv1 * mv1                 # both sweeps of the step (phi and psi) are in the counters
+    env = 2 * (3 * L - 4) * mv1
+    splits = 2 * (2 * L - 3) * (merge + split)
+    shifts = 4 * (L - 1) * shift
+    total = sweep_krylov + env + splits + shifts + n_jumps * jump
+    return {"total": total, "krylov": sweep_krylov, "environments": env, "merge_and_split": splits, "gauge_shifts": shifts, "jumps": n_jumps * jump}
+
+
+# ----------------------------------------------------------------------------------------------------------------------
 # clocks
 # ----------------------------------------------------------------------------------------------------------------------
 class ClockSampler:
@@ -252,11 +289,30 @@ def run_b200_arm(args):
     obs_mean = (sums[-1, :L] / sums[-1, L + 3]).cpu().numpy()
     stats = {k: sum(e.stats[k] for e in engs) - stats0.get(k, 0) for k in engs[0].stats}
     bond_mean = float(torch.cat([e.psi.bond[:, 1:L].to(torch.float64).reshape(-1) for e in engs]).mean().item())
+    whole_step = None
+    try:                                                     # reporting only: never let the model break the bench line
+        prof = torch.stack([e.psi.bond.to(torch.float64).mean(dim=0) for e in engs]).mean(dim=0).cpu().tolist()
+        mpo_b = [1.0] + [float(w.shape[3]) for w in ham.mpo.tensors]
+        per = float(nl * K)                                   # counters are per lane launch; every trajectory of the lane sees them
+        n2, n1 = stats["matvecs_2site"] / per, (stats["matvecs"] - stats["matvecs_2site"]) / per
+        fm = flop_model_step(prof, mpo_b, n2, n1, stats["jumps"] / float(B * K))
+        whole_step = {"flops_per_trajectory_step_counters": fm["total"], "breakdown": {k: v for k, v in fm.items() if k != "total"},
+                      "flops_per_trajectory_step_survey": 2.15e12,
+                      "note": "SURVEY.md 8(d) model; 'counters' = measured mean bond profile, matvec and jump counts of the timed steps; "
+                              "'survey' = the headline figure for uniform chi = 128.  Matvec counts are per lane launch (a trajectory whose Lanczos has "
+                              "converged is masked but still counted), so 'counters' is an upper bound on the algorithmic flops"}
+    except Exception as exc:  # noqa: BLE001
+        whole_step = {"error": repr(exc)}
     t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total = float(t.item())
     value = B * world * K / (ms_total / 1000.0)
+    if whole_step and "error" not in whole_step:
+        for key in ("counters", "survey"):
+            tf = whole_step[f"flops_per_trajectory_step_{key}"] * value / world / 1e12
+            whole_step[f"tflops_per_gpu_{key}"] = tf
+            whole_step[f"frac_of_fp64_peak_{key}"] = tf / FP64_PEAK_TFLOPS
 
     roofline, sweep_ms, sweep_batch = None, float("nan"), engs[0].B
     if not args.no_roofline:
@@ -340,7 +396,7 @@ def run_b200_arm(args):
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_total / K,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "complex128 (f64)", "data": "synthetic",
-                "config": workload_config(args, world), "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks.summary(),
+                "config": workload_config(args, world), "roofline": roofline, "whole_step": whole_step, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks.summary(),
                 "gpu_launches": launches, "tdvp_sweep_ms": {"per_batch": sweep_ms, "batch": sweep_batch, "per_trajectory": sweep_ms / sweep_batch},
                 "counters": {**stats, "mean_bond": bond_mean, "z_mean_first_sites": [float(x) for x in obs_mean[:4]]}}
         print(json.dumps(line))

@@ -247,7 +247,7 @@ class BatchedTJM:
         # entries: (matrix, sites) | ("entropy", (i, i+1)) | ("pvm:<bitstring>", ())
         self.observables = [(m if isinstance(m, str) else np.asarray(m, dtype=np.complex128), tuple(int(s) for s in sites)) for m, sites in observables]
         self._ones_i32 = torch.ones(B, dtype=torch.int32, device=dev)
-        self.stats = {"krylov_calls": 0, "matvecs": 0, "svd_calls": 0, "svd_sweeps": 0, "jumps": 0, "gram_svd_calls": 0, "gram_fallbacks": 0}
+        self.stats = {"krylov_calls": 0, "matvecs": 0, "matvecs_2site": 0, "svd_calls": 0, "svd_sweeps": 0, "jumps": 0, "gram_svd_calls": 0, "gram_fallbacks": 0}
 
     # ------------------------------------------------------------------------------------------------------------------
     # operator / noise contexts (one each on the analog path; per gate on the digital path)
@@ -312,6 +312,7 @@ class BatchedTJM:
         K.wapply(B, mask, el, er, dphys, dphys, Dl, Dr, w, t1, t2, cl * cr)
         K.gemm(OP_LCONTRACT, B, dphys, mask, el, er, None, dphys, Dl, Dr, self.env(i, True), t2, y, 0, cl, cr)
         self.stats["matvecs"] += 1
+        self.stats["matvecs_2site"] += int(nsites == 2)
 
     def bond_matvec(self, el: Ext, er: Ext, jbond: int, x: Buf, y: Buf, mask, cl: int, cr: int) -> None:
         """project_bond (primitives.py:207-226) at bond jbond."""
