@@ -23,3 +23,17 @@ GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
 @pytest.fixture(scope="session")
 def golden_dir():
     return GOLDEN_DIR
+
+
+# -m gpu tests that were written after round 1's GPU budget was spent and have not yet executed on a B200.
+# They are collected LAST, so a first-run surprise in one of them cannot hide the 111 tests that are known green on the box
+# (profiles/r01_pytest_gpu_v7_baseline_sizes.txt) behind `-x`.  Remove an entry once a profiles/ log shows it green.
+FIRST_RUN_ON_GPU = ("test_backend_boundary_gpu", "test_measure_shots_replays_reference_outcomes_gpu", "ising6_scheduled", "dig_ising6_periodic_swaps",
+                    "dig_ising49_c4")
+
+
+def pytest_collection_modifyitems(config, items):
+    late = [it for it in items if it.get_closest_marker("gpu") and any(tag in it.nodeid for tag in FIRST_RUN_ON_GPU)]
+    if late:
+        late_ids = {id(it) for it in late}
+        items[:] = [it for it in items if id(it) not in late_ids] + late
