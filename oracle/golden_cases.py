@@ -258,3 +258,36 @@ def run_oracle_digital_case(cfg: dict, trajectories=None):
         rng = O.UniformStream(O.trajectory_stream(cfg["seed"], tr))
         out.append(O.digital_tjm(init, layers, noise, p, obs, rng, sample_layers=cfg["sample"], gate_mode=cfg["gate_mode"]))
     return out
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# SimulationProgram cases: neutral specs; oracle/make_program_golden.py builds them from the reference's
+# classes and walks the reference's own _execute_program_trajectory, the tests build them from yaqs_b200's.
+#   analog segment : kind "A", Ising (J, g), elapsed time T, dt, order, chi, thr, sample (sample_timesteps)
+#   digital segment: kind "D", Ising Trotter circuit (J, g, dt, timesteps), chi, thr, sample (sample_layers)
+# "ham" names a Hamiltonian OBJECT: segments naming the same one share it (merge / order-2 hand-off rules test identity or equality).
+# ----------------------------------------------------------------------------------------------------------------------
+_PNOISE = [("lowering", 0.2), ("pauli_z", 0.2)]
+PROGRAM_CASES = {
+    # two order-2 segments with different Hamiltonians and equal settings -> ONE merged run with one MPO per interval
+    "prog_quench_merged_o2": dict(L=6, init="x+", noise=_PNOISE, ntraj=4, seed=11, obs="z+zz", segments=[
+        dict(kind="A", ham="h0", J=1.0, g=0.5, T=0.2, dt=0.1, order=2, chi=8, thr=1e-9, sample=True),
+        dict(kind="A", ham="h1", J=1.0, g=1.5, T=0.3, dt=0.1, order=2, chi=8, thr=1e-9, sample=True)]),
+    # same Hamiltonian, different max_bond_dim -> no merge, but the order-2 Trotter chain continues: phi hand-off, junction
+    # re-measured, global sample-stream offset; then an order-1 segment that starts from the last physical measurement copy
+    "prog_handoff_o2": dict(L=6, init="x+", noise=_PNOISE, ntraj=4, seed=12, obs="z", segments=[
+        dict(kind="A", ham="h0", J=1.0, g=0.8, T=0.2, dt=0.1, order=2, chi=4, thr=1e-9, sample=True),
+        dict(kind="A", ham="h0", J=1.0, g=0.8, T=0.3, dt=0.1, order=2, chi=8, thr=1e-9, sample=True),
+        dict(kind="A", ham="h1", J=0.5, g=1.2, T=0.2, dt=0.1, order=1, chi=8, thr=1e-9, sample=True)]),
+    # final-only sampling: merged order-1 run measured at the segment boundaries (sample_at), a digital Trotter block in the
+    # middle (its jump tests continue the same trajectory stream), an order-2 tail
+    "prog_mixed_digital": dict(L=6, init="zeros", noise=_PNOISE, ntraj=4, seed=13, obs="z+x", segments=[
+        dict(kind="A", ham="h0", J=1.0, g=0.5, T=0.2, dt=0.1, order=1, chi=8, thr=1e-9, sample=False),
+        dict(kind="A", ham="h1", J=1.0, g=1.0, T=0.2, dt=0.1, order=1, chi=8, thr=1e-9, sample=False),
+        dict(kind="D", J=1.0, g=0.7, dt=0.1, timesteps=2, chi=8, thr=1e-9, sample=True),
+        dict(kind="A", ham="h0", J=1.0, g=0.5, T=0.2, dt=0.1, order=2, chi=8, thr=1e-9, sample=False)]),
+    # noiseless program: one trajectory whatever num_traj says, merged order-2 run, final-only sampling
+    "prog_noiseless_o2": dict(L=6, init="Neel", noise=[], ntraj=3, seed=14, obs="z", segments=[
+        dict(kind="A", ham="h0", J=1.0, g=0.5, T=0.2, dt=0.1, order=2, chi=8, thr=1e-9, sample=False),
+        dict(kind="A", ham="h1", J=1.0, g=1.5, T=0.2, dt=0.1, order=2, chi=8, thr=1e-9, sample=False)]),
+}

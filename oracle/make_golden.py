@@ -143,6 +143,34 @@ def run_case(name: str, cfg: dict) -> dict:
                 sorted_obs_names=np.array(sorted_names), times=np.asarray(sim.times), krylov_tol=np.float64(sim.krylov_tol))
 
 
+def reference_ising_compiled(ref_dig, GateLibrary, L, J, g, dt, timesteps, periodic=False, sample=False):   # noqa: N803
+    """The layers the reference's _compile_circuit produces for create_ising_circuit (one gate per layer, even/odd by lowest
+    qubit), built from the reference's own GateLibrary gates (qiskit is absent here, SURVEY.md 8(c) shim 3)."""
+    alpha, beta = -2 * dt * g, -2 * dt * J
+    layers = []
+
+    def layer(single=(), even=(), odd=(), pts=0):
+        return ref_dig._CompiledCircuitLayer(tuple(single), tuple(even), tuple(odd), pts)
+
+    for step in range(timesteps):
+        for s in range(L):
+            gate = GateLibrary.rx([alpha])
+            gate.set_sites(s)
+            layers.append(layer(single=[gate]))
+        pairs = [(2 * s, 2 * s + 1) for s in range(L // 2)] + [(2 * s - 1, 2 * s) for s in range(1, L // 2)]
+        if L % 2 != 0 and L != 1:
+            pairs.append((L - 2, L - 1))
+        if periodic and L > 1:
+            pairs.append((0, L - 1))
+        for a, b in pairs:
+            gate = GateLibrary.rzz([beta])
+            gate.set_sites(a, b)
+            layers.append(layer(even=[gate]) if min(a, b) % 2 == 0 else layer(odd=[gate]))
+        if sample and step < timesteps - 1:
+            layers.append(layer(pts=1))
+    return ref_dig._CompiledCircuit(tuple(layers), sum(l.sample_points for l in layers))
+
+
 def run_digital_case(name: str, cfg: dict) -> dict:
     """Run the reference's digital_tjm (digital/digital_tjm.py:636) on a hand-compiled Ising Trotter circuit.  qiskit is
     absent here, so the DAG front end is bypassed exactly as SURVEY.md 8(c) shim 3 describes: the layers the reference's
@@ -157,30 +185,8 @@ def run_digital_case(name: str, cfg: dict) -> dict:
     from mqt.yaqs.core.random_utils import make_trajectory_rng
 
     L = cfg["L"]
-    alpha, beta = -2 * cfg["dt"] * cfg["g"], -2 * cfg["dt"] * cfg["J"]
-    layers = []
-
-    def layer(single=(), even=(), odd=(), pts=0):
-        return ref_dig._CompiledCircuitLayer(tuple(single), tuple(even), tuple(odd), pts)
-
-    for step in range(cfg["timesteps"]):
-        for s in range(L):
-            g = GateLibrary.rx([alpha])
-            g.set_sites(s)
-            layers.append(layer(single=[g]))
-        pairs = [(2 * s, 2 * s + 1) for s in range(L // 2)] + [(2 * s - 1, 2 * s) for s in range(1, L // 2)]
-        if L % 2 != 0 and L != 1:
-            pairs.append((L - 2, L - 1))
-        if cfg["periodic"] and L > 1:
-            pairs.append((0, L - 1))
-        for a, b in pairs:
-            g = GateLibrary.rzz([beta])
-            g.set_sites(a, b)
-            layers.append(layer(even=[g]) if min(a, b) % 2 == 0 else layer(odd=[g]))
-        if cfg["sample"] and step < cfg["timesteps"] - 1:
-            layers.append(layer(pts=1))
-    mid = sum(l.sample_points for l in layers)
-    compiled = ref_dig._CompiledCircuit(tuple(layers), mid)
+    compiled = reference_ising_compiled(ref_dig, GateLibrary, L, cfg["J"], cfg["g"], cfg["dt"], cfg["timesteps"], cfg["periodic"], cfg["sample"])
+    mid = compiled.num_mid_measurements
 
     obs = []
     for tok in cfg["obs"].split("+"):

@@ -47,7 +47,9 @@ def load_reference() -> None:
     except ImportError:
         for name in ("qiskit", "qiskit.circuit", "qiskit.converters", "qiskit.dagcircuit", "qiskit.exceptions",
                      "qiskit.quantum_info", "qiskit.qasm2", "qiskit.qasm3", "qiskit.circuit.library",
-                     "qiskit.quantum_info.operators", "qiskit.quantum_info.operators.predicates"):
+                     "qiskit.quantum_info.operators", "qiskit.quantum_info.operators.predicates", "qiskit.utils", "qiskit.utils.optionals",
+                     "qiskit.transpiler", "qiskit.transpiler.passes", "qiskit.providers", "qiskit.providers.fake_provider"):
             stub = types.ModuleType(name)
+            stub.__path__ = []                     # a package, so that deeper stubbed submodules resolve from sys.modules
             stub.__getattr__ = lambda attr, _n=name: type(attr, (), {})  # any name resolves to a dummy class
             sys.modules[name] = stub

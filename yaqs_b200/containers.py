@@ -278,3 +278,7 @@ class Result:
     counts: dict | None = None
     status: np.ndarray | None = None          # per-trajectory device status words (0 = clean)
     stats: dict | None = None                 # engine counters (matvecs, Krylov calls, SVD sweeps, kernel launches)
+    segment_results: list = field(default_factory=list)   # SimulationProgram runs: one Result per segment (result.py:170-189)
+    segment_index: int | None = None
+    segment_type: str | None = None
+    time_offset: float | None = None

@@ -125,6 +125,23 @@ class BatchedState:
         self.A.copy_(other.A)
         self.bond.copy_(other.bond)
 
+    def transfer_from(self, other: "BatchedState") -> None:
+        """Device-to-device hand-off between two engines whose slot capacities differ (SimulationProgram segments with different
+        ``max_bond_dim``): site tensors are stored compactly (d, l, r) at the start of their slot, so the leading
+        ``min(slot_dst, slot_src)`` elements of every slot carry the whole tensor as long as the destination capacities cover the
+        source's current bonds (BatchedTJM sizes its layout from them)."""
+        lay, src = self.layout, other.layout
+        if (lay.L, lay.B, lay.d) != (src.L, src.B, src.d):
+            raise ValueError("transfer_from needs the same chain length, batch size and physical dimension")
+        top = other.bond.max(dim=0).values.cpu().tolist()
+        if any(int(t) > c for t, c in zip(top, lay.cap)):
+            raise ValueError(f"bonds {top} exceed the destination capacities {lay.cap}")
+        self.bond.copy_(other.bond)
+        for i in range(lay.L):
+            n = min(lay.slot[i], src.slot[i])
+            dst = self.A[lay.site_off[i]: lay.site_off[i] + lay.B * lay.slot[i]].view(lay.B, lay.slot[i])
+            dst[:, :n].copy_(other.A[src.site_off[i]: src.site_off[i] + src.B * src.slot[i]].view(src.B, src.slot[i])[:, :n])
+
     def load(self, tensors_per_traj: Sequence[Sequence[np.ndarray]] | Sequence[np.ndarray]) -> None:
         """Upload host MPS tensors (s, l, r).  A single MPS (list of arrays) is broadcast to all trajectories."""
         lay = self.layout
@@ -160,27 +177,42 @@ class BatchedTJM:
 
     def __init__(self, kernels, length: int, nbatch: int, mpo: Sequence[np.ndarray], params: EngineParams,
                  noise: Sequence[dict] | None, observables: Sequence[tuple[np.ndarray, Sequence[int]]],
-                 init_tensors, svd_block_rows: int | None = None, gram_min_k: int = 33, scheduled_jumps: Sequence[dict] | None = None):
+                 init_tensors, svd_block_rows: int | None = None, gram_min_k: int = 33, scheduled_jumps: Sequence[dict] | None = None,
+                 extra_mpos: Sequence[Sequence[np.ndarray]] = ()):
+        """``init_tensors``: one MPS (list of (d, l, r) arrays, broadcast), one MPS per trajectory, or the BatchedState of another
+        engine (device-to-device hand-off between SimulationProgram segments).  ``extra_mpos``: further MPOs this engine will be
+        switched to (``run(interval_mpos=...)``); the layout takes the per-bond maximum of their bond dimensions and every MPO is
+        zero-padded to it on upload."""
         self.K = kernels
         self.scheduled_jumps = list(scheduled_jumps) if scheduled_jumps else []       # normalised {time, sites, matrix} (order 1 only)
         self.dev = kernels.device
         self.p = params
         self.L, self.B, self.d = length, nbatch, 2
-        single = isinstance(init_tensors[0], np.ndarray)
-        ref = init_tensors if single else init_tensors[0]
+        from_state = isinstance(init_tensors, BatchedState)
         init_bonds = [1] * (length + 1)
-        for tensors in ([init_tensors] if single else init_tensors):
-            for i, t in enumerate(tensors):
-                init_bonds[i] = max(init_bonds[i], t.shape[1])
-                init_bonds[i + 1] = max(init_bonds[i + 1], t.shape[2])
-        del ref
+        if from_state:
+            if init_tensors.layout.B != nbatch or init_tensors.layout.L != length:
+                raise ValueError("the handed-over BatchedState has another batch size or chain length")
+            init_bonds = [int(v) for v in init_tensors.bond.max(dim=0).values.cpu().tolist()]
+        else:
+            single = isinstance(init_tensors[0], np.ndarray)
+            for tensors in ([init_tensors] if single else init_tensors):
+                for i, t in enumerate(tensors):
+                    init_bonds[i] = max(init_bonds[i], t.shape[1])
+                    init_bonds[i + 1] = max(init_bonds[i + 1], t.shape[2])
         mpo_bonds = [int(mpo[0].shape[2])] + [int(w.shape[3]) for w in mpo]
+        for other in extra_mpos:
+            ob = [int(other[0].shape[2])] + [int(w.shape[3]) for w in other]
+            mpo_bonds = [max(a, b) for a, b in zip(mpo_bonds, ob)]
         self.lay = BatchLayout(length, nbatch, params.max_bond_dim, mpo_bonds, init_bonds)
         lay = self.lay
         dev = self.dev
         self.phi = BatchedState(lay, dev)
         self.psi = BatchedState(lay, dev) if params.order == 2 else None
-        self.phi.load(init_tensors)
+        if from_state:
+            self.phi.transfer_from(init_tensors)
+        else:
+            self.phi.load(init_tensors)
         # environments: bond-slot storage; the left and right blocks of a 2-site sweep never need the same bond at the
         # same time (see DESIGN.md), 1TDVP's bond update does.
         self.renv = torch.zeros(lay.env_elems, dtype=C128, device=dev)
@@ -254,6 +286,16 @@ class BatchedTJM:
     # ------------------------------------------------------------------------------------------------------------------
     def _upload_mpo(self, mpo: Sequence[np.ndarray]) -> dict:
         dev = self.dev
+        D = self.lay.D
+        if any(w.shape[2] != D[i] or w.shape[3] != D[i + 1] for i, w in enumerate(mpo)):      # zero-pad to the layout's bond dims
+            padded = []
+            for i, w in enumerate(mpo):
+                if w.shape[2] > D[i] or w.shape[3] > D[i + 1]:
+                    raise ValueError(f"MPO site {i}: bonds {w.shape[2:]} exceed the layout's ({D[i]}, {D[i + 1]}); pass it in extra_mpos")
+                z = np.zeros((w.shape[0], w.shape[1], D[i], D[i + 1]), dtype=np.complex128)
+                z[:, :, : w.shape[2], : w.shape[3]] = w
+                padded.append(z)
+            mpo = padded
         w1 = [torch.from_numpy(np.ascontiguousarray(w, dtype=np.complex128).reshape(-1)).to(dev) for w in mpo]
         w1t = [torch.from_numpy(np.ascontiguousarray(np.transpose(w, (1, 0, 3, 2)), dtype=np.complex128).reshape(-1)).to(dev) for w in mpo]
         w2 = []
@@ -1052,18 +1094,50 @@ class BatchedTJM:
     # ------------------------------------------------------------------------------------------------------------------
     # trajectory drivers (analog/analog_tjm.py:86-462)
     # ------------------------------------------------------------------------------------------------------------------
-    def run(self, traj_uniforms: torch.Tensor | None, sample_uniforms: torch.Tensor | None, log: list | None = None):
-        """Run all time steps.  traj_uniforms: [B, 2*n_times] trajectory stream (consumed 1 or 2 per jump test);
+    def run(self, traj_uniforms: torch.Tensor | None, sample_uniforms: torch.Tensor | None, log: list | None = None, *,
+            start_pos: torch.Tensor | None = None, sample_at: Sequence[int] | None = None, continue_trajectory: bool = False,
+            interval_mpos: Sequence[Sequence[np.ndarray]] | None = None):
+        """Run all time steps.  traj_uniforms: [B, >= 2*n_times] trajectory stream (consumed 1 or 2 per jump test);
         sample_uniforms: [B, n_times, 2] per-timestep measurement streams (order 2).  Returns (results [B, n_obs, T],
-        diagnostics [B, 3, T]) as device tensors."""
+        diagnostics [B, 3, T]) as device tensors.
+
+        Keyword arguments of SimulationProgram execution (analog_tjm.py:206-366,369-462; simulator.py:339-552):
+        ``start_pos`` [B] int64 -- where each trajectory's stream continues (one Generator is shared by all segments of a program;
+        ``self._pos`` holds the position after the run); ``sample_at`` -- time-grid indices to record instead of the
+        ``sample_timesteps`` rule (:50-62); ``continue_trajectory`` -- order 2 only: the loaded state is a mid-Trotter phi, the
+        junction is re-measured and ``initialize`` is skipped (:312-324); ``interval_mpos`` -- one MPO per interval of the grid
+        (merged segments with different Hamiltonians): step j evolves with interval j-1 (order 1), with j-2 for step_through and
+        j-1 for its measurement copy (order 2, :343-360)."""
         p = self.p
         nt = p.n_times
         ncol = nt if p.sample_timesteps else 1
         nobs = len(self.observables)
         results = torch.zeros((self.B, nobs, ncol), dtype=torch.float64, device=self.dev)
         diag = torch.zeros((self.B, 3, ncol), dtype=torch.float64, device=self.dev)
-        self._pos = torch.zeros(self.B, dtype=torch.int64, device=self.dev)
+        self._pos = torch.zeros(self.B, dtype=torch.int64, device=self.dev) if start_pos is None else start_pos.to(self.dev, torch.int64).clone()
         self._traj_u = traj_uniforms
+        measure_at = None
+        if sample_at is not None:                           # _validate_sample_at (:65-83)
+            for index in sample_at:
+                if isinstance(index, bool) or not isinstance(index, (int, np.integer)) or index < 0 or index >= nt:
+                    raise ValueError(f"sample_at index {index!r} is outside the time grid [0, {nt}).")
+            measure_at = frozenset(int(i) for i in sample_at)
+            if not p.sample_timesteps and len(measure_at) > 1:
+                raise ValueError("Selecting multiple sample_at indices requires sample_timesteps=True.")
+        if interval_mpos is not None and len(interval_mpos) != nt - 1:
+            raise ValueError(f"interval_mpos needs one MPO per interval ({nt - 1}), got {len(interval_mpos)}")
+
+        def wanted(j: int) -> bool:                         # _measure_at (:50-62)
+            if measure_at is not None:
+                return j in measure_at
+            return p.sample_timesteps or j == nt - 1
+
+        def use_interval(k: int) -> None:
+            if interval_mpos is not None:
+                key = id(interval_mpos[k])
+                if key not in self._mpo_cache:
+                    self._mpo_cache[key] = self._upload_mpo(interval_mpos[k])
+                self._set_mpo(self._mpo_cache[key])
 
         def record(state, col):
             diag[:, :, col] = self.diagnostics(state)
@@ -1083,7 +1157,10 @@ class BatchedTJM:
         if p.order == 2:
             psi = self.psi
 
-            def sample(j):
+            def sample(j, interval):
+                if not wanted(j):                           # the last column is always wanted on the paths the callers use
+                    return
+                use_interval(interval)
                 psi.copy_from(phi)
                 self.tdvp(psi)
                 self.apply_dissipation(psi, p.dt / 2)
@@ -1093,27 +1170,41 @@ class BatchedTJM:
                     self.stochastic_process(psi, p.dt, sample_uniforms[:, j, 0].contiguous(), sample_uniforms[:, j, 1].contiguous(), log, f"sample{j}")
                 record(psi, j if p.sample_timesteps else 0)
 
-            if nt == 1 or p.sample_timesteps:
-                record(phi, 0)
             if nt == 1:
+                if wanted(0):
+                    record(phi, 0)
                 return results, diag
+            if continue_trajectory:                         # :312-324 (static operator: interval 0 everywhere)
+                sample(0, 0)
+                for j in range(1, nt):
+                    use_interval(0)
+                    self.tdvp(phi)
+                    self.apply_dissipation(phi, p.dt)
+                    traj_jump_test(phi, f"step{j}")
+                    sample(j, 0)
+                return results, diag
+            if measure_at is not None and 0 in measure_at or measure_at is None and p.sample_timesteps:
+                record(phi, 0)
             self.apply_dissipation(phi, p.dt / 2)           # initialize (:86-108)
             traj_jump_test(phi, "init")
-            if p.sample_timesteps or nt == 2:
-                sample(1)
+            sample(1, 0)
             for j in range(2, nt):
+                use_interval(j - 2)
                 self.tdvp(phi)                              # step_through (:111-140)
                 self.apply_dissipation(phi, p.dt)
                 traj_jump_test(phi, f"step{j}")
-                if p.sample_timesteps or j == nt - 1:
-                    sample(j)
+                sample(j, j - 1)
             return results, diag
         # first-order scheme (:369-462)
+        if continue_trajectory:
+            raise ValueError("continue_trajectory is an order-2 hand-off")
         if self.has_scheduled_jump(0.0):                    # :428-431: before the initial sample
             self.apply_scheduled_jumps(phi, 0.0)
-        if p.sample_timesteps:
+        measure_initial = (0 in measure_at) if measure_at is not None else p.sample_timesteps
+        if measure_initial:
             record(phi, 0)
         for j in range(1, nt):
+            use_interval(j - 1)
             self.tdvp(phi)
             if self.noise is not None or self.scheduled_jumps:
                 if self.noise is not None:
@@ -1122,9 +1213,9 @@ class BatchedTJM:
                     self.apply_scheduled_jumps(phi, j * p.dt)
                 else:
                     traj_jump_test(phi, f"step{j}")
-            if p.sample_timesteps or j == nt - 1:
+            if wanted(j):
                 record(phi, j if p.sample_timesteps else 0)
-        if not p.sample_timesteps and nt <= 1:
+        if not measure_initial and not p.sample_timesteps and nt <= 1:
             record(phi, 0)
         return results, diag
 
@@ -1253,7 +1344,8 @@ class BatchedTJM:
             self._noise_cache[key] = self._make_noise_ctx([pr for pr in self._global_noise if set(pr["sites"]).issubset(gs)])
         return self._noise_cache[key]
 
-    def run_digital(self, layers, traj_uniforms: torch.Tensor | None, sample_layers: bool, gate_mode: str = "mpo", log: list | None = None):
+    def run_digital(self, layers, traj_uniforms: torch.Tensor | None, sample_layers: bool, gate_mode: str = "mpo", log: list | None = None,
+                    start_pos: torch.Tensor | None = None):
         """digital_tjm (digital_tjm.py:636-749), observable path, for the whole batch.  ``layers``: compiled circuit layers
         (single-qubit gates, even / odd two-qubit groups, sample points); traj_uniforms: [B, 2 * n_two_qubit_gates].
         Returns (results [B, n_obs, cols], diagnostics [B, 3, cols])."""
@@ -1269,7 +1361,8 @@ class BatchedTJM:
         nobs = len(self.observables)
         results = torch.zeros((self.B, nobs, ncol), dtype=torch.float64, device=self.dev)
         diag = torch.zeros((self.B, 3, ncol), dtype=torch.float64, device=self.dev)
-        pos = torch.zeros(self.B, dtype=torch.int64, device=self.dev)
+        pos = torch.zeros(self.B, dtype=torch.int64, device=self.dev) if start_pos is None else start_pos.to(self.dev, torch.int64).clone()
+        self._pos = pos                                     # read back by SimulationProgram execution (one stream per trajectory)
 
         def record(col: int) -> None:
             diag[:, :, col] = self.diagnostics(st)

@@ -94,7 +94,23 @@ class Simulator:
             self._kernels = CudaKernels(dev)
         return self._kernels
 
-    def run(self, initial_state: State, operator, sim_params=None, noise_model: NoiseModel | None = None) -> Result:
+    def run(self, initial_state: State, operator, sim_params=None, noise_model: NoiseModel | None = None, *, observables=None,
+            num_traj: int | None = None, random_seed: int | None = None, get_state: bool = False) -> Result:
+        from .program import SimulationProgram, run_program
+        program_kwargs_set = observables is not None or num_traj is not None or random_seed is not None or get_state     # :1222-1260
+        if (isinstance(operator, Sequence) and not isinstance(operator, (str, bytes))
+                and (not operator or (isinstance(operator[0], tuple) and len(operator[0]) in {2, 3}))):
+            if sim_params is not None:
+                raise TypeError("sim_params must be None when operator is a segment pair list.")
+            operator = SimulationProgram(operator, observables=observables, num_traj=num_traj, random_seed=random_seed, get_state=get_state)
+        elif program_kwargs_set and not isinstance(operator, SimulationProgram):
+            raise TypeError("observables=, num_traj=, random_seed=, and get_state= are only valid for a SimulationProgram or a segment pair list.")
+        if isinstance(operator, SimulationProgram):
+            if sim_params is not None:
+                raise TypeError("sim_params must be None when operator is a SimulationProgram.")
+            if not isinstance(initial_state, State):
+                raise TypeError("SimulationProgram execution requires a single State initial_state.")
+            return run_program(self, initial_state, operator, noise_model)
         if sim_params is None:
             raise TypeError("Standalone simulation requires AnalogSimParams or DigitalSimParams.")
         if not isinstance(sim_params, (AnalogSimParams, DigitalSimParams)):
