@@ -43,8 +43,8 @@ def _check_backends(kernels):
         assert np.max(np.abs(res_b - res)) < 1e-12
         with pytest.raises(ValueError, match="order"):
             backends.analog_tjm_1((0, state, noise, sp, ham))
-        with pytest.raises(NotImplementedError):
-            backends.analog_tjm_2((0, state, noise, sp, ham), continue_trajectory=True)
+        with pytest.raises(ValueError, match="outside the time grid"):
+            backends.analog_tjm_2((0, state, noise, sp, ham), sample_at=[len(sp.times)])
         # the batched entry: several trajectory indices in lock step, rows in sorted-observable order
         res_all, diag_all, status, final = backends.run_batch([5, 1, 2], state, noise, sp, ham)
         assert not status.any() and final is None
@@ -95,3 +95,47 @@ def test_backends_fail_loudly_without_cuda():
     cfg, state, noise, sp, ham, _ = _analog_inputs("ising10_c1_order2")
     with pytest.raises(Exception):
         backends.analog_tjm_2((0, state, noise, sp, ham))
+
+
+def _check_program_hand_off_through_backends(kernels, golden_dir):
+    """The reference's program executor drives the two analog backends with ONE Generator and the hand-off keywords
+    (simulator.py:339-402): segment 0 returns phi, segment 1 continues the Trotter chain with the global sample offset, segment 2
+    (order 1) starts from the last physical copy.  Replayed here through backends.analog_tjm_2 / analog_tjm_1 for every trajectory of
+    the fixture prog_handoff_o2 (unmodified reference)."""
+    import os
+
+    from oracle.golden_cases import PROGRAM_CASES
+    from yaqs_b200 import MPS
+    from yaqs_b200.rng import STREAM_TRAJECTORY
+    backends.set_default_kernels(kernels)
+    cfg = PROGRAM_CASES["prog_handoff_o2"]
+    g = np.load(os.path.join(golden_dir, "prog_handoff_o2.npz"))
+    L = cfg["L"]
+    obs = [Observable(Z(), s) for s in range(L)]
+    noise = NoiseModel([{"name": n, "sites": [i], "strength": s} for i in range(L) for (n, s) in cfg["noise"]])
+    hams = {"h0": Hamiltonian.ising(L, 1.0, 0.8), "h1": Hamiltonian.ising(L, 0.5, 1.2)}
+    sps = [AnalogSimParams(observables=obs, elapsed_time=seg["T"], dt=seg["dt"], max_bond_dim=seg["chi"], svd_threshold=seg["thr"],
+                           order=seg["order"], sample_timesteps=True, get_state=True, random_seed=cfg["seed"]) for seg in cfg["segments"]]
+    for t in range(cfg["ntraj"]):
+        rng = np.random.default_rng(np.random.SeedSequence([cfg["seed"], t, STREAM_TRAJECTORY]))
+        state = MPS(L, state=cfg["init"])
+        r0, d0, state = backends.analog_tjm_2((t, state, noise, sps[0], hams["h0"]), copy_initial_state=False, rng=rng, sample_timestep_offset=0,
+                                              return_trajectory_state=True, continue_trajectory=False)
+        r1, d1, state = backends.analog_tjm_2((t, state, noise, sps[1], hams["h0"]), copy_initial_state=False, rng=rng, sample_timestep_offset=2,
+                                              return_trajectory_state=False, continue_trajectory=True)
+        r2, d2, state = backends.analog_tjm_1((t, state, noise, sps[2], hams["h1"]), copy_initial_state=False, rng=rng)
+        for k, (r, d) in enumerate(((r0, d0), (r1, d1), (r2, d2))):
+            assert np.max(np.abs(r - g[f"res_{k}"][t])) < 1e-10, (t, k)
+            assert np.array_equal(d, g[f"diag_{k}"][t]), (t, k)
+        # the shared Generator advanced by exactly the doubles the reference drew
+        fresh = np.random.default_rng(np.random.SeedSequence([cfg["seed"], t, STREAM_TRAJECTORY]))
+        fresh.random(int(g["draws"][t]))
+        assert rng.random() == fresh.random()
+
+
+def test_program_hand_off_through_backends_host_twin(golden_dir):
+    from oracle.np_kernels import NumpyKernels
+    try:
+        _check_program_hand_off_through_backends(NumpyKernels(), golden_dir)
+    finally:
+        backends.set_default_kernels(None)

@@ -49,14 +49,25 @@ def _tensors(state) -> list[np.ndarray]:
 def _mpo_tensors(operator) -> list[np.ndarray]:
     if isinstance(operator, Hamiltonian):
         operator = operator.mpo
+    return operator.tensors if isinstance(operator.tensors, list) else list(operator.tensors)
+
+
+def _interval_mpos(operator, n_intervals: int):
+    """``HamiltonianOperator = MPO | tuple[MPO, ...]`` (analog_tjm.py:40-48): (first MPO's tensors, per-interval tensor lists | None)."""
     if isinstance(operator, (list, tuple)):
-        raise NotImplementedError("one MPO per analog interval (time-dependent Hamiltonians) is outside the B200 hot-path scope")
-    return list(operator.tensors)
+        if len(operator) != n_intervals:
+            raise ValueError(f"one MPO per analog interval expected ({n_intervals}), got {len(operator)}")
+        by_id: dict[int, list] = {}
+        per = [by_id.setdefault(id(m), _mpo_tensors(m)) for m in operator]       # same MPO object -> same list (engine caches by id)
+        return per[0], (per if len(by_id) > 1 else None)
+    return _mpo_tensors(operator), None
 
 
 def _generator_table(rng: np.random.Generator, n_times: int) -> np.ndarray:
     """An externally managed numpy Generator as a uniform table: a jump test draws ``rng.random()`` and, if it jumps, one more
-    double inside ``rng.choice`` (stochastic_process.py:190-245), so 2 * n_times consecutive doubles replay any history."""
+    double inside ``rng.choice`` (stochastic_process.py:190-245), so 2 * n_times consecutive doubles replay any history.
+    ``run_batch`` rewinds the Generator afterwards and advances it by the doubles the trajectory really consumed, so a caller
+    that threads one Generator through several calls (SimulationProgram execution, simulator.py:610) sees the reference's state."""
     if not isinstance(rng, np.random.Generator):
         raise TypeError("rng must be a numpy.random.Generator (the batched path replays its doubles from a table)")
     return rng.random(2 * n_times)
@@ -64,12 +75,16 @@ def _generator_table(rng: np.random.Generator, n_times: int) -> np.ndarray:
 
 def run_batch(traj_indices: Sequence[int], initial_state, noise_model: NoiseModel | None, sim_params: AnalogSimParams, operator, *,
               kernels=None, rng_mode: str = "numpy", trajectory_rngs: Sequence[np.random.Generator] | None = None,
-              sample_timestep_offset: int = 0, return_states: bool = False):
+              sample_timestep_offset: int = 0, return_states: bool = False, sample_at: Sequence[int] | None = None,
+              continue_trajectory: bool = False, return_trajectory_state: bool = False, use_trajectory_rng_for_final_sample: bool = False):
     """Analog TJM for the trajectories ``traj_indices`` as one lock-step batch.
 
     Returns ``(results [B, n_sorted_obs, T | 1], diagnostics [B, 3, T | 1], status [B], final)`` as host arrays; rows follow
     ``sim_params.sorted_observables`` exactly like the reference's per-trajectory buffers (``simulator.py:932-942`` maps them back
-    to user order).  ``final``: list of per-trajectory tensor lists when ``return_states`` is set, else None.
+    to user order).  ``final``: list of per-trajectory tensor lists when ``return_states`` is set, else None -- the physical
+    state at the final time, or the mid-Trotter trajectory state phi with ``return_trajectory_state`` (order 2).  ``sample_at``,
+    ``continue_trajectory`` and ``use_trajectory_rng_for_final_sample`` are the segment hand-off options of SimulationProgram
+    execution (analog_tjm.py:206-279); ``operator`` may be one MPO per interval.
     The noise model is used as given (``Simulator.run`` samples static disorder BEFORE dispatch, ``simulator.py:1269-1271``)."""
     if not isinstance(sim_params, AnalogSimParams):
         raise TypeError("run_batch drives the analog TJM; use digital_tjm / Simulator.run for DigitalSimParams")
@@ -85,7 +100,8 @@ def run_batch(traj_indices: Sequence[int], initial_state, noise_model: NoiseMode
                       sample_timesteps=sim_params.sample_timesteps)
     procs = noise_model.processes if noise_model is not None else None
     sched = noise_model.scheduled_jumps if noise_model is not None else None
-    eng = BatchedTJM(K, length, len(idx), _mpo_tensors(operator), ep, procs, obs, tensors, scheduled_jumps=sched)
+    mpo0, per_interval = _interval_mpos(operator, ep.n_steps)
+    eng = BatchedTJM(K, length, len(idx), mpo0, ep, procs, obs, tensors, scheduled_jumps=sched, extra_mpos=per_interval or ())
     if rng_mode == "philox":
         tu, su = philox_tables(K, sim_params.random_seed, idx, ep.n_times, ep.order, dev, sample_offset=sample_timestep_offset)
     elif rng_mode == "numpy":
@@ -93,17 +109,25 @@ def run_batch(traj_indices: Sequence[int], initial_state, noise_model: NoiseMode
         if trajectory_rngs is not None:
             if len(trajectory_rngs) != len(idx):
                 raise ValueError("trajectory_rngs must hold one Generator per trajectory")
+            tu = np.empty((len(idx), 2 * (ep.n_times + 1)))
+            rewind = [g.bit_generator.state for g in trajectory_rngs]
             for row, g in enumerate(trajectory_rngs):
-                tu[row] = _generator_table(g, ep.n_times)
+                tu[row] = _generator_table(g, ep.n_times + 1)
         tu = torch.from_numpy(tu).to(dev)
         su = torch.from_numpy(su).to(dev) if su is not None else None
     else:
         raise ValueError("rng_mode must be 'numpy' or 'philox'")
-    results, diag = eng.run(tu, su, None)
+    results, diag = eng.run(tu, su, None, sample_at=sample_at, continue_trajectory=continue_trajectory, interval_mpos=per_interval,
+                            final_sample_from_trajectory_stream=use_trajectory_rng_for_final_sample and trajectory_rngs is not None)
     status = eng.status.cpu().numpy()
+    if rng_mode == "numpy" and trajectory_rngs is not None:
+        for g, state0, used in zip(trajectory_rngs, rewind, eng._pos.cpu().tolist()):
+            g.bit_generator.state = state0
+            if used:
+                g.random(int(used))
     final = None
     if return_states:
-        st = eng.psi if ep.order == 2 and ep.n_times > 1 else eng.phi
+        st = eng.psi if ep.order == 2 and ep.n_times > 1 and not return_trajectory_state else eng.phi
         final = [st.download(b) for b in range(len(idx))]
     return results.cpu().numpy(), diag.cpu().numpy(), status, final
 
@@ -112,14 +136,19 @@ def _single(args, order: int, *, copy_initial_state, rng, sample_timestep_offset
             continue_trajectory, sample_at, kernels):
     traj_idx, initial_state, noise_model, sim_params, operator = args
     del copy_initial_state                         # the batched engine uploads a copy; the caller's MPS is never mutated
-    if use_trajectory_rng_for_final_sample or return_trajectory_state or continue_trajectory or sample_at is not None:
-        raise NotImplementedError("segment hand-off options of SimulationProgram execution (SURVEY.md 8f rank 3) are not on the B200 path yet")
+    if order == 1 and (use_trajectory_rng_for_final_sample or return_trajectory_state or continue_trajectory or sample_timestep_offset):
+        raise TypeError("analog_tjm_1 takes copy_initial_state, rng and sample_at only (analog_tjm.py:369-376)")
+    if sample_at is not None and len(sim_params.times) - 1 not in frozenset(sample_at) and sim_params.get_state and not return_trajectory_state:
+        raise NotImplementedError("get_state with a sample_at that omits the final time (the unrecorded physical copy of analog_tjm.py:"
+                                  "293-309) is not on the B200 path")
     want = 2 if sim_params.order != 1 else 1
     if want != order:
         raise ValueError(f"analog_tjm_{order} called with AnalogSimParams(order={sim_params.order})")
     res, diag, status, final = run_batch([traj_idx], initial_state, noise_model, sim_params, operator, kernels=kernels,
                                          trajectory_rngs=None if rng is None else [rng], sample_timestep_offset=sample_timestep_offset,
-                                         return_states=bool(sim_params.get_state))
+                                         return_states=bool(sim_params.get_state) or return_trajectory_state, sample_at=sample_at,
+                                         continue_trajectory=continue_trajectory, return_trajectory_state=return_trajectory_state,
+                                         use_trajectory_rng_for_final_sample=use_trajectory_rng_for_final_sample)
     if int(status[0]) != 0:
         raise RuntimeError(f"device status word {int(status[0])} for trajectory {traj_idx} (bit 1: SVD not converged, bit 2: non-finite "
                            "singular values, bit 4: zero jump weights)")

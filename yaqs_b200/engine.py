@@ -1096,7 +1096,7 @@ class BatchedTJM:
     # ------------------------------------------------------------------------------------------------------------------
     def run(self, traj_uniforms: torch.Tensor | None, sample_uniforms: torch.Tensor | None, log: list | None = None, *,
             start_pos: torch.Tensor | None = None, sample_at: Sequence[int] | None = None, continue_trajectory: bool = False,
-            interval_mpos: Sequence[Sequence[np.ndarray]] | None = None):
+            interval_mpos: Sequence[Sequence[np.ndarray]] | None = None, final_sample_from_trajectory_stream: bool = False):
         """Run all time steps.  traj_uniforms: [B, >= 2*n_times] trajectory stream (consumed 1 or 2 per jump test);
         sample_uniforms: [B, n_times, 2] per-timestep measurement streams (order 2).  Returns (results [B, n_obs, T],
         diagnostics [B, 3, T]) as device tensors.
@@ -1107,7 +1107,8 @@ class BatchedTJM:
         ``sample_timesteps`` rule (:50-62); ``continue_trajectory`` -- order 2 only: the loaded state is a mid-Trotter phi, the
         junction is re-measured and ``initialize`` is skipped (:312-324); ``interval_mpos`` -- one MPO per interval of the grid
         (merged segments with different Hamiltonians): step j evolves with interval j-1 (order 1), with j-2 for step_through and
-        j-1 for its measurement copy (order 2, :343-360)."""
+        j-1 for its measurement copy (order 2, :343-360); ``final_sample_from_trajectory_stream`` -- order 2: the measurement copy
+        of the last time draws from the trajectory stream instead of its own sample stream (:271-279)."""
         p = self.p
         nt = p.n_times
         ncol = nt if p.sample_timesteps else 1
@@ -1166,6 +1167,8 @@ class BatchedTJM:
                 self.apply_dissipation(psi, p.dt / 2)
                 if self.noise is None:
                     self.stochastic_process(psi, p.dt, None, None, log, f"sample{j}")
+                elif final_sample_from_trajectory_stream and j == nt - 1:
+                    traj_jump_test(psi, f"sample{j}")
                 else:
                     self.stochastic_process(psi, p.dt, sample_uniforms[:, j, 0].contiguous(), sample_uniforms[:, j, 1].contiguous(), log, f"sample{j}")
                 record(psi, j if p.sample_timesteps else 0)
