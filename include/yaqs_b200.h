@@ -140,6 +140,12 @@ int yb_copy_packed(int nbatch, const int32_t* mask, yb_extent e0, yb_extent e1, 
  * (dissipation.py:125-126, stochastic_process.py:255,262-263, digital_tjm.py:304-309). */
 int yb_apply_local_op(int nbatch, const int32_t* mask, const int32_t* sel, int sel_value, yb_extent el, yb_extent er, int dphys,
                       const void* op, int64_t op_stride, void* a, int64_t stride_a, int max_lr, void* stream);
+/* dst[s, (l a), (r b)] = sum_t w[s, t, a, b] src[t, l, r]: one site of MPO.multiply on an MPS (mpo.py:1511-1537,
+ * mpo_utils.py:27-56, the gate-MPO route of digital_tjm.py:536-556).  src is the packed (dphys, l, r) site tensor with l = el[b],
+ * r = er[b]; dst receives the packed (dphys, l * d_left, r * d_right) tensor (MPS bond index major) and must not alias src; w is the
+ * (dphys, dphys, d_left, d_right) MPO site tensor shared by all trajectories.  max_out_lr bounds l * d_left * r * d_right. */
+int yb_mpo_site_apply(int nbatch, const int32_t* mask, yb_extent el, yb_extent er, int dphys, int d_left, int d_right, const void* w,
+                      const void* src, int64_t stride_src, void* dst, int64_t stride_dst, int max_out_lr, void* stream);
 /* out[b] = sum |a|^2 over the packed tensor (MPS.norm at the centre site, mps.py:1539-1565). */
 int yb_norm2(int nbatch, const int32_t* mask, yb_extent el, yb_extent er, int dphys, const void* a, int64_t stride_a, double* out,
              void* stream);

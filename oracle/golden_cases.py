@@ -213,6 +213,14 @@ DIGITAL_CASES = {
     "dig_ising6_periodic_swaps": dict(L=6, J=1.0, g=0.8, dt=0.25, timesteps=3, periodic=True, chi=8, thr=1e-9, ntraj=4, seed=12,
                                       init="x+", obs="z+zz", sample=True, gate_mode="swaps",
                                       noise=[("lowering", 0.05), ("pauli_x", 0.04)]),
+    # the default long-range route (gate_mode="mpo", digital_tjm.py:536-556): MPO.from_gate(rzz(0, L-1)).multiply(state, compress=True)
+    # -- bonds chi * D before the compression sweep -- noisy, capped bonds, sampled
+    "dig_ising6_periodic_mpo": dict(L=6, J=1.0, g=0.8, dt=0.25, timesteps=3, periodic=True, chi=8, thr=1e-9, ntraj=4, seed=15,
+                                    init="x+", obs="z+zz", sample=True, gate_mode="mpo",
+                                    noise=[("lowering", 0.05), ("pauli_x", 0.04)]),
+    # the same route without noise and without a bond cap (one deterministic trajectory)
+    "dig_ising5_periodic_mpo_noiseless": dict(L=5, J=1.0, g=0.7, dt=0.3, timesteps=4, periodic=True, chi=None, thr=1e-10, ntraj=1, seed=1,
+                                              init="zeros", obs="x+z", sample=True, gate_mode="mpo", noise=[]),
 }
 
 

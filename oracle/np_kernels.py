@@ -378,6 +378,17 @@ class NumpyKernels:
             v = _view(a, t, dphys * l * r).reshape(dphys, l * r)
             v[:] = o @ v
 
+    def mpo_site_apply(self, nbatch, mask, el, er, dphys, d_left, d_right, w, src, dst, max_out_lr):
+        self._launches += 1
+        wt = _np(w)[: dphys * dphys * d_left * d_right].reshape(dphys, dphys, d_left, d_right)
+        for t in range(nbatch):
+            if not _on(mask, t):
+                continue
+            l, r = _ext(el, t), _ext(er, t)
+            a = _view(src, t, dphys * l * r).reshape(dphys, l, r)
+            out = np.einsum("stab,tlr->slarb", wt, a).reshape(-1)
+            _view(dst, t, out.size)[:] = out
+
     def norm2(self, nbatch, mask, el, er, dphys, a, out):
         self._launches += 1
         for t in range(nbatch):

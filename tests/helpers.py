@@ -57,7 +57,8 @@ def digital_engine_for_case(name, kernels, trajectories=None, **kw):
     traj = list(range(cfg["ntraj"])) if trajectories is None else list(trajectories)
     ep = EngineParams(dt=1.0, n_steps=1, order=1, max_bond_dim=cfg["chi"], svd_threshold=cfg["thr"], krylov_tol=p.krylov_tol, digital=True)
     mpo = [np.eye(2, dtype=np.complex128).reshape(2, 2, 1, 1) for _ in range(L)]
-    eng = BatchedTJM(kernels, L, len(traj), mpo, ep, noise if noise is not None else None, obs, init.tensors, **kw)
+    eng = BatchedTJM(kernels, L, len(traj), mpo, ep, noise if noise is not None else None, obs, init.tensors,
+                     bond_factor=BatchedTJM.mpo_route_bond_factor(compiled.layers, cfg["gate_mode"], L), **kw)
     n2q = sum(len(l.even_two_qubit_gates) + len(l.odd_two_qubit_gates) for l in compiled.layers)
     tu, _ = numpy_tables(cfg["seed"], traj, max(n2q, 1), 1)
     return eng, compiled, torch.from_numpy(tu).to(kernels.device), traj, cfg

@@ -401,3 +401,36 @@ def test_heev_clustered_spectra(backends, ks):
         assert np.max(np.abs(E.conj().T @ E - np.eye(k))) < 1e-12 * max(1, k / 16)
         assert np.max(np.abs(mats[t] @ E - E * lam[None, :])) < 2e-13 * max(1, k / 16)
         assert np.max(np.abs(np.sort(lam) - np.linalg.eigvalsh(mats[t]))) < 1e-13 * max(1, k / 16)
+
+
+@pytest.mark.parametrize("dl,dr", [(1, 2), (4, 4), (2, 1), (1, 1)])
+def test_mpo_site_apply_matches_twin(backends, dl, dr):
+    """yb_mpo_site_apply (one site of MPO.multiply on an MPS, mpo_utils.py:27-56) on ragged bonds with a mask: bit-comparable sums of
+    at most two products per element, and against the plain einsum of the definition."""
+    cuda, twin = backends
+    rng = np.random.default_rng(31 + dl * 7 + dr)
+    nb, d, cap = 7, 2, 9
+    ext = torch.from_numpy(rng.integers(1, cap + 1, size=(nb, 2)).astype(np.int32))
+    mask = torch.tensor([1, 1, 0, 1, 1, 1, 1], dtype=torch.int32)
+    slot_in, slot_out = d * cap * cap, d * cap * dl * cap * dr
+    a = _rand_c(rng, nb * slot_in)
+    w = _rand_c(rng, d * d * dl * dr)
+    res = {}
+    for name, kern, dev in (("cpu", twin, "cpu"), ("gpu", cuda, "cuda")):
+        e, m = ext.to(dev), mask.to(dev)
+        out = torch.zeros(nb * slot_out, dtype=torch.complex128, device=dev)
+        kern.mpo_site_apply(nb, m, Ext(e, 0, 2), Ext(e, 1, 2), d, dl, dr, w.to(dev), Buf(a.clone().to(dev), 0, slot_in), Buf(out, 0, slot_out),
+                            cap * dl * cap * dr)
+        res[name] = out
+    torch.cuda.synchronize()
+    _cmp(res["cpu"], res["gpu"], tol=1e-14)
+    got = res["gpu"].cpu().numpy()
+    wt = w.numpy().reshape(d, d, dl, dr)
+    for b in range(nb):
+        l, r = int(ext[b, 0]), int(ext[b, 1])
+        seg = got[b * slot_out: b * slot_out + d * l * dl * r * dr]
+        if not mask[b]:
+            assert not seg.any()
+            continue
+        want = np.einsum("stab,tlr->slarb", wt, a.numpy()[b * slot_in: b * slot_in + d * l * r].reshape(d, l, r)).reshape(-1)
+        assert np.max(np.abs(seg - want)) < 1e-13

@@ -200,7 +200,7 @@ def digital_tjm(args, *, compiled_circuit=None, kernels=None):
     mpo = [np.eye(2, dtype=np.complex128).reshape(2, 2, 1, 1) for _ in range(length)]
     procs = list(noise_model.processes) if noise_model is not None else None
     noisy = procs is not None and any(pr["strength"] != 0 for pr in procs)
-    eng = BatchedTJM(K, length, 1, mpo, ep, procs, obs, tensors)
+    eng = BatchedTJM(K, length, 1, mpo, ep, procs, obs, tensors, bond_factor=BatchedTJM.mpo_route_bond_factor(compiled.layers, sp.gate_mode, length))
     n2q = sum(len(l.even_two_qubit_gates) + len(l.odd_two_qubit_gates) for l in compiled.layers)
     tu, _ = numpy_tables(sp.random_seed, [int(traj_idx)], max(n2q, 1), 1)
     res, diag = eng.run_digital(compiled.layers, torch.from_numpy(tu).to(dev), sp.sample_layers, sp.gate_mode, None)

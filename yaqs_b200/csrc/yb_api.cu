@@ -288,6 +288,18 @@ int yb_apply_local_op(int nbatch, const int32_t* mask, const int32_t* sel, int s
     return done("yb_apply_local_op");
 }
 
+int yb_mpo_site_apply(int nbatch, const int32_t* mask, yb_extent el, yb_extent er, int dphys, int d_left, int d_right, const void* w,
+                      const void* src, int64_t stride_src, void* dst, int64_t stride_dst, int max_out_lr, void* stream) {
+    if (nbatch <= 0) return 0;
+    if (dphys > 4) return fail_msg("yb_mpo_site_apply: dphys > 4 unsupported");
+    if (d_left < 1 || d_right < 1) return fail_msg("yb_mpo_site_apply: MPO bond dimensions must be >= 1");
+    if (src == dst) return fail_msg("yb_mpo_site_apply: source and destination must not alias");
+    dim3 grid(grid_for(max_out_lr, 256, 64), nbatch);
+    k_mpo_site_apply<<<grid, 256, 0, (cudaStream_t)stream>>>(dphys, d_left, d_right, (const cplx*)w, (const cplx*)src, stride_src, (cplx*)dst,
+                                                              stride_dst, el.ptr, el.stride, er.ptr, er.stride, mask);
+    return done("yb_mpo_site_apply");
+}
+
 int yb_norm2(int nbatch, const int32_t* mask, yb_extent el, yb_extent er, int dphys, const void* a, int64_t stride_a, double* out, void* stream) {
     if (nbatch <= 0) return 0;
     k_norm2<<<nbatch, 1024, 0, (cudaStream_t)stream>>>(dphys, (const cplx*)a, stride_a, out, el.ptr, el.stride, er.ptr, er.stride, mask);

@@ -66,11 +66,12 @@ def run_digital(simulator, initial_state, operator, sp, noise, result):
     stats: dict = {}
     log_all = [] if simulator.collect_log else None
     measurements_local: dict[int, dict[int, int]] = {}
-    wave = simulator._wave_size(len(mine), length, ep, mpo, init, dev)
+    bond_factor = BatchedTJM.mpo_route_bond_factor(compiled.layers, sp.gate_mode, length)      # head-room of the gate-MPO route
+    wave = simulator._wave_size(len(mine), length, ep, mpo, init, dev, bond_factor=bond_factor)
     K.launch_count(reset=True)
     for w0 in range(0, len(mine), max(wave, 1)):
         idx = list(mine[w0: w0 + wave])
-        eng = BatchedTJM(K, length, len(idx), mpo, ep, procs, obs, init)
+        eng = BatchedTJM(K, length, len(idx), mpo, ep, procs, obs, init, bond_factor=bond_factor)
         if simulator.rng_mode == "numpy":
             tu, _ = numpy_tables(sp.random_seed, idx, max(n2q, 1), 1)
             tu = torch.from_numpy(tu).to(dev)

@@ -71,7 +71,10 @@ class JumpProcess:
 class BatchLayout:
     """Slot capacities and offsets of the per-trajectory tensors (DESIGN.md "Data layout in HBM")."""
 
-    def __init__(self, length: int, nbatch: int, chi_cap: int | None, mpo_bonds: Sequence[int], init_bonds: Sequence[int], d: int = 2):
+    def __init__(self, length: int, nbatch: int, chi_cap: int | None, mpo_bonds: Sequence[int], init_bonds: Sequence[int], d: int = 2,
+                 bond_factor: Sequence[int] | None = None):
+        """``bond_factor``: per-bond multiplier of the slot capacity (second capacity of the gate-MPO route: between
+        ``MPO.multiply`` and the compression sweep a bond inside the gate support holds chi * D_gate, mpo.py:1534-1549)."""
         self.L, self.B, self.d = length, nbatch, d
         natural = [d ** min(j, length - j) for j in range(length + 1)]
         if chi_cap is None:
@@ -81,6 +84,8 @@ class BatchLayout:
         else:
             cap = [min(chi_cap, n) for n in natural]
         self.cap = [max(c, int(b)) for c, b in zip(cap, init_bonds)]
+        if bond_factor is not None:
+            self.cap = [c * max(1, int(f)) for c, f in zip(self.cap, bond_factor)]
         self.cap[0] = self.cap[length] = 1
         self.D = [int(x) for x in mpo_bonds]                       # MPO bond dims, D[0] = D[L] = 1 for open chains
         self.slot = [d * self.cap[i] * self.cap[i + 1] for i in range(length)]
@@ -178,7 +183,7 @@ class BatchedTJM:
     def __init__(self, kernels, length: int, nbatch: int, mpo: Sequence[np.ndarray], params: EngineParams,
                  noise: Sequence[dict] | None, observables: Sequence[tuple[np.ndarray, Sequence[int]]],
                  init_tensors, svd_block_rows: int | None = None, gram_min_k: int = 33, scheduled_jumps: Sequence[dict] | None = None,
-                 extra_mpos: Sequence[Sequence[np.ndarray]] = ()):
+                 extra_mpos: Sequence[Sequence[np.ndarray]] = (), bond_factor: Sequence[int] | None = None):
         """``init_tensors``: one MPS (list of (d, l, r) arrays, broadcast), one MPS per trajectory, or the BatchedState of another
         engine (device-to-device hand-off between SimulationProgram segments).  ``extra_mpos``: further MPOs this engine will be
         switched to (``run(interval_mpos=...)``); the layout takes the per-bond maximum of their bond dimensions and every MPO is
@@ -204,7 +209,7 @@ class BatchedTJM:
         for other in extra_mpos:
             ob = [int(other[0].shape[2])] + [int(w.shape[3]) for w in other]
             mpo_bonds = [max(a, b) for a, b in zip(mpo_bonds, ob)]
-        self.lay = BatchLayout(length, nbatch, params.max_bond_dim, mpo_bonds, init_bonds)
+        self.lay = BatchLayout(length, nbatch, params.max_bond_dim, mpo_bonds, init_bonds, bond_factor=bond_factor)
         lay = self.lay
         dev = self.dev
         self.phi = BatchedState(lay, dev)
@@ -1302,6 +1307,80 @@ class BatchedTJM:
         self.split_theta(st, left, "right", trunc, fast=True)
         return left + 1
 
+    @staticmethod
+    def gate_support_mpo(gate) -> list[np.ndarray]:
+        """get_support_mpo / extend_gate / split_tensor for a two-qubit gate (mpo_utils.py:166-216, gate_library.py:25-126): the
+        gate tensor in ascending site order, legs grouped per site, one SVD with the singular values carried to the right and the
+        reference's hard cut-off 1e-6 (min_keep 1); identity tensors of the carried bond between the two sites.  Returns the
+        (2, 2, Dl, Dr) tensors for sites min(sites) .. max(sites)."""
+        first, last = min(gate.sites), max(gate.sites)
+        t = BatchedTJM._resolve_lr_matrix(gate).reshape(2, 2, 2, 2)                  # [o_left, o_right, i_left, i_right]
+        u, sv, vh = np.linalg.svd(np.transpose(t, (0, 2, 1, 3)).reshape(4, 4), full_matrices=False)
+        keep = max(int(np.sum(sv > 1e-6)), 1)
+        tensors = [np.transpose(u[:, :keep].reshape(1, 2, 2, keep), (1, 2, 0, 3))]
+        for _ in range(first + 1, last):
+            ident = np.zeros((2, 2, keep, keep), dtype=np.complex128)
+            for k in range(keep):
+                ident[:, :, k, k] = np.eye(2)
+            tensors.append(ident)
+        tensors.append(np.transpose((np.diag(sv[:keep]) @ vh[:keep]).reshape(keep, 2, 2), (1, 2, 0))[:, :, :, None])
+        return [np.ascontiguousarray(w, dtype=np.complex128) for w in tensors]
+
+    @staticmethod
+    def mpo_route_bond_factor(layers, gate_mode: str, length: int) -> list[int] | None:
+        """Per-bond capacity multiplier a circuit needs on the gate-MPO route (None when no gate takes it): the operator-Schmidt
+        rank of every non-adjacent two-qubit gate that ``run_digital`` will send through ``apply_long_range_gate_mpo``."""
+        factor = [1] * (length + 1)
+        for layer in layers:
+            for gate in (*layer.even_two_qubit_gates, *layer.odd_two_qubit_gates):
+                if gate.interaction != 2 or abs(gate.sites[0] - gate.sites[1]) == 1 or gate_mode == "swaps":
+                    continue
+                if gate_mode in ("tdvp", "full-tdvp") and getattr(gate, "generator", None) is not None:
+                    continue
+                rank = BatchedTJM.gate_support_mpo(gate)[0].shape[3]
+                for j in range(min(gate.sites) + 1, max(gate.sites) + 1):
+                    factor[j] = max(factor[j], rank)
+        return factor if max(factor) > 1 else None
+
+    def apply_long_range_gate_mpo(self, st: BatchedState, gate) -> int:
+        """apply_long_range_gate_mpo (digital_tjm.py:536-556): ``MPO.from_gate(gate).multiply(state, compress=True)`` for the whole
+        batch.  (1) every support site A <- W.A with fused bonds (yb_mpo_site_apply; sites outside the support see the identity
+        and are left alone); (2) ``MPS.compress`` (mps.py:841-899): right-canonical gauge without truncation, one left-to-right
+        sweep of merged two-site SVDs under the user's truncation policy (min_keep 1), centre moved back without truncation.
+        The reference restores the centre ``check_canonical_form`` finds on the un-gauged product, else L // 2; a gate's
+        operator-Schmidt factors are not isometries on both of its sites, so the fallback is what it takes -- used here for
+        every trajectory (the choice is a gauge, it does not enter any observable).  Returns the new centre."""
+        lay, K, B, d, n, p = self.lay, self.K, self.B, self.d, self.L, self.p
+        first, last = min(gate.sites), max(gate.sites)
+        key = ("gate-mpo", gate.name, tuple(gate.sites), np.asarray(gate.matrix, dtype=np.complex128).tobytes())
+        if key not in self._mpo_cache:
+            self._mpo_cache[key] = [torch.from_numpy(w.reshape(-1)).to(self.dev) for w in self.gate_support_mpo(gate)]
+        ws = self._mpo_cache[key]
+        rank = ws[0].numel() // 4
+        old = st.bond.clone()
+        grown = old[:, first + 1: last + 1] * rank
+        if bool((grown.max(dim=0).values.cpu() > torch.tensor(lay.cap[first + 1: last + 1])).any()):
+            raise ValueError("gate-MPO route: chi * D_gate exceeds the slot capacity; build the engine with bond_factor="
+                             "BatchedTJM.mpo_route_bond_factor(layers, gate_mode, length)")
+        st.bond[:, first + 1: last + 1] = grown.to(st.bond.dtype)
+        tmp = self._buf(self.tmp, lay.nloc_max)
+        for s in range(first, last + 1):
+            dl = 1 if s == first else rank
+            dr = 1 if s == last else rank
+            K.mpo_site_apply(B, None, Ext(old, s, n + 1), Ext(old, s + 1, n + 1), d, dl, dr, ws[s - first], st.site(s), tmp, lay.cap[s] * lay.cap[s + 1])
+            K.copy_packed(B, None, st.ext(s), st.ext(s + 1), d, tmp, st.site(s), lay.slot[s])
+        keep_all = self._trunc_args("discarded_weight", 0.0, None, 1)
+        for i in reversed(range(1, n)):                     # set_canonical_form(0, "QR")
+            self.shift_left(st, i, keep_all, fast=True)
+        user = self._trunc_args(p.trunc_mode, p.svd_threshold, p.max_bond_dim, 1)
+        for i in range(n - 1):
+            self.merge(st, i)
+            self.split_theta(st, i, "right", user, fast=True)
+        target = n // 2
+        for i in range(n - 1, target, -1):
+            self.shift_left(st, i, keep_all, fast=True)
+        return target
+
     def apply_two_qubit_gate_tdvp(self, st: BatchedState, gate) -> int:
         """apply_two_qubit_gate_tdvp (digital_tjm.py:324-452), entered with the centre at 0: generator MPO of bond
         dimension 1, window = support +- 1 site, one symmetric 2TDVP sweep over the window with evolution time 1.
@@ -1391,9 +1470,8 @@ class BatchedTJM:
                             centre = self.apply_two_qubit_gate_tebd(st, gate)
                         elif gate_mode == "tdvp" and has_gen:
                             centre = self.apply_two_qubit_gate_tdvp(st, gate)
-                        else:
-                            raise NotImplementedError(f"long-range gate in gate_mode={gate_mode!r}: the gate-MPO route (MPO.from_gate + multiply + "
-                                                      "compress) is a SURVEY.md 8(f) 'next' row; use gate_mode='tdvp' or 'swaps'")
+                        else:                                   # gate_mode "mpo", or a generator-free gate in a TDVP mode
+                            centre = self.apply_long_range_gate_mpo(st, gate)
                         if not noisy:
                             keep_all = self._trunc_args("discarded_weight", 0.0, None, 1)     # normalize("B", "QR")
                             for i in reversed(range(1, centre + 1)):

@@ -70,7 +70,7 @@ def load_library() -> ctypes.CDLL:
 EXPORTED_SYMBOLS = [
     "yb_last_error", "yb_version", "yb_launch_count", "yb_set_flop_counter", "yb_set_option", "yb_gemm", "yb_wapply", "yb_env_identity", "yb_lanczos_init",
     "yb_lanczos_step", "yb_lanczos_combine", "yb_svd_prepare", "yb_svd_round", "yb_svd_check", "yb_svd_finalize", "yb_heev", "yb_svd_select", "yb_svd_gather",
-    "yb_unpack_vh", "yb_copy_packed", "yb_apply_local_op", "yb_norm2", "yb_scale", "yb_local_rdm", "yb_philox_uniform",
+    "yb_unpack_vh", "yb_copy_packed", "yb_apply_local_op", "yb_mpo_site_apply", "yb_norm2", "yb_scale", "yb_local_rdm", "yb_philox_uniform",
 ]
 
 
@@ -242,6 +242,13 @@ class CudaKernels:
         self._check(self.lib.yb_apply_local_op(nbatch, self._ptr(mask), self._ptr(sel), int(sel_value), self._ext(el), self._ext(er), dphys,
                                                self._ptr(op), ctypes.c_int64(op_stride), self._cptr(a), ctypes.c_int64(a.stride), int(max_lr),
                                                self._stream()))
+
+    def mpo_site_apply(self, nbatch, mask, el, er, dphys, d_left, d_right, w: torch.Tensor, src: Buf, dst: Buf, max_out_lr):
+        if w.dtype != torch.complex128:
+            raise KernelError(f"mpo_site_apply: complex128 MPO tensor expected, got {w.dtype}")
+        self._check(self.lib.yb_mpo_site_apply(nbatch, self._ptr(mask), self._ext(el), self._ext(er), dphys, int(d_left), int(d_right), self._ptr(w),
+                                               self._cptr(src), ctypes.c_int64(src.stride), self._cptr(dst), ctypes.c_int64(dst.stride),
+                                               int(max_out_lr), self._stream()))
 
     def norm2(self, nbatch, mask, el, er, dphys, a: Buf, out):
         self._check(self.lib.yb_norm2(nbatch, self._ptr(mask), self._ext(el), self._ext(er), dphys, self._cptr(a), ctypes.c_int64(a.stride),

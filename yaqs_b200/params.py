@@ -30,8 +30,11 @@ class Observable:
     def __init__(self, gate, sites=None, **gate_kwargs) -> None:
         if isinstance(gate, str):
             if gate == "schmidt_spectrum":
-                raise NotImplementedError("observable 'schmidt_spectrum' (vector-valued, order-1 object arrays in the reference) is a "
-                                          "SURVEY.md 8(f) 'next' row of the B200 TJM path")
+                # the reference's own Simulator.run cannot store it either: _store_observable_trajectory (simulator.py:932-942) assigns
+                # the 500-vector into a float row and raises "setting an array element with a sequence" (checked against the
+                # unmodified reference); MPS.get_schmidt_spectrum works only when called directly
+                raise NotImplementedError("observable 'schmidt_spectrum' is vector-valued; the reference's Simulator.run raises ValueError for "
+                                          "it (simulator.py:942), so there is no behaviour to reproduce on the B200 TJM path")
             if gate != "pvm" and hasattr(GateLibrary, gate):
                 resolved = getattr(GateLibrary, gate)(**gate_kwargs)
             else:                                     # simulation_parameters.py:388-400: any other string is a PVM bitstring

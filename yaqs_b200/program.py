@@ -453,13 +453,17 @@ def run_program(simulator, initial_state: State, program: SimulationProgram, noi
     stats: dict = {}
     n_tests = 1 + sum(u.n_steps + 1 if u.kind == "analog" else _n_two_qubit(u.instructions[0].compiled_circuit) for u in units)
     ident = [np.eye(2, dtype=np.complex128).reshape(2, 2, 1, 1) for _ in range(length)]
+    def sp_layers(unit):
+        return unit.instructions[0].compiled_circuit.layers
+
     # waves: the most demanding unit decides how many trajectories fit (states of two engines coexist only during a hand-over)
     wave = len(mine)
     for u in units:
         sp = u.instructions[0].execution_params
         ep = _engine_params(sp, u.n_steps, True)
         mpo = ident if u.kind == "digital" else u.instructions[0].hamiltonian.tensors
-        wave = min(wave, simulator._wave_size(len(mine), length, ep, mpo, initial_state.mps.tensors, dev))
+        factor = BatchedTJM.mpo_route_bond_factor(sp_layers(u), sp.gate_mode, length) if u.kind == "digital" else None
+        wave = min(wave, simulator._wave_size(len(mine), length, ep, mpo, initial_state.mps.tensors, dev, bond_factor=factor))
     wave = max(wave, 1)
     K.launch_count(reset=True)
     for w0 in range(0, len(mine), wave):
@@ -480,7 +484,8 @@ def run_program(simulator, initial_state: State, program: SimulationProgram, noi
                 ep = _engine_params(sp, 1, True)
                 if ep.tdvp_mode != "2site":
                     raise ValueError(f'apply_two_qubit_gate_tdvp only supports tdvp_mode="2site"; got {ep.tdvp_mode!r}.')
-                new = BatchedTJM(K, length, len(idx), ident, ep, list(procs) if procs is not None else None, obs, carried)
+                new = BatchedTJM(K, length, len(idx), ident, ep, list(procs) if procs is not None else None, obs, carried,
+                                 bond_factor=BatchedTJM.mpo_route_bond_factor(first.compiled_circuit.layers, sp.gate_mode, length))
                 r, dg = new.run_digital(first.compiled_circuit.layers, tu, sp.sample_layers, sp.gate_mode, None, start_pos=pos)
                 out_state = new.phi
                 if sp.shots is not None:             # _per_call_shots with shot_distribution = (shots, ntraj) (digital_tjm.py:752-768)

@@ -253,7 +253,7 @@ class Simulator:
             raise RuntimeError(f"device status words non-zero for trajectories {bad[:8].tolist()} (bit 1: Jacobi SVD not converged, "
                                "bit 2: non-finite singular values, bit 4: zero jump weights)")
 
-    def _wave_size(self, n: int, length: int, ep: EngineParams, mpo, init, dev) -> int:
+    def _wave_size(self, n: int, length: int, ep: EngineParams, mpo, init, dev, bond_factor=None) -> int:
         if n == 0:
             return 0
         if self.batch_size is not None:
@@ -263,7 +263,7 @@ class Simulator:
             init_bonds[i] = max(init_bonds[i], t.shape[1])
             init_bonds[i + 1] = max(init_bonds[i + 1], t.shape[2])
         mpo_bonds = [int(mpo[0].shape[2])] + [int(w.shape[3]) for w in mpo]
-        one = BatchLayout(length, 1, ep.max_bond_dim, mpo_bonds, init_bonds)
+        one = BatchLayout(length, 1, ep.max_bond_dim, mpo_bonds, init_bonds, bond_factor=bond_factor)
         per = bytes_per_trajectory(one, ep.order, ep.tdvp_mode == "1site")
         if torch.device(dev).type == "cuda":
             free, _total = torch.cuda.mem_get_info(dev)
