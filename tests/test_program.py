@@ -205,3 +205,39 @@ def test_program_two_rank_gloo_sharding_matches_single_process(golden_dir):
         assert np.array_equal(a, np.asarray(seg.trajectories[0]))
     assert np.max(np.abs(mean0 - single.expectation_values[0])) < 1e-14
     assert counts == _shots_program_run().counts
+
+
+def test_piecewise_hamiltonian_equals_the_merged_program_fixture(golden_dir):
+    """Hamiltonian.piecewise (hamiltonian.py:176-232) expands to one MPO per interval (simulation_program.py:490-547), which is what
+    the reference's executor builds when it merges the two segments of prog_quench_merged_o2: a standalone run of the piecewise
+    Hamiltonian and a one-segment program of it reproduce that fixture's columns (trajectory stream and sample streams coincide)."""
+    from oracle.np_kernels import NumpyKernels
+    cfg = PROGRAM_CASES["prog_quench_merged_o2"]
+    g = np.load(os.path.join(golden_dir, "prog_quench_merged_o2.npz"))
+    L = cfg["L"]
+    a, b = cfg["segments"]
+    pw = Y.Hamiltonian.piecewise([(Y.Hamiltonian.ising(L, a["J"], a["g"]), a["T"]), (Y.Hamiltonian.ising(L, b["J"], b["g"]), b["T"])])
+    assert pw.is_piecewise and pw.duration == pytest.approx(0.5) and len(pw.pieces) == 2
+    with pytest.raises(ValueError, match="no single static operator"):
+        pw.mpo
+    prog, state, noise = build_program(cfg)
+    obs = list(prog.observables)
+    to_sorted = prepare_observable_ordering(obs)[1]
+    want = np.concatenate([g["res_0"], g["res_1"][:, :, 1:]], axis=2)                       # [traj, sorted obs, 6 columns]
+    sim = Y.Simulator(show_progress=False, kernels=NumpyKernels())
+    sp = Y.AnalogSimParams(observables=obs, elapsed_time=0.5, dt=0.1, num_traj=cfg["ntraj"], max_bond_dim=a["chi"], svd_threshold=a["thr"],
+                           order=2, sample_timesteps=True, random_seed=cfg["seed"])
+    res = sim.run(state, pw, sp, noise)
+    for i in range(len(obs)):
+        assert np.max(np.abs(np.asarray(res.trajectories[i]) - want[:, to_sorted[i]])) < 1e-10
+    seg_sp = Y.AnalogSimParams(elapsed_time=0.5, dt=0.1, num_traj=cfg["ntraj"], max_bond_dim=a["chi"], svd_threshold=a["thr"], order=2)
+    res2 = sim.run(state, [(pw, seg_sp)], None, noise, observables=obs, random_seed=cfg["seed"])
+    for i in range(len(obs)):
+        assert np.max(np.abs(np.asarray(res2.segment_results[0].trajectories[i]) - want[:, to_sorted[i]])) < 1e-10
+    with pytest.raises(ValueError, match="must sum to elapsed_time"):
+        sim.run(state, pw, Y.AnalogSimParams(observables=obs, elapsed_time=0.4, dt=0.1, order=2), noise)
+    with pytest.raises(ValueError, match="integer multiple of dt"):
+        sim.run(state, Y.Hamiltonian.piecewise([(Y.Hamiltonian.ising(L, 1.0, 0.5), 0.25)]),
+                Y.AnalogSimParams(observables=obs, elapsed_time=0.3, dt=0.1, order=2), noise)
+    with pytest.raises(ValueError, match="nested piecewise"):
+        Y.Hamiltonian.piecewise([(pw, 0.1)])

@@ -227,12 +227,13 @@ class State:
 
 
 class Hamiltonian:
-    """Analog operator wrapper (hamiltonian.py:36-441): factories delegate to :class:`MPO`."""
+    """Analog operator wrapper (hamiltonian.py:36-441): factories delegate to :class:`MPO`; ``piecewise`` switches static
+    pieces on the analog ``dt`` grid (:176-263)."""
 
     def __init__(self, mpo: MPO) -> None:
         self._mpo = mpo
+        self._pieces: tuple | None = None
         self.length = mpo.length
-        self.is_piecewise = False
 
     @classmethod
     def from_mpo(cls, mpo: MPO) -> "Hamiltonian":
@@ -250,15 +251,68 @@ class Hamiltonian:
     def pauli(cls, **kw) -> "Hamiltonian":
         return cls(MPO.pauli(**kw))
 
+    @classmethod
+    def piecewise(cls, pieces) -> "Hamiltonian":
+        """hamiltonian.py:176-232: ``[(Hamiltonian, duration), ...]``; durations must be positive multiples of ``dt`` that sum to
+        ``elapsed_time`` (checked when the run expands them to one MPO per interval)."""
+        from collections.abc import Sequence as _Seq
+        if isinstance(pieces, (str, bytes)) or not isinstance(pieces, _Seq):
+            raise TypeError("pieces must be a non-empty sequence of (Hamiltonian, duration) pairs.")
+        raw = tuple(pieces)
+        if not raw:
+            raise ValueError("pieces must be a non-empty sequence of (Hamiltonian, duration) pairs.")
+        normalized, length = [], None
+        for index, item in enumerate(raw):
+            if not isinstance(item, tuple) or len(item) != 2:
+                raise TypeError(f"pieces[{index}] must be a (Hamiltonian, duration) tuple.")
+            ham, duration = item
+            if not isinstance(ham, Hamiltonian):
+                raise TypeError(f"pieces[{index}] must start with a Hamiltonian, got {type(ham).__name__}.")
+            if ham.is_piecewise:
+                raise ValueError("pieces must be static Hamiltonians, not nested piecewise Hamiltonians.")
+            if isinstance(duration, bool) or not isinstance(duration, (int, float, np.floating, np.integer)):
+                raise TypeError(f"pieces[{index}] duration must be a real number, got {type(duration).__name__}.")
+            dur = float(duration)
+            if not np.isfinite(dur) or dur <= 0.0:
+                raise ValueError(f"pieces[{index}] duration must be finite and positive, got {dur}.")
+            if length is None:
+                length = ham.length
+            elif ham.length != length:
+                raise ValueError(f"pieces[{index}] length {ham.length} does not match piece 0 length {length}.")
+            normalized.append((ham, dur))
+        wrapped = cls.__new__(cls)
+        wrapped._mpo, wrapped._pieces, wrapped.length = None, tuple(normalized), length
+        return wrapped
+
+    @property
+    def is_piecewise(self) -> bool:
+        return getattr(self, "_pieces", None) is not None
+
+    @property
+    def pieces(self) -> tuple:
+        if self._pieces is None:
+            raise ValueError("Static Hamiltonians do not have piecewise durations.")
+        return self._pieces
+
+    @property
+    def duration(self) -> float:
+        if self._pieces is None:
+            raise ValueError("Static Hamiltonians do not have a piecewise duration.")
+        return float(sum(d for _, d in self._pieces))
+
     def ensure_mpo(self) -> "Hamiltonian":
+        if self.is_piecewise:
+            raise ValueError("A piecewise Hamiltonian has no single static operator.")
         return self
 
     @property
     def mpo(self) -> MPO:
+        if self.is_piecewise:
+            raise ValueError("A piecewise Hamiltonian has no single static operator.")
         return self._mpo
 
     def to_matrix(self) -> np.ndarray:
-        return self._mpo.to_matrix()
+        return self.mpo.to_matrix()
 
 
 @dataclass

@@ -13,8 +13,8 @@ unit of it is executed for a whole batch of trajectories in lock step by ``engin
 * merged analog runs with different Hamiltonians use one MPO per interval (``run(interval_mpos=...)``), zero-padded to a common
   bond dimension.
 
-Piecewise Hamiltonians inside one segment and the BUG integrator are not on the B200 path (``Hamiltonian.is_piecewise`` is always
-False here); QASM strings / paths need qiskit's parser and are rejected.
+Piecewise Hamiltonians expand to one MPO per interval exactly like merged runs.  The BUG integrator is not on the B200 path; QASM
+strings / paths need qiskit's parser and are rejected.
 """
 from __future__ import annotations
 
@@ -143,7 +143,7 @@ class SimulationProgram:
 @dataclass(frozen=True)
 class _AnalogInstruction:
     index: int
-    hamiltonian: object                 # containers.MPO (static per segment on this path)
+    hamiltonian: object                 # containers.MPO, or a tuple with one MPO per interval (piecewise Hamiltonian)
     sim_params: AnalogSimParams
     execution_params: AnalogSimParams
     noise_model: NoiseModel | None
@@ -214,6 +214,37 @@ def _apply_program_settings(sim_params, observables, num_traj: int, random_seed)
     return execution_params
 
 
+def _duration_to_steps(duration: float, dt: float, label: str) -> int:
+    """simulation_program.py:443-470."""
+    n_steps = round(duration / dt)
+    evolved = n_steps * dt
+    residual = abs(duration - evolved)
+    roundoff_tol = max(np.spacing(duration), abs(n_steps) * np.spacing(dt), 8 * np.finfo(np.float64).eps * max(duration, evolved, dt))
+    if n_steps <= 0 or residual > min(roundoff_tol, 0.25 * dt):
+        raise ValueError(f"{label} ({duration}) must be an integer multiple of dt ({dt}).")
+    return n_steps
+
+
+def expand_analog_operator(hamiltonian: Hamiltonian, sim_params: AnalogSimParams, label: str = ""):
+    """_expand_analog_operator (simulation_program.py:490-547): a static Hamiltonian gives its MPO, a piecewise one a tuple with
+    one MPO reference per analog interval (collapsed to the bare MPO when every interval shares the same object)."""
+    prefix = f"{label} " if label else ""
+    if not hamiltonian.is_piecewise:
+        return hamiltonian.ensure_mpo().mpo
+    dt = float(sim_params.dt)
+    n_intervals = max(len(sim_params.times) - 1, 0)
+    interval_mpos: list = []
+    for index, (piece, duration) in enumerate(hamiltonian.pieces):
+        n_steps = _duration_to_steps(duration, dt, f"{prefix}pieces[{index}] duration")
+        interval_mpos.extend([piece.ensure_mpo().mpo] * n_steps)
+    if len(interval_mpos) != n_intervals:
+        raise ValueError(f"{prefix}piecewise durations must sum to elapsed_time ({sim_params.elapsed_time}); got {len(interval_mpos) * dt}, "
+                         f"expected {sim_params.elapsed_time}.")
+    if interval_mpos and all(m is interval_mpos[0] for m in interval_mpos):
+        return interval_mpos[0]
+    return tuple(interval_mpos)
+
+
 def compile_program(program: SimulationProgram, initial_state: State, default_noise_model: NoiseModel | None = None) -> _CompiledProgram:
     """simulation_program.py:679-755."""
     if initial_state.representation != "mps":
@@ -233,7 +264,8 @@ def compile_program(program: SimulationProgram, initial_state: State, default_no
                 raise ValueError(f"segments[{index}] AnalogSimParams.order must be 1 or 2, got {segment.sim_params.order}.")
             if segment.sim_params.multi_time_observables:
                 raise ValueError(f"segments[{index}] multi_time_observables are not supported in program execution.")
-            instructions.append(_AnalogInstruction(index, segment.hamiltonian.ensure_mpo().mpo, segment.sim_params, params, noise, time_offset))
+            operator = expand_analog_operator(segment.hamiltonian, params, label=f"segments[{index}]")
+            instructions.append(_AnalogInstruction(index, operator, segment.sim_params, params, noise, time_offset))
             time_offset += float(segment.sim_params.elapsed_time)
             continue
         circuit = segment.circuit
@@ -301,6 +333,8 @@ def _same_order2_operator(left: _AnalogInstruction, right: _AnalogInstruction) -
     if left.noise_model is not right.noise_model:
         return False
     lm, rm = left.hamiltonian, right.hamiltonian
+    if isinstance(lm, tuple) or isinstance(rm, tuple):
+        return False
     if lm is rm:
         return True
     if len(lm.tensors) != len(rm.tensors):
@@ -374,15 +408,15 @@ def plan_units(instructions: Sequence) -> list[_Unit]:
         # instruction never does (:392-403)
         hand = _order2_hand_off(instructions, run[-1]) if (order2 or len(run) > 1) else False
         unit = _Unit("analog", run, n_steps=sum(steps), hand_off=hand)
+        mpos = [m for i, n in zip(run, steps) for m in (i.hamiltonian if isinstance(i.hamiltonian, tuple) else (i.hamiltonian,) * n)]
+        if mpos and not all(m is mpos[0] for m in mpos):
+            unit.interval_mpos = [m.tensors for m in mpos]
         if len(run) == 1:
             unit.sample_offset, unit.continue_trajectory = (offset, cont) if order2 else (0, False)
             ncol = len(ins.execution_params.times) if ins.execution_params.sample_timesteps else 1
             unit.columns = [(0, ncol)]
             offset = offset + max(len(ins.execution_params.times) - 1, 0) if hand else 0
         else:                                   # merged run: a fresh Trotter chain on the concatenated grid (simulator.py:514-551)
-            mpos = [i.hamiltonian for i, n in zip(run, steps) for _ in range(n)]
-            if not all(m is mpos[0] for m in mpos):
-                unit.interval_mpos = [m.tensors for m in mpos]
             user_sample = run[0].execution_params.sample_timesteps
             bounds = list(np.cumsum(steps))
             unit.sample_at = None if user_sample else tuple(int(b) for b in bounds)
@@ -407,6 +441,10 @@ def _engine_params(sp, n_steps: int, sample_timesteps: bool) -> EngineParams:
     return EngineParams(dt=sp.dt, n_steps=n_steps, order=2 if sp.order != 1 else 1, max_bond_dim=sp.max_bond_dim, svd_threshold=sp.svd_threshold,
                         trunc_mode=sp.trunc_mode, krylov_tol=sp.krylov_tol, tdvp_mode=sp.tdvp_mode, tdvp_sweeps=sp.tdvp_sweeps,
                         sample_timesteps=sample_timesteps)
+
+
+def _first_mpo(ins: _AnalogInstruction):
+    return ins.hamiltonian[0] if isinstance(ins.hamiltonian, tuple) else ins.hamiltonian
 
 
 def _n_two_qubit(compiled: CompiledCircuit) -> int:
@@ -461,7 +499,7 @@ def run_program(simulator, initial_state: State, program: SimulationProgram, noi
     for u in units:
         sp = u.instructions[0].execution_params
         ep = _engine_params(sp, u.n_steps, True)
-        mpo = ident if u.kind == "digital" else u.instructions[0].hamiltonian.tensors
+        mpo = ident if u.kind == "digital" else _first_mpo(u.instructions[0]).tensors
         factor = BatchedTJM.mpo_route_bond_factor(sp_layers(u), sp.gate_mode, length) if u.kind == "digital" else None
         wave = min(wave, simulator._wave_size(len(mine), length, ep, mpo, initial_state.mps.tensors, dev, bond_factor=factor))
     wave = max(wave, 1)
@@ -507,7 +545,7 @@ def run_program(simulator, initial_state: State, program: SimulationProgram, noi
                 ep = _engine_params(sp, u.n_steps, True if merged else sp.sample_timesteps)
                 sched = first.noise_model.scheduled_jumps if first.noise_model is not None else None
                 extra = u.interval_mpos or ()
-                new = BatchedTJM(K, length, len(idx), first.hamiltonian.tensors, ep, procs, obs, carried, scheduled_jumps=sched, extra_mpos=extra)
+                new = BatchedTJM(K, length, len(idx), _first_mpo(first).tensors, ep, procs, obs, carried, scheduled_jumps=sched, extra_mpos=extra)
                 su = None
                 if ep.order == 2:
                     if simulator.rng_mode == "numpy":

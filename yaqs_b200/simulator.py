@@ -154,7 +154,12 @@ class Simulator:
                           tdvp_sweeps=sp.tdvp_sweeps, sample_timesteps=sp.sample_timesteps)
         procs = noise.processes if noise is not None else None
         sched = noise.scheduled_jumps if noise is not None else None
-        mpo = ham.mpo.tensors
+        from .program import expand_analog_operator
+        if ham.is_piecewise and sp.multi_time_observables:
+            raise ValueError("Piecewise Hamiltonians do not support multi_time_observables.")
+        operator = expand_analog_operator(ham, sp)                  # simulator.py:1517-1534: MPO, or one MPO per interval
+        per_interval = [m.tensors for m in operator] if isinstance(operator, tuple) else None
+        mpo = (operator[0] if isinstance(operator, tuple) else operator).tensors
         init = state.mps.tensors
         ncol = ep.n_times if ep.sample_timesteps else 1
 
@@ -181,7 +186,7 @@ class Simulator:
 
         def run_job(job):
             w0, idx = job
-            eng = BatchedTJM(K, length, len(idx), mpo, ep, procs, obs, init, scheduled_jumps=sched)
+            eng = BatchedTJM(K, length, len(idx), mpo, ep, procs, obs, init, scheduled_jumps=sched, extra_mpos=per_interval or ())
             if self.rng_mode == "numpy":
                 tu, su = numpy_tables(sp.random_seed, idx, ep.n_times, ep.order)
                 tu = torch.from_numpy(tu).to(dev)
@@ -189,7 +194,7 @@ class Simulator:
             else:
                 tu, su = philox_tables(K, sp.random_seed, idx, ep.n_times, ep.order, dev)
             log = [] if self.collect_log else None
-            r, dg = eng.run(tu, su, log)
+            r, dg = eng.run(tu, su, log, interval_mpos=per_interval)
             fin = None
             if sp.get_state and noiseless:
                 fin = (eng.psi if ep.order == 2 and ep.n_times > 1 else eng.phi).download(0)
