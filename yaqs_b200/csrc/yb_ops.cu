@@ -3,6 +3,7 @@
 // kernels: coalesced 16-byte accesses along the fastest (right-bond) index, one launch covers the whole batch.
 #include "yb_common.cuh"
 #include "yb_philox.cuh"
+#include "yb_mpo_apply.cuh"
 #include <math.h>
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -279,28 +280,18 @@ __global__ void k_apply_local_op(int dphys, const cplx* __restrict__ op, long lo
 }
 
 // A'[s, (l a), (r b)] = sum_t W[s, t, a, b] A[t, l, r]: one MPO site tensor applied to one MPS site tensor with the bond
-// indices fused (MPS bond major).  One thread per output matrix element (l a, r b); reads are gathers from a tensor that is
-// Dl * Dr times smaller than the output, writes are coalesced.  dphys <= 4.
+// indices fused (MPS bond major).  One thread per output matrix element (l a, r b) (yb_mpo_apply.cuh); reads are gathers from a
+// tensor that is Dl * Dr times smaller than the output, writes are coalesced.  dphys <= 4.
 __global__ void k_mpo_site_apply(int dphys, int dl, int dr, const cplx* __restrict__ w, const cplx* __restrict__ src, long long s_src, cplx* dst,
                                  long long s_dst, const int* el, int esl, const int* er, int esr, const int* mask) {
     const int b = blockIdx.y;
     if (mask && !mask[b]) return;
     const long long l = el[(long long)b * esl], r = er[(long long)b * esr];
-    const long long lr = l * r, ro_n = r * dr, out_lr = l * dl * ro_n;
+    const long long out_lr = l * dl * r * dr;
     const cplx* a = src + (long long)b * s_src;
     cplx* o = dst + (long long)b * s_dst;
-    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < out_lr; e += (long long)gridDim.x * blockDim.x) {
-        const long long lo = e / ro_n, ro = e - lo * ro_n;
-        const long long li = lo / dl, ri = ro / dr;
-        const int ia = (int)(lo - li * dl), ib = (int)(ro - ri * dr);
-        cplx v[4];
-        for (int t = 0; t < dphys; ++t) v[t] = a[(long long)t * lr + li * r + ri];
-        for (int s = 0; s < dphys; ++s) {
-            cplx acc = make_double2(0.0, 0.0);
-            for (int t = 0; t < dphys; ++t) acc = cfma(w[((s * dphys + t) * dl + ia) * dr + ib], v[t], acc);
-            o[(long long)s * out_lr + e] = acc;
-        }
-    }
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < out_lr; e += (long long)gridDim.x * blockDim.x)
+        mpo_apply::element(e, dphys, dl, dr, l, r, w, a, o);
 }
 
 __global__ void __launch_bounds__(1024) k_norm2(int dphys, const cplx* __restrict__ a, long long s_a, double* out, const int* el, int esl,
