@@ -37,7 +37,10 @@ int64_t yb_launch_count(int reset);
 /* Optional instrumentation: a device uint64 that every contraction CTA increments by the real flops of its tile (8 per
  * complex multiply-add); NULL (default) disables it.  bench.py uses it for roofline.achieved. */
 void yb_set_flop_counter(void* device_u64);
-/* Diagnostic switches for A/B runs (defaults = production route; environment YB_HEEV_QL / YB_HEEV_RING set the initial value):
+/* Diagnostic switches for A/B runs (defaults = production route; environment YB_HEEV_QL / YB_HEEV_RING / YB_GEMM_RAGGED set the
+ * initial value):
+ *   "gemm_ragged" 1 = k_gemm with interleaved 8 x 8 sub-tiles that skip the padding of ragged tiles (bit-identical results;
+ *               not yet measured on a B200)                                                                   (default 0)
  *   "heev_ql"   1 = implicit-QL tridiagonal eigen-solver instead of divide & conquer                          (default 0)
  *   "heev_ring" depth of the cp.async row ring in k_hetrd / k_ungtr: 0 = direct register loads, 6, 12, 16;
  *               -1 = by matrix size (default: 16 rows in flight for k > 256, direct loads below)                      */

@@ -109,3 +109,20 @@ def test_cuda_digital_tjm_matches_reference(golden_dir, name, gram_min_k):
     torch.cuda.synchronize()
     assert int(eng.status.max().item()) == 0
     check_against_golden(name, golden_dir, results, diag, log, traj)
+
+
+@pytest.mark.parametrize("name", ["heis30_c2_chi64", "ising10_c1_order2"])
+def test_cuda_engine_with_ragged_gemm_option(golden_dir, name):
+    """The whole TJM step with the A/B option "gemm_ragged" switched on reproduces the reference fixtures exactly like the default
+    tiling (the option changes which warp computes which 8 x 8 sub-tile, not any sum)."""
+    kern = CudaKernels("cuda:0")
+    kern.set_option("gemm_ragged", 1)
+    try:
+        eng, tu, su, traj = engine_for_case(name, kern)
+        log = []
+        results, diag = eng.run(tu, su, log)
+        torch.cuda.synchronize()
+        assert int(eng.status.max().item()) == 0
+        check_against_golden(name, golden_dir, results, diag, log, traj)
+    finally:
+        kern.set_option("gemm_ragged", 0)

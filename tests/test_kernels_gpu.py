@@ -434,3 +434,34 @@ def test_mpo_site_apply_matches_twin(backends, dl, dr):
             continue
         want = np.einsum("stab,tlr->slarb", wt, a.numpy()[b * slot_in: b * slot_in + d * l * r].reshape(d, l, r)).reshape(-1)
         assert np.max(np.abs(seg - want)) < 1e-13
+
+
+@pytest.mark.parametrize("case", GEMM_CASES)
+@pytest.mark.parametrize("cap", [5, 37, 113])
+def test_gemm_ragged_option_is_bit_identical(backends, case, cap):
+    """A/B option "gemm_ragged" (interleaved 8 x 8 sub-tiles, padding sub-tiles skipped): every output element is the same sum in
+    the same order, so the result must equal the default tiling bit for bit on ragged and full operands."""
+    cuda, _ = backends
+    op, ngroups, dphys, Dl, Dr, conj = case
+    rng = np.random.default_rng(2000 * op + cap)
+    nb = 5
+    ext = torch.from_numpy(rng.integers(1, cap + 1, size=(nb, 3)).astype(np.int32))
+    ext[0] = cap
+    mask = torch.tensor([1, 1, 0, 1, 1], dtype=torch.int32).cuda()
+    sa, sb, sc = _gemm_sizes(op, ngroups, dphys, Dl, Dr, cap)
+    a, b = _rand_c(rng, nb * sa).cuda(), _rand_c(rng, nb * sb).cuda()
+    c0 = _rand_c(rng, nb * sc)
+    e = ext.cuda()
+    maxm = 4 * 5 * cap
+    outs = []
+    try:
+        for flag in (0, 1):
+            cuda.set_option("gemm_ragged", flag)
+            c = c0.clone().cuda()
+            cuda.gemm(op, nb, ngroups, mask, Ext(e, 0, 3), Ext(e, 1, 3), Ext(e, 2, 3), dphys, Dl, Dr, Buf(a, 0, sa), Buf(b, 0, sb), Buf(c, 0, sc),
+                      conj, maxm, maxm)
+            torch.cuda.synchronize()
+            outs.append(c.cpu().numpy())
+    finally:
+        cuda.set_option("gemm_ragged", 0)
+    assert np.array_equal(outs[0], outs[1])

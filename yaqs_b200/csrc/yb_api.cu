@@ -54,8 +54,11 @@ void yb_set_flop_counter(void* device_u64) { g_flop_counter = (unsigned long lon
 static std::atomic<int> g_opt_heev_ql{getenv("YB_HEEV_QL") != nullptr ? 1 : 0};
 static std::atomic<int> g_opt_heev_ring{getenv("YB_HEEV_RING") != nullptr ? atoi(getenv("YB_HEEV_RING")) : -1};
 
+static std::atomic<int> g_opt_gemm_ragged{getenv("YB_GEMM_RAGGED") != nullptr ? atoi(getenv("YB_GEMM_RAGGED")) : 0};
+
 int yb_set_option(const char* name, int value) {
     if (!name) return fail_msg("yb_set_option: null name");
+    if (!strcmp(name, "gemm_ragged")) { g_opt_gemm_ragged = value != 0; return 0; }
     if (!strcmp(name, "heev_ql")) { g_opt_heev_ql = value != 0; return 0; }
     if (!strcmp(name, "heev_ring")) { g_opt_heev_ring = value; return 0; }
     return fail_msg("yb_set_option: unknown option");
@@ -73,6 +76,7 @@ int yb_gemm(int op, int nbatch, int ngroups, const int32_t* mask, yb_extent e0, 
     P.dphys = dphys; P.Dl = d_left; P.Dr = d_right;
     P.A = (const cplx*)a; P.Bm = (const cplx*)b; P.C = (cplx*)c; P.sA = stride_a; P.sB = stride_b; P.sC = stride_c;
     P.conj_extra = conj_b;
+    P.ragged = g_opt_gemm_ragged.load(std::memory_order_relaxed);
     P.flops = g_flop_counter;
     cudaError_t e = yb_launch_gemm(P, max_m, max_n, (cudaStream_t)stream);
     if (e != cudaSuccess) return fail("yb_gemm", e);

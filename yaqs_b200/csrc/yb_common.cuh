@@ -81,5 +81,6 @@ struct YbGemmParams {
     const cplx* A; const cplx* Bm; cplx* C;
     long long sA, sB, sC; // per-trajectory slot strides (elements)
     int conj_extra;       // != 0: conjugate the B operand in addition to the op's own rule
+    int ragged;           // != 0: interleaved sub-tiles that skip padding (A/B option "gemm_ragged")
     unsigned long long* flops;   // optional device counter: every CTA adds the real flops of its tile (8 per complex MAC)
 };

@@ -130,7 +130,12 @@ __device__ __forceinline__ double flip_sign(double x) {
     return __hiloint2double(__double2hiint(x) ^ 0x80000000, __double2loint(x));
 }
 
-template <int ALAY, int BLAY>
+// RAGGED (A/B option "gemm_ragged", default off): the 8 x 8 sub-tiles of a warp are interleaved over the CTA tile (rows i*16 + wm*8,
+// columns j*32 + wn*8 instead of wm*32 + i*8 / wn*32 + j*8) and sub-tiles that lie entirely beyond M or N issue no fragment loads and no
+// DMMA.  With ragged bonds (chi ~ 113 of 128: M = 4*113 = 452, N = 3*113 = 339) the last tile row / column of a 64 x 128 CTA tile is
+// mostly padding; interleaving spreads the surviving sub-tiles evenly over the 8 warps (2 per SM sub-partition), so the DMMA pipe of
+// every sub-partition sees the same reduction.  Same sums in the same order per output element: results are bit-identical.
+template <int ALAY, int BLAY, bool RAGGED>
 __global__ void __launch_bounds__(NTHREADS, 1) k_gemm(const YbGemmParams P) {
     const int b = blockIdx.z, g = blockIdx.y;
     if (P.mask && !P.mask[b]) return;
@@ -193,6 +198,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm(const YbGemmParams P) {
     for (int s = 0; s < STAGES - 1; ++s) load_stage(s, s);
 
     const int fr = lane >> 2, fk = lane & 3;
+    int rbase[4], cbase[4];
+    bool ron[4], con[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        rbase[i] = i * 16 + wm * 8;
+        cbase[i] = i * 32 + wn * 8;
+        ron[i] = !RAGGED || (m0 + rbase[i] < d.M);
+        con[i] = !RAGGED || (n0 + cbase[i] < d.N);
+    }
     for (int kt = 0; kt < ktiles; ++kt) {
         cp_async_wait<STAGES - 2>();
         __syncthreads();
@@ -204,13 +218,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm(const YbGemmParams P) {
             double ar[4], ai[4], an[4], br[4], bi[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const int row = wm * 32 + i * 8 + fr, k = kk + fk;
+                if (RAGGED && !ron[i]) { ar[i] = ai[i] = an[i] = 0.0; continue; }
+                const int row = (RAGGED ? rbase[i] : wm * 32 + i * 8) + fr, k = kk + fk;
                 const cplx v = (ALAY == LAY_AK) ? as[row * A_KIN_LD + k] : as[k * A_KOUT_LD + row];
                 ar[i] = v.x; ai[i] = v.y; an[i] = flip_sign(v.y);
             }
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const int n = wn * 32 + j * 8 + fr, k = kk + fk;
+                if (RAGGED && !con[j]) { br[j] = bi[j] = 0.0; continue; }
+                const int n = (RAGGED ? cbase[j] : wn * 32 + j * 8) + fr, k = kk + fk;
                 const cplx v = (BLAY == LAY_BN) ? bs[k * B_KOUT_LD + n] : bs[n * B_KIN_LD + k];
                 br[j] = v.x; bi[j] = d.conjB ? flip_sign(v.y) : v.y;
             }
@@ -218,6 +234,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm(const YbGemmParams P) {
             for (int i = 0; i < 4; ++i)
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
+                    if (RAGGED && !(ron[i] && con[j])) continue;          // warp-uniform: the whole 8 x 8 sub-tile is padding
                     dmma(cr[i][j][0], cr[i][j][1], ar[i], br[j]);
                     dmma(ci[i][j][0], ci[i][j][1], ar[i], bi[j]);
                     dmma(cr[i][j][0], cr[i][j][1], an[i], bi[j]);
@@ -229,11 +246,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm(const YbGemmParams P) {
 
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        const int row = m0 + wm * 32 + i * 8 + fr;
+        const int row = m0 + (RAGGED ? rbase[i] : wm * 32 + i * 8) + fr;
         if (row >= d.M) continue;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const int col = n0 + wn * 32 + j * 8 + 2 * fk;
+            const int col = n0 + (RAGGED ? cbase[j] : wn * 32 + j * 8) + 2 * fk;
             cplx* dst = d.C + (long long)row * d.c_rs + col;
             if (col < d.N) dst[0] = make_double2(cr[i][j][0], ci[i][j][0]);
             if (col + 1 < d.N) dst[1] = make_double2(cr[i][j][1], ci[i][j][1]);
@@ -243,18 +260,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm(const YbGemmParams P) {
 
 constexpr size_t GEMM_SMEM = (size_t)STAGES * (A_STAGE + B_STAGE) * sizeof(cplx);
 
-template <int ALAY, int BLAY>
-cudaError_t launch_t(const YbGemmParams& P, int maxM, int maxN, cudaStream_t st) {
+template <int ALAY, int BLAY, bool RAGGED>
+cudaError_t launch_r(const YbGemmParams& P, int maxM, int maxN, cudaStream_t st) {
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(k_gemm<ALAY, BLAY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM);
+        cudaError_t e = cudaFuncSetAttribute(k_gemm<ALAY, BLAY, RAGGED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM);
         if (e != cudaSuccess) return e;
         configured = true;
     }
     const int tiles = ((maxM + BM - 1) / BM) * ((maxN + BN - 1) / BN);
     dim3 grid(tiles, P.ngroups, P.nbatch);
-    k_gemm<ALAY, BLAY><<<grid, NTHREADS, GEMM_SMEM, st>>>(P);
+    k_gemm<ALAY, BLAY, RAGGED><<<grid, NTHREADS, GEMM_SMEM, st>>>(P);
     return cudaGetLastError();
+}
+
+template <int ALAY, int BLAY>
+cudaError_t launch_t(const YbGemmParams& P, int maxM, int maxN, cudaStream_t st) {
+    return P.ragged ? launch_r<ALAY, BLAY, true>(P, maxM, maxN, st) : launch_r<ALAY, BLAY, false>(P, maxM, maxN, st);
 }
 
 }  // namespace
