@@ -299,3 +299,32 @@ PROGRAM_CASES = {
         dict(kind="A", ham="h0", J=1.0, g=0.5, T=0.2, dt=0.1, order=2, chi=8, thr=1e-9, sample=False),
         dict(kind="A", ham="h1", J=1.0, g=1.5, T=0.2, dt=0.1, order=2, chi=8, thr=1e-9, sample=False)]),
 }
+
+
+def program_oracle_inputs(cfg: dict):
+    """(initial OracleMPS, [ProgramInstruction], sorted observables) for a PROGRAM_CASES spec: one noise list object shared by all
+    segments (the program's default model), one MPO object per "ham" name."""
+    L = cfg["L"]
+    obs = []
+    for tok in cfg["obs"].split("+"):
+        if tok in ("x", "y", "z"):
+            obs += [(O.OBSERVABLE_MATRICES[tok], [s]) for s in range(L)]
+        else:
+            obs += [(O.OBSERVABLE_MATRICES[tok], [s, s + 1]) for s in range(L - 1)]
+    obs = [obs[k] for k in O.sort_observables(obs)]
+    procs = [O.make_process(n, [i], g) for i in range(L) for (n, g) in cfg["noise"]]
+    noise = procs if procs else None
+    hams: dict = {}
+    instructions = []
+    for seg in cfg["segments"]:
+        if seg["kind"] == "A":
+            if seg["ham"] not in hams:
+                hams[seg["ham"]] = O.ising_mpo(L, seg["J"], seg["g"])
+            p = O.OracleParams(dt=seg["dt"], n_steps=int(round(seg["T"] / seg["dt"])), order=seg["order"], max_bond_dim=seg["chi"],
+                               svd_threshold=seg["thr"], krylov_tol=1e-4, sample_timesteps=seg["sample"])
+            instructions.append(O.ProgramInstruction("analog", hams[seg["ham"]], p, noise))
+        else:
+            layers = O.ising_trotter_layers(L, seg["J"], seg["g"], seg["dt"], seg["timesteps"], False, sample_each_step=seg["sample"])
+            p = O.OracleParams(dt=1.0, n_steps=1, order=1, max_bond_dim=seg["chi"], svd_threshold=seg["thr"], krylov_tol=1e-4, digital=True)
+            instructions.append(O.ProgramInstruction("digital", layers, p, noise, sample_layers=seg["sample"]))
+    return O.product_state(L, cfg["init"]), instructions, obs
