@@ -110,7 +110,24 @@ STRESS_CASES = {
                             sample_timesteps=True, ntraj=1, seed=5, obs="z",
                             noise=[("lowering", 0.1), ("pauli_z", 0.1), ("pauli_x", 0.05)]),
 }
-ALL_CASES = {**CASES, **LARGE_CASES, **STRESS_CASES}
+# tdvp_mode="dynamic" (SURVEY.md 8f rank 1): pinned for the ORACLE only -- the batched engine does not run this mode yet (DESIGN.md
+# section 7), so these cases stay out of CASES, which the engine tests iterate over.
+DYNAMIC_CASES = {
+    # power-of-two cap: bonds double up to the cap, the 1-site branch takes over where they have reached it
+    "ising8_dynamic_chi4_order2": dict(model="ising", L=8, J=1.0, g=0.8, init="x+", chi=4, thr=1e-9, order=2, dt=0.1, steps=5,
+                                       sample_timesteps=True, ntraj=4, seed=21, obs="z", tdvp_mode="dynamic",
+                                       noise=[("lowering", 0.1), ("pauli_z", 0.1)]),
+    # cap 3 from a chi = 2 random state with a large step: the uncapped split overshoots the cap and the right-to-left pass takes the
+    # QR-slice branch of integrators.py:450-453
+    "ising8_dynamic_chi3_order1": dict(model="ising", L=8, J=1.0, g=1.0, init="random:2:1", chi=3, thr=1e-14, order=1, dt=0.5, steps=3,
+                                       sample_timesteps=True, ntraj=3, seed=22, obs="z", tdvp_mode="dynamic",
+                                       noise=[("lowering", 0.1), ("pauli_x", 0.1)]),
+    # no cap: every site takes the 2-site branch with the uncapped split
+    "heis6_dynamic_nocap_order2": dict(model="heisenberg", L=6, J=1.0, g=0.0, init="Neel", chi=None, thr=1e-8, order=2, dt=0.1, steps=4,
+                                       sample_timesteps=True, ntraj=3, seed=23, obs="z+zz", tdvp_mode="dynamic",
+                                       noise=[("lowering", 0.1), ("pauli_z", 0.1)]),
+}
+ALL_CASES = {**CASES, **LARGE_CASES, **STRESS_CASES, **DYNAMIC_CASES}
 
 
 
