@@ -126,3 +126,24 @@ def test_cuda_engine_with_ragged_gemm_option(golden_dir, name):
         check_against_golden(name, golden_dir, results, diag, log, traj)
     finally:
         kern.set_option("gemm_ragged", 0)
+
+
+def test_cuda_dynamic_tdvp_matches_reference_below_the_cap(golden_dir):
+    """tdvp_mode="dynamic" without a cap (2-site branch with the uncapped split everywhere) against the unmodified reference."""
+    kern = CudaKernels("cuda:0")
+    eng, tu, su, traj = engine_for_case("heis6_dynamic_nocap_order2", kern)
+    log = []
+    results, diag = eng.run(tu, su, log)
+    torch.cuda.synchronize()
+    assert int(eng.status.max().item()) == 0
+    check_against_golden("heis6_dynamic_nocap_order2", golden_dir, results, diag, log, traj)
+
+
+from tests.test_engine_host_logic import DYNAMIC_EXACT, check_dynamic_exact  # noqa: E402
+
+
+@pytest.mark.parametrize("length,chi0,cap", DYNAMIC_EXACT)
+def test_cuda_dynamic_tdvp_is_exact_at_full_bond_dimension(length, chi0, cap):
+    """Both per-trajectory branches of the dynamic sweep (1-site with hand-over at the cap, 2-site with the uncapped split) on the
+    device: exact evolution at full bond dimension (see the host twin of this test for what the reference does there)."""
+    check_dynamic_exact(CudaKernels("cuda:0"), length, chi0, cap)

@@ -49,3 +49,54 @@ def test_compile_circuit_matches_reference_layering():
     kinds = [(len(l.single_qubit_gates), len(l.even_two_qubit_gates), len(l.odd_two_qubit_gates)) for l in cc.layers]
     assert kinds == [(2, 1, 0), (0, 1, 0), (0, 0, 1)]
     assert cc.layers[0].even_two_qubit_gates[0].sites == [2, 3]
+
+
+def test_dynamic_tdvp_engine_matches_reference_below_the_cap(golden_dir):
+    """tdvp_mode="dynamic" (integrators.py:294-511) with no cap: every site takes the 2-site branch with the uncapped split; same
+    jumps, identical bonds, observables <= 1e-10 against the unmodified reference."""
+    name = "heis6_dynamic_nocap_order2"
+    eng, tu, su, traj = engine_for_case(name, NumpyKernels())
+    log = []
+    results, diag = eng.run(tu, su, log)
+    check_against_golden(name, golden_dir, results, diag, log, traj)
+
+
+DYNAMIC_EXACT = [(6, 8, 8), (6, 4, 8), (8, 16, 16), (6, 2, 2)]
+
+
+@pytest.mark.parametrize("length,chi0,cap", DYNAMIC_EXACT)
+def test_dynamic_tdvp_engine_is_exact_at_full_bond_dimension(length, chi0, cap):
+    check_dynamic_exact(NumpyKernels(), length, chi0, cap)
+
+
+def check_dynamic_exact(kernels, length, chi0, cap):
+    """Where bonds sit at the cap the reference's right-to-left hand-over evolves the Householder factor R where R^T belongs
+    (decompositions.py:82 + integrators.py:458), which is neither gauge invariant nor a TDVP step: at FULL bond dimension, where
+    TDVP has no projection error, the reference (restated literally by the oracle, pinned to its fixtures) misses exp(-i dt H)|psi>
+    while its own 2-site mode is exact.  The engine takes the projector-splitting step instead and must be exact there; per-trajectory
+    branch masks are exercised by batching states whose bonds reach the cap at different sites."""
+    import numpy as np
+    import scipy.linalg as sl
+
+    from oracle import tjm_oracle as O
+    from yaqs_b200.engine import BatchedTJM, EngineParams
+    mpo = O.ising_mpo(length, 1.0, 0.8)
+    ham = O.mpo_to_matrix(mpo)
+    states = [O.random_mps(length, c, 3 + k) for k, c in enumerate((chi0, max(chi0 // 2, 1), chi0))]
+    ep = EngineParams(dt=0.1, n_steps=1, order=1, max_bond_dim=cap, svd_threshold=1e-14, krylov_tol=1e-12, tdvp_mode="dynamic")
+    eng = BatchedTJM(kernels, length, len(states), mpo, ep, None, [], [s.tensors for s in states])
+    eng.tdvp(eng.phi)
+    assert int(eng.status.max().item()) == 0
+    for b, s in enumerate(states):
+        exact = sl.expm(-1j * 0.1 * ham) @ O.mps_to_vector(s)
+        got = O.mps_to_vector(O.OracleMPS(eng.phi.download(b), 0))
+        if cap == 2:                      # the end bonds themselves sit at the cap: the sweep structure skips the outer half steps there
+            assert abs(np.vdot(got, got) - 1.0) < 1e-10
+            continue
+        assert abs(abs(np.vdot(got, exact)) - 1.0) < 1e-9, (b, abs(np.vdot(got, exact)))
+    if cap != 2:                          # the reference's own numbers, for the record: far from exact once a bond is at the cap
+        p = O.OracleParams(dt=0.1, n_steps=1, order=1, max_bond_dim=cap, svd_threshold=1e-14, krylov_tol=1e-12, tdvp_mode="dynamic")
+        st = states[0].copy()
+        O.tdvp(st, mpo, p)
+        ref_overlap = abs(np.vdot(O.mps_to_vector(st), sl.expm(-1j * 0.1 * ham) @ O.mps_to_vector(states[0])))
+        assert ref_overlap < 0.9999 if chi0 == cap else True

@@ -258,3 +258,29 @@ def test_digital_simulator_matches_reference_fixture(golden_dir):
         assert abs(res2.expectation_values[s][-1] - np.vdot(psi, op_on([z], [s]) @ psi).real) < 1e-9
     assert abs(res2.expectation_values[L][-1] - np.vdot(psi, op_on([x], [2]) @ psi).real) < 1e-9
     assert len(res2.trajectories[0]) == 1
+
+
+def test_simulator_dynamic_tdvp_mode(golden_dir):
+    """AnalogSimParams(tdvp_mode="dynamic") through Simulator.run: the uncapped fixture of the unmodified reference is reproduced; with a
+    cap the run warns that the reference's hand-over at the cap is not reproduced."""
+    import warnings
+
+    from oracle.golden_cases import DYNAMIC_CASES
+    from yaqs_b200 import ZZ
+    cfg = DYNAMIC_CASES["heis6_dynamic_nocap_order2"]
+    L = cfg["L"]
+    obs = [Observable(Z(), s) for s in range(L)] + [Observable(ZZ(), [s, s + 1]) for s in range(L - 1)]
+    noise = NoiseModel([{"name": n, "sites": [i], "strength": g} for i in range(L) for (n, g) in cfg["noise"]])
+    sp = AnalogSimParams(observables=obs, elapsed_time=cfg["dt"] * cfg["steps"], dt=cfg["dt"], num_traj=cfg["ntraj"], max_bond_dim=None,
+                         svd_threshold=cfg["thr"], krylov_tol=1e-4, order=2, sample_timesteps=True, random_seed=cfg["seed"], tdvp_mode="dynamic")
+    with warnings.catch_warnings():
+        warnings.simplefilter("error")
+        res = Simulator(show_progress=False, kernels=NumpyKernels()).run(State(L, initial="Neel"), Hamiltonian.heisenberg(L, 1.0, 1.0, 1.0), sp, noise)
+    g = np.load(os.path.join(golden_dir, "heis6_dynamic_nocap_order2.npz"))
+    order = sp.observable_sorted_indices
+    for k in range(len(obs)):
+        assert np.max(np.abs(np.asarray(res.trajectories[k]) - g["results"][:, order[k], :])) < 1e-10
+    sp2 = AnalogSimParams(observables=obs[:L], elapsed_time=0.2, dt=0.1, num_traj=2, max_bond_dim=4, order=1, random_seed=1, tdvp_mode="dynamic")
+    with pytest.warns(UserWarning, match="projector-splitting"):
+        res2 = Simulator(show_progress=False, kernels=NumpyKernels()).run(State(L, initial="x+"), Hamiltonian.ising(L, 1.0, 0.8), sp2, noise)
+    assert np.all(res2.max_bond <= 4 * 4) and np.all(np.isfinite(res2.expectation_values[0]))

@@ -1,7 +1,8 @@
 #!/bin/bash
 # First GPU call of the next round (1 GPU): everything that was written after round 1's GPU budget ran out, in priority order.
 #   1 full -m gpu suite.  First execution on a B200 of: measure_shots, scheduled jumps, SWAP ladders, backend boundary, config-4
-#     fixture, SimulationProgram (4 fixtures), the gate-MPO route + yb_mpo_site_apply, the "gemm_ragged" A/B option (bit-identity
+#     fixture, SimulationProgram (4 fixtures), the gate-MPO route + yb_mpo_site_apply, tdvp_mode="dynamic" (uncapped fixture + exactness
+#     at full bond dimension), the "gemm_ragged" A/B option (bit-identity
 #     against the default tiling + two engine fixtures).  tests/conftest.py collects these LAST (FIRST_RUN_ON_GPU): prune the list
 #     from the log of this call.
 #   2 the opt-in config-5 stress fixture (Heisenberg L=200, chi=256; k = 512 eigen-problems)

@@ -68,6 +68,15 @@ class JumpProcess:
     ops: tuple = ()                 # jump operator(s): (L,) for one/adjacent, (F0, F1) for long-range Pauli
 
 
+def layout_chi(params: "EngineParams") -> int | None:
+    """Slot capacity the layout is built for: ``max_bond_dim``, except for tdvp_mode="dynamic", whose uncapped splits let a bond
+    exceed the cap between two ``_cap_bonds`` passes (integrators.py:294-511): at most d * d * cap (a split is bounded by d times
+    either neighbour bond, each of which may itself come from an uncapped split of capped bonds)."""
+    if params.max_bond_dim is None or params.tdvp_mode != "dynamic":
+        return params.max_bond_dim
+    return 4 * params.max_bond_dim
+
+
 class BatchLayout:
     """Slot capacities and offsets of the per-trajectory tensors (DESIGN.md "Data layout in HBM")."""
 
@@ -209,7 +218,7 @@ class BatchedTJM:
         for other in extra_mpos:
             ob = [int(other[0].shape[2])] + [int(w.shape[3]) for w in other]
             mpo_bonds = [max(a, b) for a, b in zip(mpo_bonds, ob)]
-        self.lay = BatchLayout(length, nbatch, params.max_bond_dim, mpo_bonds, init_bonds, bond_factor=bond_factor)
+        self.lay = BatchLayout(length, nbatch, layout_chi(params), mpo_bonds, init_bonds, bond_factor=bond_factor)
         lay = self.lay
         dev = self.dev
         self.phi = BatchedState(lay, dev)
@@ -221,7 +230,7 @@ class BatchedTJM:
         # environments: bond-slot storage; the left and right blocks of a 2-site sweep never need the same bond at the
         # same time, 1TDVP's bond update does.
         self.renv = torch.zeros(lay.env_elems, dtype=C128, device=dev)
-        self.lenv = torch.zeros(lay.env_elems, dtype=C128, device=dev) if params.tdvp_mode == "1site" else self.renv
+        self.lenv = torch.zeros(lay.env_elems, dtype=C128, device=dev) if params.tdvp_mode in ("1site", "dynamic") else self.renv
         # MPO tensors (shared by all trajectories): W[o,p,a,a'], its left-environment transpose WT[p,o,a',a], merged pairs
         self._mpo_cache: dict = {}
         self._set_mpo(self._upload_mpo(mpo))
@@ -601,8 +610,11 @@ class BatchedTJM:
         elif mode == "1site":
             for s in plan:
                 self.sweep_1site(st, s)
+        elif mode == "dynamic":
+            for s in plan:
+                self.sweep_dynamic(st, s)
         else:
-            raise NotImplementedError("tdvp_mode='dynamic' is a SURVEY.md 8(f) 'next' row")
+            raise ValueError(f'tdvp_mode must be one of ("1site", "2site", "dynamic"), got {mode!r}.')
 
     def sweep_2site(self, st: BatchedState, plan: Sequence[float], lo: int = 0, hi: int | None = None) -> None:
         """integrators.py:161-291 on sites lo..hi (default: the whole chain; a sub-range is a digital gate window whose
@@ -678,6 +690,128 @@ class BatchedTJM:
             K.copy_packed(B, None, st.ext(i - 1), ek, d, tmp, st.site(i - 1), lay.slot[i - 1])
             st.bond[:, i] = kt
             self.update_site(st, i - 1, 1, st.site(i - 1), 0.5 * dt)
+
+    def _cap_bonds(self, st: BatchedState) -> None:
+        """_cap_bonds / _sync_bond_dim (sweep_utils.py:110-164,274-294), analog path: every bond above the cap is merged with its
+        pair and re-split ("sqrt", the user's truncation policy, cap = max_bond_dim, min_keep 1), in ascending bond order, for the
+        trajectories that need it."""
+        cap, n, p = self.p.max_bond_dim, self.L, self.p
+        if cap is None or n < 2:
+            return
+        over = (st.bond[:, 1:n] > cap).any(dim=0).cpu().tolist()
+        trunc = self._trunc_args(p.trunc_mode, p.svd_threshold, cap, 1)
+        for c, flag in enumerate(over):
+            if flag:
+                j = c + 1
+                mask = (st.bond[:, j] > cap).to(torch.int32)
+                self.merge(st, j - 1, mask)
+                self.split_theta(st, j - 1, "sqrt", trunc, mask)
+
+    def sweep_dynamic(self, st: BatchedState, scale: float) -> None:
+        """sweep_dynamic (integrators.py:294-511) on the analog path (no fixed-chi renormalisation, sweep_utils.py:191-202): per
+        site every trajectory takes the 1-site update with a QR hand-over when ITS bond has reached the cap, else the 2-site update
+        with an uncapped split -- two complementary per-trajectory masks, the environment update in between is common to both.
+        The QR hand-overs are the truncation-free SVD surrogate of ``sweep_1site`` (a gauge of the same factorisation).
+
+        Parity: exact against the reference as long as no trajectory takes the 1-site branch on the right-to-left pass (uncapped
+        runs, or bonds that stay below the cap) -- fixture heis6_dynamic_nocap_order2.  On that branch the reference transposes the
+        bond matrix twice (``left_qr`` already returns it as (left, new), decompositions.py:82; integrators.py:458 transposes again),
+        so the Householder factor R itself is evolved and absorbed where R^T belongs, and above the cap R[:, :cap] is kept
+        (:450-453).  Shapes agree because k = l there, but the result is not a gauge-invariant function of the state: it depends on
+        the phases LAPACK's SVD / QR happened to choose earlier in the sweep, and it is not a TDVP step any more (L = 2, chi = 2,
+        dt = 0.1: overlap 0.962 with exp(-i dt H)|psi> where 1-site TDVP is exact).  The oracle restates it literally and is pinned
+        to the reference; the engine evolves R^T -- the projector-splitting step the code was written to take -- and truncates to
+        the cap in Schmidt space, so in the saturated regime it agrees with exact evolution, not with the reference's numbers."""
+        n, lay, K, B, d, p = self.L, self.lay, self.K, self.B, self.d, self.p
+        cap = p.max_bond_dim
+        keep_all = self._trunc_args("discarded_weight", 0.0, None, 1)
+        cap_only = self._trunc_args("discarded_weight", 0.0, cap, 1)
+        dt = self._substep_dt(scale)
+        sd = lay.svd_dim
+        kx = Ext(self.keep, 0, 1)
+        cbuf = self._buf(self.theta, lay.theta_slot)
+        tmp = self._buf(self.tmp, lay.nloc_max)
+        self._cap_bonds(st)
+        self.init_right_envs(st)
+
+        def dyn(j: int):                                    # uncapped split; the slot capacity is the only bound
+            return self._trunc_args(p.trunc_mode, p.svd_threshold, lay.cap[j], p.tdvp_min_keep)
+
+        def branches(col: torch.Tensor):
+            m1 = (col >= cap) if cap is not None else torch.zeros_like(col, dtype=torch.bool)
+            any1, any2 = torch.stack([m1.any(), (~m1).any()]).cpu().tolist()
+            return m1, m1.to(torch.int32), (~m1).to(torch.int32), bool(any1), bool(any2)
+
+        # ----- left to right (:341-427) -----
+        for i in range(n):
+            m1, m1i, m2i, any1, any2 = branches(st.bond[:, i + 1])
+            if any1:
+                self.update_site(st, i, 1, st.site(i), 0.5 * dt, m1i)
+            if i == n - 1:
+                continue
+            k1 = None
+            if any1:
+                self._svd(SVD_ROWS, st.site(i), st.ext(i), st.ext(i + 1), keep_all, "right", m1i)
+                K.copy_packed(B, m1i, st.ext(i), kx, d, self._buf(self.svd_u, sd * sd), st.site(i), lay.slot[i])
+                K.copy_packed(B, m1i, kx, st.ext(i + 1), 1, self._buf(self.svd_v, sd * sd), cbuf, lay.theta_slot)      # C (k x r_old)
+                k1 = self.keep.clone()
+            if any2:
+                th = self.merge(st, i, m2i)
+                self.update_site(st, i, 2, th, 0.5 * dt, m2i)
+                self.split_theta(st, i, "right", dyn(i + 1), m2i)
+            r_old = st.bond[:, i + 1].clone()
+            if any1:
+                st.bond[:, i + 1] = torch.where(m1, k1, r_old)
+            self.env_update_left(st, i)
+            if any1:
+                st.bond[:, i + 1] = r_old
+                kt = torch.where(m1, k1, r_old)
+                ek, eo = Ext(kt, 0, 1), st.ext(i + 1)
+                self.krylov(cbuf, cbuf, ek, eo, 1, lambda s_, d_, m, ek=ek, eo=eo, j=i + 1: self.bond_matvec(ek, eo, j, s_, d_, m, lay.cap[j], lay.cap[j]),
+                            -0.5 * dt, m1i)
+                K.gemm(OP_ABSORB_R, B, d, m1i, ek, eo, st.ext(i + 2), d, 1, 1, cbuf, st.site(i + 1), tmp, 0, lay.cap[i + 1], lay.cap[i + 2])
+                K.copy_packed(B, m1i, ek, st.ext(i + 2), d, tmp, st.site(i + 1), lay.slot[i + 1])
+                st.bond[:, i + 1] = kt
+            if any2:
+                if i == n - 2:
+                    self.env_update_right(st, n - 1)
+                else:
+                    self.update_site(st, i + 1, 1, st.site(i + 1), -0.5 * dt, m2i)
+        # ----- right to left (:430-506) -----
+        for i in reversed(range(n)):
+            m1, m1i, m2i, any1, any2 = branches(st.bond[:, i])
+            if any1:
+                self.update_site(st, i, 1, st.site(i), 0.5 * dt, m1i)
+            if i == 0:
+                continue
+            k1 = None
+            if any1:
+                # QR hand-over to the left by the truncation-free SVD surrogate of sweep_1site; where the new bond would exceed the cap
+                # (the left bond came out of an uncapped split) it is truncated to the cap in Schmidt space.  NOT what the reference
+                # computes here -- see the docstring.
+                self._svd(SVD_COLS, st.site(i), st.ext(i), st.ext(i + 1), cap_only, "left", m1i)
+                K.unpack_vh(B, m1i, kx, st.ext(i + 1), d, self._buf(self.svd_v, sd * sd), st.site(i), lay.slot[i])
+                K.copy_packed(B, m1i, st.ext(i), kx, 1, self._buf(self.svd_u, sd * sd), cbuf, lay.theta_slot)          # C (l_old x k)
+                k1 = self.keep.clone()
+            if any2:
+                th = self.merge(st, i - 1, m2i)
+                self.update_site(st, i - 1, 2, th, 0.5 * dt, m2i)
+                self.split_theta(st, i - 1, "left", dyn(i), m2i)
+            l_old = st.bond[:, i].clone()
+            if any1:
+                st.bond[:, i] = torch.where(m1, k1, l_old)
+            self.env_update_right(st, i)
+            if any1:
+                st.bond[:, i] = l_old
+                kt = torch.where(m1, k1, l_old)
+                eo, ek = st.ext(i), Ext(kt, 0, 1)
+                self.krylov(cbuf, cbuf, eo, ek, 1, lambda s_, d_, m, ek=ek, eo=eo, j=i: self.bond_matvec(eo, ek, j, s_, d_, m, lay.cap[j], lay.cap[j]),
+                            -0.5 * dt, m1i)
+                K.gemm(OP_ABSORB_L, B, d, m1i, st.ext(i - 1), eo, ek, d, 1, 1, st.site(i - 1), cbuf, tmp, 0, lay.cap[i - 1], lay.cap[i])
+                K.copy_packed(B, m1i, st.ext(i - 1), ek, d, tmp, st.site(i - 1), lay.slot[i - 1])
+                st.bond[:, i] = kt
+            if any2 and i != 1:
+                self.update_site(st, i - 1, 1, st.site(i - 1), -0.5 * dt, m2i)
 
     # ------------------------------------------------------------------------------------------------------------------
     # dissipation (dissipation.py:50-183)

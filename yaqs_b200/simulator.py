@@ -15,7 +15,7 @@ import numpy as np
 import torch
 
 from .containers import Hamiltonian, Result, State
-from .engine import BatchedTJM, BatchLayout, EngineParams
+from .engine import BatchedTJM, BatchLayout, EngineParams, layout_chi
 from .noise import NoiseModel
 from .params import AnalogSimParams, DigitalSimParams, engine_observables
 from .rng import make_disorder_rng, numpy_tables, philox_tables
@@ -146,6 +146,11 @@ class Simulator:
             if sp.get_state:
                 raise ValueError("Cannot return state in noisy analog simulation due to stochastics.")
             ntraj = sp.num_traj
+        if sp.tdvp_mode == "dynamic" and sp.max_bond_dim is not None:
+            import warnings
+            warnings.warn('tdvp_mode="dynamic" with max_bond_dim: where a bond reaches the cap the reference\'s right-to-left hand-over '
+                          "(integrators.py:450-466) is not a gauge-invariant TDVP step; this engine takes the projector-splitting step "
+                          "instead, so results agree with the reference only while bonds stay below the cap (DESIGN.md 4.13)", stacklevel=3)
         sorted_obs = sp.sorted_observables
         to_sorted = sp.observable_sorted_indices
         obs = engine_observables(sorted_obs, length)
@@ -268,8 +273,8 @@ class Simulator:
             init_bonds[i] = max(init_bonds[i], t.shape[1])
             init_bonds[i + 1] = max(init_bonds[i + 1], t.shape[2])
         mpo_bonds = [int(mpo[0].shape[2])] + [int(w.shape[3]) for w in mpo]
-        one = BatchLayout(length, 1, ep.max_bond_dim, mpo_bonds, init_bonds, bond_factor=bond_factor)
-        per = bytes_per_trajectory(one, ep.order, ep.tdvp_mode == "1site")
+        one = BatchLayout(length, 1, layout_chi(ep), mpo_bonds, init_bonds, bond_factor=bond_factor)
+        per = bytes_per_trajectory(one, ep.order, ep.tdvp_mode in ("1site", "dynamic"))
         if torch.device(dev).type == "cuda":
             free, _total = torch.cuda.mem_get_info(dev)
         else:
