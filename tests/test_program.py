@@ -241,3 +241,20 @@ def test_piecewise_hamiltonian_equals_the_merged_program_fixture(golden_dir):
                 Y.AnalogSimParams(observables=obs, elapsed_time=0.3, dt=0.1, order=2), noise)
     with pytest.raises(ValueError, match="nested piecewise"):
         Y.Hamiltonian.piecewise([(pw, 0.1)])
+
+
+@pytest.mark.parametrize("rng_mode", ["numpy", "philox"])
+def test_program_results_do_not_depend_on_wave_size(rng_mode):
+    """Trajectories of a program are keyed by their global index in both RNG modes (numpy streams or the Philox kernel), so running them
+    as one wave or as waves of two gives the same per-trajectory rows (results independent of batching / sharding)."""
+    from oracle.np_kernels import NumpyKernels
+    prog, state, noise = build_program(PROGRAM_CASES["prog_mixed_digital"])
+    runs = []
+    for batch in (None, 2, 3):
+        sim = Y.Simulator(show_progress=False, kernels=NumpyKernels(), rng_mode=rng_mode, batch_size=batch)
+        runs.append(sim.run(state, prog, None, noise))
+    for other in runs[1:]:
+        for a, b in zip(runs[0].segment_results, other.segment_results):
+            for ta, tb in zip(a.trajectories, b.trajectories):
+                assert np.array_equal(np.asarray(ta), np.asarray(tb))
+        assert np.array_equal(runs[0].stats["trajectory_draws"], other.stats["trajectory_draws"])
