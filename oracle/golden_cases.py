@@ -235,6 +235,12 @@ DIGITAL_CASES = {
     "dig_ising6_periodic_mpo": dict(L=6, J=1.0, g=0.8, dt=0.25, timesteps=3, periodic=True, chi=8, thr=1e-9, ntraj=4, seed=15,
                                     init="x+", obs="z+zz", sample=True, gate_mode="mpo",
                                     noise=[("lowering", 0.05), ("pauli_x", 0.04)]),
+    # three-qubit gates (ccz on adjacent qubits, ccx across a spectator, ccx with unsorted sites): gate-MPO route (digital_tjm.py:583-590)
+    "dig_toffoli6_mpo": dict(L=6, circuit="toffoli", J=1.0, g=0.8, dt=0.3, timesteps=2, periodic=False, chi=8, thr=1e-9, ntraj=4, seed=16,
+                             init="x+", obs="z+zz", sample=True, gate_mode="mpo", noise=[("lowering", 0.05), ("pauli_x", 0.04)]),
+    # the same circuit with the product-form generators of ccz / ccx evolved in TDVP windows (gate_mode="tdvp")
+    "dig_toffoli6_window": dict(L=6, circuit="toffoli", J=1.0, g=0.8, dt=0.3, timesteps=2, periodic=False, chi=None, thr=1e-9, ntraj=3, seed=17,
+                                init="zeros", obs="z", sample=False, gate_mode="tdvp", noise=[("lowering", 0.05), ("pauli_z", 0.04)]),
     # the same route without noise and without a bond cap (one deterministic trajectory)
     "dig_ising5_periodic_mpo_noiseless": dict(L=5, J=1.0, g=0.7, dt=0.3, timesteps=4, periodic=True, chi=None, thr=1e-10, ntraj=1, seed=1,
                                               init="zeros", obs="x+z", sample=True, gate_mode="mpo", noise=[]),
@@ -253,10 +259,54 @@ LARGE_DIGITAL_CASES = {
 ALL_DIGITAL_CASES = {**DIGITAL_CASES, **LARGE_DIGITAL_CASES}
 
 
+def toffoli_gate_list(cfg: dict) -> list[tuple]:
+    """Neutral gate list of the three-qubit test circuit (one gate per layer, as behind full barriers): per step rx on every qubit,
+    rzz on the even pairs, ccz(0,1,2) on adjacent qubits, ccx(1,3,4) across a spectator, ccx(5,3,2) with unsorted sites across a
+    spectator; ("sample",) marks a SAMPLE_OBSERVABLES barrier.  Entries: (name, params, qubits)."""
+    L = cfg["L"]
+    alpha, beta = -2 * cfg["dt"] * cfg["g"], -2 * cfg["dt"] * cfg["J"]
+    gates: list[tuple] = []
+    for step in range(cfg["timesteps"]):
+        gates += [("rx", (alpha,), (s,)) for s in range(L)]
+        gates += [("rzz", (beta,), (2 * s, 2 * s + 1)) for s in range(L // 2)]
+        gates += [("ccz", (), (0, 1, 2)), ("ccx", (), (1, 3, 4)), ("ccx", (), (5, 3, 2))]
+        if cfg["sample"] and step < cfg["timesteps"] - 1:
+            gates.append(("sample", (), ()))
+    return gates
+
+
+def toffoli_oracle_layers(cfg: dict) -> list:
+    x = np.array([[0, 1], [1, 0]], dtype=complex)
+    z = np.array([[1, 0], [0, -1]], dtype=complex)
+    p1 = np.array([[0, 0], [0, 1]], dtype=complex)
+    layers = []
+    for name, params, qubits in toffoli_gate_list(cfg):
+        if name == "sample":
+            layers.append(O.OracleLayer(sample_points=1))
+            continue
+        if name == "rx":
+            a = params[0]
+            layers.append(O.OracleLayer(single=(O.OracleGate("rx", np.cos(a / 2) * np.eye(2) - 1j * np.sin(a / 2) * x, qubits),)))
+            continue
+        if name == "rzz":
+            b = params[0]
+            gate = O.OracleGate("rzz", np.cos(b / 2) * np.eye(4) - 1j * np.sin(b / 2) * np.kron(z, z), qubits, [(b / 2) * z, z.copy()])
+        elif name == "ccz":
+            gate = O.OracleGate("ccz", np.diag([1, 1, 1, 1, 1, 1, 1, -1]).astype(complex), qubits, [(np.pi / 4) * 2 * p1, p1.copy(), 2 * p1])
+        else:
+            gate = O.OracleGate("ccx", np.eye(8, dtype=complex)[[0, 1, 2, 3, 4, 5, 7, 6]], qubits,
+                                [(np.pi / 4) * 2 * p1, p1.copy(), np.array([[1, -1], [-1, 1]], dtype=complex)])
+        layers.append(O.OracleLayer(even=(gate,)) if min(qubits) % 2 == 0 else O.OracleLayer(odd=(gate,)))
+    return layers
+
+
 def digital_inputs(cfg: dict):
     """(initial OracleMPS, layers, noise | None, OracleParams, sorted observables)."""
     L = cfg["L"]
-    layers = O.ising_trotter_layers(L, cfg["J"], cfg["g"], cfg["dt"], cfg["timesteps"], cfg["periodic"], sample_each_step=cfg["sample"])
+    if cfg.get("circuit") == "toffoli":
+        layers = toffoli_oracle_layers(cfg)
+    else:
+        layers = O.ising_trotter_layers(L, cfg["J"], cfg["g"], cfg["dt"], cfg["timesteps"], cfg["periodic"], sample_each_step=cfg["sample"])
     obs = []
     for tok in cfg["obs"].split("+"):
         if tok in ("x", "y", "z"):

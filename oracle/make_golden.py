@@ -185,7 +185,24 @@ def run_digital_case(name: str, cfg: dict) -> dict:
     from mqt.yaqs.core.random_utils import make_trajectory_rng
 
     L = cfg["L"]
-    compiled = reference_ising_compiled(ref_dig, GateLibrary, L, cfg["J"], cfg["g"], cfg["dt"], cfg["timesteps"], cfg["periodic"], cfg["sample"])
+    if cfg.get("circuit") == "toffoli":                      # three-qubit gates from the reference's own GateLibrary, one gate per layer
+        from oracle.golden_cases import toffoli_gate_list
+        layers = []
+        for gname, params, qubits in toffoli_gate_list(cfg):
+            if gname == "sample":
+                layers.append(ref_dig._CompiledCircuitLayer((), (), (), 1))
+                continue
+            gate = getattr(GateLibrary, gname)(list(params)) if params else getattr(GateLibrary, gname)()
+            gate.set_sites(*qubits)
+            if len(qubits) == 1:
+                layers.append(ref_dig._CompiledCircuitLayer((gate,), (), (), 0))
+            elif min(qubits) % 2 == 0:
+                layers.append(ref_dig._CompiledCircuitLayer((), (gate,), (), 0))
+            else:
+                layers.append(ref_dig._CompiledCircuitLayer((), (), (gate,), 0))
+        compiled = ref_dig._CompiledCircuit(tuple(layers), sum(l.sample_points for l in layers))
+    else:
+        compiled = reference_ising_compiled(ref_dig, GateLibrary, L, cfg["J"], cfg["g"], cfg["dt"], cfg["timesteps"], cfg["periodic"], cfg["sample"])
     mid = compiled.num_mid_measurements
 
     obs = []

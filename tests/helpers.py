@@ -52,8 +52,20 @@ def digital_engine_for_case(name, kernels, trajectories=None, **kw):
     cfg = ALL_DIGITAL_CASES[name]
     init, _layers, noise, p, obs = digital_inputs(cfg)
     L = cfg["L"]
-    compiled = compile_circuit(create_ising_circuit(L, cfg["J"], cfg["g"], cfg["dt"], cfg["timesteps"], periodic=cfg["periodic"],
-                                                    sample_every_step=cfg["sample"]))
+    if cfg.get("circuit") == "toffoli":
+        from oracle.golden_cases import toffoli_gate_list
+        from yaqs_b200.circuits import SAMPLE_LABEL, Circuit
+        circ = Circuit(L)
+        for gname, params, qubits in toffoli_gate_list(cfg):
+            if gname == "sample":
+                circ.barrier(label=SAMPLE_LABEL)
+            else:
+                getattr(circ, gname)(*params, *qubits)
+                circ.barrier()
+        compiled = compile_circuit(circ)
+    else:
+        compiled = compile_circuit(create_ising_circuit(L, cfg["J"], cfg["g"], cfg["dt"], cfg["timesteps"], periodic=cfg["periodic"],
+                                                        sample_every_step=cfg["sample"]))
     traj = list(range(cfg["ntraj"])) if trajectories is None else list(trajectories)
     ep = EngineParams(dt=1.0, n_steps=1, order=1, max_bond_dim=cfg["chi"], svd_threshold=cfg["thr"], krylov_tol=p.krylov_tol, digital=True)
     mpo = [np.eye(2, dtype=np.complex128).reshape(2, 2, 1, 1) for _ in range(L)]

@@ -18,7 +18,7 @@ from .gates import BaseGate, GateLibrary
 
 SAMPLE_LABEL = "SAMPLE_OBSERVABLES"
 _PARAM_GATES = {"rx", "ry", "rz", "p", "rxx", "ryy", "rzz", "cp", "u"}
-_FIXED_GATES = {"x", "y", "z", "h", "id", "sx", "s", "sdg", "t", "tdg", "cx", "cz", "swap"}
+_FIXED_GATES = {"x", "y", "z", "h", "id", "sx", "s", "sdg", "t", "tdg", "cx", "cz", "swap", "ccx", "ccz", "cswap"}
 
 
 @dataclass

@@ -1443,21 +1443,34 @@ class BatchedTJM:
 
     @staticmethod
     def gate_support_mpo(gate) -> list[np.ndarray]:
-        """get_support_mpo / extend_gate / split_tensor for a two-qubit gate (mpo_utils.py:166-216, gate_library.py:25-126): the
-        gate tensor in ascending site order, legs grouped per site, one SVD with the singular values carried to the right and the
-        reference's hard cut-off 1e-6 (min_keep 1); identity tensors of the carried bond between the two sites.  Returns the
-        (2, 2, Dl, Dr) tensors for sites min(sites) .. max(sites)."""
-        first, last = min(gate.sites), max(gate.sites)
-        t = BatchedTJM._resolve_lr_matrix(gate).reshape(2, 2, 2, 2)                  # [o_left, o_right, i_left, i_right]
-        u, sv, vh = np.linalg.svd(np.transpose(t, (0, 2, 1, 3)).reshape(4, 4), full_matrices=False)
-        keep = max(int(np.sum(sv > 1e-6)), 1)
-        tensors = [np.transpose(u[:, :keep].reshape(1, 2, 2, keep), (1, 2, 0, 3))]
-        for _ in range(first + 1, last):
-            ident = np.zeros((2, 2, keep, keep), dtype=np.complex128)
-            for k in range(keep):
-                ident[:, :, k, k] = np.eye(2)
-            tensors.append(ident)
-        tensors.append(np.transpose((np.diag(sv[:keep]) @ vh[:keep]).reshape(keep, 2, 2), (1, 2, 0))[:, :, :, None])
+        """BaseGate.set_sites -> extend_gate -> split_tensor (gate_library.py:25-126,196-198; what get_support_mpo returns from the
+        gate's cache, mpo_utils.py:198-204): the gate tensor with its axes permuted to ascending site order, legs grouped per site,
+        split site by site with SVDs that carry the singular values to the right under the reference's hard cut-off 1e-6
+        (min_keep 1); identity tensors of the carried bond on spectator sites.  Returns the (2, 2, Dl, Dr) tensors for the sites
+        min(sites) .. max(sites).  Two- and three-qubit gates."""
+        n = int(gate.interaction)
+        t = np.asarray(gate.matrix, dtype=np.complex128).reshape((2,) * (2 * n))
+        order = sorted(range(n), key=lambda k: gate.sites[k])
+        t = np.transpose(t, [*order, *[n + k for k in order]])
+        srt = sorted(gate.sites)
+        rem = np.transpose(t, [ax for k in range(n) for ax in (k, n + k)]).reshape(4, 4 ** (n - 1))
+        parts, left = [], 1
+        for _ in range(n - 1):
+            u, sv, vh = np.linalg.svd(rem, full_matrices=False)
+            keep = max(int(np.sum(sv > 1e-6)), 1)
+            parts.append(np.transpose(u[:, :keep].reshape(left, 2, 2, keep), (1, 2, 0, 3)))
+            left = keep
+            rem = (np.diag(sv[:keep]) @ vh[:keep]).reshape(left * 4, rem.shape[1] // 4)
+        parts.append(np.transpose(rem.reshape(left, 2, 2), (1, 2, 0))[:, :, :, None])
+        tensors = [parts[0]]
+        for k in range(1, n):
+            bond = tensors[-1].shape[3]
+            for _ in range(srt[k - 1] + 1, srt[k]):
+                ident = np.zeros((2, 2, bond, bond), dtype=np.complex128)
+                for q in range(bond):
+                    ident[:, :, q, q] = np.eye(2)
+                tensors.append(ident)
+            tensors.append(parts[k])
         return [np.ascontiguousarray(w, dtype=np.complex128) for w in tensors]
 
     @staticmethod
@@ -1467,13 +1480,13 @@ class BatchedTJM:
         factor = [1] * (length + 1)
         for layer in layers:
             for gate in (*layer.even_two_qubit_gates, *layer.odd_two_qubit_gates):
-                if gate.interaction != 2 or abs(gate.sites[0] - gate.sites[1]) == 1 or gate_mode == "swaps":
+                if gate.interaction == 2 and (abs(gate.sites[0] - gate.sites[1]) == 1 or gate_mode == "swaps"):
                     continue
                 if gate_mode in ("tdvp", "full-tdvp") and getattr(gate, "generator", None) is not None:
                     continue
-                rank = BatchedTJM.gate_support_mpo(gate)[0].shape[3]
-                for j in range(min(gate.sites) + 1, max(gate.sites) + 1):
-                    factor[j] = max(factor[j], rank)
+                for k, w in enumerate(BatchedTJM.gate_support_mpo(gate)[:-1]):
+                    j = min(gate.sites) + 1 + k
+                    factor[j] = max(factor[j], w.shape[3])
         return factor if max(factor) > 1 else None
 
     def apply_long_range_gate_mpo(self, st: BatchedState, gate) -> int:
@@ -1488,20 +1501,19 @@ class BatchedTJM:
         first, last = min(gate.sites), max(gate.sites)
         key = ("gate-mpo", gate.name, tuple(gate.sites), np.asarray(gate.matrix, dtype=np.complex128).tobytes())
         if key not in self._mpo_cache:
-            self._mpo_cache[key] = [torch.from_numpy(w.reshape(-1)).to(self.dev) for w in self.gate_support_mpo(gate)]
+            self._mpo_cache[key] = [(torch.from_numpy(w.reshape(-1)).to(self.dev), w.shape[2], w.shape[3]) for w in self.gate_support_mpo(gate)]
         ws = self._mpo_cache[key]
-        rank = ws[0].numel() // 4
+        ranks = torch.tensor([dr for _, _, dr in ws[:-1]], dtype=st.bond.dtype, device=self.dev)      # MPO bond on bonds first+1 .. last
         old = st.bond.clone()
-        grown = old[:, first + 1: last + 1] * rank
+        grown = old[:, first + 1: last + 1] * ranks[None, :]
         if bool((grown.max(dim=0).values.cpu() > torch.tensor(lay.cap[first + 1: last + 1])).any()):
             raise ValueError("gate-MPO route: chi * D_gate exceeds the slot capacity; build the engine with bond_factor="
                              "BatchedTJM.mpo_route_bond_factor(layers, gate_mode, length)")
         st.bond[:, first + 1: last + 1] = grown.to(st.bond.dtype)
         tmp = self._buf(self.tmp, lay.nloc_max)
         for s in range(first, last + 1):
-            dl = 1 if s == first else rank
-            dr = 1 if s == last else rank
-            K.mpo_site_apply(B, None, Ext(old, s, n + 1), Ext(old, s + 1, n + 1), d, dl, dr, ws[s - first], st.site(s), tmp, lay.cap[s] * lay.cap[s + 1])
+            w, dl, dr = ws[s - first]
+            K.mpo_site_apply(B, None, Ext(old, s, n + 1), Ext(old, s + 1, n + 1), d, dl, dr, w, st.site(s), tmp, lay.cap[s] * lay.cap[s + 1])
             K.copy_packed(B, None, st.ext(s), st.ext(s + 1), d, tmp, st.site(s), lay.slot[s])
         keep_all = self._trunc_args("discarded_weight", 0.0, None, 1)
         for i in reversed(range(1, n)):                     # set_canonical_form(0, "QR")
@@ -1594,11 +1606,14 @@ class BatchedTJM:
                     self.apply_single_qubit_gate(st, gate)
                 for group in (layer.even_two_qubit_gates, layer.odd_two_qubit_gates):
                     for gate in group:
-                        if gate.interaction != 2:
-                            raise NotImplementedError("gates on three or more qubits use the gate-MPO route (SURVEY.md 8f 'next' row)")
-                        nn = abs(gate.sites[0] - gate.sites[1]) == 1
                         has_gen = getattr(gate, "generator", None) is not None
-                        if gate_mode == "full-tdvp" and has_gen:
+                        nn = gate.interaction == 2 and abs(gate.sites[0] - gate.sites[1]) == 1
+                        if gate.interaction > 2:            # no TEBD path: generator window in the TDVP modes, else the gate MPO (:583-590)
+                            if gate_mode in ("tdvp", "full-tdvp") and has_gen:
+                                centre = self.apply_two_qubit_gate_tdvp(st, gate)
+                            else:
+                                centre = self.apply_long_range_gate_mpo(st, gate)
+                        elif gate_mode == "full-tdvp" and has_gen:
                             centre = self.apply_two_qubit_gate_tdvp(st, gate)
                         elif nn or gate_mode == "swaps":
                             centre = self.apply_two_qubit_gate_tebd(st, gate)

@@ -37,7 +37,7 @@ class BaseGate:
     def tensor(self) -> np.ndarray:
         if self.interaction == 1:
             return self.matrix
-        return self.matrix.reshape(2, 2, 2, 2)
+        return self.matrix.reshape((2,) * (2 * self.interaction))      # (out_0 .. out_{n-1}, in_0 .. in_{n-1}) in ``sites`` order
 
     def set_sites(self, *sites) -> None:
         flat: list[int] = []
@@ -116,6 +116,21 @@ class GateLibrary:
     cx = staticmethod(_fixed("cx", np.array([[1, 0, 0, 0], [0, 1, 0, 0], [0, 0, 0, 1], [0, 0, 1, 0]])))
     cz = staticmethod(_fixed("cz", np.diag([1, 1, 1, -1])))
     swap = staticmethod(_fixed("swap", np.array([[1, 0, 0, 0], [0, 0, 1, 0], [0, 1, 0, 0], [0, 0, 0, 1]])))
+    cswap = staticmethod(_fixed("cswap", np.eye(8)[[0, 1, 2, 3, 4, 6, 5, 7]], 3))         # no product-form generator (gate_library.py:1455-1499)
+
+    @staticmethod
+    def ccx() -> BaseGate:
+        """Toffoli (gate_library.py:1255-1302): controls on the first two sites; generator pi/4 (I - Z) (x) P1 (x) (I - X)."""
+        g = BaseGate(np.eye(8)[[0, 1, 2, 3, 4, 5, 7, 6]], name="ccx", interaction=3)
+        g.generator = [(np.pi / 4) * np.array([[0, 0], [0, 2]], dtype=C), np.array([[0, 0], [0, 1]], dtype=C), np.array([[1, -1], [-1, 1]], dtype=C)]
+        return g
+
+    @staticmethod
+    def ccz() -> BaseGate:
+        """gate_library.py:1304-1345: generator pi/4 (I - Z) (x) P1 (x) (I - Z)."""
+        g = BaseGate(np.diag([1, 1, 1, 1, 1, 1, 1, -1]), name="ccz", interaction=3)
+        g.generator = [(np.pi / 4) * np.array([[0, 0], [0, 2]], dtype=C), np.array([[0, 0], [0, 1]], dtype=C), np.array([[0, 0], [0, 2]], dtype=C)]
+        return g
 
     entropy = staticmethod(lambda: Entropy())
     pvm = staticmethod(lambda bitstring: PVM(bitstring))
