@@ -67,7 +67,7 @@ def workload_config(args, nranks):
             "observables": "Z on every site, every step", "initial_state": "seeded random MPS, bonds saturated at chi",
             "batch_per_gpu": args.batch, "global_batch": args.batch * nranks, "sharding": f"trajectories x{nranks}", "lanes_per_gpu": args.lanes,
             "l2_policy": "inputs larger than L2 (per-step working set >> 126 MB)",
-            "library_options": {k: os.environ[k] for k in ("YB_GEMM_RAGGED", "YB_HEEV_RING", "YB_HEEV_QL") if k in os.environ}}
+            "library_options": {k: os.environ[k] for k in ("YB_GEMM_RAGGED", "YB_WAPPLY_ONEPASS", "YB_HEEV_RING", "YB_HEEV_QL") if k in os.environ}}
 
 
 # ----------------------------------------------------------------------------------------------------------------------

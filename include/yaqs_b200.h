@@ -41,6 +41,8 @@ void yb_set_flop_counter(void* device_u64);
  * initial value):
  *   "gemm_ragged" 1 = k_gemm with interleaved 8 x 8 sub-tiles that skip the padding of ragged tiles (bit-identical results;
  *               not yet measured on a B200)                                                                   (default 0)
+ *   "wapply_onepass" 1 = k_wapply_onepass: every input element of the MPO-tensor step is read once and feeds all nx * ny outputs
+ *               (bit-identical results; not yet measured on a B200; env YB_WAPPLY_ONEPASS)                     (default 0)
  *   "heev_ql"   1 = implicit-QL tridiagonal eigen-solver instead of divide & conquer                          (default 0)
  *   "heev_ring" depth of the cp.async row ring in k_hetrd / k_ungtr: 0 = direct register loads, 6, 12, 16;
  *               -1 = by matrix size (default: 16 rows in flight for k > 256, direct loads below)                      */

@@ -117,6 +117,7 @@ def test_cuda_engine_with_ragged_gemm_option(golden_dir, name):
     tiling (the option changes which warp computes which 8 x 8 sub-tile, not any sum)."""
     kern = CudaKernels("cuda:0")
     kern.set_option("gemm_ragged", 1)
+    kern.set_option("wapply_onepass", 1)                     # the second A/B kernel rides along: also bit-identical by construction
     try:
         eng, tu, su, traj = engine_for_case(name, kern)
         log = []
@@ -126,6 +127,7 @@ def test_cuda_engine_with_ragged_gemm_option(golden_dir, name):
         check_against_golden(name, golden_dir, results, diag, log, traj)
     finally:
         kern.set_option("gemm_ragged", 0)
+        kern.set_option("wapply_onepass", 0)
 
 
 def test_cuda_dynamic_tdvp_matches_reference_below_the_cap(golden_dir):

@@ -465,3 +465,32 @@ def test_gemm_ragged_option_is_bit_identical(backends, case, cap):
     finally:
         cuda.set_option("gemm_ragged", 0)
     assert np.array_equal(outs[0], outs[1])
+
+
+@pytest.mark.parametrize("dims", [(4, 4, 3, 3), (2, 2, 5, 4), (2, 2, 1, 1), (4, 4, 5, 5), (4, 4, 4, 3)])
+def test_wapply_onepass_option_is_bit_identical(backends, dims):
+    """A/B option "wapply_onepass": one read of every input element, all nx * ny outputs per thread; the same (u, v) order and zero skip
+    as k_wapply, so the result must equal the default kernel bit for bit (ragged bonds, mask, sparse MPO tensor)."""
+    cuda, _ = backends
+    nx, nu, ny, nv = dims
+    rng = np.random.default_rng(17)
+    nb, cap = 6, 41
+    ext = torch.from_numpy(rng.integers(1, cap + 1, size=(nb, 2)).astype(np.int32))
+    ext[0] = cap
+    mask = torch.tensor([1, 1, 0, 1, 1, 1], dtype=torch.int32).cuda()
+    w = _rand_c(rng, nx * nu * ny * nv)
+    w[::3] = 0
+    sin, sout = nu * nv * cap * cap, nx * ny * cap * cap
+    src, dst0 = _rand_c(rng, nb * sin).cuda(), _rand_c(rng, nb * sout)
+    e = ext.cuda()
+    outs = []
+    try:
+        for flag in (0, 1):
+            cuda.set_option("wapply_onepass", flag)
+            dst = dst0.clone().cuda()
+            cuda.wapply(nb, mask, Ext(e, 0, 2), Ext(e, 1, 2), nx, nu, ny, nv, w.cuda(), Buf(src, 0, sin), Buf(dst, 0, sout), cap * cap)
+            torch.cuda.synchronize()
+            outs.append(dst.cpu().numpy())
+    finally:
+        cuda.set_option("wapply_onepass", 0)
+    assert np.array_equal(outs[0], outs[1])

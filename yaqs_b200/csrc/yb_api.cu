@@ -54,11 +54,13 @@ void yb_set_flop_counter(void* device_u64) { g_flop_counter = (unsigned long lon
 static std::atomic<int> g_opt_heev_ql{getenv("YB_HEEV_QL") != nullptr ? 1 : 0};
 static std::atomic<int> g_opt_heev_ring{getenv("YB_HEEV_RING") != nullptr ? atoi(getenv("YB_HEEV_RING")) : -1};
 
+static std::atomic<int> g_opt_wapply_onepass{getenv("YB_WAPPLY_ONEPASS") != nullptr ? atoi(getenv("YB_WAPPLY_ONEPASS")) : 0};
 static std::atomic<int> g_opt_gemm_ragged{getenv("YB_GEMM_RAGGED") != nullptr ? atoi(getenv("YB_GEMM_RAGGED")) : 0};
 
 int yb_set_option(const char* name, int value) {
     if (!name) return fail_msg("yb_set_option: null name");
     if (!strcmp(name, "gemm_ragged")) { g_opt_gemm_ragged = value != 0; return 0; }
+    if (!strcmp(name, "wapply_onepass")) { g_opt_wapply_onepass = value != 0; return 0; }
     if (!strcmp(name, "heev_ql")) { g_opt_heev_ql = value != 0; return 0; }
     if (!strcmp(name, "heev_ring")) { g_opt_heev_ring = value; return 0; }
     return fail_msg("yb_set_option: unknown option");
@@ -86,6 +88,13 @@ int yb_gemm(int op, int nbatch, int ngroups, const int32_t* mask, yb_extent e0, 
 int yb_wapply(int nbatch, const int32_t* mask, yb_extent el, yb_extent er, int nx, int nu, int ny, int nv, const void* wt, const void* in,
               int64_t stride_in, void* out, int64_t stride_out, int max_lr, void* stream) {
     if (nbatch <= 0 || max_lr <= 0) return 0;
+    if (g_opt_wapply_onepass.load(std::memory_order_relaxed) && nx <= wapply::MAX_NX && nu <= wapply::MAX_NX && ny <= wapply::MAX_NY &&
+        nv <= wapply::MAX_NY) {
+        dim3 grid1((max_lr + 127) / 128, 1, nbatch);
+        k_wapply_onepass<<<grid1, 128, 0, (cudaStream_t)stream>>>(nx, nu, ny, nv, (const cplx*)wt, (const cplx*)in, stride_in, (cplx*)out, stride_out,
+                                                                  el.ptr, el.stride, er.ptr, er.stride, mask);
+        return done("yb_wapply");
+    }
     dim3 grid((max_lr + 255) / 256, nx * ny, nbatch);
     k_wapply<<<grid, 256, 0, (cudaStream_t)stream>>>(nx, nu, ny, nv, (const cplx*)wt, (const cplx*)in, stride_in, (cplx*)out, stride_out, el.ptr,
                                                       el.stride, er.ptr, er.stride, mask);

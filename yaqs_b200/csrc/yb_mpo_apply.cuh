@@ -6,10 +6,16 @@
 #pragma once
 
 #ifdef YB_HOST_EMU
+#ifndef YB_HOST_CPLX
+#define YB_HOST_CPLX
 struct double2 { double x, y; };
 static inline double2 make_double2(double x, double y) { return double2{x, y}; }
 typedef double2 cplx;
-static inline cplx cfma(cplx a, cplx b, cplx c) { return make_double2(a.x * b.x - a.y * b.y + c.x, a.x * b.y + a.y * b.x + c.y); }
+#include <cmath>
+static inline cplx cfma(cplx a, cplx b, cplx c) {
+    return make_double2(std::fma(a.x, b.x, std::fma(-a.y, b.y, c.x)), std::fma(a.x, b.y, std::fma(a.y, b.x, c.y)));
+}
+#endif
 #define YB_MPO_FN static inline
 #else
 #define YB_MPO_FN __device__ __forceinline__

@@ -4,6 +4,7 @@
 #include "yb_common.cuh"
 #include "yb_philox.cuh"
 #include "yb_mpo_apply.cuh"
+#include "yb_wapply.cuh"
 #include <math.h>
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -31,6 +32,24 @@ __global__ void k_wapply(int nx, int nu, int ny, int nv, const cplx* __restrict_
             acc = cfma(w, t, acc);
         }
     out[(long long)b * s_out + (((long long)x * l + li) * ny + y) * r + ri] = acc;
+}
+
+// One-pass variant (yb_wapply.cuh): a thread owns one (l, r) position and produces all nx * ny outputs from one read of the input.
+// grid = (ceil(l*r / 128), 1, B); wt staged in shared memory (<= 400 complex).
+__global__ void __launch_bounds__(128) k_wapply_onepass(int nx, int nu, int ny, int nv, const cplx* __restrict__ wt, const cplx* __restrict__ in,
+                                                        long long s_in, cplx* __restrict__ out, long long s_out, const int* el, int esl,
+                                                        const int* er, int esr, const int* mask) {
+    __shared__ cplx ws[wapply::MAX_NX * wapply::MAX_NX * wapply::MAX_NY * wapply::MAX_NY];
+    const int b = blockIdx.z;
+    if (mask && !mask[b]) return;
+    const int l = el[(long long)b * esl], r = er[(long long)b * esr];
+    const long long lr = (long long)l * r;
+    if ((long long)blockIdx.x * blockDim.x >= lr) return;                 // block-uniform: nobody waits at the barrier below
+    for (int e = threadIdx.x; e < nx * nu * ny * nv; e += blockDim.x) ws[e] = wt[e];
+    __syncthreads();
+    const long long pos = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pos >= lr) return;
+    wapply::element(pos, nx, nu, ny, nv, l, r, ws, in + (long long)b * s_in, out + (long long)b * s_out);
 }
 
 // env[i,a,j] = delta_ij
