@@ -226,6 +226,11 @@ DIGITAL_CASES = {
     "dig_ising5_periodic_window": dict(L=5, J=1.0, g=0.8, dt=0.25, timesteps=4, periodic=True, chi=None, thr=1e-9, ntraj=4, seed=11,
                                        init="zeros", obs="z", sample=True, gate_mode="tdvp",
                                        noise=[("lowering", 0.04), ("pauli_z", 0.04)]),
+    # TDVP gate windows under a tight bond cap: truncation loses enough norm for the fixed-chi renorm_drift of digital_tjm.py:445-446
+    # (sweep_utils.py:231-243) to fire
+    "dig_ising6_window_capped": dict(L=6, J=1.0, g=0.8, dt=0.5, timesteps=3, periodic=True, chi=2, thr=1e-9, ntraj=3, seed=18,
+                                     init="x+", obs="z+zz", sample=True, gate_mode="tdvp",
+                                     noise=[("lowering", 0.05), ("pauli_z", 0.04)]),
     # the same periodic circuit with the long-range gate routed through a SWAP ladder (gate_mode="swaps", digital_tjm.py:463-481)
     "dig_ising6_periodic_swaps": dict(L=6, J=1.0, g=0.8, dt=0.25, timesteps=3, periodic=True, chi=8, thr=1e-9, ntraj=4, seed=12,
                                       init="x+", obs="z+zz", sample=True, gate_mode="swaps",
