@@ -284,3 +284,26 @@ def test_simulator_dynamic_tdvp_mode(golden_dir):
     with pytest.warns(UserWarning, match="projector-splitting"):
         res2 = Simulator(show_progress=False, kernels=NumpyKernels()).run(State(L, initial="x+"), Hamiltonian.ising(L, 1.0, 0.8), sp2, noise)
     assert np.all(res2.max_bond <= 4 * 4) and np.all(np.isfinite(res2.expectation_values[0]))
+
+
+def test_digital_get_state_only_run():
+    """DigitalSimParams(get_state=True) without observables or shots (simulator.py:1282-1290,1714-1716): the noise-free final state comes
+    back as Result.output_state and carries the observables of an observable run; a noisy model is rejected."""
+    from yaqs_b200 import DigitalSimParams
+    from yaqs_b200.circuits import create_ising_circuit
+    L = 5
+    circ = create_ising_circuit(L, 1.0, 0.6, 0.2, 3)
+    sim = Simulator(show_progress=False, kernels=NumpyKernels())
+    res = sim.run(State(L, initial="zeros"), circ, DigitalSimParams(get_state=True, max_bond_dim=None, svd_threshold=1e-12))
+    vec = res.output_state.mps.to_vector()
+    assert abs(np.vdot(vec, vec) - 1.0) < 1e-12
+    obs = sim.run(State(L, initial="zeros"), circ, DigitalSimParams(observables=[Observable(Z(), s) for s in range(L)], max_bond_dim=None,
+                                                                    svd_threshold=1e-12))
+    psi = vec.reshape((2,) * L)
+    for s in range(L):
+        z = sum((1 - 2 * i) * float(np.sum(np.abs(np.take(psi, i, axis=s)) ** 2)) for i in (0, 1))
+        assert abs(z - obs.expectation_values[s][-1]) < 1e-10
+    with pytest.raises(ValueError, match="No output specified"):
+        sim.run(State(L), circ, DigitalSimParams())
+    with pytest.raises(ValueError, match="noisy circuit simulation"):
+        sim.run(State(L), circ, DigitalSimParams(get_state=True), NoiseModel([{"name": "pauli_x", "sites": [0], "strength": 0.1}]))

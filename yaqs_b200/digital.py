@@ -32,13 +32,15 @@ def validate_digital_noise(noise, length: int) -> None:
 def run_digital(simulator, initial_state, operator, sp, noise, result):
     from .simulator import shard_range
     wants_obs, wants_shots = bool(sp.observables), sp.shots is not None
-    if not wants_obs and not wants_shots:
-        raise ValueError("No output specified: set observables= and/or shots= (get_state-only runs are outside the B200 hot path).")
+    if not wants_obs and not wants_shots and not sp.get_state:
+        raise ValueError("No output specified: set observables, shots, and/or get_state.")             # simulator.py:1282-1290
     compiled = operator if isinstance(operator, CompiledCircuit) else compile_circuit(operator)
     length = initial_state.length
     if noise is not None:
         validate_digital_noise(noise, length)
     noiseless = noise is None or all(pr["strength"] == 0 for pr in noise.processes)
+    if not noiseless and sp.get_state:
+        raise ValueError("Cannot return state in noisy circuit simulation due to stochastics.")          # simulator.py:1714-1716
     ntraj, shots_of = plan_digital_shots(sp, noisy=not noiseless)
     sorted_obs = sp.sorted_observables
     to_sorted = sp.observable_sorted_indices
@@ -95,6 +97,9 @@ def run_digital(simulator, initial_state, operator, sp, noise, result):
             stats[k] = stats.get(k, 0) + v
         if log_all is not None:
             log_all.append((idx, log))
+        if sp.get_state and noiseless:
+            from .containers import State
+            result.output_state = State(tensors=eng.phi.download(0))
         del eng
     stats["kernel_launches"] = K.launch_count()
     simulator.last_log = log_all
