@@ -100,3 +100,27 @@ def check_dynamic_exact(kernels, length, chi0, cap):
         O.tdvp(st, mpo, p)
         ref_overlap = abs(np.vdot(O.mps_to_vector(st), sl.expm(-1j * 0.1 * ham) @ O.mps_to_vector(states[0])))
         assert ref_overlap < 0.9999 if chi0 == cap else True
+
+
+@pytest.mark.parametrize("mode", ["2site", "dynamic"])
+def test_tdvp_sweeps_greater_than_one_matches_oracle(mode):
+    """tdvp_sweeps = 3 (tdvp.py:24-66: three symmetric substeps of dt / 3): engine on the numpy twin against the oracle restatement
+    (pinned to the reference) on an uncapped chain, both sweep geometries that take a sweep plan."""
+    import numpy as np
+
+    from oracle import tjm_oracle as O
+    from yaqs_b200.engine import BatchedTJM, EngineParams
+    length = 6
+    init = O.random_mps(length, 2, 11)
+    mpo = O.heisenberg_mpo(length, 1.0, 0.7, 0.4, 0.2)
+    p = O.OracleParams(dt=0.2, n_steps=1, order=1, max_bond_dim=None, svd_threshold=1e-10, krylov_tol=1e-8, tdvp_mode=mode, tdvp_sweeps=3)
+    st = init.copy()
+    O.tdvp(st, mpo, p)
+    ep = EngineParams(dt=0.2, n_steps=1, order=1, max_bond_dim=None, svd_threshold=1e-10, krylov_tol=1e-8, tdvp_mode=mode, tdvp_sweeps=3)
+    eng = BatchedTJM(NumpyKernels(), length, 2, mpo, ep, None, [], init.tensors)
+    eng.tdvp(eng.phi)
+    got = eng.phi.download(1)
+    assert [t.shape[2] for t in got] == [t.shape[2] for t in st.tensors]
+    want = O.mps_to_vector(st)
+    vec = O.mps_to_vector(O.OracleMPS(got, 0))
+    assert abs(np.vdot(want, vec) - np.vdot(want, want)) < 1e-10 * 10 and abs(np.vdot(vec, vec) - np.vdot(want, want)) < 1e-9
