@@ -101,7 +101,10 @@ int yb_lanczos_combine(int nbatch, const int32_t* mask, yb_extent el, yb_extent 
  * yb_svd_round does one round of a cyclic block sweep (round r of `nrounds`), counting rotations per trajectory.
  * yb_svd_finalize sorts the singular values, applies truncate(mode, threshold, max_bond, min_keep) and writes
  *   keep[b], sval[b][:], U f(S) as rows x keep (row-major) to `uout`, g(S) Vh as keep x cols to `vout`
- *   (dist: 0 = S to the left factor, 1 = right, 2 = sqrt on both). */
+ *   (dist: 0 = S to the left factor, 1 = right, 2 = sqrt on both).
+ * meta[b][7] carries the matrix scale (biased exponent of max |W_ij|^2, accumulated by yb_svd_prepare, cleared by
+ *   yb_svd_finalize; the buffer must be zero before the first yb_svd_prepare): rows whose norm falls below tol * 2^(scale/2) are
+ *   rounding residue of a rank-deficient input, take no part in further rotations and count as exact zeros in finalize. */
 int yb_svd_prepare(int nbatch, const int32_t* mask, int mode, yb_extent el, yb_extent er, int dphys, const void* src, int64_t stride_src,
                    void* w, int64_t stride_w, void* q, int64_t stride_q, int32_t* meta, int32_t* rot_count, void* stream);
 int yb_svd_round(int nbatch, const int32_t* mask, int32_t* meta, int block_rows, int nblocks, int round, int full_panel, int inner_sweeps,
@@ -128,7 +131,7 @@ int yb_svd_gather(int nbatch, const int32_t* mask, const int32_t* meta, const in
                   int64_t stride_w, void* q, int64_t stride_q, void* ws, int64_t stride_ws, void* qs, int64_t stride_qs, void* stream);
 /* After a sweep: meta.done = (rot_count == 0); n_pending (device int32, zeroed by caller) counts unfinished trajectories. */
 int yb_svd_check(int nbatch, const int32_t* mask, int32_t* meta, int32_t* rot_count, int32_t* n_pending, void* stream);
-int yb_svd_finalize(int nbatch, const int32_t* mask, const int32_t* meta, int trunc_mode, double threshold, int max_bond, int min_keep,
+int yb_svd_finalize(int nbatch, const int32_t* mask, int32_t* meta, int trunc_mode, double threshold, int max_bond, int min_keep,
                     int dist, const void* w, int64_t stride_w, const void* q, int64_t stride_q, double* sval, int64_t stride_s,
                     int32_t* keep, int32_t keep_stride, void* uout, int64_t stride_u, void* vout, int64_t stride_v, int32_t* status,
                     int max_k, void* stream);

@@ -296,6 +296,63 @@ def test_svd_rank_deficient_min_keep(backends):
             assert sg[t, 1] < 1e-14 * sg[t, 0]
 
 
+def _run_jacobi_on_matrix(kern, w0, pitch, block_rows, nblocks, inner, max_sweeps=40):
+    """One matrix (k x len, rows to orthogonalise) through prepare / sweeps / finalize(keep all) with a given panel geometry.
+    Returns (singular values, U, Vh, sweeps, rotations per sweep, status)."""
+    dev = kern.device
+    k, ln = w0.shape
+    sq = pitch * pitch
+    src = torch.zeros(sq, dtype=torch.complex128, device=dev)
+    src[: k * ln] = torch.from_numpy(np.ascontiguousarray(w0).reshape(-1)).to(dev)
+    el = torch.tensor([k], dtype=torch.int32, device=dev)
+    er = torch.tensor([ln], dtype=torch.int32, device=dev)
+    w, q, u, v = (torch.zeros(sq, dtype=torch.complex128, device=dev) for _ in range(4))
+    meta = torch.zeros(8, dtype=torch.int32, device=dev)
+    rot = torch.zeros(1, dtype=torch.int32, device=dev)
+    pend = torch.zeros(1, dtype=torch.int32, device=dev)
+    wb, qb = Buf(w, 0, sq), Buf(q, 0, sq)
+    kern.svd_prepare(1, None, K.SVD_ROWS, Ext(el, 0, 1), Ext(er, 0, 1), 1, Buf(src, 0, sq), wb, qb, meta, rot)
+    hist = []
+    for sweep in range(max_sweeps):
+        for rnd in range(nblocks - 1):
+            kern.svd_round(1, None, meta, block_rows, nblocks, rnd, rnd == 0, inner, wb, qb, rot, pitch, pitch)
+        hist.append(int(rot.item()))
+        pend.zero_()
+        kern.svd_check(1, None, meta, rot, pend)
+        if kern.sync_int(pend) == 0:
+            break
+    sval = torch.zeros(pitch, dtype=torch.float64, device=dev)
+    keep = torch.zeros(1, dtype=torch.int32, device=dev)
+    status = torch.zeros(1, dtype=torch.int32, device=dev)
+    kern.svd_finalize(1, None, meta, 0, 0.0, 0, 1, 1, wb, qb, sval, pitch, Ext(keep, 0, 1), Buf(u, 0, sq), Buf(v, 0, sq), status, pitch)
+    kp = int(keep.item())
+    return (sval.cpu().numpy()[:k], u.cpu().numpy()[: k * kp].reshape(k, kp), v.cpu().numpy()[: kp * ln].reshape(kp, ln), sweep + 1, hist,
+            int(status.item()), int(meta.cpu().numpy()[7]))
+
+
+@pytest.mark.parametrize("which", [1, 2, 3])
+@pytest.mark.parametrize("geometry", ["block8_of_256", "block4_of_256", "single_panel"])
+def test_jacobi_converges_on_rank_deficient_post_jump_matrices(backends, golden_dir, which, geometry):
+    """tests/golden/jacobi/rankdef_c3_*.npy: the three chain-end matrices (24 x 28, 14 x 16, 12 x 32; numerical rank 10 / 6 / 8, the
+    rest rounding residue at 1e-19) on which the block schedule of round 1 still rotated after 60 sweeps -- 3 of 256 trajectories of
+    the driver's C3 run ended with status bit 1.  With the per-matrix noise floor every geometry converges in a few sweeps; the
+    factors reproduce the matrix, U is an isometry and the singular values above the floor agree with LAPACK."""
+    cuda, _ = backends
+    w0 = np.load(f"{golden_dir}/jacobi/rankdef_c3_{which}.npy").astype(np.complex128)
+    k, ln = w0.shape
+    pitch, rows, nb, inner = {"block8_of_256": (256, 8, 32, 1), "block4_of_256": (256, 4, 64, 1), "single_panel": (32, 16, 2, 30)}[geometry]
+    sv, u, vh, sweeps, hist, status, scale_word = _run_jacobi_on_matrix(cuda, w0, pitch, rows, nb, inner)
+    ref = np.linalg.svd(w0, compute_uv=False)
+    assert status == 0 and sweeps <= 20, (sweeps, hist)
+    assert scale_word == 0                                       # finalize hands the scale word back cleared
+    floor = 20 * 2.3e-16 * ref[0]
+    big = ref > floor
+    assert np.max(np.abs(sv[: big.sum()] - ref[big])) < 1e-14 * ref[0]
+    assert np.all(sv[big.sum():] <= floor)
+    assert np.max(np.abs(u @ vh - w0)) < 1e-14 * ref[0]          # dist = right: U isometry, S Vh carries the weights
+    assert np.max(np.abs(u.conj().T @ u - np.eye(u.shape[1]))) < 1e-12
+
+
 def _run_heev(kern, dev, ks, mats):
     nb, kmax = len(ks), max(ks)
     sq = kmax * kmax

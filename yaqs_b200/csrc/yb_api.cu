@@ -170,7 +170,7 @@ int yb_svd_check(int nbatch, const int32_t* mask, int32_t* meta, int32_t* rot_co
     return done("yb_svd_check");
 }
 
-int yb_svd_finalize(int nbatch, const int32_t* mask, const int32_t* meta, int trunc_mode, double threshold, int max_bond, int min_keep, int dist,
+int yb_svd_finalize(int nbatch, const int32_t* mask, int32_t* meta, int trunc_mode, double threshold, int max_bond, int min_keep, int dist,
                     const void* w, int64_t stride_w, const void* q, int64_t stride_q, double* sval, int64_t stride_s, int32_t* keep,
                     int32_t keep_stride, void* uout, int64_t stride_u, void* vout, int64_t stride_v, int32_t* status, int max_k, void* stream) {
     if (nbatch <= 0) return 0;

@@ -10,9 +10,27 @@
 #include "yb_common.cuh"
 #include <math.h>
 
-// meta[b][8]: 0 k (rows of W), 1 len (row length), 2 orient (0: W = M, 1: W = M^H), 3 rows(M), 4 cols(M), 5 done, 6 sweeps, 7 spare
+// meta[b][8]: 0 k (rows of W), 1 len (row length), 2 orient (0: W = M, 1: W = M^H), 3 rows(M), 4 cols(M), 5 done, 6 sweeps,
+//             7 scale: SCALE_BIAS + ilogb(max |W_ij|^2), 0 = unset (written by atomicMax in k_svd_prepare, cleared by k_svd_finalize)
 constexpr int META = 8;
 constexpr int SVD_KMAX = 1024;
+constexpr int SCALE_BIAS = 4096;
+
+// Noise floor of a trajectory's matrix (squared): rows whose squared norm is below tol^2 * 2^ilogb(max |W_ij|^2) <= (tol * sigma_max)^2
+// are rounding residue of earlier rotations (rank-deficient input, e.g. a state right after a lowering-operator jump).  They take no
+// further part in the sweeps and count as exact zeros in k_svd_finalize.  The rule is ABSOLUTE per matrix: the pairwise rule it
+// replaces ("skip a pair whose norms differ by more than 1/eps") was not transitive -- a residue row could be skipped against a
+// large row while its equally small neighbour was not, and rotations among the residue rows kept re-mixing the component that
+// was never removed; the block schedule then needed > 60 sweeps on 3 of 256 trajectories of the C3 run
+// (tests/golden/jacobi/rankdef_c3_*.npy are those matrices).
+__device__ __forceinline__ double noise_floor2(const int* m, double tol2) {
+    const int sc = m[7];
+    return sc > 0 ? ldexp(tol2, sc - SCALE_BIAS) : 0.0;
+}
+__device__ __forceinline__ double jacobi_tol2(int len) {
+    const double tolr = fmax(10.0, sqrt((double)len)) * 2.220446049250313e-16;
+    return tolr * tolr;
+}
 
 __global__ void k_svd_prepare(int mode, int dphys, const cplx* __restrict__ src, long long s_src, cplx* w, long long s_w, cplx* q, long long s_q,
                               int* meta, int* rot_count, const int* el, int esl, const int* er, int esr, const int* mask) {
@@ -29,13 +47,14 @@ __global__ void k_svd_prepare(int mode, int dphys, const cplx* __restrict__ src,
     const int k = orient ? cols : rows, len = orient ? rows : cols;
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         int* m = meta + b * META;
-        m[0] = k; m[1] = len; m[2] = orient; m[3] = rows; m[4] = cols; m[5] = 0; m[6] = 0; m[7] = 0;
+        m[0] = k; m[1] = len; m[2] = orient; m[3] = rows; m[4] = cols; m[5] = 0; m[6] = 0;      // m[7]: see META
         rot_count[b] = 0;
     }
     const cplx* sb = src + (long long)b * s_src;
     cplx* wb = w + (long long)b * s_w;
     cplx* qb = q + (long long)b * s_q;
     const long long nw = (long long)k * len;
+    double vmax = 0.0;
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < nw; e += (long long)gridDim.x * blockDim.x) {
         const int i = (int)(e / len), jj = (int)(e % len);
         const int row = orient ? jj : i, col = orient ? i : jj;           // element M[row][col]
@@ -52,14 +71,18 @@ __global__ void k_svd_prepare(int mode, int dphys, const cplx* __restrict__ src,
         cplx v = sb[idx];
         if (orient) v.y = -v.y;
         wb[e] = v;
+        vmax = fmax(vmax, cabs2(v));
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) vmax = fmax(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+    if ((threadIdx.x & 31) == 0 && vmax > 0.0 && isfinite(vmax)) atomicMax(&meta[b * META + 7], SCALE_BIAS + ilogb(vmax));
     const long long nq = (long long)k * k;
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < nq; e += (long long)gridDim.x * blockDim.x)
         qb[e] = make_double2((e / k) == (e % k) ? 1.0 : 0.0, 0.0);
 }
 
 // One pair rotation by a full warp.  wi/wj: rows of W (length len) in shared memory, qi/qj: rows of Q (length k).
-__device__ __forceinline__ int jacobi_pair(cplx* wi, cplx* wj, int len, cplx* qi, cplx* qj, int k, double tol2, int lane) {
+__device__ __forceinline__ int jacobi_pair(cplx* wi, cplx* wj, int len, cplx* qi, cplx* qj, int k, double tol2, double floor2, int lane) {
     double a = 0.0, bb = 0.0, cr = 0.0, ci = 0.0;
     for (int e = lane; e < len; e += 32) {
         const cplx x = wi[e], y = wj[e];
@@ -71,11 +94,9 @@ __device__ __forceinline__ int jacobi_pair(cplx* wi, cplx* wj, int len, cplx* qi
     a = warp_sum(a); bb = warp_sum(bb); cr = warp_sum(cr); ci = warp_sum(ci);
     const double c2 = cr * cr + ci * ci;
     if (!(c2 > tol2 * a * bb) || c2 == 0.0) return 0;
-    // A row whose norm is below eps times its partner's is rounding residue of earlier rotations (rank-deficient input):
-    // orthogonalising it again only produces residue of residue (1e-16 -> 1e-32 -> ...), so it is deflated here.  Its
-    // singular value stays <= eps * sigma_max, i.e. within the absolute accuracy zgesdd gives the reference.
-    constexpr double EPS2 = 2.220446049250313e-16 * 2.220446049250313e-16;
-    if (a < EPS2 * bb || bb < EPS2 * a) return 0;
+    // rows below the matrix's noise floor are deflated (noise_floor2): their singular values stay <= tol * sigma_max, i.e. within
+    // the absolute accuracy zgesdd gives the reference
+    if (a < floor2 || bb < floor2) return 0;
     const double absc = sqrt(c2);
     const double zeta = (bb - a) / (2.0 * absc);
     const double t = fabs(zeta) > 1e100 ? 0.5 / zeta : copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
@@ -129,8 +150,8 @@ __global__ void __launch_bounds__(512) k_svd_round(int block_rows, int nblocks, 
     }
     if (tid == 0) s_rot = 0;
     __syncthreads();
-    const double tolr = fmax(10.0, sqrt((double)len)) * 2.220446049250313e-16;
-    const double tol2 = tolr * tolr;
+    const double tol2 = jacobi_tol2(len);
+    const double floor2 = noise_floor2(m, tol2);
     int report_rot = 0;
     for (int sweep = 0; sweep < inner_sweeps; ++sweep) {
         int my_rot = 0;
@@ -143,7 +164,7 @@ __global__ void __launch_bounds__(512) k_svd_round(int block_rows, int nblocks, 
                     if (pp == 0) { x = n1; y = rr % n1; } else { x = (rr + pp) % n1; y = ((rr - pp) % n1 + n1) % n1; }
                     if (x < nrows && y < nrows)
                         my_rot += jacobi_pair(Wp + (size_t)min(x, y) * max_len, Wp + (size_t)max(x, y) * max_len, len,
-                                              Qp + (size_t)min(x, y) * max_k, Qp + (size_t)max(x, y) * max_k, k, tol2, lane);
+                                              Qp + (size_t)min(x, y) * max_k, Qp + (size_t)max(x, y) * max_k, k, tol2, floor2, lane);
                 }
                 __syncthreads();
             }
@@ -154,7 +175,7 @@ __global__ void __launch_bounds__(512) k_svd_round(int block_rows, int nblocks, 
                     const int x = t, y = (t + qq) % mm;
                     if (x < ni && y < nj)
                         my_rot += jacobi_pair(Wp + (size_t)x * max_len, Wp + (size_t)(ni + y) * max_len, len, Qp + (size_t)x * max_k,
-                                              Qp + (size_t)(ni + y) * max_k, k, tol2, lane);
+                                              Qp + (size_t)(ni + y) * max_k, k, tol2, floor2, lane);
                 }
                 __syncthreads();
             }
@@ -225,13 +246,14 @@ __device__ int truncate_keep(const double* s, int n, int mode, double threshold,
 
 // One CTA per trajectory.
 __global__ void __launch_bounds__(512) k_svd_finalize(int trunc_mode, double threshold, int max_bond, int min_keep, int dist, const cplx* __restrict__ w,
-                                                       long long s_w, const cplx* __restrict__ q, long long s_q, const int* meta, double* sval,
+                                                       long long s_w, const cplx* __restrict__ q, long long s_q, int* meta, double* sval,
                                                        long long s_s, int* keep_out, int keep_stride, cplx* uout, long long s_u, cplx* vout,
                                                        long long s_v, int* status, const int* mask) {
     __shared__ double sig[SVD_KMAX];
     __shared__ double ssort[SVD_KMAX];
     __shared__ int perm[SVD_KMAX];
     __shared__ int s_keep, s_ndef;
+    __shared__ double s_tiny;
     __shared__ double red[32];
     const int b = blockIdx.x;
     if (mask && !mask[b]) return;
@@ -260,17 +282,19 @@ __global__ void __launch_bounds__(512) k_svd_finalize(int trunc_mode, double thr
         for (int i = 0; i < k; ++i) bad |= !isfinite(ssort[i]);
         if (bad || !m[5]) atomicOr(&status[b], bad ? 2 : 1);       // 2: non-finite, 1: Jacobi not converged
         int nd = 0;
-        const double tiny = ssort[0] * 4.5e-16;
+        const double tiny = fmax(ssort[0] * 4.5e-16, sqrt(noise_floor2(m, jacobi_tol2(len))));
+        s_tiny = tiny;
         for (int i = 0; i < s_keep; ++i) nd += !(ssort[i] > tiny);
         s_ndef = nd;
         keep_out[(long long)b * keep_stride] = s_keep;
     }
     __syncthreads();
+    if (tid == 0) meta[b * META + 7] = 0;          // scale word is per factorisation (k_svd_prepare accumulates it with atomicMax)
     const int keep = s_keep;
     for (int i = tid; i < k; i += blockDim.x) sval[(long long)b * s_s + i] = ssort[i];
     cplx* ub = uout + (long long)b * s_u;    // rows x keep
     cplx* vb = vout + (long long)b * s_v;    // keep x cols
-    const double tiny = ssort[0] * 4.5e-16;        // deflated rows (see jacobi_pair) count as exact zeros
+    const double tiny = s_tiny;                    // deflated rows (see noise_floor2) count as exact zeros
     // Q-side factor (exactly unitary rows of Q) and W-side factor (rows of W / sigma)
     if (orient == 0) {
         // U[:, c] = conj(Q[perm c, :]) * f ;  Vh[c, :] = W[perm c, :] * (g / sigma)

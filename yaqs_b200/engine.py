@@ -263,15 +263,12 @@ class BatchedTJM:
         self.scale_buf = torch.zeros(B, dtype=torch.float64, device=dev)
         self.rdm1 = torch.zeros(B * 4, dtype=C128, device=dev)
         self.rdm2 = torch.zeros(B * 16, dtype=C128, device=dev)
-        # Jacobi panel height: largest power of two whose 2*rows*(len+k) panel fits in ~200 KB of shared memory
-        if svd_block_rows is None:
-            svd_block_rows = 16
-            while svd_block_rows > 1 and 2 * svd_block_rows * (2 * sd) * 16 > 200 * 1024:
-                svd_block_rows //= 2
-        self.svd_block_rows = svd_block_rows
-        self.svd_nblocks = max(2, 2 * ((sd + 2 * svd_block_rows - 1) // (2 * svd_block_rows)))
+        # Jacobi panel geometry is chosen per call from the capacities of the matrix at hand (_jacobi_geometry); a test may force
+        # the panel height to exercise the multi-block schedule on small matrices
+        self.svd_block_rows_forced = svd_block_rows
         # Gram-matrix SVD route (Hermitian eigen-solver) for matrices whose Jacobi side would exceed one shared-memory panel
         self.gram_min_k = gram_min_k
+        self._jac_geo: dict = {}
         self.use_gram = sd >= gram_min_k and sd <= 512
         if self.use_gram:
             self.heev_g = torch.zeros(B * sd * sd, dtype=C128, device=dev)
@@ -451,17 +448,38 @@ class BatchedTJM:
     # ------------------------------------------------------------------------------------------------------------------
     # SVD driver + splits / gauge shifts
     # ------------------------------------------------------------------------------------------------------------------
-    def _svd(self, mode: int, src: Buf, el: Ext, er: Ext, trunc, dist: str, mask, kcap: int = 0) -> None:
+    def _svd(self, mode: int, src: Buf, el: Ext, er: Ext, trunc, dist: str, mask, kcap: int = 0, dims: tuple[int, int] | None = None) -> None:
         """Truncated SVD of every trajectory's matrix.  kcap > 0 (capacity of the side that becomes the isometry) selects the
-        Gram-matrix route for large matrices; the one-sided Jacobi is used otherwise and as its accurate fallback."""
+        Gram-matrix route for large matrices; the one-sided Jacobi is used otherwise and as its accurate fallback.  ``dims``:
+        capacities (rows, cols) of the matrix -- they size the Jacobi panels (default: the layout's largest matrix)."""
         if self.use_gram and kcap > 0 and kcap >= self.gram_min_k and dist in ("left", "right") and trunc[0] in (0, 1):
-            self._svd_gram(mode, src, el, er, trunc, dist, mask)
+            self._svd_gram(mode, src, el, er, trunc, dist, mask, dims)
         else:
-            self._svd_jacobi(mode, src, el, er, trunc, dist, mask)
+            self._svd_jacobi(mode, src, el, er, trunc, dist, mask, dims)
+
+    def _jacobi_geometry(self, dims: tuple[int, int] | None) -> tuple[int, int, int, int, int]:
+        """(block_rows, nblocks, inner_sweeps, max_len, max_k) of the one-sided Jacobi for matrices of at most ``dims`` = (rows,
+        cols): the rows being orthogonalised are those of the smaller side (k = min, length = max).  Panel height = the largest
+        power of two <= 16 whose 2 * rows * (len + k) complex panel fits in ~200 KB of shared memory; matrices whose smaller side
+        fits one panel pair (k <= 2 * rows: every chain-end site) take the single-launch schedule with up to 30 in-kernel sweeps."""
+        sd = self.lay.svd_dim
+        kmax, lmax = (sd, sd) if dims is None else (max(1, min(dims)), max(1, max(dims)))
+        kmax, lmax = min(kmax, sd), min(lmax, sd)
+        key = (kmax, lmax)
+        geo = self._jac_geo.get(key)
+        if geo is None:
+            rows = self.svd_block_rows_forced
+            if rows is None:
+                rows = 16
+                while rows > 1 and 2 * rows * (lmax + kmax) * 16 > 200 * 1024:
+                    rows //= 2
+            nb = max(2, 2 * ((kmax + 2 * rows - 1) // (2 * rows)))
+            geo = self._jac_geo[key] = (rows, nb, 30 if nb == 2 else 1, lmax, kmax)
+        return geo
 
     GRAM_TAU = 1e-6          # rows below GRAM_TAU * s_max^2 are re-diagonalised at their own scale (second level)
 
-    def _svd_gram(self, mode: int, src: Buf, el: Ext, er: Ext, trunc, dist: str, mask) -> None:
+    def _svd_gram(self, mode: int, src: Buf, el: Ext, er: Ext, trunc, dist: str, mask, dims: tuple[int, int] | None = None) -> None:
         """M = U S Vh through the Hermitian eigen-problem of a Gram matrix.
         * split_two_site matrices (THETA): the Gram matrix is taken over the index that must become an isometry (rows for
           dist='right', columns for dist='left'), so the isometric factor is the eigenvector matrix itself and the other
@@ -485,7 +503,9 @@ class BatchedTJM:
         K.heev(B, mask, ek, g, qh, zt, self.heev_zr, sq, self.heev_d, self.heev_e, self.heev_tau, sd, self.svd_meta, self.status_scratch, sd)
         K.gemm(OP_EVEC, B, 1, mask, ek, None, None, 1, 1, 1, zt, qh, q, 0, sd, sd)
         K.gemm(OP_ROTATE, B, 1, mask, ek, eln, None, 1, 1, 1, q, w, g, 0, sd, sd)          # Wf -> heev_g
-        two_level = thr < 1e-7
+        # second level only where a threshold has to be resolved below the Gram accuracy; a truncation-free factorisation (thr == 0:
+        # the QR-equivalent gauge moves) needs no singular value at all -- U is the unitary eigenvector matrix, S Vh the exact product
+        two_level = 0.0 < thr < 1e-7
         if two_level:
             ws, qs, g2, hs = w, self._buf(self.svd_u, sq), self._buf(self.svd_v, sq), self._buf(self.heev_s, sq)
             K.svd_select(B, mask, self.svd_meta, g, self.GRAM_TAU, self.sel_n, self.sel_idx, sd)
@@ -525,20 +545,19 @@ class BatchedTJM:
         nfb = K.sync_int(amb.sum())
         if nfb > 0:
             self.stats["gram_fallbacks"] += nfb
-            self._svd_jacobi(mode, src, el, er, trunc, dist, amb.to(torch.int32))
+            self._svd_jacobi(mode, src, el, er, trunc, dist, amb.to(torch.int32), dims)
 
-    def _svd_jacobi(self, mode: int, src: Buf, el: Ext, er: Ext, trunc, dist: str, mask) -> None:
+    def _svd_jacobi(self, mode: int, src: Buf, el: Ext, er: Ext, trunc, dist: str, mask, dims: tuple[int, int] | None = None) -> None:
         """prepare -> cyclic Jacobi sweeps until every trajectory is clean -> finalize (keep, U f(S), g(S) Vh)."""
         K, B, lay = self.K, self.B, self.lay
         sd = lay.svd_dim
         w, q = self._buf(self.svd_w, sd * sd), self._buf(self.svd_q, sd * sd)
         K.svd_prepare(B, mask, mode, el, er, self.d, src, w, q, self.svd_meta, self.svd_rot)
-        nb, rows = self.svd_nblocks, self.svd_block_rows
-        inner = 30 if nb == 2 else 1
+        rows, nb, inner, max_len, max_k = self._jacobi_geometry(dims)
         self.stats["svd_calls"] += 1
         for _sweep in range(60):
             for rnd in range(nb - 1):
-                K.svd_round(B, mask, self.svd_meta, rows, nb, rnd, rnd == 0, inner, w, q, self.svd_rot, sd, sd)
+                K.svd_round(B, mask, self.svd_meta, rows, nb, rnd, rnd == 0, inner, w, q, self.svd_rot, max_len, max_k)
             self.counter.zero_()
             K.svd_check(B, mask, self.svd_meta, self.svd_rot, self.counter)
             self.stats["svd_sweeps"] += 1
@@ -553,7 +572,7 @@ class BatchedTJM:
         lay, K, B, d = self.lay, self.K, self.B, self.d
         sd = lay.svd_dim
         kcap = (d * (lay.cap[i] if dist == "right" else lay.cap[i + 2])) if fast else 0
-        self._svd(SVD_THETA, self._buf(self.theta, lay.theta_slot), st.ext(i), st.ext(i + 2), trunc, dist, mask, kcap)
+        self._svd(SVD_THETA, self._buf(self.theta, lay.theta_slot), st.ext(i), st.ext(i + 2), trunc, dist, mask, kcap, (d * lay.cap[i], d * lay.cap[i + 2]))
         kx = Ext(self.keep, 0, 1)
         K.copy_packed(B, mask, st.ext(i), kx, d, self._buf(self.svd_u, sd * sd), st.site(i), lay.slot[i])
         K.unpack_vh(B, mask, kx, st.ext(i + 2), d, self._buf(self.svd_v, sd * sd), st.site(i + 1), lay.slot[i + 1])
@@ -564,7 +583,8 @@ class BatchedTJM:
         isometry the SVD of the centre tensor alone gives the same singular values / keep decision."""
         lay, K, B, d = self.lay, self.K, self.B, self.d
         sd = lay.svd_dim
-        self._svd(SVD_ROWS, st.site(i), st.ext(i), st.ext(i + 1), trunc, "right", mask, min(d * lay.cap[i], lay.cap[i + 1]) if fast else 0)
+        self._svd(SVD_ROWS, st.site(i), st.ext(i), st.ext(i + 1), trunc, "right", mask, min(d * lay.cap[i], lay.cap[i + 1]) if fast else 0,
+                  (d * lay.cap[i], lay.cap[i + 1]))
         kx = Ext(self.keep, 0, 1)
         K.copy_packed(B, mask, st.ext(i), kx, d, self._buf(self.svd_u, sd * sd), st.site(i), lay.slot[i])
         tmp = self._buf(self.tmp, lay.nloc_max)
@@ -577,7 +597,8 @@ class BatchedTJM:
         """Centre i -> i-1 (mps.py:771-788), reduced form (site i-1 must be a left isometry)."""
         lay, K, B, d = self.lay, self.K, self.B, self.d
         sd = lay.svd_dim
-        self._svd(SVD_COLS, st.site(i), st.ext(i), st.ext(i + 1), trunc, "left", mask, min(lay.cap[i], d * lay.cap[i + 1]) if fast else 0)
+        self._svd(SVD_COLS, st.site(i), st.ext(i), st.ext(i + 1), trunc, "left", mask, min(lay.cap[i], d * lay.cap[i + 1]) if fast else 0,
+                  (lay.cap[i], d * lay.cap[i + 1]))
         kx = Ext(self.keep, 0, 1)
         tmp = self._buf(self.tmp, lay.nloc_max)
         K.gemm(OP_ABSORB_L, B, d, mask, st.ext(i - 1), st.ext(i), kx, d, 1, 1, st.site(i - 1), self._buf(self.svd_u, sd * sd), tmp, 0,
@@ -659,7 +680,7 @@ class BatchedTJM:
             return
         for i in range(n - 1):
             self.update_site(st, i, 1, st.site(i), 0.5 * dt)
-            self._svd(SVD_ROWS, st.site(i), st.ext(i), st.ext(i + 1), keep_all, "right", None)
+            self._svd(SVD_ROWS, st.site(i), st.ext(i), st.ext(i + 1), keep_all, "right", None, 0, (d * lay.cap[i], lay.cap[i + 1]))
             K.copy_packed(B, None, st.ext(i), kx, d, self._buf(self.svd_u, sd * sd), st.site(i), lay.slot[i])
             K.copy_packed(B, None, kx, st.ext(i + 1), 1, self._buf(self.svd_v, sd * sd), cbuf, lay.theta_slot)      # C (k x r_old)
             r_old = st.bond[:, i + 1].clone()
@@ -675,7 +696,7 @@ class BatchedTJM:
             st.bond[:, i + 1] = kt
         self.update_site(st, n - 1, 1, st.site(n - 1), dt)
         for i in reversed(range(1, n)):
-            self._svd(SVD_COLS, st.site(i), st.ext(i), st.ext(i + 1), keep_all, "left", None)
+            self._svd(SVD_COLS, st.site(i), st.ext(i), st.ext(i + 1), keep_all, "left", None, 0, (lay.cap[i], d * lay.cap[i + 1]))
             K.unpack_vh(B, None, kx, st.ext(i + 1), d, self._buf(self.svd_v, sd * sd), st.site(i), lay.slot[i])
             K.copy_packed(B, None, st.ext(i), kx, 1, self._buf(self.svd_u, sd * sd), cbuf, lay.theta_slot)          # C (l_old x k)
             l_old = st.bond[:, i].clone()
@@ -751,7 +772,7 @@ class BatchedTJM:
                 continue
             k1 = None
             if any1:
-                self._svd(SVD_ROWS, st.site(i), st.ext(i), st.ext(i + 1), keep_all, "right", m1i)
+                self._svd(SVD_ROWS, st.site(i), st.ext(i), st.ext(i + 1), keep_all, "right", m1i, 0, (d * lay.cap[i], lay.cap[i + 1]))
                 K.copy_packed(B, m1i, st.ext(i), kx, d, self._buf(self.svd_u, sd * sd), st.site(i), lay.slot[i])
                 K.copy_packed(B, m1i, kx, st.ext(i + 1), 1, self._buf(self.svd_v, sd * sd), cbuf, lay.theta_slot)      # C (k x r_old)
                 k1 = self.keep.clone()
@@ -789,7 +810,7 @@ class BatchedTJM:
                 # QR hand-over to the left by the truncation-free SVD surrogate of sweep_1site; where the new bond would exceed the cap
                 # (the left bond came out of an uncapped split) it is truncated to the cap in Schmidt space.  NOT what the reference
                 # computes here -- see the docstring.
-                self._svd(SVD_COLS, st.site(i), st.ext(i), st.ext(i + 1), cap_only, "left", m1i)
+                self._svd(SVD_COLS, st.site(i), st.ext(i), st.ext(i + 1), cap_only, "left", m1i, 0, (lay.cap[i], d * lay.cap[i + 1]))
                 K.unpack_vh(B, m1i, kx, st.ext(i + 1), d, self._buf(self.svd_v, sd * sd), st.site(i), lay.slot[i])
                 K.copy_packed(B, m1i, st.ext(i), kx, 1, self._buf(self.svd_u, sd * sd), cbuf, lay.theta_slot)          # C (l_old x k)
                 k1 = self.keep.clone()
@@ -957,7 +978,8 @@ class BatchedTJM:
         sd = lay.svd_dim
         self.merge(st, i)
         keep_all = self._trunc_args("discarded_weight", 0.0, None, 1)
-        self._svd(SVD_THETA, self._buf(self.theta, lay.theta_slot), st.ext(i), st.ext(i + 2), keep_all, "right", None, self.d * lay.cap[i])
+        self._svd(SVD_THETA, self._buf(self.theta, lay.theta_slot), st.ext(i), st.ext(i + 2), keep_all, "right", None, self.d * lay.cap[i],
+                  (self.d * lay.cap[i], self.d * lay.cap[i + 2]))
         meta = self.svd_meta.view(B, SVD_META)
         nsv = torch.minimum(meta[:, 3], meta[:, 4])
         sv = self.svd_s.view(B, sd)
