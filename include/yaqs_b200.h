@@ -131,6 +131,12 @@ int yb_svd_gather(int nbatch, const int32_t* mask, const int32_t* meta, const in
                   int64_t stride_w, void* q, int64_t stride_q, void* ws, int64_t stride_ws, void* qs, int64_t stride_qs, void* stream);
 /* After a sweep: meta.done = (rot_count == 0); n_pending (device int32, zeroed by caller) counts unfinished trajectories. */
 int yb_svd_check(int nbatch, const int32_t* mask, int32_t* meta, int32_t* rot_count, int32_t* n_pending, void* stream);
+/* Gram route, closing test: amb[b] = 1 when trajectory b's keep decision lies within the error bound of the threshold (noise_rel *
+ * s_max^2; tau_rel times less for second-level rows), its eigen-solve did not converge (meta done flag / status[b]) or its spectrum is
+ * not finite -- those trajectories are redone by the one-sided Jacobi.  n_amb (one int, zeroed by the caller) counts them.  Replaces the
+ * host-side comparison the reference never needs because LAPACK's zgesdd is backward stable (core/linalg/svd.py:89-104). */
+int yb_svd_ambiguous(int nbatch, const int32_t* mask, const int32_t* meta, const double* sval, int64_t stride_s, int trunc_mode, double threshold,
+                     int two_level, double tau_rel, double noise_rel, const int32_t* status, int32_t* amb, int32_t* n_amb, void* stream);
 int yb_svd_finalize(int nbatch, const int32_t* mask, int32_t* meta, int trunc_mode, double threshold, int max_bond, int min_keep,
                     int dist, const void* w, int64_t stride_w, const void* q, int64_t stride_q, double* sval, int64_t stride_s,
                     int32_t* keep, int32_t keep_stride, void* uout, int64_t stride_u, void* vout, int64_t stride_v, int32_t* status,

@@ -302,6 +302,31 @@ class NumpyKernels:
             _view(uout, t, rows * kp)[:] = np.ascontiguousarray(u).reshape(-1)
             _view(vout, t, kp * cols)[:] = np.ascontiguousarray(vh).reshape(-1)
 
+    def svd_ambiguous(self, nbatch, mask, meta, sval, stride_s, trunc_mode, threshold, two_level, tau_rel, noise_rel, status, amb, n_amb):
+        """Twin of k_svd_ambiguous (csrc/yb_svd.cu): same comparisons, same suffix-sum order."""
+        self._launches += 1
+        mt = _np(meta).reshape(-1, SVD_META)
+        count = 0
+        for t in range(nbatch):
+            if not _on(mask, t):
+                _np(amb)[t] = 0
+                continue
+            nsv = int(min(mt[t, 3], mt[t, 4]))
+            s2 = _np(sval)[t * stride_s: t * stride_s + nsv] ** 2
+            smax2 = float(s2[0]) if nsv else 0.0
+            err_hi = noise_rel * smax2
+            err = np.where(s2 >= tau_rel * smax2, err_hi, err_hi * tau_rel if two_level else err_hi)
+            flag = (mt[t, 5] == 0) or (status is not None and _np(status)[t] != 0) or not np.isfinite(smax2)
+            if trunc_mode == 0:
+                if threshold > 0.0 and nsv:
+                    cum = np.cumsum(s2[::-1])[::-1]
+                    flag = flag or bool(np.any(np.abs(cum - threshold) <= err + 1e-9 * threshold))
+            elif nsv:
+                flag = flag or bool(np.any(np.abs(s2 - threshold * threshold * smax2) <= err))
+            _np(amb)[t] = 1 if flag else 0
+            count += int(bool(flag))
+        _np(n_amb)[0] += count
+
     def svd_select(self, nbatch, mask, meta, w, tau_rel, sel_n, sel_idx, max_k):
         self._launches += 1
         mt = _np(meta).reshape(-1, SVD_META)

@@ -32,3 +32,23 @@ def test_flop_model_matches_survey_headline():
     assert 1.9e12 < fm["total"] < 2.4e12
     assert abs(sum(v for k, v in fm.items() if k != "total") - fm["total"]) < 1e-6 * fm["total"]
     assert 1.1e12 < fm["krylov"] < 1.4e12 and 1.0e11 < fm["gauge_shifts"] < 1.6e11
+
+
+def test_cpu_extrapolation_is_linear_in_chain_length():
+    """The reference arm samples two short saturated chains and extrapolates the half-step time linearly in the chain length
+    (bench.cpu_extrapolate); chains that are not longer than the second sample are timed as they are."""
+    from bench import CPU_SAMPLE_LENGTHS, cpu_extrapolate
+    a, b = CPU_SAMPLE_LENGTHS
+    v, t = cpu_extrapolate({"length": 100}, {a: 4.0, b: 9.0}, 16)
+    assert abs(t - (9.0 + (100 - b) * 5.0 / (b - a))) < 1e-12 and abs(v - 0.5 * 16 / t) < 1e-12
+    v, t = cpu_extrapolate({"length": 10}, {10: 0.5}, 4)
+    assert t == 0.5 and v == 4.0
+
+
+def test_hbm_byte_model():
+    """15 S + 4 E bytes per trajectory-step; C1 (L = 10, chi <= 16, D = 3) is quoted as ~1.7 MB with all bonds at 16."""
+    from bench import hbm_bytes_step
+    bonds = [1.0] + [16.0] * 9 + [1.0]
+    mpo = [1.0] + [3.0] * 9 + [1.0]
+    by = hbm_bytes_step(bonds, mpo)
+    assert 1.2e6 < by < 2.0e6

@@ -307,3 +307,65 @@ def test_digital_get_state_only_run():
         sim.run(State(L), circ, DigitalSimParams())
     with pytest.raises(ValueError, match="noisy circuit simulation"):
         sim.run(State(L), circ, DigitalSimParams(get_state=True), NoiseModel([{"name": "pauli_x", "sites": [0], "strength": 0.1}]))
+
+
+def test_open_advance_result_equals_run():
+    """Simulator.open / AnalogRun.advance / result (step-wise, per-step host I/O) == Simulator.run, bit for bit; the per-step I/O is
+    counted (2 trajectory + 2 sample uniforms per trajectory and step in, one result + diagnostics column out)."""
+    length = 5
+    sp = AnalogSimParams(observables=[Observable(Z(), s) for s in range(length)], elapsed_time=0.5, dt=0.1, num_traj=6, max_bond_dim=4,
+                         svd_threshold=1e-6, order=2, sample_timesteps=True, random_seed=7)
+    noise = NoiseModel([{"name": n, "sites": [i], "strength": 0.3} for i in range(length) for n in ["lowering", "pauli_z"]])
+    args = (State(length, initial="x+"), Hamiltonian.ising(length, J=1, g=0.5), sp, noise)
+    ref = Simulator(show_progress=False, kernels=NumpyKernels()).run(*args)
+    run = Simulator(show_progress=False, kernels=NumpyKernels(), lanes=2, batch_size=6).open(*args)
+    assert run.n_times == 6
+    assert run.advance(1) == 0 and run.advance(2) == 2            # index 0 = initial measurement
+    partial = run.result()
+    assert np.array_equal(partial.trajectories[0][:, :3], ref.trajectories[0][:, :3]) and not partial.trajectories[0][:, 3:].any()
+    assert run.advance(None) == 5 and run.advance(1) == 5
+    res = run.result()
+    for x, y in zip(res.trajectories, ref.trajectories):
+        assert np.array_equal(x, y)
+    assert np.array_equal(res.max_bond, ref.max_bond)
+    h2d, d2h = run.io_bytes()
+    assert h2d == 6 * 6 * 4 * 8 and d2h == 6 * 6 * (length + 3) * 8
+    with pytest.raises(ValueError, match="resident"):
+        Simulator(show_progress=False, kernels=NumpyKernels(), batch_size=2).open(*args)
+
+
+@pytest.mark.parametrize("bit,etype,text", [(1, np.linalg.LinAlgError, "SVD did not converge"), (2, ValueError, "infs or NaNs"),
+                                            (4, ValueError, "Jump probability weights are zero or non-finite"), (8, AssertionError, "Measurement should be real")])
+def test_status_bits_become_reference_exceptions(bit, etype, text):
+    """SURVEY 8b error row: every device status bit maps to the exception type / message of the reference (stochastic_process.py:
+    179-187, mps.py:1233, the scipy.linalg.svd failure modes) and the complete Result travels with it; on_trajectory_error="flag"
+    returns the Result instead, flagged trajectories excluded from the means."""
+    from yaqs_b200 import engine as E
+    from yaqs_b200.simulator import TrajectoryError
+    length = 4
+    sp = AnalogSimParams(observables=[Observable(Z(), s) for s in range(length)], elapsed_time=0.2, dt=0.1, num_traj=5, max_bond_dim=4, order=1,
+                         random_seed=3)
+    noise = NoiseModel([{"name": "pauli_z", "sites": [i], "strength": 0.1} for i in range(length)])
+    args = (State(length, initial="x+"), Hamiltonian.ising(length, J=1, g=0.5), sp, noise)
+    orig = E.BatchedTJM.run_iter
+
+    def flagged(self, *a, **k):
+        for j in orig(self, *a, **k):
+            self.status[1] |= bit                               # what a kernel does when trajectory 1 of the batch goes wrong
+            yield j
+
+    E.BatchedTJM.run_iter = flagged
+    try:
+        with pytest.raises(etype, match=text) as info:
+            Simulator(show_progress=False, kernels=NumpyKernels()).run(*args)
+        exc = info.value
+        assert isinstance(exc, TrajectoryError) and exc.trajectories == (1,) and int(exc.status[1]) == bit
+        assert exc.result is not None and exc.result.trajectories[0].shape == (5, 3)
+        res = Simulator(show_progress=False, kernels=NumpyKernels(), on_trajectory_error="flag").run(*args)
+    finally:
+        E.BatchedTJM.run_iter = orig
+    clean = Simulator(show_progress=False, kernels=NumpyKernels()).run(*args)
+    assert list(res.status) == [0, bit, 0, 0, 0]
+    keep = [0, 2, 3, 4]
+    for k in range(length):
+        assert np.allclose(res.expectation_values[k], clean.trajectories[k][keep].mean(axis=0), atol=1e-15)

@@ -36,9 +36,9 @@ def main():
     ctx = {"call": "?", "tdvp_calls": 0}
     orig_jac = eng._svd_jacobi
 
-    def jac(mode, src, el, er, trunc, dist, mask):
+    def jac(mode, src, el, er, trunc, dist, mask, dims=None):
         before = eng.status.clone()
-        orig_jac(mode, src, el, er, trunc, dist, mask)
+        orig_jac(mode, src, el, er, trunc, dist, mask, dims)
         new = (eng.status != before).nonzero().flatten().tolist()
         if new:
             meta = eng.svd_meta.view(B, -1).cpu().numpy()

@@ -149,9 +149,9 @@ def _single(args, order: int, *, copy_initial_state, rng, sample_timestep_offset
                                          return_states=bool(sim_params.get_state) or return_trajectory_state, sample_at=sample_at,
                                          continue_trajectory=continue_trajectory, return_trajectory_state=return_trajectory_state,
                                          use_trajectory_rng_for_final_sample=use_trajectory_rng_for_final_sample)
-    if int(status[0]) != 0:
-        raise RuntimeError(f"device status word {int(status[0])} for trajectory {traj_idx} (bit 1: SVD not converged, bit 2: non-finite "
-                           "singular values, bit 4: zero jump weights)")
+    if int(status[0]) != 0:                      # the exception type / message the reference raises in that situation (simulator.STATUS_ERRORS)
+        from .simulator import status_exception
+        raise status_exception(np.asarray(status, dtype=np.int32))
     final_mps = None
     if final is not None:
         final_mps = MPS(len(final[0]), tensors=final[0])
@@ -205,7 +205,8 @@ def digital_tjm(args, *, compiled_circuit=None, kernels=None):
     tu, _ = numpy_tables(sp.random_seed, [int(traj_idx)], max(n2q, 1), 1)
     res, diag = eng.run_digital(compiled.layers, torch.from_numpy(tu).to(dev), sp.sample_layers, sp.gate_mode, None)
     if int(eng.status.max().item()) != 0:
-        raise RuntimeError(f"device status word {int(eng.status.max().item())} for trajectory {traj_idx}")
+        from .simulator import status_exception
+        raise status_exception(eng.status.cpu().numpy().astype(np.int32))
     counts = None
     if wants_shots:
         _, shots_of = plan_digital_shots(sp, noisy=noisy)

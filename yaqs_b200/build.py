@@ -12,12 +12,25 @@ SOURCES = ["yb_api.cu", "yb_gemm.cu", "yb_ops.cu", "yb_svd.cu", "yb_heev.cu", "y
 HEADER = os.path.join(os.path.dirname(HERE), "include", "yaqs_b200.h")
 
 
+STAMP = LIB + ".sha256"
+
+
+def source_digest() -> str:
+    """Content hash of every source the library is built from (a checkout or a copy resets mtimes, contents do not lie)."""
+    import hashlib
+    h = hashlib.sha256()
+    for path in sorted([os.path.join(CSRC, s) for s in os.listdir(CSRC) if s.endswith((".cu", ".cuh", ".h"))] + [HEADER]):
+        h.update(os.path.basename(path).encode())
+        with open(path, "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()
+
+
 def needs_build() -> bool:
-    if not os.path.exists(LIB):
+    if not os.path.exists(LIB) or not os.path.exists(STAMP):
         return True
-    t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, s) for s in SOURCES] + [HEADER]
-    return any(os.path.getmtime(d) > t for d in deps)
+    with open(STAMP) as fh:
+        return fh.read().strip() != source_digest()
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
@@ -34,6 +47,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         raise RuntimeError(f"nvcc failed:\n{res.stdout}\n{res.stderr}")
     if verbose:
         print(res.stderr)
+    with open(STAMP, "w") as fh:
+        fh.write(source_digest())
     return LIB
 
 

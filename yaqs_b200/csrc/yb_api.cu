@@ -181,6 +181,15 @@ int yb_svd_finalize(int nbatch, const int32_t* mask, int32_t* meta, int trunc_mo
     return done("yb_svd_finalize");
 }
 
+int yb_svd_ambiguous(int nbatch, const int32_t* mask, const int32_t* meta, const double* sval, int64_t stride_s, int trunc_mode, double threshold,
+                     int two_level, double tau_rel, double noise_rel, const int32_t* status, int32_t* amb, int32_t* n_amb, void* stream) {
+    if (nbatch <= 0) return 0;
+    if (trunc_mode != 0 && trunc_mode != 1) return fail_msg("yb_svd_ambiguous: the Gram route serves truncation modes 0 and 1 only");
+    k_svd_ambiguous<<<(nbatch + 127) / 128, 128, 0, (cudaStream_t)stream>>>(nbatch, meta, sval, stride_s, trunc_mode, threshold, two_level, tau_rel,
+                                                                             noise_rel, status, amb, n_amb, mask);
+    return done("yb_svd_ambiguous");
+}
+
 int yb_svd_select(int nbatch, const int32_t* mask, const int32_t* meta, const void* w, int64_t stride_w, double tau_rel, int32_t* sel_n,
                   int32_t* sel_idx, int max_k, void* stream) {
     if (nbatch <= 0) return 0;

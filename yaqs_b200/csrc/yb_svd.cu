@@ -441,3 +441,43 @@ __global__ void k_svd_gather(int dir, cplx* w, long long s_w, cplx* q, long long
         }
     }
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Gram route, last step: is a trajectory's keep decision within the error bound of its threshold?  Gram eigenvalues carry an
+// absolute error ~ noise_rel * s_max^2 (tau_rel times less for the rows the second level re-diagonalised).  A trajectory is
+// AMBIGUOUS -- and is redone by the one-sided Jacobi -- when a cumulative discarded weight (mode 0) or a relative singular value
+// (mode 1) lies within that bound of the threshold, when the eigen-solver did not converge, or when the spectrum is not finite.
+// One thread per trajectory (the suffix sums run from the smallest value upward, like truncate()); n_amb counts the flagged ones.
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void k_svd_ambiguous(int nbatch, const int* meta, const double* __restrict__ sval, long long s_s, int trunc_mode, double threshold,
+                                int two_level, double tau_rel, double noise_rel, const int* status, int* amb, int* n_amb, const int* mask) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nbatch) return;
+    if (mask && !mask[b]) { amb[b] = 0; return; }
+    const int* m = meta + b * META;
+    const int nsv = min(m[3], m[4]);
+    const double* s = sval + (long long)b * s_s;
+    const double smax2 = nsv > 0 ? s[0] * s[0] : 0.0;
+    const double err_hi = noise_rel * smax2, err_lo = two_level ? err_hi * tau_rel : err_hi;
+    bool flag = (m[5] == 0) || (status && status[b] != 0) || !isfinite(smax2);
+    if (trunc_mode == 0) {
+        if (threshold > 0.0) {
+            double cum = 0.0;
+            for (int i = nsv - 1; i >= 0; --i) {
+                const double s2 = s[i] * s[i];
+                cum += s2;
+                const double err = (s2 >= tau_rel * smax2) ? err_hi : err_lo;
+                flag |= fabs(cum - threshold) <= err + 1e-9 * threshold;
+            }
+        }
+    } else {
+        const double cut = threshold * threshold * smax2;
+        for (int i = 0; i < nsv; ++i) {
+            const double s2 = s[i] * s[i];
+            const double err = (s2 >= tau_rel * smax2) ? err_hi : err_lo;
+            flag |= fabs(s2 - cut) <= err;
+        }
+    }
+    amb[b] = flag ? 1 : 0;
+    if (flag) atomicAdd(n_amb, 1);
+}

@@ -31,6 +31,7 @@ SHIFT_THRESHOLD = 1e-12  # hard-coded policy of SVD gauge shifts (mps.py:757-759
 STATUS_SVD_NOT_CONVERGED = 1
 STATUS_NONFINITE = 2
 STATUS_ZERO_JUMP_WEIGHT = 4
+STATUS_IMAG_PART = 8            # an observable came out with imag >= 1e-13 (the reference asserts, mps.py:1233)
 
 
 @dataclass
@@ -157,22 +158,27 @@ class BatchedState:
             dst[:, :n].copy_(other.A[src.site_off[i]: src.site_off[i] + src.B * src.slot[i]].view(src.B, src.slot[i])[:, :n])
 
     def load(self, tensors_per_traj: Sequence[Sequence[np.ndarray]] | Sequence[np.ndarray]) -> None:
-        """Upload host MPS tensors (s, l, r).  A single MPS (list of arrays) is broadcast to all trajectories."""
+        """Upload host MPS tensors (s, l, r).  A single MPS (list of arrays) is uploaded once and broadcast to all trajectories on
+        the device; per-trajectory states are staged site by site (bounded host memory: one site of the batch at a time)."""
         lay = self.layout
         single = isinstance(tensors_per_traj[0], np.ndarray)
-        host = torch.zeros(lay.state_elems, dtype=C128)
         bond = torch.ones((lay.B, lay.L + 1), dtype=torch.int32)
-        hn = host.numpy()
-        for b in range(lay.B):
-            tensors = tensors_per_traj if single else tensors_per_traj[b]
-            for i, t in enumerate(tensors):
+        dev = self.A.device
+        for i in range(lay.L):
+            per = [tensors_per_traj[i]] if single else [tensors_per_traj[b][i] for b in range(lay.B)]
+            stage = torch.zeros((len(per), lay.slot[i]), dtype=C128)
+            sn = stage.numpy()
+            for row, t in enumerate(per):
                 d, l, r = t.shape
                 if l > lay.cap[i] or r > lay.cap[i + 1] or d != lay.d:
                     raise ValueError(f"site {i}: tensor {t.shape} exceeds the slot capacity ({lay.d},{lay.cap[i]},{lay.cap[i + 1]})")
-                off = lay.site_off[i] + b * lay.slot[i]
-                hn[off: off + t.size] = np.ascontiguousarray(t, dtype=np.complex128).reshape(-1)
-                bond[b, i], bond[b, i + 1] = l, r
-        self.A.copy_(host)
+                sn[row, : t.size] = np.ascontiguousarray(t, dtype=np.complex128).reshape(-1)
+                if single:
+                    bond[:, i], bond[:, i + 1] = l, r
+                else:
+                    bond[row, i], bond[row, i + 1] = l, r
+            dst = self.A[lay.site_off[i]: lay.site_off[i] + lay.B * lay.slot[i]].view(lay.B, lay.slot[i])
+            dst.copy_(stage.to(dev).expand(lay.B, lay.slot[i]) if single else stage.to(dev))
         self.bond.copy_(bond)
 
     def download(self, b: int) -> list[np.ndarray]:
@@ -198,6 +204,7 @@ class BatchedTJM:
         switched to (``run(interval_mpos=...)``); the layout takes the per-bond maximum of their bond dimensions and every MPO is
         zero-padded to it on upload."""
         self.K = kernels
+        self._const_cache = {}
         self.scheduled_jumps = list(scheduled_jumps) if scheduled_jumps else []       # normalised {time, sites, matrix} (order 1 only)
         self.dev = kernels.device
         self.p = params
@@ -262,7 +269,8 @@ class BatchedTJM:
         self.norm_buf = torch.zeros(B, dtype=torch.float64, device=dev)
         self.scale_buf = torch.zeros(B, dtype=torch.float64, device=dev)
         self.rdm1 = torch.zeros(B * 4, dtype=C128, device=dev)
-        self.rdm2 = torch.zeros(B * 16, dtype=C128, device=dev)
+        self._rdm1_all = self._rdm2_all = None          # [L, B, 4] / [L - 1, B, 16] tables of rho_sweep (allocated on first use)
+        self._obs_tab = None
         # Jacobi panel geometry is chosen per call from the capacities of the matrix at hand (_jacobi_geometry); a test may force
         # the panel height to exercise the multi-block schedule on small matrices
         self.svd_block_rows_forced = svd_block_rows
@@ -282,7 +290,7 @@ class BatchedTJM:
             self.sel_n = torch.zeros(B, dtype=torch.int32, device=dev)
             self.sel_idx = torch.zeros(B * sd, dtype=torch.int32, device=dev)
             self.status_scratch = torch.zeros(B, dtype=torch.int32, device=dev)
-            self._iota_sd = torch.arange(sd, device=dev)
+            self.amb = torch.zeros(B, dtype=torch.int32, device=dev)
         # noise tables
         self._noise_cache: dict = {}
         self._set_noise(self._make_noise_ctx(noise))
@@ -339,6 +347,16 @@ class BatchedTJM:
 
     def _buf(self, t: torch.Tensor, slot: int) -> Buf:
         return Buf(t, 0, slot)
+
+    def _const(self, array) -> torch.Tensor:
+        """Device copy of a small host constant (gate, dissipator, jump operator), uploaded once and cached by value: the same
+        2 x 2 / 4 x 4 operators recur at every site, step and gate, and a pageable upload per use is a host synchronisation."""
+        a = np.ascontiguousarray(array, dtype=np.complex128).reshape(-1)
+        key = a.tobytes()
+        t = self._const_cache.get(key)
+        if t is None:
+            t = self._const_cache[key] = torch.from_numpy(a.copy()).to(self.dev)
+        return t
 
     def _set_bond(self, st: BatchedState, j: int, mask) -> None:
         if mask is None:
@@ -436,7 +454,9 @@ class BatchedTJM:
             self.counter.zero_()
             K.lanczos_step(B, j, KRYLOV_MAX, dt, self.p.krylov_tol, el, er, dphys, basis, self.svec, self.alpha, self.beta, self.nrm,
                            self.active, self.kdone, self.coef, self.counter)
-            if K.sync_int(self.counter) == 0:
+            # convergence is per trajectory on the device (`active`); the host only needs to know when nobody is left.  The error
+            # estimate needs j >= 1 and rarely passes before the third vector, so the first two iterations are not read back
+            if j >= 2 and K.sync_int(self.counter) == 0:
                 break
         K.lanczos_combine(B, mask, el, er, dphys, basis, self.svec, self.coef, KRYLOV_MAX, self.kdone, out)
 
@@ -520,32 +540,14 @@ class BatchedTJM:
         K.svd_finalize(B, mask, self.svd_meta, tm, thr, mb, mk, DIST[dist], g, q, self.svd_s, sd, Ext(self.keep, 0, 1),
                        self._buf(self.svd_u, sq), self._buf(self.svd_v, sq), self.status_scratch, sd)
         self.stats["gram_svd_calls"] += 1
-        # ---- keep decisions within the error bound of the threshold -> Jacobi
-        meta = self.svd_meta.view(B, SVD_META)
-        nsv = torch.minimum(meta[:, 3], meta[:, 4])
-        valid = self._iota_sd[None, :] < nsv[:, None]
-        s = self.svd_s.view(B, sd)
-        s2 = torch.where(valid, s * s, torch.zeros_like(s))
-        smax2 = s2[:, 0]
-        noise = 16.0 * sd * 2.220446049250313e-16
-        err = noise * smax2[:, None].expand(B, sd)
-        if two_level:
-            err = torch.where(s2 >= self.GRAM_TAU * smax2[:, None], err, err * self.GRAM_TAU)
-        if tm == 0:
-            if thr > 0.0:
-                cum = torch.flip(torch.cumsum(torch.flip(s2, dims=[1]), dim=1), dims=[1])
-                amb = (((cum - thr).abs() <= err + 1e-9 * thr) & valid).any(dim=1)
-            else:
-                amb = torch.zeros(B, dtype=torch.bool, device=self.dev)
-        else:
-            amb = (((s2 - thr * thr * smax2[:, None]).abs() <= err) & valid).any(dim=1)
-        amb |= (meta[:, 5] == 0) | (self.status_scratch != 0) | ~torch.isfinite(smax2)
-        if mask is not None:
-            amb &= (mask != 0)
-        nfb = K.sync_int(amb.sum())
+        # ---- keep decisions within the error bound of the threshold -> Jacobi (one kernel + one host read per factorisation)
+        self.counter.zero_()
+        K.svd_ambiguous(B, mask, self.svd_meta, self.svd_s, sd, tm, thr, two_level, self.GRAM_TAU, 16.0 * sd * 2.220446049250313e-16,
+                        self.status_scratch, self.amb, self.counter)
+        nfb = K.sync_int(self.counter)
         if nfb > 0:
             self.stats["gram_fallbacks"] += nfb
-            self._svd_jacobi(mode, src, el, er, trunc, dist, amb.to(torch.int32), dims)
+            self._svd_jacobi(mode, src, el, er, trunc, dist, self.amb.clone(), dims)
 
     def _svd_jacobi(self, mode: int, src: Buf, el: Ext, er: Ext, trunc, dist: str, mask, dims: tuple[int, int] | None = None) -> None:
         """prepare -> cyclic Jacobi sweeps until every trajectory is clean -> finalize (keep, U f(S), g(S) Vh)."""
@@ -908,14 +910,14 @@ class BatchedTJM:
         for i in reversed(range(n)):
             op1, scalar2, pair = facs[i]
             if op1 is not None:
-                op_t = torch.from_numpy(np.ascontiguousarray(op1, dtype=np.complex128).reshape(-1)).to(self.dev)
+                op_t = self._const(op1)
                 K.apply_local_op(B, None, None, 0, st.ext(i), st.ext(i + 1), d, op_t, 0, st.site(i), lay.cap[i] * lay.cap[i + 1])
             if scalar2 is not None:
-                op_t = torch.from_numpy((scalar2 * np.eye(2, dtype=np.complex128)).reshape(-1)).to(self.dev)
+                op_t = self._const(scalar2 * np.eye(2, dtype=np.complex128))
                 K.apply_local_op(B, None, None, 0, st.ext(i), st.ext(i + 1), d, op_t, 0, st.site(i), lay.cap[i] * lay.cap[i + 1])
             if pair is not None:
                 th = self.merge(st, i - 1)
-                op_t = torch.from_numpy(np.ascontiguousarray(pair, dtype=np.complex128).reshape(-1)).to(self.dev)
+                op_t = self._const(pair)
                 K.apply_local_op(B, None, None, 0, st.ext(i - 1), st.ext(i + 1), d * d, op_t, 0, th, lay.cap[i - 1] * lay.cap[i + 1])
                 self.split_theta(st, i - 1, "right", user, fast=True)
             if i != 0:
@@ -925,13 +927,18 @@ class BatchedTJM:
     # local reduced density matrices by a left-to-right transfer sweep (observables + jump weights)
     # ------------------------------------------------------------------------------------------------------------------
     def rho_sweep(self, st: BatchedState, need1: Sequence[int], need2: Sequence[int], mask=None):
-        """g1[i][b,o,p] = <psi| |o><p|_i |psi> for i in need1 and the two-site analogue for pairs (i,i+1), i in need2,
+        """g1[i, b, o, p] = <psi| |o><p|_i |psi> for i in need1 and the two-site analogue g2[i] for pairs (i, i+1), i in need2,
         valid when every site right of the queried one is a right isometry (centre 0).  Replaces the reference's
-        copy + QR-shift + local contraction (mps.py:1178-1234, stochastic_process.py:139-176) by two GEMMs per site."""
+        copy + QR-shift + local contraction (mps.py:1178-1234, stochastic_process.py:139-176) by two GEMMs per site.  The local
+        density matrices of all sites land in two device tables ([L, B, d, d] and [L - 1, B, d^2, d^2]; rows outside need1 /
+        need2 are stale), so one batched contraction per observable kind follows instead of one per observable."""
         lay, K, B, d, n = self.lay, self.K, self.B, self.d, self.L
         need1, need2 = set(need1), set(need2)
         last = max([*need1, *[i + 1 for i in need2], 0])
-        out1, out2 = {}, {}
+        if self._rdm1_all is None:
+            self._rdm1_all = torch.zeros((n, B, d * d), dtype=C128, device=self.dev)
+        if need2 and self._rdm2_all is None:
+            self._rdm2_all = torch.zeros((max(n - 1, 1), B, d ** 4), dtype=C128, device=self.dev)
         x = self._buf(self.T1, lay.t_slot)
         K.env_identity(B, mask, st.ext(0), 1, Buf(self.lenv, lay.env_off[0], lay.env_slot[0]), 1)
         for i in range(last + 1):
@@ -939,36 +946,50 @@ class BatchedTJM:
             if i in need2:
                 th = self.merge(st, i, mask)
                 K.gemm(OP_LCONTRACT, B, d * d, mask, st.ext(i), st.ext(i + 2), None, d * d, 1, 1, e_i, th, x, 0, lay.cap[i], lay.cap[i + 2])
-                K.local_rdm(B, mask, st.ext(i), st.ext(i + 2), d * d, th, x, self.rdm2)
-                out2[i] = self.rdm2.view(B, d * d, d * d).clone()
+                K.local_rdm(B, mask, st.ext(i), st.ext(i + 2), d * d, th, x, self._rdm2_all[i])
             a = st.site(i)
             K.gemm(OP_LCONTRACT, B, d, mask, st.ext(i), st.ext(i + 1), None, d, 1, 1, e_i, a, x, 0, lay.cap[i], lay.cap[i + 1])
             if i in need1:
-                K.local_rdm(B, mask, st.ext(i), st.ext(i + 1), d, a, x, self.rdm1)
-                out1[i] = self.rdm1.view(B, d, d).clone()
+                K.local_rdm(B, mask, st.ext(i), st.ext(i + 1), d, a, x, self._rdm1_all[i])
             if i < last:
                 e_n = Buf(self.lenv, lay.env_off[i + 1], lay.env_slot[i + 1])
                 K.gemm(OP_ENVL3, B, 1, mask, st.ext(i), st.ext(i + 1), None, d, 1, 1, x, a, e_n, 1, lay.cap[i + 1], lay.cap[i + 1])
-        return out1, out2
+        g2 = self._rdm2_all.view(-1, B, d * d, d * d) if self._rdm2_all is not None else None
+        return self._rdm1_all.view(n, B, d, d), g2
+
+    def _observable_tables(self) -> dict:
+        """Device tables of the local observables, built once: operator stacks and site / column indices per kind."""
+        if self._obs_tab is None:
+            one = [(k, m, s[0]) for k, (m, s) in enumerate(self.observables) if not isinstance(m, str) and len(s) == 1]
+            two = [(k, m, s[0]) for k, (m, s) in enumerate(self.observables) if not isinstance(m, str) and len(s) == 2]
+            for _, (m, s) in enumerate(self.observables):
+                if not isinstance(m, str) and len(s) == 2 and s[1] != s[0] + 1:
+                    raise AssertionError("Only nearest-neighbor observables are currently implemented.")
+            tab = {"need1": sorted({s for _, _, s in one}), "need2": sorted({s for _, _, s in two}), "any": bool(one or two)}
+            for name, items in (("one", one), ("two", two)):
+                if items:
+                    tab[name] = (torch.tensor([k for k, _, _ in items], dtype=torch.int64, device=self.dev),
+                                 torch.tensor([s for _, _, s in items], dtype=torch.int64, device=self.dev),
+                                 torch.from_numpy(np.stack([m for _, m, _ in items])).to(self.dev))
+            self._obs_tab = tab
+        return self._obs_tab
 
     def evaluate_observables(self, st: BatchedState) -> torch.Tensor:
-        """[B, n_obs] expectation values in the given (sorted) observable order (mps.py:1178-1234)."""
-        local = [(m, s) for m, s in self.observables if not isinstance(m, str)]
-        need1 = [s[0] for _, s in local if len(s) == 1]
-        need2 = [s[0] for _, s in local if len(s) == 2]
-        for _, s in local:
-            if len(s) == 2 and s[1] != s[0] + 1:
-                raise AssertionError("Only nearest-neighbor observables are currently implemented.")
-        g1, g2 = self.rho_sweep(st, need1, need2) if local else ({}, {})
+        """[B, n_obs] expectation values in the given (sorted) observable order (mps.py:1178-1234).  A value whose imaginary
+        part violates the reference's ``assert exp.imag < 1e-13`` (mps.py:1233) raises status bit 8 for that trajectory."""
+        tab = self._observable_tables()
         res = torch.zeros((self.B, len(self.observables)), dtype=torch.float64, device=self.dev)
+        if tab["any"]:
+            g1, g2 = self.rho_sweep(st, tab["need1"], tab["need2"])
+            for name, g in (("one", g1), ("two", g2)):
+                if name in tab:
+                    cols, sites, mats = tab[name]
+                    val = torch.einsum("kop,kbop->bk", mats, g[sites])
+                    res[:, cols] = val.real
+                    self.status |= (val.imag >= 1e-13).any(dim=1).to(torch.int32) * STATUS_IMAG_PART
         for k, (mat, sites) in enumerate(self.observables):
             if isinstance(mat, str):
                 res[:, k] = self.entropy_of_cut(st, sites[0]) if mat == "entropy" else self.project_onto_bitstring(st, mat[4:])
-                continue
-            g = g1[sites[0]] if len(sites) == 1 else g2[sites[0]]
-            m = torch.from_numpy(mat).to(self.dev)
-            val = torch.einsum("op,bop->b", m, g)
-            res[:, k] = val.real
         return res
 
     def entropy_of_cut(self, st: BatchedState, i: int) -> torch.Tensor:
@@ -1009,7 +1030,7 @@ class BatchedTJM:
                 K.gemm(OP_ABSORB_R, B, d, None, one, st.ext(site), er, d, 1, 1, carry, st.site(site), tmp, 0, 1, lay.cap[site + 1])
             sel = np.zeros((d, d), dtype=np.complex128)
             sel[0, bit] = 1.0                                            # slice 0 <- slice `bit`, the rest <- 0
-            K.apply_local_op(B, None, None, 0, one, er, d, torch.from_numpy(sel.reshape(-1)).to(self.dev), 0, tmp, lay.cap[site + 1])
+            K.apply_local_op(B, None, None, 0, one, er, d, self._const(sel), 0, tmp, lay.cap[site + 1])
             K.norm2(B, None, one, er, d, tmp, self.norm_buf)
             nrm = torch.sqrt(self.norm_buf)
             total = total * nrm
@@ -1098,28 +1119,53 @@ class BatchedTJM:
                             raise NotImplementedError("Non-Pauli long-range two-site jumps are not supported")
         return table
 
+    def _jump_tables(self) -> dict:
+        """Device tables of the current noise context's jump table (built once per context): for the weights, L^dagger L stacks
+        with site / column indices per kind; for the application, the operator of every process as a 2 x 2 / 4 x 4 row."""
+        ctx = self._nctx
+        tab = ctx.get("dev")
+        if tab is None:
+            procs, dev = self.jump_table, self.dev
+            eye2, eye4 = np.eye(2, dtype=np.complex128), np.eye(4, dtype=np.complex128)
+            one = [(k, pr.sites[0], pr.ldl if pr.kind == "one" else eye2) for k, pr in enumerate(procs) if pr.kind in ("one", "pauli_lr", "pauli_adj")]
+            two = [(k, pr.sites[0], pr.ldl) for k, pr in enumerate(procs) if pr.kind == "adjacent"]
+            tab = {"need1": sorted({s for _, s, _ in one}), "need2": sorted({s for _, s, _ in two}),
+                   "strength": torch.tensor([pr.strength for pr in procs], dtype=torch.float64, device=dev)}
+            for name, items in (("one", one), ("two", two)):
+                if items:
+                    tab[name] = (torch.tensor([k for k, _, _ in items], dtype=torch.int64, device=dev),
+                                 torch.tensor([s_ for _, s_, _ in items], dtype=torch.int64, device=dev),
+                                 torch.from_numpy(np.stack([m for _, _, m in items]).astype(np.complex128)).to(dev))
+            # application tables (host copies drive the per-site launch plan, device copies are gathered by `choice`)
+            tab["kind"] = [pr.kind for pr in procs]
+            tab["site_a"] = np.array([pr.sites[0] if pr.kind in ("one", "pauli_lr") else -1 for pr in procs], dtype=np.int32)
+            tab["site_b"] = np.array([pr.sites[1] if pr.kind == "pauli_lr" else -1 for pr in procs], dtype=np.int32)
+            tab["site_c"] = np.array([pr.sites[0] if pr.kind in ("adjacent", "pauli_adj") else -1 for pr in procs], dtype=np.int32)
+            tab["ops_a"] = torch.from_numpy(np.stack([pr.ops[0] if pr.kind in ("one", "pauli_lr") else eye2 for pr in procs]).astype(np.complex128)).to(dev)
+            tab["ops_b"] = torch.from_numpy(np.stack([pr.ops[1] if pr.kind == "pauli_lr" else eye2 for pr in procs]).astype(np.complex128)).to(dev)
+            tab["ops_c"] = torch.from_numpy(np.stack([pr.ops[0] if pr.kind in ("adjacent", "pauli_adj") else eye4 for pr in procs]).astype(np.complex128)).to(dev)
+            ctx["dev"] = tab
+        return tab
+
     def jump_weights(self, st: BatchedState, dt: float, mask) -> torch.Tensor:
-        """[B, n_proc] un-normalised weights dt * gamma * ||L psi||^2 in site-sweep order (stochastic_process.py:86-187)."""
-        tab = self.jump_table
-        need1 = sorted({p.sites[0] for p in tab if p.kind in ("one", "pauli_lr", "pauli_adj")})
-        need2 = sorted({p.sites[0] for p in tab if p.kind == "adjacent"})
-        g1, g2 = self.rho_sweep(st, need1, need2, mask)
-        w = torch.zeros((self.B, len(tab)), dtype=torch.float64, device=self.dev)
-        for k, pr in enumerate(tab):
-            if pr.kind == "one":
-                m = torch.from_numpy(pr.ldl).to(self.dev)
-                w[:, k] = dt * pr.strength * torch.einsum("op,bop->b", m, g1[pr.sites[0]]).real
-            elif pr.kind in ("pauli_lr", "pauli_adj"):
-                w[:, k] = dt * pr.strength * torch.einsum("boo->b", g1[pr.sites[0]]).real
-            else:
-                m = torch.from_numpy(pr.ldl).to(self.dev)
-                w[:, k] = dt * pr.strength * torch.einsum("op,bop->b", m, g2[pr.sites[0]]).real
-        return w
+        """[B, n_proc] un-normalised weights dt * gamma * ||L psi||^2 in site-sweep order (stochastic_process.py:86-187): one
+        transfer sweep for the local density matrices, then one batched contraction Tr(L^dagger L rho) per process kind (Pauli
+        processes: L^dagger L = 1, the centre-site norm of :159-163)."""
+        tab = self._jump_tables()
+        g1, g2 = self.rho_sweep(st, tab["need1"], tab["need2"], mask)
+        w = torch.zeros((self.B, len(self.jump_table)), dtype=torch.float64, device=self.dev)
+        for name, g in (("one", g1), ("two", g2)):
+            if name in tab:
+                cols, sites, mats = tab[name]
+                w[:, cols] = torch.einsum("kop,kbop->bk", mats, g[sites]).real
+        return w * (dt * tab["strength"])[None, :]
 
     def stochastic_process(self, st: BatchedState, dt: float, u1: torch.Tensor | None, u2: torch.Tensor | None, log: list | None = None,
                            tag: str = "") -> torch.Tensor | None:
         """One jump test for every trajectory.  u1/u2: [B] uniforms (u2 is consumed only by trajectories that jump).
-        Returns the int32 jump mask (or None when there is no noise model)."""
+        Returns the int32 jump mask (or None when there is no noise model).  Host synchronisations: one read of the jump mask,
+        and -- only when somebody jumps -- one read of (weight totals, selected processes), from which the whole launch plan
+        of the jump application is made on the host."""
         K, B, lay, d, n = self.K, self.B, self.lay, self.d, self.L
         if self.noise is None:
             self.normalize_site(st, 0)                      # :226-231 (the uniform is not drawn)
@@ -1128,10 +1174,11 @@ class BatchedTJM:
         dp = 1.0 - self.norm_buf
         jump = (u1 < dp)
         jmask = jump.to(torch.int32)
-        njump = K.sync_int(jmask.sum())
+        jump_h = jump.cpu().numpy()                         # sync 1
+        njump = int(jump_h.sum())
         rec = None
         if log is not None:
-            rec = dict(tag=tag, dp=dp.cpu().numpy().copy(), u1=u1.cpu().numpy().copy(), jumped=jump.cpu().numpy().copy(), choice=None, pdf=None)
+            rec = dict(tag=tag, dp=dp.cpu().numpy().copy(), u1=u1.cpu().numpy().copy(), jumped=jump_h.copy(), choice=None, pdf=None)
             log.append(rec)
         if njump < B:
             self.normalize_site(st, 0, None if njump == 0 else (1 - jmask))
@@ -1140,21 +1187,23 @@ class BatchedTJM:
         self.stats["jumps"] += njump
         w = self.jump_weights(st, dt, jmask)
         total = w.sum(dim=1)
-        bad = jump & ~(torch.isfinite(total) & (total > 0))
-        if K.sync_int(bad.to(torch.int32).sum()) > 0:
-            self.status |= bad.to(torch.int32) * STATUS_ZERO_JUMP_WEIGHT
-            raise ValueError("Jump probability weights are zero or non-finite. Reduce process strengths and/or the timestep dt so that "
-                             "dt * strength * ||L|psi>||^2 remains representable.")
-        total = torch.where(jump, total, torch.ones_like(total))
-        probs = w / total[:, None]
+        safe = torch.where(jump & torch.isfinite(total) & (total > 0), total, torch.ones_like(total))
+        probs = w / safe[:, None]
         cdf = torch.cumsum(probs, dim=1)
         cdf = cdf / torch.where(jump, cdf[:, -1], torch.ones_like(total))[:, None]
         choice = torch.searchsorted(cdf, u2[:, None].contiguous(), right=True).squeeze(1).clamp(max=len(self.jump_table) - 1)
+        host = torch.stack([total, choice.to(torch.float64)]).cpu().numpy()      # sync 2
+        total_h, choice_h = host[0], host[1].astype(np.int64)
+        bad_h = jump_h & ~(np.isfinite(total_h) & (total_h > 0))
+        if bad_h.any():
+            self.status |= torch.from_numpy(bad_h.astype(np.int32) * STATUS_ZERO_JUMP_WEIGHT).to(self.dev)
+            raise ValueError("Jump probability weights are zero or non-finite. Reduce process strengths and/or the timestep dt so that "
+                             "dt * strength * ||L|psi>||^2 remains representable.")
         if rec is not None:
-            rec["choice"] = choice.cpu().numpy().copy()
+            rec["choice"] = choice_h.copy()
             rec["pdf"] = probs.cpu().numpy().copy()
             rec["u2"] = u2.cpu().numpy().copy()
-        self._apply_jumps(st, jmask, choice)
+        self._apply_jumps(st, jmask, choice, jump_h, choice_h)
         return jmask
 
     def has_scheduled_jump(self, time: float) -> bool:
@@ -1173,7 +1222,7 @@ class BatchedTJM:
             if not np.isclose(jump["time"], time, atol=p.dt * 1e-3, rtol=0.0):
                 continue
             sites = list(jump["sites"])
-            op = torch.from_numpy(np.ascontiguousarray(jump["matrix"], dtype=np.complex128).reshape(-1)).to(self.dev)
+            op = self._const(jump["matrix"])
             if len(sites) == 1:
                 s_ = sites[0]
                 K.apply_local_op(B, None, None, 0, st.ext(s_), st.ext(s_ + 1), d, op, 0, st.site(s_), lay.cap[s_] * lay.cap[s_ + 1])
@@ -1194,71 +1243,84 @@ class BatchedTJM:
                              "The jump operator annihilates the current state.")
         self.normalize_site(st, 0)
 
-    def _apply_jumps(self, st: BatchedState, jmask: torch.Tensor, choice: torch.Tensor) -> None:
+    def _apply_jumps(self, st: BatchedState, jmask: torch.Tensor, choice: torch.Tensor, jump_h: np.ndarray, choice_h: np.ndarray) -> None:
         """Left-canonicalise the jumping trajectories (the reference's PDF sweep leaves the centre at L-1,
         stochastic_process.py:139-141), apply the selected operators (:251-288) and renormalise with the right-to-left
-        SVD sweep of normalize("B", "SVD") (:291, mps.py:815-839)."""
+        SVD sweep of normalize("B", "SVD") (:291, mps.py:815-839).  ``jump_h`` / ``choice_h``: host copies of the jump mask and
+        the selected process per trajectory -- every launch decision below is made from them, no further host reads."""
         K, B, lay, d, n, p = self.K, self.B, self.lay, self.d, self.L, self.p
-        tab = self.jump_table
+        tab = self._jump_tables()
         dev = self.dev
         keep_all = self._trunc_args("discarded_weight", 0.0, None, 1)
         shift = self._trunc_args("discarded_weight", SHIFT_THRESHOLD, None, 1)
         user = self._trunc_args(p.trunc_mode, p.svd_threshold, p.max_bond_dim, 1)
         for i in range(n - 1):
             self.shift_right(st, i, keep_all, jmask, fast=True)
-        # per-trajectory operator tables
-        kinds = {pr.kind for pr in tab}
-        site_a = torch.tensor([pr.sites[0] for pr in tab], dtype=torch.int32, device=dev)[choice]
-        ops_a = torch.from_numpy(np.stack([pr.ops[0] if pr.kind in ("one", "pauli_lr") else np.eye(2) for pr in tab]).astype(np.complex128)).to(dev)[choice].contiguous()
-        is_a = torch.tensor([1 if pr.kind in ("one", "pauli_lr") else 0 for pr in tab], dtype=torch.int32, device=dev)[choice]
-        broken = [torch.where((jmask != 0) & (is_a != 0), site_a, torch.full_like(site_a, -1))]
-        mask_a = jmask * is_a
-        for s in range(n):
-            K.apply_local_op(B, mask_a, site_a, s, st.ext(s), st.ext(s + 1), d, ops_a.view(-1), d * d, st.site(s), lay.cap[s] * lay.cap[s + 1])
-        if "pauli_lr" in kinds:
-            site_b = torch.tensor([pr.sites[1] if pr.kind == "pauli_lr" else -1 for pr in tab], dtype=torch.int32, device=dev)[choice]
-            ops_b = torch.from_numpy(np.stack([pr.ops[1] if pr.kind == "pauli_lr" else np.eye(2) for pr in tab]).astype(np.complex128)).to(dev)[choice].contiguous()
-            mask_b = jmask * (site_b >= 0).to(torch.int32)
-            for s in range(n):
-                K.apply_local_op(B, mask_b, site_b, s, st.ext(s), st.ext(s + 1), d, ops_b.view(-1), d * d, st.site(s), lay.cap[s] * lay.cap[s + 1])
-            broken.append(torch.where(mask_b != 0, site_b, torch.full_like(site_b, -1)))
-        if kinds & {"adjacent", "pauli_adj"}:
-            site_c = torch.tensor([pr.sites[0] if pr.kind in ("adjacent", "pauli_adj") else -1 for pr in tab], dtype=torch.int32, device=dev)[choice]
-            ops_c = torch.from_numpy(np.stack([pr.ops[0] if pr.kind in ("adjacent", "pauli_adj") else np.eye(4) for pr in tab]).astype(np.complex128)).to(dev)[choice].contiguous()
-            mask_c = jmask * (site_c >= 0).to(torch.int32)
-            if K.sync_int(mask_c.sum()) > 0:
-                for s in range(n - 1):
-                    m_s = mask_c * (site_c == s).to(torch.int32)
-                    if K.sync_int(m_s.sum()) == 0:
-                        continue
-                    th = self.merge(st, s, m_s)
-                    K.apply_local_op(B, m_s, None, 0, st.ext(s), st.ext(s + 2), d * d, ops_c.view(-1), d * d * d * d, th, lay.cap[s] * lay.cap[s + 2])
-                    self.split_theta(st, s, "right", user, m_s, fast=True)
-                broken.append(torch.where(mask_c != 0, site_c + 1, torch.full_like(site_c, -1)))
+        # per-trajectory sites (host) and operators (device, gathered by the selected process)
+        sa_h = np.where(jump_h, tab["site_a"][choice_h], -1).astype(np.int32)
+        sb_h = np.where(jump_h, tab["site_b"][choice_h], -1).astype(np.int32)
+        sc_h = np.where(jump_h, tab["site_c"][choice_h], -1).astype(np.int32)
+        # site whose left-isometry property a jump breaks: the site itself for one-site operators, the right site of a pair
+        broken = np.zeros((n, B), dtype=bool)
+        for arr, off in ((sa_h, 0), (sb_h, 0), (sc_h, 1)):
+            rows = np.nonzero(arr >= 0)[0]
+            broken[arr[rows] + off, rows] = True
+        lit_h = np.zeros((n, B), dtype=np.int32)           # row i: trajectories that need the literal merge + split at bond i
+        lit_h[1:] = (broken[:-1] & jump_h[None, :])
+        red_h = (jump_h[None, :] & (lit_h == 0)).astype(np.int32)
+        plan = torch.from_numpy(np.concatenate([sa_h[None], sb_h[None], sc_h[None], lit_h, red_h])).to(dev)      # one upload
+        site_a, site_b, site_c = plan[0], plan[1], plan[2]
+        lit_d, red_d = plan[3: 3 + n], plan[3 + n: 3 + 2 * n]
+        if (sa_h >= 0).any():
+            ops_a = tab["ops_a"][choice].contiguous()
+            mask_a = (site_a >= 0).to(torch.int32)
+            for s_ in np.unique(sa_h[sa_h >= 0]):
+                s_ = int(s_)
+                K.apply_local_op(B, mask_a, site_a, s_, st.ext(s_), st.ext(s_ + 1), d, ops_a.view(-1), d * d, st.site(s_), lay.cap[s_] * lay.cap[s_ + 1])
+        if (sb_h >= 0).any():
+            ops_b = tab["ops_b"][choice].contiguous()
+            mask_b = (site_b >= 0).to(torch.int32)
+            for s_ in np.unique(sb_h[sb_h >= 0]):
+                s_ = int(s_)
+                K.apply_local_op(B, mask_b, site_b, s_, st.ext(s_), st.ext(s_ + 1), d, ops_b.view(-1), d * d, st.site(s_), lay.cap[s_] * lay.cap[s_ + 1])
+        if (sc_h >= 0).any():
+            ops_c = tab["ops_c"][choice].contiguous()
+            for s_ in np.unique(sc_h[sc_h >= 0]):
+                s_ = int(s_)
+                m_s = (site_c == s_).to(torch.int32)
+                th = self.merge(st, s_, m_s)
+                K.apply_local_op(B, m_s, None, 0, st.ext(s_), st.ext(s_ + 2), d * d, ops_c.view(-1), d * d * d * d, th, lay.cap[s_] * lay.cap[s_ + 2])
+                self.split_theta(st, s_, "right", user, m_s, fast=True)
         # normalize("B", "SVD"): right-to-left merged SVD shifts.  Where the left neighbour is still a left isometry the
         # reduced shift is identical; where it carries a jump operator the literal merge + split is needed.
-        th_trunc_left = shift
+        nlit, nred = lit_h.sum(axis=1), red_h.sum(axis=1)
         for i in reversed(range(1, n)):
-            lit = torch.zeros(B, dtype=torch.bool, device=dev)
-            for br in broken:
-                lit |= (br == (i - 1))
-            lit_mask = jmask * lit.to(torch.int32)
-            red_mask = jmask * (~lit).to(torch.int32)
-            nlit = K.sync_int(lit_mask.sum())
-            if nlit > 0:
-                self.merge(st, i - 1, lit_mask)
-                self.split_theta(st, i - 1, "left", th_trunc_left, lit_mask, fast=True)
-            if nlit < K.sync_int(jmask.sum()):
-                self.shift_left(st, i, shift, red_mask, fast=True)
+            if nlit[i] > 0:
+                self.merge(st, i - 1, lit_d[i])
+                self.split_theta(st, i - 1, "left", shift, lit_d[i], fast=True)
+            if nred[i] > 0:
+                self.shift_left(st, i, shift, red_d[i], fast=True)
         self.normalize_site(st, 0, jmask)
 
     # ------------------------------------------------------------------------------------------------------------------
     # trajectory drivers (analog/analog_tjm.py:86-462)
     # ------------------------------------------------------------------------------------------------------------------
-    def run(self, traj_uniforms: torch.Tensor | None, sample_uniforms: torch.Tensor | None, log: list | None = None, *,
-            start_pos: torch.Tensor | None = None, sample_at: Sequence[int] | None = None, continue_trajectory: bool = False,
-            interval_mpos: Sequence[Sequence[np.ndarray]] | None = None, final_sample_from_trajectory_stream: bool = False):
-        """Run all time steps.  traj_uniforms: [B, >= 2*n_times] trajectory stream (consumed 1 or 2 per jump test);
+    def run(self, traj_uniforms: torch.Tensor | None, sample_uniforms: torch.Tensor | None, log: list | None = None, **kwargs):
+        """All time steps in one call: exhausts ``run_iter`` (same arguments) and returns (results [B, n_obs, T | 1],
+        diagnostics [B, 3, T | 1]) as device tensors."""
+        for _ in self.run_iter(traj_uniforms, sample_uniforms, log, **kwargs):
+            pass
+        return self.results, self.diag
+
+    def run_iter(self, traj_uniforms: torch.Tensor | None, sample_uniforms: torch.Tensor | None, log: list | None = None, *,
+                 start_pos: torch.Tensor | None = None, sample_at: Sequence[int] | None = None, continue_trajectory: bool = False,
+                 interval_mpos: Sequence[Sequence[np.ndarray]] | None = None, final_sample_from_trajectory_stream: bool = False):
+        """Generator over the time grid: yields the time index j after ALL work belonging to it has been enqueued (for order 2: the
+        trajectory step and its measurement copy), so a caller can stream that step's inputs in before resuming and its result
+        column (``self.results[:, :, col]``, ``self.diag``) out afterwards -- ``Simulator.open`` does exactly that.  Uniforms are
+        read when a step runs: columns 2j, 2j+1 of the trajectory table and row j of the sample table must be on the device before
+        the generator is resumed for time index j (a jump test at step j reads a position <= 2j - 1).
+        Run all time steps.  traj_uniforms: [B, >= 2*n_times] trajectory stream (consumed 1 or 2 per jump test);
         sample_uniforms: [B, n_times, 2] per-timestep measurement streams (order 2).  Returns (results [B, n_obs, T],
         diagnostics [B, 3, T]) as device tensors.
 
@@ -1276,6 +1338,7 @@ class BatchedTJM:
         nobs = len(self.observables)
         results = torch.zeros((self.B, nobs, ncol), dtype=torch.float64, device=self.dev)
         diag = torch.zeros((self.B, 3, ncol), dtype=torch.float64, device=self.dev)
+        self.results, self.diag = results, diag
         self._pos = torch.zeros(self.B, dtype=torch.int64, device=self.dev) if start_pos is None else start_pos.to(self.dev, torch.int64).clone()
         self._traj_u = traj_uniforms
         measure_at = None
@@ -1337,28 +1400,34 @@ class BatchedTJM:
             if nt == 1:
                 if wanted(0):
                     record(phi, 0)
-                return results, diag
+                yield 0
+                return
             if continue_trajectory:                         # :312-324 (static operator: interval 0 everywhere)
                 sample(0, 0)
+                yield 0
                 for j in range(1, nt):
                     use_interval(0)
                     self.tdvp(phi)
                     self.apply_dissipation(phi, p.dt)
                     traj_jump_test(phi, f"step{j}")
                     sample(j, 0)
-                return results, diag
+                    yield j
+                return
             if measure_at is not None and 0 in measure_at or measure_at is None and p.sample_timesteps:
                 record(phi, 0)
+            yield 0
             self.apply_dissipation(phi, p.dt / 2)           # initialize (:86-108)
             traj_jump_test(phi, "init")
             sample(1, 0)
+            yield 1
             for j in range(2, nt):
                 use_interval(j - 2)
                 self.tdvp(phi)                              # step_through (:111-140)
                 self.apply_dissipation(phi, p.dt)
                 traj_jump_test(phi, f"step{j}")
                 sample(j, j - 1)
-            return results, diag
+                yield j
+            return
         # first-order scheme (:369-462)
         if continue_trajectory:
             raise ValueError("continue_trajectory is an order-2 hand-off")
@@ -1367,6 +1436,8 @@ class BatchedTJM:
         measure_initial = (0 in measure_at) if measure_at is not None else p.sample_timesteps
         if measure_initial:
             record(phi, 0)
+        if nt > 1:
+            yield 0
         for j in range(1, nt):
             use_interval(j - 1)
             self.tdvp(phi)
@@ -1379,9 +1450,11 @@ class BatchedTJM:
                     traj_jump_test(phi, f"step{j}")
             if wanted(j):
                 record(phi, j if p.sample_timesteps else 0)
+            yield j
         if not measure_initial and not p.sample_timesteps and nt <= 1:
             record(phi, 0)
-        return results, diag
+        if nt <= 1:
+            yield 0
 
     def steady_state_step(self, u_traj: torch.Tensor, u_sample: torch.Tensor):
         """One steady-state sampled time step of the second-order scheme for the whole batch: step_through on the
@@ -1405,7 +1478,7 @@ class BatchedTJM:
         """_apply_single_qubit_gate (digital_tjm.py:304-309).  A unitary on the physical index keeps every isometry
         condition, so the batch stays in B form (the reference merely loses track of the centre)."""
         s = gate.sites[0]
-        op = torch.from_numpy(np.ascontiguousarray(gate.matrix, dtype=np.complex128).reshape(-1)).to(self.dev)
+        op = self._const(gate.matrix)
         self.K.apply_local_op(self.B, None, None, 0, st.ext(s), st.ext(s + 1), self.d, op, 0, st.site(s), self.lay.cap[s] * self.lay.cap[s + 1])
 
     @staticmethod
@@ -1457,7 +1530,7 @@ class BatchedTJM:
         if centre not in (left, left + 1):
             self._move_centre(st, centre, left)
         th = self.merge(st, left)
-        op = torch.from_numpy(np.ascontiguousarray(self._resolve_lr_matrix(gate)).reshape(-1)).to(self.dev)
+        op = self._const(self._resolve_lr_matrix(gate))
         K.apply_local_op(B, None, None, 0, st.ext(left), st.ext(left + 2), d * d, op, 0, th, lay.cap[left] * lay.cap[left + 2])
         trunc = self._trunc_args(p.trunc_mode, p.svd_threshold, p.max_bond_dim, p.tdvp_min_keep)
         self.split_theta(st, left, "right", trunc, fast=True)

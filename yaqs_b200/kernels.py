@@ -69,7 +69,7 @@ def load_library() -> ctypes.CDLL:
 
 EXPORTED_SYMBOLS = [
     "yb_last_error", "yb_version", "yb_launch_count", "yb_set_flop_counter", "yb_set_option", "yb_gemm", "yb_wapply", "yb_env_identity", "yb_lanczos_init",
-    "yb_lanczos_step", "yb_lanczos_combine", "yb_svd_prepare", "yb_svd_round", "yb_svd_check", "yb_svd_finalize", "yb_heev", "yb_svd_select", "yb_svd_gather",
+    "yb_lanczos_step", "yb_lanczos_combine", "yb_svd_prepare", "yb_svd_round", "yb_svd_check", "yb_svd_finalize", "yb_svd_ambiguous", "yb_heev", "yb_svd_select", "yb_svd_gather",
     "yb_unpack_vh", "yb_copy_packed", "yb_apply_local_op", "yb_mpo_site_apply", "yb_norm2", "yb_scale", "yb_local_rdm", "yb_philox_uniform",
 ]
 
@@ -210,6 +210,11 @@ class CudaKernels:
             self._cptr(w), ctypes.c_int64(w.stride), self._cptr(q), ctypes.c_int64(q.stride), self._ptr(sval), ctypes.c_int64(stride_s),
             self._ptr(keep.tensor, 4 * keep.offset), keep.stride, self._cptr(uout), ctypes.c_int64(uout.stride), self._cptr(vout),
             ctypes.c_int64(vout.stride), self._ptr(status), int(max_k), self._stream()))
+
+    def svd_ambiguous(self, nbatch, mask, meta, sval, stride_s, trunc_mode, threshold, two_level, tau_rel, noise_rel, status, amb, n_amb):
+        self._check(self.lib.yb_svd_ambiguous(nbatch, self._ptr(mask), self._ptr(meta), self._ptr(sval), ctypes.c_int64(stride_s), int(trunc_mode),
+                                              ctypes.c_double(threshold), int(bool(two_level)), ctypes.c_double(tau_rel), ctypes.c_double(noise_rel),
+                                              self._ptr(status), self._ptr(amb), self._ptr(n_amb), self._stream()))
 
     def heev(self, nbatch, mask, ek: Ext, g: Buf, qh: Buf, zt: Buf, zr: torch.Tensor, stride_zr, d, e, tau: torch.Tensor, stride_vec, meta, status,
              max_k):

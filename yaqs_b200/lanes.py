@@ -23,10 +23,12 @@ class Lanes:
         self.cuda = self.device.type == "cuda"
         self.streams = [torch.cuda.Stream(self.device) for _ in range(self.n)] if (self.cuda and self.n > 1) else []
 
-    def map(self, fn: Callable, items: Sequence) -> list:
-        """fn(item) for every item, at most ``n`` at a time, each on its own stream; results in item order."""
+    def map(self, fn: Callable, items: Sequence, serial: bool = False) -> list:
+        """fn(item) for every item, at most ``n`` at a time, each on its own stream; results in item order.  ``serial``: one
+        after the other on the caller's stream (bench.py's instrumented steps: a kernel timed with CUDA events must have the GPU
+        to itself)."""
         items = list(items)
-        if not self.streams or len(items) <= 1:
+        if serial or not self.streams or len(items) <= 1:
             return [fn(it) for it in items]
         out: list = [None] * len(items)
         errs: list = []
