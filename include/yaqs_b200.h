@@ -67,6 +67,15 @@ int yb_gemm(int op, int nbatch, int ngroups, const int32_t* mask, yb_extent e0, 
             int d_right, const void* a, int64_t stride_a, const void* b, int64_t stride_b, void* c, int64_t stride_c, int conj_b,
             int max_m, int max_n, void* stream);
 
+/* project_site, first two contractions in one kernel (primitives.py:201-202; update_right_environment :105-106):
+ *   out[x,l,y,r'] = sum_(u,v) wt[x,u,y,v] sum_r x[u,l,r] renv[r,v,r']
+ * x: packed (dphys, l, r) local tensor; renv: (r, d_right, r) right environment block; wt: (dphys, dphys, d_left, d_right) MPO tensor
+ * (W1 or the merged W2), shared by all trajectories; out: packed (dphys, l, d_left, r) -- what yb_gemm(LCONTRACT / ENVR3) consumes.
+ * The MPO step runs in the GEMM epilogue while the tile is on chip (no intermediate in HBM).  dphys in {1, 2, 4}, d_right <= 16. */
+int yb_rcontract_mpo(int nbatch, const int32_t* mask, yb_extent el, yb_extent er, int dphys, int d_left, int d_right, const void* x,
+                     int64_t stride_x, const void* renv, int64_t stride_r, const void* wt, void* out, int64_t stride_out, int max_l, int max_r,
+                     void* stream);
+
 /* out[x,l,y,r] = sum_(u,v) wt[x,u,y,v] in[u,l,v,r]: the MPO-tensor step of project_site / update_*_environment
  * (tensordot(op, tensor, axes=((1,3),(0,2))) primitives.py:106,202; tensordot(op, tensor, ((0,2),(2,1))) :135 with the
  * host-transposed MPO tensor).  wt is shared by all trajectories. */

@@ -142,6 +142,19 @@ class NumpyKernels:
             else:
                 raise ValueError(op)
 
+    def rcontract_mpo(self, nbatch, mask, el, er, dphys, d_left, d_right, x, renv, wt, out, max_l, max_r):
+        """Twin of yb_rcontract_mpo: out[x,l,y,r'] = sum_(u,v) wt[x,u,y,v] sum_r X[u,l,r] R[r,v,r']."""
+        self._launches += 1
+        W = _np(wt)[: dphys * dphys * d_left * d_right].reshape(dphys, dphys, d_left, d_right)
+        for t in range(nbatch):
+            if not _on(mask, t):
+                continue
+            l, r = _ext(el, t), _ext(er, t)
+            X = _view(x, t, dphys * l * r).reshape(dphys * l, r)
+            R = _view(renv, t, r * d_right * r).reshape(r, d_right * r)
+            T1 = (X @ R).reshape(dphys, l, d_right, r)
+            _view(out, t, dphys * l * d_left * r)[:] = np.einsum("xuyv,ulvr->xlyr", W, T1).reshape(-1)
+
     def wapply(self, nbatch, mask, el, er, nx, nu, ny, nv, wt, src, dst, max_lr):
         self._launches += 1
         W = _np(wt)[: nx * nu * ny * nv].reshape(nx, nu, ny, nv)

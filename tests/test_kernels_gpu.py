@@ -107,6 +107,43 @@ def test_wapply_matches_twin(backends, dims):
     _cmp(d_c, d_g)
 
 
+@pytest.mark.parametrize("bk16", [0, 1])
+@pytest.mark.parametrize("dims", [(4, 3, 3, 40), (4, 4, 3, 128), (2, 3, 3, 37), (2, 5, 5, 64), (4, 5, 4, 33), (1, 3, 3, 17), (4, 1, 1, 21), (2, 4, 1, 8),
+                                  (4, 5, 5, 130)])
+def test_rcontract_mpo_matches_twin(backends, dims, bk16):
+    """project_site's first two contractions in one kernel (MPO tensor applied in the GEMM epilogue) against the numpy twin --
+    ragged extents, both tile depths, MPO tensors with the reference's sparsity (~30 % non-zero)."""
+    cuda, twin = backends
+    dphys, dl, dr, cap = dims
+    rng = np.random.default_rng(11 * cap + dphys + dl)
+    nb = 5
+    ext = rng.integers(1, cap + 1, size=(nb, 2)).astype(np.int32)
+    ext[0] = cap
+    ext[1] = (cap, 1)
+    ext[2] = (1, cap)
+    mask = np.array([1, 1, 1, 0, 1], dtype=np.int32)
+    sx, sr, so = dphys * cap * cap, cap * dr * cap, dphys * cap * dl * cap
+    rc = lambda n: rng.standard_normal(n) + 1j * rng.standard_normal(n)      # noqa: E731
+    x, r, w = rc(nb * sx), rc(nb * sr), rc(dphys * dphys * dl * dr)
+    w[rng.random(w.shape) > 0.35] = 0
+    outs = []
+    cuda.set_option("gemm_bk16", bk16)
+    try:
+        for kern, dev in ((twin, "cpu"), (cuda, "cuda")):
+            et = torch.from_numpy(ext).to(dev)
+            out = torch.full((nb * so,), 7.0 + 0j, dtype=torch.complex128, device=dev)
+            kern.rcontract_mpo(nb, torch.from_numpy(mask).to(dev), Ext(et, 0, 2), Ext(et, 1, 2), dphys, dl, dr, Buf(torch.from_numpy(x).to(dev), 0, sx),
+                               Buf(torch.from_numpy(r).to(dev), 0, sr), torch.from_numpy(w).to(dev), Buf(out, 0, so), cap, cap)
+            outs.append(out.cpu().numpy().reshape(nb, so))
+    finally:
+        cuda.set_option("gemm_bk16", 0)
+    for t in range(nb):
+        n = dphys * ext[t, 0] * dl * ext[t, 1] if mask[t] else 0
+        scale = max(1.0, np.abs(outs[0][t, :n]).max()) if n else 1.0
+        assert np.max(np.abs(outs[0][t, :n] - outs[1][t, :n]), initial=0.0) < 1e-12 * scale * cap
+        assert np.all(outs[1][t, n:] == 7.0)                     # nothing written beyond the packed tensor / for masked trajectories
+
+
 def test_small_utilities_match_twin(backends):
     cuda, twin = backends
     rng = np.random.default_rng(11)

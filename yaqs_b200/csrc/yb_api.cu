@@ -55,11 +55,13 @@ static std::atomic<int> g_opt_heev_ql{getenv("YB_HEEV_QL") != nullptr ? 1 : 0};
 static std::atomic<int> g_opt_heev_ring{getenv("YB_HEEV_RING") != nullptr ? atoi(getenv("YB_HEEV_RING")) : -1};
 
 static std::atomic<int> g_opt_wapply_onepass{getenv("YB_WAPPLY_ONEPASS") != nullptr ? atoi(getenv("YB_WAPPLY_ONEPASS")) : 0};
+static std::atomic<int> g_opt_gemm_bk16{getenv("YB_GEMM_BK16") != nullptr ? atoi(getenv("YB_GEMM_BK16")) : 0};
 static std::atomic<int> g_opt_gemm_ragged{getenv("YB_GEMM_RAGGED") != nullptr ? atoi(getenv("YB_GEMM_RAGGED")) : 0};
 
 int yb_set_option(const char* name, int value) {
     if (!name) return fail_msg("yb_set_option: null name");
     if (!strcmp(name, "gemm_ragged")) { g_opt_gemm_ragged = value != 0; return 0; }
+    if (!strcmp(name, "gemm_bk16")) { g_opt_gemm_bk16 = value != 0; return 0; }
     if (!strcmp(name, "wapply_onepass")) { g_opt_wapply_onepass = value != 0; return 0; }
     if (!strcmp(name, "heev_ql")) { g_opt_heev_ql = value != 0; return 0; }
     if (!strcmp(name, "heev_ring")) { g_opt_heev_ring = value; return 0; }
@@ -83,6 +85,19 @@ int yb_gemm(int op, int nbatch, int ngroups, const int32_t* mask, yb_extent e0, 
     cudaError_t e = yb_launch_gemm(P, max_m, max_n, (cudaStream_t)stream);
     if (e != cudaSuccess) return fail("yb_gemm", e);
     return done("yb_gemm");
+}
+
+int yb_rcontract_mpo(int nbatch, const int32_t* mask, yb_extent el, yb_extent er, int dphys, int d_left, int d_right, const void* x, int64_t stride_x,
+                     const void* renv, int64_t stride_r, const void* wt, void* out, int64_t stride_out, int max_l, int max_r, void* stream) {
+    if (nbatch <= 0) return 0;
+    if (dphys != 1 && dphys != 2 && dphys != 4) return fail_msg("yb_rcontract_mpo: dphys must be 1, 2 or 4");
+    if (d_left < 1 || d_right < 1 || d_right > 16 || dphys * dphys * d_left * d_right > rw::W_MAX)
+        return fail_msg("yb_rcontract_mpo: MPO bond dimensions out of range (right bond <= 16, tensor <= 1024 entries)");
+    cudaError_t e = yb_launch_gemm_rw(nbatch, mask, el.ptr, el.stride, er.ptr, er.stride, dphys, d_left, d_right, (const cplx*)x, stride_x,
+                                      (const cplx*)renv, stride_r, (const cplx*)wt, (cplx*)out, stride_out, max_l, max_r, g_flop_counter,
+                                      g_opt_gemm_bk16.load(std::memory_order_relaxed), (cudaStream_t)stream);
+    if (e != cudaSuccess) return fail("yb_rcontract_mpo", e);
+    return done("yb_rcontract_mpo");
 }
 
 int yb_wapply(int nbatch, const int32_t* mask, yb_extent el, yb_extent er, int nx, int nu, int ny, int nv, const void* wt, const void* in,

@@ -1,0 +1,211 @@
+// project_site, first two steps in ONE kernel (primitives.py:201-202 / :105-106):
+//     T1[(u,l),(v,r')] = sum_r X[(u,l),r] R[r,(v,r')]          the GEMM of YB_OP_RCONTRACT (DMMA main loop of yb_gemm.cu)
+//     T2[x,l,y,r']     = sum_(u,v) W[x,u,y,v] T1[u,l,v,r']      the MPO-tensor step, applied to the tile while it is on chip
+// Round 1 ran them as k_gemm + k_wapply: a d~ D chi^2 intermediate written and re-read per matvec (re-read ~3.6x because k_wapply
+// gathers one (x, y) slab per block) -- 7 % of the C3 step for an element-wise combination of values the GEMM already holds.
+//
+// The W step mixes ALL physical indices u and ALL right MPO bonds v at a fixed (l, r'), so the CTA tile is laid out in a virtual
+// index space: tile row m = (u, li) with li < TL = 64 / d~, tile column n = (v, ri) with ri < TR = the largest multiple of 8 with
+// Dr * TR <= 128.  Rows / columns are gathered by the cp.async loads (address arithmetic only), the main loop is the 64 x 128 DMMA
+// loop of k_gemm, and the epilogue goes through shared memory (the pipeline buffers are free by then): the accumulator tile is
+// parked as T[64][128], every thread then produces T2 elements (x, li, y, ri) with ri fastest, i.e. coalesced runs of TR
+// complex numbers, skipping the zero entries of the (~30 % dense) MPO tensor exactly like k_wapply.
+#pragma once
+
+namespace rw {
+
+constexpr int BM = 64, BN = 128, NTHREADS = 256;
+constexpr int T_LD = BN + 2;                     // epilogue tile pitch (complex)
+constexpr int W_MAX = 4 * 4 * 8 * 8;             // MPO tensor entries held in shared memory (d~ <= 4, bonds <= 8)
+
+template <int BKT, int STAGES>
+struct Cfg {
+    static constexpr int A_LD = BKT + 4;                         // A stored [m][k]
+    static constexpr int B_LD = BN + 2;                          // B stored [k][n]
+    static constexpr int A_STAGE = BM * A_LD, B_STAGE = BKT * B_LD;
+    static constexpr size_t PIPE = (size_t)STAGES * (A_STAGE + B_STAGE);
+    static constexpr size_t TILE = (size_t)BM * T_LD;
+    static constexpr size_t SMEM = ((PIPE > TILE ? PIPE : TILE) + W_MAX) * sizeof(cplx);
+};
+
+struct Params {
+    int nbatch;
+    const int* mask;
+    const int* el; const int* er; int esl, esr;
+    int dphys, Dl, Dr;                 // d~ (= nx = nu), left MPO bond (ny, kept), right MPO bond (nv, contracted)
+    const cplx* X; const cplx* R; const cplx* W; cplx* Out;
+    long long sX, sR, sOut;
+    unsigned long long* flops;
+};
+
+template <int BKT, int STAGES>
+__global__ void __launch_bounds__(NTHREADS, 1) k_gemm_rw(const Params P) {
+    using C = Cfg<BKT, STAGES>;
+    const int b = blockIdx.z;
+    if (P.mask && !P.mask[b]) return;
+    const int chil = P.el[(long long)b * P.esl], chir = P.er[(long long)b * P.esr];
+    if (chil <= 0 || chir <= 0) return;
+    const int dph = P.dphys, Dr = P.Dr, Dl = P.Dl;
+    const int TL = BM / dph, TR = (BN / Dr) & ~7;
+    const int tiles_r = (chir + TR - 1) / TR, tiles_l = (chil + TL - 1) / TL;
+    if ((int)blockIdx.x >= tiles_l * tiles_r) return;
+    const int l0 = ((int)blockIdx.x / tiles_r) * TL, r0 = ((int)blockIdx.x % tiles_r) * TR;
+    const int nl = min(TL, chil - l0), nr = min(TR, chir - r0);
+    if (P.flops && threadIdx.x == 0)
+        atomicAdd(P.flops, 8ull * (unsigned long long)(dph * nl) * (unsigned long long)(Dr * nr) * (unsigned long long)chir +
+                               8ull * (unsigned long long)(dph * dph * Dl * Dr) * (unsigned long long)nl * (unsigned long long)nr);
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cplx* As = reinterpret_cast<cplx*>(smem_raw);
+    cplx* Bs = As + STAGES * C::A_STAGE;
+    cplx* Ws = reinterpret_cast<cplx*>(smem_raw) + (C::PIPE > C::TILE ? C::PIPE : C::TILE);
+    const cplx* Xb = P.X + (long long)b * P.sX;
+    const cplx* Rb = P.R + (long long)b * P.sR;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = warp >> 2, wn = warp & 3;
+    const int K = chir;
+    const int ktiles = (K + BKT - 1) / BKT;
+    const int nw = dph * dph * Dl * Dr;
+    for (int e = tid; e < nw; e += NTHREADS) Ws[e] = P.W[e];
+
+    // per-thread gather offsets of the loads (fixed over the k loop)
+    constexpr int AQ = (BM * BKT) / NTHREADS, BQ = (BN * BKT) / NTHREADS;
+    long long a_off[AQ]; int a_k[AQ], a_dst[AQ]; bool a_ok[AQ];
+#pragma unroll
+    for (int q = 0; q < AQ; ++q) {
+        const int e = tid + q * NTHREADS;
+        const int k = e % BKT, m = e / BKT;
+        const int u = m / TL, li = m - u * TL;
+        a_ok[q] = li < nl;
+        a_off[q] = ((long long)u * chil + l0 + li) * chir;
+        a_k[q] = k;
+        a_dst[q] = m * C::A_LD + k;
+    }
+    long long b_off[BQ]; int b_k[BQ], b_dst[BQ]; bool b_ok[BQ];
+#pragma unroll
+    for (int q = 0; q < BQ; ++q) {
+        const int e = tid + q * NTHREADS;
+        const int n = e % BN, k = e / BN;
+        const int v = n / TR, ri = n - v * TR;
+        b_ok[q] = v < Dr && ri < nr;
+        b_off[q] = (long long)v * chir + r0 + ri;
+        b_k[q] = k;
+        b_dst[q] = k * C::B_LD + n;
+    }
+    const long long r_rs = (long long)Dr * chir;
+
+    auto load_stage = [&](int kt, int stage) {
+        if (kt < ktiles) {
+            const int k0 = kt * BKT;
+            cplx* as = As + stage * C::A_STAGE;
+            cplx* bs = Bs + stage * C::B_STAGE;
+#pragma unroll
+            for (int q = 0; q < AQ; ++q) {
+                const bool ok = a_ok[q] && (k0 + a_k[q] < K);
+                cp_async16(as + a_dst[q], ok ? (Xb + a_off[q] + k0 + a_k[q]) : Xb, ok);
+            }
+#pragma unroll
+            for (int q = 0; q < BQ; ++q) {
+                const bool ok = b_ok[q] && (k0 + b_k[q] < K);
+                cp_async16(bs + b_dst[q], ok ? (Rb + (long long)(k0 + b_k[q]) * r_rs + b_off[q]) : Rb, ok);
+            }
+        }
+        cp_async_commit();
+    };
+
+    double cr[4][4][2], ci[4][4][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { cr[i][j][0] = cr[i][j][1] = ci[i][j][0] = ci[i][j][1] = 0.0; }
+
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; ++s) load_stage(s, s);
+
+    const int fr = lane >> 2, fk = lane & 3;
+    for (int kt = 0; kt < ktiles; ++kt) {
+        cp_async_wait<STAGES - 2>();
+        __syncthreads();
+        load_stage(kt + STAGES - 1, (kt + STAGES - 1) % STAGES);
+        const cplx* as = As + (kt % STAGES) * C::A_STAGE;
+        const cplx* bs = Bs + (kt % STAGES) * C::B_STAGE;
+#pragma unroll
+        for (int kk = 0; kk < BKT; kk += 4) {
+            double ar[4], ai[4], an[4], br[4], bi[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const cplx v = as[(wm * 32 + i * 8 + fr) * C::A_LD + kk + fk];
+                ar[i] = v.x; ai[i] = v.y; an[i] = flip_sign(v.y);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const cplx v = bs[(kk + fk) * C::B_LD + wn * 32 + j * 8 + fr];
+                br[j] = v.x; bi[j] = v.y;
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    dmma(cr[i][j][0], cr[i][j][1], ar[i], br[j]);
+                    dmma(ci[i][j][0], ci[i][j][1], ar[i], bi[j]);
+                    dmma(cr[i][j][0], cr[i][j][1], an[i], bi[j]);
+                    dmma(ci[i][j][0], ci[i][j][1], ai[i], br[j]);
+                }
+        }
+    }
+    cp_async_wait<0>();
+    __syncthreads();                                  // every warp is done with the pipeline buffers
+
+    // ---- epilogue: park the tile, apply the MPO tensor, write T2 coalesced along r' -------------------------------------
+    cplx* Ts = reinterpret_cast<cplx*>(smem_raw);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int row = wm * 32 + i * 8 + fr;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int col = wn * 32 + j * 8 + 2 * fk;
+            Ts[row * T_LD + col] = make_double2(cr[i][j][0], ci[i][j][0]);
+            Ts[row * T_LD + col + 1] = make_double2(cr[i][j][1], ci[i][j][1]);
+        }
+    }
+    __syncthreads();
+    cplx* Ob = P.Out + (long long)b * P.sOut;
+    const int per_x = nl * Dl * nr;                   // outputs of one physical index x: (li, y, ri), ri fastest
+    const int total = dph * per_x;
+    for (int o = tid; o < total; o += NTHREADS) {
+        const int x = o / per_x;
+        int rem = o - x * per_x;
+        const int li = rem / (Dl * nr);
+        rem -= li * (Dl * nr);
+        const int y = rem / nr, ri = rem - y * nr;
+        cplx acc = make_double2(0.0, 0.0);
+        for (int u = 0; u < dph; ++u) {
+            const cplx* trow = Ts + (u * TL + li) * T_LD + ri;
+            const cplx* wrow = Ws + ((x * dph + u) * Dl + y) * Dr;
+            for (int v = 0; v < Dr; ++v) {
+                const cplx w = wrow[v];
+                if (w.x == 0.0 && w.y == 0.0) continue;
+                acc = cfma(w, trow[v * TR], acc);
+            }
+        }
+        Ob[(((long long)x * chil + l0 + li) * Dl + y) * chir + r0 + ri] = acc;
+    }
+}
+
+template <int BKT, int STAGES>
+cudaError_t launch(const Params& P, int max_l, int max_r, cudaStream_t st) {
+    using C = Cfg<BKT, STAGES>;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(k_gemm_rw<BKT, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    const int TL = BM / P.dphys, TR = (BN / P.Dr) & ~7;
+    const int tiles = ((max_l + TL - 1) / TL) * ((max_r + TR - 1) / TR);
+    dim3 grid(tiles, 1, P.nbatch);
+    k_gemm_rw<BKT, STAGES><<<grid, NTHREADS, C::SMEM, st>>>(P);
+    return cudaGetLastError();
+}
+
+}  // namespace rw

@@ -12,6 +12,7 @@ numpy twin from ``oracle/`` to exercise this host logic on CPU; the package itse
 from __future__ import annotations
 
 import copy
+import os
 from dataclasses import dataclass, field
 from typing import Sequence
 
@@ -277,6 +278,9 @@ class BatchedTJM:
         # Gram-matrix SVD route (Hermitian eigen-solver) for matrices whose Jacobi side would exceed one shared-memory panel
         self.gram_min_k = gram_min_k
         self._jac_geo: dict = {}
+        # project_site / update_right_environment: the MPO-tensor step runs in the epilogue of the first GEMM (yb_rcontract_mpo);
+        # YB_FUSED_MPO=0 selects the separate k_gemm + k_wapply launches (A/B runs)
+        self.fused_mpo = os.environ.get("YB_FUSED_MPO", "1") != "0"
         self.use_gram = sd >= gram_min_k and sd <= 512
         if self.use_gram:
             self.heev_g = torch.zeros(B * sd * sd, dtype=C128, device=dev)
@@ -379,8 +383,11 @@ class BatchedTJM:
         cl, cr = lay.cap[i], lay.cap[i + nsites]
         w = self.W1[i] if nsites == 1 else self.W2[i]
         t1, t2 = self._buf(self.T1, lay.t_slot), self._buf(self.T2, lay.t_slot)
-        K.gemm(OP_RCONTRACT, B, 1, mask, el, er, None, dphys, Dl, Dr, x, self.env(i + nsites, False), t1, 0, dphys * cl, Dr * cr)
-        K.wapply(B, mask, el, er, dphys, dphys, Dl, Dr, w, t1, t2, cl * cr)
+        if self.fused_mpo and Dr <= 16:
+            K.rcontract_mpo(B, mask, el, er, dphys, Dl, Dr, x, self.env(i + nsites, False), w, t2, cl, cr)
+        else:
+            K.gemm(OP_RCONTRACT, B, 1, mask, el, er, None, dphys, Dl, Dr, x, self.env(i + nsites, False), t1, 0, dphys * cl, Dr * cr)
+            K.wapply(B, mask, el, er, dphys, dphys, Dl, Dr, w, t1, t2, cl * cr)
         K.gemm(OP_LCONTRACT, B, dphys, mask, el, er, None, dphys, Dl, Dr, self.env(i, True), t2, y, 0, cl, cr)
         self.stats["matvecs"] += 1
         self.stats["matvecs_2site"] += int(nsites == 2)
@@ -408,8 +415,11 @@ class BatchedTJM:
         cl, cr = lay.cap[s], lay.cap[s + 1]
         a = st.site(s)
         t1, t2 = self._buf(self.T1, lay.t_slot), self._buf(self.T2, lay.t_slot)
-        K.gemm(OP_RCONTRACT, B, 1, None, el, er, None, d, Dl, Dr, a, self.env(s + 1, False), t1, 0, d * cl, Dr * cr)
-        K.wapply(B, None, el, er, d, d, Dl, Dr, self.W1[s], t1, t2, cl * cr)
+        if self.fused_mpo and Dr <= 16:
+            K.rcontract_mpo(B, None, el, er, d, Dl, Dr, a, self.env(s + 1, False), self.W1[s], t2, cl, cr)
+        else:
+            K.gemm(OP_RCONTRACT, B, 1, None, el, er, None, d, Dl, Dr, a, self.env(s + 1, False), t1, 0, d * cl, Dr * cr)
+            K.wapply(B, None, el, er, d, d, Dl, Dr, self.W1[s], t1, t2, cl * cr)
         K.gemm(OP_ENVR3, B, 1, None, el, er, None, d, Dl, Dr, t2, a, self.env(s, False), 0, Dl * cl, cl)
 
     def env_update_left(self, st: BatchedState, s: int) -> None:

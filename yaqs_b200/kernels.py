@@ -68,7 +68,7 @@ def load_library() -> ctypes.CDLL:
 
 
 EXPORTED_SYMBOLS = [
-    "yb_last_error", "yb_version", "yb_launch_count", "yb_set_flop_counter", "yb_set_option", "yb_gemm", "yb_wapply", "yb_env_identity", "yb_lanczos_init",
+    "yb_last_error", "yb_version", "yb_launch_count", "yb_set_flop_counter", "yb_set_option", "yb_gemm", "yb_rcontract_mpo", "yb_wapply", "yb_env_identity", "yb_lanczos_init",
     "yb_lanczos_step", "yb_lanczos_combine", "yb_svd_prepare", "yb_svd_round", "yb_svd_check", "yb_svd_finalize", "yb_svd_ambiguous", "yb_heev", "yb_svd_select", "yb_svd_gather",
     "yb_unpack_vh", "yb_copy_packed", "yb_apply_local_op", "yb_mpo_site_apply", "yb_norm2", "yb_scale", "yb_local_rdm", "yb_philox_uniform",
 ]
@@ -160,6 +160,14 @@ class CudaKernels:
             op, nbatch, ngroups, self._ptr(mask), self._ext(e0), self._ext(e1), self._ext(e2), dphys, d_left, d_right,
             self._cptr(a), ctypes.c_int64(a.stride), self._cptr(b), ctypes.c_int64(b.stride), self._cptr(c), ctypes.c_int64(c.stride),
             int(conj_b), int(max_m), int(max_n), self._stream())))
+
+    def rcontract_mpo(self, nbatch, mask, el, er, dphys, d_left, d_right, x: Buf, renv: Buf, wt: torch.Tensor, out: Buf, max_l, max_r):
+        if wt.dtype != torch.complex128:
+            raise KernelError(f"rcontract_mpo: complex128 MPO tensor expected, got {wt.dtype}")
+        self._timed_call("gemm", lambda: self._check(self.lib.yb_rcontract_mpo(
+            nbatch, self._ptr(mask), self._ext(el), self._ext(er), int(dphys), int(d_left), int(d_right), self._cptr(x), ctypes.c_int64(x.stride),
+            self._cptr(renv), ctypes.c_int64(renv.stride), self._ptr(wt), self._cptr(out), ctypes.c_int64(out.stride), int(max_l), int(max_r),
+            self._stream())))
 
     def wapply(self, nbatch, mask, el, er, nx, nu, ny, nv, wt: torch.Tensor, src: Buf, dst: Buf, max_lr):
         if wt.dtype != torch.complex128:
