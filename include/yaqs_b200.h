@@ -130,6 +130,13 @@ int yb_svd_round(int nbatch, const int32_t* mask, int32_t* meta, int block_rows,
 int yb_heev(int nbatch, const int32_t* mask, yb_extent ek, void* g, int64_t stride_g, void* qh, int64_t stride_q, void* zt, int64_t stride_z,
             double* zr, int64_t stride_zr, double* d, double* e, void* tau, int64_t stride_vec, int32_t* meta, int32_t* status, int max_k,
             void* stream);
+/* yb_heev_rows (round 2): the same eigen-decomposition with the eigenvectors delivered as ROWS, eh[c][:] = (eigenvector c)^H -- what
+ * yb_gemm(ROTATE) takes -- so the Gram route is yb_gemm(GRAM) -> yb_heev_rows -> yb_gemm(ROTATE) -> yb_svd_finalize.  Blocked
+ * tridiagonalisation (zlatrd panels held in shared memory, one rank-2nb update of the trailing block per panel), divide & conquer on
+ * the tridiagonal, then the reflectors are applied to the rows of Z^T directly (no explicit Qh, no EVEC product).  g is overwritten
+ * with the reflectors (row j = v_j), eh must not alias g; zr (k*k doubles), e, tau are workspace; d = eigenvalues (unsorted). */
+int yb_heev_rows(int nbatch, const int32_t* mask, yb_extent ek, void* g, int64_t stride_g, void* eh, int64_t stride_eh, double* zr, int64_t stride_zr,
+                 double* d, double* e, void* tau, int64_t stride_vec, int32_t* meta, int32_t* status, int max_k, void* stream);
 /* Second level of the Gram route: yb_svd_select lists, per trajectory, the rows of the rotated work matrix whose squared
  * norm is below tau_rel * max (sel_n[b] rows, indices in sel_idx[b][0..max_k)); yb_svd_gather copies those rows of (w, q)
  * into the compact blocks (ws, qs) (dir = 0) or back (dir = 1).  Between the two the caller re-diagonalises the block with

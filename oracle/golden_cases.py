@@ -127,7 +127,19 @@ DYNAMIC_CASES = {
                                        sample_timesteps=True, ntraj=3, seed=23, obs="z+zz", tdvp_mode="dynamic",
                                        noise=[("lowering", 0.1), ("pauli_z", 0.1)]),
 }
-ALL_CASES = {**CASES, **LARGE_CASES, **STRESS_CASES, **DYNAMIC_CASES}
+# BASELINE configs 3 and 2 over TEN sampled steps for two trajectories picked from inside a large batch (traj_ids = global
+# trajectory indices; fixture rows follow that order).  103 and 113 are two of the three trajectories whose post-jump chain-end
+# matrices kept the round-1 Jacobi schedule rotating for 60 sweeps in the driver's C3 run: every later step of
+# theirs depends on those factorisations, so ten steps of agreement pin the fix.
+LONG_CASES = {
+    "ising100_c3_10steps": dict(model="ising", L=100, J=1.0, g=0.5, init="random:128:1234", chi=128, thr=1e-6, order=2, dt=0.1, steps=10,
+                                sample_timesteps=True, ntraj=2, traj_ids=[103, 113], seed=42, obs="z",
+                                noise=[("lowering", 0.1), ("pauli_z", 0.1)]),
+    "heis30_c2_10steps": dict(model="heisenberg", L=30, J=1.0, g=0.0, init="random:64:5", chi=64, thr=1e-6, order=2, dt=0.1, steps=10,
+                              sample_timesteps=True, ntraj=2, traj_ids=[517, 999], seed=13, obs="z+zz",
+                              noise=[("lowering", 0.1)]),
+}
+ALL_CASES = {**CASES, **LARGE_CASES, **STRESS_CASES, **DYNAMIC_CASES, **LONG_CASES}
 
 
 

@@ -91,7 +91,7 @@ def run_case(name: str, cfg: dict) -> dict:
     ncol = len(sim.times) if cfg["sample_timesteps"] else 1
     out_res, out_diag, out_bonds, logs = [], [], [], []
     orig_record = MPS.record_diagnostics
-    for tr in range(cfg["ntraj"]):
+    for tr in cfg.get("traj_ids", range(cfg["ntraj"])):       # global trajectory indices (fixture rows follow this order)
         log: list[dict] = []
         bonds: list[list[int]] = []
 
@@ -221,7 +221,7 @@ def run_digital_case(name: str, cfg: dict) -> dict:
     sim.num_mid_measurements = mid
     out_res, out_diag, out_bonds, logs = [], [], [], []
     orig_record = MPS.record_diagnostics
-    for tr in range(cfg["ntraj"]):
+    for tr in cfg.get("traj_ids", range(cfg["ntraj"])):       # global trajectory indices (fixture rows follow this order)
         log: list[dict] = []
         bonds: list[list[int]] = []
 

@@ -385,6 +385,21 @@ class NumpyKernels:
             if mt is not None:
                 mt[t, 5] = 1
 
+    def heev_rows(self, nbatch, mask, ek, g, eh, zr, stride_zr, d, e, tau, stride_vec, meta, status, max_k):
+        """Twin of yb_heev_rows: LAPACK eigh; row c of eh = (eigenvector c)^H."""
+        self._launches += 3
+        mt = _np(meta).reshape(-1, SVD_META) if meta is not None else None
+        for t in range(nbatch):
+            if not _on(mask, t):
+                continue
+            k = _ext(ek, t)
+            G = _view(g, t, k * k).reshape(k, k)
+            lam, vec = np.linalg.eigh(0.5 * (G + G.conj().T))
+            _view(eh, t, k * k)[:] = np.ascontiguousarray(vec.conj().T).reshape(-1)
+            _np(d)[t * stride_vec: t * stride_vec + k] = lam
+            if mt is not None:
+                mt[t, 5] = 1
+
     # -- site-tensor utilities ----------------------------------------------------------------------------------------
     def unpack_vh(self, nbatch, mask, ek, er, dphys, src, dst, max_elems):
         self._launches += 1

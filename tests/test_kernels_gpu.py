@@ -435,6 +435,75 @@ def test_heev_eigendecomposition(backends, ks):
         assert np.max(np.abs(np.sort(lam) - np.linalg.eigvalsh(mats[t]))) < 1e-13 * scale * max(1, k / 16)
 
 
+def _run_heev_rows(kern, dev, ks, mats, mask=None):
+    nb, kmax = len(ks), max(ks)
+    sq = kmax * kmax
+    ek = torch.tensor(ks, dtype=torch.int32, device=dev)
+    g = torch.zeros(nb * sq, dtype=torch.complex128, device=dev)
+    for t, (k, m) in enumerate(zip(ks, mats)):
+        g[t * sq: t * sq + k * k] = torch.from_numpy(np.ascontiguousarray(m).reshape(-1)).to(dev)
+    eh = torch.full((nb * sq,), 3.0 + 0j, dtype=torch.complex128, device=dev)
+    zr = torch.zeros(nb * sq, dtype=torch.float64, device=dev)
+    d = torch.zeros(nb * kmax, dtype=torch.float64, device=dev)
+    e = torch.zeros(nb * kmax, dtype=torch.float64, device=dev)
+    tau = torch.zeros(nb * kmax, dtype=torch.complex128, device=dev)
+    meta = torch.zeros(nb * 8, dtype=torch.int32, device=dev)
+    status = torch.zeros(nb, dtype=torch.int32, device=dev)
+    mk = None if mask is None else torch.tensor(mask, dtype=torch.int32, device=dev)
+    kern.heev_rows(nb, mk, Ext(ek, 0, 1), Buf(g, 0, sq), Buf(eh, 0, sq), zr, sq, d, e, tau, kmax, meta, status, kmax)
+    return d.cpu().numpy().reshape(nb, kmax), eh.cpu().numpy().reshape(nb, sq), meta.cpu().numpy().reshape(nb, 8), status.cpu().numpy()
+
+
+@pytest.mark.parametrize("ks", [[1, 2, 3, 5, 33], [16, 17, 31, 32, 34], [64, 130, 17, 128], [256, 200, 255], [512, 300], [257, 48]])
+def test_heev_rows_eigendecomposition(backends, ks):
+    """yb_heev_rows (blocked zlatrd panels + divide & conquer + reflectors applied to the rows of Z^T): row c of the output is
+    (eigenvector c)^H.  Graded and rank-deficient Gram matrices as on the SVD route; sizes around every panel / tile boundary."""
+    cuda, _ = backends
+    rng = np.random.default_rng(sum(ks) + 1)
+    mats = []
+    for i, k in enumerate(ks):
+        r = max(1, k // 2) if i % 2 else k
+        a = rng.standard_normal((k, r)) + 1j * rng.standard_normal((k, r))
+        a *= np.logspace(0, -6, r)[None, :]
+        mats.append(a @ a.conj().T)
+    mask = [1] * len(ks)
+    d, eh, meta, status = _run_heev_rows(cuda, "cuda", ks, mats, mask)
+    assert not status.any()
+    for t, k in enumerate(ks):
+        assert meta[t, 5] == 1
+        E = eh[t, : k * k].reshape(k, k).conj().T           # columns = eigenvectors
+        lam = d[t, :k]
+        scale = np.abs(np.linalg.eigvalsh(mats[t])).max()
+        assert np.max(np.abs(E.conj().T @ E - np.eye(k))) < 1e-12 * max(1, k / 16)
+        assert np.max(np.abs(mats[t] @ E - E * lam[None, :])) < 2e-13 * scale * max(1, k / 16)
+        assert np.max(np.abs(np.sort(lam) - np.linalg.eigvalsh(mats[t]))) < 1e-13 * scale * max(1, k / 16)
+
+
+def test_heev_rows_special_matrices_and_mask(backends):
+    """Diagonal, identity, 2 x 2 with a complex off-diagonal, a matrix with an exactly zero first column below the diagonal (tau = 0
+    reflector); a masked trajectory is left untouched."""
+    cuda, _ = backends
+    rng = np.random.default_rng(5)
+    k = 40
+    diag = np.diag(np.linspace(1.0, 2.0, k)).astype(np.complex128)
+    ident = np.eye(k, dtype=np.complex128)
+    two = np.array([[2.0, 1.0 - 2.0j], [1.0 + 2.0j, -1.0]], dtype=np.complex128)
+    a = rng.standard_normal((k, k)) + 1j * rng.standard_normal((k, k))
+    blockd = a @ a.conj().T
+    blockd[1:, 0] = 0
+    blockd[0, 1:] = 0
+    mats, ks = [diag, ident, two, blockd, blockd], [k, k, 2, k, k]
+    d, eh, meta, status = _run_heev_rows(cuda, "cuda", ks, mats, [1, 1, 1, 1, 0])
+    assert not status.any()
+    for t, kk in enumerate(ks[:4]):
+        E = eh[t, : kk * kk].reshape(kk, kk).conj().T
+        lam = d[t, :kk]
+        scale = max(1.0, np.abs(mats[t]).max())
+        assert np.max(np.abs(E.conj().T @ E - np.eye(kk))) < 1e-12
+        assert np.max(np.abs(mats[t] @ E - E * lam[None, :])) < 1e-12 * scale * kk
+    assert np.all(eh[4] == 3.0)
+
+
 @pytest.mark.parametrize("ks", [[256, 200, 131], [512, 97, 64, 33, 7]])
 def test_heev_row_ring_is_bit_identical(backends, ks):
     """The cp.async row ring of k_hetrd / k_ungtr only changes HOW the trailing block is streamed: same operations in the same

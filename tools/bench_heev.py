@@ -1,51 +1,56 @@
-"""Micro-benchmark of the Hermitian eigen-solver stages (run under ncu for per-kernel times, or alone for totals)."""
+"""Micro-benchmark of the Hermitian eigen-solver: round-1 route (yb_heev + EVEC product) against yb_heev_rows (blocked, round 2)."""
+import json
 import sys
-import time
 
 import numpy as np
 import torch
 
 sys.path.insert(0, ".")
-from yaqs_b200 import kernels as K
-from yaqs_b200.kernels import Buf, Ext
+from yaqs_b200 import kernels as K  # noqa: E402
+from yaqs_b200.kernels import Buf, Ext  # noqa: E402
 
 
 def main():
     kern = K.CudaKernels("cuda:0")
     dev = "cuda:0"
     out = {}
-    for ring, (k, nb) in [(r, c) for r in (0, 6, 12, 16) for c in [(256, 8), (256, 128), (256, 296), (128, 296), (512, 74)]]:
-        kern.set_option("heev_ring", ring)
+    for (k, nb) in [(256, 128), (256, 64), (256, 148), (128, 128), (128, 64), (64, 128), (512, 74), (512, 16)]:
         sq = k * k
         rng = np.random.default_rng(k + nb)
         a = rng.standard_normal((k, k)) + 1j * rng.standard_normal((k, k))
         a *= np.logspace(0, -5, k)[None, :]
-        g0 = torch.from_numpy(a @ a.conj().T).to(dev).reshape(-1)
+        g0 = torch.from_numpy(a @ a.conj().T).to(dev).reshape(-1).repeat(nb)
         ek = torch.full((nb,), k, dtype=torch.int32, device=dev)
-        g = g0.repeat(nb)
-        qh, zt, qa = (torch.zeros(nb * sq, dtype=torch.complex128, device=dev) for _ in range(3))
+        g = g0.clone()
+        qh, zt, qa, eh = (torch.zeros(nb * sq, dtype=torch.complex128, device=dev) for _ in range(4))
         zr = torch.zeros(nb * sq, dtype=torch.float64, device=dev)
         d, e = (torch.zeros(nb * k, dtype=torch.float64, device=dev) for _ in range(2))
         tau = torch.zeros(nb * k, dtype=torch.complex128, device=dev)
         meta = torch.zeros(nb * 8, dtype=torch.int32, device=dev)
         status = torch.zeros(nb, dtype=torch.int32, device=dev)
         ext = Ext(ek, 0, 1)
-        for rep in range(2):
-            g.copy_(g0.repeat(nb))
-            torch.cuda.synchronize()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            kern.heev(nb, None, ext, Buf(g, 0, sq), Buf(qh, 0, sq), Buf(zt, 0, sq), zr, sq, d, e, tau, k, meta, status, k)
-            e1.record()
-            torch.cuda.synchronize()
-            ms = e0.elapsed_time(e1)
-        e0.record()
-        kern.gemm(K.OP_EVEC, nb, 1, None, ext, None, None, 1, 1, 1, Buf(zt, 0, sq), Buf(qh, 0, sq), Buf(qa, 0, sq), 0, k, k)
-        e1.record()
-        torch.cuda.synchronize()
-        out[f"k{k}_b{nb}_ring{ring}"] = {"heev_ms": ms, "evec_gemm_ms": e0.elapsed_time(e1), "status": int(status.max().item())}
-    kern.set_option("heev_ring", -1)
-    import json
+        res = {}
+        for name in ("round1", "rows"):
+            for rep in range(3):
+                g.copy_(g0)
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                if name == "round1":
+                    kern.heev(nb, None, ext, Buf(g, 0, sq), Buf(qh, 0, sq), Buf(zt, 0, sq), zr, sq, d, e, tau, k, meta, status, k)
+                    kern.gemm(K.OP_EVEC, nb, 1, None, ext, None, None, 1, 1, 1, Buf(zt, 0, sq), Buf(qh, 0, sq), Buf(qa, 0, sq), 0, k, k)
+                else:
+                    kern.heev_rows(nb, None, ext, Buf(g, 0, sq), Buf(eh, 0, sq), zr, sq, d, e, tau, k, meta, status, k)
+                e1.record()
+                torch.cuda.synchronize()
+                res[name + "_ms"] = e0.elapsed_time(e1)
+            lam = d[:k].cpu().numpy().copy()
+            E = (qa if name == "round1" else eh)[:sq].view(k, k).cpu().numpy().conj().T
+            gm = g0[:sq].view(k, k).cpu().numpy()
+            res[name + "_resid"] = float(np.abs(gm @ E - E * lam[None, :]).max() / np.abs(lam).max())
+        res["status"] = int(status.max().item())
+        out[f"k{k}_b{nb}"] = res
+        print(f"k{k}_b{nb}", res, flush=True)
     print(json.dumps(out))
 
 

@@ -91,8 +91,8 @@ int yb_rcontract_mpo(int nbatch, const int32_t* mask, yb_extent el, yb_extent er
                      const void* renv, int64_t stride_r, const void* wt, void* out, int64_t stride_out, int max_l, int max_r, void* stream) {
     if (nbatch <= 0) return 0;
     if (dphys != 1 && dphys != 2 && dphys != 4) return fail_msg("yb_rcontract_mpo: dphys must be 1, 2 or 4");
-    if (d_left < 1 || d_right < 1 || d_right > 16 || dphys * dphys * d_left * d_right > rw::W_MAX)
-        return fail_msg("yb_rcontract_mpo: MPO bond dimensions out of range (right bond <= 16, tensor <= 1024 entries)");
+    if (d_left < 1 || d_right < 1 || d_left > 8 || d_right > 8)
+        return fail_msg("yb_rcontract_mpo: MPO bond dimensions out of range (1 .. 8)");
     cudaError_t e = yb_launch_gemm_rw(nbatch, mask, el.ptr, el.stride, er.ptr, er.stride, dphys, d_left, d_right, (const cplx*)x, stride_x,
                                       (const cplx*)renv, stride_r, (const cplx*)wt, (cplx*)out, stride_out, max_l, max_r, g_flop_counter,
                                       g_opt_gemm_bk16.load(std::memory_order_relaxed), (cudaStream_t)stream);
@@ -295,6 +295,60 @@ int yb_heev(int nbatch, const int32_t* mask, yb_extent ek, void* g, int64_t stri
     }
     cudaStreamWaitEvent(st, ev_join[dev], 0);
     return done("yb_heev(stedc)");
+}
+
+// Round-2 eigen-solver: blocked tridiagonalisation, divide & conquer, eigenvector rows straight from the reflectors (yb_hetrd.cuh).
+int yb_heev_rows(int nbatch, const int32_t* mask, yb_extent ek, void* g, int64_t stride_g, void* eh, int64_t stride_eh, double* zr, int64_t stride_zr,
+                 double* d, double* e, void* tau, int64_t stride_vec, int32_t* meta, int32_t* status, int max_k, void* stream) {
+    if (nbatch <= 0) return 0;
+    if (max_k > heev::KMAX) return fail_msg("yb_heev_rows: max_k > 512 unsupported");
+    if (g == eh) return fail_msg("yb_heev_rows: the eigenvector rows must not alias the input matrix (it keeps the reflectors)");
+    cudaStream_t st = (cudaStream_t)stream;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e1 = cudaFuncSetAttribute(hetrd::k_hetrd_blocked<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hetrd::smem_bytes<16>(256));
+        if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(hetrd::k_hetrd_blocked<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hetrd::smem_bytes<8>(512));
+        const int orm = (int)((size_t)(32 * 256 + 32) * sizeof(cplx));
+        if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(hetrd::k_ormtr_rows<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, orm);
+        if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(hetrd::k_ormtr_rows<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, orm);
+        if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(hetrd::k_ormtr_rows<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, orm);
+        if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(heev::k_stedc<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(stedc::Smem<128>));
+        if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(heev::k_stedc<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(stedc::Smem<256>));
+        if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(heev::k_stedc<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(stedc::Smem<512>));
+        if (e1 != cudaSuccess) return fail("yb_heev_rows(attr)", e1);
+        configured = true;
+    }
+    if (max_k <= 256)
+        hetrd::k_hetrd_blocked<16><<<nbatch, hetrd::THREADS, hetrd::smem_bytes<16>(max_k), st>>>((cplx*)g, stride_g, ek.ptr, ek.stride, d, e, (cplx*)tau,
+                                                                                              stride_vec, max_k, mask);
+    else
+        hetrd::k_hetrd_blocked<8><<<nbatch, hetrd::THREADS, hetrd::smem_bytes<8>(max_k), st>>>((cplx*)g, stride_g, ek.ptr, ek.stride, d, e, (cplx*)tau,
+                                                                                            stride_vec, max_k, mask);
+    if (int rc = done("yb_heev_rows(hetrd)")) return rc;
+    if (max_k <= 128)
+        heev::k_stedc<128><<<nbatch, stedc::THREADS, sizeof(stedc::Smem<128>), st>>>(d, e, stride_vec, zr, stride_zr, (cplx*)eh, stride_eh, ek.ptr, ek.stride,
+                                                                                  meta, status, mask);
+    else if (max_k <= 256)
+        heev::k_stedc<256><<<nbatch, stedc::THREADS, sizeof(stedc::Smem<256>), st>>>(d, e, stride_vec, zr, stride_zr, (cplx*)eh, stride_eh, ek.ptr, ek.stride,
+                                                                                  meta, status, mask);
+    else
+        heev::k_stedc<512><<<nbatch, stedc::THREADS, sizeof(stedc::Smem<512>), st>>>(d, e, stride_vec, zr, stride_zr, (cplx*)eh, stride_eh, ek.ptr, ek.stride,
+                                                                                  meta, status, mask);
+    if (int rc = done("yb_heev_rows(stedc)")) return rc;
+    if (max_k <= 128) {
+        const int pb = 32;
+        hetrd::k_ormtr_rows<4><<<nbatch, hetrd::THREADS, (size_t)(pb * 128 + pb) * sizeof(cplx), st>>>((const cplx*)g, stride_g, (const cplx*)tau, stride_vec,
+                                                                                                    (cplx*)eh, stride_eh, ek.ptr, ek.stride, pb, mask);
+    } else if (max_k <= 256) {
+        const int pb = 32;
+        hetrd::k_ormtr_rows<8><<<nbatch, hetrd::THREADS, (size_t)(pb * 256 + pb) * sizeof(cplx), st>>>((const cplx*)g, stride_g, (const cplx*)tau, stride_vec,
+                                                                                                    (cplx*)eh, stride_eh, ek.ptr, ek.stride, pb, mask);
+    } else {
+        const int pb = 16;
+        hetrd::k_ormtr_rows<16><<<nbatch, hetrd::THREADS, (size_t)(pb * 512 + pb) * sizeof(cplx), st>>>((const cplx*)g, stride_g, (const cplx*)tau, stride_vec,
+                                                                                                     (cplx*)eh, stride_eh, ek.ptr, ek.stride, pb, mask);
+    }
+    return done("yb_heev_rows(ormtr)");
 }
 
 int yb_unpack_vh(int nbatch, const int32_t* mask, yb_extent ek, yb_extent er, int dphys, const void* src, int64_t stride_src, void* dst,

@@ -8,8 +8,9 @@
 // index space: tile row m = (u, li) with li < TL = 64 / d~, tile column n = (v, ri) with ri < TR = the largest multiple of 8 with
 // Dr * TR <= 128.  Rows / columns are gathered by the cp.async loads (address arithmetic only), the main loop is the 64 x 128 DMMA
 // loop of k_gemm, and the epilogue goes through shared memory (the pipeline buffers are free by then): the accumulator tile is
-// parked as T[64][128], every thread then produces T2 elements (x, li, y, ri) with ri fastest, i.e. coalesced runs of TR
-// complex numbers, skipping the zero entries of the (~30 % dense) MPO tensor exactly like k_wapply.
+// parked as T[64][128] and the MPO step runs as a second small GEMM on the tensor pipe (see the epilogue).  A first version did
+// the combination with scalar FMAs per output element and was SLOWER than the two-kernel chain it replaces (1.94 ms against 0.93 +
+// 0.44 ms at B = 128, chi = 128, profiles/r02_matvec_microbench_v1.json): with one CTA per SM nothing overlaps the epilogue.
 #pragma once
 
 namespace rw {
@@ -17,6 +18,7 @@ namespace rw {
 constexpr int BM = 64, BN = 128, NTHREADS = 256;
 constexpr int T_LD = BN + 2;                     // epilogue tile pitch (complex)
 constexpr int W_MAX = 4 * 4 * 8 * 8;             // MPO tensor entries held in shared memory (d~ <= 4, bonds <= 8)
+constexpr int W2_MAX = 32 * 33;                  // the same tensor as a zero-padded (d~ Dl) x (d~ Dr) matrix, pitch Kp + 1
 
 template <int BKT, int STAGES>
 struct Cfg {
@@ -25,7 +27,7 @@ struct Cfg {
     static constexpr int A_STAGE = BM * A_LD, B_STAGE = BKT * B_LD;
     static constexpr size_t PIPE = (size_t)STAGES * (A_STAGE + B_STAGE);
     static constexpr size_t TILE = (size_t)BM * T_LD;
-    static constexpr size_t SMEM = ((PIPE > TILE ? PIPE : TILE) + W_MAX) * sizeof(cplx);
+    static constexpr size_t SMEM = ((PIPE > TILE ? PIPE : TILE) + W_MAX + W2_MAX) * sizeof(cplx);
 };
 
 struct Params {
@@ -156,7 +158,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_rw(const Params P) {
     cp_async_wait<0>();
     __syncthreads();                                  // every warp is done with the pipeline buffers
 
-    // ---- epilogue: park the tile, apply the MPO tensor, write T2 coalesced along r' -------------------------------------
+    // ---- epilogue: the MPO-tensor step as a second, small GEMM on the tensor pipe ----------------------------------------------
+    //   T2[(x,y), pos] = sum_(u,v) W2[(x,y),(u,v)] T1[(u,v), pos],   pos = (li, ri), W2 = the MPO tensor read as a (d~ Dl) x (d~ Dr) matrix
+    // The accumulator tile is parked in shared memory (the pipeline buffers are free), W2 sits zero-padded to multiples of 8 x 4 next
+    // to it, and every warp takes 8-position column tiles (8 consecutive ri of one li): B fragments are gathered from the parked
+    // tile, A fragments from W2, C fragments go straight to global memory (2 adjacent r' per lane: 32-byte stores).  Cost: d~ Dl x
+    // d~ Dr x TL TR complex multiply-adds per CTA, ~10 % of the main loop at C3 sizes, instead of a second kernel and an HBM round trip.
     cplx* Ts = reinterpret_cast<cplx*>(smem_raw);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -168,27 +175,51 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_rw(const Params P) {
             Ts[row * T_LD + col + 1] = make_double2(cr[i][j][1], ci[i][j][1]);
         }
     }
+    const int Mw = dph * Dl, Kw = dph * Dr;                 // W2 extents
+    const int Mp = (Mw + 7) & ~7, Kp = (Kw + 3) & ~3;
+    const int W2_LD = Kp + 1;
+    cplx* W2 = Ws + W_MAX;                                  // [Mp][Kp + 1], zero-padded
+    for (int e = tid; e < Mp * W2_LD; e += NTHREADS) {
+        const int m = e / W2_LD, k = e - m * W2_LD;
+        cplx w = make_double2(0.0, 0.0);
+        if (m < Mw && k < Kw) {
+            const int x = m / Dl, y = m - x * Dl, u = k / Dr, v = k - u * Dr;
+            w = Ws[((x * dph + u) * Dl + y) * Dr + v];
+        }
+        W2[e] = w;
+    }
     __syncthreads();
     cplx* Ob = P.Out + (long long)b * P.sOut;
-    const int per_x = nl * Dl * nr;                   // outputs of one physical index x: (li, y, ri), ri fastest
-    const int total = dph * per_x;
-    for (int o = tid; o < total; o += NTHREADS) {
-        const int x = o / per_x;
-        int rem = o - x * per_x;
-        const int li = rem / (Dl * nr);
-        rem -= li * (Dl * nr);
-        const int y = rem / nr, ri = rem - y * nr;
-        cplx acc = make_double2(0.0, 0.0);
-        for (int u = 0; u < dph; ++u) {
-            const cplx* trow = Ts + (u * TL + li) * T_LD + ri;
-            const cplx* wrow = Ws + ((x * dph + u) * Dl + y) * Dr;
-            for (int v = 0; v < Dr; ++v) {
-                const cplx w = wrow[v];
-                if (w.x == 0.0 && w.y == 0.0) continue;
-                acc = cfma(w, trow[v * TR], acc);
+    const int tiles_per_row = TR >> 3;                      // 8-position tiles per li
+    const int ntile = TL * tiles_per_row;
+    for (int nt_ = warp; nt_ < ntile; nt_ += NTHREADS / 32) {
+        const int li = nt_ / tiles_per_row, ri0 = (nt_ - li * tiles_per_row) << 3;
+        if (li >= nl || ri0 >= nr) continue;                // warp-uniform: nothing to store from this tile
+        const cplx* tpos = Ts + li * T_LD + ri0 + fr;       // + u * TL * T_LD + v * TR per k
+        for (int m0 = 0; m0 < Mp; m0 += 8) {
+            double c_r0 = 0.0, c_r1 = 0.0, c_i0 = 0.0, c_i1 = 0.0;
+            for (int k0 = 0; k0 < Kp; k0 += 4) {
+                const int k = k0 + fk;
+                const cplx av = W2[(m0 + fr) * W2_LD + k];
+                cplx bv = make_double2(0.0, 0.0);
+                if (k < Kw) {
+                    const int u = k / Dr, v = k - u * Dr;
+                    bv = tpos[u * TL * T_LD + v * TR];
+                }
+                dmma(c_r0, c_r1, av.x, bv.x);
+                dmma(c_i0, c_i1, av.x, bv.y);
+                dmma(c_r0, c_r1, flip_sign(av.y), bv.y);
+                dmma(c_i0, c_i1, av.y, bv.x);
+            }
+            const int m = m0 + fr;
+            const int ri = ri0 + 2 * fk;
+            if (m < Mw && ri < nr) {
+                const int x = m / Dl, y = m - x * Dl;
+                cplx* dst = Ob + (((long long)x * chil + l0 + li) * Dl + y) * chir + r0 + ri;
+                dst[0] = make_double2(c_r0, c_i0);
+                if (ri + 1 < nr) dst[1] = make_double2(c_r1, c_i1);
             }
         }
-        Ob[(((long long)x * chil + l0 + li) * Dl + y) * chir + r0 + ri] = acc;
     }
 }
 

@@ -11,6 +11,7 @@
 #include "yb_common.cuh"
 #include <math.h>
 #include "yb_stedc.cuh"
+#include "yb_hetrd.cuh"
 
 namespace heev {
 

@@ -281,6 +281,8 @@ class BatchedTJM:
         # project_site / update_right_environment: the MPO-tensor step runs in the epilogue of the first GEMM (yb_rcontract_mpo);
         # YB_FUSED_MPO=0 selects the separate k_gemm + k_wapply launches (A/B runs)
         self.fused_mpo = os.environ.get("YB_FUSED_MPO", "1") != "0"
+        # Gram-route eigen-solver: yb_heev_rows (blocked, round 2) unless YB_HEEV_ROWS=0 selects the round-1 kernels + EVEC product
+        self.heev_rows = os.environ.get("YB_HEEV_ROWS", "1") != "0"
         self.use_gram = sd >= gram_min_k and sd <= 512
         if self.use_gram:
             self.heev_g = torch.zeros(B * sd * sd, dtype=C128, device=dev)
@@ -383,7 +385,7 @@ class BatchedTJM:
         cl, cr = lay.cap[i], lay.cap[i + nsites]
         w = self.W1[i] if nsites == 1 else self.W2[i]
         t1, t2 = self._buf(self.T1, lay.t_slot), self._buf(self.T2, lay.t_slot)
-        if self.fused_mpo and Dr <= 16:
+        if self.fused_mpo and Dl <= 8 and Dr <= 8:
             K.rcontract_mpo(B, mask, el, er, dphys, Dl, Dr, x, self.env(i + nsites, False), w, t2, cl, cr)
         else:
             K.gemm(OP_RCONTRACT, B, 1, mask, el, er, None, dphys, Dl, Dr, x, self.env(i + nsites, False), t1, 0, dphys * cl, Dr * cr)
@@ -415,7 +417,7 @@ class BatchedTJM:
         cl, cr = lay.cap[s], lay.cap[s + 1]
         a = st.site(s)
         t1, t2 = self._buf(self.T1, lay.t_slot), self._buf(self.T2, lay.t_slot)
-        if self.fused_mpo and Dr <= 16:
+        if self.fused_mpo and Dl <= 8 and Dr <= 8:
             K.rcontract_mpo(B, None, el, er, d, Dl, Dr, a, self.env(s + 1, False), self.W1[s], t2, cl, cr)
         else:
             K.gemm(OP_RCONTRACT, B, 1, None, el, er, None, d, Dl, Dr, a, self.env(s + 1, False), t1, 0, d * cl, Dr * cr)
@@ -530,8 +532,12 @@ class BatchedTJM:
         ek, eln = Ext(self.svd_meta, 0, SVD_META), Ext(self.svd_meta, 1, SVD_META)
         K.gemm(OP_GRAM, B, 1, mask, ek, eln, None, 1, 1, 1, w, w, g, 0, sd, sd)
         self.status_scratch.zero_()
-        K.heev(B, mask, ek, g, qh, zt, self.heev_zr, sq, self.heev_d, self.heev_e, self.heev_tau, sd, self.svd_meta, self.status_scratch, sd)
-        K.gemm(OP_EVEC, B, 1, mask, ek, None, None, 1, 1, 1, zt, qh, q, 0, sd, sd)
+        kdim = sd if dims is None else max(1, min(sd, min(dims) if mode != SVD_THETA else (dims[0] if dist == "right" else dims[1])))      # bound of k = rows of W
+        if self.heev_rows:                               # blocked tridiagonalisation, eigenvector rows straight from the reflectors
+            K.heev_rows(B, mask, ek, g, q, self.heev_zr, sq, self.heev_d, self.heev_e, self.heev_tau, sd, self.svd_meta, self.status_scratch, kdim)
+        else:
+            K.heev(B, mask, ek, g, qh, zt, self.heev_zr, sq, self.heev_d, self.heev_e, self.heev_tau, sd, self.svd_meta, self.status_scratch, sd)
+            K.gemm(OP_EVEC, B, 1, mask, ek, None, None, 1, 1, 1, zt, qh, q, 0, sd, sd)
         K.gemm(OP_ROTATE, B, 1, mask, ek, eln, None, 1, 1, 1, q, w, g, 0, sd, sd)          # Wf -> heev_g
         # second level only where a threshold has to be resolved below the Gram accuracy; a truncation-free factorisation (thr == 0:
         # the QR-equivalent gauge moves) needs no singular value at all -- U is the unitary eigenvector matrix, S Vh the exact product
@@ -542,10 +548,15 @@ class BatchedTJM:
             K.svd_gather(B, mask, self.svd_meta, self.sel_n, self.sel_idx, sd, 0, g, q, ws, qs)
             en = Ext(self.sel_n, 0, 1)
             K.gemm(OP_GRAM, B, 1, mask, en, eln, None, 1, 1, 1, ws, ws, g2, 0, sd, sd)
-            K.heev(B, mask, en, g2, qh, zt, self.heev_zr, sq, self.heev_d, self.heev_e, self.heev_tau, sd, None, self.status_scratch, sd)
-            K.gemm(OP_EVEC, B, 1, mask, en, None, None, 1, 1, 1, zt, qh, g2, 0, sd, sd)
-            K.gemm(OP_ROTATE, B, 1, mask, en, eln, None, 1, 1, 1, g2, ws, hs, 0, sd, sd)
-            K.gemm(OP_ROTATE, B, 1, mask, en, ek, None, 1, 1, 1, g2, qs, ws, 0, sd, sd)
+            if self.heev_rows:
+                K.heev_rows(B, mask, en, g2, zt, self.heev_zr, sq, self.heev_d, self.heev_e, self.heev_tau, sd, None, self.status_scratch, kdim)
+                e2 = zt
+            else:
+                K.heev(B, mask, en, g2, qh, zt, self.heev_zr, sq, self.heev_d, self.heev_e, self.heev_tau, sd, None, self.status_scratch, sd)
+                K.gemm(OP_EVEC, B, 1, mask, en, None, None, 1, 1, 1, zt, qh, g2, 0, sd, sd)
+                e2 = g2
+            K.gemm(OP_ROTATE, B, 1, mask, en, eln, None, 1, 1, 1, e2, ws, hs, 0, sd, sd)
+            K.gemm(OP_ROTATE, B, 1, mask, en, ek, None, 1, 1, 1, e2, qs, ws, 0, sd, sd)
             K.svd_gather(B, mask, self.svd_meta, self.sel_n, self.sel_idx, sd, 1, g, q, hs, ws)
         K.svd_finalize(B, mask, self.svd_meta, tm, thr, mb, mk, DIST[dist], g, q, self.svd_s, sd, Ext(self.keep, 0, 1),
                        self._buf(self.svd_u, sq), self._buf(self.svd_v, sq), self.status_scratch, sd)

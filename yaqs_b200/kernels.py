@@ -69,7 +69,7 @@ def load_library() -> ctypes.CDLL:
 
 EXPORTED_SYMBOLS = [
     "yb_last_error", "yb_version", "yb_launch_count", "yb_set_flop_counter", "yb_set_option", "yb_gemm", "yb_rcontract_mpo", "yb_wapply", "yb_env_identity", "yb_lanczos_init",
-    "yb_lanczos_step", "yb_lanczos_combine", "yb_svd_prepare", "yb_svd_round", "yb_svd_check", "yb_svd_finalize", "yb_svd_ambiguous", "yb_heev", "yb_svd_select", "yb_svd_gather",
+    "yb_lanczos_step", "yb_lanczos_combine", "yb_svd_prepare", "yb_svd_round", "yb_svd_check", "yb_svd_finalize", "yb_svd_ambiguous", "yb_heev", "yb_heev_rows", "yb_svd_select", "yb_svd_gather",
     "yb_unpack_vh", "yb_copy_packed", "yb_apply_local_op", "yb_mpo_site_apply", "yb_norm2", "yb_scale", "yb_local_rdm", "yb_philox_uniform",
 ]
 
@@ -230,6 +230,12 @@ class CudaKernels:
             nbatch, self._ptr(mask), self._ext(ek), self._cptr(g), ctypes.c_int64(g.stride), self._cptr(qh), ctypes.c_int64(qh.stride),
             self._cptr(zt), ctypes.c_int64(zt.stride), self._ptr(zr), ctypes.c_int64(stride_zr), self._ptr(d), self._ptr(e), self._ptr(tau),
             ctypes.c_int64(stride_vec), self._ptr(meta), self._ptr(status), int(max_k), self._stream())))
+
+    def heev_rows(self, nbatch, mask, ek: Ext, g: Buf, eh: Buf, zr: torch.Tensor, stride_zr, d, e, tau: torch.Tensor, stride_vec, meta, status, max_k):
+        self._timed_call("heev", lambda: self._check(self.lib.yb_heev_rows(
+            nbatch, self._ptr(mask), self._ext(ek), self._cptr(g), ctypes.c_int64(g.stride), self._cptr(eh), ctypes.c_int64(eh.stride),
+            self._ptr(zr), ctypes.c_int64(stride_zr), self._ptr(d), self._ptr(e), self._ptr(tau), ctypes.c_int64(stride_vec), self._ptr(meta),
+            self._ptr(status), int(max_k), self._stream())))
 
     def svd_select(self, nbatch, mask, meta, w: Buf, tau_rel, sel_n, sel_idx, max_k):
         self._check(self.lib.yb_svd_select(nbatch, self._ptr(mask), self._ptr(meta), self._cptr(w), ctypes.c_int64(w.stride),
