@@ -48,6 +48,17 @@ void yb_set_flop_counter(void* device_u64);
  *               -1 = by matrix size (default: 16 rows in flight for k > 256, direct loads below)                      */
 int yb_set_option(const char* name, int value);
 
+/* Device memory a batch needs (SURVEY.md 8b "Ownership": the library never allocates; the caller sizes its buffers -- and the
+ * number of trajectories per wave -- from this).  cap[0..length]: slot capacity of every bond (cap[0] = cap[length] = 1);
+ * mpo_bond[0..length]: MPO bond dimensions; order: 1 or 2 (order 2 keeps the measurement copy psi next to phi); two_envs != 0: left and
+ * right environments in separate storage (1-site / dynamic TDVP); gram != 0: include the Hermitian eigen-solver work matrices.
+ * Pure host arithmetic: callable without a device. */
+typedef struct {
+    int64_t state, environments, theta, matvec, krylov, svd, heev, small, total;
+} yb_workspace;
+int yb_workspace_bytes(int length, int nbatch, int dphys, const int32_t* cap, const int32_t* mpo_bond, int order, int two_envs, int gram,
+                       yb_workspace* out);
+
 /* ---- contractions -------------------------------------------------------------------------------------------------
  * One grouped / K-segmented batched complex GEMM; `op` selects the index pattern (enum YbGemmOp in csrc/yb_common.cuh):
  *   0 RCONTRACT  T1[(p,l),(a',r')] = sum_r X[(p,l),r] R[r,(a',r')]          tensordot(ket, right_env, axes=1)     methods/tdvp/primitives.py:105,201

@@ -139,3 +139,50 @@ def test_program_hand_off_through_backends_host_twin(golden_dir):
         _check_program_hand_off_through_backends(NumpyKernels(), golden_dir)
     finally:
         backends.set_default_kernels(None)
+
+
+def _check_schmidt(kernels):
+    """schmidt_spectrum at the backend boundary (missing #7): analog_tjm_1 returns a dtype=object array whose
+    Schmidt rows hold the 500-vectors (analog_tjm.py:424-426, mps.py:644-678); fixture = the unmodified reference's own call
+    (oracle/make_schmidt_golden.py).  analog_tjm_2 and Simulator.run fail the way the reference fails (float result buffers)."""
+    from yaqs_b200 import Simulator
+    g = np.load(os.path.join(GOLDEN, "schmidt_ising6_order1.npz"))
+    L = int(g["L"])
+    obs = [Observable(Z(), s) for s in range(L)] + [Observable("schmidt_spectrum", [s, s + 1]) for s in range(L - 1)]
+    noise = NoiseModel([{"name": n, "sites": [i], "strength": float(g["gamma"])} for i in range(L) for n in ("lowering", "pauli_z")])
+    sp = AnalogSimParams(observables=obs, elapsed_time=float(g["dt"]) * int(g["steps"]), dt=float(g["dt"]), num_traj=int(g["ntraj"]),
+                         max_bond_dim=int(g["chi"]), svd_threshold=float(g["thr"]), order=1, sample_timesteps=True, random_seed=int(g["seed"]))
+    names = [o.gate.name for o in sp.sorted_observables]
+    assert names == [str(n) for n in g["names"]]
+    ham = Hamiltonian.ising(L, float(g["J"]), float(g["g"]))
+    backends.set_default_kernels(kernels)
+    try:
+        for t in range(int(g["ntraj"])):
+            res, diag, _ = backends.analog_tjm_1((t, State(L, initial="x+"), noise, sp, ham))
+            assert res.dtype == object and res.shape == (len(names), int(g["steps"]) + 1)
+            for k, name in enumerate(names):
+                for col in range(res.shape[1]):
+                    if name == "schmidt_spectrum":
+                        got, want = np.asarray(res[k, col], dtype=np.float64), g["spectra"][t, k, col]
+                        assert got.shape == (500,) and np.array_equal(np.isnan(got), np.isnan(want))
+                        assert np.nanmax(np.abs(got - want)) < 1e-10
+                    else:
+                        assert abs(float(res[k, col]) - g["scalars"][t, k, col]) < 1e-10
+        sp2 = AnalogSimParams(observables=obs, elapsed_time=0.2, dt=0.1, num_traj=1, max_bond_dim=8, order=2, random_seed=1)
+        with pytest.raises(ValueError, match="setting an array element with a sequence"):
+            backends.analog_tjm_2((0, State(L, initial="x+"), noise, sp2, ham))
+        with pytest.raises(ValueError, match="setting an array element with a sequence"):
+            Simulator(show_progress=False, kernels=kernels).run(State(L, initial="x+"), ham, sp, noise)
+    finally:
+        backends.set_default_kernels(None)
+
+
+def test_schmidt_spectrum_at_the_backend_boundary():
+    from oracle.np_kernels import NumpyKernels
+    _check_schmidt(NumpyKernels())
+
+
+@pytest.mark.gpu
+def test_schmidt_spectrum_at_the_backend_boundary_gpu():
+    from yaqs_b200.kernels import CudaKernels
+    _check_schmidt(CudaKernels("cuda:0"))

@@ -657,3 +657,21 @@ def test_wapply_onepass_option_is_bit_identical(backends, dims):
     finally:
         cuda.set_option("wapply_onepass", 0)
     assert np.array_equal(outs[0], outs[1])
+
+
+def test_workspace_bytes_covers_the_engine_allocations(backends):
+    """What yb_workspace_bytes promises is what BatchedTJM allocates (within 2 %: a few small per-trajectory vectors)."""
+    from yaqs_b200.engine import BatchedTJM, EngineParams
+    from yaqs_b200.kernels import workspace_bytes
+    cuda, _ = backends
+    L, B, chi = 12, 6, 32
+    mpo = [np.zeros((2, 2, 1 if i == 0 else 3, 1 if i == L - 1 else 3), dtype=np.complex128) for i in range(L)]
+    init = [np.ones((2, 1, 1), dtype=np.complex128) for _ in range(L)]
+    noise = [{"name": "pauli_z", "sites": [i], "strength": 0.1, "matrix": np.diag([1.0, -1.0]).astype(np.complex128)} for i in range(L)]
+    torch.cuda.synchronize()
+    before = torch.cuda.memory_allocated()
+    eng = BatchedTJM(cuda, L, B, mpo, EngineParams(max_bond_dim=chi, order=2), noise, [(np.diag([1.0, -1.0]).astype(np.complex128), [0])], init)
+    torch.cuda.synchronize()
+    used = torch.cuda.memory_allocated() - before
+    want = workspace_bytes(L, B, eng.lay.cap, eng.lay.D, 2, False)["total"]
+    assert used <= 1.02 * want + (1 << 20) and want <= 1.02 * used + (1 << 20), (used, want)

@@ -82,8 +82,7 @@ def test_entropy_and_pvm_observables_through_simulator(golden_dir):
         assert np.max(np.abs(np.asarray(res.trajectories[k]) - g["results"][:, k, :])) < 1e-10
     with pytest.raises(AssertionError, match="mixed observable and projective-measurement"):
         AnalogSimParams(observables=[Observable(Z(), 0), Observable("0" * L)], elapsed_time=0.1, dt=0.1)
-    with pytest.raises(NotImplementedError):
-        Observable("schmidt_spectrum", [0, 1])
+    assert Observable("schmidt_spectrum", [0, 1]).gate.name == "schmidt_spectrum"      # accepted; see test_backends_host for where it runs
 
 
 def test_scheduled_jumps_through_simulator(golden_dir):
@@ -369,3 +368,20 @@ def test_status_bits_become_reference_exceptions(bit, etype, text):
     keep = [0, 2, 3, 4]
     for k in range(length):
         assert np.allclose(res.expectation_values[k], clean.trajectories[k][keep].mean(axis=0), atol=1e-15)
+
+
+def test_digital_tdvp_mode_only_matters_for_window_gates():
+    """A nearest-neighbour circuit never takes a TDVP window, so tdvp_mode="1site" runs (the reference raises only inside
+    apply_two_qubit_gate_tdvp, digital_tjm.py:324-340); a periodic circuit in gate_mode="tdvp" does take one and raises there."""
+    from yaqs_b200 import DigitalSimParams
+    from yaqs_b200.circuits import create_ising_circuit
+    L = 4
+    obs = [Observable(Z(), s) for s in range(L)]
+    sim = Simulator(show_progress=False, kernels=NumpyKernels())
+    a = sim.run(State(L, initial="zeros"), create_ising_circuit(L, 1.0, 0.6, 0.2, 2), DigitalSimParams(observables=obs, tdvp_mode="1site"))
+    b = sim.run(State(L, initial="zeros"), create_ising_circuit(L, 1.0, 0.6, 0.2, 2), DigitalSimParams(observables=obs))
+    for x, y in zip(a.expectation_values, b.expectation_values):
+        assert np.array_equal(x, y)
+    with pytest.raises(ValueError, match='only supports tdvp_mode="2site"'):
+        sim.run(State(L, initial="zeros"), create_ising_circuit(L, 1.0, 0.6, 0.2, 1, periodic=True),
+                DigitalSimParams(observables=obs, tdvp_mode="1site", gate_mode="tdvp"))

@@ -120,6 +120,15 @@ def run_batch(traj_indices: Sequence[int], initial_state, noise_model: NoiseMode
     results, diag = eng.run(tu, su, None, sample_at=sample_at, continue_trajectory=continue_trajectory, interval_mpos=per_interval,
                             final_sample_from_trajectory_stream=use_trajectory_rng_for_final_sample and trajectory_rngs is not None)
     status = eng.status.cpu().numpy()
+    res_host = results.cpu().numpy()
+    if eng.spectra:                                # schmidt_spectrum rows: an object array whose entries are the 500-vectors (analog_tjm.py:424-426)
+        obj = np.empty(res_host.shape, dtype=object)
+        obj[...] = res_host
+        for (k, col), spec in eng.spectra.items():
+            sh = spec.cpu().numpy()
+            for b in range(len(idx)):
+                obj[b, k, col] = sh[b].copy()
+        res_host = obj
     if rng_mode == "numpy" and trajectory_rngs is not None:
         for g, state0, used in zip(trajectory_rngs, rewind, eng._pos.cpu().tolist()):
             g.bit_generator.state = state0
@@ -129,7 +138,7 @@ def run_batch(traj_indices: Sequence[int], initial_state, noise_model: NoiseMode
     if return_states:
         st = eng.psi if ep.order == 2 and ep.n_times > 1 and not return_trajectory_state else eng.phi
         final = [st.download(b) for b in range(len(idx))]
-    return results.cpu().numpy(), diag.cpu().numpy(), status, final
+    return res_host, diag.cpu().numpy(), status, final
 
 
 def _single(args, order: int, *, copy_initial_state, rng, sample_timestep_offset, use_trajectory_rng_for_final_sample, return_trajectory_state,
@@ -141,6 +150,10 @@ def _single(args, order: int, *, copy_initial_state, rng, sample_timestep_offset
     if sample_at is not None and len(sim_params.times) - 1 not in frozenset(sample_at) and sim_params.get_state and not return_trajectory_state:
         raise NotImplementedError("get_state with a sample_at that omits the final time (the unrecorded physical copy of analog_tjm.py:"
                                   "293-309) is not on the B200 path")
+    if order == 2 and any(o.gate.name == "schmidt_spectrum" for o in sim_params.observables):
+        # analog_tjm_2 allocates a float result buffer (analog_tjm.py:289-292), so storing the 500-vector fails inside numpy with
+        # exactly this message; only the first-order backend (dtype=object, :424-426) can return a Schmidt spectrum
+        raise ValueError("setting an array element with a sequence.")
     want = 2 if sim_params.order != 1 else 1
     if want != order:
         raise ValueError(f"analog_tjm_{order} called with AnalogSimParams(order={sim_params.order})")

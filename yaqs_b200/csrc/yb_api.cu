@@ -48,6 +48,40 @@ int64_t yb_launch_count(int reset) {
     return v;
 }
 
+// Device bytes a batch of `nbatch` trajectories needs (host arithmetic only; mirrors engine.BatchLayout / BatchedTJM.__init__).
+int yb_workspace_bytes(int length, int nbatch, int dphys, const int32_t* cap, const int32_t* mpo_bond, int order, int two_envs, int gram,
+                       yb_workspace* out) {
+    if (!cap || !mpo_bond || !out || length < 1 || nbatch < 1 || dphys < 1) return fail_msg("yb_workspace_bytes: bad arguments");
+    const int64_t C = 16, B = nbatch, d = dphys;
+    int64_t state = 0, env = 0, pair = 1, single = 1, cmax = 1, dmax = 1;
+    for (int i = 0; i < length; ++i) {
+        state += d * cap[i] * (int64_t)cap[i + 1];
+        single = single > (int64_t)cap[i] * cap[i + 1] ? single : (int64_t)cap[i] * cap[i + 1];
+        if (i + 2 <= length) pair = pair > (int64_t)cap[i] * cap[i + 2] ? pair : (int64_t)cap[i] * cap[i + 2];
+    }
+    for (int j = 0; j <= length; ++j) {
+        env += (int64_t)cap[j] * mpo_bond[j] * cap[j];
+        cmax = cmax > cap[j] ? cmax : cap[j];
+        dmax = dmax > mpo_bond[j] ? dmax : mpo_bond[j];
+    }
+    if (length < 2) pair = 1;
+    const int64_t theta_slot = d * d * pair;
+    const int64_t nloc = theta_slot > d * single ? theta_slot : d * single;
+    const int64_t t_slot = nloc * dmax, sd = d * cmax, sq = sd * sd;
+    memset(out, 0, sizeof(*out));
+    out->state = C * state * B * (order == 2 ? 2 : 1) + 4 * B * (length + 1) * (order == 2 ? 2 : 1);
+    out->environments = C * env * B * (two_envs ? 2 : 1);
+    out->theta = C * B * theta_slot;
+    out->matvec = C * B * 2 * t_slot;
+    out->krylov = C * B * (26 + 1) * nloc + B * (2 * 32 * 8 + 32 * 16);
+    out->svd = C * B * 4 * sq + 8 * B * sd + 4 * B * 8;
+    const bool use_gram = gram && sd >= 33 && sd <= 512;
+    out->heev = use_gram ? (C * B * 4 * sq + 8 * B * sq + 2 * 8 * B * sd + C * B * sd + 4 * B * sd) : 0;
+    out->small = C * B * 4 * length + 64 * B;
+    out->total = out->state + out->environments + out->theta + out->matvec + out->krylov + out->svd + out->heev + out->small;
+    return 0;
+}
+
 void yb_set_flop_counter(void* device_u64) { g_flop_counter = (unsigned long long*)device_u64; }
 
 // diagnostic switches (A/B runs and bisecting a failure); the defaults are the production route

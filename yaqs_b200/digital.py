@@ -47,8 +47,6 @@ def run_digital(simulator, initial_state, operator, sp, noise, result):
     obs = engine_observables(sorted_obs, length)
     ep = EngineParams(dt=1.0, n_steps=1, order=1, max_bond_dim=sp.max_bond_dim, svd_threshold=sp.svd_threshold, trunc_mode=sp.trunc_mode,
                       krylov_tol=sp.krylov_tol, tdvp_mode=sp.tdvp_mode, tdvp_sweeps=sp.tdvp_sweeps, sample_timesteps=True, digital=True)
-    if ep.tdvp_mode != "2site":
-        raise ValueError(f'apply_two_qubit_gate_tdvp only supports tdvp_mode="2site"; got {ep.tdvp_mode!r}.')
     mpo = [np.eye(2, dtype=np.complex128).reshape(2, 2, 1, 1) for _ in range(length)]      # bond-1 layout for generator windows
     procs = list(noise.processes) if noise is not None else None
     init = initial_state.mps.tensors

@@ -272,6 +272,7 @@ class BatchedTJM:
         self.rdm1 = torch.zeros(B * 4, dtype=C128, device=dev)
         self._rdm1_all = self._rdm2_all = None          # [L, B, 4] / [L - 1, B, 16] tables of rho_sweep (allocated on first use)
         self._obs_tab = None
+        self._spectra_now: dict = {}
         # Jacobi panel geometry is chosen per call from the capacities of the matrix at hand (_jacobi_geometry); a test may force
         # the panel height to exercise the multi-block schedule on small matrices
         self.svd_block_rows_forced = svd_block_rows
@@ -1008,10 +1009,42 @@ class BatchedTJM:
                     val = torch.einsum("kop,kbop->bk", mats, g[sites])
                     res[:, cols] = val.real
                     self.status |= (val.imag >= 1e-13).any(dim=1).to(torch.int32) * STATUS_IMAG_PART
+        self._spectra_now = {}
         for k, (mat, sites) in enumerate(self.observables):
-            if isinstance(mat, str):
-                res[:, k] = self.entropy_of_cut(st, sites[0]) if mat == "entropy" else self.project_onto_bitstring(st, mat[4:])
+            if not isinstance(mat, str):
+                continue
+            if mat == "entropy":
+                res[:, k] = self.entropy_of_cut(st, sites[0])
+            elif mat == "schmidt_spectrum":              # vector-valued: the row holds NaN, the spectrum goes to self.spectra[(k, column)]
+                self._spectra_now[k] = self.schmidt_of_cut(st, sites[0])
+                res[:, k] = float("nan")
+            else:
+                res[:, k] = self.project_onto_bitstring(st, mat[4:])
         return res
+
+    SCHMIDT_PAD = 500                                    # mps.py:660: the spectrum is padded / truncated to 500 entries
+
+    def schmidt_of_cut(self, st: BatchedState, i: int) -> torch.Tensor:
+        """MPS.get_schmidt_spectrum (mps.py:644-678): singular values of A_i A_{i+1} read as (d l) x (d r) on the tensors as stored,
+        NaN-padded to 500 entries; a bond of dimension 1 gives [1, NaN, ...] (:664-667).  [B, 500] float64.  The one-sided Jacobi
+        (high relative accuracy for every singular value) is used whatever the size -- this is a diagnostic, not the hot path."""
+        lay, B = self.lay, self.B
+        sd = lay.svd_dim
+        self.merge(st, i)
+        keep_all = self._trunc_args("discarded_weight", 0.0, None, 1)
+        self._svd(SVD_THETA, self._buf(self.theta, lay.theta_slot), st.ext(i), st.ext(i + 2), keep_all, "right", None, 0,
+                  (self.d * lay.cap[i], self.d * lay.cap[i + 2]))
+        meta = self.svd_meta.view(B, SVD_META)
+        nsv = torch.minimum(meta[:, 3], meta[:, 4])
+        n = min(self.SCHMIDT_PAD, sd)
+        out = torch.full((B, self.SCHMIDT_PAD), float("nan"), dtype=torch.float64, device=self.dev)
+        sv = self.svd_s.view(B, sd)[:, :n]
+        out[:, :n] = torch.where(torch.arange(n, device=self.dev)[None, :] < nsv[:, None], sv, torch.full_like(sv, float("nan")))
+        trivial = st.bond[:, i + 1] == 1
+        if bool(trivial.any()):
+            out[trivial] = float("nan")
+            out[trivial, 0] = 1.0
+        return out
 
     def entropy_of_cut(self, st: BatchedState, i: int) -> torch.Tensor:
         """MPS.get_entropy (mps.py:604-639): von Neumann entropy of the singular values of A_i A_{i+1} read as (d l) x (d r), on
@@ -1360,6 +1393,7 @@ class BatchedTJM:
         results = torch.zeros((self.B, nobs, ncol), dtype=torch.float64, device=self.dev)
         diag = torch.zeros((self.B, 3, ncol), dtype=torch.float64, device=self.dev)
         self.results, self.diag = results, diag
+        self.spectra: dict = {}                             # (observable row, column) -> [B, 500] Schmidt spectra
         self._pos = torch.zeros(self.B, dtype=torch.int64, device=self.dev) if start_pos is None else start_pos.to(self.dev, torch.int64).clone()
         self._traj_u = traj_uniforms
         measure_at = None
@@ -1389,6 +1423,8 @@ class BatchedTJM:
             diag[:, :, col] = self.diagnostics(state)
             if nobs:
                 results[:, :, col] = self.evaluate_observables(state)
+                for k, spec in self._spectra_now.items():
+                    self.spectra[(k, col)] = spec
 
         def traj_jump_test(state, tag):
             if self.noise is None:
@@ -1648,6 +1684,8 @@ class BatchedTJM:
         dimension 1, window = support +- 1 site, one symmetric 2TDVP sweep over the window with evolution time 1.
         Returns the new centre (the first window site)."""
         n, lay, K, B, d, p = self.L, self.lay, self.K, self.B, self.d, self.p
+        if p.tdvp_mode != "2site":                   # raised where the reference raises it: only a gate that takes the window route
+            raise ValueError(f'apply_two_qubit_gate_tdvp only supports tdvp_mode="2site"; got {p.tdvp_mode!r}.')
         if gate.generator is None:
             raise NotImplementedError("gates without a product-form generator need the gate-MPO route (SURVEY.md 8f)")
         key = (gate.name, tuple(gate.sites), tuple(np.asarray(f).tobytes() for f in gate.generator))

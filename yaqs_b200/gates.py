@@ -82,6 +82,14 @@ class Entropy(BaseGate):
         super().__init__(np.eye(2), name="entropy", interaction=2)
 
 
+class SchmidtSpectrum(BaseGate):
+    """Meta-observable: the Schmidt spectrum (singular values) across a nearest-neighbour cut, a length-500 vector padded with
+    NaN (gate_library.py:1903-1940, mps.py:644-678)."""
+
+    def __init__(self) -> None:
+        super().__init__(np.eye(2), name="schmidt_spectrum", interaction=2)
+
+
 class PVM(BaseGate):
     """Projection-valued measurement onto a computational-basis bitstring, site 0 first (gate_library.py:1796-1870)."""
 
@@ -133,6 +141,7 @@ class GateLibrary:
         return g
 
     entropy = staticmethod(lambda: Entropy())
+    schmidt_spectrum = staticmethod(lambda: SchmidtSpectrum())
     pvm = staticmethod(lambda bitstring: PVM(bitstring))
 
     @staticmethod

@@ -58,6 +58,22 @@ class KernelError(RuntimeError):
     pass
 
 
+class YbWorkspace(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int64) for n in ("state", "environments", "theta", "matvec", "krylov", "svd", "heev", "small", "total")]
+
+
+def workspace_bytes(length: int, nbatch: int, cap, mpo_bond, order: int, two_envs: bool, gram: bool = True, dphys: int = 2) -> dict:
+    """yb_workspace_bytes (include/yaqs_b200.h): device bytes per component for a batch -- host arithmetic of the library, callable
+    without a device.  ``Simulator`` sizes its waves from it."""
+    lib = load_library()
+    capa = (ctypes.c_int32 * (length + 1))(*[int(c) for c in cap])
+    da = (ctypes.c_int32 * (length + 1))(*[int(c) for c in mpo_bond])
+    out = YbWorkspace()
+    if lib.yb_workspace_bytes(int(length), int(nbatch), int(dphys), capa, da, int(order), int(bool(two_envs)), int(bool(gram)), ctypes.byref(out)) != 0:
+        raise KernelError(lib.yb_last_error().decode())
+    return {n: int(getattr(out, n)) for n, _ in YbWorkspace._fields_}
+
+
 def load_library() -> ctypes.CDLL:
     if not os.path.exists(_LIB_PATH):
         raise KernelError(f"{_LIB_PATH} is missing: build it with `python -m yaqs_b200.build` (there is no CPU fallback)")
@@ -68,7 +84,7 @@ def load_library() -> ctypes.CDLL:
 
 
 EXPORTED_SYMBOLS = [
-    "yb_last_error", "yb_version", "yb_launch_count", "yb_set_flop_counter", "yb_set_option", "yb_gemm", "yb_rcontract_mpo", "yb_wapply", "yb_env_identity", "yb_lanczos_init",
+    "yb_last_error", "yb_version", "yb_launch_count", "yb_set_flop_counter", "yb_set_option", "yb_workspace_bytes", "yb_gemm", "yb_rcontract_mpo", "yb_wapply", "yb_env_identity", "yb_lanczos_init",
     "yb_lanczos_step", "yb_lanczos_combine", "yb_svd_prepare", "yb_svd_round", "yb_svd_check", "yb_svd_finalize", "yb_svd_ambiguous", "yb_heev", "yb_heev_rows", "yb_svd_select", "yb_svd_gather",
     "yb_unpack_vh", "yb_copy_packed", "yb_apply_local_op", "yb_mpo_site_apply", "yb_norm2", "yb_scale", "yb_local_rdm", "yb_philox_uniform",
 ]

@@ -29,12 +29,6 @@ class Observable:
 
     def __init__(self, gate, sites=None, **gate_kwargs) -> None:
         if isinstance(gate, str):
-            if gate == "schmidt_spectrum":
-                # the reference's own Simulator.run cannot store it either: _store_observable_trajectory (simulator.py:932-942) assigns
-                # the 500-vector into a float row and raises "setting an array element with a sequence" (checked against the
-                # unmodified reference); MPS.get_schmidt_spectrum works only when called directly
-                raise NotImplementedError("observable 'schmidt_spectrum' is vector-valued; the reference's Simulator.run raises ValueError for "
-                                          "it (simulator.py:942), so there is no behaviour to reproduce on the B200 TJM path")
             if gate != "pvm" and hasattr(GateLibrary, gate):
                 resolved = getattr(GateLibrary, gate)(**gate_kwargs)
             else:                                     # simulation_parameters.py:388-400: any other string is a PVM bitstring
@@ -77,21 +71,21 @@ def _check_observable_mix(observables) -> None:
 
 def engine_observables(sorted_observables, length: int):
     """The sorted observables as the batched engine takes them: (matrix, sites) for local one-/two-site operators,
-    ("entropy", [i, i+1]) and ("pvm:<bitstring>", []) for the meta-observables (mps.py:1200-1217)."""
+    ("entropy" | "schmidt_spectrum", [i, i+1]) and ("pvm:<bitstring>", []) for the meta-observables (mps.py:1200-1217)."""
     out = []
     for o in sorted_observables:
         name = o.gate.name
         if name == "pvm":
             assert len(o.gate.bitstring) == length, "Bitstring length must match number of sites"
             out.append(("pvm:" + o.gate.bitstring, []))
-        elif name == "entropy":
+        elif name in ("entropy", "schmidt_spectrum"):
             sites = o.sites
             assert isinstance(sites, list), "Given metric requires a list of sites"
             assert len(sites) == 2, "Given metric requires 2 sites to act on."
             assert max(sites) - min(sites) == 1, "Entropy and Schmidt cuts must be nearest neighbor."
             for s in sites:
                 assert s in range(length), f"Observable acting on non-existing site: {s}"
-            out.append(("entropy", [min(sites), max(sites)]))
+            out.append((name, [min(sites), max(sites)]))
         else:
             if o.gate.interaction not in (1, 2):
                 raise ValueError("Local observable must be one-site or nearest-neighbor two-site.")

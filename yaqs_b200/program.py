@@ -520,10 +520,9 @@ def run_program(simulator, initial_state: State, program: SimulationProgram, noi
             procs = first.noise_model.processes if first.noise_model is not None else None
             if u.kind == "digital":
                 ep = _engine_params(sp, 1, True)
-                if ep.tdvp_mode != "2site":
-                    raise ValueError(f'apply_two_qubit_gate_tdvp only supports tdvp_mode="2site"; got {ep.tdvp_mode!r}.')
                 new = BatchedTJM(K, length, len(idx), ident, ep, list(procs) if procs is not None else None, obs, carried,
                                  bond_factor=BatchedTJM.mpo_route_bond_factor(first.compiled_circuit.layers, sp.gate_mode, length))
+                carried = eng = None                 # the constructor has copied the state: release the previous unit's engine NOW
                 r, dg = new.run_digital(first.compiled_circuit.layers, tu, sp.sample_layers, sp.gate_mode, None, start_pos=pos)
                 out_state = new.phi
                 if sp.shots is not None:             # _per_call_shots with shot_distribution = (shots, ntraj) (digital_tjm.py:752-768)
@@ -546,6 +545,7 @@ def run_program(simulator, initial_state: State, program: SimulationProgram, noi
                 sched = first.noise_model.scheduled_jumps if first.noise_model is not None else None
                 extra = u.interval_mpos or ()
                 new = BatchedTJM(K, length, len(idx), _first_mpo(first).tensors, ep, procs, obs, carried, scheduled_jumps=sched, extra_mpos=extra)
+                carried = eng = None                 # (waves are sized for ONE engine; two alive while a unit runs would not fit)
                 su = None
                 if ep.order == 2:
                     if simulator.rng_mode == "numpy":
@@ -568,7 +568,7 @@ def run_program(simulator, initial_state: State, program: SimulationProgram, noi
             last = u.instructions[-1]
             if last.sim_params.get_state and not _is_stochastic(last.noise_model):
                 checkpoints[last.index] = out_state.download(0)
-            carried, eng = out_state, new         # `eng` keeps the source buffers alive until the next engine has copied them
+            carried, eng = out_state, new         # alive only until the next unit's constructor has copied the state
         draws_local[rows] = pos.cpu().numpy()
         if compiled.get_state:
             final_tensors = carried.download(0)

@@ -171,6 +171,11 @@ class Simulator:
         if noise_model is not None:
             noise_model = noise_model.sample(rng=make_disorder_rng(getattr(sim_params, "random_seed", None)))   # :1269-1271
         result = Result(sim_params=sim_params, noise_model=noise_model)
+        if any(o.gate.name == "schmidt_spectrum" for o in (sim_params.observables or [])):
+            # the reference's Simulator.run cannot store a vector-valued observable: _store_observable_trajectory assigns the 500-vector
+            # into a float row (simulator.py:932-942) and numpy raises exactly this.  The spectrum is available where the reference
+            # offers it: backends.analog_tjm_1 (dtype=object results, analog_tjm.py:424-426)
+            raise ValueError("setting an array element with a sequence.")
         if isinstance(sim_params, AnalogSimParams):
             if not sim_params.get_state and not sim_params.observables:
                 raise ValueError("No output specified: either observables or get_state must be set.")
@@ -260,7 +265,12 @@ class Simulator:
             init_bonds[i + 1] = max(init_bonds[i + 1], t.shape[2])
         mpo_bonds = [int(mpo[0].shape[2])] + [int(w.shape[3]) for w in mpo]
         one = BatchLayout(length, 1, layout_chi(ep), mpo_bonds, init_bonds, bond_factor=bond_factor)
-        per = bytes_per_trajectory(one, ep.order, ep.tdvp_mode in ("1site", "dynamic"))
+        two_envs = ep.tdvp_mode in ("1site", "dynamic")
+        try:                                         # the library's own accounting (include/yaqs_b200.h: yb_workspace_bytes)
+            from .kernels import KernelError, workspace_bytes
+            per = workspace_bytes(length, 1, one.cap, one.D, ep.order, two_envs)["total"]
+        except (KernelError, OSError):               # host-twin tests on a box without the built library
+            per = bytes_per_trajectory(one, ep.order, two_envs)
         if torch.device(dev).type == "cuda":
             free, _total = torch.cuda.mem_get_info(dev)
         else:
