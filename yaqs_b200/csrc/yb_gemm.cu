@@ -283,8 +283,7 @@ cudaError_t launch_t(const YbGemmParams& P, int maxM, int maxN, cudaStream_t st)
 
 }  // namespace
 
-// RCONTRACT with the MPO tensor applied in the epilogue (yb_gemm_rw.cuh).  bk16 != 0: 16-deep k tiles in a 3-stage pipeline (half
-// the barriers per flop) instead of 8-deep in 4 stages.
+// RCONTRACT with the MPO tensor applied in the epilogue (yb_gemm_rw.cuh): 64 x 96 CTA tiles for right MPO bonds 3 and 6, else 64 x 128.
 cudaError_t yb_launch_gemm_rw(int nbatch, const int* mask, const int* el, int esl, const int* er, int esr, int dphys, int Dl, int Dr, const cplx* X,
                               long long sX, const cplx* R, long long sR, const cplx* W, cplx* Out, long long sOut, int max_l, int max_r,
                               unsigned long long* flops, int bk16, cudaStream_t st) {
@@ -292,7 +291,8 @@ cudaError_t yb_launch_gemm_rw(int nbatch, const int* mask, const int* el, int es
     rw::Params P;
     P.nbatch = nbatch; P.mask = mask; P.el = el; P.er = er; P.esl = esl; P.esr = esr; P.dphys = dphys; P.Dl = Dl; P.Dr = Dr;
     P.X = X; P.R = R; P.W = W; P.Out = Out; P.sX = sX; P.sR = sR; P.sOut = sOut; P.flops = flops;
-    return bk16 ? rw::launch<16, 3>(P, max_l, max_r, st) : rw::launch<8, 4>(P, max_l, max_r, st);
+    (void)bk16;                                           // 16-deep k tiles measured no faster (profiles/r02_matvec_microbench_v1.json)
+    return (Dr == 3 || Dr == 6) ? rw::launch<8, 4, 3>(P, max_l, max_r, st) : rw::launch<8, 4, 4>(P, max_l, max_r, st);
 }
 
 // maxM / maxN: upper bounds of the per-trajectory M and N (grid is sized for them; empty tiles exit).

@@ -15,19 +15,23 @@
 
 namespace rw {
 
-constexpr int BM = 64, BN = 128, NTHREADS = 256;
-constexpr int T_LD = BN + 2;                     // epilogue tile pitch (complex)
+constexpr int BM = 64, NTHREADS = 256;
 constexpr int W_MAX = 4 * 4 * 8 * 8;             // MPO tensor entries held in shared memory (d~ <= 4, bonds <= 8)
 constexpr int W2_MAX = 32 * 33;                  // the same tensor as a zero-padded (d~ Dl) x (d~ Dr) matrix, pitch Kp + 1
 
-template <int BKT, int STAGES>
+// NT = 8-column tiles per warp: CTA tile 64 x (32 NT).  NT = 3 (64 x 96) when the right MPO bond is 3 or 6 -- TR = 32 / 16 then fills
+// the tile exactly and chi = 128 splits into whole column tiles (the 64 x 128 tile would run 4 column tiles of 40 with the last one
+// 20 % full, or waste a quarter of its columns); NT = 4 otherwise.
+template <int BKT, int STAGES, int NT>
 struct Cfg {
+    static constexpr int BN = 32 * NT;
+    static constexpr int T_LD = BN + 2;                          // epilogue tile pitch (complex)
     static constexpr int A_LD = BKT + 4;                         // A stored [m][k]
     static constexpr int B_LD = BN + 2;                          // B stored [k][n]
     static constexpr int A_STAGE = BM * A_LD, B_STAGE = BKT * B_LD;
     static constexpr size_t PIPE = (size_t)STAGES * (A_STAGE + B_STAGE);
     static constexpr size_t TILE = (size_t)BM * T_LD;
-    static constexpr size_t SMEM = ((PIPE > TILE ? PIPE : TILE) + W_MAX + W2_MAX) * sizeof(cplx);
+    static constexpr size_t SMEM = ((PIPE > TILE ? PIPE : TILE) + W_MAX + W2_MAX) * sizeof(cplx) + (32 + 32) * sizeof(long long);
 };
 
 struct Params {
@@ -40,9 +44,10 @@ struct Params {
     unsigned long long* flops;
 };
 
-template <int BKT, int STAGES>
+template <int BKT, int STAGES, int NT>
 __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_rw(const Params P) {
-    using C = Cfg<BKT, STAGES>;
+    using C = Cfg<BKT, STAGES, NT>;
+    constexpr int BN = C::BN, T_LD = C::T_LD;
     const int b = blockIdx.z;
     if (P.mask && !P.mask[b]) return;
     const int chil = P.el[(long long)b * P.esl], chir = P.er[(long long)b * P.esr];
@@ -115,11 +120,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_rw(const Params P) {
         cp_async_commit();
     };
 
-    double cr[4][4][2], ci[4][4][2];
+    double cr[4][NT][2], ci[4][NT][2];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) { cr[i][j][0] = cr[i][j][1] = ci[i][j][0] = ci[i][j][1] = 0.0; }
+        for (int j = 0; j < NT; ++j) { cr[i][j][0] = cr[i][j][1] = ci[i][j][0] = ci[i][j][1] = 0.0; }
 
 #pragma unroll
     for (int s = 0; s < STAGES - 1; ++s) load_stage(s, s);
@@ -133,21 +138,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_rw(const Params P) {
         const cplx* bs = Bs + (kt % STAGES) * C::B_STAGE;
 #pragma unroll
         for (int kk = 0; kk < BKT; kk += 4) {
-            double ar[4], ai[4], an[4], br[4], bi[4];
+            double ar[4], ai[4], an[4], br[NT], bi[NT];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const cplx v = as[(wm * 32 + i * 8 + fr) * C::A_LD + kk + fk];
                 ar[i] = v.x; ai[i] = v.y; an[i] = flip_sign(v.y);
             }
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const cplx v = bs[(kk + fk) * C::B_LD + wn * 32 + j * 8 + fr];
+            for (int j = 0; j < NT; ++j) {
+                const cplx v = bs[(kk + fk) * C::B_LD + wn * (8 * NT) + j * 8 + fr];
                 br[j] = v.x; bi[j] = v.y;
             }
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
+                for (int j = 0; j < NT; ++j) {
                     dmma(cr[i][j][0], cr[i][j][1], ar[i], br[j]);
                     dmma(ci[i][j][0], ci[i][j][1], ar[i], bi[j]);
                     dmma(cr[i][j][0], cr[i][j][1], an[i], bi[j]);
@@ -169,8 +174,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_rw(const Params P) {
     for (int i = 0; i < 4; ++i) {
         const int row = wm * 32 + i * 8 + fr;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int col = wn * 32 + j * 8 + 2 * fk;
+        for (int j = 0; j < NT; ++j) {
+            const int col = wn * (8 * NT) + j * 8 + 2 * fk;
             Ts[row * T_LD + col] = make_double2(cr[i][j][0], ci[i][j][0]);
             Ts[row * T_LD + col + 1] = make_double2(cr[i][j][1], ci[i][j][1]);
         }
@@ -179,6 +184,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_rw(const Params P) {
     const int Mp = (Mw + 7) & ~7, Kp = (Kw + 3) & ~3;
     const int W2_LD = Kp + 1;
     cplx* W2 = Ws + W_MAX;                                  // [Mp][Kp + 1], zero-padded
+    int* koff = reinterpret_cast<int*>(W2 + W2_MAX);        // [Kp]  offset of (u, v) in the parked tile, -1 beyond Kw   (64 ints)
+    long long* moff = reinterpret_cast<long long*>(koff + 64);   // [Mp]  offset of (x, y) in the output, -1 beyond Mw          (32)
     for (int e = tid; e < Mp * W2_LD; e += NTHREADS) {
         const int m = e / W2_LD, k = e - m * W2_LD;
         cplx w = make_double2(0.0, 0.0);
@@ -188,34 +195,35 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_rw(const Params P) {
         }
         W2[e] = w;
     }
+    if (tid < Kp) { const int u = tid / Dr, v = tid - u * Dr; koff[tid] = tid < Kw ? u * TL * T_LD + v * TR : -1; }
+    if (tid >= 64 && tid < 64 + Mp) {
+        const int m = tid - 64, x = m / Dl, y = m - x * Dl;
+        moff[m] = m < Mw ? ((long long)x * chil * Dl + y) * chir : -1;
+    }
     __syncthreads();
-    cplx* Ob = P.Out + (long long)b * P.sOut;
+    cplx* Ob = P.Out + (long long)b * P.sOut + (long long)l0 * Dl * chir + r0;
     const int tiles_per_row = TR >> 3;                      // 8-position tiles per li
-    const int ntile = TL * tiles_per_row;
+    const int ntile = nl * tiles_per_row;                   // only the rows this tile owns
     for (int nt_ = warp; nt_ < ntile; nt_ += NTHREADS / 32) {
         const int li = nt_ / tiles_per_row, ri0 = (nt_ - li * tiles_per_row) << 3;
-        if (li >= nl || ri0 >= nr) continue;                // warp-uniform: nothing to store from this tile
-        const cplx* tpos = Ts + li * T_LD + ri0 + fr;       // + u * TL * T_LD + v * TR per k
+        if (ri0 >= nr) continue;                            // warp-uniform: nothing to store from this tile
+        const cplx* tpos = Ts + li * T_LD + ri0 + fr;
+        const int ri = ri0 + 2 * fk;
+        cplx* orow = Ob + (long long)li * Dl * chir + ri;
         for (int m0 = 0; m0 < Mp; m0 += 8) {
             double c_r0 = 0.0, c_r1 = 0.0, c_i0 = 0.0, c_i1 = 0.0;
             for (int k0 = 0; k0 < Kp; k0 += 4) {
-                const int k = k0 + fk;
-                const cplx av = W2[(m0 + fr) * W2_LD + k];
-                cplx bv = make_double2(0.0, 0.0);
-                if (k < Kw) {
-                    const int u = k / Dr, v = k - u * Dr;
-                    bv = tpos[u * TL * T_LD + v * TR];
-                }
+                const cplx av = W2[(m0 + fr) * W2_LD + k0 + fk];
+                const int off = koff[k0 + fk];
+                const cplx bv = off >= 0 ? tpos[off] : make_double2(0.0, 0.0);
                 dmma(c_r0, c_r1, av.x, bv.x);
                 dmma(c_i0, c_i1, av.x, bv.y);
                 dmma(c_r0, c_r1, flip_sign(av.y), bv.y);
                 dmma(c_i0, c_i1, av.y, bv.x);
             }
-            const int m = m0 + fr;
-            const int ri = ri0 + 2 * fk;
-            if (m < Mw && ri < nr) {
-                const int x = m / Dl, y = m - x * Dl;
-                cplx* dst = Ob + (((long long)x * chil + l0 + li) * Dl + y) * chir + r0 + ri;
+            const long long mo = moff[m0 + fr];
+            if (mo >= 0 && ri < nr) {
+                cplx* dst = orow + mo;
                 dst[0] = make_double2(c_r0, c_i0);
                 if (ri + 1 < nr) dst[1] = make_double2(c_r1, c_i1);
             }
@@ -223,19 +231,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_rw(const Params P) {
     }
 }
 
-template <int BKT, int STAGES>
+template <int BKT, int STAGES, int NT>
 cudaError_t launch(const Params& P, int max_l, int max_r, cudaStream_t st) {
-    using C = Cfg<BKT, STAGES>;
+    using C = Cfg<BKT, STAGES, NT>;
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(k_gemm_rw<BKT, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+        cudaError_t e = cudaFuncSetAttribute(k_gemm_rw<BKT, STAGES, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    const int TL = BM / P.dphys, TR = (BN / P.Dr) & ~7;
+    const int TL = BM / P.dphys, TR = (C::BN / P.Dr) & ~7;
     const int tiles = ((max_l + TL - 1) / TL) * ((max_r + TR - 1) / TR);
     dim3 grid(tiles, 1, P.nbatch);
-    k_gemm_rw<BKT, STAGES><<<grid, NTHREADS, C::SMEM, st>>>(P);
+    k_gemm_rw<BKT, STAGES, NT><<<grid, NTHREADS, C::SMEM, st>>>(P);
     return cudaGetLastError();
 }
 

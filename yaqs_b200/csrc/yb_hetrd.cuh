@@ -237,39 +237,66 @@ __global__ void __launch_bounds__(THREADS, 1) k_ormtr_rows(const cplx* __restric
         if (tid < cnt) taus[tid] = cconj(tauv[jlo + tid]);
         __syncthreads();
         const int t0 = (jlo + 1) >> 5;                     // first 32-element chunk any reflector of the panel touches
-        for (int c = warp; c < n; c += NWARPS) {
-            cplx row[NE];
-            cplx* mrow = Mb + (long long)c * n;
+        // two rows per warp and iteration: the reflector is read from shared memory once for both, and the two dot -> reduce -> axpy
+        // chains are independent (the first version walked one row per warp and spent 40 % of its stalls on those shared-memory reads,
+        // profiles/r02_ncu_heev_rows_v1.json)
+        constexpr bool PAIR = NE <= 8;                      // 16 elements per lane (k > 256): two rows would not fit in 128 registers
+        constexpr int RPW = PAIR ? 2 : 1;
+        for (int c = RPW * warp; c < n; c += RPW * NWARPS) {
+            const bool two = PAIR && (c + 1 < n);
+            cplx ra[NE], rb[NE];
+            cplx* mrow_a = Mb + (long long)c * n;
+            cplx* mrow_b = mrow_a + n;
 #pragma unroll
             for (int t = 0; t < NE; ++t) {
                 const int e = lane + 32 * t;
-                row[t] = (t >= t0 && e < n) ? mrow[e] : make_double2(0.0, 0.0);
+                const bool ok = t >= t0 && e < n;
+                ra[t] = ok ? mrow_a[e] : make_double2(0.0, 0.0);
+                rb[t] = (ok && two) ? mrow_b[e] : make_double2(0.0, 0.0);
             }
             for (int q = cnt - 1; q >= 0; --q) {
                 const cplx* v = Vp + (size_t)q * LD + lane;
                 const int tq = (jlo + q + 1) >> 5;
-                double sr = 0.0, si = 0.0;
+                cplx vv[PAIR ? NE : 1];                      // the reflector stays in registers between dot and axpy when it fits
+                double sar = 0.0, sai = 0.0, sbr = 0.0, sbi = 0.0;
 #pragma unroll
                 for (int t = 0; t < NE; ++t) {
                     if (t < tq) continue;
-                    const cplx vv = v[32 * t];
-                    sr += row[t].x * vv.x - row[t].y * vv.y;
-                    si += row[t].x * vv.y + row[t].y * vv.x;
+                    const cplx x = v[32 * t];
+                    if constexpr (PAIR) vv[t] = x;
+                    sar += ra[t].x * x.x - ra[t].y * x.y;
+                    sai += ra[t].x * x.y + ra[t].y * x.x;
+                    if constexpr (PAIR) {
+                        sbr += rb[t].x * x.x - rb[t].y * x.y;
+                        sbi += rb[t].x * x.y + rb[t].y * x.x;
+                    }
                 }
-                sr = warp_sum(sr); si = warp_sum(si);
-                const cplx f = cmul(taus[q], make_double2(sr, si));          // conj(tau) (row . v)
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    sar += __shfl_xor_sync(0xffffffffu, sar, o); sai += __shfl_xor_sync(0xffffffffu, sai, o);
+                    if constexpr (PAIR) { sbr += __shfl_xor_sync(0xffffffffu, sbr, o); sbi += __shfl_xor_sync(0xffffffffu, sbi, o); }
+                }
+                const cplx fa = cmul(taus[q], make_double2(sar, sai)), fb = cmul(taus[q], make_double2(sbr, sbi));   // conj(tau) (row . v)
 #pragma unroll
                 for (int t = 0; t < NE; ++t) {
                     if (t < tq) continue;
-                    const cplx vv = v[32 * t];
-                    row[t].x -= f.x * vv.x + f.y * vv.y;                     // f * conj(v)
-                    row[t].y -= f.y * vv.x - f.x * vv.y;
+                    cplx x;
+                    if constexpr (PAIR) x = vv[t]; else x = v[32 * t];
+                    ra[t].x -= fa.x * x.x + fa.y * x.y;                        // f * conj(v)
+                    ra[t].y -= fa.y * x.x - fa.x * x.y;
+                    if constexpr (PAIR) {
+                        rb[t].x -= fb.x * x.x + fb.y * x.y;
+                        rb[t].y -= fb.y * x.x - fb.x * x.y;
+                    }
                 }
             }
 #pragma unroll
             for (int t = 0; t < NE; ++t) {
                 const int e = lane + 32 * t;
-                if (t >= t0 && e < n) mrow[e] = row[t];
+                if (t >= t0 && e < n) {
+                    mrow_a[e] = ra[t];
+                    if (two) mrow_b[e] = rb[t];
+                }
             }
         }
     }
