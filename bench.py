@@ -44,7 +44,7 @@ WORKLOADS = {
                text="Ising L=10, chi=16"),
     "C2": dict(model="heisenberg", length=30, chi=64, noise=("lowering",), gamma=0.1, batch=1000, threshold=1e-6, bound="tensor", zz=True,
                text="Heisenberg L=30, chi=64"),
-    "C3": dict(model="ising", length=100, chi=128, noise=("lowering", "pauli_z"), gamma=0.1, batch=128, threshold=1e-6, bound="tensor",
+    "C3": dict(model="ising", length=100, chi=128, noise=("lowering", "pauli_z"), gamma=0.1, batch=192, threshold=1e-6, bound="tensor",
                text="Ising L=100, chi=128"),
     "C5": dict(model="heisenberg", length=200, chi=256, noise=("lowering", "pauli_z"), gamma=0.05, xx=0.01, batch=16, threshold=1e-6, bound="tensor",
                text="Heisenberg L=200, chi=256"),

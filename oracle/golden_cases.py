@@ -207,7 +207,7 @@ def run_oracle_case(cfg: dict, trajectories=None):
     """Run the oracle with the reference's seeded numpy streams; returns a list of TrajectoryTrace."""
     init, mpo, noise, p, obs = oracle_inputs(cfg)
     out = []
-    for tr in (range(cfg["ntraj"]) if trajectories is None else trajectories):
+    for tr in (cfg.get("traj_ids", range(cfg["ntraj"])) if trajectories is None else trajectories):     # global trajectory indices
         rng = O.UniformStream(O.trajectory_stream(cfg["seed"], tr))
         if cfg["order"] == 2:
             tr_out = O.analog_tjm_2(init, mpo, noise, p, obs, rng,
@@ -273,7 +273,18 @@ LARGE_DIGITAL_CASES = {
                            noise=[("pauli_z", 0.01)],
                            noise2=[("crosstalk_xx", 0.01), ("crosstalk_yy", 0.01), ("crosstalk_zz", 0.01)]),
 }
-ALL_DIGITAL_CASES = {**DIGITAL_CASES, **LARGE_DIGITAL_CASES}
+# BASELINE config 4 AT ITS OWN SIZE: create_ising_circuit(L = 49, J = 1, g = 0.5, dt = 0.1, timesteps = 40), bond cap 64,
+# "2-qubit depolarizing" at p = 1e-3 per pair = the 15 non-identity two-qubit Paulis at p / 15 each: the 9 crosstalk_ab processes
+# on every nearest-neighbour pair and the 6 single-qubit Paulis of its two sites (a site of the bulk belongs to two pairs, so every
+# site carries pauli_x / y / z at 2 p / 15).  1920 two-qubit gates per trajectory, each followed by the reference's full-chain
+# dissipation walk: ~10 minutes per trajectory for the reference.
+FULL_DIGITAL_CASES = {
+    "dig_ising49_c4_full": dict(L=49, J=1.0, g=0.5, dt=0.1, timesteps=40, periodic=False, chi=64, thr=1e-6, ntraj=2, seed=42,
+                                init="zeros", obs="z", sample=False, gate_mode="mpo",
+                                noise=[("pauli_x", 2e-3 / 15), ("pauli_y", 2e-3 / 15), ("pauli_z", 2e-3 / 15)],
+                                noise2=[(f"crosstalk_{a}{b}", 1e-3 / 15) for a in "xyz" for b in "xyz"]),
+}
+ALL_DIGITAL_CASES = {**DIGITAL_CASES, **LARGE_DIGITAL_CASES, **FULL_DIGITAL_CASES}
 
 
 def toffoli_gate_list(cfg: dict) -> list[tuple]:
@@ -346,7 +357,7 @@ def digital_inputs(cfg: dict):
 def run_oracle_digital_case(cfg: dict, trajectories=None):
     init, layers, noise, p, obs = digital_inputs(cfg)
     out = []
-    for tr in (range(cfg["ntraj"]) if trajectories is None else trajectories):
+    for tr in (cfg.get("traj_ids", range(cfg["ntraj"])) if trajectories is None else trajectories):     # global trajectory indices
         rng = O.UniformStream(O.trajectory_stream(cfg["seed"], tr))
         out.append(O.digital_tjm(init, layers, noise, p, obs, rng, sample_layers=cfg["sample"], gate_mode=cfg["gate_mode"]))
     return out

@@ -7,7 +7,7 @@ import torch
 
 import os
 
-from oracle.golden_cases import CASES, LARGE_CASES, STRESS_CASES
+from oracle.golden_cases import CASES, LARGE_CASES, LONG_CASES, STRESS_CASES
 from tests.helpers import check_against_golden, engine_for_case
 from yaqs_b200.kernels import CudaKernels
 
@@ -55,6 +55,25 @@ def test_cuda_engine_matches_reference_stress(golden_dir, name):
     check_against_golden(name, golden_dir, results, diag, log, traj)
 
 
+@pytest.mark.parametrize("name,first,batch", [("ising100_c3_10steps", 64, 64), ("heis30_c2_10steps", 488, 512)])
+def test_cuda_engine_long_run_at_baseline_sizes(golden_dir, name, first, batch):
+    """the headline workload over TEN sampled steps as a real batch.  C3 (Ising L = 100, chi = 128): the 64
+    trajectories 64 .. 127 of the seed-42 ensemble -- among them 103 and 113, two of the three the driver's run flagged -- C2
+    (Heisenberg L = 30, chi = 64, Z and ZZ): trajectories 488 .. 999.  Every status word clean, every observable finite and in
+    [-1, 1], and the trajectories the fixture holds equal to the UNMODIFIED reference over all ten steps: same jumps, identical bond
+    dimensions, observables <= 1e-10."""
+    kern = CudaKernels("cuda:0")
+    traj = list(range(first, first + batch))
+    eng, tu, su, traj = engine_for_case(name, kern, trajectories=traj)
+    log = []
+    results, diag = eng.run(tu, su, log)
+    torch.cuda.synchronize()
+    assert int(eng.status.max().item()) == 0
+    assert bool(torch.isfinite(results).all()) and float(results.abs().max()) <= 1.0 + 1e-9
+    assert eng.stats["gram_svd_calls"] > 0 and eng.stats["jumps"] > 0
+    assert check_against_golden(name, golden_dir, results, diag, log, traj) == len(LONG_CASES[name]["traj_ids"])
+
+
 @pytest.mark.parametrize("block_rows", [1, 2])
 def test_cuda_engine_multi_block_jacobi(golden_dir, block_rows):
     """Force the multi-round block Jacobi schedule (several block pairs per matrix) on a case that reaches chi = 16."""
@@ -80,11 +99,11 @@ def test_cuda_engine_gram_svd_route(golden_dir, name):
     check_against_golden(name, golden_dir, results, diag, log, traj)
 
 
-from oracle.golden_cases import DIGITAL_CASES, LARGE_DIGITAL_CASES  # noqa: E402
+from oracle.golden_cases import DIGITAL_CASES, FULL_DIGITAL_CASES, LARGE_DIGITAL_CASES  # noqa: E402
 from tests.helpers import digital_engine_for_case  # noqa: E402
 
 
-@pytest.mark.parametrize("name", sorted(LARGE_DIGITAL_CASES))
+@pytest.mark.parametrize("name", sorted(LARGE_DIGITAL_CASES) + sorted(FULL_DIGITAL_CASES))
 def test_cuda_digital_tjm_matches_reference_at_baseline_size(golden_dir, name):
     """BASELINE.json config 4 at its own size (49 qubits, circuit depth 40, Pauli noise on every nearest-neighbour pair) against
     the unmodified reference's digital_tjm: same jumps, identical bond dimensions, observables <= 1e-10."""

@@ -510,7 +510,13 @@ class BatchedTJM:
             geo = self._jac_geo[key] = (rows, nb, 30 if nb == 2 else 1, lmax, kmax)
         return geo
 
-    GRAM_TAU = 1e-6          # rows below GRAM_TAU * s_max^2 are re-diagonalised at their own scale (second level)
+    # Rows of the rotated matrix whose squared norm is below GRAM_TAU * s_max^2 are re-diagonalised at their own scale (second level).
+    # Only the rows a 1e-12 discarded-weight decision can depend on need that: an unselected row contributes >= GRAM_TAU * s_max^2 to
+    # every cumulative sum it is part of, and s_max^2 >= 1 / chi for a normalised state, so at 1e-8 those sums stay >= 7.8e-11 (chi = 128)
+    # or 2e-11 (chi = 512) -- an order of magnitude above the threshold plus the first-level error bound (16 k eps s_max^2 <= 2e-12).
+    # Round 1 used 1e-6, which re-diagonalised every singular value below 1e-3 s_max: a second eigen-solve on ~20 % of the rows of
+    # EVERY gauge shift of the saturated C3 state for decisions that never came near the threshold.
+    GRAM_TAU = float(os.environ.get("YB_GRAM_TAU", "1e-8"))
 
     def _svd_gram(self, mode: int, src: Buf, el: Ext, er: Ext, trunc, dist: str, mask, dims: tuple[int, int] | None = None) -> None:
         """M = U S Vh through the Hermitian eigen-problem of a Gram matrix.
