@@ -107,12 +107,12 @@ def test_wapply_matches_twin(backends, dims):
     _cmp(d_c, d_g)
 
 
-@pytest.mark.parametrize("bk16", [0, 1])
+@pytest.mark.parametrize("warps16", [0, 1])
 @pytest.mark.parametrize("dims", [(4, 3, 3, 40), (4, 4, 3, 128), (2, 3, 3, 37), (2, 5, 5, 64), (4, 5, 4, 33), (1, 3, 3, 17), (4, 1, 1, 21), (2, 4, 1, 8),
                                   (4, 5, 5, 130)])
-def test_rcontract_mpo_matches_twin(backends, dims, bk16):
+def test_rcontract_mpo_matches_twin(backends, dims, warps16):
     """project_site's first two contractions in one kernel (MPO tensor applied in the GEMM epilogue) against the numpy twin --
-    ragged extents, both tile depths, MPO tensors with the reference's sparsity (~30 % non-zero)."""
+    ragged extents, both warp layouts, MPO tensors with the reference's sparsity (~30 % non-zero)."""
     cuda, twin = backends
     dphys, dl, dr, cap = dims
     rng = np.random.default_rng(11 * cap + dphys + dl)
@@ -127,7 +127,7 @@ def test_rcontract_mpo_matches_twin(backends, dims, bk16):
     x, r, w = rc(nb * sx), rc(nb * sr), rc(dphys * dphys * dl * dr)
     w[rng.random(w.shape) > 0.35] = 0
     outs = []
-    cuda.set_option("gemm_bk16", bk16)
+    cuda.set_option("gemm_warps16", warps16)
     try:
         for kern, dev in ((twin, "cpu"), (cuda, "cuda")):
             et = torch.from_numpy(ext).to(dev)
@@ -136,7 +136,7 @@ def test_rcontract_mpo_matches_twin(backends, dims, bk16):
                                Buf(torch.from_numpy(r).to(dev), 0, sr), torch.from_numpy(w).to(dev), Buf(out, 0, so), cap, cap)
             outs.append(out.cpu().numpy().reshape(nb, so))
     finally:
-        cuda.set_option("gemm_bk16", 0)
+        cuda.set_option("gemm_warps16", 0)
     for t in range(nb):
         n = dphys * ext[t, 0] * dl * ext[t, 1] if mask[t] else 0
         scale = max(1.0, np.abs(outs[0][t, :n]).max()) if n else 1.0
@@ -601,9 +601,11 @@ def test_mpo_site_apply_matches_twin(backends, dl, dr):
 
 @pytest.mark.parametrize("case", GEMM_CASES)
 @pytest.mark.parametrize("cap", [5, 37, 113])
-def test_gemm_ragged_option_is_bit_identical(backends, case, cap):
-    """A/B option "gemm_ragged" (interleaved 8 x 8 sub-tiles, padding sub-tiles skipped): every output element is the same sum in
-    the same order, so the result must equal the default tiling bit for bit on ragged and full operands."""
+@pytest.mark.parametrize("option", ["gemm_ragged", "gemm_warps16"])
+def test_gemm_ragged_option_is_bit_identical(backends, case, cap, option):
+    """Tiling options "gemm_ragged" (interleaved 8 x 8 sub-tiles, padding sub-tiles skipped) and "gemm_warps16" (16 warps with 16 x 32
+    warp tiles instead of 8 with 32 x 32): every output element is the same sum in the same order, so the result must equal the
+    default tiling bit for bit on ragged and full operands."""
     cuda, _ = backends
     op, ngroups, dphys, Dl, Dr, conj = case
     rng = np.random.default_rng(2000 * op + cap)
@@ -619,14 +621,14 @@ def test_gemm_ragged_option_is_bit_identical(backends, case, cap):
     outs = []
     try:
         for flag in (0, 1):
-            cuda.set_option("gemm_ragged", flag)
+            cuda.set_option(option, flag)
             c = c0.clone().cuda()
             cuda.gemm(op, nb, ngroups, mask, Ext(e, 0, 3), Ext(e, 1, 3), Ext(e, 2, 3), dphys, Dl, Dr, Buf(a, 0, sa), Buf(b, 0, sb), Buf(c, 0, sc),
                       conj, maxm, maxm)
             torch.cuda.synchronize()
             outs.append(c.cpu().numpy())
     finally:
-        cuda.set_option("gemm_ragged", 0)
+        cuda.set_option(option, 0)
     assert np.array_equal(outs[0], outs[1])
 
 

@@ -47,18 +47,20 @@ def main():
         f2 = lambda: kern.wapply(nb, None, el, er, dphys, dphys, D, D, w, b1, b2, c2)
         f3 = lambda: kern.gemm(K.OP_LCONTRACT, nb, dphys, None, el, er, None, dphys, D, D, bl, b2, by, 0, chi, chi)
         ff = lambda: kern.rcontract_mpo(nb, None, el, er, dphys, D, D, bx, br, w, b3, chi, chi)
-        m1, m2, m3 = timed(f1), timed(f2), timed(f3)
-        kern.set_option("gemm_bk16", 0)
-        mf8 = timed(ff)
-        err8 = float((t3 - t2).abs().max().item())
-        kern.set_option("gemm_bk16", 1)
-        mf16 = timed(ff)
-        err16 = float((t3 - t2).abs().max().item())
-        kern.set_option("gemm_bk16", 0)
         fl = 8.0 * dphys * D * chi ** 3 * nb
         flw = 8.0 * dphys * dphys * D * D * chi * chi * nb
+        m1, m2, m3 = timed(f1), timed(f2), timed(f3)
+        mf8 = timed(ff)
+        err8 = float((t3 - t2).abs().max().item())
+        kern.set_option("gemm_warps16", 1)                      # 16 warps, 16 x 32 warp tiles
+        mf16 = timed(ff)
+        err16 = float((t3 - t2).abs().max().item())
+        m1w, m3w = timed(f1), timed(f3)
+        kern.set_option("gemm_warps16", 0)
         key = f"b{nb}_chi{chi}_D{D}_d{dphys}"
         out[key] = {"rcontract_ms": m1, "wapply_ms": m2, "lcontract_ms": m3, "fused_bk8_ms": mf8, "fused_bk16_ms": mf16,
+                    "rcontract_warps16_ms": m1w, "lcontract_warps16_ms": m3w, "fused_warps16_ms": mf16,
+                    "matvec_fused_warps16_frac": (2 * fl + flw) / (mf16 + m3w) / 1e9 / PEAK,
                     "rcontract_frac": fl / m1 / 1e9 / PEAK, "lcontract_frac": fl / m3 / 1e9 / PEAK,
                     "fused_bk8_frac": (fl + flw) / mf8 / 1e9 / PEAK, "fused_bk16_frac": (fl + flw) / mf16 / 1e9 / PEAK,
                     "matvec_round1_frac": (2 * fl + flw) / (m1 + m2 + m3) / 1e9 / PEAK, "matvec_fused_frac": (2 * fl + flw) / (min(mf8, mf16) + m3) / 1e9 / PEAK,

@@ -90,12 +90,14 @@ static std::atomic<int> g_opt_heev_ring{getenv("YB_HEEV_RING") != nullptr ? atoi
 
 static std::atomic<int> g_opt_wapply_onepass{getenv("YB_WAPPLY_ONEPASS") != nullptr ? atoi(getenv("YB_WAPPLY_ONEPASS")) : 0};
 static std::atomic<int> g_opt_gemm_bk16{getenv("YB_GEMM_BK16") != nullptr ? atoi(getenv("YB_GEMM_BK16")) : 0};
+static std::atomic<int> g_opt_gemm_warps16{getenv("YB_GEMM_WARPS16") != nullptr ? atoi(getenv("YB_GEMM_WARPS16")) : 0};
 static std::atomic<int> g_opt_gemm_ragged{getenv("YB_GEMM_RAGGED") != nullptr ? atoi(getenv("YB_GEMM_RAGGED")) : 0};
 
 int yb_set_option(const char* name, int value) {
     if (!name) return fail_msg("yb_set_option: null name");
     if (!strcmp(name, "gemm_ragged")) { g_opt_gemm_ragged = value != 0; return 0; }
     if (!strcmp(name, "gemm_bk16")) { g_opt_gemm_bk16 = value != 0; return 0; }
+    if (!strcmp(name, "gemm_warps16")) { g_opt_gemm_warps16 = value != 0; return 0; }
     if (!strcmp(name, "wapply_onepass")) { g_opt_wapply_onepass = value != 0; return 0; }
     if (!strcmp(name, "heev_ql")) { g_opt_heev_ql = value != 0; return 0; }
     if (!strcmp(name, "heev_ring")) { g_opt_heev_ring = value; return 0; }
@@ -115,6 +117,7 @@ int yb_gemm(int op, int nbatch, int ngroups, const int32_t* mask, yb_extent e0, 
     P.A = (const cplx*)a; P.Bm = (const cplx*)b; P.C = (cplx*)c; P.sA = stride_a; P.sB = stride_b; P.sC = stride_c;
     P.conj_extra = conj_b;
     P.ragged = g_opt_gemm_ragged.load(std::memory_order_relaxed);
+    P.warps16 = g_opt_gemm_warps16.load(std::memory_order_relaxed);
     P.flops = g_flop_counter;
     cudaError_t e = yb_launch_gemm(P, max_m, max_n, (cudaStream_t)stream);
     if (e != cudaSuccess) return fail("yb_gemm", e);
@@ -129,7 +132,8 @@ int yb_rcontract_mpo(int nbatch, const int32_t* mask, yb_extent el, yb_extent er
         return fail_msg("yb_rcontract_mpo: MPO bond dimensions out of range (1 .. 8)");
     cudaError_t e = yb_launch_gemm_rw(nbatch, mask, el.ptr, el.stride, er.ptr, er.stride, dphys, d_left, d_right, (const cplx*)x, stride_x,
                                       (const cplx*)renv, stride_r, (const cplx*)wt, (cplx*)out, stride_out, max_l, max_r, g_flop_counter,
-                                      g_opt_gemm_bk16.load(std::memory_order_relaxed), (cudaStream_t)stream);
+                                      g_opt_gemm_bk16.load(std::memory_order_relaxed), g_opt_gemm_warps16.load(std::memory_order_relaxed),
+                                      (cudaStream_t)stream);
     if (e != cudaSuccess) return fail("yb_rcontract_mpo", e);
     return done("yb_rcontract_mpo");
 }

@@ -14,7 +14,7 @@
 
 namespace {
 
-constexpr int BM = 64, BN = 128, BKT = 8, STAGES = 4, NTHREADS = 256;
+constexpr int BM = 64, BN = 128, BKT = 8, STAGES = 4;
 constexpr int A_KIN_LD = BKT + 4;   // A stored [m][k]
 constexpr int A_KOUT_LD = BM + 2;   // A stored [k][m]
 constexpr int B_KIN_LD = BKT + 4;   // B stored [n][k]
@@ -135,8 +135,13 @@ __device__ __forceinline__ double flip_sign(double x) {
 // DMMA.  With ragged bonds (chi ~ 113 of 128: M = 4*113 = 452, N = 3*113 = 339) the last tile row / column of a 64 x 128 CTA tile is
 // mostly padding; interleaving spreads the surviving sub-tiles evenly over the 8 warps (2 per SM sub-partition), so the DMMA pipe of
 // every sub-partition sees the same reduction.  Same sums in the same order per output element: results are bit-identical.
-template <int ALAY, int BLAY, bool RAGGED>
-__global__ void __launch_bounds__(NTHREADS, 1) k_gemm(const YbGemmParams P) {
+// WM = warp rows of the CTA: 2 -> 8 warps with 32 x 32 warp tiles (round 1: 230 registers, two warps per scheduler; ncu put ~45 % of the
+// stall samples of the DMMA stream on the fixed issue latency between tensor instructions of the SAME warp, profiles/
+// r02_ncu_gemm_rw_source_hotspots_v1.txt), 4 -> 16 warps with 16 x 32 warp tiles (<= 128 registers, four warps per scheduler to fill
+// those slots).  Option "gemm_warps16" / YB_GEMM_WARPS16 selects; sums and their order per output element are the same.
+template <int ALAY, int BLAY, bool RAGGED, int WM>
+__global__ void __launch_bounds__(128 * WM, 1) k_gemm(const YbGemmParams P) {
+    constexpr int NTHREADS = 128 * WM, MT = 8 / WM;          // m-tiles of 8 rows per warp
     const int b = blockIdx.z, g = blockIdx.y;
     if (P.mask && !P.mask[b]) return;
     Desc d;
@@ -188,9 +193,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm(const YbGemmParams P) {
         cp_async_commit();
     };
 
-    double cr[4][4][2], ci[4][4][2];
+    double cr[MT][4][2], ci[MT][4][2];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < MT; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) { cr[i][j][0] = cr[i][j][1] = ci[i][j][0] = ci[i][j][1] = 0.0; }
 
@@ -198,13 +203,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm(const YbGemmParams P) {
     for (int s = 0; s < STAGES - 1; ++s) load_stage(s, s);
 
     const int fr = lane >> 2, fk = lane & 3;
-    int rbase[4], cbase[4];
-    bool ron[4], con[4];
+    int rbase[MT], cbase[4];
+    bool ron[MT], con[4];
+#pragma unroll
+    for (int i = 0; i < MT; ++i) {
+        rbase[i] = i * (8 * WM) + wm * 8;
+        ron[i] = !RAGGED || (m0 + rbase[i] < d.M);
+    }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        rbase[i] = i * 16 + wm * 8;
         cbase[i] = i * 32 + wn * 8;
-        ron[i] = !RAGGED || (m0 + rbase[i] < d.M);
         con[i] = !RAGGED || (n0 + cbase[i] < d.N);
     }
     for (int kt = 0; kt < ktiles; ++kt) {
@@ -215,11 +223,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm(const YbGemmParams P) {
         const cplx* bs = Bs + (kt % STAGES) * B_STAGE;
 #pragma unroll
         for (int kk = 0; kk < BKT; kk += 4) {
-            double ar[4], ai[4], an[4], br[4], bi[4];
+            double ar[MT], ai[MT], an[MT], br[4], bi[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
+            for (int i = 0; i < MT; ++i) {
                 if (RAGGED && !ron[i]) { ar[i] = ai[i] = an[i] = 0.0; continue; }
-                const int row = (RAGGED ? rbase[i] : wm * 32 + i * 8) + fr, k = kk + fk;
+                const int row = (RAGGED ? rbase[i] : wm * (8 * MT) + i * 8) + fr, k = kk + fk;
                 const cplx v = (ALAY == LAY_AK) ? as[row * A_KIN_LD + k] : as[k * A_KOUT_LD + row];
                 ar[i] = v.x; ai[i] = v.y; an[i] = flip_sign(v.y);
             }
@@ -231,7 +239,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm(const YbGemmParams P) {
                 br[j] = v.x; bi[j] = d.conjB ? flip_sign(v.y) : v.y;
             }
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+            for (int i = 0; i < MT; ++i)
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     if (RAGGED && !(ron[i] && con[j])) continue;          // warp-uniform: the whole 8 x 8 sub-tile is padding
@@ -245,8 +253,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm(const YbGemmParams P) {
     cp_async_wait<0>();
 
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int row = m0 + (RAGGED ? rbase[i] : wm * 32 + i * 8) + fr;
+    for (int i = 0; i < MT; ++i) {
+        const int row = m0 + (RAGGED ? rbase[i] : wm * (8 * MT) + i * 8) + fr;
         if (row >= d.M) continue;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -260,23 +268,24 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm(const YbGemmParams P) {
 
 constexpr size_t GEMM_SMEM = (size_t)STAGES * (A_STAGE + B_STAGE) * sizeof(cplx);
 
-template <int ALAY, int BLAY, bool RAGGED>
+template <int ALAY, int BLAY, bool RAGGED, int WM>
 cudaError_t launch_r(const YbGemmParams& P, int maxM, int maxN, cudaStream_t st) {
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(k_gemm<ALAY, BLAY, RAGGED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM);
+        cudaError_t e = cudaFuncSetAttribute(k_gemm<ALAY, BLAY, RAGGED, WM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM);
         if (e != cudaSuccess) return e;
         configured = true;
     }
     const int tiles = ((maxM + BM - 1) / BM) * ((maxN + BN - 1) / BN);
     dim3 grid(tiles, P.ngroups, P.nbatch);
-    k_gemm<ALAY, BLAY, RAGGED><<<grid, NTHREADS, GEMM_SMEM, st>>>(P);
+    k_gemm<ALAY, BLAY, RAGGED, WM><<<grid, 128 * WM, GEMM_SMEM, st>>>(P);
     return cudaGetLastError();
 }
 
 template <int ALAY, int BLAY>
 cudaError_t launch_t(const YbGemmParams& P, int maxM, int maxN, cudaStream_t st) {
-    return P.ragged ? launch_r<ALAY, BLAY, true>(P, maxM, maxN, st) : launch_r<ALAY, BLAY, false>(P, maxM, maxN, st);
+    if (P.warps16) return P.ragged ? launch_r<ALAY, BLAY, true, 4>(P, maxM, maxN, st) : launch_r<ALAY, BLAY, false, 4>(P, maxM, maxN, st);
+    return P.ragged ? launch_r<ALAY, BLAY, true, 2>(P, maxM, maxN, st) : launch_r<ALAY, BLAY, false, 2>(P, maxM, maxN, st);
 }
 
 #include "yb_gemm_rw.cuh"
@@ -286,13 +295,14 @@ cudaError_t launch_t(const YbGemmParams& P, int maxM, int maxN, cudaStream_t st)
 // RCONTRACT with the MPO tensor applied in the epilogue (yb_gemm_rw.cuh): 64 x 96 CTA tiles for right MPO bonds 3 and 6, else 64 x 128.
 cudaError_t yb_launch_gemm_rw(int nbatch, const int* mask, const int* el, int esl, const int* er, int esr, int dphys, int Dl, int Dr, const cplx* X,
                               long long sX, const cplx* R, long long sR, const cplx* W, cplx* Out, long long sOut, int max_l, int max_r,
-                              unsigned long long* flops, int bk16, cudaStream_t st) {
+                              unsigned long long* flops, int bk16, int warps16, cudaStream_t st) {
     if (nbatch <= 0 || max_l <= 0 || max_r <= 0) return cudaSuccess;
     rw::Params P;
     P.nbatch = nbatch; P.mask = mask; P.el = el; P.er = er; P.esl = esl; P.esr = esr; P.dphys = dphys; P.Dl = Dl; P.Dr = Dr;
     P.X = X; P.R = R; P.W = W; P.Out = Out; P.sX = sX; P.sR = sR; P.sOut = sOut; P.flops = flops;
     (void)bk16;                                           // 16-deep k tiles measured no faster (profiles/r02_matvec_microbench_v1.json)
-    return (Dr == 3 || Dr == 6) ? rw::launch<8, 4, 3>(P, max_l, max_r, st) : rw::launch<8, 4, 4>(P, max_l, max_r, st);
+    if (warps16) return (Dr == 3 || Dr == 6) ? rw::launch<8, 4, 3, 4>(P, max_l, max_r, st) : rw::launch<8, 4, 4, 4>(P, max_l, max_r, st);
+    return (Dr == 3 || Dr == 6) ? rw::launch<8, 4, 3, 2>(P, max_l, max_r, st) : rw::launch<8, 4, 4, 2>(P, max_l, max_r, st);
 }
 
 // maxM / maxN: upper bounds of the per-trajectory M and N (grid is sized for them; empty tiles exit).

@@ -15,7 +15,7 @@
 
 namespace rw {
 
-constexpr int BM = 64, NTHREADS = 256;
+constexpr int BM = 64;
 constexpr int W_MAX = 4 * 4 * 8 * 8;             // MPO tensor entries held in shared memory (d~ <= 4, bonds <= 8)
 constexpr int W2_MAX = 32 * 33;                  // the same tensor as a zero-padded (d~ Dl) x (d~ Dr) matrix, pitch Kp + 1
 
@@ -44,10 +44,11 @@ struct Params {
     unsigned long long* flops;
 };
 
-template <int BKT, int STAGES, int NT>
-__global__ void __launch_bounds__(NTHREADS, 1) k_gemm_rw(const Params P) {
+template <int BKT, int STAGES, int NT, int WM>
+__global__ void __launch_bounds__(128 * WM, 1) k_gemm_rw(const Params P) {
     using C = Cfg<BKT, STAGES, NT>;
     constexpr int BN = C::BN, T_LD = C::T_LD;
+    constexpr int NTHREADS = 128 * WM, MT = 8 / WM;          // WM warp rows x 4 warp columns; warp tile (8 MT) x (8 NT), see k_gemm
     const int b = blockIdx.z;
     if (P.mask && !P.mask[b]) return;
     const int chil = P.el[(long long)b * P.esl], chir = P.er[(long long)b * P.esr];
@@ -76,14 +77,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_rw(const Params P) {
     for (int e = tid; e < nw; e += NTHREADS) Ws[e] = P.W[e];
 
     // per-thread gather offsets of the loads (fixed over the k loop)
-    constexpr int AQ = (BM * BKT) / NTHREADS, BQ = (BN * BKT) / NTHREADS;
+    constexpr int AQ = (BM * BKT + NTHREADS - 1) / NTHREADS, BQ = (BN * BKT + NTHREADS - 1) / NTHREADS;
     long long a_off[AQ]; int a_k[AQ], a_dst[AQ]; bool a_ok[AQ];
 #pragma unroll
     for (int q = 0; q < AQ; ++q) {
         const int e = tid + q * NTHREADS;
-        const int k = e % BKT, m = e / BKT;
+        const int k = e % BKT, m = (e / BKT) % BM;
         const int u = m / TL, li = m - u * TL;
-        a_ok[q] = li < nl;
+        a_ok[q] = li < nl && e < BM * BKT;
         a_off[q] = ((long long)u * chil + l0 + li) * chir;
         a_k[q] = k;
         a_dst[q] = m * C::A_LD + k;
@@ -92,9 +93,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_rw(const Params P) {
 #pragma unroll
     for (int q = 0; q < BQ; ++q) {
         const int e = tid + q * NTHREADS;
-        const int n = e % BN, k = e / BN;
+        const int n = e % BN, k = (e / BN) % BKT;
         const int v = n / TR, ri = n - v * TR;
-        b_ok[q] = v < Dr && ri < nr;
+        const bool in_tile = e < BN * BKT;
+        b_ok[q] = v < Dr && ri < nr && in_tile;
         b_off[q] = (long long)v * chir + r0 + ri;
         b_k[q] = k;
         b_dst[q] = k * C::B_LD + n;
@@ -108,11 +110,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_rw(const Params P) {
             cplx* bs = Bs + stage * C::B_STAGE;
 #pragma unroll
             for (int q = 0; q < AQ; ++q) {
+                if (tid + q * NTHREADS >= BM * BKT) continue;           // (only when the tile does not divide among the threads)
                 const bool ok = a_ok[q] && (k0 + a_k[q] < K);
                 cp_async16(as + a_dst[q], ok ? (Xb + a_off[q] + k0 + a_k[q]) : Xb, ok);
             }
 #pragma unroll
             for (int q = 0; q < BQ; ++q) {
+                if (tid + q * NTHREADS >= BN * BKT) continue;
                 const bool ok = b_ok[q] && (k0 + b_k[q] < K);
                 cp_async16(bs + b_dst[q], ok ? (Rb + (long long)(k0 + b_k[q]) * r_rs + b_off[q]) : Rb, ok);
             }
@@ -120,9 +124,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_rw(const Params P) {
         cp_async_commit();
     };
 
-    double cr[4][NT][2], ci[4][NT][2];
+    double cr[MT][NT][2], ci[MT][NT][2];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < MT; ++i)
 #pragma unroll
         for (int j = 0; j < NT; ++j) { cr[i][j][0] = cr[i][j][1] = ci[i][j][0] = ci[i][j][1] = 0.0; }
 
@@ -138,10 +142,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_rw(const Params P) {
         const cplx* bs = Bs + (kt % STAGES) * C::B_STAGE;
 #pragma unroll
         for (int kk = 0; kk < BKT; kk += 4) {
-            double ar[4], ai[4], an[4], br[NT], bi[NT];
+            double ar[MT], ai[MT], an[MT], br[NT], bi[NT];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const cplx v = as[(wm * 32 + i * 8 + fr) * C::A_LD + kk + fk];
+            for (int i = 0; i < MT; ++i) {
+                const cplx v = as[(wm * (8 * MT) + i * 8 + fr) * C::A_LD + kk + fk];
                 ar[i] = v.x; ai[i] = v.y; an[i] = flip_sign(v.y);
             }
 #pragma unroll
@@ -150,7 +154,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_rw(const Params P) {
                 br[j] = v.x; bi[j] = v.y;
             }
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+            for (int i = 0; i < MT; ++i)
 #pragma unroll
                 for (int j = 0; j < NT; ++j) {
                     dmma(cr[i][j][0], cr[i][j][1], ar[i], br[j]);
@@ -171,8 +175,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_rw(const Params P) {
     // d~ Dr x TL TR complex multiply-adds per CTA, ~10 % of the main loop at C3 sizes, instead of a second kernel and an HBM round trip.
     cplx* Ts = reinterpret_cast<cplx*>(smem_raw);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int row = wm * 32 + i * 8 + fr;
+    for (int i = 0; i < MT; ++i) {
+        const int row = wm * (8 * MT) + i * 8 + fr;
 #pragma unroll
         for (int j = 0; j < NT; ++j) {
             const int col = wn * (8 * NT) + j * 8 + 2 * fk;
@@ -231,19 +235,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_rw(const Params P) {
     }
 }
 
-template <int BKT, int STAGES, int NT>
+template <int BKT, int STAGES, int NT, int WM>
 cudaError_t launch(const Params& P, int max_l, int max_r, cudaStream_t st) {
     using C = Cfg<BKT, STAGES, NT>;
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(k_gemm_rw<BKT, STAGES, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+        cudaError_t e = cudaFuncSetAttribute(k_gemm_rw<BKT, STAGES, NT, WM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
         if (e != cudaSuccess) return e;
         configured = true;
     }
     const int TL = BM / P.dphys, TR = (C::BN / P.Dr) & ~7;
     const int tiles = ((max_l + TL - 1) / TL) * ((max_r + TR - 1) / TR);
     dim3 grid(tiles, 1, P.nbatch);
-    k_gemm_rw<BKT, STAGES, NT><<<grid, NTHREADS, C::SMEM, st>>>(P);
+    k_gemm_rw<BKT, STAGES, NT, WM><<<grid, 128 * WM, C::SMEM, st>>>(P);
     return cudaGetLastError();
 }
 
