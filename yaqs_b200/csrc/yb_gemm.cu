@@ -238,6 +238,9 @@ __global__ void __launch_bounds__(128 * WM, 1) k_gemm(const YbGemmParams P) {
                 const cplx v = (BLAY == LAY_BN) ? bs[k * B_KOUT_LD + n] : bs[n * B_KIN_LD + k];
                 br[j] = v.x; bi[j] = d.conjB ? flip_sign(v.y) : v.y;
             }
+            // two passes: the second DMMA on an accumulator is issued a whole tile sweep after the first (the asm statements are
+            // volatile, so source order is issue order; back to back, the dependent pair stalled on the tensor pipe's latency --
+            // "wait" was 44 % of the stall samples on this line, profiles/r02_ncu_gemm_rw_source_hotspots_v1.txt)
 #pragma unroll
             for (int i = 0; i < MT; ++i)
 #pragma unroll
@@ -245,6 +248,12 @@ __global__ void __launch_bounds__(128 * WM, 1) k_gemm(const YbGemmParams P) {
                     if (RAGGED && !(ron[i] && con[j])) continue;          // warp-uniform: the whole 8 x 8 sub-tile is padding
                     dmma(cr[i][j][0], cr[i][j][1], ar[i], br[j]);
                     dmma(ci[i][j][0], ci[i][j][1], ar[i], bi[j]);
+                }
+#pragma unroll
+            for (int i = 0; i < MT; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (RAGGED && !(ron[i] && con[j])) continue;
                     dmma(cr[i][j][0], cr[i][j][1], an[i], bi[j]);
                     dmma(ci[i][j][0], ci[i][j][1], ai[i], br[j]);
                 }

@@ -154,11 +154,16 @@ __global__ void __launch_bounds__(128 * WM, 1) k_gemm_rw(const Params P) {
                 br[j] = v.x; bi[j] = v.y;
             }
 #pragma unroll
-            for (int i = 0; i < MT; ++i)
+            for (int i = 0; i < MT; ++i)                      // two passes: dependent DMMAs a tile sweep apart (see k_gemm)
 #pragma unroll
                 for (int j = 0; j < NT; ++j) {
                     dmma(cr[i][j][0], cr[i][j][1], ar[i], br[j]);
                     dmma(ci[i][j][0], ci[i][j][1], ar[i], bi[j]);
+                }
+#pragma unroll
+            for (int i = 0; i < MT; ++i)
+#pragma unroll
+                for (int j = 0; j < NT; ++j) {
                     dmma(cr[i][j][0], cr[i][j][1], an[i], bi[j]);
                     dmma(ci[i][j][0], ci[i][j][1], ai[i], br[j]);
                 }
