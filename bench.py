@@ -296,7 +296,7 @@ def run_reference_arm(args):
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": cpu_sample_text(wl, cores),
                              "pool_wall_s": mean_walls, "full_chain_half_step_s": t_full},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -501,7 +501,7 @@ def run_b200_arm(args):
         line["traceback"] = traceback.format_exc()[-1500:]
     line["bench_wall_s"] = time.perf_counter() - t_start
     if rank == 0:
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         try:
             dist.destroy_process_group()
@@ -510,8 +510,31 @@ def run_b200_arm(args):
     return 0 if "error" not in line else 1
 
 
+_REAL_STDOUT = None
+
+
+def _claim_stdout() -> None:
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner on the first collective),
+    so file descriptor 1 is pointed at stderr for the whole run and the line goes to the saved descriptor."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
     args = parse_args()
+    _claim_stdout()
     if args.impl == "reference":
         return run_reference_arm(args)
     return run_b200_arm(args)

@@ -477,11 +477,25 @@ __global__ void __launch_bounds__(stedc::THREADS, 2) k_stedc(double* dio, const 
     double* q = stedc::solve<KM>(S, dio + (long long)b * s_vec, ein + (long long)b * s_vec, k, QA, QB, blockDim.x, &fail);
     const int tid = threadIdx.x, nthr = blockDim.x;
     const long long kk = (long long)k * k;
+    // (four independent loads in flight per thread: these two passes were 8 % of the kernel on one dependent load each)
     if (q != QA) {
-        for (long long x = tid; x < kk; x += nthr) QA[x] = QB[x];
+        long long x = tid;
+        for (; x + 3LL * nthr < kk; x += 4LL * nthr) {
+            const double a0 = QB[x], a1 = QB[x + nthr], a2 = QB[x + 2LL * nthr], a3 = QB[x + 3LL * nthr];
+            QA[x] = a0; QA[x + nthr] = a1; QA[x + 2LL * nthr] = a2; QA[x + 3LL * nthr] = a3;
+        }
+        for (; x < kk; x += nthr) QA[x] = QB[x];
         __syncthreads();
     }
-    for (long long x = tid; x < kk; x += nthr) zt[x] = make_double2(QA[x], 0.0);
+    {
+        long long x = tid;
+        for (; x + 3LL * nthr < kk; x += 4LL * nthr) {
+            const double a0 = QA[x], a1 = QA[x + nthr], a2 = QA[x + 2LL * nthr], a3 = QA[x + 3LL * nthr];
+            zt[x] = make_double2(a0, 0.0); zt[x + nthr] = make_double2(a1, 0.0);
+            zt[x + 2LL * nthr] = make_double2(a2, 0.0); zt[x + 3LL * nthr] = make_double2(a3, 0.0);
+        }
+        for (; x < kk; x += nthr) zt[x] = make_double2(QA[x], 0.0);
+    }
     if (tid == 0) {
         if (meta) meta[b * 8 + 5] = fail ? 0 : 1;
         if (fail && status) atomicOr(&status[b], 1);

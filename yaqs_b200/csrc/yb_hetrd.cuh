@@ -258,25 +258,28 @@ __global__ void __launch_bounds__(THREADS, 1) k_ormtr_rows(const cplx* __restric
                 const cplx* v = Vp + (size_t)q * LD + lane;
                 const int tq = (jlo + q + 1) >> 5;
                 cplx vv[PAIR ? NE : 1];                      // the reflector stays in registers between dot and axpy when it fits
-                double sar = 0.0, sai = 0.0, sbr = 0.0, sbi = 0.0;
+                // two partial sums per dot product (even / odd chunks): half the length of the dependent FMA chain in front of the
+                // warp reduction (the chain, not the FP64 pipe, bounded this kernel: 42 % pipe utilisation in profiles/r02_ncu_target_v1.json)
+                double sar[2] = {0.0, 0.0}, sai[2] = {0.0, 0.0}, sbr[2] = {0.0, 0.0}, sbi[2] = {0.0, 0.0};
 #pragma unroll
                 for (int t = 0; t < NE; ++t) {
                     if (t < tq) continue;
                     const cplx x = v[32 * t];
                     if constexpr (PAIR) vv[t] = x;
-                    sar += ra[t].x * x.x - ra[t].y * x.y;
-                    sai += ra[t].x * x.y + ra[t].y * x.x;
+                    sar[t & 1] += ra[t].x * x.x - ra[t].y * x.y;
+                    sai[t & 1] += ra[t].x * x.y + ra[t].y * x.x;
                     if constexpr (PAIR) {
-                        sbr += rb[t].x * x.x - rb[t].y * x.y;
-                        sbi += rb[t].x * x.y + rb[t].y * x.x;
+                        sbr[t & 1] += rb[t].x * x.x - rb[t].y * x.y;
+                        sbi[t & 1] += rb[t].x * x.y + rb[t].y * x.x;
                     }
                 }
+                sar[0] += sar[1]; sai[0] += sai[1]; sbr[0] += sbr[1]; sbi[0] += sbi[1];
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) {
-                    sar += __shfl_xor_sync(0xffffffffu, sar, o); sai += __shfl_xor_sync(0xffffffffu, sai, o);
-                    if constexpr (PAIR) { sbr += __shfl_xor_sync(0xffffffffu, sbr, o); sbi += __shfl_xor_sync(0xffffffffu, sbi, o); }
+                    sar[0] += __shfl_xor_sync(0xffffffffu, sar[0], o); sai[0] += __shfl_xor_sync(0xffffffffu, sai[0], o);
+                    if constexpr (PAIR) { sbr[0] += __shfl_xor_sync(0xffffffffu, sbr[0], o); sbi[0] += __shfl_xor_sync(0xffffffffu, sbi[0], o); }
                 }
-                const cplx fa = cmul(taus[q], make_double2(sar, sai)), fb = cmul(taus[q], make_double2(sbr, sbi));   // conj(tau) (row . v)
+                const cplx fa = cmul(taus[q], make_double2(sar[0], sai[0])), fb = cmul(taus[q], make_double2(sbr[0], sbi[0]));   // conj(tau) (row . v)
 #pragma unroll
                 for (int t = 0; t < NE; ++t) {
                     if (t < tq) continue;

@@ -389,12 +389,20 @@ YB_DC_FN double* solve(Smem<KM>& S, double* d_io, const double* e_in, int k, dou
             YB_THREADS_BEGIN
             for (int j = tid; j < K; j += nthr) {
                 const double dj = S.dk[j];
-                double p = -((dj - S.dk[S.org[j]]) - S.mu[j]) / rho;
-                for (int i = 0; i < K; ++i) {
-                    if (i == j) continue;
-                    const double del = (dj - S.dk[S.org[i]]) - S.mu[i];          // d_j - lam_i
-                    p *= -del / (S.dk[i] - dj);
+                // four interleaved partial products: the quotients are independent, only the running product is a dependent chain, and
+                // an FP64 division is ~200 cycles of latency -- one chain of K of them kept the whole CTA at the barrier below for 18 %
+                // of the kernel (profiles/r02_ncu_stedc_source_hotspots_v1.txt)
+                double pp[4] = {-((dj - S.dk[S.org[j]]) - S.mu[j]) / rho, 1.0, 1.0, 1.0};
+                for (int i0 = 0; i0 < K; i0 += 4) {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int i = i0 + u;
+                        if (i >= K || i == j) continue;
+                        const double del = (dj - S.dk[S.org[i]]) - S.mu[i];      // d_j - lam_i
+                        pp[u] *= -del / (S.dk[i] - dj);
+                    }
                 }
+                const double p = (pp[0] * pp[1]) * (pp[2] * pp[3]);
                 S.zh[j] = copysign(sqrt(fabs(p)), S.zk[j]);
             }
             YB_THREADS_END
@@ -402,12 +410,17 @@ YB_DC_FN double* solve(Smem<KM>& S, double* d_io, const double* e_in, int k, dou
             YB_THREADS_BEGIN
             for (int i = tid; i < K; i += nthr) {
                 const double dorg = S.dk[S.org[i]], m = S.mu[i];
-                double s2 = 0.0;
-                for (int j = 0; j < K; ++j) {
-                    const double v = S.zh[j] / ((S.dk[j] - dorg) - m);
-                    s2 += v * v;
+                double s4[4] = {0.0, 0.0, 0.0, 0.0};
+                for (int j0 = 0; j0 < K; j0 += 4) {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int j = j0 + u;
+                        if (j >= K) continue;
+                        const double v = S.zh[j] / ((S.dk[j] - dorg) - m);
+                        s4[u] += v * v;
+                    }
                 }
-                S.vn[i] = 1.0 / sqrt(s2);
+                S.vn[i] = 1.0 / sqrt((s4[0] + s4[1]) + (s4[2] + s4[3]));
             }
             YB_THREADS_END
             // ---- Qd[a + i][a + cc] = sum_j V[i][j] Qs[a + krow[j]][a + cc],  V[i][j] = vn_i zhat_j / (d_j - lam_i) ----
