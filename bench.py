@@ -93,8 +93,10 @@ def saturated_tensors(length: int, chi: int, seed: int = 1234):
     """Seeded random MPS with bonds min(chi, 2**k); normalised by MPS(tensors=...) / the oracle's normalize."""
     rng = np.random.default_rng(seed)
     bonds = [1] + [min(chi, 2 ** min(i + 1, length - 1 - i)) for i in range(length - 1)] + [1]
-    return [(rng.standard_normal((2, bonds[i], bonds[i + 1])) + 1j * rng.standard_normal((2, bonds[i], bonds[i + 1]))).astype(np.complex128)
-            for i in range(length)]
+    # every tensor is scaled to a transfer-matrix norm of order one: the state is normalised afterwards anyway, but the raw norm of a
+    # product of 200 unscaled 2 x 256 x 256 Gaussian tensors (~1e271, squared in the norm) overflows a double (config 5)
+    return [((rng.standard_normal((2, bonds[i], bonds[i + 1])) + 1j * rng.standard_normal((2, bonds[i], bonds[i + 1]))) / np.sqrt(4.0 * bonds[i]))
+            .astype(np.complex128) for i in range(length)]
 
 
 def noise_processes(wl: dict) -> list[dict]:

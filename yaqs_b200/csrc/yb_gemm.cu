@@ -275,6 +275,37 @@ __global__ void __launch_bounds__(128 * WM, 1) k_gemm(const YbGemmParams P) {
     }
 }
 
+// Small products (every M and N of the launch <= 64: chi <= 16 chains -- BASELINE configs 1 and 4 -- and the chain-end sites of the
+// large ones): the 64 x 128 DMMA tile would be mostly padding and its pipeline prologue / epilogue a fixed ~5 us per CTA, i.e. ~300 us
+// per launch for 2048 trajectories (profiles/r02_bench_C1_v1.json: 0.75 s per step at L = 10, chi = 16).  Here a thread owns one output
+// element and walks K with FP64 FMAs; a warp's loads of A are broadcasts (same row), of B coalesced (consecutive columns), both served
+// by L1 (the operands of a trajectory are a few KB).  Same descriptors, same sums per element in the same k order.
+template <int DUMMY>
+__global__ void __launch_bounds__(128) k_gemm_small(const YbGemmParams P) {
+    const int b = blockIdx.z, g = blockIdx.y;
+    if (P.mask && !P.mask[b]) return;
+    Desc d;
+    if (!make_desc(P, b, g, d)) return;
+    const int total = d.M * d.N;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (P.flops && threadIdx.x == 0 && blockIdx.x == 0) atomicAdd(P.flops, 8ull * (unsigned long long)total * (unsigned long long)d.K * d.nseg);
+    if (idx >= total) return;
+    const int m = idx / d.N, n = idx - m * d.N;
+    double cr = 0.0, ci = 0.0;
+    for (int seg = 0; seg < d.nseg; ++seg) {
+        const cplx* a = d.A + seg * d.a_ss + (long long)m * d.a_rs;
+        const cplx* bp = d.B + seg * d.b_ss + (long long)n * d.b_cs;
+        for (int k = 0; k < d.K; ++k) {
+            const cplx x = a[(long long)k * d.a_cs];
+            cplx y = bp[(long long)k * d.b_rs];
+            if (d.conjB) y.y = -y.y;
+            cr = fma(x.x, y.x, cr); cr = fma(-x.y, y.y, cr);
+            ci = fma(x.x, y.y, ci); ci = fma(x.y, y.x, ci);
+        }
+    }
+    d.C[(long long)m * d.c_rs + n] = make_double2(cr, ci);
+}
+
 constexpr size_t GEMM_SMEM = (size_t)STAGES * (A_STAGE + B_STAGE) * sizeof(cplx);
 
 template <int ALAY, int BLAY, bool RAGGED, int WM>
@@ -317,6 +348,11 @@ cudaError_t yb_launch_gemm_rw(int nbatch, const int* mask, const int* el, int es
 // maxM / maxN: upper bounds of the per-trajectory M and N (grid is sized for them; empty tiles exit).
 cudaError_t yb_launch_gemm(const YbGemmParams& P, int maxM, int maxN, cudaStream_t st) {
     if (P.nbatch <= 0 || maxM <= 0 || maxN <= 0) return cudaSuccess;
+    if (maxM <= 64 && maxN <= 64 && !P.no_small) {
+        dim3 grid((maxM * maxN + 127) / 128, P.ngroups, P.nbatch);
+        k_gemm_small<0><<<grid, 128, 0, st>>>(P);
+        return cudaGetLastError();
+    }
     switch (P.op) {
     case YB_OP_LCONTRACT:
     case YB_OP_ENVL3: return launch_t<LAY_AM, LAY_BN>(P, maxM, maxN, st);

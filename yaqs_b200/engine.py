@@ -386,7 +386,7 @@ class BatchedTJM:
         cl, cr = lay.cap[i], lay.cap[i + nsites]
         w = self.W1[i] if nsites == 1 else self.W2[i]
         t1, t2 = self._buf(self.T1, lay.t_slot), self._buf(self.T2, lay.t_slot)
-        if self.fused_mpo and Dl <= 8 and Dr <= 8:
+        if self.fused_mpo and Dl <= 8 and Dr <= 8 and (dphys * cl > 64 or Dr * cr > 64):      # small products: thread-per-element kernels instead
             K.rcontract_mpo(B, mask, el, er, dphys, Dl, Dr, x, self.env(i + nsites, False), w, t2, cl, cr)
         else:
             K.gemm(OP_RCONTRACT, B, 1, mask, el, er, None, dphys, Dl, Dr, x, self.env(i + nsites, False), t1, 0, dphys * cl, Dr * cr)
@@ -418,7 +418,7 @@ class BatchedTJM:
         cl, cr = lay.cap[s], lay.cap[s + 1]
         a = st.site(s)
         t1, t2 = self._buf(self.T1, lay.t_slot), self._buf(self.T2, lay.t_slot)
-        if self.fused_mpo and Dl <= 8 and Dr <= 8:
+        if self.fused_mpo and Dl <= 8 and Dr <= 8 and (d * cl > 64 or Dr * cr > 64):
             K.rcontract_mpo(B, None, el, er, d, Dl, Dr, a, self.env(s + 1, False), self.W1[s], t2, cl, cr)
         else:
             K.gemm(OP_RCONTRACT, B, 1, None, el, er, None, d, Dl, Dr, a, self.env(s + 1, False), t1, 0, d * cl, Dr * cr)
