@@ -351,6 +351,7 @@ def run_b200_arm(args):
         fam_ms: dict = {}
         fam_n: dict = {}
         gemm_flops = 0
+        detail: dict = {}
         sweep_events: list = []
         orig_tdvp = {}
 
@@ -383,6 +384,10 @@ def run_b200_arm(args):
                     for e in engs:
                         e.tdvp = orig_tdvp.pop(id(e))
                     gemm_flops += timing.pop("gemm_flops")
+                    for key, v in timing.pop("detail", {}).items():
+                        cur = detail.setdefault(key, [0, 0.0])
+                        cur[0] += v["launches"]
+                        cur[1] += v["ms"]
                     for fam, v in timing.items():
                         fam_ms[fam] = fam_ms.get(fam, 0.0) + v["ms"]
                         fam_n[fam] = fam_n.get(fam, 0) + v["launches"]
@@ -470,6 +475,9 @@ def run_b200_arm(args):
                                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": src,
                                     "algorithmic_bytes_per_trajectory_step": by,
                                     "note": "at chi <= 16 the step is launch/latency-bound, not bandwidth-bound: the fraction is reported as measured"}
+            if detail:                                        # where the instrumented step goes: (family, size key, phase), largest first
+                rows = sorted(detail.items(), key=lambda kv: -kv[1][1])
+                line["kernel_breakdown"] = [{"family": k[0], "key": k[1], "phase": k[2], "launches": v[0], "ms": round(v[1], 2)} for k, v in rows[:40]]
             if sweep_events:
                 sw = [a.elapsed_time(b) for a, b in sweep_events]
                 line["tdvp_sweep_ms"] = {"per_batch": float(np.mean(sw)), "batch": engs[0].B, "per_trajectory": float(np.mean(sw)) / engs[0].B, "sweeps_timed": len(sw)}

@@ -164,6 +164,26 @@ int yb_svd_check(int nbatch, const int32_t* mask, int32_t* meta, int32_t* rot_co
  * host-side comparison the reference never needs because LAPACK's zgesdd is backward stable (core/linalg/svd.py:89-104). */
 int yb_svd_ambiguous(int nbatch, const int32_t* mask, const int32_t* meta, const double* sval, int64_t stride_s, int trunc_mode, double threshold,
                      int two_level, double tau_rel, double noise_rel, const int32_t* status, int32_t* amb, int32_t* n_amb, void* stream);
+/* ---- truncation-free gauge shifts by Cholesky-QR (csrc/yb_cholqr.cuh) -----------------------------------------------------------
+ * Replaces scipy.linalg.svd + truncate at core/data_structures/mps.py:747-764 (SVD gauge shifts with the hard-coded 1e-12 discarded
+ * weight; the QR moves of :736-746) for the trajectories that provably keep EVERY singular value: truncate() (core/linalg/svd_utils.py:
+ * 60-75) keeps all of them iff sigma_min^2 >= threshold, and then any orthonormal basis times the complementary factor is the same MPS
+ * up to a unitary on the bond.  Sequence: yb_svd_prepare (orientation forced so that the bond side indexes the rows of w) ->
+ * yb_gemm(GRAM: g = w w^H) -> yb_cholqr_factor -> yb_gemm(ROTATE: y1 = linv w) -> yb_gemm(GRAM: g2 = y1 y1^H) -> yb_cholqr_refine ->
+ * yb_gemm(ROTATE: y2 = x y1) -> yb_gemm(GRAM: l2 = w y2^H) -> yb_cholqr_finalize.
+ * yb_cholqr_factor: g = L L^H (packed lower triangle in shared memory, max_k <= 128), linv = L^-1 (k x k row-major, zeros above the
+ * diagonal) and the certificate lambda_min(g) >= 1 / ||L^-1||_F^2: flag[b] = 0 iff that bound, less 64 k eps trace(g), is positive and
+ * >= 4 * threshold; flag[b] = 1 otherwise (non-positive pivot, k > len, non-finite input, bound too small) -- the caller
+ * redoes flagged trajectories with the eigen-solver route.  n_flag (one int, zeroed by the caller) counts them.
+ * yb_cholqr_refine: x = (3 I - g2) / 2 (one Newton-Schulz step towards g2^-1/2); flags trajectories with ||g2 - I||_F > tol.
+ * yb_cholqr_finalize: for unflagged trajectories keep = k and (uout, vout) in the layout of yb_svd_finalize: orient 1 (w = M^H):
+ * U = y2^H, "S Vh" = l2^H; orient 0 (w = M): "U S" = l2, Vh = y2. */
+int yb_cholqr_factor(int nbatch, const int32_t* mask, const int32_t* meta, const void* g, int64_t stride_g, void* linv, int64_t stride_l,
+                     double threshold, int32_t* flag, int32_t* n_flag, int max_k, void* stream);
+int yb_cholqr_refine(int nbatch, const int32_t* mask, const int32_t* meta, const void* g2, int64_t stride_g, void* x, int64_t stride_x, double tol,
+                     int32_t* flag, int32_t* n_flag, void* stream);
+int yb_cholqr_finalize(int nbatch, const int32_t* mask, int32_t* meta, const void* y2, int64_t stride_y, const void* l2, int64_t stride_l, int32_t* keep,
+                       int32_t keep_stride, void* uout, int64_t stride_u, void* vout, int64_t stride_v, const int32_t* flag, int max_elems, void* stream);
 int yb_svd_finalize(int nbatch, const int32_t* mask, int32_t* meta, int trunc_mode, double threshold, int max_bond, int min_keep,
                     int dist, const void* w, int64_t stride_w, const void* q, int64_t stride_q, double* sval, int64_t stride_s,
                     int32_t* keep, int32_t keep_stride, void* uout, int64_t stride_u, void* vout, int64_t stride_v, int32_t* status,

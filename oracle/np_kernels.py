@@ -400,6 +400,72 @@ class NumpyKernels:
             if mt is not None:
                 mt[t, 5] = 1
 
+    # -- truncation-free gauge shifts by Cholesky-QR (twin of csrc/yb_cholqr.cuh: same certificate, same outputs) ---------
+    def cholqr_factor(self, nbatch, mask, meta, g, linv, threshold, flag, n_flag, max_k):
+        self._launches += 1
+        mt = _np(meta).reshape(-1, SVD_META)
+        for t in range(nbatch):
+            if not _on(mask, t):
+                _np(flag)[t] = 0
+                continue
+            k, ln = int(mt[t, 0]), int(mt[t, 1])
+            ok = 1 <= k <= min(ln, max_k)
+            if ok:
+                G = _view(g, t, k * k).reshape(k, k)
+                H = np.tril(G) + np.tril(G, -1).conj().T                  # the kernel reads the lower triangle only
+                H[np.diag_indices(k)] = G.diagonal().real
+                trace = float(H.diagonal().real.sum())
+                try:
+                    with np.errstate(all="ignore"):
+                        L = np.linalg.cholesky(H)
+                        Li = scipy.linalg.solve_triangular(L, np.eye(k, dtype=np.complex128), lower=True, check_finite=False)
+                    fn = float((np.abs(Li) ** 2).sum())
+                    lb = 1.0 / fn - 64.0 * k * 2.220446049250313e-16 * trace
+                    ok = bool(np.isfinite(fn) and np.isfinite(trace) and trace > 0.0 and lb >= 4.0 * threshold and lb > 0.0)
+                    if ok:
+                        _view(linv, t, k * k)[:] = np.ascontiguousarray(Li).reshape(-1)
+                except np.linalg.LinAlgError:
+                    ok = False
+            _np(flag)[t] = 0 if ok else 1
+            if not ok:
+                _np(n_flag)[0] += 1
+
+    def cholqr_refine(self, nbatch, mask, meta, g2, x, tol, flag, n_flag):
+        self._launches += 1
+        mt = _np(meta).reshape(-1, SVD_META)
+        for t in range(nbatch):
+            if not _on(mask, t) or _np(flag)[t]:
+                continue
+            k = int(mt[t, 0])
+            G2 = _view(g2, t, k * k).reshape(k, k)
+            with np.errstate(all="ignore"):
+                e2 = float((np.abs(G2 - np.eye(k)) ** 2).sum())
+            _view(x, t, k * k)[:] = (1.5 * np.eye(k) - 0.5 * G2).reshape(-1)
+            if not e2 <= tol * tol:
+                _np(flag)[t] = 1
+                _np(n_flag)[0] += 1
+
+    def cholqr_finalize(self, nbatch, mask, meta, y2, l2, keep, uout, vout, flag, max_elems):
+        self._launches += 1
+        mt = _np(meta).reshape(-1, SVD_META)
+        for t in range(nbatch):
+            if not _on(mask, t):
+                continue
+            mt[t, 7] = 0
+            if _np(flag)[t]:
+                continue
+            k, ln, orient = int(mt[t, 0]), int(mt[t, 1]), int(mt[t, 2])
+            mt[t, 5] = 1
+            Y2 = _view(y2, t, k * ln).reshape(k, ln)
+            L2 = _view(l2, t, k * k).reshape(k, k)
+            _np(keep.tensor)[keep.offset + t * keep.stride] = k
+            if orient:
+                _view(uout, t, ln * k)[:] = np.ascontiguousarray(Y2.conj().T).reshape(-1)
+                _view(vout, t, k * k)[:] = np.ascontiguousarray(L2.conj().T).reshape(-1)
+            else:
+                _view(uout, t, k * k)[:] = np.ascontiguousarray(L2).reshape(-1)
+                _view(vout, t, k * ln)[:] = np.ascontiguousarray(Y2).reshape(-1)
+
     # -- site-tensor utilities ----------------------------------------------------------------------------------------
     def unpack_vh(self, nbatch, mask, ek, er, dphys, src, dst, max_elems):
         self._launches += 1

@@ -20,6 +20,19 @@ def test_engine_with_twin_matches_reference(golden_dir, name):
     check_against_golden(name, golden_dir, results, diag, log, traj)
 
 
+@pytest.mark.parametrize("name", ["ising10_c1_order2", "heis8_c2_order2", "ising8_strong_order2", "ising10_c1_order1", "heis6_1site_order1"])
+def test_engine_with_twin_gram_and_cholqr_routes(golden_dir, name):
+    """The Gram / eigen-solver SVD route and the Cholesky-QR route of the keep-all gauge shifts (csrc/yb_cholqr.cuh), forced onto the
+    small fixtures (production takes them from 2 chi >= 33): same jumps, identical bonds, observables <= 1e-10; the shifts of
+    rank-deficient bonds (product states, bonds right after a lowering jump) must come back through the fallback."""
+    eng, tu, su, traj = engine_for_case(name, NumpyKernels(), gram_min_k=0)
+    log = []
+    results, diag = eng.run(tu, su, log)
+    assert eng.stats["cholqr_calls"] > 0 and eng.stats["gram_svd_calls"] > 0
+    assert 0 < eng.stats["cholqr_fallbacks"] < eng.stats["cholqr_calls"] * eng.B
+    check_against_golden(name, golden_dir, results, diag, log, traj)
+
+
 from oracle.golden_cases import DIGITAL_CASES  # noqa: E402
 from tests.helpers import digital_engine_for_case  # noqa: E402
 

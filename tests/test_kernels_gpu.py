@@ -677,3 +677,101 @@ def test_workspace_bytes_covers_the_engine_allocations(backends):
     used = torch.cuda.memory_allocated() - before
     want = workspace_bytes(L, B, eng.lay.cap, eng.lay.D, 2, False)["total"]
     assert used <= 1.02 * want + (1 << 20) and want <= 1.02 * used + (1 << 20), (used, want)
+
+
+def _cholqr_chain(kern, dev, mode, dist, dphys, ext_np, src_np, slot, thr, sd, mask_np=None):
+    """prepare -> GRAM -> factor -> ROTATE -> GRAM -> refine -> ROTATE -> GRAM -> finalize on one backend (the engine's _svd_cholqr)."""
+    nb = ext_np.shape[0]
+    ext = torch.from_numpy(ext_np.copy()).to(dev)
+    src = torch.from_numpy(src_np.copy()).to(dev)
+    mask = None if mask_np is None else torch.from_numpy(mask_np.astype(np.int32)).to(dev)
+    sq = sd * sd
+    bufs = {n: torch.zeros(nb * sq, dtype=torch.complex128, device=dev) for n in ("w", "linv", "g", "y1", "g2", "y2", "u", "v")}
+    meta = torch.zeros(nb * K.SVD_META, dtype=torch.int32, device=dev)
+    rot = torch.zeros(nb, dtype=torch.int32, device=dev)
+    flag = torch.full((nb,), 7, dtype=torch.int32, device=dev)
+    nflag = torch.zeros(1, dtype=torch.int32, device=dev)
+    keep = torch.full((nb,), -1, dtype=torch.int32, device=dev)
+    B = lambda n: Buf(bufs[n], 0, sq)      # noqa: E731
+    orient = K.SVD_ORIENT_COLS if dist == "right" else K.SVD_ORIENT_ROWS
+    kern.svd_prepare(nb, mask, mode | orient, Ext(ext, 0, 2), Ext(ext, 1, 2), dphys, Buf(src, 0, slot), B("w"), B("linv"), meta, rot)
+    ek, eln = Ext(meta, 0, K.SVD_META), Ext(meta, 1, K.SVD_META)
+    kern.gemm(K.OP_GRAM, nb, 1, mask, ek, eln, None, 1, 1, 1, B("w"), B("w"), B("g"), 0, sd, sd)
+    kern.cholqr_factor(nb, mask, meta, B("g"), B("linv"), thr, flag, nflag, min(sd, 128))
+    kern.gemm(K.OP_ROTATE, nb, 1, mask, ek, eln, None, 1, 1, 1, B("linv"), B("w"), B("y1"), 0, sd, sd)
+    kern.gemm(K.OP_GRAM, nb, 1, mask, ek, eln, None, 1, 1, 1, B("y1"), B("y1"), B("g2"), 0, sd, sd)
+    kern.cholqr_refine(nb, mask, meta, B("g2"), B("g"), 1e-7, flag, nflag)
+    kern.gemm(K.OP_ROTATE, nb, 1, mask, ek, eln, None, 1, 1, 1, B("g"), B("y1"), B("y2"), 0, sd, sd)
+    kern.gemm(K.OP_GRAM, nb, 1, mask, ek, eln, None, 1, 1, 1, B("w"), B("y2"), B("g2"), 0, sd, sd)
+    kern.cholqr_finalize(nb, mask, meta, B("y2"), B("g2"), Ext(keep, 0, 1), B("u"), B("v"), flag, sd * 2 * sd)
+    if dev != "cpu":
+        torch.cuda.synchronize()
+    return (flag.cpu().numpy(), int(nflag.item()), keep.cpu().numpy(), bufs["u"].cpu().numpy().reshape(nb, sq), bufs["v"].cpu().numpy().reshape(nb, sq),
+            bufs["linv"].cpu().numpy().reshape(nb, sq), meta.cpu().numpy().reshape(nb, K.SVD_META))
+
+
+@pytest.mark.parametrize("mode,dist", [(K.SVD_ROWS, "right"), (K.SVD_COLS, "left")])
+def test_cholqr_gauge_shift_matches_twin_and_is_exact(backends, mode, dist):
+    """Keep-all gauge shifts by Cholesky-QR (csrc/yb_cholqr.cuh): flags / certificate agree with the twin; for accepted trajectories
+    keep = bond side, the isometric factor is orthonormal to 1e-14 and the two factors reproduce the centre tensor to 1e-13; graded
+    spectra down to 1e-4 relative pass, rank-deficient and too-thin matrices are flagged, masked trajectories are untouched."""
+    cuda, twin = backends
+    rng = np.random.default_rng(5)
+    d = 2
+    # (l, r) per trajectory; bond side = r for ROWS / right, l for COLS / left
+    shapes = [(64, 128), (128, 128), (20, 33), (1, 2), (7, 5), (100, 128), (64, 128), (3, 128), (64, 128), (37, 70)]
+    kinds = ["random", "graded", "random", "random", "random", "rankdef", "tiny_sv", "thin", "masked", "graded"]
+    if mode == K.SVD_COLS:
+        shapes = [(r, l) for l, r in shapes]
+    nb = len(shapes)
+    sd = 256
+    slot = sd * sd
+    ext = np.array(shapes, dtype=np.int32)
+    src = np.zeros(nb * slot, dtype=np.complex128)
+    mats = []
+    for t, ((l, r), kind) in enumerate(zip(shapes, kinds)):
+        rows, cols = (d * l, r) if mode == K.SVD_ROWS else (l, d * r)
+        kb = cols if mode == K.SVD_ROWS else rows
+        M = rng.standard_normal((rows, cols)) + 1j * rng.standard_normal((rows, cols))
+        if kind in ("graded", "rankdef", "tiny_sv") and min(rows, cols) == kb:
+            u, s, vh = np.linalg.svd(M, full_matrices=False)
+            s = 10.0 ** (-np.linspace(0, 4, kb))
+            if kind == "rankdef":
+                s[-3:] = 0.0
+            if kind == "tiny_sv":
+                s[-1] = 3e-7                                  # sigma^2 = 9e-14 < 1e-12: must be truncated, i.e. NOT certified
+            M = (u * s) @ vh
+        M /= np.linalg.norm(M)
+        mats.append(M)
+        if mode == K.SVD_ROWS:
+            src[t * slot: t * slot + M.size] = M.reshape(-1)
+        else:                                                 # l x (s r) stored as (s, l, r)
+            src[t * slot: t * slot + M.size] = M.reshape(l, d, r).transpose(1, 0, 2).reshape(-1)
+    mask = np.array([0 if k == "masked" else 1 for k in kinds])
+    fg, ng, kg, ug, vg, lg, mg = _cholqr_chain(cuda, "cuda:0", mode, dist, d, ext, src, slot, 1e-12, sd, mask)
+    fc, nc, kc, uc, vc, lc, mc = _cholqr_chain(twin, "cpu", mode, dist, d, ext, src, slot, 1e-12, sd, mask)
+    assert np.array_equal(fg, fc) and ng == nc, (fg, fc)
+    for t, ((l, r), kind) in enumerate(zip(shapes, kinds)):
+        M = mats[t]
+        rows, cols = M.shape
+        kb = cols if mode == K.SVD_ROWS else rows
+        if kind == "masked":
+            assert fg[t] == 0 and kg[t] == -1 and not ug[t].any()
+            continue
+        expect_flag = kind in ("rankdef", "tiny_sv", "thin") or kb > min(rows, cols)
+        assert bool(fg[t]) == expect_flag, (t, kind, fg[t])
+        assert mg[t, 7] == 0
+        if expect_flag:
+            assert kg[t] == -1
+            continue
+        assert kg[t] == kb
+        U, V = ug[t, : rows * kb].reshape(rows, kb), vg[t, : kb * cols].reshape(kb, cols)
+        iso = U.conj().T @ U if dist == "right" else V @ V.conj().T
+        assert np.max(np.abs(iso - np.eye(kb))) < 1e-14, (t, kind, float(np.max(np.abs(iso - np.eye(kb)))))
+        assert np.max(np.abs(U @ V - M)) < 1e-13, (t, kind)
+        # the first-pass triangular inverse against LAPACK
+        G = (M.conj().T @ M) if mode == K.SVD_ROWS else (M @ M.conj().T)
+        Li = np.linalg.inv(np.linalg.cholesky(G))
+        got = lg[t, : kb * kb].reshape(kb, kb)
+        assert np.max(np.abs(got - Li)) <= 1e-9 * np.max(np.abs(Li)), (t, kind)
+        assert not np.triu(got, 1).any()

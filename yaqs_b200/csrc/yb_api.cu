@@ -392,6 +392,38 @@ int yb_heev_rows(int nbatch, const int32_t* mask, yb_extent ek, void* g, int64_t
     return done("yb_heev_rows(ormtr)");
 }
 
+int yb_cholqr_factor(int nbatch, const int32_t* mask, const int32_t* meta, const void* g, int64_t stride_g, void* linv, int64_t stride_l,
+                     double threshold, int32_t* flag, int32_t* n_flag, int max_k, void* stream) {
+    if (nbatch <= 0) return 0;
+    if (max_k > cholqr::KMAX) return fail_msg("yb_cholqr_factor: max_k > 128 unsupported (packed triangle must fit in shared memory)");
+    if (max_k < 1) max_k = 1;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(cholqr::k_cholqr_factor, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cholqr::smem_bytes(cholqr::KMAX));
+        if (e != cudaSuccess) return fail("yb_cholqr_factor(attr)", e);
+        configured = true;
+    }
+    cholqr::k_cholqr_factor<<<nbatch, cholqr::THREADS, cholqr::smem_bytes(max_k), (cudaStream_t)stream>>>((const cplx*)g, stride_g, (cplx*)linv, stride_l, meta,
+                                                                                                         threshold, flag, n_flag, max_k, mask);
+    return done("yb_cholqr_factor");
+}
+
+int yb_cholqr_refine(int nbatch, const int32_t* mask, const int32_t* meta, const void* g2, int64_t stride_g, void* x, int64_t stride_x, double tol,
+                     int32_t* flag, int32_t* n_flag, void* stream) {
+    if (nbatch <= 0) return 0;
+    cholqr::k_cholqr_refine<<<nbatch, cholqr::THREADS, 0, (cudaStream_t)stream>>>((const cplx*)g2, stride_g, (cplx*)x, stride_x, meta, tol, flag, n_flag, mask);
+    return done("yb_cholqr_refine");
+}
+
+int yb_cholqr_finalize(int nbatch, const int32_t* mask, int32_t* meta, const void* y2, int64_t stride_y, const void* l2, int64_t stride_l, int32_t* keep,
+                       int32_t keep_stride, void* uout, int64_t stride_u, void* vout, int64_t stride_v, const int32_t* flag, int max_elems, void* stream) {
+    if (nbatch <= 0) return 0;
+    dim3 grid(grid_for(max_elems, 256, 64), nbatch);
+    cholqr::k_cholqr_finalize<<<grid, 256, 0, (cudaStream_t)stream>>>((const cplx*)y2, stride_y, (const cplx*)l2, stride_l, meta, keep, keep_stride, (cplx*)uout,
+                                                                       stride_u, (cplx*)vout, stride_v, flag, mask);
+    return done("yb_cholqr_finalize");
+}
+
 int yb_unpack_vh(int nbatch, const int32_t* mask, yb_extent ek, yb_extent er, int dphys, const void* src, int64_t stride_src, void* dst,
                  int64_t stride_dst, int max_elems, void* stream) {
     if (nbatch <= 0) return 0;

@@ -481,3 +481,5 @@ __global__ void k_svd_ambiguous(int nbatch, const int* meta, const double* __res
     amb[b] = flag ? 1 : 0;
     if (flag) atomicAdd(n_amb, 1);
 }
+
+#include "yb_cholqr.cuh"

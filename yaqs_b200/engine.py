@@ -284,6 +284,8 @@ class BatchedTJM:
         self.fused_mpo = os.environ.get("YB_FUSED_MPO", "1") != "0"
         # Gram-route eigen-solver: yb_heev_rows (blocked, round 2) unless YB_HEEV_ROWS=0 selects the round-1 kernels + EVEC product
         self.heev_rows = os.environ.get("YB_HEEV_ROWS", "1") != "0"
+        # keep-all gauge shifts by Cholesky-QR (round 2, second session); YB_CHOLQR=0 sends them through the eigen-solver (A/B runs)
+        self.cholqr = os.environ.get("YB_CHOLQR", "1") != "0"
         self.use_gram = sd >= gram_min_k and sd <= 512
         if self.use_gram:
             self.heev_g = torch.zeros(B * sd * sd, dtype=C128, device=dev)
@@ -305,7 +307,8 @@ class BatchedTJM:
         # entries: (matrix, sites) | ("entropy", (i, i+1)) | ("pvm:<bitstring>", ())
         self.observables = [(m if isinstance(m, str) else np.asarray(m, dtype=np.complex128), tuple(int(s) for s in sites)) for m, sites in observables]
         self._ones_i32 = torch.ones(B, dtype=torch.int32, device=dev)
-        self.stats = {"krylov_calls": 0, "matvecs": 0, "matvecs_2site": 0, "svd_calls": 0, "svd_sweeps": 0, "jumps": 0, "gram_svd_calls": 0, "gram_fallbacks": 0}
+        self.stats = {"krylov_calls": 0, "matvecs": 0, "matvecs_2site": 0, "svd_calls": 0, "svd_sweeps": 0, "jumps": 0, "gram_svd_calls": 0, "gram_fallbacks": 0, "cholqr_calls": 0,
+                      "cholqr_fallbacks": 0}
 
     # ------------------------------------------------------------------------------------------------------------------
     # operator / noise contexts (one each on the analog path; per gate on the digital path)
@@ -486,9 +489,52 @@ class BatchedTJM:
         Gram-matrix route for large matrices; the one-sided Jacobi is used otherwise and as its accurate fallback.  ``dims``:
         capacities (rows, cols) of the matrix -- they size the Jacobi panels (default: the layout's largest matrix)."""
         if self.use_gram and kcap > 0 and kcap >= self.gram_min_k and dist in ("left", "right") and trunc[0] in (0, 1):
-            self._svd_gram(mode, src, el, er, trunc, dist, mask, dims)
+            tm, thr, mb, _mk = trunc
+            kb, lb = (0, 0) if dims is None else ((dims[1], dims[0]) if dist == "right" else (dims[0], dims[1]))      # bond side, other side
+            if (self.cholqr and mode in (SVD_ROWS, SVD_COLS) and tm == 0 and thr <= self.CHOLQR_MAX_THRESHOLD and 0 < kb <= min(lb, self.CHOLQR_KMAX)
+                    and (mb == 0 or mb >= kb)):
+                self._svd_cholqr(mode, src, el, er, trunc, dist, mask, dims)
+            else:
+                self._svd_gram(mode, src, el, er, trunc, dist, mask, dims)
         else:
             self._svd_jacobi(mode, src, el, er, trunc, dist, mask, dims)
+
+    # Gauge shifts whose truncation policy can only ever remove singular values below ~1e-6 (the hard-coded 1e-12 discarded weight of
+    # mps.py:757-759, or none at all) keep every singular value unless the matrix is numerically rank-deficient.  For those the
+    # factorisation is a Cholesky-QR with a keep-all certificate (csrc/yb_cholqr.cuh); trajectories the certificate does not cover
+    # (rank-deficient bonds right after a lowering jump, a bond side longer than the other side) take the eigen-solver route.
+    CHOLQR_MAX_THRESHOLD = 1e-9
+    CHOLQR_KMAX = 128
+    CHOLQR_TOL = 1e-7             # accepted orthonormality defect of the first pass; one Newton-Schulz step squares it
+
+    def _svd_cholqr(self, mode: int, src: Buf, el: Ext, er: Ext, trunc, dist: str, mask, dims: tuple[int, int]) -> None:
+        K, B, lay = self.K, self.B, self.lay
+        sd = lay.svd_dim
+        sq = sd * sd
+        w, linv = self._buf(self.svd_w, sq), self._buf(self.svd_q, sq)
+        g, y1, g2, y2 = self._buf(self.heev_g, sq), self._buf(self.heev_q, sq), self._buf(self.heev_z, sq), self._buf(self.heev_s, sq)
+        x, l2 = g, g2                                        # the Gram matrices are dead once factor / refine have read them
+        # the bond side must index the rows of W: W = M^H for a right shift (U = site i becomes the isometry), W = M for a left shift
+        orient = SVD_ORIENT_COLS if dist == "right" else SVD_ORIENT_ROWS
+        kdim = max(1, min(sd, dims[1] if dist == "right" else dims[0]))
+        ldim = max(1, min(sd, dims[0] if dist == "right" else dims[1]))
+        K.svd_prepare(B, mask, mode | orient, el, er, self.d, src, w, linv, self.svd_meta, self.svd_rot)
+        ek, eln = Ext(self.svd_meta, 0, SVD_META), Ext(self.svd_meta, 1, SVD_META)
+        K.gemm(OP_GRAM, B, 1, mask, ek, eln, None, 1, 1, 1, w, w, g, 0, kdim, kdim)
+        self.counter.zero_()
+        K.cholqr_factor(B, mask, self.svd_meta, g, linv, float(trunc[1]), self.amb, self.counter, kdim)
+        K.gemm(OP_ROTATE, B, 1, mask, ek, eln, None, 1, 1, 1, linv, w, y1, 0, kdim, ldim)
+        K.gemm(OP_GRAM, B, 1, mask, ek, eln, None, 1, 1, 1, y1, y1, g2, 0, kdim, kdim)
+        K.cholqr_refine(B, mask, self.svd_meta, g2, x, self.CHOLQR_TOL, self.amb, self.counter)
+        K.gemm(OP_ROTATE, B, 1, mask, ek, eln, None, 1, 1, 1, x, y1, y2, 0, kdim, ldim)
+        K.gemm(OP_GRAM, B, 1, mask, ek, eln, None, 1, 1, 1, w, y2, l2, 0, kdim, kdim)
+        K.cholqr_finalize(B, mask, self.svd_meta, y2, l2, Ext(self.keep, 0, 1), self._buf(self.svd_u, sq), self._buf(self.svd_v, sq), self.amb,
+                          kdim * (ldim + kdim))
+        self.stats["cholqr_calls"] += 1
+        nfb = K.sync_int(self.counter)
+        if nfb > 0:                                          # not certified: the eigen-solver route decides (and truncates) for those
+            self.stats["cholqr_fallbacks"] += nfb
+            self._svd_gram(mode, src, el, er, trunc, dist, self.amb.clone(), dims)
 
     def _jacobi_geometry(self, dims: tuple[int, int] | None) -> tuple[int, int, int, int, int]:
         """(block_rows, nblocks, inner_sweeps, max_len, max_k) of the one-sided Jacobi for matrices of at most ``dims`` = (rows,
@@ -652,6 +698,7 @@ class BatchedTJM:
 
     def tdvp(self, st: BatchedState) -> None:
         """tdvp (tdvp.py:69-112)."""
+        self.K.phase = "tdvp"
         mode = self.p.tdvp_mode
         if mode in ("2site", "dynamic") and self.L == 1:
             mode = "1site"
@@ -924,6 +971,7 @@ class BatchedTJM:
         """dissipation.py:50-183; ``start`` = current orthogonality centre (0 on the analog path, the right site of the
         gate pair after a TEBD gate)."""
         lay, K, B, d, n, p = self.lay, self.K, self.B, self.d, self.L, self.p
+        K.phase = "dissipation"
         if not self.noise_active:
             keep_all = self._trunc_args("discarded_weight", 0.0, None, 1)
             for i in reversed(range(1, start + 1)):         # dissipation.py:79-86: centre -> 0 with QR shifts
@@ -1006,6 +1054,7 @@ class BatchedTJM:
         """[B, n_obs] expectation values in the given (sorted) observable order (mps.py:1178-1234).  A value whose imaginary
         part violates the reference's ``assert exp.imag < 1e-13`` (mps.py:1233) raises status bit 8 for that trajectory."""
         tab = self._observable_tables()
+        self.K.phase = "observables"
         res = torch.zeros((self.B, len(self.observables)), dtype=torch.float64, device=self.dev)
         if tab["any"]:
             g1, g2 = self.rho_sweep(st, tab["need1"], tab["need2"])
@@ -1227,6 +1276,7 @@ class BatchedTJM:
         and -- only when somebody jumps -- one read of (weight totals, selected processes), from which the whole launch plan
         of the jump application is made on the host."""
         K, B, lay, d, n = self.K, self.B, self.lay, self.d, self.L
+        K.phase = "jumps"
         if self.noise is None:
             self.normalize_site(st, 0)                      # :226-231 (the uniform is not drawn)
             return None

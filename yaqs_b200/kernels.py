@@ -85,7 +85,7 @@ def load_library() -> ctypes.CDLL:
 
 EXPORTED_SYMBOLS = [
     "yb_last_error", "yb_version", "yb_launch_count", "yb_set_flop_counter", "yb_set_option", "yb_workspace_bytes", "yb_gemm", "yb_rcontract_mpo", "yb_wapply", "yb_env_identity", "yb_lanczos_init",
-    "yb_lanczos_step", "yb_lanczos_combine", "yb_svd_prepare", "yb_svd_round", "yb_svd_check", "yb_svd_finalize", "yb_svd_ambiguous", "yb_heev", "yb_heev_rows", "yb_svd_select", "yb_svd_gather",
+    "yb_lanczos_step", "yb_lanczos_combine", "yb_svd_prepare", "yb_svd_round", "yb_svd_check", "yb_svd_finalize", "yb_svd_ambiguous", "yb_heev", "yb_heev_rows", "yb_cholqr_factor", "yb_cholqr_refine", "yb_cholqr_finalize", "yb_svd_select", "yb_svd_gather",
     "yb_unpack_vh", "yb_copy_packed", "yb_apply_local_op", "yb_mpo_site_apply", "yb_norm2", "yb_scale", "yb_local_rdm", "yb_philox_uniform",
 ]
 
@@ -103,11 +103,14 @@ class CudaKernels:
         if self.device.type != "cuda":
             raise KernelError("yaqs_b200 kernels run on CUDA devices only")
         self._timed: dict[str, list] | None = None
+        self._detail: dict[tuple, list] | None = None
         self._flops = None
+        self.phase = ""              # label set by the engine (tdvp / dissipation / jumps / observables): second key of the detailed timing
 
     # -- instrumentation (bench.py): CUDA events around every launch of a kernel family + on-device flop counter --------
     def start_timing(self) -> None:
         self._timed = {}
+        self._detail = {}
         self._flops = torch.zeros(1, dtype=torch.int64, device=self.device)
         self.lib.yb_set_flop_counter(ctypes.c_void_p(self._flops.data_ptr()))
 
@@ -117,14 +120,16 @@ class CudaKernels:
         self.lib.yb_set_flop_counter(ctypes.c_void_p(0))
         out = {k: {"launches": len(v), "ms": float(sum(a.elapsed_time(b) for a, b in v))} for k, v in (self._timed or {}).items()}
         out["gemm_flops"] = int(self._flops.item()) if self._flops is not None else 0
-        self._timed, self._flops = None, None
+        # (family, sub-key, phase) -> launches / ms: where inside the step a family's time goes (bench.py `kernel_breakdown`)
+        out["detail"] = {k: {"launches": len(v), "ms": float(sum(a.elapsed_time(b) for a, b in v))} for k, v in (self._detail or {}).items()}
+        self._timed, self._detail, self._flops = None, None, None
         return out
 
     def set_option(self, name: str, value: int) -> None:
         """Diagnostic switch of the library (include/yaqs_b200.h: yb_set_option)."""
         self._check(self.lib.yb_set_option(name.encode(), int(value)))
 
-    def _timed_call(self, family: str, fn) -> None:
+    def _timed_call(self, family: str, fn, sub: str = "") -> None:
         if self._timed is None:
             fn()
             return
@@ -134,6 +139,7 @@ class CudaKernels:
         fn()
         e1.record(st)
         self._timed.setdefault(family, []).append((e0, e1))
+        self._detail.setdefault((family, sub, self.phase), []).append((e0, e1))
 
     # -- helpers ------------------------------------------------------------------------------------------------------
     def _stream(self):
@@ -175,7 +181,7 @@ class CudaKernels:
         self._timed_call("gemm", lambda: self._check(self.lib.yb_gemm(
             op, nbatch, ngroups, self._ptr(mask), self._ext(e0), self._ext(e1), self._ext(e2), dphys, d_left, d_right,
             self._cptr(a), ctypes.c_int64(a.stride), self._cptr(b), ctypes.c_int64(b.stride), self._cptr(c), ctypes.c_int64(c.stride),
-            int(conj_b), int(max_m), int(max_n), self._stream())))
+            int(conj_b), int(max_m), int(max_n), self._stream())), f"op{op}:{max_m}x{max_n}" if self._timed is not None else "")
 
     def rcontract_mpo(self, nbatch, mask, el, er, dphys, d_left, d_right, x: Buf, renv: Buf, wt: torch.Tensor, out: Buf, max_l, max_r):
         if wt.dtype != torch.complex128:
@@ -183,7 +189,7 @@ class CudaKernels:
         self._timed_call("gemm", lambda: self._check(self.lib.yb_rcontract_mpo(
             nbatch, self._ptr(mask), self._ext(el), self._ext(er), int(dphys), int(d_left), int(d_right), self._cptr(x), ctypes.c_int64(x.stride),
             self._cptr(renv), ctypes.c_int64(renv.stride), self._ptr(wt), self._cptr(out), ctypes.c_int64(out.stride), int(max_l), int(max_r),
-            self._stream())))
+            self._stream())), f"rw:{dphys * max_l}x{d_right * max_r}" if self._timed is not None else "")
 
     def wapply(self, nbatch, mask, el, er, nx, nu, ny, nv, wt: torch.Tensor, src: Buf, dst: Buf, max_lr):
         if wt.dtype != torch.complex128:
@@ -193,14 +199,14 @@ class CudaKernels:
             ctypes.c_int64(src.stride), self._cptr(dst), ctypes.c_int64(dst.stride), int(max_lr), self._stream())))
 
     def env_identity(self, nbatch, mask, echi, dmpo, env: Buf, max_chi):
-        self._check(self.lib.yb_env_identity(nbatch, self._ptr(mask), self._ext(echi), dmpo, self._cptr(env), ctypes.c_int64(env.stride),
-                                             int(max_chi), self._stream()))
+        self._timed_call("local", lambda: self._check(self.lib.yb_env_identity(nbatch, self._ptr(mask), self._ext(echi), dmpo, self._cptr(env), ctypes.c_int64(env.stride),
+                                             int(max_chi), self._stream())))
 
     # -- Lanczos ------------------------------------------------------------------------------------------------------
     def lanczos_init(self, nbatch, mask, el, er, dphys, x: Buf, basis: Buf, stride_vec, nrm, active, kdone):
-        self._check(self.lib.yb_lanczos_init(
+        self._timed_call("lanczos_misc", lambda: self._check(self.lib.yb_lanczos_init(
             nbatch, self._ptr(mask), self._ext(el), self._ext(er), dphys, self._cptr(x), ctypes.c_int64(x.stride), self._cptr(basis),
-            ctypes.c_int64(basis.stride), ctypes.c_int64(stride_vec), self._ptr(nrm), self._ptr(active), self._ptr(kdone), self._stream()))
+            ctypes.c_int64(basis.stride), ctypes.c_int64(stride_vec), self._ptr(nrm), self._ptr(active), self._ptr(kdone), self._stream())))
 
     def lanczos_step(self, nbatch, j, kmax, dt, tol, el, er, dphys, basis: Buf, stride_vec, alpha, beta, nrm, active, kdone, coef, n_active):
         self._timed_call("lanczos_step", lambda: self._check(self.lib.yb_lanczos_step(
@@ -209,15 +215,15 @@ class CudaKernels:
             self._ptr(kdone), self._ptr(coef), self._ptr(n_active), self._stream())))
 
     def lanczos_combine(self, nbatch, mask, el, er, dphys, basis: Buf, stride_vec, coef, kmax, kdone, out: Buf):
-        self._check(self.lib.yb_lanczos_combine(
+        self._timed_call("lanczos_misc", lambda: self._check(self.lib.yb_lanczos_combine(
             nbatch, self._ptr(mask), self._ext(el), self._ext(er), dphys, self._cptr(basis), ctypes.c_int64(basis.stride),
-            ctypes.c_int64(stride_vec), self._ptr(coef), kmax, self._ptr(kdone), self._cptr(out), ctypes.c_int64(out.stride), self._stream()))
+            ctypes.c_int64(stride_vec), self._ptr(coef), kmax, self._ptr(kdone), self._cptr(out), ctypes.c_int64(out.stride), self._stream())))
 
     # -- SVD ----------------------------------------------------------------------------------------------------------
     def svd_prepare(self, nbatch, mask, mode, el, er, dphys, src: Buf, w: Buf, q: Buf, meta, rot_count):
-        self._check(self.lib.yb_svd_prepare(
+        self._timed_call("svd_misc", lambda: self._check(self.lib.yb_svd_prepare(
             nbatch, self._ptr(mask), mode, self._ext(el), self._ext(er), dphys, self._cptr(src), ctypes.c_int64(src.stride), self._cptr(w),
-            ctypes.c_int64(w.stride), self._cptr(q), ctypes.c_int64(q.stride), self._ptr(meta), self._ptr(rot_count), self._stream()))
+            ctypes.c_int64(w.stride), self._cptr(q), ctypes.c_int64(q.stride), self._ptr(meta), self._ptr(rot_count), self._stream())))
 
     def svd_round(self, nbatch, mask, meta, block_rows, nblocks, rnd, full_panel, inner_sweeps, w: Buf, q: Buf, rot_count, max_len, max_k):
         self._timed_call("svd_round", lambda: self._check(self.lib.yb_svd_round(
@@ -225,73 +231,90 @@ class CudaKernels:
             ctypes.c_int64(w.stride), self._cptr(q), ctypes.c_int64(q.stride), self._ptr(rot_count), int(max_len), int(max_k), self._stream())))
 
     def svd_check(self, nbatch, mask, meta, rot_count, n_pending):
-        self._check(self.lib.yb_svd_check(nbatch, self._ptr(mask), self._ptr(meta), self._ptr(rot_count), self._ptr(n_pending), self._stream()))
+        self._timed_call("svd_misc", lambda: self._check(self.lib.yb_svd_check(nbatch, self._ptr(mask), self._ptr(meta), self._ptr(rot_count), self._ptr(n_pending), self._stream())))
 
     def svd_finalize(self, nbatch, mask, meta, trunc_mode, threshold, max_bond, min_keep, dist, w: Buf, q: Buf, sval, stride_s, keep: Ext,
                      uout: Buf, vout: Buf, status, max_k):
-        self._check(self.lib.yb_svd_finalize(
+        self._timed_call("svd_misc", lambda: self._check(self.lib.yb_svd_finalize(
             nbatch, self._ptr(mask), self._ptr(meta), trunc_mode, ctypes.c_double(threshold), int(max_bond), int(min_keep), dist,
             self._cptr(w), ctypes.c_int64(w.stride), self._cptr(q), ctypes.c_int64(q.stride), self._ptr(sval), ctypes.c_int64(stride_s),
             self._ptr(keep.tensor, 4 * keep.offset), keep.stride, self._cptr(uout), ctypes.c_int64(uout.stride), self._cptr(vout),
-            ctypes.c_int64(vout.stride), self._ptr(status), int(max_k), self._stream()))
+            ctypes.c_int64(vout.stride), self._ptr(status), int(max_k), self._stream())))
 
     def svd_ambiguous(self, nbatch, mask, meta, sval, stride_s, trunc_mode, threshold, two_level, tau_rel, noise_rel, status, amb, n_amb):
-        self._check(self.lib.yb_svd_ambiguous(nbatch, self._ptr(mask), self._ptr(meta), self._ptr(sval), ctypes.c_int64(stride_s), int(trunc_mode),
+        self._timed_call("svd_misc", lambda: self._check(self.lib.yb_svd_ambiguous(nbatch, self._ptr(mask), self._ptr(meta), self._ptr(sval), ctypes.c_int64(stride_s), int(trunc_mode),
                                               ctypes.c_double(threshold), int(bool(two_level)), ctypes.c_double(tau_rel), ctypes.c_double(noise_rel),
-                                              self._ptr(status), self._ptr(amb), self._ptr(n_amb), self._stream()))
+                                              self._ptr(status), self._ptr(amb), self._ptr(n_amb), self._stream())))
 
     def heev(self, nbatch, mask, ek: Ext, g: Buf, qh: Buf, zt: Buf, zr: torch.Tensor, stride_zr, d, e, tau: torch.Tensor, stride_vec, meta, status,
              max_k):
         self._timed_call("heev", lambda: self._check(self.lib.yb_heev(
             nbatch, self._ptr(mask), self._ext(ek), self._cptr(g), ctypes.c_int64(g.stride), self._cptr(qh), ctypes.c_int64(qh.stride),
             self._cptr(zt), ctypes.c_int64(zt.stride), self._ptr(zr), ctypes.c_int64(stride_zr), self._ptr(d), self._ptr(e), self._ptr(tau),
-            ctypes.c_int64(stride_vec), self._ptr(meta), self._ptr(status), int(max_k), self._stream())))
+            ctypes.c_int64(stride_vec), self._ptr(meta), self._ptr(status), int(max_k), self._stream())), f"k{max_k}")
 
     def heev_rows(self, nbatch, mask, ek: Ext, g: Buf, eh: Buf, zr: torch.Tensor, stride_zr, d, e, tau: torch.Tensor, stride_vec, meta, status, max_k):
         self._timed_call("heev", lambda: self._check(self.lib.yb_heev_rows(
             nbatch, self._ptr(mask), self._ext(ek), self._cptr(g), ctypes.c_int64(g.stride), self._cptr(eh), ctypes.c_int64(eh.stride),
             self._ptr(zr), ctypes.c_int64(stride_zr), self._ptr(d), self._ptr(e), self._ptr(tau), ctypes.c_int64(stride_vec), self._ptr(meta),
-            self._ptr(status), int(max_k), self._stream())))
+            self._ptr(status), int(max_k), self._stream())), f"k{max_k}")
+
+    # -- truncation-free gauge shifts by Cholesky-QR (csrc/yb_cholqr.cuh) ----------------------------------------------
+    def cholqr_factor(self, nbatch, mask, meta, g: Buf, linv: Buf, threshold, flag, n_flag, max_k):
+        self._timed_call("cholqr", lambda: self._check(self.lib.yb_cholqr_factor(
+            nbatch, self._ptr(mask), self._ptr(meta), self._cptr(g), ctypes.c_int64(g.stride), self._cptr(linv), ctypes.c_int64(linv.stride),
+            ctypes.c_double(threshold), self._ptr(flag), self._ptr(n_flag), int(max_k), self._stream())), f"k{max_k}")
+
+    def cholqr_refine(self, nbatch, mask, meta, g2: Buf, x: Buf, tol, flag, n_flag):
+        self._timed_call("svd_misc", lambda: self._check(self.lib.yb_cholqr_refine(
+            nbatch, self._ptr(mask), self._ptr(meta), self._cptr(g2), ctypes.c_int64(g2.stride), self._cptr(x), ctypes.c_int64(x.stride),
+            ctypes.c_double(tol), self._ptr(flag), self._ptr(n_flag), self._stream())))
+
+    def cholqr_finalize(self, nbatch, mask, meta, y2: Buf, l2: Buf, keep: Ext, uout: Buf, vout: Buf, flag, max_elems):
+        self._timed_call("svd_misc", lambda: self._check(self.lib.yb_cholqr_finalize(
+            nbatch, self._ptr(mask), self._ptr(meta), self._cptr(y2), ctypes.c_int64(y2.stride), self._cptr(l2), ctypes.c_int64(l2.stride),
+            self._ptr(keep.tensor, 4 * keep.offset), keep.stride, self._cptr(uout), ctypes.c_int64(uout.stride), self._cptr(vout),
+            ctypes.c_int64(vout.stride), self._ptr(flag), int(max_elems), self._stream())))
 
     def svd_select(self, nbatch, mask, meta, w: Buf, tau_rel, sel_n, sel_idx, max_k):
-        self._check(self.lib.yb_svd_select(nbatch, self._ptr(mask), self._ptr(meta), self._cptr(w), ctypes.c_int64(w.stride),
-                                           ctypes.c_double(tau_rel), self._ptr(sel_n), self._ptr(sel_idx), int(max_k), self._stream()))
+        self._timed_call("svd_misc", lambda: self._check(self.lib.yb_svd_select(nbatch, self._ptr(mask), self._ptr(meta), self._cptr(w), ctypes.c_int64(w.stride),
+                                           ctypes.c_double(tau_rel), self._ptr(sel_n), self._ptr(sel_idx), int(max_k), self._stream())))
 
     def svd_gather(self, nbatch, mask, meta, sel_n, sel_idx, max_k, direction, w: Buf, q: Buf, ws: Buf, qs: Buf):
-        self._check(self.lib.yb_svd_gather(nbatch, self._ptr(mask), self._ptr(meta), self._ptr(sel_n), self._ptr(sel_idx), int(max_k),
+        self._timed_call("svd_misc", lambda: self._check(self.lib.yb_svd_gather(nbatch, self._ptr(mask), self._ptr(meta), self._ptr(sel_n), self._ptr(sel_idx), int(max_k),
                                            int(direction), self._cptr(w), ctypes.c_int64(w.stride), self._cptr(q), ctypes.c_int64(q.stride),
-                                           self._cptr(ws), ctypes.c_int64(ws.stride), self._cptr(qs), ctypes.c_int64(qs.stride), self._stream()))
+                                           self._cptr(ws), ctypes.c_int64(ws.stride), self._cptr(qs), ctypes.c_int64(qs.stride), self._stream())))
 
     # -- site-tensor utilities ----------------------------------------------------------------------------------------
     def unpack_vh(self, nbatch, mask, ek, er, dphys, src: Buf, dst: Buf, max_elems):
-        self._check(self.lib.yb_unpack_vh(nbatch, self._ptr(mask), self._ext(ek), self._ext(er), dphys, self._cptr(src),
-                                          ctypes.c_int64(src.stride), self._cptr(dst), ctypes.c_int64(dst.stride), int(max_elems), self._stream()))
+        self._timed_call("pack", lambda: self._check(self.lib.yb_unpack_vh(nbatch, self._ptr(mask), self._ext(ek), self._ext(er), dphys, self._cptr(src),
+                                          ctypes.c_int64(src.stride), self._cptr(dst), ctypes.c_int64(dst.stride), int(max_elems), self._stream())))
 
     def copy_packed(self, nbatch, mask, e0, e1, mult, src: Buf, dst: Buf, max_elems):
-        self._check(self.lib.yb_copy_packed(nbatch, self._ptr(mask), self._ext(e0), self._ext(e1), mult, self._cptr(src),
-                                            ctypes.c_int64(src.stride), self._cptr(dst), ctypes.c_int64(dst.stride), int(max_elems), self._stream()))
+        self._timed_call("pack", lambda: self._check(self.lib.yb_copy_packed(nbatch, self._ptr(mask), self._ext(e0), self._ext(e1), mult, self._cptr(src),
+                                            ctypes.c_int64(src.stride), self._cptr(dst), ctypes.c_int64(dst.stride), int(max_elems), self._stream())))
 
     def apply_local_op(self, nbatch, mask, sel, sel_value, el, er, dphys, op: torch.Tensor, op_stride, a: Buf, max_lr):
         if op.dtype != torch.complex128:
             raise KernelError(f"apply_local_op: complex128 operator expected, got {op.dtype}")
-        self._check(self.lib.yb_apply_local_op(nbatch, self._ptr(mask), self._ptr(sel), int(sel_value), self._ext(el), self._ext(er), dphys,
+        self._timed_call("local", lambda: self._check(self.lib.yb_apply_local_op(nbatch, self._ptr(mask), self._ptr(sel), int(sel_value), self._ext(el), self._ext(er), dphys,
                                                self._ptr(op), ctypes.c_int64(op_stride), self._cptr(a), ctypes.c_int64(a.stride), int(max_lr),
-                                               self._stream()))
+                                               self._stream())))
 
     def mpo_site_apply(self, nbatch, mask, el, er, dphys, d_left, d_right, w: torch.Tensor, src: Buf, dst: Buf, max_out_lr):
         if w.dtype != torch.complex128:
             raise KernelError(f"mpo_site_apply: complex128 MPO tensor expected, got {w.dtype}")
-        self._check(self.lib.yb_mpo_site_apply(nbatch, self._ptr(mask), self._ext(el), self._ext(er), dphys, int(d_left), int(d_right), self._ptr(w),
+        self._timed_call("local", lambda: self._check(self.lib.yb_mpo_site_apply(nbatch, self._ptr(mask), self._ext(el), self._ext(er), dphys, int(d_left), int(d_right), self._ptr(w),
                                                self._cptr(src), ctypes.c_int64(src.stride), self._cptr(dst), ctypes.c_int64(dst.stride),
-                                               int(max_out_lr), self._stream()))
+                                               int(max_out_lr), self._stream())))
 
     def norm2(self, nbatch, mask, el, er, dphys, a: Buf, out):
-        self._check(self.lib.yb_norm2(nbatch, self._ptr(mask), self._ext(el), self._ext(er), dphys, self._cptr(a), ctypes.c_int64(a.stride),
-                                      self._ptr(out), self._stream()))
+        self._timed_call("local", lambda: self._check(self.lib.yb_norm2(nbatch, self._ptr(mask), self._ext(el), self._ext(er), dphys, self._cptr(a), ctypes.c_int64(a.stride),
+                                      self._ptr(out), self._stream())))
 
     def scale(self, nbatch, mask, el, er, dphys, scale, a: Buf, max_elems):
-        self._check(self.lib.yb_scale(nbatch, self._ptr(mask), self._ext(el), self._ext(er), dphys, self._ptr(scale), self._cptr(a),
-                                      ctypes.c_int64(a.stride), int(max_elems), self._stream()))
+        self._timed_call("local", lambda: self._check(self.lib.yb_scale(nbatch, self._ptr(mask), self._ext(el), self._ext(er), dphys, self._ptr(scale), self._cptr(a),
+                                      ctypes.c_int64(a.stride), int(max_elems), self._stream())))
 
     def philox_uniform(self, seed: int, traj_index, tag: int, nblocks: int, block0: int, out):
         """out [nbatch, 2 * nblocks] float64 (contiguous rows); traj_index int64 [nbatch] on the device."""
@@ -300,5 +323,5 @@ class CudaKernels:
                                                ctypes.c_uint32(block0), self._ptr(out), ctypes.c_int64(out.stride(0)), self._stream()))
 
     def local_rdm(self, nbatch, mask, el, er, dphys, a: Buf, x: Buf, g):
-        self._check(self.lib.yb_local_rdm(nbatch, self._ptr(mask), self._ext(el), self._ext(er), dphys, self._cptr(a), ctypes.c_int64(a.stride),
-                                          self._cptr(x), ctypes.c_int64(x.stride), self._ptr(g), self._stream()))
+        self._timed_call("local", lambda: self._check(self.lib.yb_local_rdm(nbatch, self._ptr(mask), self._ext(el), self._ext(er), dphys, self._cptr(a), ctypes.c_int64(a.stride),
+                                          self._cptr(x), ctypes.c_int64(x.stride), self._ptr(g), self._stream())))
