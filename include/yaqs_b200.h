@@ -72,6 +72,7 @@ int yb_workspace_bytes(int length, int nbatch, int dphys, const int32_t* cap, co
  *   8 GRAM       G[i,j] = sum_e W[i,e] conj(W[j,e])       Gram matrix of the packed SVD work matrix (k rows of length len)
  *   9 EVEC       Qacc[c,j] = sum_i Zt[c,i] conj(Qh[j,i])  conjugated eigenvectors of G as rows (yb_heev outputs)
  *  10 ROTATE     Wf[c,e] = sum_j Qacc[c,j] W[j,e]         rows of Wf are orthogonal with norms = singular values
+ *  11 ROTATE_TOP Wf[c,e] = sum_j Etop[c,j] W[j,e], c < e2  the same product for the compact eigenvector block of yb_heev_rows_top (e0 = k, e1 = len, e2 = rows)
  * e0,e1,e2: the op's extents (l, r | l, c, r | k, j, r | l, j, k | k, len).  conj_b != 0 conjugates the B operand in addition.
  * max_m / max_n bound the per-trajectory GEMM M and N (grid sizing). */
 int yb_gemm(int op, int nbatch, int ngroups, const int32_t* mask, yb_extent e0, yb_extent e1, yb_extent e2, int dphys, int d_left,
@@ -148,6 +149,19 @@ int yb_heev(int nbatch, const int32_t* mask, yb_extent ek, void* g, int64_t stri
  * with the reflectors (row j = v_j), eh must not alias g; zr (k*k doubles), e, tau are workspace; d = eigenvalues (unsorted). */
 int yb_heev_rows(int nbatch, const int32_t* mask, yb_extent ek, void* g, int64_t stride_g, void* eh, int64_t stride_eh, double* zr, int64_t stride_zr,
                  double* d, double* e, void* tau, int64_t stride_vec, int32_t* meta, int32_t* status, int max_k, void* stream);
+/* yb_heev_rows_top: yb_heev_rows for a split that is capped at max_bond <= top < k (split_two_site under max_bond_dim,
+ * core/methods/decompositions.py:105-185 with svd_utils.py:99-101): only the eigenvectors of the `top` largest eigenvalues can be kept,
+ * so only those rows are back-transformed.  order[b][rank] = index of the rank-th largest eigenvalue, dsorted[b][rank] = its value,
+ * ntop[b] = min(k, top); eh rows 0 .. ntop[b]) = the eigenvector rows in that order (compact).  Follow with yb_gemm(ROTATE_TOP, e2 =
+ * ntop) and yb_svd_finalize_top, which takes the singular values behind row ntop -- needed for the discarded weight only -- from
+ * sqrt(max(dsorted, 0)). */
+int yb_heev_rows_top(int nbatch, const int32_t* mask, yb_extent ek, void* g, int64_t stride_g, void* eh, int64_t stride_eh, double* zr, int64_t stride_zr,
+                     double* d, double* e, void* tau, int64_t stride_vec, int32_t* meta, int32_t* status, int max_k, int top, int32_t* order,
+                     double* dsorted, int32_t* ntop, void* stream);
+int yb_svd_finalize_top(int nbatch, const int32_t* mask, int32_t* meta, int trunc_mode, double threshold, int max_bond, int min_keep, int dist,
+                        const void* w, int64_t stride_w, const void* q, int64_t stride_q, double* sval, int64_t stride_s, int32_t* keep,
+                        int32_t keep_stride, void* uout, int64_t stride_u, void* vout, int64_t stride_v, int32_t* status, int max_k,
+                        const double* lam, int64_t stride_lam, int top, void* stream);
 /* Second level of the Gram route: yb_svd_select lists, per trajectory, the rows of the rotated work matrix whose squared
  * norm is below tau_rel * max (sel_n[b] rows, indices in sel_idx[b][0..max_k)); yb_svd_gather copies those rows of (w, q)
  * into the compact blocks (ws, qs) (dir = 0) or back (dir = 1).  Between the two the caller re-diagonalises the block with

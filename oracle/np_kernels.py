@@ -139,6 +139,11 @@ class NumpyKernels:
                 Qa = _view(a, t, x0 * x0).reshape(x0, x0)
                 W = _view(b, t, x0 * x1).reshape(x0, x1)
                 _view(c, t, x0 * x1)[:] = (Qa @ W).reshape(-1)
+            elif op == 11:   # ROTATE_TOP: Wf[c] = Etop[c] W for the x2 compact eigenvector rows
+                nr = min(x2, x0)
+                Qa = _view(a, t, nr * x0).reshape(nr, x0)
+                W = _view(b, t, x0 * x1).reshape(x0, x1)
+                _view(c, t, nr * x1)[:] = (Qa @ W).reshape(-1)
             else:
                 raise ValueError(op)
 
@@ -399,6 +404,63 @@ class NumpyKernels:
             _np(d)[t * stride_vec: t * stride_vec + k] = lam
             if mt is not None:
                 mt[t, 5] = 1
+
+    def heev_rows_top(self, nbatch, mask, ek, g, eh, zr, stride_zr, d, e, tau, stride_vec, meta, status, max_k, top, order, dsorted, ntop):
+        """Twin of yb_heev_rows_top: eigenvector rows of the `top` largest eigenvalues (compact, descending), the descending spectrum."""
+        self._launches += 4
+        mt = _np(meta).reshape(-1, SVD_META) if meta is not None else None
+        for t in range(nbatch):
+            if not _on(mask, t):
+                continue
+            k = _ext(ek, t)
+            G = _view(g, t, k * k).reshape(k, k)
+            lam, vec = np.linalg.eigh(0.5 * (G + G.conj().T))
+            idx = np.argsort(-lam, kind="stable")
+            nt = min(k, top)
+            _view(eh, t, nt * k)[:] = np.ascontiguousarray(vec[:, idx[:nt]].conj().T).reshape(-1)
+            _np(d)[t * stride_vec: t * stride_vec + k] = lam
+            _np(order)[t * stride_vec: t * stride_vec + k] = idx
+            _np(dsorted)[t * stride_vec: t * stride_vec + k] = lam[idx]
+            _np(ntop)[t] = nt
+            if mt is not None:
+                mt[t, 5] = 1
+
+    def svd_finalize_top(self, nbatch, mask, meta, trunc_mode, threshold, max_bond, min_keep, dist, w, q, sval, stride_s, keep, uout, vout, status, max_k,
+                         lam, stride_lam, top):
+        """Twin of yb_svd_finalize_top: the kept factors from the compact top block (w = Etop W, q = Etop), the singular values behind
+        it from the Gram eigenvalues."""
+        self._launches += 1
+        mt = _np(meta).reshape(-1, SVD_META)
+        for t in range(nbatch):
+            if not _on(mask, t):
+                continue
+            k, ln, orient, rows, cols = (int(v) for v in mt[t, :5])
+            nt = min(k, top)
+            Wf = _view(w, t, nt * ln).reshape(nt, ln)
+            Q = _view(q, t, nt * k).reshape(nt, k)
+            sig = np.sqrt((np.abs(Wf) ** 2).sum(axis=1))
+            perm = np.argsort(-sig, kind="stable")
+            tail = np.sqrt(np.maximum(_np(lam)[t * stride_lam + nt: t * stride_lam + k], 0.0))
+            s = np.concatenate([sig[perm], tail])
+            nsv = min(k, rows, cols)
+            kp = oracle_truncate(s[:nsv], _TRUNC_NAMES[trunc_mode], threshold, max_bond if max_bond > 0 else None, min_keep)
+            assert kp <= nt
+            _np(sval)[t * stride_s: t * stride_s + k] = s
+            _np(keep.tensor)[keep.offset + t * keep.stride] = kp
+            sk = s[:kp]
+            f = {0: sk, 1: np.ones(kp), 2: np.sqrt(sk)}[dist]            # factor on U
+            gq = {0: np.ones(kp), 1: sk, 2: np.sqrt(sk)}[dist]           # factor on Vh
+            with np.errstate(all="ignore"):
+                inv = np.where(sk > 0, 1.0 / np.where(sk > 0, sk, 1.0), 0.0)
+            Qk, Wk = Q[perm[:kp]], Wf[perm[:kp]]
+            if orient == 0:      # W = M: U[:, c] = conj(Q[c]) f, Vh[c] = Wf[c] g / sigma
+                u = Qk.conj().T * f
+                vh = Wk * (gq * inv)[:, None]
+            else:                # W = M^H: U[:, c] = conj(Wf[c]) f / sigma, Vh[c] = Q[c] g
+                u = Wk.conj().T * (f * inv)
+                vh = Qk * gq[:, None]
+            _view(uout, t, rows * kp)[:] = np.ascontiguousarray(u).reshape(-1)
+            _view(vout, t, kp * cols)[:] = np.ascontiguousarray(vh).reshape(-1)
 
     # -- truncation-free gauge shifts by Cholesky-QR (twin of csrc/yb_cholqr.cuh: same certificate, same outputs) ---------
     def cholqr_factor(self, nbatch, mask, meta, g, linv, threshold, flag, n_flag, max_k):

@@ -33,6 +33,17 @@ def test_engine_with_twin_gram_and_cholqr_routes(golden_dir, name):
     check_against_golden(name, golden_dir, results, diag, log, traj)
 
 
+@pytest.mark.parametrize("name", ["heis8_c2_order2", "ising10_c1_order2"])
+def test_engine_with_twin_capped_split_keeps_top_rows_only(golden_dir, name):
+    """Capped splits on the Gram route back-transform only the eigenvector rows they can keep (yb_heev_rows_top / ROTATE_TOP /
+    yb_svd_finalize_top): same jumps, identical bonds, observables <= 1e-10 against the unmodified reference."""
+    eng, tu, su, traj = engine_for_case(name, NumpyKernels(), gram_min_k=0)
+    log = []
+    results, diag = eng.run(tu, su, log)
+    assert eng.stats["heev_top_calls"] > 0
+    check_against_golden(name, golden_dir, results, diag, log, traj)
+
+
 from oracle.golden_cases import DIGITAL_CASES  # noqa: E402
 from tests.helpers import digital_engine_for_case  # noqa: E402
 

@@ -773,5 +773,76 @@ def test_cholqr_gauge_shift_matches_twin_and_is_exact(backends, mode, dist):
         G = (M.conj().T @ M) if mode == K.SVD_ROWS else (M @ M.conj().T)
         Li = np.linalg.inv(np.linalg.cholesky(G))
         got = lg[t, : kb * kb].reshape(kb, kb)
-        assert np.max(np.abs(got - Li)) <= 1e-9 * np.max(np.abs(Li)), (t, kind)
+        assert np.max(np.abs(got @ np.linalg.cholesky(G) - np.eye(kb))) < 1e-7, (t, kind)      # graded spectra: cond(L) ~ 1e4
         assert not np.triu(got, 1).any()
+
+
+@pytest.mark.parametrize("ks,top", [([1, 2, 3, 5, 33], 4), ([16, 17, 31, 32, 34], 16), ([64, 130, 17, 128], 64), ([256, 200, 255], 128), ([512, 300], 256)])
+def test_heev_rows_top_and_capped_finalize(backends, ks, top):
+    """yb_heev_rows_top -> ROTATE_TOP -> yb_svd_finalize_top (the capped split of the Gram route): the compact block holds the
+    eigenvector rows of the `top` largest eigenvalues in descending order; a capped truncation of W = random k x len matrices through
+    that block gives LAPACK's singular values, its keep count, an isometric U and U (S Vh) = the best rank-keep approximation."""
+    cuda, _ = backends
+    dev = "cuda"
+    rng = np.random.default_rng(sum(ks) + top)
+    nb, kmax = len(ks), max(ks)
+    sq = kmax * kmax
+    mats = []
+    for i, k in enumerate(ks):
+        a = rng.standard_normal((k, k)) + 1j * rng.standard_normal((k, k))
+        u, _, vh = np.linalg.svd(a)
+        sv = np.logspace(0, -5 if i % 2 else -2, k)
+        mats.append((u * sv) @ vh)
+    ek = torch.tensor(ks, dtype=torch.int32, device=dev)
+    w = torch.zeros(nb * sq, dtype=torch.complex128, device=dev)
+    meta = torch.zeros(nb * 8, dtype=torch.int32, device=dev)
+    for t, (k, m) in enumerate(zip(ks, mats)):
+        w[t * sq: t * sq + k * k] = torch.from_numpy(np.ascontiguousarray(m).reshape(-1)).to(dev)
+        meta[t * 8: t * 8 + 8] = torch.tensor([k, k, 0, k, k, 0, 0, 0], dtype=torch.int32)        # W = M (orient 0), rows = cols = k
+    g = torch.zeros(nb * sq, dtype=torch.complex128, device=dev)
+    eh = torch.full((nb * sq,), 3.0 + 0j, dtype=torch.complex128, device=dev)
+    wf = torch.zeros(nb * sq, dtype=torch.complex128, device=dev)
+    zr = torch.zeros(nb * sq, dtype=torch.float64, device=dev)
+    d = torch.zeros(nb * kmax, dtype=torch.float64, device=dev)
+    e = torch.zeros(nb * kmax, dtype=torch.float64, device=dev)
+    ds = torch.zeros(nb * kmax, dtype=torch.float64, device=dev)
+    order = torch.zeros(nb * kmax, dtype=torch.int32, device=dev)
+    ntop = torch.zeros(nb, dtype=torch.int32, device=dev)
+    tau = torch.zeros(nb * kmax, dtype=torch.complex128, device=dev)
+    status = torch.zeros(nb, dtype=torch.int32, device=dev)
+    keep = torch.zeros(nb, dtype=torch.int32, device=dev)
+    sval = torch.zeros(nb * kmax, dtype=torch.float64, device=dev)
+    uo = torch.zeros(nb * sq, dtype=torch.complex128, device=dev)
+    vo = torch.zeros(nb * sq, dtype=torch.complex128, device=dev)
+    X = Ext(ek, 0, 1)
+    cuda.gemm(K.OP_GRAM, nb, 1, None, X, X, None, 1, 1, 1, Buf(w, 0, sq), Buf(w, 0, sq), Buf(g, 0, sq), 0, kmax, kmax)
+    cuda.heev_rows_top(nb, None, X, Buf(g, 0, sq), Buf(eh, 0, sq), zr, sq, d, e, tau, kmax, meta, status, kmax, top, order, ds, ntop)
+    cuda.gemm(K.OP_ROTATE_TOP, nb, 1, None, X, X, Ext(ntop, 0, 1), 1, 1, 1, Buf(eh, 0, sq), Buf(w, 0, sq), Buf(wf, 0, sq), 0, min(kmax, top), kmax)
+    thr = 1e-7
+    cuda.svd_finalize_top(nb, None, meta, 0, thr, top, 1, 1, Buf(wf, 0, sq), Buf(eh, 0, sq), sval, kmax, Ext(keep, 0, 1), Buf(uo, 0, sq), Buf(vo, 0, sq),
+                          status, kmax, ds, kmax, top)
+    torch.cuda.synchronize()
+    assert not status.cpu().numpy().any()
+    from oracle.tjm_oracle import truncate
+    for t, k in enumerate(ks):
+        m = mats[t]
+        nt = min(k, top)
+        assert int(ntop[t]) == nt
+        G = m @ m.conj().T
+        lam = np.linalg.eigvalsh(G)[::-1]
+        scale = lam[0]
+        assert np.max(np.abs(ds.cpu().numpy()[t * kmax: t * kmax + k] - lam)) < 1e-13 * scale * max(1, k / 16)
+        E = eh.cpu().numpy()[t * sq: t * sq + nt * k].reshape(nt, k).conj().T       # columns = top eigenvectors, descending
+        assert np.max(np.abs(E.conj().T @ E - np.eye(nt))) < 1e-12 * max(1, k / 16)
+        assert np.max(np.abs(G @ E - E * lam[None, :nt])) < 2e-13 * scale * max(1, k / 16)
+        u_ref, s_ref, vh_ref = np.linalg.svd(m)
+        kp = truncate(s_ref, "discarded_weight", thr, top, 1)
+        assert int(keep[t]) == kp, (t, k, int(keep[t]), kp)
+        got_s = sval.cpu().numpy()[t * kmax: t * kmax + k]
+        assert np.max(np.abs(got_s[:nt] - s_ref[:nt])) < 1e-12
+        assert nt == k or np.max(np.abs(got_s[nt:] ** 2 - s_ref[nt:] ** 2)) < 1e-12
+        U = uo.cpu().numpy()[t * sq: t * sq + k * kp].reshape(k, kp)
+        V = vo.cpu().numpy()[t * sq: t * sq + kp * k].reshape(kp, k)
+        assert np.max(np.abs(U.conj().T @ U - np.eye(kp))) < 1e-12 * max(1, k / 16)
+        best = (u_ref[:, :kp] * s_ref[:kp]) @ vh_ref[:kp]
+        assert np.max(np.abs(U @ V - best)) < 1e-10

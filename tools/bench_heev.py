@@ -30,7 +30,10 @@ def main():
         status = torch.zeros(nb, dtype=torch.int32, device=dev)
         ext = Ext(ek, 0, 1)
         res = {}
-        for name in ("round1", "rows"):
+        order = torch.zeros(nb * k, dtype=torch.int32, device=dev)
+        ds = torch.zeros(nb * k, dtype=torch.float64, device=dev)
+        ntop = torch.zeros(nb, dtype=torch.int32, device=dev)
+        for name in ("round1", "rows", "rows_top"):
             for rep in range(3):
                 g.copy_(g0)
                 torch.cuda.synchronize()
@@ -39,11 +42,19 @@ def main():
                 if name == "round1":
                     kern.heev(nb, None, ext, Buf(g, 0, sq), Buf(qh, 0, sq), Buf(zt, 0, sq), zr, sq, d, e, tau, k, meta, status, k)
                     kern.gemm(K.OP_EVEC, nb, 1, None, ext, None, None, 1, 1, 1, Buf(zt, 0, sq), Buf(qh, 0, sq), Buf(qa, 0, sq), 0, k, k)
+                elif name == "rows_top":                       # capped split: only the k / 2 rows it can keep are back-transformed
+                    kern.heev_rows_top(nb, None, ext, Buf(g, 0, sq), Buf(eh, 0, sq), zr, sq, d, e, tau, k, meta, status, k, k // 2, order, ds, ntop)
                 else:
                     kern.heev_rows(nb, None, ext, Buf(g, 0, sq), Buf(eh, 0, sq), zr, sq, d, e, tau, k, meta, status, k)
                 e1.record()
                 torch.cuda.synchronize()
                 res[name + "_ms"] = e0.elapsed_time(e1)
+            if name == "rows_top":
+                lam = ds[: k // 2].cpu().numpy().copy()
+                E = eh[: (k // 2) * k].view(k // 2, k).cpu().numpy().conj().T
+                gm = g0[:sq].view(k, k).cpu().numpy()
+                res[name + "_resid"] = float(np.abs(gm @ E - E * lam[None, :]).max() / np.abs(lam).max())
+                continue
             lam = d[:k].cpu().numpy().copy()
             E = (qa if name == "round1" else eh)[:sq].view(k, k).cpu().numpy().conj().T
             gm = g0[:sq].view(k, k).cpu().numpy()

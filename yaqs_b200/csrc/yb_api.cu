@@ -237,6 +237,20 @@ int yb_svd_finalize(int nbatch, const int32_t* mask, int32_t* meta, int trunc_mo
     return done("yb_svd_finalize");
 }
 
+int yb_svd_finalize_top(int nbatch, const int32_t* mask, int32_t* meta, int trunc_mode, double threshold, int max_bond, int min_keep, int dist,
+                        const void* w, int64_t stride_w, const void* q, int64_t stride_q, double* sval, int64_t stride_s, int32_t* keep,
+                        int32_t keep_stride, void* uout, int64_t stride_u, void* vout, int64_t stride_v, int32_t* status, int max_k,
+                        const double* lam, int64_t stride_lam, int top, void* stream) {
+    if (nbatch <= 0) return 0;
+    if (max_k > 1024) return fail_msg("yb_svd_finalize_top: max_k > 1024 unsupported");
+    if (top <= 0 || !lam) return fail_msg("yb_svd_finalize_top: needs the sorted eigenvalues and top > 0");
+    if (max_bond <= 0 || max_bond > top) return fail_msg("yb_svd_finalize_top: the split must be capped at max_bond <= top");
+    k_svd_finalize<<<nbatch, 512, 0, (cudaStream_t)stream>>>(trunc_mode, threshold, max_bond, min_keep, dist, (const cplx*)w, stride_w, (const cplx*)q,
+                                                              stride_q, meta, sval, stride_s, keep, keep_stride, (cplx*)uout, stride_u, (cplx*)vout,
+                                                              stride_v, status, mask, lam, stride_lam, top);
+    return done("yb_svd_finalize_top");
+}
+
 int yb_svd_ambiguous(int nbatch, const int32_t* mask, const int32_t* meta, const double* sval, int64_t stride_s, int trunc_mode, double threshold,
                      int two_level, double tau_rel, double noise_rel, const int32_t* status, int32_t* amb, int32_t* n_amb, void* stream) {
     if (nbatch <= 0) return 0;
@@ -339,9 +353,30 @@ int yb_heev(int nbatch, const int32_t* mask, yb_extent ek, void* g, int64_t stri
 }
 
 // Round-2 eigen-solver: blocked tridiagonalisation, divide & conquer, eigenvector rows straight from the reflectors (yb_hetrd.cuh).
+static int heev_rows_impl(int nbatch, const int32_t* mask, yb_extent ek, void* g, int64_t stride_g, void* eh, int64_t stride_eh, double* zr,
+                          int64_t stride_zr, double* d, double* e, void* tau, int64_t stride_vec, int32_t* meta, int32_t* status, int max_k, int top,
+                          int32_t* order, double* dsorted, int32_t* ntop, void* stream);
+
 int yb_heev_rows(int nbatch, const int32_t* mask, yb_extent ek, void* g, int64_t stride_g, void* eh, int64_t stride_eh, double* zr, int64_t stride_zr,
                  double* d, double* e, void* tau, int64_t stride_vec, int32_t* meta, int32_t* status, int max_k, void* stream) {
+    return heev_rows_impl(nbatch, mask, ek, g, stride_g, eh, stride_eh, zr, stride_zr, d, e, tau, stride_vec, meta, status, max_k, 0, nullptr, nullptr,
+                          nullptr, stream);
+}
+
+int yb_heev_rows_top(int nbatch, const int32_t* mask, yb_extent ek, void* g, int64_t stride_g, void* eh, int64_t stride_eh, double* zr, int64_t stride_zr,
+                     double* d, double* e, void* tau, int64_t stride_vec, int32_t* meta, int32_t* status, int max_k, int top, int32_t* order,
+                     double* dsorted, int32_t* ntop, void* stream) {
+    if (top <= 0 || !order || !dsorted || !ntop) return fail_msg("yb_heev_rows_top: needs top > 0 and the order / dsorted / ntop outputs");
+    return heev_rows_impl(nbatch, mask, ek, g, stride_g, eh, stride_eh, zr, stride_zr, d, e, tau, stride_vec, meta, status, max_k, top, order, dsorted,
+                          ntop, stream);
+}
+
+static int heev_rows_impl(int nbatch, const int32_t* mask, yb_extent ek, void* g, int64_t stride_g, void* eh, int64_t stride_eh, double* zr,
+                          int64_t stride_zr, double* d, double* e, void* tau, int64_t stride_vec, int32_t* meta, int32_t* status, int max_k, int top,
+                          int32_t* order, double* dsorted, int32_t* ntop, void* stream) {
     if (nbatch <= 0) return 0;
+    const int expand = top > 0 ? 0 : 1;
+    const double* srcR = top > 0 ? zr : nullptr;
     if (max_k > heev::KMAX) return fail_msg("yb_heev_rows: max_k > 512 unsupported");
     if (g == eh) return fail_msg("yb_heev_rows: the eigenvector rows must not alias the input matrix (it keeps the reflectors)");
     cudaStream_t st = (cudaStream_t)stream;
@@ -368,26 +403,30 @@ int yb_heev_rows(int nbatch, const int32_t* mask, yb_extent ek, void* g, int64_t
     if (int rc = done("yb_heev_rows(hetrd)")) return rc;
     if (max_k <= 128)
         heev::k_stedc<128><<<nbatch, stedc::THREADS, sizeof(stedc::Smem<128>), st>>>(d, e, stride_vec, zr, stride_zr, (cplx*)eh, stride_eh, ek.ptr, ek.stride,
-                                                                                  meta, status, mask);
+                                                                                  meta, status, mask, expand);
     else if (max_k <= 256)
         heev::k_stedc<256><<<nbatch, stedc::THREADS, sizeof(stedc::Smem<256>), st>>>(d, e, stride_vec, zr, stride_zr, (cplx*)eh, stride_eh, ek.ptr, ek.stride,
-                                                                                  meta, status, mask);
+                                                                                  meta, status, mask, expand);
     else
         heev::k_stedc<512><<<nbatch, stedc::THREADS, sizeof(stedc::Smem<512>), st>>>(d, e, stride_vec, zr, stride_zr, (cplx*)eh, stride_eh, ek.ptr, ek.stride,
-                                                                                  meta, status, mask);
+                                                                                  meta, status, mask, expand);
     if (int rc = done("yb_heev_rows(stedc)")) return rc;
+    if (top > 0) {
+        heev::k_heev_order<<<nbatch, 512, 0, st>>>(d, stride_vec, ek.ptr, ek.stride, top, order, dsorted, ntop, mask);
+        if (int rc = done("yb_heev_rows_top(order)")) return rc;
+    }
     if (max_k <= 128) {
         const int pb = 32;
         hetrd::k_ormtr_rows<4><<<nbatch, hetrd::THREADS, (size_t)(pb * 128 + pb) * sizeof(cplx), st>>>((const cplx*)g, stride_g, (const cplx*)tau, stride_vec,
-                                                                                                    (cplx*)eh, stride_eh, ek.ptr, ek.stride, pb, mask);
+                                                                                                    (cplx*)eh, stride_eh, ek.ptr, ek.stride, pb, mask, srcR, stride_zr, order, stride_vec, top);
     } else if (max_k <= 256) {
         const int pb = 32;
         hetrd::k_ormtr_rows<8><<<nbatch, hetrd::THREADS, (size_t)(pb * 256 + pb) * sizeof(cplx), st>>>((const cplx*)g, stride_g, (const cplx*)tau, stride_vec,
-                                                                                                    (cplx*)eh, stride_eh, ek.ptr, ek.stride, pb, mask);
+                                                                                                    (cplx*)eh, stride_eh, ek.ptr, ek.stride, pb, mask, srcR, stride_zr, order, stride_vec, top);
     } else {
         const int pb = 16;
         hetrd::k_ormtr_rows<16><<<nbatch, hetrd::THREADS, (size_t)(pb * 512 + pb) * sizeof(cplx), st>>>((const cplx*)g, stride_g, (const cplx*)tau, stride_vec,
-                                                                                                     (cplx*)eh, stride_eh, ek.ptr, ek.stride, pb, mask);
+                                                                                                     (cplx*)eh, stride_eh, ek.ptr, ek.stride, pb, mask, srcR, stride_zr, order, stride_vec, top);
     }
     return done("yb_heev_rows(ormtr)");
 }

@@ -64,7 +64,8 @@ enum YbGemmOp {
     YB_OP_GRAM = 8,        // G[i,j]            = sum_e W[i,e] conj(W[j,e])                         x0 = k, x1 = len
     YB_OP_EVEC = 9,        // Qacc[c,j]         = sum_i Zt[c,i] conj(Qh[j,i])   (rows = conj eigenvectors)   x0 = k
     YB_OP_ROTATE = 10,     // Wf[c,e]           = sum_j Qacc[c,j] W[j,e]                            x0 = k, x1 = len
-    YB_OP_LAST = 10,
+    YB_OP_ROTATE_TOP = 11, // Wf[c,e]           = sum_j Etop[c,j] W[j,e], c < x2 (the eigenvector rows a capped split can keep)   x0 = k, x1 = len, x2 = rows
+    YB_OP_LAST = 11,
 };
 
 struct YbGemmParams {

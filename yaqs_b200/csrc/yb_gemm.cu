@@ -108,6 +108,12 @@ __device__ __forceinline__ bool make_desc(const YbGemmParams& P, int b, int g, D
         d.B = B; d.b_rs = x1;
         d.C = C; d.c_rs = x1;
     } break;
+    case YB_OP_ROTATE_TOP: {          // x0 = k, x1 = len, x2 = rows of the compact eigenvector block
+        d.M = min(x2, x0); d.K = x0; d.N = x1;
+        d.A = A; d.a_rs = x0;
+        d.B = B; d.b_rs = x1;
+        d.C = C; d.c_rs = x1;
+    } break;
     default: return false;
     }
     if (P.conj_extra) d.conjB = !d.conjB;

@@ -463,7 +463,7 @@ __global__ void __launch_bounds__(NT + 32) k_steqr(double* dio, const double* ei
 // real work matrices of the merge tree.
 template <int KM>
 __global__ void __launch_bounds__(stedc::THREADS, 2) k_stedc(double* dio, const double* ein, long long s_vec, double* ZR, long long sZR, cplx* Zt,
-                                                              long long sZ, const int* ek, int esk, int* meta, int* status, const int* mask) {
+                                                              long long sZ, const int* ek, int esk, int* meta, int* status, const int* mask, int expand = 1) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int b = blockIdx.x;
     if (mask && !mask[b]) return;
@@ -487,7 +487,7 @@ __global__ void __launch_bounds__(stedc::THREADS, 2) k_stedc(double* dio, const 
         for (; x < kk; x += nthr) QA[x] = QB[x];
         __syncthreads();
     }
-    {
+    if (expand) {                        // (the "top" mode of yb_heev_rows_top gathers the rows it needs from QA itself)
         long long x = tid;
         for (; x + 3LL * nthr < kk; x += 4LL * nthr) {
             const double a0 = QA[x], a1 = QA[x + nthr], a2 = QA[x + 2LL * nthr], a3 = QA[x + 3LL * nthr];
@@ -500,6 +500,27 @@ __global__ void __launch_bounds__(stedc::THREADS, 2) k_stedc(double* dio, const 
         if (meta) meta[b * 8 + 5] = fail ? 0 : 1;
         if (fail && status) atomicOr(&status[b], 1);
     }
+}
+
+// Descending order of the eigenvalues of one trajectory: order[rank] = index, dsorted[rank] = value, ntop = min(k, top).
+__global__ void __launch_bounds__(512) k_heev_order(const double* __restrict__ d, long long s_vec, const int* ek, int esk, int top, int* order,
+                                                     double* dsorted, int* ntop, const int* mask) {
+    __shared__ double ev[KMAX];
+    const int b = blockIdx.x;
+    if (mask && !mask[b]) return;
+    const int k = ek[(long long)b * esk];
+    if (k <= 0) { if (threadIdx.x == 0) ntop[b] = 0; return; }
+    const double* db = d + (long long)b * s_vec;
+    for (int i = threadIdx.x; i < k; i += blockDim.x) ev[i] = db[i];
+    __syncthreads();
+    for (int i = threadIdx.x; i < k; i += blockDim.x) {
+        const double vi = ev[i];
+        int rank = 0;
+        for (int j = 0; j < k; ++j) { const double vj = ev[j]; rank += (vj > vi) || (vj == vi && j < i) || (vj == vj && vi != vi); }     // NaN last
+        order[(long long)b * s_vec + rank] = i;
+        dsorted[(long long)b * s_vec + rank] = vi;
+    }
+    if (threadIdx.x == 0) ntop[b] = top > 0 ? min(k, top) : k;
 }
 
 }  // namespace heev

@@ -214,7 +214,9 @@ __global__ void __launch_bounds__(THREADS, 1) k_hetrd_blocked(cplx* G, long long
 // NE = ceil(nmax / 32) elements per lane.
 template <int NE>
 __global__ void __launch_bounds__(THREADS, 1) k_ormtr_rows(const cplx* __restrict__ G, long long sG, const cplx* __restrict__ tauin, long long s_vec,
-                                                           cplx* M, long long sM, const int* ek, int esk, int pb, const int* mask) {
+                                                           cplx* M, long long sM, const int* ek, int esk, int pb, const int* mask,
+                                                           const double* __restrict__ srcR = nullptr, long long sR = 0, const int* __restrict__ order = nullptr,
+                                                           long long s_ord = 0, int top = 0) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int b = blockIdx.x;
     if (mask && !mask[b]) return;
@@ -227,6 +229,19 @@ __global__ void __launch_bounds__(THREADS, 1) k_ormtr_rows(const cplx* __restric
     cplx* Mb = M + (long long)b * sM;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int LD = NE * 32;
+    // "top" mode (a split capped at max_bond < n can only keep the eigenvectors of the `top` largest eigenvalues): the rows order[0 ..
+    // nrows) of the REAL eigenvector matrix of the tridiagonal (srcR, row c = eigenvector c) are gathered into rows 0 .. nrows of M and
+    // only those are back-transformed -- half the reflector applications at chi = 128 of 2 chi = 256
+    const int nrows = (srcR && top > 0) ? min(n, top) : n;
+    if (srcR) {
+        const double* Rb = srcR + (long long)b * sR;
+        const int* ord = order + (long long)b * s_ord;
+        for (int x = tid; x < nrows * n; x += THREADS) {
+            const int c = x / n, e = x - c * n;
+            Mb[x] = make_double2(Rb[(long long)ord[c] * n + e], 0.0);
+        }
+        __syncthreads();
+    }
     for (int jhi = n - 2; jhi >= 0; jhi -= pb) {
         const int jlo = max(0, jhi - pb + 1), cnt = jhi - jlo + 1;
         __syncthreads();                                    // previous panel fully consumed
@@ -242,8 +257,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_ormtr_rows(const cplx* __restric
         // profiles/r02_ncu_heev_rows_v1.json)
         constexpr bool PAIR = NE <= 8;                      // 16 elements per lane (k > 256): two rows would not fit in 128 registers
         constexpr int RPW = PAIR ? 2 : 1;
-        for (int c = RPW * warp; c < n; c += RPW * NWARPS) {
-            const bool two = PAIR && (c + 1 < n);
+        for (int c = RPW * warp; c < nrows; c += RPW * NWARPS) {
+            const bool two = PAIR && (c + 1 < nrows);
             cplx ra[NE], rb[NE];
             cplx* mrow_a = Mb + (long long)c * n;
             cplx* mrow_b = mrow_a + n;

@@ -248,7 +248,8 @@ __device__ int truncate_keep(const double* s, int n, int mode, double threshold,
 __global__ void __launch_bounds__(512) k_svd_finalize(int trunc_mode, double threshold, int max_bond, int min_keep, int dist, const cplx* __restrict__ w,
                                                        long long s_w, const cplx* __restrict__ q, long long s_q, int* meta, double* sval,
                                                        long long s_s, int* keep_out, int keep_stride, cplx* uout, long long s_u, cplx* vout,
-                                                       long long s_v, int* status, const int* mask) {
+                                                       long long s_v, int* status, const int* mask, const double* __restrict__ lam = nullptr,
+                                                       long long s_lam = 0, int top = 0) {
     __shared__ double sig[SVD_KMAX];
     __shared__ double ssort[SVD_KMAX];
     __shared__ int perm[SVD_KMAX];
@@ -262,17 +263,25 @@ __global__ void __launch_bounds__(512) k_svd_finalize(int trunc_mode, double thr
     const cplx* wb = w + (long long)b * s_w;
     const cplx* qb = q + (long long)b * s_q;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
-    for (int i = warp; i < k; i += nwarps) {
+    // "top" mode of the Gram route (yb_heev_rows_top): w / q hold only the rows of the `top` largest eigenvalues (all a split capped at
+    // max_bond <= top can keep); the singular values behind them -- needed for the discarded weight only -- are the square roots of the
+    // remaining Gram eigenvalues lam[ntop ..) (descending), accurate to the absolute level yb_svd_ambiguous already allows for
+    const int ntop = (lam && top > 0) ? min(k, top) : k;
+    for (int i = warp; i < ntop; i += nwarps) {
         double s = 0.0;
         for (int e = lane; e < len; e += 32) s += cabs2(wb[(long long)i * len + e]);
         s = warp_sum(s);
         if (lane == 0) sig[i] = sqrt(s);
     }
+    for (int i = ntop + tid; i < k; i += blockDim.x) sig[i] = sqrt(fmax(lam[(long long)b * s_lam + i], 0.0));
     __syncthreads();
     for (int i = tid; i < k; i += blockDim.x) {
         const double si = sig[i];
-        int rank = 0;
-        for (int j = 0; j < k; ++j) { const double sj = sig[j]; rank += (sj > si) || (sj == si && j < i); }
+        int rank = i;
+        if (i < ntop) {
+            rank = 0;
+            for (int j = 0; j < ntop; ++j) { const double sj = sig[j]; rank += (sj > si) || (sj == si && j < i); }
+        }
         perm[rank] = i; ssort[rank] = si;
     }
     __syncthreads();

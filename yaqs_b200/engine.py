@@ -22,7 +22,7 @@ import torch
 
 from .gates import GateLibrary
 from .kernels import (DIST, LANCZOS_PITCH, OP_ABSORB_L, OP_ABSORB_R, OP_ENVL1, OP_ENVL3, OP_ENVR3, OP_EVEC, OP_GRAM, OP_LCONTRACT, OP_MERGE,
-                      OP_RCONTRACT, OP_ROTATE, SVD_COLS, SVD_META, SVD_ORIENT_COLS, SVD_ORIENT_ROWS, SVD_ROWS, SVD_THETA, TRUNC_MODES, Buf, Ext)
+                      OP_RCONTRACT, OP_ROTATE, OP_ROTATE_TOP, SVD_COLS, SVD_META, SVD_ORIENT_COLS, SVD_ORIENT_ROWS, SVD_ROWS, SVD_THETA, TRUNC_MODES, Buf, Ext)
 
 C128 = torch.complex128
 KRYLOV_MAX = 25          # max_lanczos_iterations (matrix_exponential.py:37)
@@ -286,6 +286,8 @@ class BatchedTJM:
         self.heev_rows = os.environ.get("YB_HEEV_ROWS", "1") != "0"
         # keep-all gauge shifts by Cholesky-QR (round 2, second session); YB_CHOLQR=0 sends them through the eigen-solver (A/B runs)
         self.cholqr = os.environ.get("YB_CHOLQR", "1") != "0"
+        # capped splits back-transform only the eigenvector rows they can keep (yb_heev_rows_top); YB_HEEV_TOP=0 for A/B runs
+        self.heev_top = os.environ.get("YB_HEEV_TOP", "1") != "0"
         self.use_gram = sd >= gram_min_k and sd <= 512
         if self.use_gram:
             self.heev_g = torch.zeros(B * sd * sd, dtype=C128, device=dev)
@@ -300,6 +302,9 @@ class BatchedTJM:
             self.sel_idx = torch.zeros(B * sd, dtype=torch.int32, device=dev)
             self.status_scratch = torch.zeros(B, dtype=torch.int32, device=dev)
             self.amb = torch.zeros(B, dtype=torch.int32, device=dev)
+            self.heev_order = torch.zeros(B * sd, dtype=torch.int32, device=dev)
+            self.heev_ds = torch.zeros(B * sd, dtype=torch.float64, device=dev)
+            self.heev_ntop = torch.zeros(B, dtype=torch.int32, device=dev)
         # noise tables
         self._noise_cache: dict = {}
         self._set_noise(self._make_noise_ctx(noise))
@@ -308,7 +313,7 @@ class BatchedTJM:
         self.observables = [(m if isinstance(m, str) else np.asarray(m, dtype=np.complex128), tuple(int(s) for s in sites)) for m, sites in observables]
         self._ones_i32 = torch.ones(B, dtype=torch.int32, device=dev)
         self.stats = {"krylov_calls": 0, "matvecs": 0, "matvecs_2site": 0, "svd_calls": 0, "svd_sweeps": 0, "jumps": 0, "gram_svd_calls": 0, "gram_fallbacks": 0, "cholqr_calls": 0,
-                      "cholqr_fallbacks": 0}
+                      "cholqr_fallbacks": 0, "heev_top_calls": 0}
 
     # ------------------------------------------------------------------------------------------------------------------
     # operator / noise contexts (one each on the analog path; per gate on the digital path)
@@ -586,6 +591,25 @@ class BatchedTJM:
         K.gemm(OP_GRAM, B, 1, mask, ek, eln, None, 1, 1, 1, w, w, g, 0, sd, sd)
         self.status_scratch.zero_()
         kdim = sd if dims is None else max(1, min(sd, min(dims) if mode != SVD_THETA else (dims[0] if dist == "right" else dims[1])))      # bound of k = rows of W
+        # a split capped at max_bond < k can only keep the eigenvectors of the max_bond largest Gram eigenvalues: back-transform and
+        # rotate only those rows; the singular values behind them (discarded weight) come from the eigenvalues (yb_heev_rows_top)
+        top = mb if (self.heev_rows and self.heev_top and mode == SVD_THETA and 0 < mb < kdim and not (0.0 < thr < 1e-7)) else 0
+        if top:
+            K.heev_rows_top(B, mask, ek, g, q, self.heev_zr, sq, self.heev_d, self.heev_e, self.heev_tau, sd, self.svd_meta, self.status_scratch, kdim,
+                            top, self.heev_order, self.heev_ds, self.heev_ntop)
+            K.gemm(OP_ROTATE_TOP, B, 1, mask, ek, eln, Ext(self.heev_ntop, 0, 1), 1, 1, 1, q, w, g, 0, min(sd, top), sd)
+            K.svd_finalize_top(B, mask, self.svd_meta, tm, thr, mb, mk, DIST[dist], g, q, self.svd_s, sd, Ext(self.keep, 0, 1),
+                               self._buf(self.svd_u, sq), self._buf(self.svd_v, sq), self.status_scratch, sd, self.heev_ds, sd, top)
+            self.stats["gram_svd_calls"] += 1
+            self.stats["heev_top_calls"] += 1
+            self.counter.zero_()
+            K.svd_ambiguous(B, mask, self.svd_meta, self.svd_s, sd, tm, thr, False, self.GRAM_TAU, 16.0 * sd * 2.220446049250313e-16,
+                            self.status_scratch, self.amb, self.counter)
+            nfb = K.sync_int(self.counter)
+            if nfb > 0:
+                self.stats["gram_fallbacks"] += nfb
+                self._svd_jacobi(mode, src, el, er, trunc, dist, self.amb.clone(), dims)
+            return
         if self.heev_rows:                               # blocked tridiagonalisation, eigenvector rows straight from the reflectors
             K.heev_rows(B, mask, ek, g, q, self.heev_zr, sq, self.heev_d, self.heev_e, self.heev_tau, sd, self.svd_meta, self.status_scratch, kdim)
         else:
@@ -1252,6 +1276,11 @@ class BatchedTJM:
             tab["site_c"] = np.array([pr.sites[0] if pr.kind in ("adjacent", "pauli_adj") else -1 for pr in procs], dtype=np.int32)
             tab["ops_a"] = torch.from_numpy(np.stack([pr.ops[0] if pr.kind in ("one", "pauli_lr") else eye2 for pr in procs]).astype(np.complex128)).to(dev)
             tab["ops_b"] = torch.from_numpy(np.stack([pr.ops[1] if pr.kind == "pauli_lr" else eye2 for pr in procs]).astype(np.complex128)).to(dev)
+            # a unitary one-site operator (every Pauli) leaves its site a left isometry: no literal merge + split behind it
+            def unitary(m):
+                return bool(np.array_equal(m.conj().T @ m, np.eye(m.shape[0])))
+            tab["unitary_a"] = np.array([unitary(pr.ops[0]) if pr.kind in ("one", "pauli_lr") else True for pr in procs], dtype=bool)
+            tab["unitary_b"] = np.array([unitary(pr.ops[1]) if pr.kind == "pauli_lr" else True for pr in procs], dtype=bool)
             tab["ops_c"] = torch.from_numpy(np.stack([pr.ops[0] if pr.kind in ("adjacent", "pauli_adj") else eye4 for pr in procs]).astype(np.complex128)).to(dev)
             ctx["dev"] = tab
         return tab
@@ -1370,10 +1399,12 @@ class BatchedTJM:
         sa_h = np.where(jump_h, tab["site_a"][choice_h], -1).astype(np.int32)
         sb_h = np.where(jump_h, tab["site_b"][choice_h], -1).astype(np.int32)
         sc_h = np.where(jump_h, tab["site_c"][choice_h], -1).astype(np.int32)
-        # site whose left-isometry property a jump breaks: the site itself for one-site operators, the right site of a pair
+        # site whose left-isometry property a jump breaks: the site itself for one-site operators that are not unitary (a Pauli jump
+        # leaves A^dagger A = 1 untouched, so the reduced shift behind it is still the reference's merged SVD), the right site of a pair
         broken = np.zeros((n, B), dtype=bool)
-        for arr, off in ((sa_h, 0), (sb_h, 0), (sc_h, 1)):
-            rows = np.nonzero(arr >= 0)[0]
+        safe_choice = np.where(jump_h, choice_h, 0)
+        for arr, off, keeps in ((sa_h, 0, tab["unitary_a"][safe_choice]), (sb_h, 0, tab["unitary_b"][safe_choice]), (sc_h, 1, None)):
+            rows = np.nonzero((arr >= 0) if keeps is None else ((arr >= 0) & ~keeps))[0]
             broken[arr[rows] + off, rows] = True
         lit_h = np.zeros((n, B), dtype=np.int32)           # row i: trajectories that need the literal merge + split at bond i
         lit_h[1:] = (broken[:-1] & jump_h[None, :])

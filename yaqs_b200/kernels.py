@@ -15,7 +15,7 @@ import torch
 _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libyaqs_b200.so")
 
 # op codes of yb_gemm (csrc/yb_common.cuh)
-OP_RCONTRACT, OP_LCONTRACT, OP_ENVR3, OP_ENVL1, OP_ENVL3, OP_MERGE, OP_ABSORB_R, OP_ABSORB_L, OP_GRAM, OP_EVEC, OP_ROTATE = range(11)
+OP_RCONTRACT, OP_LCONTRACT, OP_ENVR3, OP_ENVL1, OP_ENVL3, OP_MERGE, OP_ABSORB_R, OP_ABSORB_L, OP_GRAM, OP_EVEC, OP_ROTATE, OP_ROTATE_TOP = range(12)
 # yb_svd_prepare modes
 SVD_THETA, SVD_ROWS, SVD_COLS = 0, 1, 2
 SVD_ORIENT_ROWS, SVD_ORIENT_COLS = 1 << 4, 2 << 4      # force W = M / W = M^H (Gram path)
@@ -85,7 +85,7 @@ def load_library() -> ctypes.CDLL:
 
 EXPORTED_SYMBOLS = [
     "yb_last_error", "yb_version", "yb_launch_count", "yb_set_flop_counter", "yb_set_option", "yb_workspace_bytes", "yb_gemm", "yb_rcontract_mpo", "yb_wapply", "yb_env_identity", "yb_lanczos_init",
-    "yb_lanczos_step", "yb_lanczos_combine", "yb_svd_prepare", "yb_svd_round", "yb_svd_check", "yb_svd_finalize", "yb_svd_ambiguous", "yb_heev", "yb_heev_rows", "yb_cholqr_factor", "yb_cholqr_refine", "yb_cholqr_finalize", "yb_svd_select", "yb_svd_gather",
+    "yb_lanczos_step", "yb_lanczos_combine", "yb_svd_prepare", "yb_svd_round", "yb_svd_check", "yb_svd_finalize", "yb_svd_ambiguous", "yb_heev", "yb_heev_rows", "yb_heev_rows_top", "yb_svd_finalize_top", "yb_cholqr_factor", "yb_cholqr_refine", "yb_cholqr_finalize", "yb_svd_select", "yb_svd_gather",
     "yb_unpack_vh", "yb_copy_packed", "yb_apply_local_op", "yb_mpo_site_apply", "yb_norm2", "yb_scale", "yb_local_rdm", "yb_philox_uniform",
 ]
 
@@ -258,6 +258,21 @@ class CudaKernels:
             nbatch, self._ptr(mask), self._ext(ek), self._cptr(g), ctypes.c_int64(g.stride), self._cptr(eh), ctypes.c_int64(eh.stride),
             self._ptr(zr), ctypes.c_int64(stride_zr), self._ptr(d), self._ptr(e), self._ptr(tau), ctypes.c_int64(stride_vec), self._ptr(meta),
             self._ptr(status), int(max_k), self._stream())), f"k{max_k}")
+
+    def heev_rows_top(self, nbatch, mask, ek: Ext, g: Buf, eh: Buf, zr: torch.Tensor, stride_zr, d, e, tau: torch.Tensor, stride_vec, meta, status, max_k,
+                      top, order, dsorted, ntop):
+        self._timed_call("heev", lambda: self._check(self.lib.yb_heev_rows_top(
+            nbatch, self._ptr(mask), self._ext(ek), self._cptr(g), ctypes.c_int64(g.stride), self._cptr(eh), ctypes.c_int64(eh.stride),
+            self._ptr(zr), ctypes.c_int64(stride_zr), self._ptr(d), self._ptr(e), self._ptr(tau), ctypes.c_int64(stride_vec), self._ptr(meta),
+            self._ptr(status), int(max_k), int(top), self._ptr(order), self._ptr(dsorted), self._ptr(ntop), self._stream())), f"k{max_k}top{top}")
+
+    def svd_finalize_top(self, nbatch, mask, meta, trunc_mode, threshold, max_bond, min_keep, dist, w: Buf, q: Buf, sval, stride_s, keep: Ext,
+                         uout: Buf, vout: Buf, status, max_k, lam, stride_lam, top):
+        self._timed_call("svd_misc", lambda: self._check(self.lib.yb_svd_finalize_top(
+            nbatch, self._ptr(mask), self._ptr(meta), trunc_mode, ctypes.c_double(threshold), int(max_bond), int(min_keep), dist,
+            self._cptr(w), ctypes.c_int64(w.stride), self._cptr(q), ctypes.c_int64(q.stride), self._ptr(sval), ctypes.c_int64(stride_s),
+            self._ptr(keep.tensor, 4 * keep.offset), keep.stride, self._cptr(uout), ctypes.c_int64(uout.stride), self._cptr(vout),
+            ctypes.c_int64(vout.stride), self._ptr(status), int(max_k), self._ptr(lam), ctypes.c_int64(stride_lam), int(top), self._stream())))
 
     # -- truncation-free gauge shifts by Cholesky-QR (csrc/yb_cholqr.cuh) ----------------------------------------------
     def cholqr_factor(self, nbatch, mask, meta, g: Buf, linv: Buf, threshold, flag, n_flag, max_k):
