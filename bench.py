@@ -3,7 +3,7 @@
 
     python bench.py --gpus N --steps K --warmup W              # our arm (torchrun launches one rank per GPU for N > 1)
     python bench.py --impl reference --gpus N --steps K --warmup W   # CPU arm: the oracle port on the host cores
-    python bench.py --workload C1|C2|C3|C5 ...                  # other BASELINE.json configs (C3 is the headline and the default)
+    python bench.py --workload C1|C2|C3|C4|C5 ...                  # other BASELINE.json configs (C3 is the headline and the default)
 
 Workload C3 = BASELINE.json configs[2]: transverse-field Ising chain L=100, chi_max=128, relaxation+dephasing (lowering +
 pauli_z, gamma=0.1 on every site), second-order TJM with Z on every site sampled every step, started from a seeded random MPS
@@ -46,12 +46,17 @@ WORKLOADS = {
                text="Heisenberg L=30, chi=64"),
     "C3": dict(model="ising", length=100, chi=128, noise=("lowering", "pauli_z"), gamma=0.1, batch=192, threshold=1e-6, bound="tensor",
                text="Ising L=100, chi=128"),
+    # BASELINE.json configs[3]: digital noisy Trotterized Ising circuit, 49 qubits, 2-qubit depolarizing noise as the 15 two-qubit Paulis
+    # per pair (9 crosstalk_ab per pair + pauli_x/y/z per site, tests/golden dig_ising49_c4_full); a step = one Trotter step of the circuit
+    "C4": dict(kind="digital", model="ising", length=49, chi=64, gamma=1e-3, batch=2048, threshold=1e-6, bound="hbm", text="digital Ising circuit, 49 qubits"),
     "C5": dict(model="heisenberg", length=200, chi=256, noise=("lowering", "pauli_z"), gamma=0.05, xx=0.01, batch=16, threshold=1e-6, bound="tensor",
                text="Heisenberg L=200, chi=256"),
 }
 
 
 def metric_name(wl: dict) -> str:
+    if wl.get("kind") == "digital":
+        return f"noisy-MPS trajectory-steps/s (digital Trotterized Ising circuit, {wl['length']} qubits, chi_max={wl['chi']}, digital TJM, one step = one Trotter step)"
     name = "Ising" if wl["model"] == "ising" else "Heisenberg"
     return f"noisy-MPS trajectory-steps/s ({name} L={wl['length']}, chi={wl['chi']}, order-2 TJM, sampled every step)"
 
@@ -303,6 +308,177 @@ def run_reference_arm(args):
 
 
 # ----------------------------------------------------------------------------------------------------------------------
+# digital workload (BASELINE.json configs[3])
+# ----------------------------------------------------------------------------------------------------------------------
+def digital_noise(wl: dict) -> list[dict]:
+    """2-qubit depolarizing noise of strength p = gamma per pair as the 15 two-qubit Paulis at p / 15 each: 9 crosstalk_ab per pair
+    plus the 6 single-qubit Paulis of the pair, i.e. pauli_x / y / z at 2 p / 15 per site (noise_model.py:52-60; fixture dig_ising49_c4_full)."""
+    L, p = wl["length"], wl["gamma"]
+    procs = [{"name": f"pauli_{a}", "sites": [i], "strength": 2.0 * p / 15.0} for i in range(L) for a in "xyz"]
+    procs += [{"name": f"crosstalk_{a}{b}", "sites": [i, i + 1], "strength": p / 15.0} for i in range(L - 1) for a in "xyz" for b in "xyz"]
+    return procs
+
+
+def digital_config(args, nranks, nsteps):
+    wl = args.wl
+    return {"workload": wl["name"], "model": None, "circuit": f"create_ising_circuit(L={wl['length']}, J=1, g=0.5, dt=0.1, timesteps={nsteps}), sampled after every Trotter step",
+            "length": wl["length"], "chi_max": wl["chi"], "noise": f"2-qubit depolarizing p={wl['gamma']} per pair (15 two-qubit Paulis at p/15)", "gate_mode": "mpo",
+            "svd_threshold": wl["threshold"], "observables": "Z on every qubit, every Trotter step", "initial_state": "|0...0>",
+            "batch_per_gpu": wl["batch"], "global_batch": wl["batch"] * nranks, "sharding": f"trajectories x{nranks}", "lanes_per_gpu": 1,
+            "l2_policy": "state of the batch exceeds L2 from the first Trotter steps on (2048 trajectories x 49 sites)"}
+
+
+def _cpu_digital(job):
+    """One trajectory of the oracle's digital_tjm over `nsteps` Trotter steps (the reference's per-trajectory worker)."""
+    wl, nsteps, traj = job
+    from threadpoolctl import threadpool_limits
+
+    from oracle import tjm_oracle as O
+    with threadpool_limits(1):
+        L = wl["length"]
+        layers = O.ising_trotter_layers(L, 1.0, 0.5, 0.1, nsteps, False, sample_each_step=True)
+        procs = [O.make_process(pr["name"], pr["sites"], pr["strength"]) for pr in digital_noise(wl)]
+        obs = [(O.OBSERVABLE_MATRICES["z"], [s]) for s in range(L)]
+        p = O.OracleParams(dt=1.0, n_steps=1, order=1, max_bond_dim=wl["chi"], svd_threshold=wl["threshold"], krylov_tol=1e-4, digital=True)
+        rng = O.UniformStream(O.trajectory_stream(42, traj))
+        t0 = time.perf_counter()
+        O.digital_tjm(O.product_state(L, "zeros"), layers, procs, p, obs, rng, sample_layers=True, gate_mode="mpo")
+        return time.perf_counter() - t0
+
+
+def cpu_digital_value(wl: dict, nsteps: int, cores: int, first_traj: int = 0) -> tuple[float, float]:
+    import multiprocessing as mp
+    t0 = time.perf_counter()
+    with mp.get_context("fork").Pool(cores) as pool:
+        pool.map(_cpu_digital, [(wl, nsteps, first_traj + t) for t in range(cores)])
+    wall = time.perf_counter() - t0
+    return cores * nsteps / wall, wall
+
+
+def run_reference_digital(args):
+    if int(os.environ.get("RANK", "0")) != 0:
+        return 0
+    wl = args.wl
+    cores = args.cpu_cores or os.cpu_count() or 1
+    nsteps = max(args.warmup, 0) + max(args.steps, 1)
+    value, wall = cpu_digital_value(wl, nsteps, cores)
+    emit({"impl": "reference", "metric": metric_name(wl), "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+          "ms_per_step": 1000.0 * wall / nsteps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "complex128 (f64)",
+          "data": "synthetic", "config": digital_config(args, 1, nsteps),
+          "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                           "sample": f"{cores} trajectories in parallel (fork pool, 1 BLAS thread each), each the first {nsteps} Trotter steps of the circuit"},
+          "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+    return 0
+
+
+def run_b200_digital(args):
+    """ONE call of the public API -- Simulator.run(State, circuit, DigitalSimParams(sample_layers=True), NoiseModel) on a circuit of W + K
+    Trotter steps; the engine's sample hook marks the end of every Trotter step (CUDA event + a device -> host read of that step's
+    observable column), `value` / `e2e` are the K steps after the first W by the device / wall clock."""
+    import torch
+    import torch.distributed as dist
+
+    from yaqs_b200 import DigitalSimParams, NoiseModel, Observable, Simulator, State, Z
+    from yaqs_b200.circuits import create_ising_circuit
+    from yaqs_b200.kernels import CudaKernels
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device(f"cuda:{local}")
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    wl = args.wl
+    L, B, K, W = wl["length"], wl["batch"], max(args.steps, 1), max(args.warmup, 0)
+    nsteps = W + K
+    line = {"metric": metric_name(wl), "value": None, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": None, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "complex128 (f64)", "data": "synthetic", "config": digital_config(args, world, nsteps)}
+    t_start = time.perf_counter()
+    try:
+        kern = CudaKernels(dev)
+        circ = create_ising_circuit(L, 1.0, 0.5, 0.1, nsteps, sample_every_step=True)
+        sp = DigitalSimParams(observables=[Observable(Z(), s) for s in range(L)], num_traj=B * world, max_bond_dim=wl["chi"], svd_threshold=wl["threshold"],
+                              sample_layers=True, random_seed=42, gate_mode="mpo")
+        sim = Simulator(show_progress=False, device=dev, kernels=kern, on_trajectory_error="flag")
+        marks: list = []
+        engines: list = []
+
+        def on_sample(eng, col, results, diag):
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            host = results[:, :, col].cpu()                   # the step's result column, device -> host (synchronises)
+            marks.append((col, ev, time.perf_counter(), host.numel() * 8, kern.launch_count()))
+            if not engines or engines[-1] is not eng:
+                engines.append(eng)
+        sim.on_sample = on_sample
+        with ClockSampler(local) as clocks:
+            res = sim.run(State(L, initial="zeros"), circ, sp, NoiseModel(digital_noise(wl)))
+            torch.cuda.synchronize(dev)
+        if len(engines) != 1:
+            raise RuntimeError(f"the batch was split into {len(engines)} waves; choose --batch so that one wave holds it")
+        by_col = {m[0]: m for m in marks}
+        a, b = by_col[W], by_col[W + K]                      # column j is recorded at the end of Trotter step j (column 0: the initial state)
+        ms_dev, t_wall = a[1].elapsed_time(b[1]), b[2] - a[2]
+        t = torch.tensor([ms_dev, t_wall], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_dev, t_wall = float(t[0].item()), float(t[1].item())
+        value = B * world * K / (ms_dev / 1000.0)
+        line.update(value=value, ms_per_step=ms_dev / K, gpu_launches=int(b[4] - a[4]), clocks=clocks.summary())
+        line["e2e"] = {"value": B * world * K / t_wall, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": int(b[3]), "seconds": t_wall,
+                       "api": "Simulator.run(State, circuit, DigitalSimParams(sample_layers=True), NoiseModel): one call; the uniforms of the whole circuit "
+                              "go host -> device at set-up (2 doubles per two-qubit gate and trajectory), every Trotter step's observable column comes "
+                              "back device -> host; same K steps as `value` by the wall clock",
+                       "setup_h2d_bytes": int(B * 16 * (L - 1) * nsteps)}
+        eng = engines[0]
+        prof = eng.phi.bond.to(torch.float64).mean(dim=0).cpu().tolist()
+        S = sum(16.0 * 2 * prof[i] * prof[i + 1] for i in range(L))
+        by = 4.0 * S * (L - 1)                               # per Trotter step: every two-qubit gate walks the chain twice (dissipation.py:79-183), read + write
+        peak, src = 6468.3, "fallback = the figure MEASURED_PEAKS.json held in round 1"
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+                peak, src = float(json.load(fh)["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
+        except Exception:
+            pass
+        achieved = by * B * K / (ms_dev / 1000.0) / 1e9
+        line["roofline"] = {"kernel": "whole Trotter step (state streaming: L - 1 two-qubit gates x 2 chain walks x read + write of the state = 4 (L - 1) S bytes)",
+                            "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": src,
+                            "algorithmic_bytes_per_trajectory_step": by, "mean_bond_final": float(np.mean(prof[1:L])),
+                            "note": "bonds stay <= 11 in this circuit: the step is launch / latency-bound, the fraction is reported as measured"}
+        line["counters"] = {k: int(v) for k, v in eng.stats.items()}
+        zlast = np.array([res.expectation_values[s][-1] for s in range(L)])
+        line["consistency"] = {"status_nonzero": int(np.count_nonzero(res.status)), "status_values": sorted({int(v) for v in res.status}),
+                               "observables_finite": bool(all(np.isfinite(ev).all() for ev in res.expectation_values)),
+                               "max_abs_z": float(np.max(np.abs(zlast))), "z_mean_first_sites": [float(x) for x in zlast[:4]],
+                               "trajectories": int(len(res.status)), "columns": int(len(marks))}
+        del eng, engines
+        torch.cuda.empty_cache()
+        if rank == 0 and world == 1 and not args.no_cpu_baseline:
+            try:
+                cores = args.cpu_cores or os.cpu_count() or 1
+                v, wall = cpu_digital_value(wl, nsteps, cores)
+                line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "pool_wall_s": wall,
+                                        "sample": f"{cores} trajectories in parallel (fork pool, 1 BLAS thread each), each the first {nsteps} Trotter steps "
+                                                  f"of the circuit (the warm-up steps, whose bonds are smaller, are counted: favours the CPU)"}
+            except Exception as exc:  # noqa: BLE001
+                line["cpu_baseline"] = {"error": repr(exc)}
+    except Exception as exc:  # noqa: BLE001 -- never lose the line
+        import traceback
+        line["error"] = repr(exc)
+        line["traceback"] = traceback.format_exc()[-1500:]
+    line["bench_wall_s"] = time.perf_counter() - t_start
+    if rank == 0:
+        emit(line)
+    if world > 1:
+        try:
+            dist.destroy_process_group()
+        except Exception:
+            pass
+    return 0 if "error" not in line else 1
+
+
+# ----------------------------------------------------------------------------------------------------------------------
 # GPU arm
 # ----------------------------------------------------------------------------------------------------------------------
 def run_b200_arm(args):
@@ -545,9 +721,10 @@ def emit(line: dict) -> None:
 def main():
     args = parse_args()
     _claim_stdout()
+    digital = args.wl.get("kind") == "digital"
     if args.impl == "reference":
-        return run_reference_arm(args)
-    return run_b200_arm(args)
+        return run_reference_digital(args) if digital else run_reference_arm(args)
+    return run_b200_digital(args) if digital else run_b200_arm(args)
 
 
 if __name__ == "__main__":

@@ -52,3 +52,15 @@ def test_hbm_byte_model():
     mpo = [1.0] + [3.0] * 9 + [1.0]
     by = hbm_bytes_step(bonds, mpo)
     assert 1.2e6 < by < 2.0e6
+
+
+def test_reference_arm_of_the_digital_workload():
+    """--workload C4 (BASELINE.json configs[3]): the CPU arm runs the oracle's digital_tjm over the first W + K Trotter steps on every worker."""
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "C4", "--length", "5", "--steps", "1",
+                          "--warmup", "1", "--cpu-cores", "2"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.strip().splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["config"]["workload"] == "C4" and d["value"] > 0 and d["cpu_baseline"]["cores"] == 2
+    assert "Trotter" in d["metric"] and d["e2e"]["value"] == d["value"]

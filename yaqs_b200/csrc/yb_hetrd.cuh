@@ -221,7 +221,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_ormtr_rows(const cplx* __restric
     const int b = blockIdx.x;
     if (mask && !mask[b]) return;
     const int n = ek[(long long)b * esk];
-    if (n <= 1) return;
+    if (n <= 0 || (n == 1 && !srcR)) return;               // (a 1 x 1 matrix has no reflector; in "top" mode its row is still gathered)
     cplx* Vp = reinterpret_cast<cplx*>(smem_raw);          // [pb][NE * 32]
     cplx* taus = Vp + (size_t)pb * NE * 32;                // [pb] conj(tau)
     const cplx* Gb = G + (long long)b * sG;
@@ -242,6 +242,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_ormtr_rows(const cplx* __restric
         }
         __syncthreads();
     }
+    if (n == 1) return;
     for (int jhi = n - 2; jhi >= 0; jhi -= pb) {
         const int jlo = max(0, jhi - pb + 1), cnt = jhi - jlo + 1;
         __syncthreads();                                    // previous panel fully consumed

@@ -72,6 +72,7 @@ def run_digital(simulator, initial_state, operator, sp, noise, result):
     for w0 in range(0, len(mine), max(wave, 1)):
         idx = list(mine[w0: w0 + wave])
         eng = BatchedTJM(K, length, len(idx), mpo, ep, procs, obs, init, bond_factor=bond_factor)
+        eng.on_sample = getattr(simulator, "on_sample", None)
         if simulator.rng_mode == "numpy":
             tu, _ = numpy_tables(sp.random_seed, idx, max(n2q, 1), 1)
             tu = torch.from_numpy(tu).to(dev)

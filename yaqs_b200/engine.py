@@ -312,6 +312,7 @@ class BatchedTJM:
         # entries: (matrix, sites) | ("entropy", (i, i+1)) | ("pvm:<bitstring>", ())
         self.observables = [(m if isinstance(m, str) else np.asarray(m, dtype=np.complex128), tuple(int(s) for s in sites)) for m, sites in observables]
         self._ones_i32 = torch.ones(B, dtype=torch.int32, device=dev)
+        self.on_sample = None                               # callback(engine, column, results, diagnostics) after every recorded column of run_digital
         self.stats = {"krylov_calls": 0, "matvecs": 0, "matvecs_2site": 0, "svd_calls": 0, "svd_sweeps": 0, "jumps": 0, "gram_svd_calls": 0, "gram_fallbacks": 0, "cholqr_calls": 0,
                       "cholqr_fallbacks": 0, "heev_top_calls": 0}
 
@@ -1837,6 +1838,8 @@ class BatchedTJM:
             diag[:, :, col] = self.diagnostics(st)
             if nobs:
                 results[:, :, col] = self.evaluate_observables(st)
+            if self.on_sample is not None:                  # step-wise consumers (bench.py times Trotter steps between sample points)
+                self.on_sample(self, col, results, diag)
 
         if sample_layers:
             record(0)
