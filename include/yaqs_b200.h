@@ -101,14 +101,17 @@ int yb_env_identity(int nbatch, const int32_t* mask, yb_extent echi, int dmpo, v
  * basis: [nbatch][kmax+1][nloc_max] Lanczos vectors; the matvec writes H v_j into slot j+1, yb_lanczos_step turns it into
  * v_{j+1} in place.  n_loc[b] = dphys * el[b] * er[b]. */
 int yb_lanczos_init(int nbatch, const int32_t* mask, yb_extent el, yb_extent er, int dphys, const void* x, int64_t stride_x,
-                    void* basis, int64_t stride_basis, int64_t stride_vec, double* nrm, int32_t* active, int32_t* kdone, void* stream);
+                    void* basis, int64_t stride_basis, int64_t stride_vec, double* nrm, int32_t* active, int32_t* kdone, int32_t* n_zero,
+                    void* stream);
 /* One Lanczos iteration for all active trajectories: alpha_j, orthogonalise, beta_j, breakdown / convergence test
  * (k x k tridiagonal eigen-solve = scipy.linalg.eigh_tridiagonal, linalg/eigh.py:29), normalise.  On finish writes the
  * k complex combination coefficients y (already times |v|) to coef[b][0..k) and kdone[b] = k, clears active[b].
- * n_active (device int32) is zeroed by the caller and receives the number of trajectories still iterating. */
+ * n_active (device int32, zero on entry) receives the number of trajectories still iterating.  n_zero (optional, must not alias
+ * n_active) is set to 0 by the same launch: with a PAIR of counters -- step j counts into c[j & 1] and clears c[(j + 1) & 1], and
+ * yb_lanczos_init clears c[0] through its own n_zero -- the iteration needs no fill launch between its steps. */
 int yb_lanczos_step(int nbatch, int j, int kmax, double dt, double tol, yb_extent el, yb_extent er, int dphys, void* basis,
                     int64_t stride_basis, int64_t stride_vec, double* alpha, double* beta, const double* nrm, int32_t* active,
-                    int32_t* kdone, void* coef, int32_t* n_active, void* stream);
+                    int32_t* kdone, void* coef, int32_t* n_active, int32_t* n_zero, void* stream);
 /* out = sum_j coef_j v_j for trajectories with kdone[b] > 0 (zero-norm inputs are returned untouched, :67-69). */
 int yb_lanczos_combine(int nbatch, const int32_t* mask, yb_extent el, yb_extent er, int dphys, const void* basis, int64_t stride_basis,
                        int64_t stride_vec, const void* coef, int kmax, const int32_t* kdone, void* out, int64_t stride_out, void* stream);
@@ -127,9 +130,13 @@ int yb_lanczos_combine(int nbatch, const int32_t* mask, yb_extent el, yb_extent 
  *   yb_svd_finalize; the buffer must be zero before the first yb_svd_prepare): rows whose norm falls below tol * 2^(scale/2) are
  *   rounding residue of a rank-deficient input, take no part in further rotations and count as exact zeros in finalize. */
 int yb_svd_prepare(int nbatch, const int32_t* mask, int mode, yb_extent el, yb_extent er, int dphys, const void* src, int64_t stride_src,
-                   void* w, int64_t stride_w, void* q, int64_t stride_q, int32_t* meta, int32_t* rot_count, void* stream);
+                   void* w, int64_t stride_w, void* q, int64_t stride_q, int32_t* meta, int32_t* rot_count, int32_t* n_zero, int32_t* status_zero,
+                   void* stream);
 int yb_svd_round(int nbatch, const int32_t* mask, int32_t* meta, int block_rows, int nblocks, int round, int full_panel, int inner_sweeps,
-                 void* w, int64_t stride_w, void* q, int64_t stride_q, int32_t* rot_count, int max_len, int max_k, void* stream);
+                 void* w, int64_t stride_w, void* q, int64_t stride_q, int32_t* rot_count, int max_len, int max_k, int32_t* n_zero, void* stream);
+/* status_zero (optional, yb_svd_prepare): int32[nbatch] cleared by the launch (the scratch status words of the Gram route).
+ * n_zero (optional, both calls): a device int32 cleared by the launch -- the counter yb_svd_check / yb_svd_ambiguous / yb_cholqr_* add
+ * to afterwards, so a factorisation needs no separate fill launch. */
 /* yb_svd_prepare `mode` may carry an orientation request in bits 4-5 (0: by shape, 1: W = M, 2: W = M^H).
  *
  * Gram-matrix route for the large matrices (replaces the bulk of zgesdd at linalg/svd.py:89-104): after yb_svd_prepare,
@@ -206,10 +213,13 @@ int yb_svd_finalize(int nbatch, const int32_t* mask, int32_t* meta, int trunc_mo
 /* ---- site-tensor utilities -----------------------------------------------------------------------------------------
  * dst(s', k, r) = src(k, (s', r)): unpack g(S) Vh rows into an MPS site tensor (decompositions.py:171-184). */
 int yb_unpack_vh(int nbatch, const int32_t* mask, yb_extent ek, yb_extent er, int dphys, const void* src, int64_t stride_src, void* dst,
-                 int64_t stride_dst, int max_elems, void* stream);
-/* Packed copy of n[b] = mult * e0[b] * e1[b] complex elements per trajectory. */
+                 int64_t stride_dst, int max_elems, yb_extent set_ext, void* stream);
+/* Packed copy of n[b] = mult * e0[b] * e1[b] complex elements per trajectory.
+ * set_ext (both calls; ptr may be NULL): after the copy, trajectory b's int at set_ext is set to ek[b] / e0[b] -- the bond dimension
+ * the factorisation kept is written into the state's bond array by the launch that installs the new site tensor (the array entry
+ * must not be an extent of the same launch). */
 int yb_copy_packed(int nbatch, const int32_t* mask, yb_extent e0, yb_extent e1, int mult, const void* src, int64_t stride_src, void* dst,
-                   int64_t stride_dst, int max_elems, void* stream);
+                   int64_t stride_dst, int max_elems, yb_extent set_ext, void* stream);
 /* A_s <- sum_t op[s,t] A_t  with a dphys x dphys complex matrix, either shared (op_stride = 0) or per trajectory; optional
  * per-trajectory site selection: trajectory b is touched only if sel == NULL or sel[b] == sel_value.
  * (dissipation.py:125-126, stochastic_process.py:255,262-263, digital_tjm.py:304-309). */
@@ -224,9 +234,9 @@ int yb_mpo_site_apply(int nbatch, const int32_t* mask, yb_extent el, yb_extent e
 /* out[b] = sum |a|^2 over the packed tensor (MPS.norm at the centre site, mps.py:1539-1565). */
 int yb_norm2(int nbatch, const int32_t* mask, yb_extent el, yb_extent er, int dphys, const void* a, int64_t stride_a, double* out,
              void* stream);
-/* a <- a * scale[b] (real). */
+/* a <- a * scale[b] (real); rsqrt_mode != 0: a <- a / sqrt(scale[b]) (scale = the squared norm of yb_norm2: mps.py:736-746 in one launch). */
 int yb_scale(int nbatch, const int32_t* mask, yb_extent el, yb_extent er, int dphys, const double* scale, void* a, int64_t stride_a,
-             int max_elems, void* stream);
+             int max_elems, int rsqrt_mode, void* stream);
 /* g[b][o][p] = sum_(l,r) conj(a_o[l,r]) x_p[l,r]: local reduced density matrix used for observables
  * (mps.py:961-1047) and jump weights (stochastic_process.py:139-176). */
 int yb_local_rdm(int nbatch, const int32_t* mask, yb_extent el, yb_extent er, int dphys, const void* a, int64_t stride_a, const void* x,

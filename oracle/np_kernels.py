@@ -182,8 +182,10 @@ class NumpyKernels:
             _view(env, t, e.size)[:] = e.reshape(-1)
 
     # -- Lanczos ------------------------------------------------------------------------------------------------------
-    def lanczos_init(self, nbatch, mask, el, er, dphys, x, basis, stride_vec, nrm, active, kdone):
+    def lanczos_init(self, nbatch, mask, el, er, dphys, x, basis, stride_vec, nrm, active, kdone, n_zero=None):
         self._launches += 1
+        if n_zero is not None:
+            _np(n_zero)[0] = 0
         for t in range(nbatch):
             if not _on(mask, t):
                 _np(active)[t] = 0
@@ -198,8 +200,10 @@ class NumpyKernels:
             if nr > 0:
                 _view(basis, t, n)[:] = v / nr
 
-    def lanczos_step(self, nbatch, j, kmax, dt, tol, el, er, dphys, basis, stride_vec, alpha, beta, nrm, active, kdone, coef, n_active):
+    def lanczos_step(self, nbatch, j, kmax, dt, tol, el, er, dphys, basis, stride_vec, alpha, beta, nrm, active, kdone, coef, n_active, n_zero=None):
         self._launches += 1
+        if n_zero is not None:
+            _np(n_zero)[0] = 0
         al = _np(alpha).reshape(-1, LANCZOS_PITCH)
         be = _np(beta).reshape(-1, LANCZOS_PITCH)
         cf = _np(coef).reshape(-1, LANCZOS_PITCH)
@@ -256,8 +260,12 @@ class NumpyKernels:
             _view(out, t, n)[:] = acc
 
     # -- SVD (LAPACK stands in for the Jacobi rounds; outputs are gauge-equivalent) ------------------------------------
-    def svd_prepare(self, nbatch, mask, mode, el, er, dphys, src, w, q, meta, rot_count):
+    def svd_prepare(self, nbatch, mask, mode, el, er, dphys, src, w, q, meta, rot_count, n_zero=None, status_zero=None):
         self._launches += 1
+        if n_zero is not None:
+            _np(n_zero)[0] = 0
+        if status_zero is not None:
+            _np(status_zero)[:nbatch] = 0
         mt = _np(meta).reshape(-1, SVD_META)
         force, mode = (mode >> 4) & 3, mode & 3
         for t in range(nbatch):
@@ -282,8 +290,10 @@ class NumpyKernels:
             _view(q, t, k * k)[:] = np.eye(k, dtype=np.complex128).reshape(-1)
             _np(rot_count)[t] = 0
 
-    def svd_round(self, nbatch, mask, meta, block_rows, nblocks, rnd, full_panel, inner_sweeps, w, q, rot_count, max_len, max_k):
+    def svd_round(self, nbatch, mask, meta, block_rows, nblocks, rnd, full_panel, inner_sweeps, w, q, rot_count, max_len, max_k, n_zero=None):
         self._launches += 1          # the twin factorises in svd_finalize with LAPACK
+        if n_zero is not None:
+            _np(n_zero)[0] = 0
 
     def svd_check(self, nbatch, mask, meta, rot_count, n_pending):
         self._launches += 1
@@ -529,7 +539,7 @@ class NumpyKernels:
                 _view(vout, t, k * ln)[:] = np.ascontiguousarray(Y2).reshape(-1)
 
     # -- site-tensor utilities ----------------------------------------------------------------------------------------
-    def unpack_vh(self, nbatch, mask, ek, er, dphys, src, dst, max_elems):
+    def unpack_vh(self, nbatch, mask, ek, er, dphys, src, dst, max_elems, set_ext=None):
         self._launches += 1
         for t in range(nbatch):
             if not _on(mask, t):
@@ -537,14 +547,18 @@ class NumpyKernels:
             k, r = _ext(ek, t), _ext(er, t)
             v = _view(src, t, k * dphys * r).reshape(k, dphys, r)
             _view(dst, t, k * dphys * r)[:] = np.ascontiguousarray(v.transpose(1, 0, 2)).reshape(-1)
+            if set_ext is not None:
+                _np(set_ext.tensor)[set_ext.offset + t * set_ext.stride] = k
 
-    def copy_packed(self, nbatch, mask, e0, e1, mult, src, dst, max_elems):
+    def copy_packed(self, nbatch, mask, e0, e1, mult, src, dst, max_elems, set_ext=None):
         self._launches += 1
         for t in range(nbatch):
             if not _on(mask, t):
                 continue
             n = mult * _ext(e0, t) * (_ext(e1, t) if e1 is not None else 1)
             _view(dst, t, n)[:] = _view(src, t, n)
+            if set_ext is not None:
+                _np(set_ext.tensor)[set_ext.offset + t * set_ext.stride] = _ext(e0, t)
 
     def apply_local_op(self, nbatch, mask, sel, sel_value, el, er, dphys, op, op_stride, a, max_lr):
         self._launches += 1
@@ -578,13 +592,15 @@ class NumpyKernels:
             v = _view(a, t, dphys * _ext(el, t) * _ext(er, t))
             _np(out)[t] = float(np.vdot(v, v).real)
 
-    def scale(self, nbatch, mask, el, er, dphys, scale, a, max_elems):
+    def scale(self, nbatch, mask, el, er, dphys, scale, a, max_elems, rsqrt_mode=False):
         self._launches += 1
         for t in range(nbatch):
             if not _on(mask, t):
                 continue
             v = _view(a, t, dphys * _ext(el, t) * _ext(er, t))
-            v *= float(_np(scale)[t])
+            f = float(_np(scale)[t])
+            with np.errstate(all="ignore"):
+                v *= (1.0 / np.sqrt(f)) if rsqrt_mode else f
 
     def philox_uniform(self, seed, traj_index, tag, nblocks, block0, out):
         """numpy restatement of csrc/yb_philox.cuh (Philox4x32-10, key = seed, counter = (block, tag, traj_lo, traj_hi))."""

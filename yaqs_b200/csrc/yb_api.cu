@@ -165,21 +165,22 @@ int yb_env_identity(int nbatch, const int32_t* mask, yb_extent echi, int dmpo, v
 }
 
 int yb_lanczos_init(int nbatch, const int32_t* mask, yb_extent el, yb_extent er, int dphys, const void* x, int64_t stride_x, void* basis,
-                    int64_t stride_basis, int64_t stride_vec, double* nrm, int32_t* active, int32_t* kdone, void* stream) {
+                    int64_t stride_basis, int64_t stride_vec, double* nrm, int32_t* active, int32_t* kdone, int32_t* n_zero, void* stream) {
     (void)stride_vec;
     if (nbatch <= 0) return 0;
     k_lanczos_init<<<nbatch, 1024, 0, (cudaStream_t)stream>>>(dphys, (const cplx*)x, stride_x, (cplx*)basis, stride_basis, nrm, active, kdone, el.ptr,
-                                                               el.stride, er.ptr, er.stride, mask);
+                                                               el.stride, er.ptr, er.stride, mask, n_zero);
     return done("yb_lanczos_init");
 }
 
 int yb_lanczos_step(int nbatch, int j, int kmax, double dt, double tol, yb_extent el, yb_extent er, int dphys, void* basis, int64_t stride_basis,
                     int64_t stride_vec, double* alpha, double* beta, const double* nrm, int32_t* active, int32_t* kdone, void* coef,
-                    int32_t* n_active, void* stream) {
+                    int32_t* n_active, int32_t* n_zero, void* stream) {
     if (nbatch <= 0) return 0;
+    if (n_zero && n_zero == n_active) return fail_msg("yb_lanczos_step: n_zero must not alias n_active");
     if (kmax > 32 || j >= kmax) return fail_msg("yb_lanczos_step: kmax must be <= 32 and j < kmax");
     k_lanczos_step<<<nbatch, 1024, 0, (cudaStream_t)stream>>>(j, kmax, dt, tol, dphys, (cplx*)basis, stride_basis, stride_vec, alpha, beta, nrm, active,
-                                                               kdone, (cplx*)coef, n_active, el.ptr, el.stride, er.ptr, er.stride);
+                                                               kdone, (cplx*)coef, n_active, el.ptr, el.stride, er.ptr, er.stride, n_zero);
     return done("yb_lanczos_step");
 }
 
@@ -194,16 +195,17 @@ int yb_lanczos_combine(int nbatch, const int32_t* mask, yb_extent el, yb_extent 
 }
 
 int yb_svd_prepare(int nbatch, const int32_t* mask, int mode, yb_extent el, yb_extent er, int dphys, const void* src, int64_t stride_src, void* w,
-                   int64_t stride_w, void* q, int64_t stride_q, int32_t* meta, int32_t* rot_count, void* stream) {
+                   int64_t stride_w, void* q, int64_t stride_q, int32_t* meta, int32_t* rot_count, int32_t* n_zero, int32_t* status_zero,
+                   void* stream) {
     if (nbatch <= 0) return 0;
     dim3 grid(grid_for(stride_w, 256, 64), nbatch);
     k_svd_prepare<<<grid, 256, 0, (cudaStream_t)stream>>>(mode, dphys, (const cplx*)src, stride_src, (cplx*)w, stride_w, (cplx*)q, stride_q, meta,
-                                                           rot_count, el.ptr, el.stride, er.ptr, er.stride, mask);
+                                                           rot_count, el.ptr, el.stride, er.ptr, er.stride, mask, n_zero, status_zero);
     return done("yb_svd_prepare");
 }
 
 int yb_svd_round(int nbatch, const int32_t* mask, int32_t* meta, int block_rows, int nblocks, int round, int full_panel, int inner_sweeps, void* w,
-                 int64_t stride_w, void* q, int64_t stride_q, int32_t* rot_count, int max_len, int max_k, void* stream) {
+                 int64_t stride_w, void* q, int64_t stride_q, int32_t* rot_count, int max_len, int max_k, int32_t* n_zero, void* stream) {
     if (nbatch <= 0) return 0;
     if (nblocks < 2 || (nblocks & 1)) return fail_msg("yb_svd_round: nblocks must be even and >= 2");
     const size_t smem = (size_t)2 * block_rows * ((size_t)max_len + max_k) * sizeof(cplx);
@@ -216,7 +218,7 @@ int yb_svd_round(int nbatch, const int32_t* mask, int32_t* meta, int block_rows,
     }
     dim3 grid(nblocks / 2, nbatch);
     k_svd_round<<<grid, 512, smem, (cudaStream_t)stream>>>(block_rows, nblocks, round, full_panel, inner_sweeps, (cplx*)w, stride_w, (cplx*)q, stride_q,
-                                                            meta, rot_count, max_len, max_k, mask);
+                                                            meta, rot_count, max_len, max_k, mask, n_zero);
     return done("yb_svd_round");
 }
 
@@ -464,20 +466,20 @@ int yb_cholqr_finalize(int nbatch, const int32_t* mask, int32_t* meta, const voi
 }
 
 int yb_unpack_vh(int nbatch, const int32_t* mask, yb_extent ek, yb_extent er, int dphys, const void* src, int64_t stride_src, void* dst,
-                 int64_t stride_dst, int max_elems, void* stream) {
+                 int64_t stride_dst, int max_elems, yb_extent set_ext, void* stream) {
     if (nbatch <= 0) return 0;
     dim3 grid(grid_for(max_elems, 256, 64), nbatch);
     k_unpack_vh<<<grid, 256, 0, (cudaStream_t)stream>>>(dphys, (const cplx*)src, stride_src, (cplx*)dst, stride_dst, ek.ptr, ek.stride, er.ptr,
-                                                         er.stride, mask);
+                                                         er.stride, mask, (int*)set_ext.ptr, set_ext.stride);
     return done("yb_unpack_vh");
 }
 
 int yb_copy_packed(int nbatch, const int32_t* mask, yb_extent e0, yb_extent e1, int mult, const void* src, int64_t stride_src, void* dst,
-                   int64_t stride_dst, int max_elems, void* stream) {
+                   int64_t stride_dst, int max_elems, yb_extent set_ext, void* stream) {
     if (nbatch <= 0) return 0;
     dim3 grid(grid_for(max_elems, 256, 64), nbatch);
     k_copy_packed<<<grid, 256, 0, (cudaStream_t)stream>>>(mult, (const cplx*)src, stride_src, (cplx*)dst, stride_dst, e0.ptr, e0.stride, e1.ptr,
-                                                           e1.stride, mask);
+                                                           e1.stride, mask, (int*)set_ext.ptr, set_ext.stride);
     return done("yb_copy_packed");
 }
 
@@ -510,10 +512,10 @@ int yb_norm2(int nbatch, const int32_t* mask, yb_extent el, yb_extent er, int dp
 }
 
 int yb_scale(int nbatch, const int32_t* mask, yb_extent el, yb_extent er, int dphys, const double* scale, void* a, int64_t stride_a, int max_elems,
-             void* stream) {
+             int rsqrt_mode, void* stream) {
     if (nbatch <= 0) return 0;
     dim3 grid(grid_for(max_elems, 256, 64), nbatch);
-    k_scale<<<grid, 256, 0, (cudaStream_t)stream>>>(dphys, scale, (cplx*)a, stride_a, el.ptr, el.stride, er.ptr, er.stride, mask);
+    k_scale<<<grid, 256, 0, (cudaStream_t)stream>>>(dphys, scale, (cplx*)a, stride_a, el.ptr, el.stride, er.ptr, er.stride, mask, rsqrt_mode);
     return done("yb_scale");
 }
 

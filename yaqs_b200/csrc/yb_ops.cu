@@ -73,9 +73,10 @@ constexpr int LZ_KMAX = 32;
 
 __global__ void __launch_bounds__(LZ_THREADS) k_lanczos_init(int dphys, const cplx* __restrict__ x, long long s_x, cplx* basis, long long s_basis,
                                                                double* nrm, int* active, int* kdone, const int* el, int esl, const int* er,
-                                                               int esr, const int* mask) {
+                                                               int esr, const int* mask, int* n_zero) {
     __shared__ double red[32];
     const int b = blockIdx.x;
+    if (n_zero && b == 0 && threadIdx.x == 0) *n_zero = 0;      // counter of the first Lanczos step (no separate fill launch)
     if (mask && !mask[b]) { active[b] = 0; kdone[b] = -1; return; }
     const long long n = (long long)dphys * el[(long long)b * esl] * er[(long long)b * esr];
     const cplx* xb = x + (long long)b * s_x;
@@ -150,11 +151,12 @@ __device__ void tridiag_eig_warp(int k, double* d, double* e, double* z, int lan
 __global__ void __launch_bounds__(LZ_THREADS) k_lanczos_step(int j, int kmax, double dt, double tol, int dphys, cplx* basis, long long s_basis,
                                                                long long s_vec, double* alpha, double* beta, const double* nrm, int* active,
                                                                int* kdone, cplx* coef, int* n_active, const int* el, int esl, const int* er,
-                                                               int esr) {
+                                                               int esr, int* n_zero) {
     __shared__ double red[64];
     __shared__ double sd[LZ_KMAX], se[LZ_KMAX], sz[LZ_KMAX * LZ_KMAX];
     __shared__ int s_finish, s_k;
     const int b = blockIdx.x;
+    if (n_zero && b == 0 && threadIdx.x == 0) *n_zero = 0;      // the OTHER counter of the pair: the next step counts into it
     if (!active[b]) return;
     const long long n = (long long)dphys * el[(long long)b * esl] * er[(long long)b * esr];
     cplx* vj = basis + (long long)b * s_basis + (long long)j * s_vec;
@@ -254,11 +256,13 @@ __global__ void k_lanczos_combine(int dphys, const cplx* __restrict__ basis, lon
 // site-tensor utilities
 // ---------------------------------------------------------------------------------------------------------------------
 // dst(s, k, r) = src(k, (s, r))
+// set_ext (optional): after the copy the trajectory's extent at set_ext := k (the new bond dimension; no launch reads it meanwhile)
 __global__ void k_unpack_vh(int dphys, const cplx* __restrict__ src, long long s_src, cplx* dst, long long s_dst, const int* ek, int esk,
-                            const int* er, int esr, const int* mask) {
+                            const int* er, int esr, const int* mask, int* set_ext, int set_stride) {
     const int b = blockIdx.y;
     if (mask && !mask[b]) return;
     const int k = ek[(long long)b * esk], r = er[(long long)b * esr];
+    if (set_ext && blockIdx.x == 0 && threadIdx.x == 0) set_ext[(long long)b * set_stride] = k;
     const long long n = (long long)dphys * k * r;
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
         const int ri = (int)(e % r);
@@ -269,10 +273,11 @@ __global__ void k_unpack_vh(int dphys, const cplx* __restrict__ src, long long s
 }
 
 __global__ void k_copy_packed(int mult, const cplx* __restrict__ src, long long s_src, cplx* dst, long long s_dst, const int* e0, int es0,
-                              const int* e1, int es1, const int* mask) {
+                              const int* e1, int es1, const int* mask, int* set_ext, int set_stride) {
     const int b = blockIdx.y;
     if (mask && !mask[b]) return;
     const long long n = (long long)mult * e0[(long long)b * es0] * (e1 ? e1[(long long)b * es1] : 1);
+    if (set_ext && blockIdx.x == 0 && threadIdx.x == 0) set_ext[(long long)b * set_stride] = e0[(long long)b * es0];      // see k_unpack_vh
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x)
         dst[(long long)b * s_dst + e] = src[(long long)b * s_src + e];
 }
@@ -326,11 +331,12 @@ __global__ void __launch_bounds__(1024) k_norm2(int dphys, const cplx* __restric
     if (threadIdx.x == 0) out[b] = s[0];
 }
 
-__global__ void k_scale(int dphys, const double* scale, cplx* a, long long s_a, const int* el, int esl, const int* er, int esr, const int* mask) {
+__global__ void k_scale(int dphys, const double* scale, cplx* a, long long s_a, const int* el, int esl, const int* er, int esr, const int* mask,
+                        int rsqrt_mode) {
     const int b = blockIdx.y;
     if (mask && !mask[b]) return;
     const long long n = (long long)dphys * el[(long long)b * esl] * er[(long long)b * esr];
-    const double f = scale[b];
+    const double f = rsqrt_mode ? 1.0 / sqrt(scale[b]) : scale[b];       // rsqrt_mode: scale holds a squared norm (normalisation in one launch)
     cplx* ab = a + (long long)b * s_a;
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
         cplx v = ab[e]; v.x *= f; v.y *= f; ab[e] = v;

@@ -33,8 +33,11 @@ __device__ __forceinline__ double jacobi_tol2(int len) {
 }
 
 __global__ void k_svd_prepare(int mode, int dphys, const cplx* __restrict__ src, long long s_src, cplx* w, long long s_w, cplx* q, long long s_q,
-                              int* meta, int* rot_count, const int* el, int esl, const int* er, int esr, const int* mask) {
+                              int* meta, int* rot_count, const int* el, int esl, const int* er, int esr, const int* mask, int* n_zero,
+                              int* status_zero) {
     const int b = blockIdx.y;
+    if (n_zero && b == 0 && blockIdx.x == 0 && threadIdx.x == 0) *n_zero = 0;     // pending / flagged counter of the factorisation that starts here
+    if (status_zero && blockIdx.x == 0 && threadIdx.x == 0) status_zero[b] = 0;   // per-trajectory scratch status of the Gram route
     if (mask && !mask[b]) { if (blockIdx.x == 0 && threadIdx.x == 0) meta[b * META + 5] = 1; return; }
     const int l = el[(long long)b * esl], r = er[(long long)b * esr];
     const int force = (mode >> 4) & 3;          // 0: orient by shape, 1: W = M, 2: W = M^H (Gram path picks the isometric side)
@@ -120,10 +123,12 @@ __device__ __forceinline__ int jacobi_pair(cplx* wi, cplx* wj, int len, cplx* qi
 
 // grid = (nblocks/2, B); block = 512 threads; dynamic smem = 2*block_rows*(max_len + max_k) complex.
 __global__ void __launch_bounds__(512) k_svd_round(int block_rows, int nblocks, int round, int full_panel, int inner_sweeps, cplx* w, long long s_w,
-                                                    cplx* q, long long s_q, int* meta, int* rot_count, int max_len, int max_k, const int* mask) {
+                                                    cplx* q, long long s_q, int* meta, int* rot_count, int max_len, int max_k, const int* mask,
+                                                    int* n_zero) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ int s_rot;
     const int b = blockIdx.y;
+    if (n_zero && b == 0 && blockIdx.x == 0 && threadIdx.x == 0) *n_zero = 0;     // counter k_svd_check adds to after the rounds of this sweep
     if (mask && !mask[b]) return;
     const int* m = meta + b * META;
     if (m[5]) return;

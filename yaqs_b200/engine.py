@@ -260,6 +260,7 @@ class BatchedTJM:
         self.svd_rot = torch.zeros(B, dtype=torch.int32, device=dev)
         self.keep = torch.ones(B, dtype=torch.int32, device=dev)
         self.counter = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.lz_count = torch.zeros(2, dtype=torch.int32, device=dev)
         self.status = torch.zeros(B, dtype=torch.int32, device=dev)
         self.alpha = torch.zeros(B * LANCZOS_PITCH, dtype=torch.float64, device=dev)
         self.beta = torch.zeros(B * LANCZOS_PITCH, dtype=torch.float64, device=dev)
@@ -469,16 +470,19 @@ class BatchedTJM:
     def krylov(self, x: Buf, out: Buf, el: Ext, er: Ext, dphys: int, matvec, dt: float, mask) -> None:
         K, B = self.K, self.B
         basis = self._buf(self.basis, (KRYLOV_MAX + 1) * self.svec)
-        K.lanczos_init(B, mask, el, er, dphys, x, basis, self.svec, self.nrm, self.active, self.kdone)
+        # "anyone still iterating?" lives in a pair of device counters: step j counts into c[j & 1] and clears c[(j + 1) & 1] in the
+        # same launch (lanczos_init clears c[0]), so the iteration issues no fill launch between its steps
+        c2 = self.lz_count
+        K.lanczos_init(B, mask, el, er, dphys, x, basis, self.svec, self.nrm, self.active, self.kdone, c2[0:1])
         self.stats["krylov_calls"] += 1
         for j in range(KRYLOV_MAX):
             matvec(basis.at(j * self.svec), basis.at((j + 1) * self.svec), self.active)
-            self.counter.zero_()
+            cur, nxt = c2[(j & 1):(j & 1) + 1], c2[((j + 1) & 1):((j + 1) & 1) + 1]
             K.lanczos_step(B, j, KRYLOV_MAX, dt, self.p.krylov_tol, el, er, dphys, basis, self.svec, self.alpha, self.beta, self.nrm,
-                           self.active, self.kdone, self.coef, self.counter)
+                           self.active, self.kdone, self.coef, cur, nxt)
             # convergence is per trajectory on the device (`active`); the host only needs to know when nobody is left.  The error
             # estimate needs j >= 1 and rarely passes before the third vector, so the first two iterations are not read back
-            if j >= 2 and K.sync_int(self.counter) == 0:
+            if j >= 2 and K.sync_int(cur) == 0:
                 break
         K.lanczos_combine(B, mask, el, er, dphys, basis, self.svec, self.coef, KRYLOV_MAX, self.kdone, out)
 
@@ -524,10 +528,9 @@ class BatchedTJM:
         orient = SVD_ORIENT_COLS if dist == "right" else SVD_ORIENT_ROWS
         kdim = max(1, min(sd, dims[1] if dist == "right" else dims[0]))
         ldim = max(1, min(sd, dims[0] if dist == "right" else dims[1]))
-        K.svd_prepare(B, mask, mode | orient, el, er, self.d, src, w, linv, self.svd_meta, self.svd_rot)
+        K.svd_prepare(B, mask, mode | orient, el, er, self.d, src, w, linv, self.svd_meta, self.svd_rot, self.counter)      # (clears the flag counter)
         ek, eln = Ext(self.svd_meta, 0, SVD_META), Ext(self.svd_meta, 1, SVD_META)
         K.gemm(OP_GRAM, B, 1, mask, ek, eln, None, 1, 1, 1, w, w, g, 0, kdim, kdim)
-        self.counter.zero_()
         K.cholqr_factor(B, mask, self.svd_meta, g, linv, float(trunc[1]), self.amb, self.counter, kdim)
         K.gemm(OP_ROTATE, B, 1, mask, ek, eln, None, 1, 1, 1, linv, w, y1, 0, kdim, ldim)
         K.gemm(OP_GRAM, B, 1, mask, ek, eln, None, 1, 1, 1, y1, y1, g2, 0, kdim, kdim)
@@ -587,10 +590,9 @@ class BatchedTJM:
         g, qh, zt = self._buf(self.heev_g, sq), self._buf(self.heev_q, sq), self._buf(self.heev_z, sq)
         tm, thr, mb, mk = trunc
         orient = 0 if mode != SVD_THETA else (SVD_ORIENT_ROWS if dist == "right" else SVD_ORIENT_COLS)
-        K.svd_prepare(B, mask, mode | orient, el, er, self.d, src, w, q, self.svd_meta, self.svd_rot)
+        K.svd_prepare(B, mask, mode | orient, el, er, self.d, src, w, q, self.svd_meta, self.svd_rot, self.counter, self.status_scratch)     # (clears the counter of svd_ambiguous and the scratch status)
         ek, eln = Ext(self.svd_meta, 0, SVD_META), Ext(self.svd_meta, 1, SVD_META)
         K.gemm(OP_GRAM, B, 1, mask, ek, eln, None, 1, 1, 1, w, w, g, 0, sd, sd)
-        self.status_scratch.zero_()
         kdim = sd if dims is None else max(1, min(sd, min(dims) if mode != SVD_THETA else (dims[0] if dist == "right" else dims[1])))      # bound of k = rows of W
         # a split capped at max_bond < k can only keep the eigenvectors of the max_bond largest Gram eigenvalues: back-transform and
         # rotate only those rows; the singular values behind them (discarded weight) come from the eigenvalues (yb_heev_rows_top)
@@ -603,7 +605,6 @@ class BatchedTJM:
                                self._buf(self.svd_u, sq), self._buf(self.svd_v, sq), self.status_scratch, sd, self.heev_ds, sd, top)
             self.stats["gram_svd_calls"] += 1
             self.stats["heev_top_calls"] += 1
-            self.counter.zero_()
             K.svd_ambiguous(B, mask, self.svd_meta, self.svd_s, sd, tm, thr, False, self.GRAM_TAU, 16.0 * sd * 2.220446049250313e-16,
                             self.status_scratch, self.amb, self.counter)
             nfb = K.sync_int(self.counter)
@@ -640,7 +641,6 @@ class BatchedTJM:
                        self._buf(self.svd_u, sq), self._buf(self.svd_v, sq), self.status_scratch, sd)
         self.stats["gram_svd_calls"] += 1
         # ---- keep decisions within the error bound of the threshold -> Jacobi (one kernel + one host read per factorisation)
-        self.counter.zero_()
         K.svd_ambiguous(B, mask, self.svd_meta, self.svd_s, sd, tm, thr, two_level, self.GRAM_TAU, 16.0 * sd * 2.220446049250313e-16,
                         self.status_scratch, self.amb, self.counter)
         nfb = K.sync_int(self.counter)
@@ -658,8 +658,7 @@ class BatchedTJM:
         self.stats["svd_calls"] += 1
         for _sweep in range(60):
             for rnd in range(nb - 1):
-                K.svd_round(B, mask, self.svd_meta, rows, nb, rnd, rnd == 0, inner, w, q, self.svd_rot, max_len, max_k)
-            self.counter.zero_()
+                K.svd_round(B, mask, self.svd_meta, rows, nb, rnd, rnd == 0, inner, w, q, self.svd_rot, max_len, max_k, self.counter)      # (clears the counter of svd_check)
             K.svd_check(B, mask, self.svd_meta, self.svd_rot, self.counter)
             self.stats["svd_sweeps"] += 1
             if K.sync_int(self.counter) == 0:
@@ -676,8 +675,7 @@ class BatchedTJM:
         self._svd(SVD_THETA, self._buf(self.theta, lay.theta_slot), st.ext(i), st.ext(i + 2), trunc, dist, mask, kcap, (d * lay.cap[i], d * lay.cap[i + 2]))
         kx = Ext(self.keep, 0, 1)
         K.copy_packed(B, mask, st.ext(i), kx, d, self._buf(self.svd_u, sd * sd), st.site(i), lay.slot[i])
-        K.unpack_vh(B, mask, kx, st.ext(i + 2), d, self._buf(self.svd_v, sd * sd), st.site(i + 1), lay.slot[i + 1])
-        self._set_bond(st, i + 1, mask)
+        K.unpack_vh(B, mask, kx, st.ext(i + 2), d, self._buf(self.svd_v, sd * sd), st.site(i + 1), lay.slot[i + 1], st.ext(i + 1))      # bond i+1 <- keep
 
     def shift_right(self, st: BatchedState, i: int, trunc, mask=None, fast: bool = False) -> None:
         """Centre i -> i+1 (mps.py:719-769).  The reference merges the pair and splits it; because site i+1 is a right
@@ -691,8 +689,7 @@ class BatchedTJM:
         tmp = self._buf(self.tmp, lay.nloc_max)
         K.gemm(OP_ABSORB_R, B, d, mask, kx, st.ext(i + 1), st.ext(i + 2), d, 1, 1, self._buf(self.svd_v, sd * sd), st.site(i + 1), tmp, 0,
                lay.cap[i + 1], lay.cap[i + 2])
-        K.copy_packed(B, mask, kx, st.ext(i + 2), d, tmp, st.site(i + 1), lay.slot[i + 1])
-        self._set_bond(st, i + 1, mask)
+        K.copy_packed(B, mask, kx, st.ext(i + 2), d, tmp, st.site(i + 1), lay.slot[i + 1], st.ext(i + 1))      # bond i+1 <- keep
 
     def shift_left(self, st: BatchedState, i: int, trunc, mask=None, fast: bool = False) -> None:
         """Centre i -> i-1 (mps.py:771-788), reduced form (site i-1 must be a left isometry)."""
@@ -705,15 +702,13 @@ class BatchedTJM:
         K.gemm(OP_ABSORB_L, B, d, mask, st.ext(i - 1), st.ext(i), kx, d, 1, 1, st.site(i - 1), self._buf(self.svd_u, sd * sd), tmp, 0,
                lay.cap[i - 1], lay.cap[i])
         K.copy_packed(B, mask, st.ext(i - 1), kx, d, tmp, st.site(i - 1), lay.slot[i - 1])
-        K.unpack_vh(B, mask, kx, st.ext(i + 1), d, self._buf(self.svd_v, sd * sd), st.site(i), lay.slot[i])
-        self._set_bond(st, i, mask)
+        K.unpack_vh(B, mask, kx, st.ext(i + 1), d, self._buf(self.svd_v, sd * sd), st.site(i), lay.slot[i], st.ext(i))      # bond i <- keep
 
     def normalize_site(self, st: BatchedState, i: int, mask=None) -> None:
         """QR at a chain end with R dropped == divide the (1-column) centre tensor by its norm (mps.py:736-746)."""
         K, B = self.K, self.B
         K.norm2(B, mask, st.ext(i), st.ext(i + 1), self.d, st.site(i), self.norm_buf)
-        torch.rsqrt(self.norm_buf, out=self.scale_buf)
-        K.scale(B, mask, st.ext(i), st.ext(i + 1), self.d, self.scale_buf, st.site(i), self.lay.slot[i])
+        K.scale(B, mask, st.ext(i), st.ext(i + 1), self.d, self.norm_buf, st.site(i), self.lay.slot[i], True)
 
     # ------------------------------------------------------------------------------------------------------------------
     # TDVP sweeps (integrators.py:44-291)

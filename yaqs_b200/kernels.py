@@ -203,16 +203,17 @@ class CudaKernels:
                                              int(max_chi), self._stream())))
 
     # -- Lanczos ------------------------------------------------------------------------------------------------------
-    def lanczos_init(self, nbatch, mask, el, er, dphys, x: Buf, basis: Buf, stride_vec, nrm, active, kdone):
+    def lanczos_init(self, nbatch, mask, el, er, dphys, x: Buf, basis: Buf, stride_vec, nrm, active, kdone, n_zero=None):
         self._timed_call("lanczos_misc", lambda: self._check(self.lib.yb_lanczos_init(
             nbatch, self._ptr(mask), self._ext(el), self._ext(er), dphys, self._cptr(x), ctypes.c_int64(x.stride), self._cptr(basis),
-            ctypes.c_int64(basis.stride), ctypes.c_int64(stride_vec), self._ptr(nrm), self._ptr(active), self._ptr(kdone), self._stream())))
+            ctypes.c_int64(basis.stride), ctypes.c_int64(stride_vec), self._ptr(nrm), self._ptr(active), self._ptr(kdone), self._ptr(n_zero),
+            self._stream())))
 
-    def lanczos_step(self, nbatch, j, kmax, dt, tol, el, er, dphys, basis: Buf, stride_vec, alpha, beta, nrm, active, kdone, coef, n_active):
+    def lanczos_step(self, nbatch, j, kmax, dt, tol, el, er, dphys, basis: Buf, stride_vec, alpha, beta, nrm, active, kdone, coef, n_active, n_zero=None):
         self._timed_call("lanczos_step", lambda: self._check(self.lib.yb_lanczos_step(
             nbatch, j, kmax, ctypes.c_double(dt), ctypes.c_double(tol), self._ext(el), self._ext(er), dphys, self._cptr(basis),
             ctypes.c_int64(basis.stride), ctypes.c_int64(stride_vec), self._ptr(alpha), self._ptr(beta), self._ptr(nrm), self._ptr(active),
-            self._ptr(kdone), self._ptr(coef), self._ptr(n_active), self._stream())))
+            self._ptr(kdone), self._ptr(coef), self._ptr(n_active), self._ptr(n_zero), self._stream())))
 
     def lanczos_combine(self, nbatch, mask, el, er, dphys, basis: Buf, stride_vec, coef, kmax, kdone, out: Buf):
         self._timed_call("lanczos_misc", lambda: self._check(self.lib.yb_lanczos_combine(
@@ -220,15 +221,17 @@ class CudaKernels:
             ctypes.c_int64(stride_vec), self._ptr(coef), kmax, self._ptr(kdone), self._cptr(out), ctypes.c_int64(out.stride), self._stream())))
 
     # -- SVD ----------------------------------------------------------------------------------------------------------
-    def svd_prepare(self, nbatch, mask, mode, el, er, dphys, src: Buf, w: Buf, q: Buf, meta, rot_count):
+    def svd_prepare(self, nbatch, mask, mode, el, er, dphys, src: Buf, w: Buf, q: Buf, meta, rot_count, n_zero=None, status_zero=None):
         self._timed_call("svd_misc", lambda: self._check(self.lib.yb_svd_prepare(
             nbatch, self._ptr(mask), mode, self._ext(el), self._ext(er), dphys, self._cptr(src), ctypes.c_int64(src.stride), self._cptr(w),
-            ctypes.c_int64(w.stride), self._cptr(q), ctypes.c_int64(q.stride), self._ptr(meta), self._ptr(rot_count), self._stream())))
+            ctypes.c_int64(w.stride), self._cptr(q), ctypes.c_int64(q.stride), self._ptr(meta), self._ptr(rot_count), self._ptr(n_zero), self._ptr(status_zero),
+            self._stream())))
 
-    def svd_round(self, nbatch, mask, meta, block_rows, nblocks, rnd, full_panel, inner_sweeps, w: Buf, q: Buf, rot_count, max_len, max_k):
+    def svd_round(self, nbatch, mask, meta, block_rows, nblocks, rnd, full_panel, inner_sweeps, w: Buf, q: Buf, rot_count, max_len, max_k, n_zero=None):
         self._timed_call("svd_round", lambda: self._check(self.lib.yb_svd_round(
             nbatch, self._ptr(mask), self._ptr(meta), block_rows, nblocks, rnd, int(full_panel), inner_sweeps, self._cptr(w),
-            ctypes.c_int64(w.stride), self._cptr(q), ctypes.c_int64(q.stride), self._ptr(rot_count), int(max_len), int(max_k), self._stream())))
+            ctypes.c_int64(w.stride), self._cptr(q), ctypes.c_int64(q.stride), self._ptr(rot_count), int(max_len), int(max_k), self._ptr(n_zero),
+            self._stream())))
 
     def svd_check(self, nbatch, mask, meta, rot_count, n_pending):
         self._timed_call("svd_misc", lambda: self._check(self.lib.yb_svd_check(nbatch, self._ptr(mask), self._ptr(meta), self._ptr(rot_count), self._ptr(n_pending), self._stream())))
@@ -301,13 +304,13 @@ class CudaKernels:
                                            self._cptr(ws), ctypes.c_int64(ws.stride), self._cptr(qs), ctypes.c_int64(qs.stride), self._stream())))
 
     # -- site-tensor utilities ----------------------------------------------------------------------------------------
-    def unpack_vh(self, nbatch, mask, ek, er, dphys, src: Buf, dst: Buf, max_elems):
+    def unpack_vh(self, nbatch, mask, ek, er, dphys, src: Buf, dst: Buf, max_elems, set_ext: Ext | None = None):
         self._timed_call("pack", lambda: self._check(self.lib.yb_unpack_vh(nbatch, self._ptr(mask), self._ext(ek), self._ext(er), dphys, self._cptr(src),
-                                          ctypes.c_int64(src.stride), self._cptr(dst), ctypes.c_int64(dst.stride), int(max_elems), self._stream())))
+                                          ctypes.c_int64(src.stride), self._cptr(dst), ctypes.c_int64(dst.stride), int(max_elems), self._ext(set_ext), self._stream())))
 
-    def copy_packed(self, nbatch, mask, e0, e1, mult, src: Buf, dst: Buf, max_elems):
+    def copy_packed(self, nbatch, mask, e0, e1, mult, src: Buf, dst: Buf, max_elems, set_ext: Ext | None = None):
         self._timed_call("pack", lambda: self._check(self.lib.yb_copy_packed(nbatch, self._ptr(mask), self._ext(e0), self._ext(e1), mult, self._cptr(src),
-                                            ctypes.c_int64(src.stride), self._cptr(dst), ctypes.c_int64(dst.stride), int(max_elems), self._stream())))
+                                            ctypes.c_int64(src.stride), self._cptr(dst), ctypes.c_int64(dst.stride), int(max_elems), self._ext(set_ext), self._stream())))
 
     def apply_local_op(self, nbatch, mask, sel, sel_value, el, er, dphys, op: torch.Tensor, op_stride, a: Buf, max_lr):
         if op.dtype != torch.complex128:
@@ -327,9 +330,9 @@ class CudaKernels:
         self._timed_call("local", lambda: self._check(self.lib.yb_norm2(nbatch, self._ptr(mask), self._ext(el), self._ext(er), dphys, self._cptr(a), ctypes.c_int64(a.stride),
                                       self._ptr(out), self._stream())))
 
-    def scale(self, nbatch, mask, el, er, dphys, scale, a: Buf, max_elems):
+    def scale(self, nbatch, mask, el, er, dphys, scale, a: Buf, max_elems, rsqrt_mode: bool = False):
         self._timed_call("local", lambda: self._check(self.lib.yb_scale(nbatch, self._ptr(mask), self._ext(el), self._ext(er), dphys, self._ptr(scale), self._cptr(a),
-                                      ctypes.c_int64(a.stride), int(max_elems), self._stream())))
+                                      ctypes.c_int64(a.stride), int(max_elems), int(bool(rsqrt_mode)), self._stream())))
 
     def philox_uniform(self, seed: int, traj_index, tag: int, nblocks: int, block0: int, out):
         """out [nbatch, 2 * nblocks] float64 (contiguous rows); traj_index int64 [nbatch] on the device."""
