@@ -385,3 +385,30 @@ def test_digital_tdvp_mode_only_matters_for_window_gates():
     with pytest.raises(ValueError, match='only supports tdvp_mode="2site"'):
         sim.run(State(L, initial="zeros"), create_ising_circuit(L, 1.0, 0.6, 0.2, 1, periodic=True),
                 DigitalSimParams(observables=obs, tdvp_mode="1site", gate_mode="tdvp"))
+
+
+def test_user_tensors_keep_their_norm():
+    """The reference keeps user tensors as given (core/data_structures/mps.py:112-114).  Here they are re-gauged (right-canonical,
+    centre 0) WITHOUT rescaling: the represented vector is unchanged, an unnormalised input stays unnormalised, and MPS.normalize()
+    is what divides the norm out."""
+    from yaqs_b200.containers import MPS
+    rng = np.random.default_rng(3)
+    bonds = [1, 2, 4, 2, 1]
+    tensors = [rng.standard_normal((2, bonds[i], bonds[i + 1])) + 1j * rng.standard_normal((2, bonds[i], bonds[i + 1])) for i in range(4)]
+
+    def dense(ts):
+        v = np.ones((1, 1), dtype=np.complex128)
+        for t in ts:
+            v = np.einsum("xl,slr->xsr", v, t).reshape(-1, t.shape[2])
+        return v.reshape(-1)
+
+    ref = dense(tensors)
+    mps = MPS(4, tensors=[t.copy() for t in tensors])
+    assert mps.orthogonality_center == 0
+    assert np.max(np.abs(dense(mps.tensors) - ref)) < 1e-12 * np.abs(ref).max()
+    assert abs(np.linalg.norm(mps.tensors[0]) - np.linalg.norm(ref)) < 1e-12 * np.linalg.norm(ref)
+    for t in mps.tensors[1:]:                                  # right isometries
+        m = t.transpose(1, 0, 2).reshape(t.shape[1], -1)
+        assert np.max(np.abs(m @ m.conj().T - np.eye(t.shape[1]))) < 1e-12
+    mps.normalize()
+    assert abs(np.linalg.norm(dense(mps.tensors)) - 1.0) < 1e-12

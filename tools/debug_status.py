@@ -26,6 +26,7 @@ def main():
     kern = CudaKernels(dev)
     ham = Hamiltonian.ising(L, J=1.0, g=0.5)
     state = State(tensors=saturated_tensors(L, chi))
+    state.mps.normalize()
     noise = NoiseModel([{"name": n, "sites": [i], "strength": 0.1} for i in range(L) for n in ("lowering", "pauli_z")])
     obs = [(np.array([[1, 0], [0, -1]], dtype=np.complex128), [s]) for s in range(L)]
     ep = E.EngineParams(dt=0.1, n_steps=steps, order=2, max_bond_dim=chi, svd_threshold=1e-6, krylov_tol=1e-4)

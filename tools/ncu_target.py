@@ -47,7 +47,30 @@ def main():
     for _ in range(2):
         g = g0.clone()
         kern.heev_rows(nb, None, Ext(ek, 0, 1), Buf(g, 0, sq), Buf(eh, 0, sq), zr, sq, d, e, tau, k, meta, status, k)
+    # round 2, second session: the capped-split variant (top rows only) and the Cholesky-QR factorisation of the keep-all gauge shifts
+    order = torch.zeros(nb * k, dtype=torch.int32, device=dev)
+    ds = torch.zeros(nb * k, dtype=torch.float64, device=dev)
+    ntop = torch.zeros(nb, dtype=torch.int32, device=dev)
+    for _ in range(2):
+        g = g0.clone()
+        kern.heev_rows_top(nb, None, Ext(ek, 0, 1), Buf(g, 0, sq), Buf(eh, 0, sq), zr, sq, d, e, tau, k, meta, status, k, k // 2, order, ds, ntop)
+    nb2, k2, len2 = 96, 128, 256
+    a = rng.standard_normal((k2, len2)) + 1j * rng.standard_normal((k2, len2))
+    a *= np.logspace(0, -3, k2)[:, None]
+    w0 = torch.from_numpy(a).to(dev).reshape(-1).repeat(nb2)
+    meta2 = torch.zeros(nb2 * 8, dtype=torch.int32, device=dev)
+    meta2.view(nb2, 8)[:, 0] = k2
+    meta2.view(nb2, 8)[:, 1] = len2
+    g2 = torch.zeros(nb2 * k2 * k2, dtype=torch.complex128, device=dev)
+    linv = torch.zeros(nb2 * k2 * k2, dtype=torch.complex128, device=dev)
+    flag = torch.zeros(nb2, dtype=torch.int32, device=dev)
+    nflag = torch.zeros(1, dtype=torch.int32, device=dev)
+    ek2, el2 = Ext(meta2, 0, 8), Ext(meta2, 1, 8)
+    for _ in range(2):
+        kern.gemm(K.OP_GRAM, nb2, 1, None, ek2, el2, None, 1, 1, 1, Buf(w0, 0, k2 * len2), Buf(w0, 0, k2 * len2), Buf(g2, 0, k2 * k2), 0, k2, k2)
+        kern.cholqr_factor(nb2, None, meta2, Buf(g2, 0, k2 * k2), Buf(linv, 0, k2 * k2), 1e-12, flag, nflag, k2)
     torch.cuda.synchronize()
+    assert int(flag.max().item()) == 0
 
 
 if __name__ == "__main__":

@@ -47,7 +47,10 @@ class MPS:
                 raise ValueError("Number of tensors must match the chain length.")
             self.tensors = [np.asarray(t, dtype=C) for t in tensors]
             self.orthogonality_center = None
-            self.normalize()
+            # the reference keeps user tensors as given (mps.py:112-114); the batched engine needs them right-canonical with the centre
+            # at site 0, so they are re-gauged WITHOUT rescaling: an unnormalised input stays unnormalised, and an evolved state handed
+            # back as output_state keeps the norm it has (truncation loss stays visible)
+            self._canonicalize(rescale=False)
             return
         self.tensors = []
         if state == "haar-random":
@@ -85,6 +88,10 @@ class MPS:
 
     # mps.py:815-839 with QR: right-canonical form, centre 0, unit norm
     def normalize(self) -> None:
+        """Right-canonical form with the centre at site 0 and unit norm (mps.py:815-839, form "B")."""
+        self._canonicalize(rescale=True)
+
+    def _canonicalize(self, rescale: bool) -> None:
         t = self.tensors
         for i in reversed(range(1, self.length)):
             d, l, r = t[i].shape
@@ -92,7 +99,7 @@ class MPS:
             t[i] = q.reshape(d, r, q.shape[1]).transpose(0, 2, 1)
             t[i - 1] = np.einsum("slj,kj->slk", t[i - 1], rm)
         nrm = np.linalg.norm(t[0])
-        if nrm > 0:
+        if rescale and nrm > 0:
             t[0] = t[0] / nrm
         self.orthogonality_center = 0
 
