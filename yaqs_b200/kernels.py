@@ -102,6 +102,8 @@ class CudaKernels:
         self.device = torch.device(device if device is not None else "cuda:0")
         if self.device.type != "cuda":
             raise KernelError("yaqs_b200 kernels run on CUDA devices only")
+        self._dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        self._raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
         self._timed: dict[str, list] | None = None
         self._detail: dict[tuple, list] | None = None
         self._flops = None
@@ -143,6 +145,10 @@ class CudaKernels:
 
     # -- helpers ------------------------------------------------------------------------------------------------------
     def _stream(self):
+        # torch's CURRENT stream of the calling thread, as a raw cudaStream_t (the private accessor skips the Stream object: this runs
+        # once per launch, and small-chi workloads are bounded by the host cost of a launch)
+        if self._raw_stream is not None:
+            return ctypes.c_void_p(self._raw_stream(self._dev_index))
         return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
     @staticmethod
