@@ -253,6 +253,25 @@ int yb_local_rdm(int nbatch, const int32_t* mask, yb_extent el, yb_extent er, in
 int yb_philox_uniform(int nbatch, uint64_t seed, const int64_t* traj_index, uint32_t tag, int nblocks, uint32_t block0, double* out,
                       int64_t stride_out, void* stream);
 
+/* ---- stochastic_process on the device (methods/stochastic_process.py:190-292) -------------------------------------------
+ * yb_jump_test: dp[b] = 1 - norm2[b] (calculate_stochastic_factor, :36-60), jmask[b] = (u1 < dp) (:238), njump = number of jumps.
+ * The two uniforms of a test sit at positions p, p + 1 of the trajectory's stream, p = pos[b] (or `col` when pos == NULL):
+ * table mode (use_philox = 0): table[b * table_stride + p] -- streams replayed from the reference's seeded numpy generators;
+ * philox mode: drawn in the kernel, component (q & 1) of Philox block (q >> 1), q = 2 * block0 + p, of stream (seed, traj_index[b],
+ * tag) -- the same numbers yb_philox_uniform would put into a table.  pos[b] advances by 1 + jumped (what the reference's Generator
+ * hands out); u1 / u2 return the uniforms (u2 feeds yb_jump_select and the test logs).
+ * yb_jump_select (trajectories with jmask != 0): w[b][k] = dt * proc_strength[k] * Re sum_e proc_ldl[k][e] * rdm[site_k][b][e] with the
+ * local reduced density matrices of the transfer sweep (rdm1: [L][B][4]; rdm2: [L - 1][B][16] for proc_two[k] != 0) -- :139-176;
+ * total = sum_k w (zero / non-finite: status bit 4, the reference's ValueError :179-187); w is overwritten with the pdf w / total;
+ * choice = #{k : cumsum(pdf)_k / cumsum(pdf)_last <= u2}, clamped (numpy's Generator.choice, :257); ops_sel[b] = ops_table[choice]
+ * (nops complex numbers per process: the operator rows the application launches take). */
+int yb_jump_test(int nbatch, const double* norm2, const double* table, int64_t table_stride, int64_t col, int64_t* pos, int use_philox,
+                 uint64_t seed, const int64_t* traj_index, uint32_t tag, uint32_t block0, double* dp, double* u1, double* u2, int32_t* jmask,
+                 int32_t* njump, void* stream);
+int yb_jump_select(int nbatch, const int32_t* jmask, const double* u2, const void* rdm1, const void* rdm2, int nproc, const int32_t* proc_site,
+                   const int32_t* proc_two, const void* proc_ldl, const double* proc_strength, double dt, const void* ops_table, int nops, double* w,
+                   double* total, int32_t* choice, void* ops_sel, int32_t* status, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -602,6 +602,63 @@ class NumpyKernels:
             with np.errstate(all="ignore"):
                 v *= (1.0 / np.sqrt(f)) if rsqrt_mode else f
 
+    # -- stochastic_process on the device (twin of k_jump_test / k_jump_select) -------------------------------------------
+    def jump_test(self, nbatch, norm2, table, col, pos, philox, dp, u1, u2, jmask, njump):
+        self._launches += 1
+        count = 0
+        for t in range(nbatch):
+            p = int(_np(pos)[t]) if pos is not None else int(col)
+            if philox is not None:
+                seed, traj, tag, block0 = philox
+                q = 2 * int(block0) + p
+                pr = philox_pairs(int(seed), int(_np(traj)[t]), int(tag), np.array([q >> 1, (q >> 1) + 1], dtype=np.uint64)).reshape(-1)
+                a, b = (pr[1], pr[2]) if (q & 1) else (pr[0], pr[1])
+            else:
+                row = table[t].numpy() if table.dim() == 2 else table.numpy()
+                a, b = float(row[p]), float(row[p + 1])
+            d = 1.0 - float(_np(norm2)[t])
+            j = 1 if a < d else 0
+            _np(dp)[t], _np(u1)[t], _np(u2)[t], _np(jmask)[t] = d, a, b, j
+            if pos is not None:
+                _np(pos)[t] = p + 1 + j
+            count += j
+        _np(njump)[0] = count
+
+    def jump_select(self, nbatch, jmask, u2, rdm1, rdm2, nproc, proc_site, proc_two, proc_ldl, proc_strength, dt, ops_table, nops, w, total, choice,
+                    ops_sel, status):
+        self._launches += 1
+        site, two = _np(proc_site), _np(proc_two)
+        ldl = _np(proc_ldl).reshape(nproc, 16)
+        strength = _np(proc_strength)
+        g1 = _np(rdm1).reshape(-1, nbatch, 4)
+        g2 = _np(rdm2).reshape(-1, nbatch, 16) if rdm2 is not None else None
+        wv = _np(w).reshape(-1, nproc)
+        ops = _np(ops_table).reshape(nproc, nops)
+        sel = _np(ops_sel).reshape(-1, nops)
+        for t in range(nbatch):
+            if not _np(jmask)[t]:
+                _np(total)[t], _np(choice)[t] = 0.0, -1
+                continue
+            tot = 0.0
+            for k in range(nproc):
+                if two[k]:
+                    acc = float(np.sum((ldl[k] * g2[site[k], t]).real))
+                else:
+                    acc = float(np.sum((ldl[k, :4] * g1[site[k], t]).real))
+                wv[t, k] = acc * (dt * float(strength[k]))
+                tot += wv[t, k]
+            _np(total)[t] = tot
+            ok = np.isfinite(tot) and tot > 0.0
+            if not ok:
+                _np(status)[t] |= 4
+            with np.errstate(all="ignore"):
+                wv[t] = wv[t] / (tot if ok else 1.0)
+                cdf = np.cumsum(wv[t])
+                ch = int(np.sum((cdf / cdf[-1]) <= float(_np(u2)[t])))
+            ch = min(ch, nproc - 1)
+            _np(choice)[t] = ch
+            sel[t] = ops[ch]
+
     def philox_uniform(self, seed, traj_index, tag, nblocks, block0, out):
         """numpy restatement of csrc/yb_philox.cuh (Philox4x32-10, key = seed, counter = (block, tag, traj_lo, traj_hi))."""
         o = out.numpy()

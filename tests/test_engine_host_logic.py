@@ -148,3 +148,25 @@ def test_tdvp_sweeps_greater_than_one_matches_oracle(mode):
     want = O.mps_to_vector(st)
     vec = O.mps_to_vector(O.OracleMPS(got, 0))
     assert abs(np.vdot(want, vec) - np.vdot(want, want)) < 1e-10 * 10 and abs(np.vdot(vec, vec) - np.vdot(want, want)) < 1e-9
+
+
+def test_in_kernel_philox_equals_philox_tables():
+    """rng_mode="philox": drawing the uniforms inside yb_jump_test (BatchedTJM.philox) gives bit for bit the run that reads them from the
+    tables yb_philox_uniform fills -- trajectory stream positions and the per-time-step sample streams included."""
+    import numpy as np
+    from yaqs_b200.rng import philox_source, philox_tables
+    name = "ising10_c1_order2"
+    K = NumpyKernels()
+    eng_t, _, _, traj = engine_for_case(name, K)
+    tu, su = philox_tables(K, 1234, traj, eng_t.p.n_times, eng_t.p.order, K.device)
+    log_t = []
+    res_t, diag_t = eng_t.run(tu, su, log_t)
+    eng_k, _, _, _ = engine_for_case(name, K)
+    eng_k.philox = philox_source(1234, traj, K.device)
+    log_k = []
+    res_k, diag_k = eng_k.run(None, None, log_k)
+    assert eng_t.stats["jumps"] > 0
+    assert np.array_equal(res_t.numpy(), res_k.numpy()) and np.array_equal(diag_t.numpy(), diag_k.numpy())
+    assert len(log_t) == len(log_k)
+    for a, b in zip(log_t, log_k):
+        assert np.array_equal(a["u1"], b["u1"]) and np.array_equal(a["jumped"], b["jumped"])

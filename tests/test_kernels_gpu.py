@@ -846,3 +846,95 @@ def test_heev_rows_top_and_capped_finalize(backends, ks, top):
         assert np.max(np.abs(U.conj().T @ U - np.eye(kp))) < 1e-12 * max(1, k / 16)
         best = (u_ref[:, :kp] * s_ref[:kp]) @ vh_ref[:kp]
         assert np.max(np.abs(U @ V - best)) < 1e-10
+
+
+def test_jump_test_and_select_match_twin(backends):
+    """yb_jump_test (table and in-kernel Philox modes: dp, the uniforms, the mask, stream positions, the jump count) and yb_jump_select
+    (weights from the local density matrices, pdf, numpy's Generator.choice rule, gathered operator rows, zero-weight status) against
+    the numpy twin; the Philox mode also against the table yb_philox_uniform fills."""
+    cuda, twin = backends
+    rng = np.random.default_rng(11)
+    B, L, nproc, nops = 37, 6, 13, 24
+    norm2 = torch.from_numpy(rng.uniform(0.5, 1.0, B))
+    table = torch.from_numpy(rng.random((B, 40)))
+    pos0 = torch.from_numpy(rng.integers(0, 30, B).astype(np.int64))
+    traj = torch.from_numpy(rng.integers(0, 2 ** 40, B).astype(np.int64))
+
+    def run_test(kern, dev, mode):
+        nd = norm2.to(dev)
+        out = {n: torch.zeros(B, dtype=torch.float64, device=dev) for n in ("dp", "u1", "u2")}
+        jm, nj = torch.zeros(B, dtype=torch.int32, device=dev), torch.full((1,), -5, dtype=torch.int32, device=dev)
+        pos = pos0.clone().to(dev)
+        if mode == "table_pos":
+            kern.jump_test(B, nd, table.to(dev), 0, pos, None, out["dp"], out["u1"], out["u2"], jm, nj)
+        elif mode == "table_col":
+            kern.jump_test(B, nd, table.to(dev), 6, None, None, out["dp"], out["u1"], out["u2"], jm, nj)
+        elif mode == "philox_pos":
+            kern.jump_test(B, nd, None, 0, pos, (77, traj.to(dev), 0x5452414A, 0), out["dp"], out["u1"], out["u2"], jm, nj)
+        else:
+            kern.jump_test(B, nd, None, 0, None, (77, traj.to(dev), 0x53414D50, 9), out["dp"], out["u1"], out["u2"], jm, nj)
+        return {k: v.cpu().numpy() for k, v in out.items()}, jm.cpu().numpy(), int(nj.item()), pos.cpu().numpy()
+
+    for mode in ("table_pos", "table_col", "philox_pos", "philox_col"):
+        og, jg, ng, pg = run_test(cuda, "cuda", mode)
+        oc, jc, nc, pc = run_test(twin, "cpu", mode)
+        for k in og:
+            assert np.array_equal(og[k], oc[k]), (mode, k)
+        assert np.array_equal(jg, jc) and ng == nc == int(jg.sum()) and np.array_equal(pg, pc), mode
+        if mode.endswith("pos"):
+            assert np.array_equal(pg, pos0.numpy() + 1 + jg)
+        assert np.array_equal(jg.astype(bool), og["u1"] < og["dp"])
+    # Philox mode == the table yb_philox_uniform fills (positions across block boundaries included)
+    tab = torch.zeros((B, 40), dtype=torch.float64, device="cuda")
+    cuda.philox_uniform(77, traj.cuda(), 0x5452414A, 20, 0, tab)
+    og, _, _, _ = run_test(cuda, "cuda", "philox_pos")
+    tn = tab.cpu().numpy()
+    assert np.array_equal(og["u1"], tn[np.arange(B), pos0.numpy()]) and np.array_equal(og["u2"], tn[np.arange(B), pos0.numpy() + 1])
+
+    # ---- selection
+    rdm1 = torch.from_numpy(rng.standard_normal((L, B, 4)) + 1j * rng.standard_normal((L, B, 4)))
+    rdm1[..., 0] = rdm1[..., 0].abs() + 0.1
+    rdm1[..., 3] = rdm1[..., 3].abs() + 0.1
+    rdm2 = torch.from_numpy(rng.standard_normal((L - 1, B, 16)) + 1j * rng.standard_normal((L - 1, B, 16)))
+    psite = torch.from_numpy(rng.integers(0, L - 1, nproc).astype(np.int32))
+    ptwo = torch.from_numpy((rng.random(nproc) < 0.3).astype(np.int32))
+    ldl = np.zeros((nproc, 16), dtype=np.complex128)
+    for k in range(nproc):
+        m = rng.standard_normal((4, 4)) + 1j * rng.standard_normal((4, 4)) if ptwo[k] else np.pad(np.diag(rng.uniform(0.2, 1.0, 2)), ((0, 2), (0, 2)))
+        mm = m.conj().T @ m if ptwo[k] else m
+        ldl[k] = mm.reshape(-1) if ptwo[k] else np.concatenate([mm[:2, :2].reshape(-1), np.zeros(12)])
+    pldl = torch.from_numpy(ldl)
+    for k in range(nproc):                                    # keep two-site weights positive: rho_2 = identity-like
+        if ptwo[k]:
+            rdm2[psite[k]] = torch.from_numpy(np.tile(np.eye(4).reshape(-1), (B, 1)) * rng.uniform(0.5, 1.0, (B, 1)))
+    strength = torch.from_numpy(rng.uniform(0.05, 0.3, nproc))
+    ops = torch.from_numpy(rng.standard_normal((nproc, nops)) + 1j * rng.standard_normal((nproc, nops)))
+    jmask = torch.from_numpy((rng.random(B) < 0.6).astype(np.int32))
+    jmask[0] = 1
+    u2 = torch.from_numpy(rng.random(B))
+    u2[0] = 0.999999999
+    zero_w = 3                                                # one jumping trajectory with all weights zero -> status bit 4
+    jmask[zero_w] = 1
+    rdm1[:, zero_w] = 0
+    rdm2[:, zero_w] = 0
+
+    def run_sel(kern, dev):
+        w = torch.zeros((B, nproc), dtype=torch.float64, device=dev)
+        tot = torch.zeros(B, dtype=torch.float64, device=dev)
+        ch = torch.zeros(B, dtype=torch.int32, device=dev)
+        sel = torch.zeros(B * nops, dtype=torch.complex128, device=dev)
+        status = torch.zeros(B, dtype=torch.int32, device=dev)
+        kern.jump_select(B, jmask.to(dev), u2.to(dev), rdm1.contiguous().to(dev), rdm2.contiguous().to(dev), nproc, psite.to(dev), ptwo.to(dev), pldl.to(dev),
+                         strength.to(dev), 0.1, ops.contiguous().to(dev), nops, w, tot, ch, sel, status)
+        return w.cpu().numpy(), tot.cpu().numpy(), ch.cpu().numpy(), sel.cpu().numpy().reshape(B, nops), status.cpu().numpy()
+
+    wg, tg, cg, sg, stg = run_sel(cuda, "cuda")
+    wc, tc, cc, sc, stc = run_sel(twin, "cpu")
+    jm = jmask.numpy().astype(bool)
+    assert np.array_equal(cg, cc) and np.array_equal(stg, stc) and stg[zero_w] == 4 and not stg[np.arange(B) != zero_w].any()
+    ok = jm & (np.arange(B) != zero_w)
+    assert np.max(np.abs(tg[ok] - tc[ok])) < 1e-13 and np.max(np.abs(wg[ok] - wc[ok])) < 1e-13
+    assert np.array_equal(sg[ok], ops.numpy()[cg[ok]]) and (cg[~jm] == -1).all()
+    for b in np.nonzero(ok)[0]:                                # numpy's own choice rule on the kernel's pdf
+        cdf = np.cumsum(wg[b]); cdf /= cdf[-1]
+        assert cg[b] == min(int(np.searchsorted(cdf, u2[b].item(), side="right")), nproc - 1)

@@ -537,4 +537,25 @@ int yb_philox_uniform(int nbatch, uint64_t seed, const int64_t* traj_index, uint
     return done("yb_philox_uniform");
 }
 
+int yb_jump_test(int nbatch, const double* norm2, const double* table, int64_t table_stride, int64_t col, int64_t* pos, int use_philox,
+                 uint64_t seed, const int64_t* traj_index, uint32_t tag, uint32_t block0, double* dp, double* u1, double* u2, int32_t* jmask,
+                 int32_t* njump, void* stream) {
+    if (nbatch <= 0) return 0;
+    if (!use_philox && !table) return fail_msg("yb_jump_test: table mode needs the uniform table");
+    if (use_philox && !traj_index) return fail_msg("yb_jump_test: philox mode needs the global trajectory indices");
+    k_jump_test<<<1, 256, 0, (cudaStream_t)stream>>>(nbatch, norm2, table, table_stride, col, (long long*)pos, use_philox, (unsigned long long)seed,
+                                                      (const long long*)traj_index, tag, block0, dp, u1, u2, jmask, njump);
+    return done("yb_jump_test");
+}
+
+int yb_jump_select(int nbatch, const int32_t* jmask, const double* u2, const void* rdm1, const void* rdm2, int nproc, const int32_t* proc_site,
+                   const int32_t* proc_two, const void* proc_ldl, const double* proc_strength, double dt, const void* ops_table, int nops, double* w,
+                   double* total, int32_t* choice, void* ops_sel, int32_t* status, void* stream) {
+    if (nbatch <= 0 || nproc <= 0) return 0;
+    k_jump_select<<<(nbatch + 63) / 64, 64, 0, (cudaStream_t)stream>>>(nbatch, jmask, u2, (const cplx*)rdm1, (const cplx*)rdm2, nproc, proc_site, proc_two,
+                                                                        (const cplx*)proc_ldl, proc_strength, dt, (const cplx*)ops_table, nops, w, total,
+                                                                        choice, (cplx*)ops_sel, status);
+    return done("yb_jump_select");
+}
+
 }  // extern "C"

@@ -388,3 +388,88 @@ __global__ void k_philox_uniform(unsigned long long seed, const long long* __res
         reinterpret_cast<double2*>(ob)[c] = make_double2(u0, u1);
     }
 }
+
+
+// ---------------------------------------------------------------------------------------------------------------------
+// stochastic_process on the device (methods/stochastic_process.py:190-292): the jump test and the selection of the jump process.
+// ---------------------------------------------------------------------------------------------------------------------
+// Jump test for every trajectory: dp = 1 - <psi|psi> (calculate_stochastic_factor, :36-60), jump iff u1 < dp (:238).  The two
+// uniforms a test can consume sit at positions p, p + 1 of the trajectory's stream, p = pos[b] (or `col` for all when pos == NULL):
+//   table mode   u = table[b * stride + p]                       (streams replayed from the reference's seeded numpy generators)
+//   philox mode  u = component (q & 1) of block (q >> 1), q = 2 * block0 + p, of stream (seed, traj[b], tag), drawn HERE
+// pos[b] advances by 1 + jumped -- the doubles the reference's Generator hands out (rng.random() at :238, rng.choice at :257).
+// One CTA walks the whole batch, so the number of jumps needs no atomics and no cleared counter.
+__global__ void __launch_bounds__(256) k_jump_test(int nbatch, const double* __restrict__ norm2, const double* __restrict__ table, long long stride,
+                                                    long long col, long long* pos, int use_philox, unsigned long long seed,
+                                                    const long long* __restrict__ traj, unsigned tag, unsigned block0, double* dp_out,
+                                                    double* u1_out, double* u2_out, int* jmask, int* njump) {
+    __shared__ int cnt[8];
+    int mine = 0;
+    for (int b = threadIdx.x; b < nbatch; b += blockDim.x) {
+        const long long p = pos ? pos[b] : col;
+        double u1, u2;
+        if (use_philox) {
+            const unsigned long long q = 2ull * block0 + (unsigned long long)p;
+            double a0, a1;
+            philox::pair(seed, traj[b], tag, (unsigned)(q >> 1), a0, a1);
+            if (q & 1) { u1 = a1; double c0, c1; philox::pair(seed, traj[b], tag, (unsigned)(q >> 1) + 1u, c0, c1); u2 = c0; }
+            else { u1 = a0; u2 = a1; }
+        } else {
+            u1 = table[(long long)b * stride + p];
+            u2 = table[(long long)b * stride + p + 1];
+        }
+        const double dp = 1.0 - norm2[b];
+        const int jump = (u1 < dp) ? 1 : 0;
+        dp_out[b] = dp; u1_out[b] = u1; u2_out[b] = u2; jmask[b] = jump;
+        if (pos) pos[b] = p + 1 + jump;
+        mine += jump;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+    if ((threadIdx.x & 31) == 0) cnt[threadIdx.x >> 5] = mine;
+    __syncthreads();
+    if (threadIdx.x == 0) { int s = 0; for (int w = 0; w < 8; ++w) s += cnt[w]; *njump = s; }
+}
+
+// Selection of the jump process for the trajectories that jump (create_probability_distribution + rng.choice, :86-187, :257):
+//   w_k = dt gamma_k Re Tr(L_k^dagger L_k rho_site(k))   from the local reduced density matrices of the transfer sweep
+//   total = sum_k w_k (zero / non-finite: status bit 4, :179-187), pdf = w / total, cdf = cumsum(pdf) / cdf[-1],
+//   choice = #{k : cdf_k <= u2} (numpy's Generator.choice: searchsorted(cdf, u, side="right")), clamped to the last process.
+// All sums run in process order, one thread per trajectory.  ops_sel[b] = ops_table[choice]: the operator(s) the application launches take.
+__global__ void k_jump_select(int nbatch, const int* __restrict__ jmask, const double* __restrict__ u2, const cplx* __restrict__ rdm1,
+                              const cplx* __restrict__ rdm2, int nproc, const int* __restrict__ psite, const int* __restrict__ ptwo,
+                              const cplx* __restrict__ pldl, const double* __restrict__ pstrength, double dt, const cplx* __restrict__ ops_table,
+                              int nops, double* w, double* total_out, int* choice_out, cplx* ops_sel, int* status) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nbatch) return;
+    if (!jmask[b]) { total_out[b] = 0.0; choice_out[b] = -1; return; }
+    double* wb = w + (long long)b * nproc;
+    double total = 0.0;
+    for (int k = 0; k < nproc; ++k) {
+        const int site = psite[k];
+        const cplx* m = pldl + (long long)k * 16;
+        double acc = 0.0;
+        if (ptwo[k]) {
+            const cplx* g = rdm2 + ((long long)site * nbatch + b) * 16;
+            for (int e = 0; e < 16; ++e) acc += m[e].x * g[e].x - m[e].y * g[e].y;
+        } else {
+            const cplx* g = rdm1 + ((long long)site * nbatch + b) * 4;
+            for (int e = 0; e < 4; ++e) acc += m[e].x * g[e].x - m[e].y * g[e].y;
+        }
+        const double wk = acc * (dt * pstrength[k]);
+        wb[k] = wk;
+        total += wk;
+    }
+    total_out[b] = total;
+    const bool ok = isfinite(total) && total > 0.0;
+    if (!ok) atomicOr(&status[b], 4);
+    const double safe = ok ? total : 1.0;
+    double last = 0.0;
+    for (int k = 0; k < nproc; ++k) { const double p = wb[k] / safe; wb[k] = p; last += p; }
+    int choice = 0;
+    double cum = 0.0;
+    for (int k = 0; k < nproc; ++k) { cum += wb[k]; choice += ((cum / last) <= u2[b]) ? 1 : 0; }
+    choice = min(choice, nproc - 1);
+    choice_out[b] = choice;
+    for (int e = 0; e < nops; ++e) ops_sel[(long long)b * nops + e] = ops_table[(long long)choice * nops + e];
+}

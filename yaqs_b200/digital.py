@@ -13,7 +13,7 @@ import torch
 from .circuits import CompiledCircuit, compile_circuit
 from .engine import BatchedTJM, EngineParams
 from .params import engine_observables
-from .rng import STREAM_SHOTS, numpy_tables, philox_tables
+from .rng import STREAM_SHOTS, numpy_tables, philox_source
 
 
 def validate_digital_noise(noise, length: int) -> None:
@@ -77,7 +77,8 @@ def run_digital(simulator, initial_state, operator, sp, noise, result):
             tu, _ = numpy_tables(sp.random_seed, idx, max(n2q, 1), 1)
             tu = torch.from_numpy(tu).to(dev)
         else:
-            tu, _ = philox_tables(K, sp.random_seed, idx, max(n2q, 1), 1, dev)
+            tu = None
+            eng.philox = philox_source(sp.random_seed, idx, dev)
         log = [] if simulator.collect_log else None
         r, dg = eng.run_digital(compiled.layers, tu, sp.sample_layers, sp.gate_mode, log)
         res_local[w0: w0 + len(idx)] = r.cpu().numpy()

@@ -21,6 +21,7 @@ import scipy.linalg
 import torch
 
 from .gates import GateLibrary
+from .rng import STREAM_SAMPLE, STREAM_TRAJECTORY
 from .kernels import (DIST, LANCZOS_PITCH, OP_ABSORB_L, OP_ABSORB_R, OP_ENVL1, OP_ENVL3, OP_ENVR3, OP_EVEC, OP_GRAM, OP_LCONTRACT, OP_MERGE,
                       OP_RCONTRACT, OP_ROTATE, OP_ROTATE_TOP, SVD_COLS, SVD_META, SVD_ORIENT_COLS, SVD_ORIENT_ROWS, SVD_ROWS, SVD_THETA, TRUNC_MODES, Buf, Ext)
 
@@ -68,6 +69,17 @@ class JumpProcess:
     strength: float
     ldl: np.ndarray | None = None   # L^dagger L (2x2 or 4x4) for non-scalar weights
     ops: tuple = ()                 # jump operator(s): (L,) for one/adjacent, (F0, F1) for long-range Pauli
+
+
+@dataclass
+class Uniforms:
+    """Where the two uniforms of one jump test come from (yb_jump_test): rows of a device table (streams replayed from the reference's
+    seeded numpy generators, or pre-filled Philox tables) or the Philox generator inside the kernel; ``pos`` = per-trajectory stream
+    position (advanced by the kernel by 1 + jumped), else column ``col`` for every trajectory."""
+    table: torch.Tensor | None = None       # [B, n] float64, contiguous rows
+    col: int = 0
+    pos: torch.Tensor | None = None         # int64 [B]
+    philox: tuple | None = None             # (seed, global trajectory indices int64 [B], stream tag, first block)
 
 
 def layout_chi(params: "EngineParams") -> int | None:
@@ -261,6 +273,17 @@ class BatchedTJM:
         self.keep = torch.ones(B, dtype=torch.int32, device=dev)
         self.counter = torch.zeros(1, dtype=torch.int32, device=dev)
         self.lz_count = torch.zeros(2, dtype=torch.int32, device=dev)
+        # jump test / selection outputs (yb_jump_test, yb_jump_select)
+        self.jt_dp = torch.zeros(B, dtype=torch.float64, device=dev)
+        self.jt_u1 = torch.zeros(B, dtype=torch.float64, device=dev)
+        self.jt_u2 = torch.zeros(B, dtype=torch.float64, device=dev)
+        self.jt_mask = torch.zeros(B, dtype=torch.int32, device=dev)
+        self.jt_n = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.jt_total = torch.zeros(B, dtype=torch.float64, device=dev)
+        self.jt_choice = torch.zeros(B, dtype=torch.int32, device=dev)
+        self.jt_ops = torch.zeros(B * self.JT_NOPS, dtype=C128, device=dev)
+        self.jt_w = None                                    # [B, n_proc] weights / pdf of the current noise context (allocated per context)
+        self.philox = None                                  # (seed, global trajectory indices int64 [B], sample offset): draw the uniforms in the kernel
         self.status = torch.zeros(B, dtype=torch.int32, device=dev)
         self.alpha = torch.zeros(B * LANCZOS_PITCH, dtype=torch.float64, device=dev)
         self.beta = torch.zeros(B * LANCZOS_PITCH, dtype=torch.float64, device=dev)
@@ -359,6 +382,8 @@ class BatchedTJM:
     # ------------------------------------------------------------------------------------------------------------------
     # small helpers
     # ------------------------------------------------------------------------------------------------------------------
+    JT_NOPS = 24                 # operator row of a process: one-site op on its first site (4), on its second site (4), two-site op (16)
+
     def env(self, j: int, left: bool) -> Buf:
         return Buf(self.lenv if left else self.renv, self.lay.env_off[j], self.lay.env_slot[j])
 
@@ -1278,66 +1303,67 @@ class BatchedTJM:
             tab["unitary_a"] = np.array([unitary(pr.ops[0]) if pr.kind in ("one", "pauli_lr") else True for pr in procs], dtype=bool)
             tab["unitary_b"] = np.array([unitary(pr.ops[1]) if pr.kind == "pauli_lr" else True for pr in procs], dtype=bool)
             tab["ops_c"] = torch.from_numpy(np.stack([pr.ops[0] if pr.kind in ("adjacent", "pauli_adj") else eye4 for pr in procs]).astype(np.complex128)).to(dev)
+            # process tables of yb_jump_select: site, one- / two-site weight, L^dagger L (identity for Pauli processes), operator rows
+            ldl = np.zeros((len(procs), 16), dtype=np.complex128)
+            for k, pr in enumerate(procs):
+                if pr.kind == "adjacent":
+                    ldl[k] = np.asarray(pr.ldl, dtype=np.complex128).reshape(-1)
+                else:
+                    ldl[k, :4] = (np.asarray(pr.ldl, dtype=np.complex128) if pr.kind == "one" else eye2).reshape(-1)
+            tab["psite"] = torch.tensor([pr.sites[0] for pr in procs], dtype=torch.int32, device=dev)
+            tab["ptwo"] = torch.tensor([1 if pr.kind == "adjacent" else 0 for pr in procs], dtype=torch.int32, device=dev)
+            tab["pldl"] = torch.from_numpy(ldl).to(dev)
+            tab["ops_all"] = torch.cat([tab["ops_a"].reshape(len(procs), 4), tab["ops_b"].reshape(len(procs), 4), tab["ops_c"].reshape(len(procs), 16)],
+                                       dim=1).contiguous()
             ctx["dev"] = tab
         return tab
 
-    def jump_weights(self, st: BatchedState, dt: float, mask) -> torch.Tensor:
-        """[B, n_proc] un-normalised weights dt * gamma * ||L psi||^2 in site-sweep order (stochastic_process.py:86-187): one
-        transfer sweep for the local density matrices, then one batched contraction Tr(L^dagger L rho) per process kind (Pauli
-        processes: L^dagger L = 1, the centre-site norm of :159-163)."""
-        tab = self._jump_tables()
-        g1, g2 = self.rho_sweep(st, tab["need1"], tab["need2"], mask)
-        w = torch.zeros((self.B, len(self.jump_table)), dtype=torch.float64, device=self.dev)
-        for name, g in (("one", g1), ("two", g2)):
-            if name in tab:
-                cols, sites, mats = tab[name]
-                w[:, cols] = torch.einsum("kop,kbop->bk", mats, g[sites]).real
-        return w * (dt * tab["strength"])[None, :]
-
-    def stochastic_process(self, st: BatchedState, dt: float, u1: torch.Tensor | None, u2: torch.Tensor | None, log: list | None = None,
+    def stochastic_process(self, st: BatchedState, dt: float, u1, u2: torch.Tensor | None = None, log: list | None = None,
                            tag: str = "") -> torch.Tensor | None:
-        """One jump test for every trajectory.  u1/u2: [B] uniforms (u2 is consumed only by trajectories that jump).
-        Returns the int32 jump mask (or None when there is no noise model).  Host synchronisations: one read of the jump mask,
-        and -- only when somebody jumps -- one read of (weight totals, selected processes), from which the whole launch plan
-        of the jump application is made on the host."""
+        """One jump test for every trajectory (stochastic_process.py:190-292).  ``u1``: a ``Uniforms`` source, or (older callers) the
+        [B] tensors u1 / u2 themselves (u2 is consumed only by trajectories that jump).  Returns the int32 jump mask (or None when
+        there is no noise model).  The test itself (dp = 1 - norm, u1 < dp, stream positions) is yb_jump_test; when somebody jumps,
+        one transfer sweep gives the local density matrices and yb_jump_select turns them into weights, pdf, the selected process
+        and its operator rows.  Host synchronisations: one read of the jump mask, and -- only when somebody jumps -- one read of
+        (weight totals, selected processes), from which the whole launch plan of the jump application is made on the host."""
         K, B, lay, d, n = self.K, self.B, self.lay, self.d, self.L
         K.phase = "jumps"
         if self.noise is None:
             self.normalize_site(st, 0)                      # :226-231 (the uniform is not drawn)
             return None
+        src = u1 if isinstance(u1, Uniforms) else Uniforms(table=torch.stack([u1, u2], dim=1).contiguous())
         K.norm2(B, None, st.ext(0), st.ext(1), d, st.site(0), self.norm_buf)
-        dp = 1.0 - self.norm_buf
-        jump = (u1 < dp)
-        jmask = jump.to(torch.int32)
-        jump_h = jump.cpu().numpy()                         # sync 1
+        K.jump_test(B, self.norm_buf, src.table, src.col, src.pos, src.philox, self.jt_dp, self.jt_u1, self.jt_u2, self.jt_mask, self.jt_n)
+        jmask = self.jt_mask.clone()                        # (the buffer belongs to the next test)
+        jump_h = jmask.cpu().numpy().astype(bool)           # sync 1
         njump = int(jump_h.sum())
         rec = None
         if log is not None:
-            rec = dict(tag=tag, dp=dp.cpu().numpy().copy(), u1=u1.cpu().numpy().copy(), jumped=jump_h.copy(), choice=None, pdf=None)
+            rec = dict(tag=tag, dp=self.jt_dp.cpu().numpy().copy(), u1=self.jt_u1.cpu().numpy().copy(), jumped=jump_h.copy(), choice=None, pdf=None)
             log.append(rec)
         if njump < B:
             self.normalize_site(st, 0, None if njump == 0 else (1 - jmask))
         if njump == 0:
             return jmask
         self.stats["jumps"] += njump
-        w = self.jump_weights(st, dt, jmask)
-        total = w.sum(dim=1)
-        safe = torch.where(jump & torch.isfinite(total) & (total > 0), total, torch.ones_like(total))
-        probs = w / safe[:, None]
-        cdf = torch.cumsum(probs, dim=1)
-        cdf = cdf / torch.where(jump, cdf[:, -1], torch.ones_like(total))[:, None]
-        choice = torch.searchsorted(cdf, u2[:, None].contiguous(), right=True).squeeze(1).clamp(max=len(self.jump_table) - 1)
-        host = torch.stack([total, choice.to(torch.float64)]).cpu().numpy()      # sync 2
-        total_h, choice_h = host[0], host[1].astype(np.int64)
+        tab = self._jump_tables()
+        nproc = len(self.jump_table)
+        if self.jt_w is None or self.jt_w.shape[1] != nproc:
+            self.jt_w = torch.zeros((B, nproc), dtype=torch.float64, device=self.dev)
+        self.rho_sweep(st, tab["need1"], tab["need2"], jmask)          # local density matrices of the jumping trajectories
+        K.jump_select(B, jmask, self.jt_u2, self._rdm1_all, self._rdm2_all if tab["need2"] else None, nproc, tab["psite"], tab["ptwo"], tab["pldl"],
+                      tab["strength"], dt, tab["ops_all"], self.JT_NOPS, self.jt_w, self.jt_total, self.jt_choice, self.jt_ops, self.status)
+        choice = self.jt_choice.to(torch.int64)
+        host = torch.stack([self.jt_total, choice.to(torch.float64)]).cpu().numpy()      # sync 2
+        total_h, choice_h = host[0], np.where(jump_h, host[1], 0).astype(np.int64)
         bad_h = jump_h & ~(np.isfinite(total_h) & (total_h > 0))
         if bad_h.any():
-            self.status |= torch.from_numpy(bad_h.astype(np.int32) * STATUS_ZERO_JUMP_WEIGHT).to(self.dev)
             raise ValueError("Jump probability weights are zero or non-finite. Reduce process strengths and/or the timestep dt so that "
                              "dt * strength * ||L|psi>||^2 remains representable.")
         if rec is not None:
             rec["choice"] = choice_h.copy()
-            rec["pdf"] = probs.cpu().numpy().copy()
-            rec["u2"] = u2.cpu().numpy().copy()
+            rec["pdf"] = self.jt_w.cpu().numpy().copy()
+            rec["u2"] = self.jt_u2.cpu().numpy().copy()
         self._apply_jumps(st, jmask, choice, jump_h, choice_h)
         return jmask
 
@@ -1408,25 +1434,25 @@ class BatchedTJM:
         plan = torch.from_numpy(np.concatenate([sa_h[None], sb_h[None], sc_h[None], lit_h, red_h])).to(dev)      # one upload
         site_a, site_b, site_c = plan[0], plan[1], plan[2]
         lit_d, red_d = plan[3: 3 + n], plan[3 + n: 3 + 2 * n]
+        # the operator rows of the selected processes were gathered by yb_jump_select: [B][4 | 4 | 16] = first-site op, second-site op, pair op
+        nops = self.JT_NOPS
+        ops_a, ops_b, ops_c = self.jt_ops, self.jt_ops[4:], self.jt_ops[8:]
         if (sa_h >= 0).any():
-            ops_a = tab["ops_a"][choice].contiguous()
             mask_a = (site_a >= 0).to(torch.int32)
             for s_ in np.unique(sa_h[sa_h >= 0]):
                 s_ = int(s_)
-                K.apply_local_op(B, mask_a, site_a, s_, st.ext(s_), st.ext(s_ + 1), d, ops_a.view(-1), d * d, st.site(s_), lay.cap[s_] * lay.cap[s_ + 1])
+                K.apply_local_op(B, mask_a, site_a, s_, st.ext(s_), st.ext(s_ + 1), d, ops_a, nops, st.site(s_), lay.cap[s_] * lay.cap[s_ + 1])
         if (sb_h >= 0).any():
-            ops_b = tab["ops_b"][choice].contiguous()
             mask_b = (site_b >= 0).to(torch.int32)
             for s_ in np.unique(sb_h[sb_h >= 0]):
                 s_ = int(s_)
-                K.apply_local_op(B, mask_b, site_b, s_, st.ext(s_), st.ext(s_ + 1), d, ops_b.view(-1), d * d, st.site(s_), lay.cap[s_] * lay.cap[s_ + 1])
+                K.apply_local_op(B, mask_b, site_b, s_, st.ext(s_), st.ext(s_ + 1), d, ops_b, nops, st.site(s_), lay.cap[s_] * lay.cap[s_ + 1])
         if (sc_h >= 0).any():
-            ops_c = tab["ops_c"][choice].contiguous()
             for s_ in np.unique(sc_h[sc_h >= 0]):
                 s_ = int(s_)
                 m_s = (site_c == s_).to(torch.int32)
                 th = self.merge(st, s_, m_s)
-                K.apply_local_op(B, m_s, None, 0, st.ext(s_), st.ext(s_ + 2), d * d, ops_c.view(-1), d * d * d * d, th, lay.cap[s_] * lay.cap[s_ + 2])
+                K.apply_local_op(B, m_s, None, 0, st.ext(s_), st.ext(s_ + 2), d * d, ops_c, nops, th, lay.cap[s_] * lay.cap[s_ + 2])
                 self.split_theta(st, s_, "right", user, m_s, fast=True)
         # normalize("B", "SVD"): right-to-left merged SVD shifts.  Where the left neighbour is still a left isometry the
         # reduced shift is identical; where it carries a jump operator the literal merge + split is needed.
@@ -1513,10 +1539,12 @@ class BatchedTJM:
             if self.noise is None:
                 self.stochastic_process(state, p.dt, None, None, log, tag)
                 return
-            u1 = self._traj_u.gather(1, self._pos[:, None]).squeeze(1)
-            u2 = self._traj_u.gather(1, (self._pos + 1)[:, None]).squeeze(1)
-            jm = self.stochastic_process(state, p.dt, u1, u2, log, tag)
-            self._pos += 1 + jm.to(torch.int64)
+            # the trajectory stream: position _pos[b], advanced inside yb_jump_test by the doubles the reference's Generator hands out
+            if self.philox is not None:
+                src = Uniforms(philox=(self.philox[0], self.philox[1], STREAM_TRAJECTORY, 0), pos=self._pos)
+            else:
+                src = Uniforms(table=self._traj_u, pos=self._pos)
+            self.stochastic_process(state, p.dt, src, None, log, tag)
 
         phi = self.phi
         if p.order == 2:
@@ -1533,8 +1561,11 @@ class BatchedTJM:
                     self.stochastic_process(psi, p.dt, None, None, log, f"sample{j}")
                 elif final_sample_from_trajectory_stream and j == nt - 1:
                     traj_jump_test(psi, f"sample{j}")
+                elif self.philox is not None:               # the measurement copy's own stream: block j + offset of the "SAMP" stream
+                    self.stochastic_process(psi, p.dt, Uniforms(philox=(self.philox[0], self.philox[1], STREAM_SAMPLE, j + self.philox[2])), None,
+                                            log, f"sample{j}")
                 else:
-                    self.stochastic_process(psi, p.dt, sample_uniforms[:, j, 0].contiguous(), sample_uniforms[:, j, 1].contiguous(), log, f"sample{j}")
+                    self.stochastic_process(psi, p.dt, Uniforms(table=sample_uniforms.view(self.B, -1), col=2 * j), None, log, f"sample{j}")
                 record(psi, j if p.sample_timesteps else 0)
 
             if nt == 1:
@@ -1871,10 +1902,11 @@ class BatchedTJM:
                             if self.noise is None:
                                 self.stochastic_process(st, 1.0, None, None, log, f"gate{tuple(gate.sites)}")
                             else:
-                                u1 = traj_uniforms.gather(1, pos[:, None]).squeeze(1)
-                                u2 = traj_uniforms.gather(1, (pos + 1)[:, None]).squeeze(1)
-                                jm = self.stochastic_process(st, 1.0, u1, u2, log, f"gate{tuple(gate.sites)}")
-                                pos += 1 + jm.to(torch.int64)
+                                if self.philox is not None:
+                                    src = Uniforms(philox=(self.philox[0], self.philox[1], STREAM_TRAJECTORY, 0), pos=pos)
+                                else:
+                                    src = Uniforms(table=traj_uniforms, pos=pos)
+                                self.stochastic_process(st, 1.0, src, None, log, f"gate{tuple(gate.sites)}")      # (advances pos)
                 if sample_layers:
                     for _ in range(layer.sample_points):
                         col += 1

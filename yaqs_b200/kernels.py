@@ -86,7 +86,7 @@ def load_library() -> ctypes.CDLL:
 EXPORTED_SYMBOLS = [
     "yb_last_error", "yb_version", "yb_launch_count", "yb_set_flop_counter", "yb_set_option", "yb_workspace_bytes", "yb_gemm", "yb_rcontract_mpo", "yb_wapply", "yb_env_identity", "yb_lanczos_init",
     "yb_lanczos_step", "yb_lanczos_combine", "yb_svd_prepare", "yb_svd_round", "yb_svd_check", "yb_svd_finalize", "yb_svd_ambiguous", "yb_heev", "yb_heev_rows", "yb_heev_rows_top", "yb_svd_finalize_top", "yb_cholqr_factor", "yb_cholqr_refine", "yb_cholqr_finalize", "yb_svd_select", "yb_svd_gather",
-    "yb_unpack_vh", "yb_copy_packed", "yb_apply_local_op", "yb_mpo_site_apply", "yb_norm2", "yb_scale", "yb_local_rdm", "yb_philox_uniform",
+    "yb_jump_test", "yb_jump_select", "yb_unpack_vh", "yb_copy_packed", "yb_apply_local_op", "yb_mpo_site_apply", "yb_norm2", "yb_scale", "yb_local_rdm", "yb_philox_uniform",
 ]
 
 
@@ -339,6 +339,26 @@ class CudaKernels:
     def scale(self, nbatch, mask, el, er, dphys, scale, a: Buf, max_elems, rsqrt_mode: bool = False):
         self._timed_call("local", lambda: self._check(self.lib.yb_scale(nbatch, self._ptr(mask), self._ext(el), self._ext(er), dphys, self._ptr(scale), self._cptr(a),
                                       ctypes.c_int64(a.stride), int(max_elems), int(bool(rsqrt_mode)), self._stream())))
+
+    # -- stochastic_process on the device -------------------------------------------------------------------------------
+    def jump_test(self, nbatch, norm2, table, col, pos, philox, dp, u1, u2, jmask, njump):
+        """table: [B, n] float64 rows (table mode) or None; philox: (seed, traj int64 [B], tag, block0) or None; pos: int64 [B] or None."""
+        use_philox = philox is not None
+        seed, traj, tag, block0 = philox if use_philox else (0, None, 0, 0)
+        if not use_philox and (table.dtype != torch.float64 or table.stride(-1) != 1):
+            raise KernelError("jump_test: contiguous float64 rows expected")
+        stride = 0 if table is None else (table.stride(0) if table.dim() == 2 else 0)
+        self._timed_call("local", lambda: self._check(self.lib.yb_jump_test(
+            int(nbatch), self._ptr(norm2), self._ptr(table), ctypes.c_int64(stride), ctypes.c_int64(int(col)), self._ptr(pos), int(use_philox),
+            ctypes.c_uint64(int(seed) & (2 ** 64 - 1)), self._ptr(traj), ctypes.c_uint32(int(tag)), ctypes.c_uint32(int(block0)), self._ptr(dp),
+            self._ptr(u1), self._ptr(u2), self._ptr(jmask), self._ptr(njump), self._stream())))
+
+    def jump_select(self, nbatch, jmask, u2, rdm1, rdm2, nproc, proc_site, proc_two, proc_ldl, proc_strength, dt, ops_table, nops, w, total, choice,
+                    ops_sel, status):
+        self._timed_call("local", lambda: self._check(self.lib.yb_jump_select(
+            int(nbatch), self._ptr(jmask), self._ptr(u2), self._ptr(rdm1), self._ptr(rdm2), int(nproc), self._ptr(proc_site), self._ptr(proc_two),
+            self._ptr(proc_ldl), self._ptr(proc_strength), ctypes.c_double(dt), self._ptr(ops_table), int(nops), self._ptr(w), self._ptr(total),
+            self._ptr(choice), self._ptr(ops_sel), self._ptr(status), self._stream())))
 
     def philox_uniform(self, seed: int, traj_index, tag: int, nblocks: int, block0: int, out):
         """out [nbatch, 2 * nblocks] float64 (contiguous rows); traj_index int64 [nbatch] on the device."""

@@ -64,3 +64,10 @@ def philox_tables(kernels, seed: int | None, traj_indices, n_times: int, order: 
         kernels.philox_uniform(base, idx, STREAM_SAMPLE, n_times, sample_offset, flat)
         samp = flat.view(nb, n_times, 2)
     return traj, samp
+
+
+def philox_source(seed: int | None, traj_indices, device, sample_offset: int = 0):
+    """(seed, global trajectory indices int64 [B] on the device, sample offset): what ``BatchedTJM.philox`` takes to draw the uniforms
+    of every jump test inside ``yb_jump_test`` -- the same numbers ``philox_tables`` would hold, without the tables."""
+    base = int(seed) if seed is not None else int(np.random.SeedSequence().entropy % (2 ** 64))
+    return base, torch.as_tensor(np.asarray(traj_indices, dtype=np.int64), device=device), int(sample_offset)

@@ -18,7 +18,7 @@ from .containers import Hamiltonian, Result, State
 from .engine import BatchedTJM, BatchLayout, EngineParams, layout_chi
 from .noise import NoiseModel
 from .params import AnalogSimParams, DigitalSimParams, engine_observables
-from .rng import make_disorder_rng, numpy_tables, philox_tables
+from .rng import make_disorder_rng, numpy_tables, philox_source
 
 
 # Per-trajectory device status bits (engine.STATUS_*) and the exception the reference raises in the same situation:
@@ -298,8 +298,9 @@ class _LaneRun:
                 self.su_host = self.su_host.pin_memory() if self.su_host is not None else None
             self.tu = torch.zeros_like(self.tu_host, device=dev)
             self.su = torch.zeros_like(self.su_host, device=dev) if self.su_host is not None else None
-        else:                                              # device generator: a step has no host input at all
-            self.tu, self.su = philox_tables(K, seed, idx, nt, ep.order, dev)
+        else:                                              # device generator: the uniforms are drawn inside the jump-test kernel (no tables, no host input)
+            self.tu = self.su = None
+            self.eng.philox = philox_source(seed, idx, dev)
         nobs = len(obs)
         self.res_host = torch.zeros((self.ncol, nb, nobs), dtype=torch.float64)
         self.diag_host = torch.zeros((self.ncol, nb, 3), dtype=torch.float64)
