@@ -272,6 +272,16 @@ int yb_jump_select(int nbatch, const int32_t* jmask, const double* u2, const voi
                    const int32_t* proc_two, const void* proc_ldl, const double* proc_strength, double dt, const void* ops_table, int nops, double* w,
                    double* total, int32_t* choice, void* ops_sel, int32_t* status, void* stream);
 
+/* ---- observables and diagnostics of a recorded column ------------------------------------------------------------------
+ * yb_observables: out[b * out_stride + col[k]] = Re sum_e mats[k][e] * rdm[site[k]][b][e] for the nobs local observables (one-site:
+ * 4 entries of rdm1 [L][B][4]; two[k] != 0: 16 entries of rdm2 [L - 1][B][16]) -- MPS.expect / evaluate_observables
+ * (core/data_structures/mps.py:1178-1234) on the local reduced density matrices of the transfer sweep; an imaginary part >= 1e-13
+ * raises status bit 8 (the reference asserts, :1233).
+ * yb_diagnostics: out[b] = (sum chi^3, max(dphys, max chi), sum chi) over the inner bonds (mps.py:549-602), bond = int32 [B][L + 1]. */
+int yb_observables(int nbatch, int nobs, const int32_t* col, const int32_t* site, const int32_t* two, const void* mats, const void* rdm1,
+                   const void* rdm2, double* out, int64_t out_stride, int32_t* status, void* stream);
+int yb_diagnostics(int nbatch, int length, int dphys, const int32_t* bond, double* out, int64_t out_stride, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -659,6 +659,29 @@ class NumpyKernels:
             _np(choice)[t] = ch
             sel[t] = ops[ch]
 
+    def observables(self, nbatch, nobs, col, site, two, mats, rdm1, rdm2, out, out_stride, status):
+        self._launches += 1
+        m = _np(mats).reshape(nobs, 16)
+        g1 = _np(rdm1).reshape(-1, nbatch, 4)
+        g2 = _np(rdm2).reshape(-1, nbatch, 16) if rdm2 is not None else None
+        o = _np(out)
+        for k in range(nobs):
+            s_, c = int(_np(site)[k]), int(_np(col)[k])
+            for t in range(nbatch):
+                v = complex(np.sum(m[k] * g2[s_, t])) if _np(two)[k] else complex(np.sum(m[k, :4] * g1[s_, t]))
+                o[t * out_stride + c] = v.real
+                if v.imag >= 1e-13:
+                    _np(status)[t] |= 8
+
+    def diagnostics(self, nbatch, length, dphys, bond, out, out_stride):
+        self._launches += 1
+        bd = _np(bond).reshape(-1, length + 1)[:nbatch, 1:length].astype(np.float64)
+        o = _np(out)
+        for t in range(nbatch):
+            o[t * out_stride + 0] = float((bd[t] ** 3).sum())
+            o[t * out_stride + 1] = float(max(dphys, bd[t].max())) if bd.shape[1] else float(dphys)
+            o[t * out_stride + 2] = float(bd[t].sum())
+
     def philox_uniform(self, seed, traj_index, tag, nblocks, block0, out):
         """numpy restatement of csrc/yb_philox.cuh (Philox4x32-10, key = seed, counter = (block, tag, traj_lo, traj_hi))."""
         o = out.numpy()

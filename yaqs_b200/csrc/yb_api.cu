@@ -558,4 +558,19 @@ int yb_jump_select(int nbatch, const int32_t* jmask, const double* u2, const voi
     return done("yb_jump_select");
 }
 
+int yb_observables(int nbatch, int nobs, const int32_t* col, const int32_t* site, const int32_t* two, const void* mats, const void* rdm1,
+                   const void* rdm2, double* out, int64_t out_stride, int32_t* status, void* stream) {
+    if (nbatch <= 0 || nobs <= 0) return 0;
+    const long long n = (long long)nbatch * nobs;
+    k_observables<<<(int)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(nbatch, nobs, col, site, two, (const cplx*)mats, (const cplx*)rdm1,
+                                                                             (const cplx*)rdm2, out, out_stride, status);
+    return done("yb_observables");
+}
+
+int yb_diagnostics(int nbatch, int length, int dphys, const int32_t* bond, double* out, int64_t out_stride, void* stream) {
+    if (nbatch <= 0) return 0;
+    k_diagnostics<<<(nbatch + 127) / 128, 128, 0, (cudaStream_t)stream>>>(nbatch, length, dphys, bond, out, out_stride);
+    return done("yb_diagnostics");
+}
+
 }  // extern "C"

@@ -473,3 +473,34 @@ __global__ void k_jump_select(int nbatch, const int* __restrict__ jmask, const d
     choice_out[b] = choice;
     for (int e = 0; e < nops; ++e) ops_sel[(long long)b * nops + e] = ops_table[(long long)choice * nops + e];
 }
+
+
+// Expectation values of the local observables from the reduced density matrices of the transfer sweep (mps.py:1178-1234):
+// out[b][col_k] = Re sum_e mats[k][e] rdm[site_k][b][e]; an imaginary part >= 1e-13 raises status bit 8 (the reference asserts, :1233).
+__global__ void k_observables(int nbatch, int nobs, const int* __restrict__ col, const int* __restrict__ site, const int* __restrict__ two,
+                              const cplx* __restrict__ mats, const cplx* __restrict__ rdm1, const cplx* __restrict__ rdm2, double* out,
+                              long long out_stride, int* status) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)nbatch * nobs) return;
+    const int k = (int)(t / nbatch), b = (int)(t - (long long)k * nbatch);       // consecutive threads = consecutive trajectories of one observable
+    const cplx* m = mats + (long long)k * 16;
+    const int ne = two[k] ? 16 : 4;
+    const cplx* g = two[k] ? rdm2 + ((long long)site[k] * nbatch + b) * 16 : rdm1 + ((long long)site[k] * nbatch + b) * 4;
+    double re = 0.0, im = 0.0;
+    for (int e = 0; e < ne; ++e) { re += m[e].x * g[e].x - m[e].y * g[e].y; im += m[e].x * g[e].y + m[e].y * g[e].x; }
+    out[(long long)b * out_stride + col[k]] = re;
+    if (im >= 1e-13) atomicOr(&status[b], 8);
+}
+
+// Bond diagnostics of every trajectory (mps.py:549-602): out[b] = (sum chi^3, max(d, max chi), sum chi) over the inner bonds 1 .. L-1.
+__global__ void k_diagnostics(int nbatch, int length, int dphys, const int* __restrict__ bond, double* out, long long out_stride) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nbatch) return;
+    const int* bb = bond + (long long)b * (length + 1);
+    double cost = 0.0, total = 0.0;
+    int mx = dphys;
+    for (int j = 1; j < length; ++j) { const double c = (double)bb[j]; cost += c * c * c; total += c; mx = max(mx, bb[j]); }
+    out[(long long)b * out_stride + 0] = cost;
+    out[(long long)b * out_stride + 1] = (double)mx;
+    out[(long long)b * out_stride + 2] = total;
+}

@@ -1087,11 +1087,16 @@ class BatchedTJM:
                 if not isinstance(m, str) and len(s) == 2 and s[1] != s[0] + 1:
                     raise AssertionError("Only nearest-neighbor observables are currently implemented.")
             tab = {"need1": sorted({s for _, _, s in one}), "need2": sorted({s for _, _, s in two}), "any": bool(one or two)}
-            for name, items in (("one", one), ("two", two)):
-                if items:
-                    tab[name] = (torch.tensor([k for k, _, _ in items], dtype=torch.int64, device=self.dev),
-                                 torch.tensor([s for _, _, s in items], dtype=torch.int64, device=self.dev),
-                                 torch.from_numpy(np.stack([m for _, m, _ in items])).to(self.dev))
+            items = [(k, m, s, 0) for k, m, s in one] + [(k, m, s, 1) for k, m, s in two]
+            if items:                                       # tables of yb_observables: result column, site, one- / two-site, operator (16 slots)
+                mats = np.zeros((len(items), 16), dtype=np.complex128)
+                for row, (_, m, _, tw) in enumerate(items):
+                    mats[row, : 16 if tw else 4] = np.asarray(m, dtype=np.complex128).reshape(-1)
+                tab["n"] = len(items)
+                tab["col"] = torch.tensor([k for k, _, _, _ in items], dtype=torch.int32, device=self.dev)
+                tab["site"] = torch.tensor([s for _, _, s, _ in items], dtype=torch.int32, device=self.dev)
+                tab["two"] = torch.tensor([tw for _, _, _, tw in items], dtype=torch.int32, device=self.dev)
+                tab["mats"] = torch.from_numpy(mats).to(self.dev)
             self._obs_tab = tab
         return self._obs_tab
 
@@ -1102,13 +1107,9 @@ class BatchedTJM:
         self.K.phase = "observables"
         res = torch.zeros((self.B, len(self.observables)), dtype=torch.float64, device=self.dev)
         if tab["any"]:
-            g1, g2 = self.rho_sweep(st, tab["need1"], tab["need2"])
-            for name, g in (("one", g1), ("two", g2)):
-                if name in tab:
-                    cols, sites, mats = tab[name]
-                    val = torch.einsum("kop,kbop->bk", mats, g[sites])
-                    res[:, cols] = val.real
-                    self.status |= (val.imag >= 1e-13).any(dim=1).to(torch.int32) * STATUS_IMAG_PART
+            self.rho_sweep(st, tab["need1"], tab["need2"])
+            self.K.observables(self.B, tab["n"], tab["col"], tab["site"], tab["two"], tab["mats"], self._rdm1_all,
+                               self._rdm2_all if tab["need2"] else None, res, res.shape[1], self.status)
         self._spectra_now = {}
         for k, (mat, sites) in enumerate(self.observables):
             if not isinstance(mat, str):
@@ -1234,14 +1235,8 @@ class BatchedTJM:
 
     def diagnostics(self, st: BatchedState) -> torch.Tensor:
         """[B, 3]: cost = sum chi^3, max bond (includes d, mps.py:560-565), total bond (mps.py:549-602)."""
-        inner = st.bond[:, 1:self.L].to(torch.float64)
         out = torch.zeros((self.B, 3), dtype=torch.float64, device=self.dev)
-        if inner.shape[1] > 0:
-            out[:, 0] = (inner ** 3).sum(dim=1)
-            out[:, 2] = inner.sum(dim=1)
-            out[:, 1] = torch.clamp(inner.max(dim=1).values, min=float(self.d))
-        else:
-            out[:, 1] = float(self.d)
+        self.K.diagnostics(self.B, self.L, self.d, st.bond, out, 3)
         return out
 
     # ------------------------------------------------------------------------------------------------------------------

@@ -86,7 +86,7 @@ def load_library() -> ctypes.CDLL:
 EXPORTED_SYMBOLS = [
     "yb_last_error", "yb_version", "yb_launch_count", "yb_set_flop_counter", "yb_set_option", "yb_workspace_bytes", "yb_gemm", "yb_rcontract_mpo", "yb_wapply", "yb_env_identity", "yb_lanczos_init",
     "yb_lanczos_step", "yb_lanczos_combine", "yb_svd_prepare", "yb_svd_round", "yb_svd_check", "yb_svd_finalize", "yb_svd_ambiguous", "yb_heev", "yb_heev_rows", "yb_heev_rows_top", "yb_svd_finalize_top", "yb_cholqr_factor", "yb_cholqr_refine", "yb_cholqr_finalize", "yb_svd_select", "yb_svd_gather",
-    "yb_jump_test", "yb_jump_select", "yb_unpack_vh", "yb_copy_packed", "yb_apply_local_op", "yb_mpo_site_apply", "yb_norm2", "yb_scale", "yb_local_rdm", "yb_philox_uniform",
+    "yb_jump_test", "yb_jump_select", "yb_observables", "yb_diagnostics", "yb_unpack_vh", "yb_copy_packed", "yb_apply_local_op", "yb_mpo_site_apply", "yb_norm2", "yb_scale", "yb_local_rdm", "yb_philox_uniform",
 ]
 
 
@@ -359,6 +359,15 @@ class CudaKernels:
             int(nbatch), self._ptr(jmask), self._ptr(u2), self._ptr(rdm1), self._ptr(rdm2), int(nproc), self._ptr(proc_site), self._ptr(proc_two),
             self._ptr(proc_ldl), self._ptr(proc_strength), ctypes.c_double(dt), self._ptr(ops_table), int(nops), self._ptr(w), self._ptr(total),
             self._ptr(choice), self._ptr(ops_sel), self._ptr(status), self._stream())))
+
+    def observables(self, nbatch, nobs, col, site, two, mats, rdm1, rdm2, out, out_stride, status):
+        self._timed_call("local", lambda: self._check(self.lib.yb_observables(
+            int(nbatch), int(nobs), self._ptr(col), self._ptr(site), self._ptr(two), self._ptr(mats), self._ptr(rdm1), self._ptr(rdm2), self._ptr(out),
+            ctypes.c_int64(int(out_stride)), self._ptr(status), self._stream())))
+
+    def diagnostics(self, nbatch, length, dphys, bond, out, out_stride):
+        self._timed_call("local", lambda: self._check(self.lib.yb_diagnostics(int(nbatch), int(length), int(dphys), self._ptr(bond), self._ptr(out),
+                                                                             ctypes.c_int64(int(out_stride)), self._stream())))
 
     def philox_uniform(self, seed: int, traj_index, tag: int, nblocks: int, block0: int, out):
         """out [nbatch, 2 * nblocks] float64 (contiguous rows); traj_index int64 [nbatch] on the device."""
