@@ -65,10 +65,14 @@ __global__ void __launch_bounds__(THREADS, 1) k_cholqr_factor(const cplx* __rest
     block_sum<1>(tr, red);                                   // (contains the barrier that publishes P)
     const double trace = tr[0];
     // ---- G = L~ D L~^H, left-looking by columns.  S[r][j] = G[r][j] - sum_{q<j} S[r][q] conj(S[j][q]) w[q], pivot_j = S[j][j], w = 1 / pivot.
-    // 4 threads per row (q = part, part + 4, ...), rows r = j + (tid >> 2) + 128 t; one barrier per column: the reciprocal of the newest
-    // pivot is recomputed by every thread that needs it and published through w[] for the columns after the next barrier.
-    const int part = tid & 3, rslot = tid >> 2;
+    // PT threads per row (q = part, part + PT, ...): 4 while more than 64 rows are left, then 8 / 16 / 32 as the triangle narrows, so that
+    // the 512 threads stay busy (with a fixed split 43 % of the stall samples were warps waiting at the column / row barriers,
+    // profiles/r02_ncu_cholqr_factor_source_hotspots_v1.txt).  One barrier per column: the reciprocal of the newest pivot is recomputed by
+    // every thread that needs it and published through w[] for the columns after the next barrier.
     for (int j = 0; j < k; ++j) {
+        const int left = k - j;
+        const int PT = left > 64 ? 4 : (left > 32 ? 8 : (left > 16 ? 16 : 32));
+        const int part = tid & (PT - 1), rslot = tid / PT;
         double wlast = 0.0;
         if (j > 0) {
             const double pv = P[tri(j - 1) + (j - 1)].x;
@@ -76,20 +80,19 @@ __global__ void __launch_bounds__(THREADS, 1) k_cholqr_factor(const cplx* __rest
             if (tid == 0) { w[j - 1] = wlast; if (wlast == 0.0) s_bad = 1; }
         }
         const cplx* sj = P + tri(j);
-        for (int r0 = j; r0 < k; r0 += THREADS / 4) {      // block-uniform trip count: every lane takes part in the shuffles
+        for (int r0 = j; r0 < k; r0 += THREADS / PT) {     // block-uniform trip count: every lane takes part in the shuffles
             const int r = r0 + rslot;
             const bool live = r < k;
             const cplx* sr = P + tri(live ? r : j);
             double ar = 0.0, ai = 0.0;
             if (live)
-                for (int q = part; q < j; q += 4) {
+                for (int q = part; q < j; q += PT) {
                     const cplx x = sr[q], y = sj[q];
                     const double wq = (q == j - 1) ? wlast : w[q];
                     ar = fma(x.x * y.x + x.y * y.y, wq, ar);     // x * conj(y) * w
                     ai = fma(x.y * y.x - x.x * y.y, wq, ai);
                 }
-            ar += __shfl_xor_sync(0xffffffffu, ar, 1); ai += __shfl_xor_sync(0xffffffffu, ai, 1);
-            ar += __shfl_xor_sync(0xffffffffu, ar, 2); ai += __shfl_xor_sync(0xffffffffu, ai, 2);
+            for (int o = 1; o < PT; o <<= 1) { ar += __shfl_xor_sync(0xffffffffu, ar, o); ai += __shfl_xor_sync(0xffffffffu, ai, o); }
             if (live && part == 0) {
                 cplx g = sr[j];
                 g.x -= ar; g.y -= ai;
@@ -106,23 +109,25 @@ __global__ void __launch_bounds__(THREADS, 1) k_cholqr_factor(const cplx* __rest
     }
     __syncthreads();
     // ---- Z = L~^-1 in place, row by row: Z[i][j] = - sum_{q=j}^{i-1} (S[i][q] w[q]) Z[q][j], Z[i][i] = 1.  Lane layout inside a warp:
-    // column j = 8 warp + (lane & 7), part = lane >> 3 (q = j + part, j + part + 4, ...): a quarter-warp reads 8 consecutive Z[q][.].
+    // JW = 32 / PT columns per warp, column j = JW warp + (lane % JW), part = lane / JW (q = j + part, j + part + PT, ...): lanes of one
+    // part read JW consecutive Z[q][.]; PT follows the row length as above (4 for i > 64 ... 32 for i <= 16).
     for (int i = 1; i < k; ++i) {
         for (int q = tid; q < i; q += THREADS) { const cplx s = P[tri(i) + q]; const double wq = w[q]; trow[q] = make_double2(s.x * wq, s.y * wq); }
         __syncthreads();
-        const int j = 8 * warp + (lane & 7), pr = lane >> 3;
-        if (8 * warp < i) {
+        const int PT = i > 64 ? 4 : (i > 32 ? 8 : (i > 16 ? 16 : 32));
+        const int JW = 32 / PT;
+        const int j = JW * warp + (lane & (JW - 1)), pr = lane / JW;
+        if (JW * warp < i) {
             double ar = 0.0, ai = 0.0;
             if (j < i) {
-                for (int q = j + pr; q < i; q += 4) {
+                for (int q = j + pr; q < i; q += PT) {
                     const cplx t = trow[q];
                     const cplx z = (q == j) ? make_double2(1.0, 0.0) : P[tri(q) + j];
                     ar += t.x * z.x - t.y * z.y;
                     ai += t.x * z.y + t.y * z.x;
                 }
             }
-            ar += __shfl_xor_sync(0xffffffffu, ar, 8); ai += __shfl_xor_sync(0xffffffffu, ai, 8);
-            ar += __shfl_xor_sync(0xffffffffu, ar, 16); ai += __shfl_xor_sync(0xffffffffu, ai, 16);
+            for (int o = JW; o < 32; o <<= 1) { ar += __shfl_xor_sync(0xffffffffu, ar, o); ai += __shfl_xor_sync(0xffffffffu, ai, o); }
             if (pr == 0 && j < i) P[tri(i) + j] = make_double2(-ar, -ai);      // row i of S is dead: its scaled copy lives in trow
         }
         __syncthreads();
