@@ -282,6 +282,21 @@ int yb_observables(int nbatch, int nobs, const int32_t* col, const int32_t* site
                    const void* rdm2, double* out, int64_t out_stride, int32_t* status, void* stream);
 int yb_diagnostics(int nbatch, int length, int dphys, const int32_t* bond, double* out, int64_t out_stride, void* stream);
 
+/* work[b] = (mask == NULL || mask[b]) && !flag[b]. */
+int yb_mask_andnot(int nbatch, const int32_t* mask, const int32_t* flag, int32_t* work, void* stream);
+
+/* ---- CUDA graphs of fixed launch sequences ------------------------------------------------------------------------------
+ * The launches of one gauge shift (yb_svd_prepare ... yb_cholqr_finalize, the copies that install the factors) depend on the host only
+ * through pointers and capacities that are fixed per (site, direction, policy); every extent is read on the device.  yb_graph_begin
+ * puts `stream` into (thread-local) capture, the yb_* calls issued on it are recorded instead of executed, yb_graph_end returns an
+ * executable graph, yb_graph_launch replays it on any stream: one host call per shift instead of ~14 (dispatch row of SURVEY 8b; the
+ * reference has no counterpart -- it is one Python interpreter per trajectory, core/parallel_utils.py:331-390).  Kernels with
+ * one-time attribute configuration must have run once before they are captured. */
+int yb_graph_begin(void* stream);
+int yb_graph_end(void* stream, void** graph_exec);
+int yb_graph_launch(void* graph_exec, void* stream);
+int yb_graph_destroy(void* graph_exec);
+
 #ifdef __cplusplus
 }
 #endif

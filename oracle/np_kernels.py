@@ -682,6 +682,11 @@ class NumpyKernels:
             o[t * out_stride + 1] = float(max(dphys, bd[t].max())) if bd.shape[1] else float(dphys)
             o[t * out_stride + 2] = float(bd[t].sum())
 
+    def mask_andnot(self, nbatch, mask, flag, work):
+        self._launches += 1
+        for t in range(nbatch):
+            _np(work)[t] = 1 if (_on(mask, t) and not _np(flag)[t]) else 0
+
     def philox_uniform(self, seed, traj_index, tag, nblocks, block0, out):
         """numpy restatement of csrc/yb_philox.cuh (Philox4x32-10, key = seed, counter = (block, tag, traj_lo, traj_hi))."""
         o = out.numpy()

@@ -66,8 +66,12 @@ def test_cuda_engine_long_run_at_baseline_sizes(golden_dir, name, first, batch):
     traj = list(range(first, first + batch))
     eng, tu, su, traj = engine_for_case(name, kern, trajectories=traj)
     log = []
-    results, diag = eng.run(tu, su, log)
+    side = torch.cuda.Stream()                              # as a lane runs it: on a side stream the gauge shifts replay CUDA graphs
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        results, diag = eng.run(tu, su, log)
     torch.cuda.synchronize()
+    assert eng.stats["graph_capture_failed"] == 0 and eng.stats["graph_launches"] > 0, (eng.stats, eng.graph_error)
     assert int(eng.status.max().item()) == 0
     assert bool(torch.isfinite(results).all()) and float(results.abs().max()) <= 1.0 + 1e-9
     assert eng.stats["gram_svd_calls"] > 0 and eng.stats["jumps"] > 0
@@ -168,3 +172,28 @@ def test_cuda_dynamic_tdvp_is_exact_at_full_bond_dimension(length, chi0, cap):
     """Both per-trajectory branches of the dynamic sweep (1-site with hand-over at the cap, 2-site with the uncapped split) on the
     device: exact evolution at full bond dimension (see the host twin of this test for what the reference does there)."""
     check_dynamic_exact(CudaKernels("cuda:0"), length, chi0, cap)
+
+
+@pytest.mark.parametrize("name", ["ising10_c1_order2", "heis8_c2_order2", "ising8_strong_order2", "ising6_1site_noiseless"])
+def test_cuda_engine_graphed_gauge_shifts(golden_dir, name):
+    """The keep-all gauge shifts as CUDA graphs (yb_graph_*: first use eager, second captured, then replayed): on a side stream, with
+    the Gram / Cholesky-QR routes forced onto the small fixtures -- masked shifts of the jump walks and certificate fallbacks included --
+    same jumps, identical bonds, observables <= 1e-10; and bit for bit the eager run (YB_GRAPHS=0 semantics)."""
+    kern = CudaKernels("cuda:0")
+    eng, tu, su, traj = engine_for_case(name, kern, gram_min_k=0)
+    log = []
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        results, diag = eng.run(tu, su, log)
+    torch.cuda.synchronize()
+    assert int(eng.status.max().item()) == 0
+    assert eng.stats["graph_capture_failed"] == 0, eng.graph_error
+    assert eng.stats["graphs_captured"] > 0 and eng.stats["graph_launches"] > 0 and eng.stats["cholqr_calls"] > 0
+    check_against_golden(name, golden_dir, results, diag, log, traj)
+    eng2, tu2, su2, _ = engine_for_case(name, kern, gram_min_k=0)
+    eng2.use_graphs = False
+    res2, diag2 = eng2.run(tu2, su2, [])
+    torch.cuda.synchronize()
+    assert torch.equal(results, res2) and torch.equal(diag, diag2)
+    eng.release_graphs()

@@ -573,4 +573,44 @@ int yb_diagnostics(int nbatch, int length, int dphys, const int32_t* bond, doubl
     return done("yb_diagnostics");
 }
 
+int yb_mask_andnot(int nbatch, const int32_t* mask, const int32_t* flag, int32_t* work, void* stream) {
+    if (nbatch <= 0) return 0;
+    k_mask_andnot<<<(nbatch + 127) / 128, 128, 0, (cudaStream_t)stream>>>(nbatch, mask, flag, work);
+    return done("yb_mask_andnot");
+}
+
+// ---- CUDA graphs of fixed launch sequences (the gauge shifts of a chain walk: every extent is read on the device, so one captured
+// sequence per (site, direction, policy) serves every step).  Capture is thread-local: other lanes keep launching and reading back.
+int yb_graph_begin(void* stream) {
+    cudaError_t e = cudaStreamBeginCapture((cudaStream_t)stream, cudaStreamCaptureModeThreadLocal);
+    return e == cudaSuccess ? 0 : fail("yb_graph_begin", e);
+}
+
+int yb_graph_end(void* stream, void** graph_exec) {
+    if (!graph_exec) return fail_msg("yb_graph_end: graph_exec is NULL");
+    *graph_exec = nullptr;
+    cudaGraph_t g = nullptr;
+    cudaError_t e = cudaStreamEndCapture((cudaStream_t)stream, &g);
+    if (e != cudaSuccess || !g) return fail("yb_graph_end(capture)", e != cudaSuccess ? e : cudaErrorUnknown);
+    cudaGraphExec_t ex = nullptr;
+    e = cudaGraphInstantiate(&ex, g, 0);
+    cudaGraphDestroy(g);
+    if (e != cudaSuccess) return fail("yb_graph_end(instantiate)", e);
+    *graph_exec = (void*)ex;
+    return 0;
+}
+
+int yb_graph_launch(void* graph_exec, void* stream) {
+    if (!graph_exec) return fail_msg("yb_graph_launch: no graph");
+    cudaError_t e = cudaGraphLaunch((cudaGraphExec_t)graph_exec, (cudaStream_t)stream);
+    if (e != cudaSuccess) return fail("yb_graph_launch", e);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return 0;
+}
+
+int yb_graph_destroy(void* graph_exec) {
+    if (graph_exec) cudaGraphExecDestroy((cudaGraphExec_t)graph_exec);
+    return 0;
+}
+
 }  // extern "C"

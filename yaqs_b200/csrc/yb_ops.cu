@@ -504,3 +504,11 @@ __global__ void k_diagnostics(int nbatch, int length, int dphys, const int* __re
     out[(long long)b * out_stride + 1] = (double)mx;
     out[(long long)b * out_stride + 2] = total;
 }
+
+
+// work[b] = (mask == NULL || mask[b]) && !flag[b]: the trajectories of a masked call that a certificate accepted (the launches that
+// install the factors of a Cholesky-QR shift run under it; the flagged rest is redone by the eigen-solver route and installed afterwards)
+__global__ void k_mask_andnot(int nbatch, const int* __restrict__ mask, const int* __restrict__ flag, int* work) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < nbatch) work[b] = ((!mask || mask[b]) && !flag[b]) ? 1 : 0;
+}

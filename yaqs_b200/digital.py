@@ -80,7 +80,14 @@ def run_digital(simulator, initial_state, operator, sp, noise, result):
             tu = None
             eng.philox = philox_source(sp.random_seed, idx, dev)
         log = [] if simulator.collect_log else None
-        r, dg = eng.run_digital(compiled.layers, tu, sp.sample_layers, sp.gate_mode, log)
+        if torch.device(dev).type == "cuda":               # a side stream: the legacy default stream cannot hold CUDA-graph captures (engine._run_graphed)
+            side, cur = torch.cuda.Stream(dev), torch.cuda.current_stream(dev)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                r, dg = eng.run_digital(compiled.layers, tu, sp.sample_layers, sp.gate_mode, log)
+            cur.wait_stream(side)
+        else:
+            r, dg = eng.run_digital(compiled.layers, tu, sp.sample_layers, sp.gate_mode, log)
         res_local[w0: w0 + len(idx)] = r.cpu().numpy()
         diag_local[w0: w0 + len(idx)] = dg.cpu().numpy()
         status_local[w0: w0 + len(idx)] = eng.status.cpu().numpy()

@@ -282,6 +282,11 @@ class BatchedTJM:
         self.jt_total = torch.zeros(B, dtype=torch.float64, device=dev)
         self.jt_choice = torch.zeros(B, dtype=torch.int32, device=dev)
         self.jt_ops = torch.zeros(B * self.JT_NOPS, dtype=C128, device=dev)
+        self.use_graphs = os.environ.get("YB_GRAPHS", "1") != "0" and bool(getattr(kernels, "supports_graphs", False))
+        self._graphs: dict = {}
+        self._graph_seen: set = set()
+        self.g_mask = torch.zeros(B, dtype=torch.int32, device=dev)
+        self.g_work = torch.zeros(B, dtype=torch.int32, device=dev)
         self.jt_w = None                                    # [B, n_proc] weights / pdf of the current noise context (allocated per context)
         self.philox = None                                  # (seed, global trajectory indices int64 [B], sample offset): draw the uniforms in the kernel
         self.status = torch.zeros(B, dtype=torch.int32, device=dev)
@@ -338,7 +343,8 @@ class BatchedTJM:
         self._ones_i32 = torch.ones(B, dtype=torch.int32, device=dev)
         self.on_sample = None                               # callback(engine, column, results, diagnostics) after every recorded column of run_digital
         self.stats = {"krylov_calls": 0, "matvecs": 0, "matvecs_2site": 0, "svd_calls": 0, "svd_sweeps": 0, "jumps": 0, "gram_svd_calls": 0, "gram_fallbacks": 0, "cholqr_calls": 0,
-                      "cholqr_fallbacks": 0, "heev_top_calls": 0}
+                      "cholqr_fallbacks": 0, "heev_top_calls": 0, "graphs_captured": 0, "graph_launches": 0, "graph_capture_failed": 0}
+        self.graph_error = None
 
     # ------------------------------------------------------------------------------------------------------------------
     # operator / noise contexts (one each on the analog path; per gate on the digital path)
@@ -543,6 +549,16 @@ class BatchedTJM:
     CHOLQR_TOL = 1e-7             # accepted orthonormality defect of the first pass; one Newton-Schulz step squares it
 
     def _svd_cholqr(self, mode: int, src: Buf, el: Ext, er: Ext, trunc, dist: str, mask, dims: tuple[int, int]) -> None:
+        self._cholqr_chain(mode, src, el, er, trunc, dist, mask, dims)
+        nfb = self.K.sync_int(self.counter)
+        if nfb > 0:                                          # not certified: the eigen-solver route decides (and truncates) for those
+            self.stats["cholqr_fallbacks"] += nfb
+            self._svd_gram(mode, src, el, er, trunc, dist, self.amb.clone(), dims)
+
+    def _cholqr_chain(self, mode: int, src: Buf, el: Ext, er: Ext, trunc, dist: str, mask, dims: tuple[int, int]) -> None:
+        """The launches of one Cholesky-QR factorisation, nothing else: no host read, no host decision -- the sequence can be captured
+        into a CUDA graph.  Leaves the factors of the accepted trajectories in svd_u / svd_v / keep, the flags in ``amb`` and their
+        number in ``counter``."""
         K, B, lay = self.K, self.B, self.lay
         sd = lay.svd_dim
         sq = sd * sd
@@ -564,11 +580,59 @@ class BatchedTJM:
         K.gemm(OP_GRAM, B, 1, mask, ek, eln, None, 1, 1, 1, w, y2, l2, 0, kdim, kdim)
         K.cholqr_finalize(B, mask, self.svd_meta, y2, l2, Ext(self.keep, 0, 1), self._buf(self.svd_u, sq), self._buf(self.svd_v, sq), self.amb,
                           kdim * (ldim + kdim))
-        self.stats["cholqr_calls"] += 1
-        nfb = K.sync_int(self.counter)
-        if nfb > 0:                                          # not certified: the eigen-solver route decides (and truncates) for those
-            self.stats["cholqr_fallbacks"] += nfb
-            self._svd_gram(mode, src, el, er, trunc, dist, self.amb.clone(), dims)
+
+    def _cholqr_applies(self, trunc, dist: str, dims: tuple[int, int], kcap: int) -> bool:
+        """The routing rule of ``_svd`` for gauge shifts: Gram route wanted, keep-all policy, bond side fits the shared-memory factorisation."""
+        tm, thr, mb, _mk = trunc
+        kb, lb = (dims[1], dims[0]) if dist == "right" else (dims[0], dims[1])
+        return (self.use_gram and self.cholqr and kcap > 0 and kcap >= self.gram_min_k and tm == 0 and thr <= self.CHOLQR_MAX_THRESHOLD
+                and 0 < kb <= min(lb, self.CHOLQR_KMAX) and (mb == 0 or mb >= kb))
+
+    # ------------------------------------------------------------------------------------------------------------------
+    # CUDA graphs of fixed launch sequences (include/yaqs_b200.h: yb_graph_*)
+    # ------------------------------------------------------------------------------------------------------------------
+    def _run_graphed(self, key, fn) -> None:
+        """Run the launch sequence ``fn`` -- which must consist of library launches only, all decided by host-known parameters that
+        ``key`` captures -- as a CUDA graph: the first use runs eagerly (kernels configure their attributes outside a capture), the
+        second is captured, every later one is ONE host call.  Eager whenever graphs are off, the backend has none (numpy twin) or
+        per-launch timing is active (bench.py's instrumented step)."""
+        K = self.K
+        if not self.use_graphs or K.timing_active or K.on_default_stream():
+            fn()
+            return
+        handle = self._graphs.get(key)
+        if handle is None:
+            if key not in self._graph_seen:
+                self._graph_seen.add(key)
+                fn()
+                return
+            try:
+                K.graph_begin()
+                try:
+                    fn()
+                finally:
+                    handle = K.graph_end()
+            except Exception as exc:                         # capture refused: stay eager for the rest of the run
+                self.use_graphs = False
+                self.graph_error = repr(exc)
+                self.stats["graph_capture_failed"] += 1
+                fn()
+                return
+            self._graphs[key] = handle
+            self.stats["graphs_captured"] += 1
+        K.graph_launch(handle)
+        self.stats["graph_launches"] += 1
+
+    def release_graphs(self) -> None:
+        for handle in self._graphs.values():
+            self.K.graph_destroy(handle)
+        self._graphs.clear()
+
+    def __del__(self):
+        try:
+            self.release_graphs()
+        except Exception:
+            pass
 
     def _jacobi_geometry(self, dims: tuple[int, int] | None) -> tuple[int, int, int, int, int]:
         """(block_rows, nblocks, inner_sweeps, max_len, max_k) of the one-sided Jacobi for matrices of at most ``dims`` = (rows,
@@ -707,27 +771,67 @@ class BatchedTJM:
         isometry the SVD of the centre tensor alone gives the same singular values / keep decision."""
         lay, K, B, d = self.lay, self.K, self.B, self.d
         sd = lay.svd_dim
-        self._svd(SVD_ROWS, st.site(i), st.ext(i), st.ext(i + 1), trunc, "right", mask, min(d * lay.cap[i], lay.cap[i + 1]) if fast else 0,
-                  (d * lay.cap[i], lay.cap[i + 1]))
-        kx = Ext(self.keep, 0, 1)
-        K.copy_packed(B, mask, st.ext(i), kx, d, self._buf(self.svd_u, sd * sd), st.site(i), lay.slot[i])
-        tmp = self._buf(self.tmp, lay.nloc_max)
-        K.gemm(OP_ABSORB_R, B, d, mask, kx, st.ext(i + 1), st.ext(i + 2), d, 1, 1, self._buf(self.svd_v, sd * sd), st.site(i + 1), tmp, 0,
-               lay.cap[i + 1], lay.cap[i + 2])
-        K.copy_packed(B, mask, kx, st.ext(i + 2), d, tmp, st.site(i + 1), lay.slot[i + 1], st.ext(i + 1))      # bond i+1 <- keep
+        dims = (d * lay.cap[i], lay.cap[i + 1])
+        kcap = min(d * lay.cap[i], lay.cap[i + 1]) if fast else 0
+
+        def install(m):                                      # U -> site i, (S Vh) absorbed into site i+1, bond i+1 <- keep
+            kx = Ext(self.keep, 0, 1)
+            K.copy_packed(B, m, st.ext(i), kx, d, self._buf(self.svd_u, sd * sd), st.site(i), lay.slot[i])
+            tmp = self._buf(self.tmp, lay.nloc_max)
+            K.gemm(OP_ABSORB_R, B, d, m, kx, st.ext(i + 1), st.ext(i + 2), d, 1, 1, self._buf(self.svd_v, sd * sd), st.site(i + 1), tmp, 0,
+                   lay.cap[i + 1], lay.cap[i + 2])
+            K.copy_packed(B, m, kx, st.ext(i + 2), d, tmp, st.site(i + 1), lay.slot[i + 1], st.ext(i + 1))
+
+        if self._cholqr_applies(trunc, "right", dims, kcap):
+            self._shift_cholqr(("shr", id(st), i), SVD_ROWS, st.site(i), st.ext(i), st.ext(i + 1), trunc, "right", mask, dims, install)
+            return
+        self._svd(SVD_ROWS, st.site(i), st.ext(i), st.ext(i + 1), trunc, "right", mask, kcap, dims)
+        install(mask)
 
     def shift_left(self, st: BatchedState, i: int, trunc, mask=None, fast: bool = False) -> None:
         """Centre i -> i-1 (mps.py:771-788), reduced form (site i-1 must be a left isometry)."""
         lay, K, B, d = self.lay, self.K, self.B, self.d
         sd = lay.svd_dim
-        self._svd(SVD_COLS, st.site(i), st.ext(i), st.ext(i + 1), trunc, "left", mask, min(lay.cap[i], d * lay.cap[i + 1]) if fast else 0,
-                  (lay.cap[i], d * lay.cap[i + 1]))
-        kx = Ext(self.keep, 0, 1)
-        tmp = self._buf(self.tmp, lay.nloc_max)
-        K.gemm(OP_ABSORB_L, B, d, mask, st.ext(i - 1), st.ext(i), kx, d, 1, 1, st.site(i - 1), self._buf(self.svd_u, sd * sd), tmp, 0,
-               lay.cap[i - 1], lay.cap[i])
-        K.copy_packed(B, mask, st.ext(i - 1), kx, d, tmp, st.site(i - 1), lay.slot[i - 1])
-        K.unpack_vh(B, mask, kx, st.ext(i + 1), d, self._buf(self.svd_v, sd * sd), st.site(i), lay.slot[i], st.ext(i))      # bond i <- keep
+        dims = (lay.cap[i], d * lay.cap[i + 1])
+        kcap = min(lay.cap[i], d * lay.cap[i + 1]) if fast else 0
+
+        def install(m):                                      # (U S) absorbed into site i-1, Vh -> site i, bond i <- keep
+            kx = Ext(self.keep, 0, 1)
+            tmp = self._buf(self.tmp, lay.nloc_max)
+            K.gemm(OP_ABSORB_L, B, d, m, st.ext(i - 1), st.ext(i), kx, d, 1, 1, st.site(i - 1), self._buf(self.svd_u, sd * sd), tmp, 0,
+                   lay.cap[i - 1], lay.cap[i])
+            K.copy_packed(B, m, st.ext(i - 1), kx, d, tmp, st.site(i - 1), lay.slot[i - 1])
+            K.unpack_vh(B, m, kx, st.ext(i + 1), d, self._buf(self.svd_v, sd * sd), st.site(i), lay.slot[i], st.ext(i))
+
+        if self._cholqr_applies(trunc, "left", dims, kcap):
+            self._shift_cholqr(("shl", id(st), i), SVD_COLS, st.site(i), st.ext(i), st.ext(i + 1), trunc, "left", mask, dims, install)
+            return
+        self._svd(SVD_COLS, st.site(i), st.ext(i), st.ext(i + 1), trunc, "left", mask, kcap, dims)
+        install(mask)
+
+    def _shift_cholqr(self, key, mode: int, src: Buf, el: Ext, er: Ext, trunc, dist: str, mask, dims, install) -> None:
+        """One keep-all gauge shift on the Cholesky-QR route as a fixed launch sequence (CUDA graph from its third use on): the
+        factorisation, the mask of the accepted trajectories, the launches that install their factors.  One host read afterwards;
+        flagged trajectories (their site tensor is untouched) take the eigen-solver route and are installed under their own mask."""
+        K, B = self.K, self.B
+        gm = None
+        if mask is not None:                                 # a captured sequence needs the mask at a fixed address
+            self.g_mask.copy_(mask)
+            gm = self.g_mask
+
+        def seq():
+            self._cholqr_chain(mode, src, el, er, trunc, dist, gm, dims)
+            K.mask_andnot(B, gm, self.amb, self.g_work)
+            install(self.g_work)
+
+        self._run_graphed(key + (float(trunc[1]), mask is not None), seq)
+        self.stats["cholqr_calls"] += 1
+        nfb = K.sync_int(self.counter)
+        if nfb > 0:
+            self.stats["cholqr_fallbacks"] += nfb
+            redo = self.amb.clone()
+            self._svd_gram(mode, src, el, er, trunc, dist, redo, dims)
+            install(redo)
 
     def normalize_site(self, st: BatchedState, i: int, mask=None) -> None:
         """QR at a chain end with R dropped == divide the (1-column) centre tensor by its norm (mps.py:736-746)."""

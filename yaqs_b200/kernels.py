@@ -86,7 +86,7 @@ def load_library() -> ctypes.CDLL:
 EXPORTED_SYMBOLS = [
     "yb_last_error", "yb_version", "yb_launch_count", "yb_set_flop_counter", "yb_set_option", "yb_workspace_bytes", "yb_gemm", "yb_rcontract_mpo", "yb_wapply", "yb_env_identity", "yb_lanczos_init",
     "yb_lanczos_step", "yb_lanczos_combine", "yb_svd_prepare", "yb_svd_round", "yb_svd_check", "yb_svd_finalize", "yb_svd_ambiguous", "yb_heev", "yb_heev_rows", "yb_heev_rows_top", "yb_svd_finalize_top", "yb_cholqr_factor", "yb_cholqr_refine", "yb_cholqr_finalize", "yb_svd_select", "yb_svd_gather",
-    "yb_jump_test", "yb_jump_select", "yb_observables", "yb_diagnostics", "yb_unpack_vh", "yb_copy_packed", "yb_apply_local_op", "yb_mpo_site_apply", "yb_norm2", "yb_scale", "yb_local_rdm", "yb_philox_uniform",
+    "yb_jump_test", "yb_jump_select", "yb_observables", "yb_diagnostics", "yb_mask_andnot", "yb_graph_begin", "yb_graph_end", "yb_graph_launch", "yb_graph_destroy", "yb_unpack_vh", "yb_copy_packed", "yb_apply_local_op", "yb_mpo_site_apply", "yb_norm2", "yb_scale", "yb_local_rdm", "yb_philox_uniform",
 ]
 
 
@@ -368,6 +368,36 @@ class CudaKernels:
     def diagnostics(self, nbatch, length, dphys, bond, out, out_stride):
         self._timed_call("local", lambda: self._check(self.lib.yb_diagnostics(int(nbatch), int(length), int(dphys), self._ptr(bond), self._ptr(out),
                                                                              ctypes.c_int64(int(out_stride)), self._stream())))
+
+    def mask_andnot(self, nbatch, mask, flag, work):
+        self._timed_call("local", lambda: self._check(self.lib.yb_mask_andnot(int(nbatch), self._ptr(mask), self._ptr(flag), self._ptr(work), self._stream())))
+
+    # -- CUDA graphs of fixed launch sequences (include/yaqs_b200.h) ----------------------------------------------------------
+    supports_graphs = True
+
+    def graph_begin(self) -> None:
+        self._check(self.lib.yb_graph_begin(self._stream()))
+
+    def graph_end(self) -> int:
+        handle = ctypes.c_void_p(0)
+        self._check(self.lib.yb_graph_end(self._stream(), ctypes.byref(handle)))
+        return int(handle.value)
+
+    def graph_launch(self, handle: int) -> None:
+        self._check(self.lib.yb_graph_launch(ctypes.c_void_p(handle), self._stream()))
+
+    def graph_destroy(self, handle: int) -> None:
+        self.lib.yb_graph_destroy(ctypes.c_void_p(handle))
+
+    @property
+    def timing_active(self) -> bool:
+        return self._timed is not None
+
+    def on_default_stream(self) -> bool:
+        """The legacy default stream cannot be captured: sequences issued there stay eager."""
+        if self._raw_stream is not None:
+            return int(self._raw_stream(self._dev_index)) == 0
+        return int(torch.cuda.current_stream(self.device).cuda_stream) == 0
 
     def philox_uniform(self, seed: int, traj_index, tag: int, nblocks: int, block0: int, out):
         """out [nbatch, 2 * nblocks] float64 (contiguous rows); traj_index int64 [nbatch] on the device."""
