@@ -174,7 +174,7 @@ def test_cuda_dynamic_tdvp_is_exact_at_full_bond_dimension(length, chi0, cap):
     check_dynamic_exact(CudaKernels("cuda:0"), length, chi0, cap)
 
 
-@pytest.mark.parametrize("name", ["ising10_c1_order2", "heis8_c2_order2", "ising8_strong_order2", "ising6_1site_noiseless"])
+@pytest.mark.parametrize("name", ["ising10_c1_order2", "heis8_c2_order2", "ising8_strong_order2", "ising10_c1_order1"])
 def test_cuda_engine_graphed_gauge_shifts(golden_dir, name):
     """The keep-all gauge shifts as CUDA graphs (yb_graph_*: first use eager, second captured, then replayed): on a side stream, with
     the Gram / Cholesky-QR routes forced onto the small fixtures -- masked shifts of the jump walks and certificate fallbacks included --
