@@ -36,6 +36,17 @@ inline int grid_for(long long n, int threads, int cap = 4096) {
     if (g > cap) g = cap;
     return (int)g;
 }
+// CTAs per trajectory for the element-wise kernels (all of them grid-stride over their elements).  The element count is a CAPACITY
+// (the largest admissible bond dimensions), the actual extents are known on the device only: at 2048 trajectories with bonds of 11
+// inside slots of 64 (config 4) a grid of 64 CTAs per trajectory is 131 k CTAs of which 129 k find nothing to do -- ~40 us per
+// launch, 14 launches per gauge shift (profiles/r02_bench_C4_v2_graphs.json: 4.6 s per Trotter step at a quarter of the host calls).
+// Enough CTAs to fill the GPU a few times over, never more than the capacity needs.
+inline int grid_batch(long long n, int threads, int nbatch, int cap = 64) {
+    const int need = grid_for(n, threads, cap);
+    int want = (8 * 148 + nbatch - 1) / (nbatch > 0 ? nbatch : 1);
+    if (want < 1) want = 1;
+    return need < want ? need : want;
+}
 }  // namespace
 
 extern "C" {
@@ -159,7 +170,7 @@ int yb_wapply(int nbatch, const int32_t* mask, yb_extent el, yb_extent er, int n
 
 int yb_env_identity(int nbatch, const int32_t* mask, yb_extent echi, int dmpo, void* env, int64_t stride_env, int max_chi, void* stream) {
     if (nbatch <= 0) return 0;
-    dim3 grid(grid_for((long long)max_chi * dmpo * max_chi, 256, 64), nbatch);
+    dim3 grid(grid_batch((long long)max_chi * dmpo * max_chi, 256, nbatch), nbatch);
     k_env_identity<<<grid, 256, 0, (cudaStream_t)stream>>>(dmpo, (cplx*)env, stride_env, echi.ptr, echi.stride, mask);
     return done("yb_env_identity");
 }
@@ -188,7 +199,7 @@ int yb_lanczos_combine(int nbatch, const int32_t* mask, yb_extent el, yb_extent 
                        int64_t stride_vec, const void* coef, int kmax, const int32_t* kdone, void* out, int64_t stride_out, void* stream) {
     (void)kmax;
     if (nbatch <= 0) return 0;
-    dim3 grid(grid_for(stride_vec, 256, 64), nbatch);
+    dim3 grid(grid_batch(stride_vec, 256, nbatch), nbatch);
     k_lanczos_combine<<<grid, 256, 0, (cudaStream_t)stream>>>(dphys, (const cplx*)basis, stride_basis, stride_vec, (const cplx*)coef, kdone, (cplx*)out,
                                                                stride_out, el.ptr, el.stride, er.ptr, er.stride, mask);
     return done("yb_lanczos_combine");
@@ -198,7 +209,7 @@ int yb_svd_prepare(int nbatch, const int32_t* mask, int mode, yb_extent el, yb_e
                    int64_t stride_w, void* q, int64_t stride_q, int32_t* meta, int32_t* rot_count, int32_t* n_zero, int32_t* status_zero,
                    void* stream) {
     if (nbatch <= 0) return 0;
-    dim3 grid(grid_for(stride_w, 256, 64), nbatch);
+    dim3 grid(grid_batch(stride_w, 256, nbatch), nbatch);
     k_svd_prepare<<<grid, 256, 0, (cudaStream_t)stream>>>(mode, dphys, (const cplx*)src, stride_src, (cplx*)w, stride_w, (cplx*)q, stride_q, meta,
                                                            rot_count, el.ptr, el.stride, er.ptr, er.stride, mask, n_zero, status_zero);
     return done("yb_svd_prepare");
@@ -459,7 +470,7 @@ int yb_cholqr_refine(int nbatch, const int32_t* mask, const int32_t* meta, const
 int yb_cholqr_finalize(int nbatch, const int32_t* mask, int32_t* meta, const void* y2, int64_t stride_y, const void* l2, int64_t stride_l, int32_t* keep,
                        int32_t keep_stride, void* uout, int64_t stride_u, void* vout, int64_t stride_v, const int32_t* flag, int max_elems, void* stream) {
     if (nbatch <= 0) return 0;
-    dim3 grid(grid_for(max_elems, 256, 64), nbatch);
+    dim3 grid(grid_batch(max_elems, 256, nbatch), nbatch);
     cholqr::k_cholqr_finalize<<<grid, 256, 0, (cudaStream_t)stream>>>((const cplx*)y2, stride_y, (const cplx*)l2, stride_l, meta, keep, keep_stride, (cplx*)uout,
                                                                        stride_u, (cplx*)vout, stride_v, flag, mask);
     return done("yb_cholqr_finalize");
@@ -468,7 +479,7 @@ int yb_cholqr_finalize(int nbatch, const int32_t* mask, int32_t* meta, const voi
 int yb_unpack_vh(int nbatch, const int32_t* mask, yb_extent ek, yb_extent er, int dphys, const void* src, int64_t stride_src, void* dst,
                  int64_t stride_dst, int max_elems, yb_extent set_ext, void* stream) {
     if (nbatch <= 0) return 0;
-    dim3 grid(grid_for(max_elems, 256, 64), nbatch);
+    dim3 grid(grid_batch(max_elems, 256, nbatch), nbatch);
     k_unpack_vh<<<grid, 256, 0, (cudaStream_t)stream>>>(dphys, (const cplx*)src, stride_src, (cplx*)dst, stride_dst, ek.ptr, ek.stride, er.ptr,
                                                          er.stride, mask, (int*)set_ext.ptr, set_ext.stride);
     return done("yb_unpack_vh");
@@ -477,7 +488,7 @@ int yb_unpack_vh(int nbatch, const int32_t* mask, yb_extent ek, yb_extent er, in
 int yb_copy_packed(int nbatch, const int32_t* mask, yb_extent e0, yb_extent e1, int mult, const void* src, int64_t stride_src, void* dst,
                    int64_t stride_dst, int max_elems, yb_extent set_ext, void* stream) {
     if (nbatch <= 0) return 0;
-    dim3 grid(grid_for(max_elems, 256, 64), nbatch);
+    dim3 grid(grid_batch(max_elems, 256, nbatch), nbatch);
     k_copy_packed<<<grid, 256, 0, (cudaStream_t)stream>>>(mult, (const cplx*)src, stride_src, (cplx*)dst, stride_dst, e0.ptr, e0.stride, e1.ptr,
                                                            e1.stride, mask, (int*)set_ext.ptr, set_ext.stride);
     return done("yb_copy_packed");
@@ -487,7 +498,7 @@ int yb_apply_local_op(int nbatch, const int32_t* mask, const int32_t* sel, int s
                       int64_t op_stride, void* a, int64_t stride_a, int max_lr, void* stream) {
     if (nbatch <= 0) return 0;
     if (dphys > 4) return fail_msg("yb_apply_local_op: dphys > 4 unsupported");
-    dim3 grid(grid_for(max_lr, 256, 64), nbatch);
+    dim3 grid(grid_batch(max_lr, 256, nbatch), nbatch);
     k_apply_local_op<<<grid, 256, 0, (cudaStream_t)stream>>>(dphys, (const cplx*)op, op_stride, (cplx*)a, stride_a, el.ptr, el.stride, er.ptr,
                                                               er.stride, mask, sel, sel_value);
     return done("yb_apply_local_op");
@@ -499,7 +510,7 @@ int yb_mpo_site_apply(int nbatch, const int32_t* mask, yb_extent el, yb_extent e
     if (dphys > 4) return fail_msg("yb_mpo_site_apply: dphys > 4 unsupported");
     if (d_left < 1 || d_right < 1) return fail_msg("yb_mpo_site_apply: MPO bond dimensions must be >= 1");
     if (src == dst) return fail_msg("yb_mpo_site_apply: source and destination must not alias");
-    dim3 grid(grid_for(max_out_lr, 256, 64), nbatch);
+    dim3 grid(grid_batch(max_out_lr, 256, nbatch), nbatch);
     k_mpo_site_apply<<<grid, 256, 0, (cudaStream_t)stream>>>(dphys, d_left, d_right, (const cplx*)w, (const cplx*)src, stride_src, (cplx*)dst,
                                                               stride_dst, el.ptr, el.stride, er.ptr, er.stride, mask);
     return done("yb_mpo_site_apply");
@@ -514,7 +525,7 @@ int yb_norm2(int nbatch, const int32_t* mask, yb_extent el, yb_extent er, int dp
 int yb_scale(int nbatch, const int32_t* mask, yb_extent el, yb_extent er, int dphys, const double* scale, void* a, int64_t stride_a, int max_elems,
              int rsqrt_mode, void* stream) {
     if (nbatch <= 0) return 0;
-    dim3 grid(grid_for(max_elems, 256, 64), nbatch);
+    dim3 grid(grid_batch(max_elems, 256, nbatch), nbatch);
     k_scale<<<grid, 256, 0, (cudaStream_t)stream>>>(dphys, scale, (cplx*)a, stride_a, el.ptr, el.stride, er.ptr, er.stride, mask, rsqrt_mode);
     return done("yb_scale");
 }

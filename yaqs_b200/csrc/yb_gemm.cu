@@ -136,6 +136,29 @@ __device__ __forceinline__ double flip_sign(double x) {
     return __hiloint2double(__double2hiint(x) ^ 0x80000000, __double2loint(x));
 }
 
+// One output element per thread and K walked with FP64 FMAs: the small-product kernel, and the path a tile CTA takes when the ACTUAL
+// product is tiny although its slot is not (bonds of 11 in slots of 64: a 64 x 128 DMMA tile per trajectory would be ~99 % padding).
+__device__ __forceinline__ void gemm_elements(const Desc& d, int first, int stride) {
+    const int total = d.M * d.N;
+    for (int idx = first; idx < total; idx += stride) {
+        const int m = idx / d.N, n = idx - m * d.N;
+        double cr = 0.0, ci = 0.0;
+        for (int seg = 0; seg < d.nseg; ++seg) {
+            const cplx* a = d.A + seg * d.a_ss + (long long)m * d.a_rs;
+            const cplx* bp = d.B + seg * d.b_ss + (long long)n * d.b_cs;
+            for (int k = 0; k < d.K; ++k) {
+                const cplx x = a[(long long)k * d.a_cs];
+                cplx y = bp[(long long)k * d.b_rs];
+                if (d.conjB) y.y = -y.y;
+                cr = fma(x.x, y.x, cr); cr = fma(-x.y, y.y, cr);
+                ci = fma(x.x, y.y, ci); ci = fma(x.y, y.x, ci);
+            }
+        }
+        d.C[(long long)m * d.c_rs + n] = make_double2(cr, ci);
+    }
+}
+constexpr int TINY_MN = 1024;      // actual M * N up to which a tile CTA walks the product element-wise (one CTA per trajectory and group)
+
 // RAGGED (A/B option "gemm_ragged", default off): the 8 x 8 sub-tiles of a warp are interleaved over the CTA tile (rows i*16 + wm*8,
 // columns j*32 + wn*8 instead of wm*32 + i*8 / wn*32 + j*8) and sub-tiles that lie entirely beyond M or N issue no fragment loads and no
 // DMMA.  With ragged bonds (chi ~ 113 of 128: M = 4*113 = 452, N = 3*113 = 339) the last tile row / column of a 64 x 128 CTA tile is
@@ -152,6 +175,12 @@ __global__ void __launch_bounds__(128 * WM, 1) k_gemm(const YbGemmParams P) {
     if (P.mask && !P.mask[b]) return;
     Desc d;
     if (!make_desc(P, b, g, d)) return;
+    if (d.M * d.N <= TINY_MN && !P.no_small) {               // tiny actual product in a large slot: no tile, no pipeline
+        if (blockIdx.x != 0) return;
+        if (P.flops && threadIdx.x == 0) atomicAdd(P.flops, 8ull * (unsigned long long)(d.M * d.N) * (unsigned long long)d.K * d.nseg);
+        gemm_elements(d, threadIdx.x, NTHREADS);
+        return;
+    }
     const int tiles_n = (d.N + BN - 1) / BN;
     const int tiles_m = (d.M + BM - 1) / BM;
     if ((int)blockIdx.x >= tiles_m * tiles_n) return;
@@ -293,23 +322,9 @@ __global__ void __launch_bounds__(128) k_gemm_small(const YbGemmParams P) {
     Desc d;
     if (!make_desc(P, b, g, d)) return;
     const int total = d.M * d.N;
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (P.flops && threadIdx.x == 0 && blockIdx.x == 0) atomicAdd(P.flops, 8ull * (unsigned long long)total * (unsigned long long)d.K * d.nseg);
-    if (idx >= total) return;
-    const int m = idx / d.N, n = idx - m * d.N;
-    double cr = 0.0, ci = 0.0;
-    for (int seg = 0; seg < d.nseg; ++seg) {
-        const cplx* a = d.A + seg * d.a_ss + (long long)m * d.a_rs;
-        const cplx* bp = d.B + seg * d.b_ss + (long long)n * d.b_cs;
-        for (int k = 0; k < d.K; ++k) {
-            const cplx x = a[(long long)k * d.a_cs];
-            cplx y = bp[(long long)k * d.b_rs];
-            if (d.conjB) y.y = -y.y;
-            cr = fma(x.x, y.x, cr); cr = fma(-x.y, y.y, cr);
-            ci = fma(x.x, y.y, ci); ci = fma(x.y, y.x, ci);
-        }
-    }
-    d.C[(long long)m * d.c_rs + n] = make_double2(cr, ci);
+    // grid-stride over the output elements: the grid is sized from the batch (yb_launch_gemm), not from the capacity of the product
+    gemm_elements(d, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
 }
 
 constexpr size_t GEMM_SMEM = (size_t)STAGES * (A_STAGE + B_STAGE) * sizeof(cplx);
@@ -355,7 +370,13 @@ cudaError_t yb_launch_gemm_rw(int nbatch, const int* mask, const int* el, int es
 cudaError_t yb_launch_gemm(const YbGemmParams& P, int maxM, int maxN, cudaStream_t st) {
     if (P.nbatch <= 0 || maxM <= 0 || maxN <= 0) return cudaSuccess;
     if (maxM <= 64 && maxN <= 64 && !P.no_small) {
-        dim3 grid((maxM * maxN + 127) / 128, P.ngroups, P.nbatch);
+        // CTAs per (trajectory, group): what the capacity needs, but no more than fills the GPU a few times over -- the actual products
+        // are often far smaller than their slots (bonds of 11 in slots of 64 at 2048 trajectories: 65 k CTAs, 63 k of them empty)
+        const int need = (maxM * maxN + 127) / 128;
+        const long long cells = (long long)P.ngroups * P.nbatch;
+        int want = (int)((8LL * 148 + cells - 1) / (cells > 0 ? cells : 1));
+        if (want < 1) want = 1;
+        dim3 grid(need < want ? need : want, P.ngroups, P.nbatch);
         k_gemm_small<0><<<grid, 128, 0, st>>>(P);
         return cudaGetLastError();
     }
