@@ -374,7 +374,7 @@ cudaError_t yb_launch_gemm(const YbGemmParams& P, int maxM, int maxN, cudaStream
         // are often far smaller than their slots (bonds of 11 in slots of 64 at 2048 trajectories: 65 k CTAs, 63 k of them empty)
         const int need = (maxM * maxN + 127) / 128;
         const long long cells = (long long)P.ngroups * P.nbatch;
-        int want = (int)((8LL * 148 + cells - 1) / (cells > 0 ? cells : 1));
+        int want = (int)((64LL * 148 + cells - 1) / (cells > 0 ? cells : 1));      // (64 CTAs per SM in total, see grid_batch in yb_api.cu)
         if (want < 1) want = 1;
         dim3 grid(need < want ? need : want, P.ngroups, P.nbatch);
         k_gemm_small<0><<<grid, 128, 0, st>>>(P);
