@@ -125,7 +125,7 @@ def workload_config(args, nranks):
             "initial_state": "seeded random MPS, bonds saturated at chi",
             "batch_per_gpu": wl["batch"], "global_batch": wl["batch"] * nranks, "sharding": f"trajectories x{nranks}", "lanes_per_gpu": args.lanes,
             "l2_policy": "inputs larger than L2 (per-step working set >> 126 MB)" if wl["chi"] >= 64 else "state + environments of the batch exceed L2",
-            "library_options": {k: os.environ[k] for k in ("YB_GEMM_RAGGED", "YB_WAPPLY_ONEPASS", "YB_HEEV_RING", "YB_HEEV_QL", "YB_HETRD_BLOCKED") if k in os.environ}}
+            "library_options": {k: os.environ[k] for k in ("YB_GEMM_RAGGED", "YB_WAPPLY_ONEPASS", "YB_HEEV_RING", "YB_HEEV_QL", "YB_HETRD_BLOCKED", "YB_GEMM_SMALL_MAX", "YB_CHOLQR", "YB_HEEV_TOP", "YB_GRAPHS") if k in os.environ}}
 
 
 # ----------------------------------------------------------------------------------------------------------------------

@@ -103,6 +103,7 @@ static std::atomic<int> g_opt_heev_ring{getenv("YB_HEEV_RING") != nullptr ? atoi
 static std::atomic<int> g_opt_wapply_onepass{getenv("YB_WAPPLY_ONEPASS") != nullptr ? atoi(getenv("YB_WAPPLY_ONEPASS")) : 0};
 static std::atomic<int> g_opt_gemm_bk16{getenv("YB_GEMM_BK16") != nullptr ? atoi(getenv("YB_GEMM_BK16")) : 0};
 static std::atomic<int> g_opt_gemm_no_small{getenv("YB_GEMM_NO_SMALL") != nullptr ? atoi(getenv("YB_GEMM_NO_SMALL")) : 0};
+static std::atomic<int> g_opt_gemm_small_max{getenv("YB_GEMM_SMALL_MAX") != nullptr ? atoi(getenv("YB_GEMM_SMALL_MAX")) : 32};
 static std::atomic<int> g_opt_gemm_warps16{getenv("YB_GEMM_WARPS16") != nullptr ? atoi(getenv("YB_GEMM_WARPS16")) : 0};
 static std::atomic<int> g_opt_gemm_ragged{getenv("YB_GEMM_RAGGED") != nullptr ? atoi(getenv("YB_GEMM_RAGGED")) : 0};
 
@@ -112,6 +113,7 @@ int yb_set_option(const char* name, int value) {
     if (!strcmp(name, "gemm_bk16")) { g_opt_gemm_bk16 = value != 0; return 0; }
     if (!strcmp(name, "gemm_warps16")) { g_opt_gemm_warps16 = value != 0; return 0; }
     if (!strcmp(name, "gemm_no_small")) { g_opt_gemm_no_small = value != 0; return 0; }
+    if (!strcmp(name, "gemm_small_max")) { g_opt_gemm_small_max = value; return 0; }
     if (!strcmp(name, "wapply_onepass")) { g_opt_wapply_onepass = value != 0; return 0; }
     if (!strcmp(name, "heev_ql")) { g_opt_heev_ql = value != 0; return 0; }
     if (!strcmp(name, "heev_ring")) { g_opt_heev_ring = value; return 0; }
@@ -133,6 +135,7 @@ int yb_gemm(int op, int nbatch, int ngroups, const int32_t* mask, yb_extent e0, 
     P.ragged = g_opt_gemm_ragged.load(std::memory_order_relaxed);
     P.warps16 = g_opt_gemm_warps16.load(std::memory_order_relaxed);
     P.no_small = g_opt_gemm_no_small.load(std::memory_order_relaxed);
+    P.small_max = g_opt_gemm_small_max.load(std::memory_order_relaxed);
     P.flops = g_flop_counter;
     cudaError_t e = yb_launch_gemm(P, max_m, max_n, (cudaStream_t)stream);
     if (e != cudaSuccess) return fail("yb_gemm", e);

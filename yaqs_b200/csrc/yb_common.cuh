@@ -83,6 +83,7 @@ struct YbGemmParams {
     long long sA, sB, sC; // per-trajectory slot strides (elements)
     int conj_extra;       // != 0: conjugate the B operand in addition to the op's own rule
     int ragged;           // != 0: interleaved sub-tiles that skip padding (A/B option "gemm_ragged")
+    int small_max;        // launches whose capacity M and N are both <= small_max take the element kernel (option "gemm_small_max", default 32)
     int no_small;         // != 0: never take the small-product kernel (option "gemm_no_small": A/B runs and the tile kernel's edge tests)
     int warps16;          // != 0: 16 warps with 16 x 32 warp tiles instead of 8 warps with 32 x 32 (option "gemm_warps16")
     unsigned long long* flops;   // optional device counter: every CTA adds the real flops of its tile (8 per complex MAC)

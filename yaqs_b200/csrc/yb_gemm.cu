@@ -369,14 +369,11 @@ cudaError_t yb_launch_gemm_rw(int nbatch, const int* mask, const int* el, int es
 // maxM / maxN: upper bounds of the per-trajectory M and N (grid is sized for them; empty tiles exit).
 cudaError_t yb_launch_gemm(const YbGemmParams& P, int maxM, int maxN, cudaStream_t st) {
     if (P.nbatch <= 0 || maxM <= 0 || maxN <= 0) return cudaSuccess;
-    if (maxM <= 64 && maxN <= 64 && !P.no_small) {
-        // CTAs per (trajectory, group): what the capacity needs, but no more than fills the GPU a few times over -- the actual products
-        // are often far smaller than their slots (bonds of 11 in slots of 64 at 2048 trajectories: 65 k CTAs, 63 k of them empty)
-        const int need = (maxM * maxN + 127) / 128;
-        const long long cells = (long long)P.ngroups * P.nbatch;
-        int want = (int)((64LL * 148 + cells - 1) / (cells > 0 ? cells : 1));      // (64 CTAs per SM in total, see grid_batch in yb_api.cu)
-        if (want < 1) want = 1;
-        dim3 grid(need < want ? need : want, P.ngroups, P.nbatch);
+    if (maxM <= P.small_max && maxN <= P.small_max && !P.no_small) {
+        // one thread per capacity element.  Slots up to small_max x small_max only (default 32: chi <= 16 chains and chain ends): a 64 x 64
+        // slot is either full (config 2: the DMMA tile wins) or nearly empty (config 4: a tile CTA walks a tiny actual product element-wise,
+        // one CTA per trajectory and group instead of 32 mostly idle ones here)
+        dim3 grid((maxM * maxN + 127) / 128, P.ngroups, P.nbatch);
         k_gemm_small<0><<<grid, 128, 0, st>>>(P);
         return cudaGetLastError();
     }
