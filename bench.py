@@ -75,9 +75,9 @@ def parse_args():
     ap.add_argument("--length", type=int, default=0)
     ap.add_argument("--chi", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--roofline-steps", type=int, default=1, help="the last n timed steps run their lanes one after the other with CUDA events "
-                    "around every launch of the dominant kernel families (0: none).  Such a step is slower than a concurrent one (measured: 17.7 s "
-                    "vs 12.6 s at 2 x 64 trajectories), and it counts in `value` and `e2e` like every other timed step")
+    ap.add_argument("--roofline-steps", type=int, default=1, help="in the last n timed steps ONE lane runs alone with CUDA events around "
+                    "every launch (0: none), the other lanes follow concurrently.  Such a step is slower than a fully concurrent one and it "
+                    "counts in `value` and `e2e` like every other timed step")
     ap.add_argument("--cpu-cores", type=int, default=0, help="cores for the CPU arm (0 = all)")
     args = ap.parse_args()
     wl = dict(WORKLOADS[args.workload])
@@ -556,14 +556,17 @@ def run_b200_arm(args):
             for k in range(K):
                 instr = k in instrumented
                 if instr:
+                    # ONE lane runs alone under per-launch CUDA events (a timed launch must have the GPU to itself); the events are
+                    # switched off when it is through and the other lanes do their part of the step concurrently, as in every other step
                     kern.start_timing()
-                    for e in engs:
-                        hook_tdvp(e)
-                run.advance(1, serial=instr)
-                if instr:
-                    timing = kern.stop_timing()
-                    for e in engs:
-                        e.tdvp = orig_tdvp.pop(id(e))
+                    hook_tdvp(engs[0])
+                    closed: dict = {}
+
+                    def close_timing():
+                        closed["timing"] = kern.stop_timing()
+                        engs[0].tdvp = orig_tdvp.pop(id(engs[0]))
+                    run.advance(1, serial="first", between=close_timing)
+                    timing = closed["timing"]
                     gemm_flops += timing.pop("gemm_flops")
                     for key, v in timing.pop("detail", {}).items():
                         cur = detail.setdefault(key, [0, 0.0])
@@ -572,6 +575,8 @@ def run_b200_arm(args):
                     for fam, v in timing.items():
                         fam_ms[fam] = fam_ms.get(fam, 0.0) + v["ms"]
                         fam_n[fam] = fam_n.get(fam, 0) + v["launches"]
+                else:
+                    run.advance(1)
             torch.cuda.synchronize(dev)
             t_wall = time.perf_counter() - t0
             if world > 1:
@@ -588,6 +593,7 @@ def run_b200_arm(args):
                     spans[j] = (min(a, lo), max(b, hi))
         step_ms = [spans[j][1] - spans[j][0] for j in sorted(spans)]
         assert len(step_ms) == K, (len(step_ms), K)
+        lane0_ms = {j - first_timed: e0.elapsed_time(e1) for j, e0, e1 in run.lane_runs[0].step_events if j >= first_timed}      # the instrumented lane's own steps
         ms_dev = float(sum(step_ms))
         t = torch.tensor([ms_dev, t_wall], dtype=torch.float64, device=dev)
         if world > 1:
@@ -625,7 +631,7 @@ def run_b200_arm(args):
         try:
             if wl["bound"] == "tensor" and instrumented and fam_ms.get("gemm", 0.0) > 0:
                 gemm_ms, gemm_n = fam_ms["gemm"], fam_n["gemm"]
-                instr_ms = sum(step_ms[k] for k in instrumented)
+                instr_ms = sum(lane0_ms[k] for k in instrumented)      # the instrumented lane's own step (it runs alone)
                 achieved = gemm_flops / (gemm_ms / 1000.0) / 1e12
                 traffic = None
                 try:
@@ -639,8 +645,10 @@ def run_b200_arm(args):
                     "peak_source": "measured FP64 DMMA issue peak on this pool (profiles/r01_fp64_peak.json); MEASURED_PEAKS.json carries only HBM and bf16",
                     "launches": gemm_n, "avg_launch_ms": gemm_ms / max(gemm_n, 1), "algorithmic_flops_per_launch": gemm_flops / max(gemm_n, 1),
                     "share_of_step": gemm_ms / instr_ms,
-                    "timing": f"CUDA events around every launch inside timed steps {instrumented} (their lanes run one after the other so that a "
-                              f"launch has the GPU to itself); flops counted on the device by every CTA (8 per complex multiply-add of its tile)",
+                    "timing": f"CUDA events around every launch of ONE lane ({engs[0].B} trajectories) inside timed steps {instrumented}: that lane runs "
+                              f"alone so that a launch has the GPU to itself, the other lanes do their part of the step concurrently afterwards; "
+                              f"flops counted on the device by every CTA (8 per complex multiply-add of its tile)",
+                    "instrumented_lane_batch": engs[0].B,
                     "other_kernels_ms_per_step": {k: v / len(instrumented) for k, v in fam_ms.items() if k != "gemm"},
                     "gemm_ms_per_step": gemm_ms / len(instrumented)}
             else:                                             # HBM-bound regime: the whole step against the copy bandwidth

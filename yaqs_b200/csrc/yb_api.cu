@@ -40,13 +40,13 @@ inline int grid_for(long long n, int threads, int cap = 4096) {
 // (the largest admissible bond dimensions), the actual extents are known on the device only: at 2048 trajectories with bonds of 11
 // inside slots of 64 (config 4) a grid of 64 CTAs per trajectory is 131 k CTAs of which 129 k find nothing to do -- ~40 us per
 // launch, 14 launches per gauge shift (profiles/r02_bench_C4_v2_graphs.json: 4.6 s per Trotter step at a quarter of the host calls).
-// Enough CTAs to fill the GPU a few times over (16 per SM in total, 256 threads each: these kernels move a few bytes per element),
-// never more than the capacity needs.  Measured on config 4 (`gpurun_out` calls 24-26): 8 per SM 2055, 64 per SM 1635 trajectory-steps/s;
+// Enough CTAs to fill the GPU a few times over (8 per SM in total, 256 threads each: these kernels move a few bytes per element),
+// never more than the capacity needs.  Measured on config 4 (`gpurun_out` calls 24-26): 8 per SM 2055, 16 per SM 1524 (with 64 x 64 slots on the tile kernel), 64 per SM 1635 trajectory-steps/s;
 // compute-heavy element kernels must not be capped this way (config 2's 64 x 64 x 320 products on one CTA per trajectory: 149.5 -> 67.6),
 // which is why the small-product GEMM keeps its full grid and 64 x 64 slots go to the tile kernel.
 inline int grid_batch(long long n, int threads, int nbatch, int cap = 64) {
     const int need = grid_for(n, threads, cap);
-    int want = (16 * 148 + nbatch - 1) / (nbatch > 0 ? nbatch : 1);
+    int want = (8 * 148 + nbatch - 1) / (nbatch > 0 ? nbatch : 1);
     if (want < 1) want = 1;
     return need < want ? need : want;
 }

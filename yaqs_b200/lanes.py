@@ -23,13 +23,24 @@ class Lanes:
         self.cuda = self.device.type == "cuda"
         self.streams = [torch.cuda.Stream(self.device) for _ in range(self.n)] if (self.cuda and self.n > 1) else []
 
-    def map(self, fn: Callable, items: Sequence, serial: bool = False) -> list:
+    def map(self, fn: Callable, items: Sequence, serial: bool | str = False, between: Callable | None = None) -> list:
         """fn(item) for every item, at most ``n`` at a time, each on its own stream; results in item order.  ``serial``: one
-        after the other on the caller's stream (bench.py's instrumented steps: a kernel timed with CUDA events must have the GPU
-        to itself)."""
+        after the other on the caller's stream (a kernel timed with CUDA events must have the GPU to itself); ``serial="first"``:
+        only the first item runs alone on the caller's stream, ``between()`` is called, the others run concurrently afterwards
+        (bench.py's instrumented step: one lane under per-launch events, the rest of the step at full speed)."""
         items = list(items)
+        if serial == "first" and self.streams and len(items) > 1:
+            first = fn(items[0])
+            if self.cuda:
+                torch.cuda.current_stream(self.device).synchronize()
+            if between is not None:
+                between()
+            return [first] + self.map(fn, items[1:], serial=False)
         if serial or not self.streams or len(items) <= 1:
-            return [fn(it) for it in items]
+            out = [fn(it) for it in items]
+            if between is not None:
+                between()
+            return out
         out: list = [None] * len(items)
         errs: list = []
         main = torch.cuda.current_stream(self.device)

@@ -437,7 +437,7 @@ class AnalogRun:
     def n_times(self) -> int:
         return self.ep.n_times
 
-    def advance(self, nsteps: int | None = 1, serial: bool = False) -> int:
+    def advance(self, nsteps: int | None = 1, serial: bool | str = False, between=None) -> int:
         """Execute the next ``nsteps`` time indices (None: all that remain) for every trajectory of this rank; returns the last
         time index done.  Index 0 is the initial measurement, index j the state at ``times[j]``.  ``serial``: lanes one after
         the other instead of concurrently (instrumented steps of bench.py)."""
@@ -446,7 +446,7 @@ class AnalogRun:
         if target <= self.j_done:
             return self.j_done
         if self.resident:
-            self.lanes.map(lambda lane: lane.advance(target), self.lane_runs, serial=serial)
+            self.lanes.map(lambda lane: lane.advance(target), self.lane_runs, serial=serial, between=between)
         else:                                              # wave by wave: every job runs its whole time grid, then frees its engine
             if target != last:
                 raise ValueError("step-wise execution needs Simulator.open (resident shard)")
