@@ -412,3 +412,14 @@ def test_user_tensors_keep_their_norm():
         assert np.max(np.abs(m @ m.conj().T - np.eye(t.shape[1]))) < 1e-12
     mps.normalize()
     assert abs(np.linalg.norm(dense(mps.tensors)) - 1.0) < 1e-12
+
+
+def test_lanes_first_mode_runs_first_item_then_calls_between():
+    """Lanes.map(serial="first") (bench.py's instrumented step): the first item alone, the callback, then the rest; on a CPU device
+    (no streams) it degrades to the serial order with the callback at the end."""
+    from yaqs_b200.lanes import Lanes
+    order = []
+    lanes = Lanes("cpu", 3)
+    out = lanes.map(lambda x: (order.append(x), x * 2)[1], [1, 2, 3], serial="first", between=lambda: order.append("between"))
+    assert out == [2, 4, 6]
+    assert order[0] == 1 and "between" in order and order.index("between") >= 1

@@ -603,30 +603,41 @@ int yb_graph_begin(void* stream) {
     return e == cudaSuccess ? 0 : fail("yb_graph_begin", e);
 }
 
+struct YbGraph { cudaGraphExec_t exec; long long kernels; };      // the handle yb_graph_end returns: executable + its number of kernel nodes
+
 int yb_graph_end(void* stream, void** graph_exec) {
     if (!graph_exec) return fail_msg("yb_graph_end: graph_exec is NULL");
     *graph_exec = nullptr;
     cudaGraph_t g = nullptr;
     cudaError_t e = cudaStreamEndCapture((cudaStream_t)stream, &g);
     if (e != cudaSuccess || !g) return fail("yb_graph_end(capture)", e != cudaSuccess ? e : cudaErrorUnknown);
+    size_t nodes = 0;
+    cudaGraphGetNodes(g, nullptr, &nodes);
     cudaGraphExec_t ex = nullptr;
     e = cudaGraphInstantiate(&ex, g, 0);
     cudaGraphDestroy(g);
     if (e != cudaSuccess) return fail("yb_graph_end(instantiate)", e);
-    *graph_exec = (void*)ex;
+    // the launches recorded during the capture were counted by done() although nothing ran: take them back, a replay counts them
+    g_launches.fetch_sub((long long)nodes, std::memory_order_relaxed);
+    *graph_exec = (void*)new YbGraph{ex, (long long)nodes};
     return 0;
 }
 
 int yb_graph_launch(void* graph_exec, void* stream) {
     if (!graph_exec) return fail_msg("yb_graph_launch: no graph");
-    cudaError_t e = cudaGraphLaunch((cudaGraphExec_t)graph_exec, (cudaStream_t)stream);
+    YbGraph* gr = (YbGraph*)graph_exec;
+    cudaError_t e = cudaGraphLaunch(gr->exec, (cudaStream_t)stream);
     if (e != cudaSuccess) return fail("yb_graph_launch", e);
-    g_launches.fetch_add(1, std::memory_order_relaxed);
+    g_launches.fetch_add(gr->kernels, std::memory_order_relaxed);     // yb_launch_count counts KERNELS, replayed ones included
     return 0;
 }
 
 int yb_graph_destroy(void* graph_exec) {
-    if (graph_exec) cudaGraphExecDestroy((cudaGraphExec_t)graph_exec);
+    if (graph_exec) {
+        YbGraph* gr = (YbGraph*)graph_exec;
+        cudaGraphExecDestroy(gr->exec);
+        delete gr;
+    }
     return 0;
 }
 
