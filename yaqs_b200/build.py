@@ -8,7 +8,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libyaqs_b200.so")
-SOURCES = ["yb_api.cu", "yb_gemm.cu", "yb_ops.cu", "yb_svd.cu", "yb_heev.cu", "yb_stedc.cuh", "yb_philox.cuh", "yb_mpo_apply.cuh", "yb_wapply.cuh", "yb_common.cuh"]
+SOURCES = ["yb_api.cu", "yb_gemm.cu", "yb_ops.cu", "yb_svd.cu", "yb_heev.cu", "yb_stedc.cuh", "yb_philox.cuh", "yb_mpo_apply.cuh", "yb_wapply.cuh", "yb_common.cuh", "yb_truncate.cuh", "yb_cholqr.cuh", "yb_hetrd.cuh", "yb_gemm_rw.cuh"]
 HEADER = os.path.join(os.path.dirname(HERE), "include", "yaqs_b200.h")
 
 

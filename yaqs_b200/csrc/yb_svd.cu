@@ -212,41 +212,7 @@ __global__ void k_svd_check(int nbatch, int* meta, int* rot_count, int* n_pendin
     rot_count[b] = 0;
 }
 
-// truncate() of core/linalg/svd_utils.py:22-104 on a descending spectrum (serial: the discarded-weight mode accumulates
-// from the smallest value upward, and that summation order is part of the keep decision).
-__device__ int truncate_keep(const double* s, int n, int mode, double threshold, int max_bond, int min_keep) {
-    if (n == 0) return 0;
-    int keep = n;
-    if (mode == 2) {                     // hard_cutoff
-        keep = 0;
-        for (int i = 0; i < n; ++i) keep += s[i] > threshold;
-    } else if (mode == 1) {              // relative
-        keep = 0;
-        if (s[0] > 0.0) for (int i = 0; i < n; ++i) keep += (s[i] / s[0]) >= threshold;
-    } else if (mode == 0) {              // discarded_weight
-        double acc = 0.0;
-        for (int idx = 0; idx < n; ++idx) {
-            const double v = s[n - 1 - idx];
-            acc += v * v;
-            if (acc >= threshold) { keep = max(n - idx, min_keep); break; }
-        }
-    } else {                             // relative_discarded_weight
-        if (s[0] <= 0.0) keep = 0;
-        else {
-            double total = 0.0;
-            for (int i = 0; i < n; ++i) { const double x = s[i] / s[0]; total += x * x; }
-            double acc = 0.0;
-            for (int idx = 0; idx < n; ++idx) {
-                const double x = s[n - 1 - idx] / s[0];
-                const double cand = acc + x * x;
-                if (cand / total <= threshold) { acc = cand; keep = n - idx - 1; } else break;
-            }
-        }
-    }
-    if (max_bond > 0) keep = min(keep, max_bond);
-    keep = max(keep, min_keep);
-    return min(keep, n);
-}
+#include "yb_truncate.cuh"
 
 
 // One CTA per trajectory.
