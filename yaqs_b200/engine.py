@@ -1529,10 +1529,9 @@ class BatchedTJM:
             broken[arr[rows] + off, rows] = True
         lit_h = np.zeros((n, B), dtype=np.int32)           # row i: trajectories that need the literal merge + split at bond i
         lit_h[1:] = (broken[:-1] & jump_h[None, :])
-        red_h = (jump_h[None, :] & (lit_h == 0)).astype(np.int32)
-        plan = torch.from_numpy(np.concatenate([sa_h[None], sb_h[None], sc_h[None], lit_h, red_h])).to(dev)      # one upload
+        plan = torch.from_numpy(np.concatenate([sa_h[None], sb_h[None], sc_h[None], lit_h])).to(dev)      # one upload
         site_a, site_b, site_c = plan[0], plan[1], plan[2]
-        lit_d, red_d = plan[3: 3 + n], plan[3 + n: 3 + 2 * n]
+        lit_d = plan[3: 3 + n]
         # the operator rows of the selected processes were gathered by yb_jump_select: [B][4 | 4 | 16] = first-site op, second-site op, pair op
         nops = self.JT_NOPS
         ops_a, ops_b, ops_c = self.jt_ops, self.jt_ops[4:], self.jt_ops[8:]
@@ -1553,15 +1552,17 @@ class BatchedTJM:
                 th = self.merge(st, s_, m_s)
                 K.apply_local_op(B, m_s, None, 0, st.ext(s_), st.ext(s_ + 2), d * d, ops_c, nops, th, lay.cap[s_] * lay.cap[s_ + 2])
                 self.split_theta(st, s_, "right", user, m_s, fast=True)
-        # normalize("B", "SVD"): right-to-left merged SVD shifts.  Where the left neighbour is still a left isometry the
-        # reduced shift is identical; where it carries a jump operator the literal merge + split is needed.
-        nlit, nred = lit_h.sum(axis=1), red_h.sum(axis=1)
+        # normalize("B", "SVD"): right-to-left merged SVD shifts (mps.py:815-839).  Where the left neighbour is still a left isometry the
+        # reduced shift has the merged pair's singular values; where it carries a non-unitary jump operator it is made an isometry again
+        # first -- A'_{i-1} = Q R without truncation (a keep-all shift to the right: Cholesky-QR, or the eigen-solver route when the
+        # operator left it rank-deficient), R into the centre -- so that theta = Q (R C_i) has the singular values of R C_i and the
+        # reduced shift decides exactly what the reference's merged SVD decides.  (Round 1 took the literal merge + split: a 256 x 256
+        # eigen-solve for the one or two trajectories concerned, 3.9 ms of latency each.)
+        nlit = lit_h.sum(axis=1)
         for i in reversed(range(1, n)):
             if nlit[i] > 0:
-                self.merge(st, i - 1, lit_d[i])
-                self.split_theta(st, i - 1, "left", shift, lit_d[i], fast=True)
-            if nred[i] > 0:
-                self.shift_left(st, i, shift, red_d[i], fast=True)
+                self.shift_right(st, i - 1, keep_all, lit_d[i], fast=True)
+            self.shift_left(st, i, shift, jmask, fast=True)
         self.normalize_site(st, 0, jmask)
 
     # ------------------------------------------------------------------------------------------------------------------
