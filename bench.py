@@ -118,7 +118,7 @@ def noise_processes(wl: dict) -> list[dict]:
 
 def workload_config(args, nranks):
     wl = args.wl
-    return {"workload": wl["name"], "model": None, "hamiltonian": "ising J=1 g=0.5" if wl["model"] == "ising" else "heisenberg Jx=Jy=Jz=1",
+    return {"workload": wl["name"], "hamiltonian": "ising J=1 g=0.5" if wl["model"] == "ising" else "heisenberg Jx=Jy=Jz=1",
             "length": wl["length"], "chi_max": wl["chi"], "noise": "+".join(wl["noise"]) + f" gamma={wl['gamma']} per site" + (f", crosstalk_xx {wl['xx']} per pair" if wl.get("xx") else ""),
             "order": 2, "dt": 0.1, "svd_threshold": wl["threshold"], "krylov_tol": 1e-4,
             "observables": "Z on every site" + (" + ZZ on every pair" if wl.get("zz") else "") + ", every step",
@@ -325,7 +325,7 @@ def digital_noise(wl: dict) -> list[dict]:
 
 def digital_config(args, nranks, nsteps):
     wl = args.wl
-    return {"workload": wl["name"], "model": None, "circuit": f"create_ising_circuit(L={wl['length']}, J=1, g=0.5, dt=0.1, timesteps={nsteps}), sampled after every Trotter step",
+    return {"workload": wl["name"], "circuit": f"create_ising_circuit(L={wl['length']}, J=1, g=0.5, dt=0.1, timesteps={nsteps}), sampled after every Trotter step",
             "length": wl["length"], "chi_max": wl["chi"], "noise": f"2-qubit depolarizing p={wl['gamma']} per pair (15 two-qubit Paulis at p/15)", "gate_mode": "mpo",
             "svd_threshold": wl["threshold"], "observables": "Z on every qubit, every Trotter step", "initial_state": "|0...0>",
             "batch_per_gpu": wl["batch"], "global_batch": wl["batch"] * nranks, "sharding": f"trajectories x{nranks}", "lanes_per_gpu": 1,
