@@ -24,8 +24,9 @@ def engine_for_case(name, kernels, trajectories=None, **kw):
     return eng, tu, su, traj
 
 
-def check_against_golden(name, golden_dir, results, diag, log, traj, obs_tol=1e-10):
-    """Same seeds => same jump sequence, observables within obs_tol, identical diagnostics (bond dimensions)."""
+def check_against_golden(name, golden_dir, results, diag, log, traj, obs_tol=1e-10, pdf_tol=1e-10):
+    """Same seeds => same jump sequence, observables within obs_tol, jump pdfs within pdf_tol, identical diagnostics (bond dimensions).
+    On the kernel twin the pdfs agree with the reference's to 3e-15 over all fixtures; 1e-10 is BASELINE.json's bar."""
     g = np.load(os.path.join(golden_dir, f"{name}.npz"))
     res, dg = results.cpu().numpy(), diag.cpu().numpy()
     cfg = ALL_CASES.get(name, {})
@@ -49,7 +50,7 @@ def check_against_golden(name, golden_dir, results, diag, log, traj, obs_tol=1e-
             if g["jumped"][t, c]:
                 assert int(rec["choice"][row]) == int(g["choice"][t, c]), (name, t, c)
                 npr = rec["pdf"].shape[1]
-                assert np.max(np.abs(rec["pdf"][row] - g["pdf"][t, c, :npr])) < 1e-9
+                assert np.max(np.abs(rec["pdf"][row] - g["pdf"][t, c, :npr])) < pdf_tol
     return checked
 
 
