@@ -82,7 +82,7 @@ def run_case(name: str, cfg: dict) -> dict:
     sim = AnalogSimParams(observables=obs, elapsed_time=cfg["dt"] * cfg["steps"], dt=cfg["dt"], num_traj=cfg["ntraj"],
                           max_bond_dim=cfg["chi"], svd_threshold=cfg["thr"], order=cfg["order"],
                           sample_timesteps=cfg["sample_timesteps"], random_seed=cfg["seed"],
-                          tdvp_mode=cfg.get("tdvp_mode", "2site"))
+                          tdvp_mode=cfg.get("tdvp_mode", "2site"), trunc_mode=cfg.get("trunc_mode", "discarded_weight"))
     assert len(sim.times) == cfg["steps"] + 1, (len(sim.times), cfg["steps"])
     # the workers see observables in sorted order (simulator.py:1561-1562)
     sorted_sites = [getattr(o, "sites", -1) for o in sim.sorted_observables]          # PVM observables carry no sites

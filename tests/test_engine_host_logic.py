@@ -2,7 +2,7 @@
 numpy twin of the kernels, checked against the fixtures produced by the unmodified reference."""
 import pytest
 
-from oracle.golden_cases import CASES
+from oracle.golden_cases import CASES, EDGE_CASES
 from oracle.np_kernels import NumpyKernels
 from tests.helpers import check_against_golden, engine_for_case
 
@@ -17,6 +17,19 @@ def test_engine_with_twin_matches_reference(golden_dir, name):
     eng, tu, su, traj = engine_for_case(name, NumpyKernels())
     log = []
     results, diag = eng.run(tu, su, log)
+    check_against_golden(name, golden_dir, results, diag, log, traj)
+
+
+@pytest.mark.parametrize("name", sorted(EDGE_CASES))
+@pytest.mark.parametrize("gram_min_k", [33, 0])
+def test_engine_with_twin_edge_cases(golden_dir, name, gram_min_k):
+    """Edge cases of the domain against the unmodified reference: a two-site and a three-site chain, max_bond_dim = 1, the truncation
+    modes "relative", "hard_cutoff", "relative_discarded_weight" inside whole runs, a threshold that truncates at almost every split --
+    on the Jacobi route and with the Gram / Cholesky-QR routes forced onto these sizes."""
+    eng, tu, su, traj = engine_for_case(name, NumpyKernels(), gram_min_k=gram_min_k)
+    log = []
+    results, diag = eng.run(tu, su, log)
+    assert int(eng.status.abs().sum()) == 0
     check_against_golden(name, golden_dir, results, diag, log, traj)
 
 
