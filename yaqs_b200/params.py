@@ -203,7 +203,7 @@ class DigitalSimParams(_Ordering):
     def __init__(self, *, observables=None, num_traj: int | None = None, max_bond_dim=_USE_PRESET, trunc_mode: str = "discarded_weight",
                  svd_threshold: float | None = None, krylov_tol: float | None = None, preset: str = "balanced", get_state: bool = False,
                  sample_layers: bool = False, shots: int | None = None, random_seed: int | None = None, gate_mode: str = "mpo",
-                 tdvp_sweeps: int = 1, tdvp_mode: str = "2site") -> None:
+                 tdvp_sweeps: int = 1, tdvp_mode: str = "2site", num_mid_measurements: int = 0) -> None:
         _common(self, preset, num_traj, max_bond_dim, trunc_mode, svd_threshold, krylov_tol, tdvp_sweeps, tdvp_mode, random_seed)
         self.observables = [] if observables is None else list(observables)
         _check_observable_mix(self.observables)
@@ -213,7 +213,7 @@ class DigitalSimParams(_Ordering):
         self.get_state = get_state
         self.sample_layers = sample_layers
         self.shots = shots
-        self.num_mid_measurements = 0
+        self.num_mid_measurements = num_mid_measurements      # (:682,746) the run takes the count from the compiled circuit, as simulator.py:1723-1741 does
 
 
 StrongSimParams = DigitalSimParams   # pre-0.6 names used by BASELINE.json's north_star (UPGRADING.md:49-60)
