@@ -123,6 +123,159 @@ class MPS:
             acc = np.einsum("sr,prq->spq", acc, t).reshape(-1, t.shape[2])
         return acc[:, 0]
 
+    # ------------------------------------------------------------------------------------------------------------------------------
+    # Read-only inspection of a host MPS: what a user does with ``Result.output_state.mps`` (mps.py:514-678, 901-1047, 1236-1280,
+    # 1495-1660).  Host numpy, transfer-matrix contractions; nothing here is on the device path.
+    # ------------------------------------------------------------------------------------------------------------------------------
+    def bond_dimensions(self) -> list[int]:
+        """Outgoing bond of every site but the last (mps.py:514-520)."""
+        return [int(t.shape[2]) for t in self.tensors[:-1]]
+
+    def get_max_bond(self) -> int:
+        """mps.py:549-565 (the reference compares the physical and the right index of every tensor; kept as is)."""
+        return max(max(int(t.shape[0]), int(t.shape[2])) for t in self.tensors)
+
+    def get_total_bond(self) -> int:
+        """Sum of the internal bonds (mps.py:567-578)."""
+        return sum(int(t.shape[1]) for t in self.tensors[1:])
+
+    def get_cost(self) -> int:
+        """Sum of chi^3 over the internal bonds (mps.py:580-591)."""
+        return sum(int(t.shape[1]) ** 3 for t in self.tensors[1:])
+
+    def check_if_valid_mps(self) -> None:
+        """Neighbouring bonds must agree (mps.py:1567-1579)."""
+        for a, b in zip(self.tensors[:-1], self.tensors[1:]):
+            assert a.shape[2] == b.shape[1], "bond dimensions of neighbouring tensors differ"
+
+    def almost_equal(self, other: "MPS") -> bool:
+        """Tensor-by-tensor comparison, not a comparison of the represented vectors (mps.py:700-717)."""
+        return (self.length == other.length
+                and all(a.shape == b.shape and np.allclose(a, b) for a, b in zip(self.tensors, other.tensors)))
+
+    def to_vec(self) -> np.ndarray:
+        """Dense state vector in the reference's index order (mps.py:1633-1660: site 0 is the fastest-running index)."""
+        acc = np.ones((1, 1), dtype=C)                                  # (physical multi-index, open left bond), built from the right end
+        for t in reversed(self.tensors):
+            acc = np.einsum("slr,xr->xsl", t, acc).reshape(-1, t.shape[1])
+        return acc[:, 0].copy()
+
+    def _cut_values(self, sites) -> np.ndarray | None:
+        assert len(sites) == 2 and sites[0] + 1 == sites[1], "defined on a bond (two adjacent sites)"
+        a, b = self.tensors[sites[0]], self.tensors[sites[1]]
+        if a.shape[2] == 1:
+            return None
+        theta = np.einsum("slk,tkr->lstr", a, b).reshape(a.shape[1] * a.shape[0], b.shape[0] * b.shape[2])
+        return np.linalg.svd(theta, compute_uv=False)
+
+    def get_entropy(self, sites) -> np.float64:
+        """Von Neumann entropy of the two-site block's singular values (mps.py:604-642)."""
+        sv = self._cut_values(list(sites))
+        if sv is None:
+            return np.float64(0.0)
+        w = sv.astype(np.float64) ** 2
+        total = np.sum(w, dtype=np.float64)
+        if total == 0.0:
+            return np.float64(0.0)
+        prob = w / total
+        return np.float64(-np.sum(prob * np.log(prob + np.finfo(np.float64).tiny), dtype=np.float64))
+
+    def get_schmidt_spectrum(self, sites) -> np.ndarray:
+        """The block's singular values in a NaN-padded vector of 500 (mps.py:644-678)."""
+        out = np.full(500, np.nan)
+        sv = self._cut_values(list(sites))
+        if sv is None:
+            out[0] = 1.0
+        else:
+            out[: min(500, len(sv))] = sv[:500]
+        return out
+
+    def scalar_product(self, other: "MPS", sites=None) -> np.complex128:
+        """<self|other>: over the whole chain, or the local contraction at one site / one adjacent pair (mps.py:901-959)."""
+        if sites is None:
+            env = np.ones((1, 1), dtype=C)                               # (bra bond, ket bond)
+            for a, b in zip(self.tensors, other.tensors):
+                env = np.einsum("xy,sxp,syq->pq", env, a.conj(), b)
+            return np.complex128(env[0, 0])
+        where = [sites] if isinstance(sites, (int, np.integer)) else list(sites)
+        if len(where) == 1:
+            return np.complex128(np.vdot(self.tensors[where[0]], other.tensors[where[0]]))
+        if len(where) == 2:
+            i, j = where
+            assert j == i + 1, "Only nearest-neighbor two-site overlaps supported."
+            bra = np.einsum("slk,tkr->sltr", self.tensors[i], self.tensors[j])
+            ket = np.einsum("slk,tkr->sltr", other.tensors[i], other.tensors[j])
+            return np.complex128(np.vdot(bra, ket))
+        raise ValueError(f"Invalid `sites` argument: {sites!r}")
+
+    def norm(self, site: int | None = None) -> np.float64:
+        """<psi|psi> (the reference returns the squared norm, mps.py:1539-1565); with ``site`` the local contraction is taken where the
+        tracked centre sits on that site, which is the same number for a canonical state."""
+        if site is not None and self.orthogonality_center is not None and site == self.orthogonality_center:
+            return np.float64(self.scalar_product(self, site).real)
+        return np.float64(self.scalar_product(self).real)
+
+    def _operator_factors(self, observable):
+        """(sites ascending, per-site operator factors [k][2][2]): a one-site matrix as is, a two-site matrix split into a sum of
+        products (operator Schmidt decomposition), so that any two sites -- adjacent or not -- contract along the chain."""
+        raw = observable.sites
+        where = [int(raw)] if isinstance(raw, (int, np.integer)) else [int(v) for v in raw]
+        assert len(where) < 3, "Only one- and two-site observables are currently implemented."
+        for site in where:
+            assert 0 <= site < self.length, f"Observable acting on non-existing site: {site}"
+        m = np.asarray(observable.gate.matrix, dtype=C)
+        if len(where) == 1:
+            if m.shape != (2, 2):
+                raise ValueError(f"Local observable matrix shape {m.shape} does not match site {where[0]} dimension 2.")
+            return where, [m[None]]
+        if m.shape != (4, 4):
+            raise ValueError(f"Two-site observable matrix shape {m.shape} does not match site dimensions 2 and 2.")
+        t = m.reshape(2, 2, 2, 2)                                        # (out_0, out_1, in_0, in_1) in ``sites`` order
+        if where[0] > where[1]:
+            where, t = where[::-1], t.transpose(1, 0, 3, 2)
+        u, sv, vh = np.linalg.svd(t.transpose(0, 2, 1, 3).reshape(4, 4))
+        return where, [(u * sv).T.reshape(4, 2, 2), vh.reshape(4, 2, 2)]
+
+    def expect(self, observable) -> np.float64:
+        """Re <psi|O|psi> for a one- or two-site observable (mps.py:1236-1280; not divided by the norm, like the reference)."""
+        where, factors = self._operator_factors(observable)
+        nk = factors[0].shape[0]
+        env = np.zeros((nk, 1, 1), dtype=C)                              # one transfer chain per term of the operator sum
+        env[:, 0, 0] = 1.0
+        for site, t in enumerate(self.tensors):
+            if site in where:
+                op = factors[where.index(site)]
+                env = np.einsum("kxy,sxp,kst,tyq->kpq", env, t.conj(), op, t)
+            else:
+                env = np.einsum("kxy,sxp,syq->kpq", env, t.conj(), t)
+        val = complex(env[:, 0, 0].sum())
+        assert val.imag < 1e-13, f"Measurement should be real, '{val.real:16f}+{val.imag:16f}i'."
+        return np.float64(val.real)
+
+    def local_expect(self, operator, sites) -> np.complex128:
+        """The contraction restricted to the observable's site(s) -- the expectation value when the centre covers them
+        (mps.py:961-1047); one site or an adjacent pair."""
+        where = [sites] if isinstance(sites, (int, np.integer)) else list(sites)
+        m = np.asarray(operator.gate.matrix, dtype=C)
+        if len(where) == 1:
+            a = self.tensors[where[0]]
+            return np.complex128(np.vdot(a, np.einsum("st,tlr->slr", m, a)))
+        if len(where) == 2 and where[1] == where[0] + 1:
+            theta = np.einsum("slk,tkr->stlr", self.tensors[where[0]], self.tensors[where[1]])
+            acted = np.einsum("abst,stlr->ablr", m.reshape(2, 2, 2, 2), theta)
+            return np.complex128(np.vdot(theta, acted))
+        raise ValueError("Local observable must be one-site or nearest-neighbor two-site.")
+
+    def project_onto_bitstring(self, bitstring: str) -> np.complex128:
+        """|<bitstring|psi>|^2, site 0 first (mps.py:1495-1537)."""
+        assert len(bitstring) == self.length, "Bitstring length must match number of sites"
+        row = np.ones(1, dtype=C)
+        for site, char in enumerate(bitstring):
+            index = int(char)
+            assert 0 <= index < 2, f"Invalid state index {index} at site {site}"
+            row = row @ self.tensors[site][index]
+        return np.complex128(abs(row[0]) ** 2)
+
 
 class MPO:
     """Matrix product operator: tensors (s_out, s_in, l, r).  Factories build the operator with an exact finite-state
