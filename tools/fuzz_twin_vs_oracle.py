@@ -178,11 +178,18 @@ def main() -> int:
     ap.add_argument("--cases", type=int, default=40)
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--keep-going", action="store_true")
+    ap.add_argument("--dynamic", action="store_true", help='tdvp_mode="dynamic" without a cap or with one the bonds stay below (DESIGN.md 4.13)')
     args = ap.parse_args()
     rng = np.random.default_rng(args.seed)
     bad = 0
     for n in range(args.cases):
-        cfg = draw_case(rng)
+        cfg = draw_case(rng, allow_1site=not args.dynamic)
+        if args.dynamic:
+            cfg["tdvp_mode"], cfg["chi"], cfg["L"] = "dynamic", (None if rng.random() < 0.7 else 64), min(cfg["L"], 6)
+            cfg["noise2"] = [pr for pr in cfg.get("noise2", []) if max(pr[1]) < cfg["L"]]
+            if cfg["init"].startswith("random:"):
+                _, chi0, seed0 = cfg["init"].split(":")
+                cfg["init"] = f"random:{min(int(chi0), 4)}:{seed0}"
         for route in (None, 0):
             t0 = time.time()
             try:
