@@ -74,7 +74,7 @@ class IllPosedWatch:
     singular values, a discarded weight within 1e-6 (relative) of the threshold, a Lanczos stop / breakdown test within 1e-3 of its bound.  The reference itself is not reproducible across
     LAPACK builds on such a case (tools/fuzz notes in DESIGN.md section 2), so it is reported as ill-posed, not as a mismatch."""
 
-    def __init__(self, gap: float = 1e-7, rel: float = 1e-6):
+    def __init__(self, gap: float = 1e-4, rel: float = 1e-6):
         self.gap, self.rel, self.notes = gap, rel, []
 
     def __enter__(self):
