@@ -69,9 +69,13 @@ def main() -> int:
     ap.add_argument("--cases", type=int, default=100)
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--digital", action="store_true")
+    ap.add_argument("--gates", action="store_true", help="digital: random gate lists over the whole gate registry")
     ap.add_argument("--keep-going", action="store_true")
     args = ap.parse_args()
-    if args.digital:
+    args.digital = args.digital or args.gates
+    if args.gates:
+        from fuzz_digital_twin_vs_oracle import draw_gate_case as draw_case
+    elif args.digital:
         from fuzz_digital_twin_vs_oracle import draw_case
     else:
         from fuzz_twin_vs_oracle import draw_case

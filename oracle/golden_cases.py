@@ -316,7 +316,25 @@ FULL_DIGITAL_CASES = {
                                 noise=[("pauli_x", 2e-3 / 15), ("pauli_y", 2e-3 / 15), ("pauli_z", 2e-3 / 15)],
                                 noise2=[(f"crosstalk_{a}{b}", 1e-3 / 15) for a in "xyz" for b in "xyz"]),
 }
-ALL_DIGITAL_CASES = {**DIGITAL_CASES, **LARGE_DIGITAL_CASES, **FULL_DIGITAL_CASES}
+# Controlled gates and the remaining single-qubit names of the reference's registry (third session of round 2): cx / cz / cp carry
+# product-form generators in the reference (gate_library.py:1193-1197, 1244-1248, 1397-1401), so a long-range one takes the TDVP
+# window in gate_mode="tdvp" and EVERY one does in "full-tdvp" (digital_tjm.py:605-623); control and target in both orders, adjacent
+# and across spectators; u2 / u3 / u1 / sxdg / i from the qiskit name table (dag_utils.py:51-83).  The GPU twin of these cases is
+# opt-in (YB_RUN_EDGE_CASES=1) until it has been seen green on a B200.
+_CGATES = ([("h", (), (q,)) for q in range(6)]
+           + [("u2", (0.3, -0.8), (1,)), ("u3", (0.5, 0.2, -0.4), (2,)), ("sxdg", (), (3,)), ("u1", (0.6,), (4,)), ("i", (), (5,)),
+              ("cx", (), (0, 1)), ("cx", (), (4, 1)), ("cz", (), (2, 5)), ("cp", (0.7,), (5, 2)), ("cp", (0.4,), (1, 2)),
+              ("swap", (), (3, 4)), ("rxx", (0.3,), (0, 3)), ("sample", (), ()),
+              ("ry", (0.4,), (0,)), ("cx", (), (3, 2)), ("cz", (), (4, 5)), ("cp", (-0.9,), (0, 5)), ("cx", (), (1, 4)), ("tdg", (), (2,))])
+CONTROLLED_DIGITAL_CASES = {
+    # (the window cases start from a seeded random bond-2 state: on a product state min_keep = 2 makes every TDVP window keep a
+    # numerically zero singular value, whose vector is LAPACK's null-space completion -- the reference is not reproducible there)
+    f"dig_cgates6_{tag}": dict(L=6, circuit="gates", gates=_CGATES, chi=chi, thr=1e-9, ntraj=3, seed=60 + k, init=init, obs="x+z", sample=True,
+                               gate_mode=mode, noise=[("lowering", 0.05), ("pauli_z", 0.03)])
+    for k, (tag, mode, chi, init) in enumerate([("window", "tdvp", None, "random:2:71"), ("full_window", "full-tdvp", None, "random:2:72"),
+                                                ("mpo", "mpo", 8, "zeros"), ("swaps", "swaps", 8, "zeros")])
+}
+ALL_DIGITAL_CASES = {**DIGITAL_CASES, **LARGE_DIGITAL_CASES, **FULL_DIGITAL_CASES, **CONTROLLED_DIGITAL_CASES}
 
 
 def toffoli_gate_list(cfg: dict) -> list[tuple]:
@@ -333,6 +351,14 @@ def toffoli_gate_list(cfg: dict) -> list[tuple]:
         if cfg["sample"] and step < cfg["timesteps"] - 1:
             gates.append(("sample", (), ()))
     return gates
+
+
+def gate_list_for(cfg: dict) -> list[tuple]:
+    """Neutral gate list of a fixture whose circuit is not an Ising Trotter circuit: cfg["circuit"] == "toffoli" (above) or "gates"
+    (cfg["gates"] holds the list; entries (name, params, qubits), ("sample", (), ()) = SAMPLE_OBSERVABLES barrier)."""
+    if cfg.get("circuit") == "toffoli":
+        return toffoli_gate_list(cfg)
+    return [(n, tuple(pr), tuple(q)) for n, pr, q in cfg["gates"]]
 
 
 def toffoli_oracle_layers(cfg: dict) -> list:
@@ -365,6 +391,8 @@ def digital_inputs(cfg: dict):
     L = cfg["L"]
     if cfg.get("circuit") == "toffoli":
         layers = toffoli_oracle_layers(cfg)
+    elif cfg.get("circuit") == "gates":
+        layers = O.layers_from_gate_list(gate_list_for(cfg))
     else:
         layers = O.ising_trotter_layers(L, cfg["J"], cfg["g"], cfg["dt"], cfg["timesteps"], cfg["periodic"], sample_each_step=cfg["sample"])
     obs = []
@@ -383,7 +411,7 @@ def digital_inputs(cfg: dict):
     procs += [O.make_process(n, [i, i + 1], g) for i in range(L - 1) for (n, g) in cfg.get("noise2", [])]
     p = O.OracleParams(dt=1.0, n_steps=1, order=1, max_bond_dim=cfg["chi"], svd_threshold=cfg["thr"], krylov_tol=cfg.get("krylov_tol", 1e-4),
                        digital=True)
-    return O.product_state(L, cfg["init"]), layers, (procs if procs else None), p, obs
+    return initial_state(cfg), layers, (procs if procs else None), p, obs
 
 
 def run_oracle_digital_case(cfg: dict, trajectories=None):

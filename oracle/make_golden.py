@@ -185,10 +185,10 @@ def run_digital_case(name: str, cfg: dict) -> dict:
     from mqt.yaqs.core.random_utils import make_trajectory_rng
 
     L = cfg["L"]
-    if cfg.get("circuit") == "toffoli":                      # three-qubit gates from the reference's own GateLibrary, one gate per layer
-        from oracle.golden_cases import toffoli_gate_list
+    if cfg.get("circuit") in ("toffoli", "gates"):           # gates from the reference's own GateLibrary, one gate per layer
+        from oracle.golden_cases import gate_list_for
         layers = []
-        for gname, params, qubits in toffoli_gate_list(cfg):
+        for gname, params, qubits in gate_list_for(cfg):
             if gname == "sample":
                 layers.append(ref_dig._CompiledCircuitLayer((), (), (), 1))
                 continue
@@ -231,7 +231,12 @@ def run_digital_case(name: str, cfg: dict) -> dict:
 
         MPS.record_diagnostics = rec
         try:
-            mps = MPS(L, state=cfg["init"])
+            if cfg["init"].startswith("random:"):
+                mps = MPS(L, state="zeros")
+                mps.tensors = [t.copy() for t in initial_state(cfg).tensors]
+                mps.set_center(0)
+            else:
+                mps = MPS(L, state=cfg["init"])
             rng = _RecordingRng(make_trajectory_rng(tr, base_seed=cfg["seed"]), log, "traj")
             res, diag, _counts, _final = ref_dig.digital_tjm((tr, mps, noise, sim, None), rng=rng, compiled_circuit=compiled)
         finally:

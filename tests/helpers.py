@@ -61,11 +61,11 @@ def digital_engine_for_case(name, kernels, trajectories=None, **kw):
     cfg = ALL_DIGITAL_CASES[name]
     init, _layers, noise, p, obs = digital_inputs(cfg)
     L = cfg["L"]
-    if cfg.get("circuit") == "toffoli":
-        from oracle.golden_cases import toffoli_gate_list
+    if cfg.get("circuit") in ("toffoli", "gates"):
+        from oracle.golden_cases import gate_list_for
         from yaqs_b200.circuits import SAMPLE_LABEL, Circuit
         circ = Circuit(L)
-        for gname, params, qubits in toffoli_gate_list(cfg):
+        for gname, params, qubits in gate_list_for(cfg):
             if gname == "sample":
                 circ.barrier(label=SAMPLE_LABEL)
             else:

@@ -57,7 +57,7 @@ def test_engine_with_twin_capped_split_keeps_top_rows_only(golden_dir, name):
     check_against_golden(name, golden_dir, results, diag, log, traj)
 
 
-from oracle.golden_cases import DIGITAL_CASES  # noqa: E402
+from oracle.golden_cases import CONTROLLED_DIGITAL_CASES, DIGITAL_CASES  # noqa: E402
 from tests.helpers import digital_engine_for_case  # noqa: E402
 
 
@@ -68,6 +68,18 @@ def test_digital_engine_with_twin_matches_reference(golden_dir, name):
     eng, compiled, tu, traj, cfg = digital_engine_for_case(name, NumpyKernels())
     log = []
     results, diag = eng.run_digital(compiled.layers, tu, cfg["sample"], cfg["gate_mode"], log)
+    check_against_golden(name, golden_dir, results, diag, log, traj)
+
+
+@pytest.mark.parametrize("name", sorted(CONTROLLED_DIGITAL_CASES))
+def test_digital_engine_with_twin_controlled_gates(golden_dir, name):
+    """cx / cz / cp with control and target in both orders, adjacent and across spectators, through all four gate routes -- in the
+    TDVP modes they evolve under the product-form generators the reference gives them (gate_library.py:1193-1197, 1244-1248,
+    1397-1401) -- and the single-qubit names u2 / u3 / u1 / sxdg / i of the qiskit name table; fixtures of the unmodified reference."""
+    eng, compiled, tu, traj, cfg = digital_engine_for_case(name, NumpyKernels())
+    log = []
+    results, diag = eng.run_digital(compiled.layers, tu, cfg["sample"], cfg["gate_mode"], log)
+    assert int(eng.status.abs().sum()) == 0
     check_against_golden(name, golden_dir, results, diag, log, traj)
 
 

@@ -40,6 +40,42 @@ def draw_case(rng: np.random.Generator) -> dict:
                 gate_mode=str(rng.choice(["mpo", "swaps", "tdvp"])) if periodic else "mpo", noise=noise, noise2=noise2)
 
 
+ONE_Q = ["x", "y", "z", "h", "s", "sdg", "t", "tdg", "sx", "sxdg", "id", "rx", "ry", "rz", "p", "u1", "u2", "u3", "u"]
+TWO_Q = ["cx", "cz", "cp", "rxx", "ryy", "rzz", "swap"]
+THREE_Q = ["ccx", "ccz", "cswap"]
+N_ANGLES = {"rx": 1, "ry": 1, "rz": 1, "p": 1, "u1": 1, "u2": 2, "u3": 3, "u": 3, "cp": 1, "rxx": 1, "ryy": 1, "rzz": 1}
+
+
+def draw_gate_case(rng: np.random.Generator) -> dict:
+    """A random gate list over the whole registry (dag_utils.py:51-83), one gate per layer: one-, two- (adjacent and long-range, both
+    site orders) and three-qubit gates, through a random gate route, from a seeded random bond-2 state (a product state makes every
+    TDVP window ill-posed: min_keep = 2 keeps a numerically zero singular value)."""
+    L = int(rng.integers(3, 8))
+    gates = []
+    for _ in range(int(rng.integers(4, 16))):
+        kind = rng.random()
+        if kind < 0.4:
+            name = str(rng.choice(ONE_Q))
+            qubits = (int(rng.integers(0, L)),)
+        elif kind < 0.92 or L < 4:
+            name = str(rng.choice(TWO_Q))
+            a, b = (int(v) for v in rng.choice(L, size=2, replace=False))
+            qubits = (a, b)
+        else:
+            name = str(rng.choice(THREE_Q))
+            qubits = tuple(int(v) for v in rng.choice(L, size=3, replace=False))
+        params = tuple(float(np.round(rng.uniform(-2.5, 2.5), 3)) for _ in range(N_ANGLES.get(name, 0)))
+        gates.append((name, params, qubits))
+        if rng.random() < 0.12:
+            gates.append(("sample", (), ()))
+    n_one = int(rng.integers(0, 3))
+    noise = [(str(n), float(np.round(rng.uniform(0.01, 0.3), 3))) for n in rng.choice(ONE_SITE, size=n_one, replace=False)]
+    return dict(L=L, circuit="gates", gates=gates, chi=(None if rng.random() < 0.5 else int(rng.choice([4, 8, 16]))), thr=float(10.0 ** rng.uniform(-12, -6)),
+                ntraj=int(rng.integers(1, 4)), seed=int(rng.integers(0, 10000)), init=f"random:2:{int(rng.integers(1, 1000))}",
+                obs=str(rng.choice(["z", "x+z", "z+zz"])), sample=bool(rng.random() < 0.6), gate_mode=str(rng.choice(["mpo", "swaps", "tdvp", "full-tdvp"])),
+                noise=noise, noise2=[])
+
+
 def run_one(cfg: dict):
     import torch
 
@@ -99,11 +135,12 @@ def main() -> int:
     ap.add_argument("--cases", type=int, default=40)
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--keep-going", action="store_true")
+    ap.add_argument("--gates", action="store_true", help="random gate lists over the whole gate registry instead of Ising Trotter circuits")
     args = ap.parse_args()
     rng = np.random.default_rng(args.seed)
     bad = 0
     for n in range(args.cases):
-        cfg = draw_case(rng)
+        cfg = draw_gate_case(rng) if args.gates else draw_case(rng)
         t0 = time.time()
         try:
             why, worst = run_one(cfg)

@@ -17,8 +17,8 @@ from dataclasses import dataclass, field
 from .gates import BaseGate, GateLibrary
 
 SAMPLE_LABEL = "SAMPLE_OBSERVABLES"
-_PARAM_GATES = {"rx", "ry", "rz", "p", "rxx", "ryy", "rzz", "cp", "u"}
-_FIXED_GATES = {"x", "y", "z", "h", "id", "sx", "s", "sdg", "t", "tdg", "cx", "cz", "swap", "ccx", "ccz", "cswap"}
+_PARAM_GATES = {"rx": 1, "ry": 1, "rz": 1, "p": 1, "u1": 1, "rxx": 1, "ryy": 1, "rzz": 1, "cp": 1, "u2": 2, "u": 3, "u3": 3}      # name -> number of angles
+_FIXED_GATES = {"x", "y", "z", "h", "id", "i", "iden", "sx", "sxdg", "s", "sdg", "t", "tdg", "cx", "cz", "swap", "ccx", "ccz", "cswap"}
 
 
 @dataclass
@@ -54,7 +54,7 @@ class Circuit:
         if name in _FIXED_GATES:
             return lambda *qubits: self._add(name, qubits)
         if name in _PARAM_GATES:
-            nparam = 3 if name == "u" else 1
+            nparam = _PARAM_GATES[name]
 
             def add(*args, **kw):
                 vals = list(args) + [kw[k] for k in ("theta", "phi", "lam") if k in kw]

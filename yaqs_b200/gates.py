@@ -108,8 +108,11 @@ class GateLibrary:
     y = staticmethod(_fixed("y", _Y))
     z = staticmethod(_fixed("z", _Z))
     id = staticmethod(_fixed("id", _I))
+    i = staticmethod(_fixed("id", _I))                 # qiskit's other names of the identity (gate_library.py:2008-2009)
+    iden = staticmethod(_fixed("id", _I))
     h = staticmethod(_fixed("h", np.array([[1, 1], [1, -1]]) / np.sqrt(2)))
     sx = staticmethod(_fixed("sx", 0.5 * np.array([[1 + 1j, 1 - 1j], [1 - 1j, 1 + 1j]])))
+    sxdg = staticmethod(_fixed("sxdg", 0.5 * np.array([[1 - 1j, 1 + 1j], [1 + 1j, 1 - 1j]])))          # gate_library.py:927-946
     s = staticmethod(_fixed("s", np.array([[1, 0], [0, 1j]])))
     sdg = staticmethod(_fixed("sdg", np.array([[1, 0], [0, -1j]])))
     t = staticmethod(_fixed("t", np.array([[1, 0], [0, np.exp(1j * np.pi / 4)]])))
@@ -121,8 +124,21 @@ class GateLibrary:
     xx = staticmethod(_fixed("xx", np.kron(_X, _X)))
     yy = staticmethod(_fixed("yy", np.kron(_Y, _Y)))
     zz = staticmethod(_fixed("zz", np.kron(_Z, _Z)))
-    cx = staticmethod(_fixed("cx", np.array([[1, 0, 0, 0], [0, 1, 0, 0], [0, 0, 0, 1], [0, 0, 1, 0]])))
-    cz = staticmethod(_fixed("cz", np.diag([1, 1, 1, -1])))
+    @staticmethod
+    def cx() -> BaseGate:
+        """gate_library.py:1148-1200: control on the first site; generator pi/4 (I - Z) (x) (I - X), which is what a long-range CX
+        evolves under in the TDVP gate window (digital_tjm.py:324-452)."""
+        g = BaseGate(np.array([[1, 0, 0, 0], [0, 1, 0, 0], [0, 0, 0, 1], [0, 0, 1, 0]]), name="cx", interaction=2)
+        g.generator = [(np.pi / 4) * np.array([[0, 0], [0, 2]], dtype=C), np.array([[1, -1], [-1, 1]], dtype=C)]
+        return g
+
+    @staticmethod
+    def cz() -> BaseGate:
+        """gate_library.py:1203-1252: generator pi/4 (I - Z) (x) (I - Z)."""
+        g = BaseGate(np.diag([1, 1, 1, -1]), name="cz", interaction=2)
+        g.generator = [(np.pi / 4) * np.array([[0, 0], [0, 2]], dtype=C), np.array([[0, 0], [0, 2]], dtype=C)]
+        return g
+
     swap = staticmethod(_fixed("swap", np.array([[1, 0, 0, 0], [0, 0, 1, 0], [0, 1, 0, 0], [0, 0, 0, 1]])))
     cswap = staticmethod(_fixed("cswap", np.eye(8)[[0, 1, 2, 3, 4, 6, 5, 7]], 3))         # no product-form generator (gate_library.py:1455-1499)
 
@@ -182,6 +198,23 @@ class GateLibrary:
         return BaseGate(m, name="u")
 
     @staticmethod
+    def u3(theta: float, phi: float, lam: float) -> BaseGate:
+        """qiskit's older name of ``u`` (gate_library.py:2015)."""
+        return GateLibrary.u(theta, phi, lam)
+
+    @staticmethod
+    def u2(phi: float, lam: float) -> BaseGate:
+        """gate_library.py:1074-1107: (1 / sqrt 2) [[1, -e^{i lam}], [e^{i phi}, e^{i (phi + lam)}]]."""
+        g = BaseGate(np.array([[1, -np.exp(1j * lam)], [np.exp(1j * phi), np.exp(1j * (phi + lam))]]) / np.sqrt(2), name="u2")
+        g.phi, g.lam = phi, lam
+        return g
+
+    @staticmethod
+    def u1(theta: float) -> BaseGate:
+        """The phase gate under its older name (gate_library.py:2017: ``u1 = Phase``)."""
+        return GateLibrary.p(theta)
+
+    @staticmethod
     def _two_rot(name: str, pa, pb, theta: float) -> BaseGate:
         g = BaseGate(_rot2(pa, pb)(theta), name=name, interaction=2)
         g.theta = theta
@@ -205,6 +238,7 @@ class GateLibrary:
     def cp(theta: float) -> BaseGate:
         g = BaseGate(np.diag([1, 1, 1, np.exp(1j * theta)]), name="cp", interaction=2)
         g.theta = theta
+        g.generator = [-theta * np.array([[0, 0], [0, 1]], dtype=C), np.array([[0, 0], [0, 1]], dtype=C)]      # gate_library.py:1397-1401
         return g
 
 
