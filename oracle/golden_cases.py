@@ -169,6 +169,16 @@ EDGE_CASES = {
     "ising8_coarse_threshold_order2": dict(model="ising", L=8, J=1.0, g=1.0, init="x+", chi=8, thr=1e-4, order=2, dt=0.1, steps=6,
                                            sample_timesteps=True, ntraj=4, seed=57, obs="z",
                                            noise=[("raising", 0.3), ("pauli_y", 0.2)]),
+    # Hamiltonians given as Pauli sums of any range (MPO.from_pauli_sum, mpo.py:1171-1317): power-law ZZ couplings between all pairs,
+    # a transverse field and a three-body string; the engine runs the product's exact finite-state MPO, the oracle a plain direct sum
+    "paulisum6_longrange_order2": dict(model="pauli_sum", L=6, init="x+", chi=16, thr=1e-9, order=2, dt=0.1, steps=5, sample_timesteps=True, ntraj=4,
+                                       seed=58, obs="x+z", noise=[("lowering", 0.2), ("pauli_z", 0.1)],
+                                       terms=[(-1.0 / (j - i) ** 2, f"Z{i} Z{j}") for i in range(6) for j in range(i + 1, 6)]
+                                       + [(-0.7, f"X{i}") for i in range(6)] + [(0.3, "Y0 X2 Z5"), (0.25, "")]),
+    "paulisum5_xy_order1": dict(model="pauli_sum", L=5, init="Neel", chi=8, thr=1e-9, order=1, dt=0.1, steps=6, sample_timesteps=True, ntraj=4,
+                                seed=59, obs="z+zz", noise=[("lowering", 0.3)],
+                                terms=[(0.5, f"X{i} X{i + 1}") for i in range(4)] + [(0.5, f"Y{i},Y{i + 1}") for i in range(4)]
+                                + [(0.2, f"X{i} Z{i + 1} X{i + 2}") for i in range(3)] + [(-0.4, f"z{i}") for i in range(5)]),
 }
 ALL_CASES = {**CASES, **LARGE_CASES, **STRESS_CASES, **DYNAMIC_CASES, **LONG_CASES, **EDGE_CASES}
 
@@ -200,6 +210,8 @@ def oracle_inputs(cfg: dict):
     L = cfg["L"]
     if cfg["model"] == "ising":
         mpo = O.ising_mpo(L, cfg["J"], cfg["g"])
+    elif cfg["model"] == "pauli_sum":
+        mpo = O.pauli_sum_mpo(L, cfg["terms"])
     else:
         mpo = O.heisenberg_mpo(L, cfg["J"], cfg["J"], cfg["J"])
     obs = []

@@ -61,6 +61,9 @@ def run_case(name: str, cfg: dict) -> dict:
     L = cfg["L"]
     if cfg["model"] == "ising":
         H = MPO.ising(L, cfg["J"], cfg["g"])
+    elif cfg["model"] == "pauli_sum":
+        H = MPO()
+        H.from_pauli_sum(terms=[(c, spec) for c, spec in cfg["terms"]], length=L)
     else:
         H = MPO.heisenberg(L, cfg["J"], cfg["J"], cfg["J"])
     obs = []

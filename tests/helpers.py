@@ -12,6 +12,11 @@ from yaqs_b200.rng import numpy_tables
 def engine_for_case(name, kernels, trajectories=None, **kw):
     cfg = ALL_CASES[name]
     init, mpo, noise, p, obs = oracle_inputs(cfg)
+    if cfg["model"] == "pauli_sum":                  # the PRODUCT's Pauli-sum MPO (exact finite-state construction), not the oracle's direct sum
+        from yaqs_b200.containers import MPO
+        built = MPO()
+        built.from_pauli_sum(terms=cfg["terms"], length=cfg["L"])
+        mpo = built.tensors
     traj = list(range(cfg["ntraj"])) if trajectories is None else list(trajectories)
     ep = EngineParams(dt=p.dt, n_steps=p.n_steps, order=p.order, max_bond_dim=p.max_bond_dim, svd_threshold=p.svd_threshold,
                       trunc_mode=p.trunc_mode, krylov_tol=p.krylov_tol, tdvp_mode=p.tdvp_mode, tdvp_sweeps=p.tdvp_sweeps,

@@ -10,6 +10,7 @@ They run once per ``Simulator.run`` on the host (numpy); the device only consume
 """
 from __future__ import annotations
 
+import re
 from dataclasses import dataclass, field
 
 import numpy as np
@@ -336,6 +337,120 @@ class MPO:
             tensors.append(np.ascontiguousarray(t.transpose(2, 3, 0, 1)))
         return cls.custom(tensors)
 
+    _TOKEN = re.compile(r"([IXYZixyz])\s*(\d+)")
+
+    @classmethod
+    def _parse_pauli_string(cls, spec: str) -> dict[int, str]:
+        """"X0 Y2 Z5" (blank- or comma-separated) -> {site: label}; "" is the identity (mpo.py:2093-2133)."""
+        text = spec.replace(",", " ").strip()
+        if not text:
+            return {}
+        out: dict[int, str] = {}
+        for op, idx in cls._TOKEN.findall(text):
+            site = int(idx)
+            if site in out:
+                raise ValueError(f"Duplicate site {site} in spec '{spec}'.")
+            out[site] = op.upper()
+        if cls._TOKEN.sub("", text).split():
+            raise ValueError(f"Invalid token(s) in spec '{spec}'. Use forms like 'X0 Y2 Z5'.")
+        return out
+
+    def from_pauli_sum(self, *, terms, length: int, physical_dimension: int = 2, tol: float = 1e-12, max_bond_dim: int | None = None,
+                       n_sweeps: int = 2) -> None:
+        """H = sum_t c_t P_t for Pauli strings of any range (mpo.py:1171-1317), filled into this MPO.
+
+        Exact finite-state construction, no compression: one "idle" state (identities until a term starts), one "done" state
+        (identities after it ended), and between the first and the last non-identity site of a term one state per distinct REMAINING
+        suffix -- terms that still have the same operators to apply share a channel, whatever came before (the coefficient and the
+        first operator sit on the transition out of "idle").  Bond dimension at a cut = 2 + number of distinct suffixes crossing it:
+        3 for the Ising chain, L - b + 1 for all-to-all Z_i Z_j.  The reference builds a suffix automaton over whole strings and
+        compresses it with SVD sweeps (``tol``, ``max_bond_dim``, ``n_sweeps`` are accepted for its call signature; the exact
+        automaton needs none of them): same operator, different MPO gauge -- H_eff does not see the gauge."""
+        if physical_dimension != 2:
+            raise ValueError("Only physical_dimension=2 is supported by this Pauli MPO builder.")
+        if length <= 0:
+            raise ValueError("length must be positive.")
+        del tol, max_bond_dim, n_sweeps
+        self.length, self.physical_dimension = int(length), 2
+        parsed = []
+        for coeff, spec in terms:
+            ops = self._parse_pauli_string(spec)
+            for site in ops:
+                if not 0 <= site < length:
+                    raise ValueError(f"Site index {site} outside [0, {length - 1}].")
+            support = tuple(sorted((site, lab) for site, lab in ops.items() if lab != "I"))
+            parsed.append((complex(coeff), support))
+        # states per internal bond b (between sites b - 1 and b): 0 = done, 1 = idle, 2... = remaining suffixes crossing the bond
+        suffix_ids: list[dict] = [dict() for _ in range(length + 1)]
+        for _, support in parsed:
+            for k in range(1, len(support)):
+                rest = support[k:]
+                for b in range(support[k - 1][0] + 1, support[k][0] + 1):
+                    suffix_ids[b].setdefault(rest, 2 + len(suffix_ids[b]))
+        dims = [1] + [2 + len(suffix_ids[b]) for b in range(1, length)] + [1]
+        DONE, IDLE = 0, 1
+
+        def left_index(b: int, state) -> int:               # index of a state on bond b (the chain ends have one state each)
+            if b == 0 or b == length:
+                return 0
+            return state if isinstance(state, int) else suffix_ids[b][state]
+
+        tensors = [np.zeros((2, 2, dims[i], dims[i + 1]), dtype=C) for i in range(length)]
+        eye = _PAULI["I"]
+        for i in range(length):
+            w = tensors[i]
+            if i > 0 and i < length - 1:
+                w[:, :, DONE, DONE] += eye
+                w[:, :, IDLE, IDLE] += eye
+            elif length > 1 and i == 0:
+                w[:, :, 0, IDLE] += eye                      # nothing has started yet
+            elif length > 1:
+                w[:, :, DONE, 0] += eye                      # everything has ended
+            for rest, idx in suffix_ids[i].items():          # channels entering site i from the left
+                site, lab = rest[0]
+                if site > i:
+                    w[:, :, idx, left_index(i + 1, rest)] += eye
+                else:
+                    nxt = rest[1:]
+                    w[:, :, idx, left_index(i + 1, nxt if nxt else DONE)] += _PAULI[lab]
+        for coeff, support in parsed:                        # transitions out of "idle": coefficient times the first operator
+            if not support:
+                site, mat, nxt = 0, coeff * eye, ()
+            else:
+                site, mat, nxt = support[0][0], coeff * _PAULI[support[0][1]], support[1:]
+            if not support and length > 1:
+                tensors[0][:, :, 0, DONE] += mat             # a constant: "done" right away, identities from there on
+                continue
+            tensors[site][:, :, left_index(site, IDLE), left_index(site + 1, nxt if nxt else DONE)] += mat
+        self.tensors = tensors
+
+    @classmethod
+    def from_matrix(cls, mat, d: int = 2, max_bond: int | None = None, cutoff: float = 1e-12) -> "MPO":
+        """Factorise a dense operator on n qubits into an MPO by successive SVDs, site 0 first (mpo.py:1852-1974): singular values
+        <= ``cutoff`` are dropped, at most ``max_bond`` kept."""
+        if d != 2:
+            raise NotImplementedError("the B200 TJM path supports qubits (d = 2) only")
+        m = np.asarray(mat, dtype=C)
+        if m.ndim != 2 or m.shape[0] != m.shape[1]:
+            raise ValueError("mat must be a square 2-D array.")
+        n = int(round(np.log2(m.shape[0])))
+        if 2 ** n != m.shape[0] or n < 1:
+            raise ValueError(f"matrix dimension {m.shape[0]} is not a power of d = 2.")
+        # (out_0 .. out_{n-1}, in_0 .. in_{n-1}) -> (out_0, in_0, out_1, in_1, ...): one (out, in) pair per site
+        t = m.reshape((2,) * (2 * n)).transpose([v for k in range(n) for v in (k, n + k)])
+        tensors, left = [], 1
+        rest = t.reshape(left * 4, -1)
+        for _site in range(n - 1):
+            u, sv, vh = np.linalg.svd(rest, full_matrices=False)
+            keep = max(1, int(np.sum(sv > cutoff)))
+            if max_bond is not None:
+                keep = min(keep, int(max_bond))
+            tensors.append(np.ascontiguousarray(u[:, :keep].reshape(left, 2, 2, keep).transpose(1, 2, 0, 3)))
+            rest = (sv[:keep, None] * vh[:keep]).reshape(keep * 4, -1)
+            left = keep
+        tensors.append(np.ascontiguousarray(rest.reshape(left, 2, 2, 1).transpose(1, 2, 0, 3)))
+        return cls.custom(tensors)
+
     @classmethod
     def ising(cls, length: int, J: float, g: float, *, bc: str = "open", **kw) -> "MPO":   # noqa: N803
         """-J sum Z Z - g sum X   (mpo.py:327-364)."""
@@ -390,10 +505,38 @@ class Hamiltonian:
     """Analog operator wrapper (hamiltonian.py:36-441): factories delegate to :class:`MPO`; ``piecewise`` switches static
     pieces on the analog ``dt`` grid (:176-263)."""
 
-    def __init__(self, mpo: MPO) -> None:
-        self._mpo = mpo
+    def __init__(self, length=None, *, tensors=None, matrix=None, sparse_matrix=None, physical_dimension: int = 2) -> None:
+        """The reference's manual constructor (hamiltonian.py:49-167): exactly one of ``tensors`` (MPO cores in the reference's
+        (left, right, out, in) index order, ``MPO.custom`` :1146-1168), ``matrix`` (dense, factorised by ``MPO.from_matrix``) or
+        ``sparse_matrix`` (densified, then the same).  The factories pass a ready MPO as the first argument."""
         self._pieces: tuple | None = None
-        self.length = mpo.length
+        if isinstance(length, MPO):
+            if tensors is not None or matrix is not None or sparse_matrix is not None:
+                raise ValueError("Pass exactly one of tensors, matrix, or sparse_matrix, or use a classmethod preset.")
+            self._mpo, self.length = length, length.length
+            return
+        if physical_dimension != 2:
+            if physical_dimension <= 0:
+                raise ValueError("physical_dimension must be a positive integer.")
+            raise NotImplementedError("the B200 TJM path supports qubits (d = 2) only")
+        if sum(x is not None for x in (tensors, matrix, sparse_matrix)) != 1:
+            raise ValueError("Pass exactly one of tensors, matrix, or sparse_matrix, or use a classmethod preset.")
+        if tensors is not None:
+            if len(tensors) == 0:
+                raise ValueError("tensors must be a non-empty list of MPO cores.")
+            if length is not None and length != len(tensors):
+                raise ValueError(f"length={length} does not match len(tensors)={len(tensors)}.")
+            self._mpo = MPO.custom([np.transpose(np.asarray(t, dtype=C), (2, 3, 0, 1)) for t in tensors])
+        else:
+            dense = matrix if matrix is not None else (sparse_matrix.toarray() if hasattr(sparse_matrix, "toarray") else np.asarray(sparse_matrix))
+            dense = np.asarray(dense, dtype=C)
+            label = "matrix" if matrix is not None else "sparse_matrix"
+            if dense.ndim != 2 or dense.shape[0] != dense.shape[1]:
+                raise ValueError("matrix must be a square 2-D array." if matrix is not None else "sparse_matrix must be square.")
+            if length is not None and dense.shape[0] != 2 ** length:
+                raise ValueError(f"{label} dimension {dense.shape[0]} does not match physical_dimension**length={2 ** length}.")
+            self._mpo = MPO.from_matrix(dense, 2)
+        self.length = self._mpo.length
 
     @classmethod
     def from_mpo(cls, mpo: MPO) -> "Hamiltonian":
