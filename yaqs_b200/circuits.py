@@ -186,3 +186,90 @@ def create_ising_circuit(L: int, J: float, g: float, dt: float, timesteps: int, 
         if sample_every_step and step < timesteps - 1:
             circ.barrier(label=SAMPLE_LABEL)
     return circ
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# The other Trotter-circuit builders of the reference's library (core/libraries/circuit_library.py:82-349), qiskit-free.
+# Each is written as (bond list per interaction layer) x (one emitting loop); tests/test_circuit_library.py holds the gate lists the
+# unmodified reference's builders emit and compares them gate by gate, barriers included.
+# ----------------------------------------------------------------------------------------------------------------------
+def _chain_bonds(length: int) -> list[tuple[int, int]]:
+    """Even pairs (0,1), (2,3), ..., then odd pairs (1,2), (3,4), ..., then the tail pair an odd chain leaves over."""
+    bonds = [(2 * k, 2 * k + 1) for k in range(length // 2)] + [(2 * k - 1, 2 * k) for k in range(1, length // 2)]
+    if length % 2 != 0 and length != 1:
+        bonds.append((length - 2, length - 1))
+    return bonds
+
+
+def _snake(num_rows: int, num_cols: int):
+    """Row-major snake through the grid (even rows left to right, odd rows right to left): neighbours in a row stay neighbours
+    on the chain, vertical neighbours are at most 2 * num_cols - 1 apart."""
+    return lambda row, col: row * num_cols + (col if row % 2 == 0 else num_cols - 1 - col)
+
+
+def _grid_bond_groups(num_rows: int, num_cols: int):
+    """Bond lines of the 2-D Heisenberg builder, group by group: (horizontal: even bonds of every row, then odd bonds of every row;
+    vertical: even bonds of every column, then odd bonds of every column).  (The 2-D Ising builder walks line by line instead.)"""
+    at = _snake(num_rows, num_cols)
+    horizontal = [[(at(r, c), at(r, c + 1)) for c in range(start, num_cols - 1, 2)] for start in (0, 1) for r in range(num_rows)]
+    vertical = [[(at(r, c), at(r + 1, c)) for r in range(start, num_rows - 1, 2)] for start in (0, 1) for c in range(num_cols)]
+    return horizontal, vertical
+
+
+def create_heisenberg_circuit(L: int, Jx: float, Jy: float, Jz: float, h: float, dt: float, timesteps: int, *,   # noqa: N803
+                              periodic: bool = False) -> Circuit:
+    """circuit_library.py:153-226: per Trotter step rz(-2 dt h) on every site, then the ZZ, XX and YY layers over even pairs, odd
+    pairs, the odd-chain tail pair and (periodic) the pair (0, L-1).  The reference places three barriers, kept where it has them:
+    behind the periodic ZZ gate, and behind the XX tail pair of an odd chain."""
+    circ = Circuit(L)
+    wrap = periodic and L > 1
+    odd_tail = L % 2 != 0 and L != 1
+    for _ in range(timesteps):
+        for site in range(L):
+            circ.rz(-2 * dt * h, site)
+        for name, coupling in (("rzz", Jz), ("rxx", Jx), ("ryy", Jy)):
+            for a, b in _chain_bonds(L):
+                getattr(circ, name)(-2 * dt * coupling, a, b)
+            if name == "rxx" and odd_tail:
+                circ.barrier()
+            if wrap:
+                getattr(circ, name)(-2 * dt * coupling, 0, L - 1)
+                if name == "rzz":
+                    circ.barrier()
+    return circ
+
+
+def create_2d_ising_circuit(num_rows: int, num_cols: int, J: float, g: float, dt: float, timesteps: int) -> Circuit:   # noqa: N803
+    """circuit_library.py:82-150: the grid mapped onto the chain along a snake; per Trotter step rx(-2 dt g) on every qubit, then
+    rzz(-2 dt J) row by row (even bonds of the row, then its odd bonds) and column by column, a full barrier behind every rzz."""
+    circ = Circuit(num_rows * num_cols)
+    at = _snake(num_rows, num_cols)
+    for _ in range(timesteps):
+        for row in range(num_rows):
+            for col in range(num_cols):
+                circ.rx(-2 * dt * g, at(row, col))
+        lines = [[(at(r, c), at(r, c + 1)) for start in (0, 1) for c in range(start, num_cols - 1, 2)] for r in range(num_rows)]
+        lines += [[(at(r, c), at(r + 1, c)) for start in (0, 1) for r in range(start, num_rows - 1, 2)] for c in range(num_cols)]
+        for line in lines:
+            for a, b in line:
+                circ.rzz(-2 * dt * J, a, b)
+                circ.barrier()
+    return circ
+
+
+def create_2d_heisenberg_circuit(num_rows: int, num_cols: int, Jx: float, Jy: float, Jz: float, h: float, dt: float,   # noqa: N803
+                                 timesteps: int) -> Circuit:
+    """circuit_library.py:229-349: snake ordering; per Trotter step rz(-2 dt h) everywhere, then for ZZ, XX, YY in turn the four bond
+    groups horizontal-even, horizontal-odd, vertical-even, vertical-odd (no barriers)."""
+    circ = Circuit(num_rows * num_cols)
+    at = _snake(num_rows, num_cols)
+    horizontal, vertical = _grid_bond_groups(num_rows, num_cols)
+    for _ in range(timesteps):
+        for row in range(num_rows):
+            for col in range(num_cols):
+                circ.rz(-2.0 * dt * h, at(row, col))
+        for name, coupling in (("rzz", Jz), ("rxx", Jx), ("ryy", Jy)):
+            for line in horizontal + vertical:
+                for a, b in line:
+                    getattr(circ, name)(-2.0 * dt * coupling, a, b)
+    return circ
