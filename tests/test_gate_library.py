@@ -53,3 +53,16 @@ def test_circuit_builder_takes_every_supported_gate(golden):
     assert len(gates) == len(names)
     for gate, name in zip(gates, names):
         assert np.max(np.abs(gate.matrix - golden[f"matrix_{name}"])) < 1e-15, name
+
+
+def test_position_observable_and_custom_alias():
+    """gate_library.py:1845-1870 / :2042-2048: ``Observable("position", site, positions=...)`` is the diagonal operator of the supplied
+    basis; ``GateLibrary.custom`` is the base class."""
+    from yaqs_b200 import Observable
+    from yaqs_b200.gates import BaseGate
+    obs = Observable("position", 2, positions=[-0.5, 0.5])
+    assert obs.gate.name == "position" and obs.sites == 2 and np.array_equal(obs.gate.matrix, np.diag([-0.5, 0.5]))
+    assert GateLibrary.custom is BaseGate
+    for bad, msg in (([1j, 0.0], "only real"), ([[0.0, 1.0]], "one-dimensional"), ([np.inf, 0.0], "finite")):
+        with pytest.raises(ValueError, match=msg):
+            GateLibrary.position(positions=bad)

@@ -631,6 +631,8 @@ class Result:
     total_bond: np.ndarray | None = None
     noise_model: object = None
     output_state: object = None
+    multi_time_times: np.ndarray | None = None     # (result.py:182-183; filled by the unitary-ensemble path only, which is out of scope here)
+    multi_time_results: np.ndarray | None = None
     measurements: list = field(default_factory=list)
     counts: dict | None = None
     status: np.ndarray | None = None          # per-trajectory device status words (0 = clean)

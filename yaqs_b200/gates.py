@@ -168,6 +168,24 @@ class GateLibrary:
         return BaseGate(m, name="local", interaction=1)
 
     @staticmethod
+    def position(*, positions) -> BaseGate:
+        """One-site operator diagonal in a supplied position basis (gate_library.py:1845-1870), e.g. ``Observable("position", 3,
+        positions=[-0.5, 0.5])``."""
+        values = np.asarray(positions)
+        if np.iscomplexobj(values):
+            raise ValueError("positions must contain only real values.")
+        values = np.asarray(values, dtype=np.float64)
+        if values.ndim != 1 or values.size == 0:
+            raise ValueError("positions must be a non-empty one-dimensional array.")
+        if not np.all(np.isfinite(values)):
+            raise ValueError("positions must contain only finite values.")
+        g = GateLibrary.local(np.diag(values))
+        g.name = "position"
+        return g
+
+    custom = BaseGate
+
+    @staticmethod
     def rx(theta: float) -> BaseGate:
         g = BaseGate(_rot(_X)(theta), name="rx")
         g.theta = theta
