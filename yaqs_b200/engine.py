@@ -51,6 +51,12 @@ class EngineParams:
     sample_timesteps: bool = True
     digital: bool = False
 
+    def __post_init__(self) -> None:
+        # The reference stores any int as max_bond_dim (simulation_parameters.py:308-327) and fails inside the first split when it is
+        # not positive; the batch sizes its slots from the cap, so it is refused here, where every run passes through.
+        if self.max_bond_dim is not None and int(self.max_bond_dim) < 1:
+            raise ValueError(f"max_bond_dim must be a positive int or None, got {self.max_bond_dim!r}.")
+
     @property
     def n_times(self) -> int:
         return self.n_steps + 1

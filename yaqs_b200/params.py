@@ -139,18 +139,28 @@ def _time_grid(elapsed_time, dt) -> int:
     return n
 
 
-def _common(self, preset, num_traj, max_bond_dim, trunc_mode, svd_threshold, krylov_tol, tdvp_sweeps, tdvp_mode, random_seed):
-    _validate_seed(random_seed)
+def _preset_values(preset) -> dict:
     if preset not in SIMULATION_PRESETS:
-        raise ValueError(f"preset must be one of {tuple(SIMULATION_PRESETS)!r}, got {preset!r}.")
-    pv = SIMULATION_PRESETS[preset]
-    self.preset = preset
+        raise ValueError(f"preset must be one of {sorted(SIMULATION_PRESETS)!r}, got {preset!r}.")
+    return SIMULATION_PRESETS[preset]
+
+
+def _resolve_max_bond_dim(max_bond_dim, preset_value):
+    """:308-327: an int, None, or left to the preset.  (Like the reference this stores any int; a cap below one is refused when a
+    run builds its EngineParams, where the reference would fail inside the first split.)"""
+    if max_bond_dim is _USE_PRESET:
+        return preset_value
+    if max_bond_dim is None or isinstance(max_bond_dim, int):
+        return max_bond_dim
+    raise TypeError(f"max_bond_dim must be int, None, or omitted, got {type(max_bond_dim).__name__}.")
+
+
+def _numerics(self, pv: dict, num_traj, max_bond_dim, trunc_mode, svd_threshold, krylov_tol) -> None:
+    """The block both constructors share, checked in the reference's order (:597-604, :744-750)."""
     self.num_traj = num_traj if num_traj is not None else pv["num_traj"]
-    self.max_bond_dim = pv["max_bond_dim"] if max_bond_dim is _USE_PRESET else max_bond_dim
-    if self.max_bond_dim is not None and (isinstance(self.max_bond_dim, bool) or int(self.max_bond_dim) < 1):
-        raise ValueError(f"max_bond_dim must be a positive int or None, got {self.max_bond_dim!r}.")
-    if trunc_mode not in _TRUNC_MODES:
-        raise ValueError(f"trunc_mode must be one of {_TRUNC_MODES!r}, got {trunc_mode!r}.")
+    self.max_bond_dim = _resolve_max_bond_dim(max_bond_dim, pv["max_bond_dim"])
+    if not isinstance(trunc_mode, str) or trunc_mode not in _TRUNC_MODES:
+        raise ValueError(f"trunc_mode must be one of {sorted(_TRUNC_MODES)!r}, got {trunc_mode!r}.")
     self.trunc_mode = trunc_mode
     thr = float(svd_threshold if svd_threshold is not None else pv["svd_threshold"])
     if not np.isfinite(thr) or thr < 0.0:
@@ -160,6 +170,9 @@ def _common(self, preset, num_traj, max_bond_dim, trunc_mode, svd_threshold, kry
     if not np.isfinite(kt) or kt <= 0.0:
         raise ValueError(f"krylov_tol must be a finite positive float, got {kt!r}.")
     self.krylov_tol = kt
+
+
+def _tdvp_settings(self, tdvp_sweeps, tdvp_mode) -> None:
     if isinstance(tdvp_sweeps, bool) or not isinstance(tdvp_sweeps, int):
         raise TypeError(f"tdvp_sweeps must be int, got {type(tdvp_sweeps).__name__}.")
     if tdvp_sweeps < 1:
@@ -168,18 +181,20 @@ def _common(self, preset, num_traj, max_bond_dim, trunc_mode, svd_threshold, kry
     if tdvp_mode not in ("1site", "2site", "dynamic"):
         raise ValueError(f"tdvp_mode must be one of ('1site', '2site', 'dynamic'), got {tdvp_mode!r}.")
     self.tdvp_mode = tdvp_mode
-    self.random_seed = random_seed
 
 
 class AnalogSimParams(_Ordering):
-    """Hamiltonian-evolution parameters (:477-613).  Defaults: order=1, tdvp_mode="2site", preset "balanced"."""
+    """Hamiltonian-evolution parameters (:477-613).  Defaults: order=1, tdvp_mode="2site", preset "balanced".  Arguments are checked in
+    the reference's order, with its exception types and messages (:579-613)."""
 
     def __init__(self, observables=None, elapsed_time: float = 0.1, dt: float = 0.1, num_traj: int | None = None,
                  max_bond_dim=_USE_PRESET, trunc_mode: str = "discarded_weight", svd_threshold: float | None = None,
                  krylov_tol: float | None = None, order: int = 1, *, preset: str = "balanced", sample_timesteps: bool = True,
                  evolution_mode: str = "tdvp", get_state: bool = False, random_seed: int | None = None,
                  multi_time_observables=None, tdvp_sweeps: int = 1, tdvp_mode: str = "2site") -> None:
-        _common(self, preset, num_traj, max_bond_dim, trunc_mode, svd_threshold, krylov_tol, tdvp_sweeps, tdvp_mode, random_seed)
+        _validate_seed(random_seed)
+        pv = _preset_values(preset)
+        self.preset = preset
         self.observables = [] if observables is None else list(observables)
         _check_observable_mix(self.observables)
         n_steps = _time_grid(elapsed_time, dt)
@@ -188,32 +203,44 @@ class AnalogSimParams(_Ordering):
         if n_steps > 0:
             self.times[-1] = self.elapsed_time
         self.sample_timesteps = sample_timesteps
+        _numerics(self, pv, num_traj, max_bond_dim, trunc_mode, svd_threshold, krylov_tol)
         self.order = order
         mode = getattr(evolution_mode, "value", evolution_mode)
-        if str(mode).lower() != "tdvp":
+        if mode not in ("tdvp", "bug"):
+            raise ValueError(f"evolution_mode must be one of ('tdvp', 'bug'), got {evolution_mode!r}.")
+        if mode != "tdvp":
             raise NotImplementedError("evolution_mode=BUG is outside the B200 hot-path scope (SURVEY.md 2.1 #20)")
         self.evolution_mode = "tdvp"
         self.get_state = get_state
+        self.random_seed = random_seed
         self.multi_time_observables = [] if multi_time_observables is None else list(multi_time_observables)
+        _tdvp_settings(self, tdvp_sweeps, tdvp_mode)
 
 
 class DigitalSimParams(_Ordering):
-    """Circuit-simulation parameters, keyword-only as in the reference (:616-750)."""
+    """Circuit-simulation parameters, keyword-only as in the reference (:616-750), checked in its order (:717-756)."""
 
-    def __init__(self, *, observables=None, num_traj: int | None = None, max_bond_dim=_USE_PRESET, trunc_mode: str = "discarded_weight",
-                 svd_threshold: float | None = None, krylov_tol: float | None = None, preset: str = "balanced", get_state: bool = False,
-                 sample_layers: bool = False, shots: int | None = None, random_seed: int | None = None, gate_mode: str = "mpo",
-                 tdvp_sweeps: int = 1, tdvp_mode: str = "2site", num_mid_measurements: int = 0) -> None:
-        _common(self, preset, num_traj, max_bond_dim, trunc_mode, svd_threshold, krylov_tol, tdvp_sweeps, tdvp_mode, random_seed)
+    def __init__(self, *, observables=None, shots: int | None = None, num_traj: int | None = None, max_bond_dim=_USE_PRESET,
+                 trunc_mode: str = "discarded_weight", svd_threshold: float | None = None, krylov_tol: float | None = None,
+                 preset: str = "balanced", get_state: bool = False, sample_layers: bool = False, num_mid_measurements: int = 0,
+                 random_seed: int | None = None, gate_mode: str = "mpo", tdvp_sweeps: int = 1, tdvp_mode: str = "2site") -> None:
+        _validate_seed(random_seed)
+        pv = _preset_values(preset)
+        self.preset = preset
         self.observables = [] if observables is None else list(observables)
         _check_observable_mix(self.observables)
+        if shots is not None and (isinstance(shots, bool) or not isinstance(shots, int) or shots < 1):
+            raise ValueError(f"shots must be a positive int or None, got {shots!r}.")
+        self.shots = shots
+        _numerics(self, pv, num_traj, max_bond_dim, trunc_mode, svd_threshold, krylov_tol)
+        self.get_state = get_state
+        self.sample_layers = sample_layers
+        self.num_mid_measurements = num_mid_measurements      # (:682,746) the run takes the count from the compiled circuit, as simulator.py:1723-1741 does
+        self.random_seed = random_seed
         if gate_mode not in ("tdvp", "full-tdvp", "swaps", "mpo"):
             raise ValueError(f"gate_mode must be one of ('tdvp', 'full-tdvp', 'swaps', 'mpo'), got {gate_mode!r}.")
         self.gate_mode = gate_mode
-        self.get_state = get_state
-        self.sample_layers = sample_layers
-        self.shots = shots
-        self.num_mid_measurements = num_mid_measurements      # (:682,746) the run takes the count from the compiled circuit, as simulator.py:1723-1741 does
+        _tdvp_settings(self, tdvp_sweeps, tdvp_mode)
 
 
 StrongSimParams = DigitalSimParams   # pre-0.6 names used by BASELINE.json's north_star (UPGRADING.md:49-60)
