@@ -55,13 +55,22 @@ class MPS:
             return
         self.tensors = []
         if state == "haar-random":
+            # mps.py:128-221: a chain of Haar-random isometries, bonds min(pad, 2^k) from either end.  Site by site, left to right, from
+            # ONE generator: a complex Ginibre block ((d chi_l) x chi_r: real part drawn first, then the imaginary part), its reduced QR,
+            # the column phases of Q fixed so that R has a positive diagonal.  The chain is left-canonical, hence normalised; the engine
+            # wants the centre at site 0, so it is re-gauged without rescaling -- the represented vector is the reference's, entry by entry.
             chi = 1 if pad is None else pad
             rng = np.random.default_rng()
             bonds = [1] + [min(chi, 2 ** min(i + 1, length - 1 - i)) for i in range(length - 1)] + [1]
-            self.tensors = [(rng.standard_normal((2, bonds[i], bonds[i + 1])) + 1j * rng.standard_normal((2, bonds[i], bonds[i + 1]))).astype(C)
-                            for i in range(length)]
+            for i in range(length):
+                rows, cols = 2 * bonds[i], bonds[i + 1]
+                ginibre = rng.standard_normal((rows, cols)) + 1j * rng.standard_normal((rows, cols))
+                q, r = np.linalg.qr(ginibre, mode="reduced")
+                diag = np.diag(r)
+                phase = np.where(np.abs(diag) > 0, diag / np.where(np.abs(diag) > 0, np.abs(diag), 1.0), 1.0)
+                self.tensors.append((q / phase[None, :]).reshape(2, bonds[i], cols).astype(C))
             self.orthogonality_center = None
-            self.normalize()
+            self._canonicalize(rescale=False)
             return
         if state == "basis":
             if basis_string is None or len(basis_string) != length:
