@@ -423,3 +423,28 @@ def test_lanes_first_mode_runs_first_item_then_calls_between():
     out = lanes.map(lambda x: (order.append(x), x * 2)[1], [1, 2, 3], serial="first", between=lambda: order.append("between"))
     assert out == [2, 4, 6]
     assert order[0] == 1 and "between" in order and order.index("between") >= 1
+
+
+def test_run_rejects_what_the_reference_rejects_with_its_messages():
+    """Messages recorded from the unmodified reference's Simulator.run / validate_noise_model_for_run (simulator.py:817,1283-1308,
+    noise_model.py:695-780) on the same calls."""
+    import yaqs_b200 as Y
+    sim = Y.Simulator(show_progress=False, kernels=NumpyKernels())
+    obs = [Y.Observable("z", 0)]
+    ap = Y.AnalogSimParams(observables=obs, elapsed_time=0.1, dt=0.1, num_traj=2)
+    with pytest.raises(ValueError, match=r"State.length=4 does not match Hamiltonian.length=3\."):
+        sim.run(Y.State(4), Y.Hamiltonian.ising(3, 1, 0.5), ap)
+    with pytest.raises(ValueError, match=r"Process site index 7 is out of range for length 3\."):
+        sim.run(Y.State(3), Y.Hamiltonian.ising(3, 1, 0.5), ap, Y.NoiseModel([{"name": "lowering", "sites": [7], "strength": 0.1}]))
+    with pytest.raises(TypeError, match="Circuit simulation requires a QuantumCircuit operator."):
+        sim.run(Y.State(3), Y.Hamiltonian.ising(3, 1, 0.5), Y.DigitalSimParams(observables=obs))
+    with pytest.raises(ValueError, match="No output specified: set observables, shots, and/or get_state."):
+        sim.run(Y.State(3), Y.create_ising_circuit(3, 1, 0.5, 0.1, 1), Y.DigitalSimParams())
+    with pytest.raises(AssertionError, match="Observable acting on non-existing site: 5"):
+        sim.run(Y.State(3), Y.Hamiltonian.ising(3, 1, 0.5), Y.AnalogSimParams(observables=[Y.Observable("z", 5)], elapsed_time=0.1, dt=0.1))
+    long_range = Y.NoiseModel([{"name": "crosstalk_xx", "sites": [0, 2], "strength": 0.1}])
+    with pytest.raises(ValueError, match=r"Digital TJM does not support non-adjacent / factorized two-site noise \(process 'crosstalk_xx' on sites \[0, 2\]\)"):
+        sim.run(Y.State(3), Y.create_ising_circuit(3, 1, 0.5, 0.1, 1), Y.DigitalSimParams(observables=obs, num_traj=2), long_range)
+    sched = Y.NoiseModel([{"name": "lowering", "sites": [0], "strength": 0.1}], scheduled_jumps=[{"time": 0.05, "sites": [1], "name": "pauli_x"}])
+    with pytest.raises(ValueError, match=r"Scheduled jump time 0.05 is not on the simulation time grid"):
+        sim.run(Y.State(3), Y.Hamiltonian.ising(3, 1, 0.5), ap, sched)

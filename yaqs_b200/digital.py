@@ -17,16 +17,9 @@ from .rng import STREAM_SHOTS, numpy_tables, philox_source
 
 
 def validate_digital_noise(noise, length: int) -> None:
-    """noise_model.py:668-757, digital branch: two-site processes must act on adjacent, ascending sites (:724-730)."""
-    if getattr(noise, "scheduled_jumps", None):
-        raise ValueError("scheduled_jumps are only supported for single-State analog MPS TJM; they are not supported for MCWF, "
-                         "Lindblad, digital, or list[State] ensemble runs.")
-    for pr in noise.processes:
-        for s in pr["sites"]:
-            if s >= length:
-                raise ValueError(f"Noise process '{pr['name']}' acts on site {s} but the chain has {length} sites.")
-        if len(pr["sites"]) == 2 and pr["sites"][1] - pr["sites"][0] != 1:
-            raise ValueError("Digital simulation supports two-site noise on adjacent sites only.")
+    """noise_model.py:668-757, digital branch (processes, then the scheduled-jump refusal), the reference's messages."""
+    from .simulator import validate_noise_model_for_run
+    validate_noise_model_for_run(noise, length, None, is_digital=True)
 
 
 def run_digital(simulator, initial_state, operator, sp, noise, result):

@@ -89,7 +89,10 @@ def engine_observables(sorted_observables, length: int):
         else:
             if o.gate.interaction not in (1, 2):
                 raise ValueError("Local observable must be one-site or nearest-neighbor two-site.")
-            out.append((np.asarray(o.gate.matrix, dtype=np.complex128), ([o.sites] if isinstance(o.sites, int) else list(o.sites))))
+            where = [o.sites] if isinstance(o.sites, (int, np.integer)) else list(o.sites)
+            for s in where:                               # (the reference trips over such a site inside its centre shifts, also with an AssertionError)
+                assert 0 <= s < length, f"Observable acting on non-existing site: {s}"
+            out.append((np.asarray(o.gate.matrix, dtype=np.complex128), where))
     return out
 
 

@@ -69,34 +69,51 @@ def shard_range(n: int, rank: int, world: int) -> range:
     return range(min(n, rank * per), min(n, (rank + 1) * per))
 
 
-def validate_noise_model_for_run(noise: NoiseModel, length: int, sim_params=None) -> None:
-    """core/data_structures/noise_model.py:668-780 (the MPS-analog checks, scheduled jumps included)."""
-    if noise.scheduled_jumps:
-        if not isinstance(sim_params, AnalogSimParams):
-            raise ValueError("scheduled_jumps are only supported for single-State analog MPS TJM; they are not supported for MCWF, "
-                             "Lindblad, digital, or list[State] ensemble runs.")
-        if sim_params.order != 1:
-            raise ValueError(f"scheduled_jumps are only supported for AnalogSimParams(order=1); got order={sim_params.order}. Order-2 TJM "
-                             "applies deterministic jumps inconsistently on the sampling versus trajectory MPS.")
-        times = np.asarray(sim_params.times, dtype=float)
-        atol = sim_params.dt * 1e-3
-        for jump in noise.scheduled_jumps:
-            want = 2 ** len(jump["sites"])
-            if np.asarray(jump["matrix"]).shape != (want, want):
-                raise ValueError(f"Scheduled jump '{jump['name']}': matrix must be {want}x{want} for qubit chains.")
-            for s_ in jump["sites"]:
-                if s_ >= length:
-                    raise ValueError(f"Scheduled jump '{jump['name']}' acts on site {s_} but the chain has {length} sites.")
-            if not np.any(np.isclose(times, float(jump["time"]), atol=atol, rtol=0.0)):
-                raise ValueError(f"Scheduled jump time {float(jump['time'])} is not on the simulation time grid (atol={atol}, rtol=0).")
+def _check_operator_dims(entry: dict, kind: str, length: int) -> None:
+    """noise_model.py:695-722: sites inside the chain, matrix / factor shapes for qubits; the reference's messages."""
+    sites = entry["sites"]
+    for site in sites:
+        if site >= length:
+            raise ValueError(f"{kind} site index {site} is out of range for length {length}.")
+    if "matrix" in entry:
+        shape = np.asarray(entry["matrix"]).shape
+        expected = 2 if len(sites) == 1 else 4
+        if shape != (expected, expected):
+            raise ValueError(f"{kind} matrix shape {shape} does not match expected ({expected}, {expected}) for sites {sites}.")
+    if "factors" in entry:
+        for site, factor in zip(sites, entry["factors"], strict=True):
+            shape = np.asarray(factor).shape
+            if shape != (2, 2):
+                raise ValueError(f"{kind} factor on site {site} has shape {shape}, expected (2, 2).")
+
+
+def validate_noise_model_for_run(noise: NoiseModel, length: int, sim_params=None, is_digital: bool = False) -> None:
+    """core/data_structures/noise_model.py:668-780, in the reference's order and with its messages: processes first (sites, operator
+    shapes, what the digital / analog MPS paths cannot take), then the scheduled jumps."""
+    from .noise import is_pauli
     for pr in noise.processes:
-        for s in pr["sites"]:
-            if s >= length:
-                raise ValueError(f"Noise process '{pr['name']}' acts on site {s} but the chain has {length} sites.")
-        if len(pr["sites"]) == 1 and np.asarray(pr["matrix"]).shape != (2, 2):
-            raise ValueError(f"Noise process '{pr['name']}': one-site matrix must be 2x2 for qubit chains.")
-        if len(pr["sites"]) == 2 and "matrix" in pr and np.asarray(pr["matrix"]).shape != (4, 4):
-            raise ValueError(f"Noise process '{pr['name']}': two-site matrix must be 4x4 for qubit chains.")
+        _check_operator_dims(pr, "Process", length)
+        long_range = len(pr["sites"]) == 2 and abs(pr["sites"][1] - pr["sites"][0]) != 1
+        if is_digital and long_range:
+            raise ValueError(f"Digital TJM does not support non-adjacent / factorized two-site noise (process '{pr['name']}' on sites "
+                             f"{pr['sites']}). Gate-local digital noise scoping remains nearest-neighbor only.")
+        if not is_digital and long_range and not is_pauli(pr):
+            raise ValueError(f"Analog MPS TJM does not support non-Pauli long-range noise (process '{pr['name']}' on sites {pr['sites']}).")
+    if not noise.scheduled_jumps:
+        return
+    if is_digital or not isinstance(sim_params, AnalogSimParams):
+        raise ValueError("scheduled_jumps are only supported for single-State analog MPS TJM; they are not supported for MCWF, "
+                         "Lindblad, digital, or list[State] ensemble runs.")
+    if sim_params.order != 1:
+        raise ValueError(f"scheduled_jumps are only supported for AnalogSimParams(order=1); got order={sim_params.order}. Order-2 TJM "
+                         "applies deterministic jumps inconsistently on the sampling versus trajectory MPS.")
+    times = np.asarray(sim_params.times, dtype=float)
+    atol = sim_params.dt * 1e-3
+    for jump in noise.scheduled_jumps:
+        _check_operator_dims(jump, "Scheduled jump", length)
+        jump_time = float(jump["time"])
+        if not np.any(np.isclose(times, jump_time, atol=atol, rtol=0.0)):
+            raise ValueError(f"Scheduled jump time {jump_time} is not on the simulation time grid (atol={atol}, rtol=0).")
 
 
 def bytes_per_trajectory(lay_one: BatchLayout, order: int, one_site: bool) -> int:
@@ -183,6 +200,11 @@ class Simulator:
                 raise TypeError("Analog simulation requires a Hamiltonian operator.")
             self._run_analog(initial_state, operator, sim_params, noise_model, result)
             return result
+        if not sim_params.get_state and not sim_params.observables and sim_params.shots is None:
+            raise ValueError("No output specified: set observables, shots, and/or get_state.")        # simulator.py:1283-1290
+        from .circuits import Circuit
+        if not isinstance(operator, Circuit) and not (hasattr(operator, "num_qubits") and hasattr(operator, "data")):
+            raise TypeError("Circuit simulation requires a QuantumCircuit operator.")                 # :1304-1306 (Circuit or a qiskit circuit)
         from .digital import run_digital                # digital TJM (digital/digital_tjm.py:636-749)
         return run_digital(self, initial_state, operator, sim_params, noise_model, result)
 
@@ -352,7 +374,7 @@ class AnalogRun:
         self.sim, self.sp, self._result = sim, sp, result
         length = state.length
         if ham.length != length:
-            raise ValueError("State and Hamiltonian must have the same number of sites.")
+            raise ValueError(f"State.length={length} does not match Hamiltonian.length={ham.length}.")
         if noise is not None:
             validate_noise_model_for_run(noise, length, sp)
         self.noiseless = noise is None or all(pr["strength"] == 0 for pr in noise.processes)
