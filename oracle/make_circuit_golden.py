@@ -15,12 +15,28 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from oracle.ref_shim import load_reference  # noqa: E402
 
 ANGLE_KEYS = ("theta", "phi", "lam")
-QUBIT_KEYS = ("qubit", "qubit1", "qubit2")
+QUBIT_KEYS = ("qubit", "qubit1", "qubit2", "control_qubit", "target_qubit")
+
+
+class Register:
+    """Stand-in for qiskit's QuantumRegister: qubit j of the k-th register of a circuit is wire offset_k + j."""
+
+    def __init__(self, size: int, name: str = "") -> None:
+        self.size, self.name, self.offset = size, name, 0
+
+    def __getitem__(self, j: int) -> int:
+        return self.offset + j
 
 
 class Recorder:
-    def __init__(self, num_qubits: int) -> None:
-        self.num_qubits = num_qubits
+    def __init__(self, *regs) -> None:
+        if len(regs) == 1 and isinstance(regs[0], int):
+            self.num_qubits = regs[0]
+        else:
+            self.num_qubits = 0
+            for reg in regs:
+                reg.offset = self.num_qubits
+                self.num_qubits += reg.size
         self.ops: list = []
 
     def barrier(self, *qubits, label=None):
@@ -28,7 +44,7 @@ class Recorder:
 
     def __getattr__(self, name):
         def add(*args, **kw):
-            nq = {"rx": 1, "ry": 1, "rz": 1, "rzz": 2, "rxx": 2, "ryy": 2}[name]
+            nq = {"rx": 1, "ry": 1, "rz": 1, "p": 1, "u": 1, "rzz": 2, "rxx": 2, "ryy": 2, "cp": 2, "cx": 2, "cz": 2}[name]
             vals = list(args) + [kw[k] for k in ANGLE_KEYS if k in kw]
             qubits = [kw[k] for k in QUBIT_KEYS if k in kw]
             params = vals[: len(vals) - (nq - len(qubits))]
@@ -47,6 +63,10 @@ CASES = {
     "heisenberg_2": ("create_heisenberg_circuit", dict(L=2, Jx=1.0, Jy=1.0, Jz=1.0, h=0.0, dt=0.1, timesteps=1)),
     "heisenberg2d_3x3": ("create_2d_heisenberg_circuit", dict(num_rows=3, num_cols=3, Jx=1.0, Jy=0.9, Jz=0.7, h=0.2, dt=0.1, timesteps=1)),
     "heisenberg2d_4x2": ("create_2d_heisenberg_circuit", dict(num_rows=4, num_cols=2, Jx=0.3, Jy=0.5, Jz=0.7, h=0.4, dt=0.1, timesteps=2)),
+    "fermi_hubbard_1d_3": ("create_1d_fermi_hubbard_circuit", dict(L=3, u=0.5, t=1.0, mu=0.3, num_trotter_steps=2, dt=0.1, timesteps=1)),
+    "fermi_hubbard_1d_4": ("create_1d_fermi_hubbard_circuit", dict(L=4, u=1.5, t=0.7, mu=-0.2, num_trotter_steps=1, dt=0.05, timesteps=2)),
+    "random_nn_5": ("nearest_neighbour_random_circuit", dict(n_qubits=5, layers=4, seed=42)),
+    "random_nn_6": ("nearest_neighbour_random_circuit", dict(n_qubits=6, layers=3, seed=7)),
 }
 
 
@@ -54,6 +74,7 @@ def main() -> int:
     load_reference()
     import mqt.yaqs.core.libraries.circuit_library as lib
     lib.QuantumCircuit = Recorder
+    lib.QuantumRegister = Register
     out = {}
     for key, (fn, kw) in CASES.items():
         circ = getattr(lib, fn)(**kw)

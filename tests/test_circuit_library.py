@@ -23,7 +23,7 @@ def test_builder_emits_the_reference_gate_list(key):
         if name == "barrier":
             continue                                 # (a full barrier either way; ours lists every wire, the recorder saw none named)
         assert list(op.qubits) == qubits, (k, op, qubits)
-        assert np.allclose(op.params, params, rtol=0, atol=1e-15), (k, op, params)
+        assert np.allclose(op.params, params, rtol=0, atol=1e-13), (k, op, params)      # (the random circuit's angles go through an expm there, a closed form here)
 
 
 def test_snake_keeps_rows_contiguous_and_compiles():

@@ -273,3 +273,72 @@ def create_2d_heisenberg_circuit(num_rows: int, num_cols: int, Jx: float, Jy: fl
                 for a, b in line:
                     getattr(circ, name)(-2.0 * dt * coupling, a, b)
     return circ
+
+
+def create_1d_fermi_hubbard_circuit(L: int, u: float, t: float, mu: float, num_trotter_steps: int, dt: float, timesteps: int) -> Circuit:   # noqa: N803
+    """circuit_library.py:352-415: H = -mu/2 (I - Z) + u/4 (I - Z)(I - Z) - t/2 (XX + YY) on two registers (spin-up = wires 0 .. L-1,
+    spin-down = wires L .. 2L-1).  One second-order Trotter slice is  chemical potential - on-site interaction - hopping - on-site
+    interaction - chemical potential,  repeated ``num_trotter_steps * timesteps`` times: p(mu dt / 2n) on every wire, cp(-u dt / 2n)
+    between the two spins of a site, and rxx / ryy(-t dt / n) on the even bonds, then the odd bonds, of each register (the hop is
+    written from the higher site to the lower one)."""
+    n = num_trotter_steps
+    circ = Circuit(2 * L)
+    up, down = range(L), range(L, 2 * L)
+
+    def chemical_potential():
+        for j in range(L):
+            circ.p(mu * dt / (2 * n), up[j])
+            circ.p(mu * dt / (2 * n), down[j])
+
+    def onsite():
+        for j in range(L):
+            circ.cp(-u * dt / (2 * n), up[j], down[j])
+
+    def hopping():
+        for parity in (0, 1):
+            for j in range(parity, L - 1, 2):
+                for reg in (up, down):
+                    circ.rxx(-dt * t / n, reg[j + 1], reg[j])
+                    circ.ryy(-dt * t / n, reg[j + 1], reg[j])
+
+    for _ in range(n * timesteps):
+        chemical_potential()
+        onsite()
+        hopping()
+        onsite()
+        chemical_potential()
+    return circ
+
+
+def _u3_angles(unitary) -> tuple[float, float, float]:
+    """(theta, phi, lambda) of u(theta, phi, lambda) equal to a 2 x 2 unitary up to a global phase (circuit_library_utils.py:32-64):
+    the phase is fixed by making the (0, 0) entry real and non-negative."""
+    import numpy as np
+    m = np.asarray(unitary, dtype=np.complex128) * np.exp(-1j * np.angle(unitary[0, 0]))
+    theta = 2 * np.arccos(np.clip(np.abs(m[0, 0]), -1.0, 1.0))
+    if np.isclose(float(np.sin(theta / 2)), 0.0):
+        return float(theta), 0.0, float(np.angle(m[1, 1]) - np.angle(m[0, 0]))
+    return float(theta), float(np.angle(m[1, 0])), float(np.angle(-m[0, 1]))
+
+
+def nearest_neighbour_random_circuit(n_qubits: int, layers: int, seed: int = 42) -> Circuit:
+    """circuit_library.py:637-680 (the prescription of arXiv:2002.07730): per layer a random rotation exp(-i theta n.sigma) on every qubit
+    -- theta and the azimuth uniform in [0, 2 pi), the polar angle uniform in [0, pi), drawn in that order from ``default_rng(seed)`` and
+    written as a ``u`` gate -- then cz or cx (a fair coin per pair) on the pairs (1,2), (3,4), ... in even layers and (0,1), (2,3), ... in
+    odd layers, and a barrier."""
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    circ = Circuit(n_qubits)
+    for layer in range(layers):
+        for qubit in range(n_qubits):
+            theta, alpha, phi = rng.uniform(0, 2 * np.pi), rng.uniform(0, np.pi), rng.uniform(0, 2 * np.pi)
+            axis = np.array([np.sin(alpha) * np.cos(phi), np.sin(alpha) * np.sin(phi), np.cos(alpha)])
+            generator = (axis[0] * np.array([[0, 1], [1, 0]]) + axis[1] * np.array([[0, -1j], [1j, 0]]) + axis[2] * np.array([[1, 0], [0, -1]]))
+            circ.u(*_u3_angles(np.cos(theta) * np.eye(2) - 1j * np.sin(theta) * generator), qubit)     # (n.sigma)^2 = 1
+        for a in range(1 if layer % 2 == 0 else 0, n_qubits - 1, 2):
+            if rng.random() < 0.5:
+                circ.cz(a, a + 1)
+            else:
+                circ.cx(a, a + 1)
+        circ.barrier()
+    return circ
