@@ -39,6 +39,10 @@ class Recorder:
                 self.num_qubits += reg.size
         self.ops: list = []
 
+    def compose(self, other, front: bool = False, inplace: bool = True):
+        assert inplace
+        self.ops = (other.ops + self.ops) if front else (self.ops + other.ops)
+
     def barrier(self, *qubits, label=None):
         self.ops.append(["barrier", [], list(qubits), label])
 
@@ -65,6 +69,9 @@ CASES = {
     "heisenberg2d_4x2": ("create_2d_heisenberg_circuit", dict(num_rows=4, num_cols=2, Jx=0.3, Jy=0.5, Jz=0.7, h=0.4, dt=0.1, timesteps=2)),
     "fermi_hubbard_1d_3": ("create_1d_fermi_hubbard_circuit", dict(L=3, u=0.5, t=1.0, mu=0.3, num_trotter_steps=2, dt=0.1, timesteps=1)),
     "fermi_hubbard_1d_4": ("create_1d_fermi_hubbard_circuit", dict(L=4, u=1.5, t=0.7, mu=-0.2, num_trotter_steps=1, dt=0.05, timesteps=2)),
+    "fermi_hubbard_2d_2x2": ("create_2d_fermi_hubbard_circuit", dict(Lx=2, Ly=2, u=0.5, t=1.0, mu=0.3, num_trotter_steps=1, dt=0.1, timesteps=1)),
+    "fermi_hubbard_2d_3x2": ("create_2d_fermi_hubbard_circuit", dict(Lx=3, Ly=2, u=1.5, t=0.7, mu=-0.2, num_trotter_steps=2, dt=0.05, timesteps=1)),
+    "fermi_hubbard_2d_2x3": ("create_2d_fermi_hubbard_circuit", dict(Lx=2, Ly=3, u=1.0, t=0.4, mu=0.1, num_trotter_steps=1, dt=0.1, timesteps=2)),
     "random_nn_5": ("nearest_neighbour_random_circuit", dict(n_qubits=5, layers=4, seed=42)),
     "random_nn_6": ("nearest_neighbour_random_circuit", dict(n_qubits=6, layers=3, seed=7)),
 }

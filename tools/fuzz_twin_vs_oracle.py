@@ -28,14 +28,14 @@ ADJACENT = ["crosstalk_xx", "crosstalk_yy", "crosstalk_zy", "crosstalk_xz", "low
 LONG_RANGE = ["crosstalk_xx", "crosstalk_zy", "crosstalk_yz"]
 
 
-def draw_case(rng: np.random.Generator, allow_1site: bool = True) -> dict:
-    L = int(rng.integers(2, 9))
+def draw_case(rng: np.random.Generator, allow_1site: bool = True, big: bool = False) -> dict:
+    L = int(rng.integers(8, 15)) if big else int(rng.integers(2, 9))
     model = str(rng.choice(["ising", "heisenberg"]))
     order = int(rng.choice([1, 2]))
     mode = "2site"
     if allow_1site and L >= 3 and rng.random() < 0.15:
         mode = "1site"
-    chi = int(rng.choice([1, 2, 3, 4, 6, 8, 16]))
+    chi = int(rng.choice([8, 12, 16, 24, 32])) if big else int(rng.choice([1, 2, 3, 4, 6, 8, 16]))
     if mode == "1site":
         chi = int(rng.choice([2, 4]))
         init = f"random:{chi}:{int(rng.integers(1, 1000))}"
@@ -62,7 +62,7 @@ def draw_case(rng: np.random.Generator, allow_1site: bool = True) -> dict:
     if L < 2 and "zz" in obs:
         obs = "z"
     cfg = dict(model=model, L=L, J=float(np.round(rng.uniform(0.3, 1.5), 3)), g=float(np.round(rng.uniform(0.0, 1.5), 3)), init=init, chi=chi, thr=thr,
-               order=order, dt=float(rng.choice([0.05, 0.1, 0.2])), steps=int(rng.integers(1, 7)), sample_timesteps=bool(rng.random() < 0.7),
+               order=order, dt=float(rng.choice([0.05, 0.1, 0.2])), steps=int(rng.integers(4, 13)) if big else int(rng.integers(1, 7)), sample_timesteps=bool(rng.random() < 0.7),
                ntraj=int(rng.integers(1, 6)), seed=int(rng.integers(0, 10000)), obs=obs, noise=noise, trunc_mode=trunc_mode, tdvp_mode=mode)
     if noise2:
         cfg["noise2"] = noise2
@@ -178,12 +178,13 @@ def main() -> int:
     ap.add_argument("--cases", type=int, default=40)
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--keep-going", action="store_true")
+    ap.add_argument("--big", action="store_true", help="chains of 8-14 sites, caps 8-32, 4-12 steps (seconds per draw instead of tenths)")
     ap.add_argument("--dynamic", action="store_true", help='tdvp_mode="dynamic" without a cap or with one the bonds stay below (DESIGN.md 4.13)')
     args = ap.parse_args()
     rng = np.random.default_rng(args.seed)
     bad = 0
     for n in range(args.cases):
-        cfg = draw_case(rng, allow_1site=not args.dynamic)
+        cfg = draw_case(rng, allow_1site=not args.dynamic, big=args.big)
         if args.dynamic:
             cfg["tdvp_mode"], cfg["chi"], cfg["L"] = "dynamic", (None if rng.random() < 0.7 else 64), min(cfg["L"], 6)
             cfg["noise2"] = [pr for pr in cfg.get("noise2", []) if max(pr[1]) < cfg["L"]]

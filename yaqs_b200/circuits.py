@@ -342,3 +342,54 @@ def nearest_neighbour_random_circuit(n_qubits: int, layers: int, seed: int = 42)
                 circ.cx(a, a + 1)
         circ.barrier()
     return circ
+
+
+def _pauli_string_hop(circ: Circuit, i: int, j: int, alpha: float) -> None:
+    """exp(-i alpha/2 (X_i Z...Z X_j)) exp(-i alpha/2 (Y_i Z...Z Y_j)) in elementary gates (circuit_library.py:442-517): for each of the
+    two strings, rotate the end qubits into the Z basis (ry(pi/2) for X, rx(pi/2) for Y), fold the parity of qubits i .. j-1 onto qubit
+    j with a CX ladder (highest control first), rz(alpha) on qubit j, and undo ladder and basis change in reverse."""
+    import numpy as np
+    if i >= j:
+        raise IndexError("Assumption i < j violated.")
+    for basis in ("ry", "rx"):
+        rotate = getattr(circ, basis)
+        rotate(np.pi / 2, i)
+        rotate(np.pi / 2, j)
+        for k in reversed(range(i, j)):
+            circ.cx(k, j)
+        circ.rz(alpha, j)
+        for k in range(i, j):
+            circ.cx(k, j)
+        rotate(-np.pi / 2, i)
+        rotate(-np.pi / 2, j)
+
+
+def create_2d_fermi_hubbard_circuit(Lx: int, Ly: int, u: float, t: float, mu: float, num_trotter_steps: int, dt: float,   # noqa: N803
+                                    timesteps: int) -> Circuit:
+    """circuit_library.py:520-634: lattice site p = y Lx + x holds qubits 2p (spin up) and 2p + 1 (spin down); one second-order slice is
+    chemical potential p(-mu dt / 2n) - on-site cp(-u dt / 2n) - hopping - on-site - chemical potential.  The hopping term walks the
+    horizontal bonds starting at even x, then odd x, then the vertical bonds starting at even y, then odd y, and hops both spins over
+    each bond as Jordan-Wigner strings (``_pauli_string_hop`` with alpha = t dt / n)."""
+    n = num_trotter_steps
+    sites = Lx * Ly
+    circ = Circuit(2 * sites)
+
+    def chemical_potential():
+        for q in range(2 * sites):
+            circ.p(-mu * dt / (2 * n), q)
+
+    def onsite():
+        for p in range(sites):
+            circ.cp(-u * dt / (2 * n), 2 * p, 2 * p + 1)
+
+    bonds = [(y * Lx + x, y * Lx + x + 1) for parity in (0, 1) for y in range(Ly) for x in range(parity, Lx - 1, 2)]
+    bonds += [(y * Lx + x, (y + 1) * Lx + x) for parity in (0, 1) for y in range(parity, Ly - 1, 2) for x in range(Lx)]
+    for _ in range(timesteps * n):
+        chemical_potential()
+        onsite()
+        for p1, p2 in bonds:
+            for spin in (0, 1):
+                _pauli_string_hop(circ, 2 * p1 + spin, 2 * p2 + spin, t * dt / n)
+        onsite()
+        chemical_potential()
+    return circ
