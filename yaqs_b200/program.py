@@ -13,8 +13,8 @@ unit of it is executed for a whole batch of trajectories in lock step by ``engin
 * merged analog runs with different Hamiltonians use one MPO per interval (``run(interval_mpos=...)``), zero-padded to a common
   bond dimension.
 
-Piecewise Hamiltonians expand to one MPO per interval exactly like merged runs.  The BUG integrator is not on the B200 path; QASM
-strings / paths need qiskit's parser and are rejected.
+Piecewise Hamiltonians expand to one MPO per interval exactly like merged runs.  The BUG integrator is not on the B200 path; OpenQASM 2
+strings / paths go through the qiskit-free reader (yaqs_b200/qasm.py).
 """
 from __future__ import annotations
 
@@ -98,7 +98,8 @@ def _normalize_segment(item, index: int):
         _reject_program_owned_fields(params, index)
         return _AnalogSegment(operator, params, noise_model)
     if isinstance(operator, str) or hasattr(operator, "__fspath__"):
-        raise NotImplementedError(f"segments[{index}]: OpenQASM sources need qiskit's parser; pass a circuit object instead")
+        from .qasm import load_circuit
+        operator = load_circuit(operator)                # OpenQASM 2 text or a path to it (simulation_program.py:181-182)
     if isinstance(operator, (Circuit, CompiledCircuit)) or type(operator).__name__ == "QuantumCircuit":
         if not isinstance(params, DigitalSimParams):
             raise TypeError(f"segments[{index}] pairs a circuit operator with {type(params).__name__}; expected DigitalSimParams.")

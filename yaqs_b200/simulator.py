@@ -203,6 +203,8 @@ class Simulator:
         if not sim_params.get_state and not sim_params.observables and sim_params.shots is None:
             raise ValueError("No output specified: set observables, shots, and/or get_state.")        # simulator.py:1283-1290
         from .circuits import Circuit
+        from .qasm import load_circuit
+        operator = load_circuit(operator)                # OpenQASM 2 text or a path to it (simulator.py:1262-1263, qasm_utils.py:133-162)
         if not isinstance(operator, Circuit) and not (hasattr(operator, "num_qubits") and hasattr(operator, "data")):
             raise TypeError("Circuit simulation requires a QuantumCircuit operator.")                 # :1304-1306 (Circuit or a qiskit circuit)
         from .digital import run_digital                # digital TJM (digital/digital_tjm.py:636-749)
