@@ -114,3 +114,30 @@ def test_runs_do_not_see_the_mpo_gauge():
         for a, b in zip(results[0].expectation_values, res.expectation_values):
             assert np.max(np.abs(np.asarray(a) - np.asarray(b))) < 1e-10
         assert np.array_equal(results[0].total_bond, res.total_bond)
+
+
+def test_fermi_hubbard_jordan_wigner_and_small_mpo_tools():
+    """MPO.fermi_hubbard_1d(jordan_wigner=True) (mpo.py:409-470) against the dense Pauli sum of its formula (the same matrix as the
+    unmodified reference's, compared in the build container: max |diff| 9e-16 at 8 orbitals); mpo_sum / +, identity, validity check."""
+    t, u, length = 0.7, 1.3, 6
+    terms = []
+    for up in range(0, length, 2):
+        terms += [(u / 4, {}), (-u / 4, {up: "Z"}), (-u / 4, {up + 1: "Z"}), (u / 4, {up: "Z", up + 1: "Z"})]
+    for a in range(length - 2):
+        terms += [(-t / 2, {a: p, a + 1: "Z", a + 2: p}) for p in "XY"]
+    mpo = MPO.fermi_hubbard_1d(length, t, u, jordan_wigner=True)
+    assert np.max(np.abs(mpo.to_matrix() - _dense(length, terms))) < 1e-14
+    assert max(w.shape[3] for w in mpo.tensors) <= 7 and mpo.check_if_valid_mpo()
+    assert np.max(np.abs(Hamiltonian.fermi_hubbard_1d(length, t, u, jordan_wigner=True).matrix - mpo.to_matrix())) == 0.0
+    with pytest.raises(ValueError, match="even integer"):
+        MPO.fermi_hubbard_1d(5, t, u, jordan_wigner=True)
+    with pytest.raises(NotImplementedError):
+        MPO.fermi_hubbard_1d(4, t, u)
+    a, b = MPO.ising(4, 1.0, 0.5), MPO.heisenberg(4, 1.0, 0.8, 0.6, 0.1)
+    total = a + b
+    assert total.check_if_valid_mpo() and np.max(np.abs(total.to_matrix() - a.to_matrix() - b.to_matrix())) < 1e-14
+    assert np.max(np.abs(MPO.mpo_sum([a, b, a]).to_matrix() - 2 * a.to_matrix() - b.to_matrix())) < 1e-14
+    assert np.array_equal(MPO.identity(3).to_matrix(), np.eye(8))
+    assert Hamiltonian.ising(3, 1.0, 0.5).sparse_matrix.shape == (8, 8)
+    broken = MPO.custom([np.zeros((2, 2, 1, 3)), np.zeros((2, 2, 2, 1))])
+    assert not broken.check_if_valid_mpo()

@@ -276,6 +276,153 @@ class MPS:
             return np.complex128(np.vdot(theta, acted))
         raise ValueError("Local observable must be one-site or nearest-neighbor two-site.")
 
+    # ------------------------------------------------------------------------------------------------------------------------------
+    # Gauge moves, compression and projective sampling of a host MPS (mps.py:355-407, 719-899, 1282-1493, 1581-1631): numpy, written
+    # around ONE primitive -- push the non-isometric factor of a site into its neighbour by a QR -- so that every move leaves the
+    # represented vector untouched; only ``compress`` truncates.
+    # ------------------------------------------------------------------------------------------------------------------------------
+    def _push(self, site: int, to_right: bool) -> None:
+        t = self.tensors[site]
+        d, l, r = t.shape
+        if to_right:
+            q, rest = np.linalg.qr(t.reshape(d * l, r))                    # rows (s, l): the site becomes a left isometry
+            self.tensors[site] = q.reshape(d, l, -1)
+            self.tensors[site + 1] = np.einsum("kr,srq->skq", rest, self.tensors[site + 1])
+        else:
+            q, rest = np.linalg.qr(t.transpose(0, 2, 1).reshape(d * r, l))
+            self.tensors[site] = q.reshape(d, r, -1).transpose(0, 2, 1)
+            self.tensors[site - 1] = np.einsum("slk,qk->slq", self.tensors[site - 1], rest)
+
+    def set_canonical_form(self, orthogonality_center: int, decomposition: str = "QR") -> None:
+        """Mixed-canonical form around ``orthogonality_center`` whatever the current gauge (mps.py:766-813); both decompositions are
+        carried out without truncation here."""
+        if not 0 <= orthogonality_center < self.length:
+            raise ValueError(f"orthogonality_center {orthogonality_center} outside the chain of length {self.length}.")
+        for site in range(orthogonality_center):
+            self._push(site, to_right=True)
+        for site in range(self.length - 1, orthogonality_center, -1):
+            self._push(site, to_right=False)
+        self.orthogonality_center = orthogonality_center
+
+    def set_center(self, site: int | None) -> None:
+        """Declare where the centre is (mps.py:303-314): bookkeeping only."""
+        self.orthogonality_center = site
+
+    def shift_center_to(self, site: int, decomposition: str = "QR") -> None:
+        """Move the tracked centre (mps.py:355-372)."""
+        if self.orthogonality_center is None:
+            raise ValueError("shift_center_to: the gauge is unknown; call set_canonical_form first.")
+        while self.orthogonality_center < site:
+            self._push(self.orthogonality_center, to_right=True)
+            self.orthogonality_center += 1
+        while self.orthogonality_center > site:
+            self._push(self.orthogonality_center, to_right=False)
+            self.orthogonality_center -= 1
+
+    def flip_network(self) -> None:
+        """Reverse the chain (mps.py:680-698): site order and the two bond indices of every tensor."""
+        self.tensors = [t.transpose(0, 2, 1).copy() for t in reversed(self.tensors)]
+        self.physical_dimensions = list(reversed(self.physical_dimensions))
+        self.flipped = not self.flipped
+        if self.orthogonality_center is not None:
+            self.orthogonality_center = self.length - 1 - self.orthogonality_center
+
+    def check_canonical_form(self) -> list[int]:
+        """The sites that can serve as orthogonality centre: everything to their left a left isometry, everything to their right a
+        right isometry, tested with numpy's allclose like the reference (mps.py:1581-1631)."""
+        left = [np.allclose(np.einsum("slk,slq->kq", t.conj(), t), np.eye(t.shape[2])) for t in self.tensors]
+        right = [np.allclose(np.einsum("slk,sqk->lq", t, t.conj()), np.eye(t.shape[1])) for t in self.tensors]
+        return [i for i in range(self.length) if all(left[:i]) and all(right[i + 1:])]
+
+    @staticmethod
+    def _keep(sv: np.ndarray, mode: str, threshold: float, max_bond_dim: int | None, min_keep: int = 1) -> int:
+        """How many singular values a split keeps (core/linalg/svd_utils.py:22-104; the device version is csrc/yb_truncate.cuh)."""
+        n = int(sv.size)
+        if n == 0:
+            return 0
+        if mode == "hard_cutoff":
+            keep = int(np.sum(sv > threshold))
+        elif mode == "relative":
+            keep = 0 if sv[0] <= 0.0 else int(np.sum(sv / sv[0] >= threshold))
+        elif mode in ("discarded_weight", "relative_discarded_weight"):
+            w = np.asarray(sv, dtype=np.float64) ** 2
+            if mode == "relative_discarded_weight":
+                if sv[0] <= 0.0:
+                    w, keep = None, 0
+                else:
+                    w = (np.asarray(sv, dtype=np.float64) / float(sv[0])) ** 2
+                    w = w / float(np.sum(w))
+            if w is not None:
+                tail = np.cumsum(w[::-1])                                # weight of the k smallest, k = 1 .. n
+                if mode == "discarded_weight":
+                    hit = np.nonzero(tail >= threshold)[0]
+                    keep = n if hit.size == 0 else max(n - int(hit[0]), min_keep)
+                else:
+                    keep = n - int(np.sum(tail <= threshold))
+        else:
+            raise ValueError(f"Unknown truncation mode: {mode!r}")
+        if max_bond_dim is not None:
+            keep = min(keep, max_bond_dim)
+        return min(max(keep, min_keep), n)
+
+    def compress(self, threshold: float, *, max_bond_dim: int | None = None, trunc_mode: str = "discarded_weight") -> None:
+        """Right-canonicalise without truncation, truncate bond by bond from the left with the singular values to the right, put the
+        centre back where it was (mps.py:841-899)."""
+        if self.length == 1:
+            return
+        if self.orthogonality_center is not None:
+            back = self.orthogonality_center
+        else:
+            sites = self.check_canonical_form()
+            back = sites[0] if sites else self.length // 2
+        self.set_canonical_form(0)
+        for site in range(self.length - 1):
+            a, b = self.tensors[site], self.tensors[site + 1]
+            theta = np.einsum("slk,tkr->sltr", a, b).reshape(a.shape[0] * a.shape[1], b.shape[0] * b.shape[2])
+            u, sv, vh = np.linalg.svd(theta, full_matrices=False)
+            keep = self._keep(sv, trunc_mode, threshold, max_bond_dim)
+            self.tensors[site] = u[:, :keep].reshape(a.shape[0], a.shape[1], keep)
+            self.tensors[site + 1] = (sv[:keep, None] * vh[:keep]).reshape(keep, b.shape[0], b.shape[2]).transpose(1, 0, 2)
+            self.orthogonality_center = site + 1
+        self.shift_center_to(back)
+
+    _BASIS_ROTATIONS = {"Z": np.eye(2, dtype=C), "X": np.array([[1, 1], [1, -1]], dtype=C) / np.sqrt(2),
+                        "Y": np.array([[1, -1j], [1, 1j]], dtype=C) / np.sqrt(2)}
+
+    def measure_single_shot(self, basis: str = "Z", rng: np.random.Generator | None = None) -> int:
+        """One projective measurement of every site, left to right, on a copy (mps.py:1282-1341): the outcome of site k conditions the
+        tensor of site k + 1; bit k of the returned integer is the outcome of site k.  One ``rng.choice`` per site, like the reference."""
+        rot = self._BASIS_ROTATIONS.get(basis.upper())
+        if rot is None:
+            raise ValueError(f"Invalid basis: {basis}. Expected 'X', 'Y', or 'Z'.")
+        rng = np.random.default_rng() if rng is None else rng
+        work = MPS.__new__(MPS)
+        work.length, work.physical_dimensions, work.flipped = self.length, list(self.physical_dimensions), self.flipped
+        work.tensors, work.orthogonality_center = [t.copy() for t in self.tensors], self.orthogonality_center
+        if work.orthogonality_center is None:
+            work.set_canonical_form(0)
+        outcome = 0
+        for site in range(work.length):
+            work.shift_center_to(site)
+            rotated = np.einsum("ab,blr->alr", rot, work.tensors[site])
+            prob = np.einsum("alr,alr->a", rotated, rotated.conj()).real.copy()
+            prob /= np.sum(prob)
+            bit = int(rng.choice(len(prob), p=prob))
+            outcome |= bit << site
+            if site != work.length - 1:
+                work.tensors[site + 1] = np.einsum("lk,skr->slr", rotated[bit], work.tensors[site + 1]) / np.sqrt(prob[bit])
+                work.orthogonality_center = site + 1
+        return outcome
+
+    def measure_shots(self, shots: int, basis: str = "Z", rng: np.random.Generator | None = None) -> dict[int, int]:
+        """Histogram of ``shots`` single shots (mps.py:1343-1417; the reference fans the shots out over a process pool with unseeded
+        generators -- here they are taken one after the other, from ``rng`` when one is given)."""
+        counts: dict[int, int] = {}
+        for _ in range(max(int(shots), 1)):
+            outcome = self.measure_single_shot(basis, rng)
+            counts[outcome] = counts.get(outcome, 0) + 1
+        return counts
+
     def project_onto_bitstring(self, bitstring: str) -> np.complex128:
         """|<bitstring|psi>|^2, site 0 first (mps.py:1495-1537)."""
         assert len(bitstring) == self.length, "Bitstring length must match number of sites"
@@ -471,6 +618,71 @@ class MPO:
         return cls.pauli(length=length, two_body=[(-Jx, "X", "X"), (-Jy, "Y", "Y"), (-Jz, "Z", "Z")],
                          one_body=[(-h, "Z")] if h != 0 else [], bc=bc)
 
+    @classmethod
+    def fermi_hubbard_1d(cls, length: int, t: float, u: float, *, jordan_wigner: bool = False) -> "MPO":
+        """1-D Fermi-Hubbard chain as a qubit Hamiltonian (mpo.py:409-470, ``jordan_wigner=True``): spin orbitals interleaved 1 up, 1 down,
+        2 up, 2 down, ... (``length`` = number of spin orbitals, even);  U n_up n_down = U/4 (I - Z_up - Z_down + Z_up Z_down) on every
+        site and hops -t/2 (X Z X + Y Z Y) between equal spins of neighbouring sites, the Z on the orbital in between.  The fermionic
+        form on four-level sites is outside the qubit path."""
+        if not jordan_wigner:
+            raise NotImplementedError("the B200 TJM path supports qubits (d = 2) only: pass jordan_wigner=True")
+        if length % 2 != 0 or length < 2:
+            raise ValueError("length must be an even integer \u2265 2 (ordering: 1\u2191,1\u2193,2\u2191,2\u2193,...).")
+        terms = []
+        for up in range(0, length, 2):
+            terms += [(u / 4, ""), (-u / 4, f"Z{up}"), (-u / 4, f"Z{up + 1}"), (u / 4, f"Z{up} Z{up + 1}")]
+        for a in range(length - 2):
+            terms += [(-t / 2, f"{p}{a} Z{a + 1} {p}{a + 2}") for p in "XY"]
+        mpo = cls()
+        mpo.from_pauli_sum(terms=terms, length=length)
+        return mpo
+
+    @classmethod
+    def identity(cls, length: int, physical_dimension: int = 2) -> "MPO":
+        """mpo.py:1015-1028."""
+        if physical_dimension != 2:
+            raise NotImplementedError("the B200 TJM path supports qubits (d = 2) only")
+        return cls.custom([np.eye(2, dtype=C).reshape(2, 2, 1, 1) for _ in range(length)])
+
+    @classmethod
+    def mpo_sum(cls, mpos) -> "MPO":
+        """Sum of MPOs of equal length as the direct sum of their bond spaces (mpo.py:1976-2058)."""
+        mpos = list(mpos)
+        if not mpos:
+            raise ValueError("mpo_sum needs at least one MPO.")
+        n = mpos[0].length
+        if any(m.length != n for m in mpos):
+            raise ValueError("MPO lengths must match.")
+        out = []
+        for i in range(n):
+            blocks = [m.tensors[i] for m in mpos]
+            if n == 1:
+                out.append(sum(blocks))
+                continue
+            dl = 1 if i == 0 else sum(b.shape[2] for b in blocks)
+            dr = 1 if i == n - 1 else sum(b.shape[3] for b in blocks)
+            w = np.zeros((2, 2, dl, dr), dtype=C)
+            lo, ro = 0, 0
+            for b in blocks:
+                ls = slice(0, 1) if i == 0 else slice(lo, lo + b.shape[2])
+                rs = slice(0, 1) if i == n - 1 else slice(ro, ro + b.shape[3])
+                w[:, :, ls, rs] += b
+                lo, ro = lo + b.shape[2], ro + b.shape[3]
+            out.append(w)
+        return cls.custom(out)
+
+    def __add__(self, other: "MPO") -> "MPO":
+        return MPO.mpo_sum([self, other])
+
+    def check_if_valid_mpo(self) -> bool:
+        """Neighbouring bonds agree and the chain ends are closed (mpo.py:2060-2076)."""
+        ok = all(a.shape[3] == b.shape[2] for a, b in zip(self.tensors[:-1], self.tensors[1:]))
+        return bool(ok and self.tensors and self.tensors[0].shape[2] == 1 and self.tensors[-1].shape[3] == 1)
+
+    def to_sparse_matrix(self):
+        import scipy.sparse
+        return scipy.sparse.csr_matrix(self.to_matrix())
+
     def to_matrix(self) -> np.ndarray:
         acc = self.tensors[0][:, :, 0, :]
         for w in self.tensors[1:]:
@@ -508,6 +720,19 @@ class State:
             self.length = length
             self.mps = MPS(length, state=initial, pad=pad, basis_string=basis_string, physical_dimensions=physical_dimensions)
         self.physical_dimensions = self.mps.physical_dimensions
+
+    @classmethod
+    def from_mps(cls, mps: MPS) -> "State":
+        """Wrap an existing MPS (state.py:175-188): the State references ``mps`` itself."""
+        wrapped = cls.__new__(cls)
+        wrapped.representation, wrapped.initial, wrapped.pad, wrapped.basis_string, wrapped.seed = "mps", "zeros", None, None, None
+        wrapped.length, wrapped.mps, wrapped.physical_dimensions = mps.length, mps, mps.physical_dimensions
+        return wrapped
+
+    def ensure_encoded(self, representation: str = "mps") -> "State":
+        if representation != "mps":
+            raise NotImplementedError("the B200 TJM path takes representation='mps' states only")
+        return self
 
 
 class Hamiltonian:
@@ -562,6 +787,10 @@ class Hamiltonian:
     @classmethod
     def pauli(cls, **kw) -> "Hamiltonian":
         return cls(MPO.pauli(**kw))
+
+    @classmethod
+    def fermi_hubbard_1d(cls, length: int, t: float, u: float, *, jordan_wigner: bool = False) -> "Hamiltonian":
+        return cls(MPO.fermi_hubbard_1d(length, t, u, jordan_wigner=jordan_wigner))
 
     @classmethod
     def piecewise(cls, pieces) -> "Hamiltonian":
@@ -625,6 +854,20 @@ class Hamiltonian:
 
     def to_matrix(self) -> np.ndarray:
         return self.mpo.to_matrix()
+
+    @property
+    def matrix(self) -> np.ndarray:
+        return self.to_matrix()
+
+    def to_sparse_matrix(self):
+        return self.mpo.to_sparse_matrix()
+
+    @property
+    def sparse_matrix(self):
+        return self.to_sparse_matrix()
+
+    def ensure_sparse(self) -> "Hamiltonian":
+        return self.ensure_mpo()
 
 
 @dataclass
