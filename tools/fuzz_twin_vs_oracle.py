@@ -66,6 +66,16 @@ def draw_case(rng: np.random.Generator, allow_1site: bool = True, big: bool = Fa
                ntraj=int(rng.integers(1, 6)), seed=int(rng.integers(0, 10000)), obs=obs, noise=noise, trunc_mode=trunc_mode, tdvp_mode=mode)
     if noise2:
         cfg["noise2"] = noise2
+    if order == 1 and mode == "2site" and rng.random() < 0.35:           # deterministic jumps on the time grid (order 1 only, scheduled_jumps.py:29-119)
+        sched = []
+        for _ in range(int(rng.integers(1, 4))):
+            when = float(np.round(cfg["dt"] * int(rng.integers(0, cfg["steps"] + 1)), 10))
+            if L >= 2 and rng.random() < 0.3:
+                i = int(rng.integers(0, L - 1))
+                sched.append((when, (i, i + 1) if rng.random() < 0.6 else (i + 1, i), str(rng.choice(["crosstalk_xy", "crosstalk_zx", "crosstalk_yy"]))))
+            else:
+                sched.append((when, (int(rng.integers(0, L)),), str(rng.choice(["pauli_x", "pauli_y", "pauli_z", "raising", "lowering"]))))
+        cfg["scheduled"] = sched
     return cfg
 
 
@@ -123,7 +133,15 @@ def run_one(cfg: dict, gram_min_k: int | None):
     from yaqs_b200.engine import BatchedTJM, EngineParams
     from yaqs_b200.rng import numpy_tables
     with IllPosedWatch() as watch:
-        traces = run_oracle_case(cfg)
+        try:
+            traces = run_oracle_case(cfg)
+        except ValueError as exc:                        # a run the reference refuses (a scheduled jump that annihilates the state, zero jump
+            try:                                         # weights): the engine has to refuse it the same way
+                _compare(cfg, None, gram_min_k)
+            except ValueError as ours:
+                same = str(ours).split("(")[0].strip() == str(exc).split("(")[0].strip()
+                return (None if same else f"both refuse the run, with different messages: {exc} / {ours}"), 0.0
+            return f"the oracle refuses the run ({exc}), the engine completes it", 0.0
     why, worst = _compare(cfg, traces, gram_min_k)
     if why is not None and watch.notes:                  # a mismatch on a case whose outcome rounding decides is not a finding
         return "ill-posed: " + watch.notes[0] + " [" + why + "]", worst
@@ -149,13 +167,15 @@ def _compare(cfg: dict, traces, gram_min_k: int | None):
     res, dg = results.cpu().numpy(), diag.cpu().numpy()
     status = int(eng.status.abs().sum())
     worst = 0.0
-    for t, tr in enumerate(traces):
+    for t, tr in enumerate(traces or []):
         if not np.array_equal(dg[t], tr.diagnostics):
             return f"diagnostics differ (trajectory {t}): engine {dg[t].tolist()} oracle {tr.diagnostics.tolist()}", worst
         err = float(np.nanmax(np.abs(res[t] - tr.results))) if res[t].size else 0.0
         worst = max(worst, err)
         if not err < 1e-10:
             return f"observables differ by {err:.3e} (trajectory {t})", worst
+        if not log and not any(rec.jumped for rec in tr.jumps):
+            continue                                      # scheduled jumps only: the reference draws a uniform per step that nothing depends on
         if len(log) < len(tr.jumps):
             return f"jump log shorter than the oracle's ({len(log)} < {len(tr.jumps)})", worst
         for c, rec in enumerate(tr.jumps):
