@@ -47,7 +47,10 @@ def draw(rng) -> dict:
             obs.append((name, [i, i + 1]))
         else:
             obs.append((name, int(rng.integers(0, L))))
-    return dict(L=L, model=str(rng.choice(["ising", "heisenberg"])), J=float(np.round(rng.uniform(0.3, 1.4), 3)), g=float(np.round(rng.uniform(0.1, 1.4), 3)),
+    pieces = None
+    if rng.random() < 0.25:                               # Hamiltonian.piecewise: static pieces switched on the dt grid (hamiltonian.py:176-263)
+        pieces = [(float(np.round(rng.uniform(0.3, 1.4), 3)), float(np.round(rng.uniform(0.1, 1.4), 3)), int(rng.integers(1, 3))) for _ in range(int(rng.integers(2, 4)))]
+    return dict(pieces=pieces, L=L, model=str(rng.choice(["ising", "heisenberg"])), J=float(np.round(rng.uniform(0.3, 1.4), 3)), g=float(np.round(rng.uniform(0.1, 1.4), 3)),
                 init=str(rng.choice(["zeros", "ones", "x+", "x-", "y+", "Neel", "wall"])), procs=procs, obs=obs,
                 params=dict(elapsed_time=0.1 * int(rng.integers(1, 5)), dt=0.1, num_traj=int(rng.integers(1, 6)), max_bond_dim=int(rng.choice([2, 4, 8, 16])),
                             svd_threshold=float(10.0 ** rng.uniform(-11, -5)), order=int(rng.choice([1, 2])), sample_timesteps=bool(rng.random() < 0.7),
@@ -55,10 +58,17 @@ def draw(rng) -> dict:
 
 
 def build(ns, cfg):
-    ham = ns["Hamiltonian"].ising(cfg["L"], cfg["J"], cfg["g"]) if cfg["model"] == "ising" else ns["Hamiltonian"].heisenberg(cfg["L"], cfg["J"], cfg["J"], cfg["g"])
+    def static(j, g):
+        return ns["Hamiltonian"].ising(cfg["L"], j, g) if cfg["model"] == "ising" else ns["Hamiltonian"].heisenberg(cfg["L"], j, j, g)
+    params_kw = dict(cfg["params"])
+    if cfg.get("pieces"):
+        ham = ns["Hamiltonian"].piecewise([(static(j, g), 0.1 * n) for j, g, n in cfg["pieces"]])
+        params_kw["elapsed_time"] = 0.1 * sum(n for _, _, n in cfg["pieces"])
+    else:
+        ham = static(cfg["J"], cfg["g"])
     obs = [ns["Observable"](name, sites) for name, sites in cfg["obs"]]
     noise = ns["NoiseModel"]([dict(p) for p in cfg["procs"]]) if cfg["procs"] else None
-    params = ns["AnalogSimParams"](observables=obs, **cfg["params"])
+    params = ns["AnalogSimParams"](observables=obs, **params_kw)
     return ns["State"](cfg["L"], initial=cfg["init"]), ham, params, noise
 
 
