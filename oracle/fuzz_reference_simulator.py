@@ -50,7 +50,7 @@ def draw(rng) -> dict:
     pieces = None
     if rng.random() < 0.25:                               # Hamiltonian.piecewise: static pieces switched on the dt grid (hamiltonian.py:176-263)
         pieces = [(float(np.round(rng.uniform(0.3, 1.4), 3)), float(np.round(rng.uniform(0.1, 1.4), 3)), int(rng.integers(1, 3))) for _ in range(int(rng.integers(2, 4)))]
-    return dict(pieces=pieces, L=L, model=str(rng.choice(["ising", "heisenberg"])), J=float(np.round(rng.uniform(0.3, 1.4), 3)), g=float(np.round(rng.uniform(0.1, 1.4), 3)),
+    return dict(pad=(int(rng.choice([2, 4])) if rng.random() < 0.2 else None), get_state=bool(not procs and rng.random() < 0.6), pieces=pieces, L=L, model=str(rng.choice(["ising", "heisenberg"])), J=float(np.round(rng.uniform(0.3, 1.4), 3)), g=float(np.round(rng.uniform(0.1, 1.4), 3)),
                 init=str(rng.choice(["zeros", "ones", "x+", "x-", "y+", "Neel", "wall"])), procs=procs, obs=obs,
                 params=dict(elapsed_time=0.1 * int(rng.integers(1, 5)), dt=0.1, num_traj=int(rng.integers(1, 6)), max_bond_dim=int(rng.choice([2, 4, 8, 16])),
                             svd_threshold=float(10.0 ** rng.uniform(-11, -5)), order=int(rng.choice([1, 2])), sample_timesteps=bool(rng.random() < 0.7),
@@ -68,8 +68,8 @@ def build(ns, cfg):
         ham = static(cfg["J"], cfg["g"])
     obs = [ns["Observable"](name, sites) for name, sites in cfg["obs"]]
     noise = ns["NoiseModel"]([dict(p) for p in cfg["procs"]]) if cfg["procs"] else None
-    params = ns["AnalogSimParams"](observables=obs, **params_kw)
-    return ns["State"](cfg["L"], initial=cfg["init"]), ham, params, noise
+    params = ns["AnalogSimParams"](observables=obs, get_state=bool(cfg.get("get_state")), **params_kw)
+    return ns["State"](cfg["L"], initial=cfg["init"], pad=cfg.get("pad")), ham, params, noise
 
 
 def compare(cfg, ref_ns, our_ns, ref_sim, our_sim):
@@ -108,6 +108,10 @@ def compare(cfg, ref_ns, our_ns, ref_sim, our_sim):
             if not np.array_equal(np.asarray(getattr(ref, name)), np.asarray(getattr(ours, name))):
                 why = f"{name} differs: {getattr(ref, name)} against {getattr(ours, name)}"
                 break
+    if why is None and cfg.get("get_state"):
+        va, vb = ref.output_state.mps.to_vec(), ours.output_state.mps.to_vec()
+        if abs(abs(np.vdot(va, vb)) - np.linalg.norm(va) * np.linalg.norm(vb)) > 1e-10 or abs(np.linalg.norm(va) - np.linalg.norm(vb)) > 1e-10:
+            why = f"output_state differs: overlap {abs(np.vdot(va, vb))}, norms {np.linalg.norm(va)} / {np.linalg.norm(vb)}"
     if why is None and cfg["procs"]:
         sa = [p["strength"] for p in ref.noise_model.processes]
         sb = [p["strength"] for p in ours.noise_model.processes]
