@@ -54,7 +54,9 @@ def draw(rng) -> dict:
                 init=str(rng.choice(["zeros", "ones", "x+", "x-", "y+", "Neel", "wall"])), procs=procs, obs=obs,
                 params=dict(elapsed_time=0.1 * int(rng.integers(1, 5)), dt=0.1, num_traj=int(rng.integers(1, 6)), max_bond_dim=int(rng.choice([2, 4, 8, 16])),
                             svd_threshold=float(10.0 ** rng.uniform(-11, -5)), order=int(rng.choice([1, 2])), sample_timesteps=bool(rng.random() < 0.7),
-                            random_seed=int(rng.integers(0, 10000))))
+                            random_seed=int(rng.integers(0, 10000)), tdvp_sweeps=int(rng.choice([1, 1, 2, 3])),
+                            trunc_mode=str(rng.choice(["discarded_weight", "discarded_weight", "relative", "hard_cutoff", "relative_discarded_weight"])),
+                            krylov_tol=float(rng.choice([1e-4, 1e-6, 1e-10])), preset=str(rng.choice(["fast", "balanced", "accurate", "exact"]))))
 
 
 def build(ns, cfg):
