@@ -1,7 +1,7 @@
 """Seeded random configurations through the UNMODIFIED reference (import shim, build container only) and through the oracle.
 
 TEST INFRASTRUCTURE.  The fixtures pin the oracle on a fixed table of cases; this walks the configuration space of
-tools/fuzz_twin_vs_oracle.py / fuzz_digital_twin_vs_oracle.py and asks, draw by draw, that the oracle reproduces what the reference
+tests/walks/fuzz_twin_vs_oracle.py / fuzz_digital_twin_vs_oracle.py and asks, draw by draw, that the oracle reproduces what the reference
 returns: observables <= 1e-10, identical diagnostics and bond dimensions, the same jump log.  Draws whose outcome rounding decides
 (IllPosedWatch) are reported, not compared.  Needs /root/reference, so it cannot run on the GPU box; results in DESIGN.md section 2.
 
@@ -19,7 +19,7 @@ import torch  # noqa: F401 -- imported before the shim registers its stand-in mo
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tools"))
+sys.path.insert(0, os.path.join(ROOT, "tests", "walks"))
 for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
     os.environ.setdefault(_v, "1")
 

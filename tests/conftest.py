@@ -29,7 +29,8 @@ def golden_dir():
 # They are collected LAST, so a first-run surprise in one of them cannot hide the 111 tests that are known green on the box
 # (profiles/r01_pytest_gpu_v7_baseline_sizes.txt) behind `-x`.  Remove an entry once a profiles/ log shows it green.
 FIRST_RUN_ON_GPU = ("test_backend_boundary_gpu", "test_measure_shots_replays_reference_outcomes_gpu", "ising6_scheduled", "dig_ising6_periodic_swaps",
-                    "dig_ising49_c4", "test_program_matches_reference_gpu", "periodic_mpo", "test_mpo_site_apply_matches_twin", "ragged_gemm_option", "gemm_ragged_option", "cuda_dynamic_tdvp", "dig_toffoli6", "wapply_onepass_option", "dig_ising6_window_capped")
+                    "dig_ising49_c4", "test_program_matches_reference_gpu", "periodic_mpo", "test_mpo_site_apply_matches_twin", "ragged_gemm_option", "gemm_ragged_option", "cuda_dynamic_tdvp", "dig_toffoli6", "wapply_onepass_option", "dig_ising6_window_capped",
+                    "test_cuda_engine_edge_cases", "test_cuda_digital_tjm_controlled_gates", "test_zz_reference_unit_kats", "heis200_c5_step")
 
 
 def _gpu_unavailable() -> str | None:

@@ -1,4 +1,4 @@
-"""A short seeded walk through the configuration space (tools/fuzz_*.py): the batched host engine on the numpy kernel twin against the
+"""A short seeded walk through the configuration space (tests/walks/fuzz_*.py): the batched host engine on the numpy kernel twin against the
 oracle on configurations no fixture holds.  The long walks (hundreds of cases per path) are run by hand, results in DESIGN.md section 2;
 this keeps the tools alive and adds a few dozen unseen configurations to every CPU run."""
 import os
@@ -7,7 +7,7 @@ import sys
 import numpy as np
 import pytest
 
-TOOLS = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools")
+TOOLS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "walks")
 if TOOLS not in sys.path:
     sys.path.insert(0, TOOLS)
 

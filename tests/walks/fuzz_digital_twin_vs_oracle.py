@@ -1,11 +1,11 @@
 """Seeded random digital configurations (Ising Trotter circuits, BASELINE config 4's path): the batched host engine on the numpy kernel
-twin against the oracle.  TEST INFRASTRUCTURE (CPU only), companion of tools/fuzz_twin_vs_oracle.py.
+twin against the oracle.  TEST INFRASTRUCTURE (CPU only), companion of tests/walks/fuzz_twin_vs_oracle.py.
 
 Draws chain length, couplings, Trotter depth, periodic closure (a long-range gate), its route (gate MPO / SWAP ladder / TDVP window),
 bond cap, threshold, noise (one-site and adjacent two-site processes) and sampling mode, and asks for the same jumps, identical
 diagnostics, observables and pdfs <= 1e-10.
 
-    python tools/fuzz_digital_twin_vs_oracle.py --cases 50 --seed 0
+    python tests/walks/fuzz_digital_twin_vs_oracle.py --cases 50 --seed 0
 """
 from __future__ import annotations
 
@@ -16,7 +16,7 @@ import time
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))

@@ -1,12 +1,12 @@
 """Seeded random SimulationPrograms: ``Simulator.run`` on the numpy kernel twin against the oracle's program executor.
-TEST INFRASTRUCTURE (CPU only), companion of tools/fuzz_twin_vs_oracle.py.
+TEST INFRASTRUCTURE (CPU only), companion of tests/walks/fuzz_twin_vs_oracle.py.
 
 Draws segment lists (analog order 1 / order 2 with shared or different Hamiltonians, equal or different settings -- so that merges,
 order-2 phi hand-offs, sample-stream offsets and final-only sampling all occur -- and digital Trotter blocks in between) and asks, per
 segment and trajectory, for the same observables (<= 1e-10), identical bond diagnostics, and the same number of doubles drawn from
 each trajectory's shared stream.
 
-    python tools/fuzz_program_twin_vs_oracle.py --cases 40 --seed 0
+    python tests/walks/fuzz_program_twin_vs_oracle.py --cases 40 --seed 0
 """
 from __future__ import annotations
 
@@ -17,7 +17,7 @@ import time
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))

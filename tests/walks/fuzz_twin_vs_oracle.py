@@ -6,7 +6,7 @@ configuration space at random -- chain length, bond cap, threshold, truncation m
 same jump sequence, identical diagnostics (bond dimensions), observables <= 1e-10, pdfs <= 1e-10, status words clean, on the
 Jacobi route and with the Gram / Cholesky-QR routes forced onto the small sizes.
 
-    python tools/fuzz_twin_vs_oracle.py --cases 50 --seed 0            # prints one line per case, exits 1 on the first mismatch
+    python tests/walks/fuzz_twin_vs_oracle.py --cases 50 --seed 0            # prints one line per case, exits 1 on the first mismatch
 """
 from __future__ import annotations
 
@@ -17,7 +17,7 @@ import time
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
@@ -82,7 +82,7 @@ def draw_case(rng: np.random.Generator, allow_1site: bool = True, big: bool = Fa
 class IllPosedWatch:
     """Wraps the oracle's ``truncate`` while a case runs and notes decisions that rounding can flip: a cut between two (nearly) equal
     singular values, a discarded weight within 1e-6 (relative) of the threshold, a Lanczos stop / breakdown test within 1e-3 of its bound.  The reference itself is not reproducible across
-    LAPACK builds on such a case (tools/fuzz notes in DESIGN.md section 2), so it is reported as ill-posed, not as a mismatch."""
+    LAPACK builds on such a case, so it is reported as ill-posed, not as a mismatch."""
 
     def __init__(self, gap: float = 1e-4, rel: float = 1e-6):
         self.gap, self.rel, self.notes = gap, rel, []
