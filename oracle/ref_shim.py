@@ -32,6 +32,9 @@ def load_reference() -> None:
         return
     if not reference_available():
         raise RuntimeError(f"reference tree not found under {REF_ROOT}")
+    # the reference tree is read-only by contract: no bytecode and no numba cache files next to its sources
+    sys.dont_write_bytecode = True
+    os.environ.setdefault("NUMBA_CACHE_DIR", os.path.join(os.environ.get("TMPDIR", "/tmp"), "yaqs_b200_numba_cache"))
     for name, path in (("mqt", REF_SRC), ("mqt.yaqs", os.path.join(REF_SRC, "yaqs"))):
         mod = types.ModuleType(name)
         mod.__path__ = [path]
